@@ -1,0 +1,10 @@
+"""B200-native (sm_100a) implementation of the elektronn3 UNet / Predictor hot path.
+
+``UNet`` is a drop-in for ``elektronn3.models.unet.UNet`` and ``Predictor`` for
+``elektronn3.inference.Predictor``; the arithmetic runs in hand-written CUDA kernels (libe3b.so, C ABI in
+include/e3b.h).  There is no CPU or cuDNN fallback.
+"""
+from .unet import UNet  # noqa: F401
+from .inference import Predictor  # noqa: F401
+
+__all__ = ['UNet', 'Predictor']

@@ -1,0 +1,441 @@
+// Implicit-GEMM 3D convolution (forward, dgrad, and the k=s=2 transposed conv as a 1-tap GEMM with a
+// pixel-shuffle scatter epilogue) on tcgen05 tensor cores, sm_100a.
+//
+// Replaces the torch/cuDNN calls behind elektronn3 `conv3` (models/unet.py:131-149), `conv1`
+// (:178-180) and `upconv2` (:152-165).
+//
+// Design ("halo-tile implicit GEMM"):
+//  * activations are QP tensors (see common.cuh).  A CTA tile is 8(x) x 16(y) x TZ(z) output voxels =
+//    TZ accumulators of M=128 rows x N columns in TMEM.
+//  * per 8 input channels ONE TMA box load brings the (8+kw-1) x (16+kh-1) x (TZ+kd-1) halo tile of
+//    those channels into shared memory (zero fill outside the volume == conv zero padding).  Because
+//    one voxel is a 16-byte quad in the no-swizzle canonical UMMA layout, every stencil tap is the
+//    same tile read through a descriptor whose start address is shifted by
+//    ((dz*HY + dy)*HX + dx) * 16 B: 27 taps x TZ planes of MMAs are issued per loaded tile, so L2->smem
+//    traffic is ~1.4x the activation size instead of 27x.
+//  * weights are pre-packed into the exact smem image (K-major, no swizzle) and streamed with 1D bulk
+//    copies in tap groups through their own mbarrier ring.
+//  * warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..5 epilogue
+//    (tcgen05.ld -> +bias -> [ReLU] -> per-channel sum / sum-of-squares for the following
+//    Group/BatchNorm -> coalesced 16-byte stores).  Two TMEM accumulator sets ping-pong so the epilogue
+//    of tile i overlaps the MMAs of tile i+1.  CTAs are persistent over a static tile schedule.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace e3b {
+
+static constexpr int kTX = 8, kTY = 16;
+static constexpr int kThreads = 192;
+
+struct ConvTcParams {
+    // geometry
+    int N, Do, Ho, Wo;           // output extents (the GEMM M space)
+    int kd, kh, kw;              // taps per dim (1 or 3)
+    int pd, ph, pw;              // zero padding
+    int TZ;                      // output planes per tile
+    int HX, HY, HZ;              // halo tile extents
+    int tiles_x, tiles_y, tiles_z, n_ntiles, total_tiles;
+    int chunks0, chunks1;        // 8-channel K chunks from source 0 / source 1
+    int off1_d, off1_h, off1_w;  // crop offset into source 1
+    int NT;                      // columns per N tile (multiple of 16, <= 256)
+    int TG;                      // taps per weight stage
+    int SA, SB;                  // pipeline depths
+    uint32_t a_stage_bytes, b_stage_bytes;
+    // epilogue
+    const float* bias;           // [n_bias] or null
+    int n_bias;
+    float* dst0; int cq0;        // channel planes [0, cq0) of the N space go to dst0 ...
+    float* dst1;                 // ... the rest to dst1 (dgrad of a virtual-concat conv)
+    int cq0_alloc, cq1_alloc;    // planes allocated in dst0 / dst1
+    int relu;
+    double* stats;               // [N][Cstat][2] sum / sumsq (fp64 atomics) or null
+    int Cstat;
+    int scatter;                 // 1: k=s transposed conv, column n = tap*Cup + co, dst is the fine grid
+    int sd, sh, sw;              // scatter strides
+    int Cup;                     // padded channels per tap in scatter mode
+    int Ds, Hs, Ws;              // (scatter) cropped fine-grid output extents
+    const float* wpk;
+};
+
+E3B_DEVINL void decode_tile(const ConvTcParams& p, int t, int& nt, int& n, int& z0, int& y0, int& x0) {
+    int xt = t % p.tiles_x; t /= p.tiles_x;
+    int yt = t % p.tiles_y; t /= p.tiles_y;
+    int zt = t % p.tiles_z; t /= p.tiles_z;
+    nt = t % p.n_ntiles;
+    n = t / p.n_ntiles;
+    x0 = xt * kTX; y0 = yt * kTY; z0 = zt * p.TZ;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+               const ConvTcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // carve: [A stages][B stages][barriers]
+    uint8_t* a_base = smem;
+    uint8_t* b_base = smem + (size_t)p.SA * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.SB * p.b_stage_bytes);
+    uint64_t* a_full = bars;              // [SA]
+    uint64_t* a_empty = a_full + p.SA;    // [SA]
+    uint64_t* b_full = a_empty + p.SA;    // [SB]
+    uint64_t* b_empty = b_full + p.SB;    // [SB]
+    uint64_t* acc_full = b_empty + p.SB;  // [2]
+    uint64_t* acc_empty = acc_full + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ntaps = p.kd * p.kh * p.kw;
+    const int ngroups = ntaps / p.TG;
+    const int nchunks = p.chunks0 + p.chunks1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.SA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < p.SB; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap0);
+        if (p.chunks1) tma_prefetch_desc(&tmap1);
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                int nt, n, z0, y0, x0;
+                decode_tile(p, t, nt, n, z0, y0, x0);
+                for (int c = 0; c < nchunks; c++) {
+                    mbar_wait(&a_empty[sa], pa ^ 1);
+                    mbar_arrive_expect_tx(&a_full[sa], p.a_stage_bytes);
+                    if (c < p.chunks0)
+                        tma_load_5d(a_base + (size_t)sa * p.a_stage_bytes, &tmap0, &a_full[sa],
+                                    (x0 - p.pw) * 4, y0 - p.ph, z0 - p.pd, c * 2, n);
+                    else
+                        tma_load_5d(a_base + (size_t)sa * p.a_stage_bytes, &tmap1, &a_full[sa],
+                                    (x0 - p.pw + p.off1_w) * 4, y0 - p.ph + p.off1_h, z0 - p.pd + p.off1_d,
+                                    (c - p.chunks0) * 2, n);
+                    if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
+                    for (int g = 0; g < ngroups; g++) {
+                        mbar_wait(&b_empty[sb], pb ^ 1);
+                        mbar_arrive_expect_tx(&b_full[sb], p.b_stage_bytes);
+                        const float* src = p.wpk + ((size_t)(nt * nchunks + c) * ntaps + (size_t)g * p.TG) *
+                                                       (size_t)(2 * p.NT * 4);
+                        bulk_load_1d(b_base + (size_t)sb * p.b_stage_bytes, src, p.b_stage_bytes, &b_full[sb]);
+                        if (++sb == (uint32_t)p.SB) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(p.NT, 0, 0);
+            const uint32_t a_lbo = (uint32_t)(p.HX * p.HY * p.HZ * 16);  // between the two 4-channel planes
+            const uint32_t a_sbo = (uint32_t)(p.HX * 16);                // next y row (8-row group)
+            const uint32_t b_lbo = (uint32_t)(p.NT * 16);
+            const uint32_t b_sbo = 128;
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it++) {
+                const uint32_t buf = it & 1, use = it >> 1;
+                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * 256;
+                for (int c = 0; c < nchunks; c++) {
+                    mbar_wait(&a_full[sa], pa);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(a_base + (size_t)sa * p.a_stage_bytes);
+                    int tap = 0;
+                    for (int g = 0; g < ngroups; g++) {
+                        mbar_wait(&b_full[sb], pb);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(b_base + (size_t)sb * p.b_stage_bytes);
+                        for (int tg = 0; tg < p.TG; tg++, tap++) {
+                            const int dz = tap / (p.kh * p.kw);
+                            const int dy = (tap / p.kw) % p.kh;
+                            const int dx = tap % p.kw;
+                            const uint64_t bdesc = umma_desc(b_addr + (uint32_t)tg * (2u * p.NT * 16u), b_lbo, b_sbo);
+                            const uint32_t accum = (c | tap) ? 1u : 0u;
+                            for (int pl = 0; pl < p.TZ; pl++) {
+                                const uint32_t off = (uint32_t)(((pl + dz) * p.HY + dy) * p.HX + dx) * 16u;
+                                umma_tf32(acc + (uint32_t)(pl * p.NT), umma_desc(a_addr + off, a_lbo, a_sbo), bdesc,
+                                          idesc, accum);
+                            }
+                        }
+                        umma_commit(&b_empty[sb]);
+                        if (++sb == (uint32_t)p.SB) { sb = 0; pb ^= 1; }
+                    }
+                    umma_commit(&a_empty[sa]);
+                    if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // GEMM row inside the tile
+        const int ry = row >> 3, rx = row & 7;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it++) {
+            const uint32_t buf = it & 1, use = it >> 1;
+            int nt, n, z0, y0, x0;
+            decode_tile(p, t, nt, n, z0, y0, x0);
+            mbar_wait(&acc_full[buf], use & 1);
+            tc_fence_after();
+            const int y = y0 + ry, x = x0 + rx;
+            const bool in_xy = (y < p.Ho) && (x < p.Wo);
+            for (int pl = 0; pl < p.TZ; pl++) {
+                const int z = z0 + pl;
+                if (z >= p.Do) break;           // warp-uniform
+                const bool valid = in_xy;
+                for (int cb = 0; cb < p.NT; cb += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)(pl * p.NT + cb), v);
+                    const int ncol = nt * p.NT + cb;     // first global N column of this group
+                    if (p.bias) {
+                        const int b0 = p.scatter ? (ncol % p.Cup) : ncol;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] += (b0 + j < p.n_bias) ? __ldg(p.bias + b0 + j) : 0.f;
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (!p.scatter) {
+                        if (valid) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; j4++) {
+                                int cq = (ncol >> 2) + j4;
+                                float* base; int cqa;
+                                if (cq < p.cq0) { base = p.dst0; cqa = p.cq0_alloc; }
+                                else { base = p.dst1; cq -= p.cq0; cqa = p.cq1_alloc; }
+                                if (base != nullptr && cq < cqa) {
+                                    size_t o = ((((size_t)n * cqa + cq) * p.Do + z) * p.Ho + y) * (size_t)p.Wo + x;
+                                    reinterpret_cast<float4*>(base)[o] =
+                                        make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                                }
+                            }
+                        }
+                    } else {
+                        // column = tap * Cup + co ; fine voxel = (z*sd+i, y*sh+j, x*sw+k)
+                        const int tapi = ncol / p.Cup, co = ncol % p.Cup;
+                        const int ti = tapi / (p.sh * p.sw), tj = (tapi / p.sw) % p.sh, tk = tapi % p.sw;
+                        const int fz = z * p.sd + ti, fy = y * p.sh + tj, fx = x * p.sw + tk;
+                        if (valid && fz < p.Ds && fy < p.Hs && fx < p.Ws) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; j4++) {
+                                int cq = (co >> 2) + j4;
+                                if (cq < p.cq0_alloc) {
+                                    size_t o = ((((size_t)n * p.cq0_alloc + cq) * p.Ds + fz) * p.Hs + fy) * (size_t)p.Ws + fx;
+                                    reinterpret_cast<float4*>(p.dst0)[o] =
+                                        make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                                }
+                            }
+                        }
+                    }
+                    if (p.stats) {
+                        // per-channel sum / sumsq over the warp's 32 rows: 16-value butterfly transpose-reduce
+                        bool sv = valid;
+                        if (p.scatter) {
+                            const int tapi = ncol / p.Cup;
+                            const int ti = tapi / (p.sh * p.sw), tj = (tapi / p.sw) % p.sh, tk = tapi % p.sw;
+                            sv = valid && (z * p.sd + ti < p.Ds) && (y * p.sh + tj < p.Hs) && (x * p.sw + tk < p.Ws);
+                        }
+                        float s[16], ss[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) { float a = sv ? v[j] : 0.f; s[j] = a; ss[j] = a * a; }
+                        // after the 4 halving steps lane L holds column (L & 15)'s partial over 2 rows-halves
+#pragma unroll
+                        for (int step = 0; step < 4; step++) {
+                            const int half = 8 >> step;           // 8,4,2,1 values kept
+                            const int bit = 1 << step;            // exchange partner lane bit
+                            const bool upper = (lane & bit) != 0;
+#pragma unroll
+                            for (int j = 0; j < half; j++) {
+                                float send_s = upper ? s[j] : s[j + half];
+                                float send_q = upper ? ss[j] : ss[j + half];
+                                float keep_s = upper ? s[j + half] : s[j];
+                                float keep_q = upper ? ss[j + half] : ss[j];
+                                s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                                ss[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+                            }
+                        }
+                        float fs = s[0] + __shfl_xor_sync(0xffffffffu, s[0], 16);
+                        float fq = ss[0] + __shfl_xor_sync(0xffffffffu, ss[0], 16);
+                        if (lane < 16) {
+                            // column index recovered from the butterfly: bit k of the column = lane bit (3-k)? no:
+                            // step 0 split on value-index bit 3 by lane bit 0, step 1 bit 2 by lane bit 1, ...
+                            const int col = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
+                            int ch = ncol + col;
+                            if (p.scatter) ch = ch % p.Cup;
+                            if (ch < p.Cstat) {
+                                atomicAdd(p.stats + ((size_t)n * p.Cstat + ch) * 2, (double)fs);
+                                atomicAdd(p.stats + ((size_t)n * p.Cstat + ch) * 2 + 1, (double)fq);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// QP tensor (N, Cq, D, H, W, 4) viewed as 5D (W*4, H, D, Cq, N); box = (bx*4, by, bz, 2, 1)
+int make_qp_tensor_map(CUtensorMap* map, const float* ptr, int N, int Cq, int D, int H, int W, int bx, int by,
+                       int bz, int bcq)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[5] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)Cq, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)W * H * 16, (cuuint64_t)W * H * D * 16,
+                             (cuuint64_t)W * H * D * 16 * Cq};
+    cuuint32_t box[5] = {(cuuint32_t)bx * 4, (cuuint32_t)by, (cuuint32_t)bz, (cuuint32_t)bcq, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (box[0] > 256 || box[1] > 256 || box[2] > 256) return set_error("TMA box dimension > 256");
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+int conv_ntile_width(int npad_total)
+{
+    if (npad_total <= 256) return npad_total;
+    if (npad_total % 256 == 0) return 256;
+    if (npad_total % 128 == 0) return 128;
+    if (npad_total % 64 == 0) return 64;
+    return -1;
+}
+
+static int g_num_sms = 0;
+int num_sms()
+{
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
+{
+    ConvTcParams p;
+    memset(&p, 0, sizeof(p));
+    const int ntaps = a->kd * a->kh * a->kw;
+    if (!((a->kd == 1 || a->kd == 3) && (a->kh == 1 || a->kh == 3) && (a->kw == 1 || a->kw == 3)))
+        return set_error("conv: taps per dim must be 1 or 3");
+    p.N = a->N;
+    p.Do = a->D + 2 * a->pd - a->kd + 1;
+    p.Ho = a->H + 2 * a->ph - a->kh + 1;
+    p.Wo = a->W + 2 * a->pw - a->kw + 1;
+    if (p.Do <= 0 || p.Ho <= 0 || p.Wo <= 0) return set_error("conv: empty output");
+    p.kd = a->kd; p.kh = a->kh; p.kw = a->kw; p.pd = a->pd; p.ph = a->ph; p.pw = a->pw;
+    const int npad_total = a->n_total;          // padded N space (multiple of 16)
+    if (npad_total % 16) return set_error("conv: n_total must be a multiple of 16");
+    p.NT = conv_ntile_width(npad_total);
+    if (p.NT <= 0) return set_error("conv: unsupported output width %d", npad_total);
+    p.n_ntiles = npad_total / p.NT;
+    // accumulator planes per tile: two ping-pong sets of <= 256 TMEM columns
+    int tz = 256 / p.NT; if (tz > 8) tz = 8; if (tz > p.Do) tz = p.Do; if (tz < 1) tz = 1;
+    if (a->force_tz > 0) tz = a->force_tz;
+    p.TZ = tz;
+    p.HX = kTX + a->kw - 1; p.HY = kTY + a->kh - 1; p.HZ = tz + a->kd - 1;
+    p.tiles_x = (p.Wo + kTX - 1) / kTX; p.tiles_y = (p.Ho + kTY - 1) / kTY; p.tiles_z = (p.Do + tz - 1) / tz;
+    p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_z * p.n_ntiles * a->N;
+    p.chunks0 = e3b_cpad(a->C0) / 8;
+    p.chunks1 = a->src1 ? e3b_cpad(a->C1) / 8 : 0;
+    p.off1_d = a->off1_d; p.off1_h = a->off1_h; p.off1_w = a->off1_w;
+    p.a_stage_bytes = (uint32_t)(p.HX * p.HY * p.HZ * 16 * 2);
+    // weight stage: largest tap group (27, 9, 3, 1) that fits 40 KB
+    int tg = ntaps;
+    while (tg > 1 && (size_t)tg * 2 * p.NT * 16 > 40 * 1024) tg /= 3;
+    p.TG = tg;
+    p.b_stage_bytes = (uint32_t)(tg * 2 * p.NT * 16);
+    const size_t budget = 227 * 1024 - 1024 - 256;
+    int sa = 2, sb = 2;
+    // grow depth while it fits (A first up to 4, then B up to 4)
+    for (;;) {
+        bool grew = false;
+        if (sa < 4 && (size_t)(sa + 1) * p.a_stage_bytes + (size_t)sb * p.b_stage_bytes <= budget) { sa++; grew = true; }
+        if (sb < 4 && (size_t)sa * p.a_stage_bytes + (size_t)(sb + 1) * p.b_stage_bytes <= budget) { sb++; grew = true; }
+        if (!grew) break;
+    }
+    if ((size_t)sa * p.a_stage_bytes + (size_t)sb * p.b_stage_bytes > budget)
+        return set_error("conv: tile does not fit shared memory");
+    p.SA = sa; p.SB = sb;
+    p.bias = a->bias; p.n_bias = a->n_bias;
+    p.dst0 = a->dst0; p.dst1 = a->dst1;
+    p.cq0_alloc = e3b_cpad(a->Cd0) / 4;
+    p.cq1_alloc = a->dst1 ? e3b_cpad(a->Cd1) / 4 : 0;
+    p.cq0 = a->dst1 ? p.cq0_alloc : (1 << 30);
+    p.relu = a->relu;
+    p.stats = a->stats; p.Cstat = a->stats_channels;
+    p.scatter = a->scatter; p.sd = a->sd; p.sh = a->sh; p.sw = a->sw;
+    p.Cup = a->scatter ? e3b_cpad(a->Cd0) : 1;
+    if (a->scatter && p.Cup % 16) p.Cup = (p.Cup + 15) & ~15;
+    p.Ds = a->Ds; p.Hs = a->Hs; p.Ws = a->Ws;
+    p.wpk = a->wpk;
+
+    CUtensorMap m0, m1;
+    int rc = make_qp_tensor_map(&m0, a->src0, a->N, p.chunks0 * 2, a->D, a->H, a->W, p.HX, p.HY, p.HZ, 2);
+    if (rc) return rc;
+    if (a->src1) {
+        rc = make_qp_tensor_map(&m1, a->src1, a->N, p.chunks1 * 2, a->D1, a->H1, a->W1, p.HX, p.HY, p.HZ, 2);
+        if (rc) return rc;
+    } else {
+        m1 = m0;
+    }
+    const size_t smem = (size_t)sa * p.a_stage_bytes + (size_t)sb * p.b_stage_bytes + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = 227 * 1024;
+    }
+    if (p.stats) {
+        cudaError_t e = cudaMemsetAsync(p.stats, 0, sizeof(double) * 2 * (size_t)a->N * p.Cstat, stream);
+        if (e != cudaSuccess) return set_error("conv: stats memset: %s", cudaGetErrorString(e));
+    }
+    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_tc_kernel<<<grid, kThreads, smem, stream>>>(m0, m1, p);
+    return check_launch("conv_tc");
+}
+
+}  // namespace e3b

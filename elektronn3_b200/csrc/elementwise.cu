@@ -1,0 +1,742 @@
+// HBM-bound kernels of the UNet path: layout conversion, weight packing, norm statistics finalisation,
+// fused normalise + ReLU (+ max-pool), their backward (with un-pooling, skip-gradient add and
+// space-to-depth output), and the 1x1x1 head fused with softmax / argmax / crop-and-place.
+// All of them move 16-byte quads with consecutive threads on consecutive voxels (coalesced 512 B/warp).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace e3b {
+
+static inline int grid_for(size_t total, int block, int max_waves = 8)
+{
+    size_t b = (total + block - 1) / block;
+    size_t cap = (size_t)num_sms() * max_waves * (2048 / block);
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCDHW box -> QP   (network input, Predictor tile gather)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const float* __restrict__ src, const int32_t* __restrict__ origins, float4* __restrict__ dst,
+                            int N, int C, int Cq, int D, int H, int W, int Dv, int Hv, int Wv, int z0, int y0, int x0,
+                            int single)
+{
+    const size_t total = (size_t)N * Cq * D * H * W;
+    const size_t plane = (size_t)Dv * Hv * Wv;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int x = (int)(r % W); r /= W;
+        const int y = (int)(r % H); r /= H;
+        const int z = (int)(r % D); r /= D;
+        const int cq = (int)(r % Cq);
+        const int n = (int)(r / Cq);
+        int oz = z0, oy = y0, ox = x0;
+        if (origins) { oz = origins[3 * n]; oy = origins[3 * n + 1]; ox = origins[3 * n + 2]; }
+        const int sz = z + oz, sy = y + oy, sx = x + ox;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (sz >= 0 && sz < Dv && sy >= 0 && sy < Hv && sx >= 0 && sx < Wv) {
+            const size_t vox = ((size_t)sz * Hv + sy) * Wv + sx;
+            const size_t nb = single ? 0 : (size_t)n * C * plane;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = cq * 4 + j;
+                if (c < C) v[j] = __ldg(src + nb + (size_t)c * plane + vox);
+            }
+        }
+        dst[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__global__ void unpack_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int C, int Cq, size_t S)
+{
+    const size_t total = (size_t)N * C * S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t v = i % S;
+        const int c = (int)((i / S) % C);
+        const int n = (int)(i / (S * C));
+        dst[i] = src[(((size_t)n * Cq + (c >> 2)) * S + v) * 4 + (c & 3)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: torch layout -> [ntile][chunk8][tap][kq 2][NT][4] (K-major no-swizzle smem image)
+// ------------------------------------------------------------------------------------------------
+struct PackDims { int ktot, ntot, taps, NT; };
+
+static PackDims pack_dims(int mode, int C0, int C1, int Co, int kd, int kh, int kw)
+{
+    PackDims d;
+    const int t = kd * kh * kw;
+    const int cin = cpad8(C0) + (C1 > 0 ? cpad8(C1) : 0);
+    switch (mode) {
+    case 0: d.ktot = cin; d.ntot = cpad16(Co); d.taps = t; break;
+    case 1: d.ktot = cpad8(Co); d.ntot = cpad16(cin); d.taps = t; break;
+    case 2: d.ktot = cpad8(C0); d.ntot = t * cpad16(Co); d.taps = 1; break;
+    default: d.ktot = t * cpad8(Co); d.ntot = cpad16(C0); d.taps = 1; break;
+    }
+    d.NT = conv_ntile_width(d.ntot);
+    return d;
+}
+
+__global__ void pack_weights_kernel(int mode, const float* __restrict__ w, const float* __restrict__ scale,
+                                    float* __restrict__ dst, int C0, int C1, int Co, int tu, PackDims d)
+{
+    const size_t total = (size_t)d.ktot * d.ntot * d.taps;
+    const int C0p = cpad8(C0), Cop8 = cpad8(Co), Cop16 = cpad16(Co);
+    const int nchunks = d.ktot / 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int k4 = (int)(r % 4); r /= 4;
+        const int nn = (int)(r % d.NT); r /= d.NT;
+        const int kq = (int)(r % 2); r /= 2;
+        const int tap = (int)(r % d.taps); r /= d.taps;
+        const int chunk = (int)(r % nchunks);
+        const int nt = (int)(r / nchunks);
+        const int k = chunk * 8 + kq * 4 + k4;
+        const int n = nt * d.NT + nn;
+        float v = 0.f;
+        if (mode == 0 || mode == 1) {
+            const int kc = mode == 0 ? k : n;      // index into the [pad8(C0) | pad8(C1)] channel space
+            const int oc = mode == 0 ? n : k;      // output channel of the torch weight
+            int ci = -1;
+            if (kc < C0p) { if (kc < C0) ci = kc; }
+            else if (kc - C0p < C1) ci = C0 + kc - C0p;
+            if (ci >= 0 && oc < Co) {
+                const int tp = mode == 0 ? tap : d.taps - 1 - tap;
+                v = w[((size_t)oc * (C0 + C1) + ci) * d.taps + tp];
+                if (scale && mode == 0) v *= scale[oc];
+            }
+        } else if (mode == 2) {
+            const int t = n / Cop16, co = n % Cop16;
+            if (k < C0 && co < Co) v = w[((size_t)k * Co + co) * tu + t];
+        } else {
+            const int t = k / Cop8, co = k % Cop8;
+            if (n < C0 && co < Co) v = w[((size_t)n * Co + co) * tu + t];
+        }
+        dst[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// normalisation statistics -> per-(n,c) scale / shift (+ running stats)
+// ------------------------------------------------------------------------------------------------
+__global__ void norm_finalize_kernel(const double* __restrict__ stats, int mode, int G, int N, int C, int Cp, double S,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                     float* running_mean, float* running_var, float momentum, float* __restrict__ scale,
+                                     float* __restrict__ shift, float* __restrict__ mean_o, float* __restrict__ rstd_o)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * Cp) return;
+    const int n = i / Cp, c = i % Cp;
+    float sc = 0.f, sh = 0.f, mu_f = 0.f, r_f = 1.f;
+    if (c < C) {
+        const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+        double mu = 0.0, var = 1.0 - (double)eps;
+        if (mode == 0) {
+            sc = 1.f; sh = 0.f;
+        } else {
+            if (mode == 1) {
+                const int cg = C / G, g = c / cg;
+                double s = 0.0, ss = 0.0;
+                for (int j = 0; j < cg; j++) {
+                    s += stats[((size_t)n * C + g * cg + j) * 2];
+                    ss += stats[((size_t)n * C + g * cg + j) * 2 + 1];
+                }
+                const double cnt = S * cg;
+                mu = s / cnt; var = ss / cnt - mu * mu;
+            } else if (mode == 2) {
+                double s = 0.0, ss = 0.0;
+                for (int j = 0; j < N; j++) { s += stats[((size_t)j * C + c) * 2]; ss += stats[((size_t)j * C + c) * 2 + 1]; }
+                const double cnt = S * N;
+                mu = s / cnt; var = ss / cnt - mu * mu;
+                if (n == 0 && running_mean) {
+                    const double unb = cnt > 1 ? var * cnt / (cnt - 1.0) : var;
+                    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mu);
+                    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+                }
+            } else {
+                mu = running_mean[c]; var = running_var[c];
+            }
+            if (var < 0.0) var = 0.0;
+            const double r = 1.0 / sqrt(var + (double)eps);
+            sc = (float)(r * ga); sh = (float)(be - mu * r * ga);
+            mu_f = (float)mu; r_f = (float)r;
+        }
+    }
+    scale[i] = sc; shift[i] = sh;
+    if (mean_o) mean_o[i] = mu_f;
+    if (rstd_o) rstd_o[i] = r_f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a = relu(y*scale+shift)  [+ pooled = maxpool(a), kernel (pkd,pkh,pkw), ceil mode]
+// one thread per pooling window (or voxel) per 4-channel plane
+// ------------------------------------------------------------------------------------------------
+__global__ void norm_act_kernel(const float4* __restrict__ y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, float4* __restrict__ a, float4* __restrict__ pooled,
+                                int N, int Cq, int D, int H, int W, int pkd, int pkh, int pkw, int relu)
+{
+    const int Dp = (D + pkd - 1) / pkd, Hp = (H + pkh - 1) / pkh, Wp = (W + pkw - 1) / pkw;
+    const size_t total = (size_t)N * Cq * Dp * Hp * Wp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int xp = (int)(r % Wp); r /= Wp;
+        const int yp = (int)(r % Hp); r /= Hp;
+        const int zp = (int)(r % Dp); r /= Dp;
+        const int cq = (int)(r % Cq);
+        const int n = (int)(r / Cq);
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (scale) {
+            sc = *reinterpret_cast<const float4*>(scale + ((size_t)n * Cq + cq) * 4);
+            sh = *reinterpret_cast<const float4*>(shift + ((size_t)n * Cq + cq) * 4);
+        }
+        float4 m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
+        const size_t base = ((size_t)n * Cq + cq) * D;
+        for (int dz = 0; dz < pkd; dz++) {
+            const int z = zp * pkd + dz; if (z >= D) break;
+            for (int dy = 0; dy < pkh; dy++) {
+                const int yy = yp * pkh + dy; if (yy >= H) break;
+                for (int dx = 0; dx < pkw; dx++) {
+                    const int x = xp * pkw + dx; if (x >= W) break;
+                    const size_t o = ((base + z) * H + yy) * W + x;
+                    float4 v = y[o];
+                    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (a) a[o] = v;
+                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                }
+            }
+        }
+        if (pooled) pooled[i] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of norm -> relu [-> pool]
+// ------------------------------------------------------------------------------------------------
+struct NormBwdDev {
+    const float4 *a, *y, *g0, *g1, *gp;
+    int N, Cq, C, D, H, W, wd, wh, ww;     // window = pooling kernel (gp) or s2d stride, else 1
+    int Dw, Hw, Ww;
+    int relu, s2d;
+    const float *gamma, *mean, *rstd, *m1, *m2;
+    double* sums;
+    float4* dy;
+};
+
+// loads one window, returns dr (masked upstream gradient) and xhat for up to 8 voxels
+E3B_DEVINL int load_window(const NormBwdDev& p, int n, int cq, int zw, int yw, int xw, const float4& mu, const float4& rs,
+                           float4* dr, float4* xh, size_t* offs, int* slot)
+{
+    const size_t base = ((size_t)n * p.Cq + cq) * p.D;
+    float4 av[8];
+    int cnt = 0;
+    for (int dz = 0; dz < p.wd; dz++) {
+        const int z = zw * p.wd + dz;
+        for (int dyy = 0; dyy < p.wh; dyy++) {
+            const int yy = yw * p.wh + dyy;
+            for (int dx = 0; dx < p.ww; dx++) {
+                const int x = xw * p.ww + dx;
+                if (z >= p.D || yy >= p.H || x >= p.W) continue;
+                const size_t o = ((base + z) * p.H + yy) * p.W + x;
+                offs[cnt] = o;
+                slot[cnt] = (dz * p.wh + dyy) * p.ww + dx;
+                av[cnt] = p.a[o];
+                const float4 yv = p.y[o];
+                xh[cnt] = make_float4((yv.x - mu.x) * rs.x, (yv.y - mu.y) * rs.y, (yv.z - mu.z) * rs.z, (yv.w - mu.w) * rs.w);
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.g0) g = p.g0[o];
+                if (p.g1) { const float4 t = p.g1[o]; g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w; }
+                dr[cnt] = g;
+                cnt++;
+            }
+        }
+    }
+    if (p.gp) {
+        // route the pooled gradient to the first maximum in (d,h,w) scan order (torch max_pool backward)
+        const float4 gpv = p.gp[((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw];
+        int bx = 0, by = 0, bz = 0, bw = 0;
+        for (int j = 1; j < cnt; j++) {
+            if (av[j].x > av[bx].x) bx = j;
+            if (av[j].y > av[by].y) by = j;
+            if (av[j].z > av[bz].z) bz = j;
+            if (av[j].w > av[bw].w) bw = j;
+        }
+        for (int j = 0; j < cnt; j++) {
+            if (j == bx) dr[j].x += gpv.x;
+            if (j == by) dr[j].y += gpv.y;
+            if (j == bz) dr[j].z += gpv.z;
+            if (j == bw) dr[j].w += gpv.w;
+        }
+    }
+    if (p.relu) {
+        for (int j = 0; j < cnt; j++) {
+            if (!(av[j].x > 0.f)) dr[j].x = 0.f;
+            if (!(av[j].y > 0.f)) dr[j].y = 0.f;
+            if (!(av[j].z > 0.f)) dr[j].z = 0.f;
+            if (!(av[j].w > 0.f)) dr[j].w = 0.f;
+        }
+    }
+    return cnt;
+}
+
+// grid: (blocks per plane, Cq, N)
+__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p)
+{
+    const int cq = blockIdx.y, n = blockIdx.z;
+    const size_t nc = ((size_t)n * p.Cq + cq) * 4;
+    const float4 mu = *reinterpret_cast<const float4*>(p.mean + nc);
+    const float4 rs = *reinterpret_cast<const float4*>(p.rstd + nc);
+    const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < wins; i += (size_t)gridDim.x * blockDim.x) {
+        const int xw = (int)(i % p.Ww), yw = (int)((i / p.Ww) % p.Hw), zw = (int)(i / ((size_t)p.Ww * p.Hw));
+        float4 dr[8], xh[8]; size_t offs[8]; int slot[8];
+        const int cnt = load_window(p, n, cq, zw, yw, xw, mu, rs, dr, xh, offs, slot);
+        for (int j = 0; j < cnt; j++) {
+            s1[0] += dr[j].x; s1[1] += dr[j].y; s1[2] += dr[j].z; s1[3] += dr[j].w;
+            s2[0] += dr[j].x * xh[j].x; s2[1] += dr[j].y * xh[j].y; s2[2] += dr[j].z * xh[j].z; s2[3] += dr[j].w * xh[j].w;
+        }
+    }
+    __shared__ float red[8][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+    }
+    if (lane == 0) {
+        for (int j = 0; j < 4; j++) { red[warp][j] = s1[j]; red[warp][4 + j] = s2[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += (double)red[w][threadIdx.x];
+        const int j = threadIdx.x & 3, which = threadIdx.x >> 2;
+        atomicAdd(p.sums + (nc + j) * 2 + which, t);
+    }
+}
+
+__global__ void norm_bwd_finalize_kernel(const double* __restrict__ sums, const double* __restrict__ fwd_stats, int mode,
+                                         int G, int N, int C, int Cp, double S, const float* __restrict__ gamma,
+                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                         float* __restrict__ m1o, float* __restrict__ m2o, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta, float* __restrict__ dbias)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * Cp) return;
+    const int n = i / Cp, c = i % Cp;
+    if (c >= C) { m1o[i] = 0.f; m2o[i] = 0.f; return; }
+    double m1 = 0.0, m2 = 0.0;
+    if (mode == 1) {
+        const int cg = C / G, g = c / cg;
+        for (int j = 0; j < cg; j++) {
+            const int cc = g * cg + j;
+            const double ga = gamma ? (double)gamma[cc] : 1.0;
+            m1 += ga * sums[((size_t)n * Cp + cc) * 2];
+            m2 += ga * sums[((size_t)n * Cp + cc) * 2 + 1];
+        }
+        m1 /= S * cg; m2 /= S * cg;
+    } else if (mode == 2) {
+        const double ga = gamma ? (double)gamma[c] : 1.0;
+        for (int j = 0; j < N; j++) { m1 += sums[((size_t)j * Cp + c) * 2]; m2 += sums[((size_t)j * Cp + c) * 2 + 1]; }
+        m1 *= ga / (S * N); m2 *= ga / (S * N);
+    }
+    m1o[i] = (float)m1; m2o[i] = (float)m2;
+    if (n != 0) return;
+    // per-channel parameter gradients (loop over the batch; for group mode m1/m2 differ per sample)
+    double dg = 0.0, db = 0.0, dbi = 0.0;
+    for (int j = 0; j < N; j++) {
+        const double S1 = sums[((size_t)j * Cp + c) * 2], S2 = sums[((size_t)j * Cp + c) * 2 + 1];
+        dg += S2; db += S1;
+        if (dbias) {
+            const double ga = (gamma && mode != 0) ? (double)gamma[c] : 1.0;
+            const double r = (double)rstd[(size_t)j * Cp + c], mu = (double)mean[(size_t)j * Cp + c];
+            double mm1 = 0.0, mm2 = 0.0;
+            if (mode == 1) {
+                const int cg = C / G, g = c / cg;
+                for (int q = 0; q < cg; q++) {
+                    const int cc = g * cg + q;
+                    const double gq = gamma ? (double)gamma[cc] : 1.0;
+                    mm1 += gq * sums[((size_t)j * Cp + cc) * 2];
+                    mm2 += gq * sums[((size_t)j * Cp + cc) * 2 + 1];
+                }
+                mm1 /= S * cg; mm2 /= S * cg;
+            } else if (mode == 2) { mm1 = m1; mm2 = m2; }
+            double sum_xhat = 0.0;
+            if (mode == 1 || mode == 2) sum_xhat = r * (fwd_stats[((size_t)j * C + c) * 2] - S * mu);
+            dbi += r * (ga * S1 - S * mm1 - mm2 * sum_xhat);
+        }
+    }
+    if (dgamma) dgamma[c] = (float)dg;
+    if (dbeta) dbeta[c] = (float)db;
+    if (dbias) dbias[c] = (float)dbi;
+}
+
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
+{
+    const int cq = blockIdx.y, n = blockIdx.z;
+    const size_t nc = ((size_t)n * p.Cq + cq) * 4;
+    const float4 mu = *reinterpret_cast<const float4*>(p.mean + nc);
+    const float4 rs = *reinterpret_cast<const float4*>(p.rstd + nc);
+    const float4 m1 = *reinterpret_cast<const float4*>(p.m1 + nc);
+    const float4 m2 = *reinterpret_cast<const float4*>(p.m2 + nc);
+    float4 ga = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.gamma) {
+        const int c = cq * 4;
+        ga.x = c < p.C ? p.gamma[c] : 0.f; ga.y = c + 1 < p.C ? p.gamma[c + 1] : 0.f;
+        ga.z = c + 2 < p.C ? p.gamma[c + 2] : 0.f; ga.w = c + 3 < p.C ? p.gamma[c + 3] : 0.f;
+    }
+    const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
+    const int nslots = p.wd * p.wh * p.ww;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < wins; i += (size_t)gridDim.x * blockDim.x) {
+        const int xw = (int)(i % p.Ww), yw = (int)((i / p.Ww) % p.Hw), zw = (int)(i / ((size_t)p.Ww * p.Hw));
+        float4 dr[8], xh[8]; size_t offs[8]; int slot[8];
+        const int cnt = load_window(p, n, cq, zw, yw, xw, mu, rs, dr, xh, offs, slot);
+        if (p.s2d) {
+            // every tap plane of the coarse voxel is written (absent fine voxels -> 0)
+            for (int s = 0; s < nslots; s++)
+                p.dy[(((size_t)n * nslots + s) * p.Cq + cq) * wins + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int j = 0; j < cnt; j++) {
+            float4 o;
+            o.x = rs.x * (ga.x * dr[j].x - m1.x - xh[j].x * m2.x);
+            o.y = rs.y * (ga.y * dr[j].y - m1.y - xh[j].y * m2.y);
+            o.z = rs.z * (ga.z * dr[j].z - m1.z - xh[j].z * m2.z);
+            o.w = rs.w * (ga.w * dr[j].w - m1.w - xh[j].w * m2.w);
+            if (p.s2d) p.dy[(((size_t)n * nslots + slot[j]) * p.Cq + cq) * wins + i] = o;
+            else p.dy[offs[j]] = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1x1x1 head (+ softmax / argmax, crop-and-place)
+// ------------------------------------------------------------------------------------------------
+static constexpr int kHeadMaxCo = 16;
+
+__global__ void __launch_bounds__(256) head_kernel(const e3b_head_args p, int Cq)
+{
+    extern __shared__ float sw[];      // [Co][Cq*4] weights then [Co] bias
+    const int Cp = Cq * 4;
+    for (int i = threadIdx.x; i < p.Co * Cp; i += blockDim.x) {
+        const int co = i / Cp, c = i % Cp;
+        sw[i] = c < p.C ? p.w[co * p.C + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < p.Co; i += blockDim.x) sw[p.Co * Cp + i] = p.b ? p.b[i] : 0.f;
+    __syncthreads();
+    const float4* a = reinterpret_cast<const float4*>(p.a);
+    const size_t box = (size_t)p.cn_d * p.cn_h * p.cn_w;
+    const size_t total = (size_t)p.N * box;
+    const size_t S = (size_t)p.D * p.H * p.W;
+    const size_t Sd = (size_t)p.Dd * p.Hd * p.Wd;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / box);
+        size_t r = i % box;
+        const int x = (int)(r % p.cn_w); r /= p.cn_w;
+        const int y = (int)(r % p.cn_h);
+        const int z = (int)(r / p.cn_h);
+        const size_t vin = ((size_t)(z + p.c0_d) * p.H + (y + p.c0_h)) * p.W + (x + p.c0_w);
+        float acc[kHeadMaxCo];
+#pragma unroll
+        for (int co = 0; co < kHeadMaxCo; co++) acc[co] = co < p.Co ? sw[p.Co * Cp + co] : 0.f;
+        for (int cq = 0; cq < Cq; cq++) {
+            const float4 v = a[((size_t)n * Cq + cq) * S + vin];
+#pragma unroll
+            for (int co = 0; co < kHeadMaxCo; co++) {
+                if (co < p.Co) {
+                    const float* wr = sw + co * Cp + cq * 4;
+                    acc[co] = fmaf(v.x, wr[0], fmaf(v.y, wr[1], fmaf(v.z, wr[2], fmaf(v.w, wr[3], acc[co]))));
+                }
+            }
+        }
+        int oz = 0, oy = 0, ox = 0;
+        if (p.dst_origin) { oz = p.dst_origin[3 * n]; oy = p.dst_origin[3 * n + 1]; ox = p.dst_origin[3 * n + 2]; }
+        // tiles of a volume that is not a multiple of the tile shape overhang the destination
+        // (the reference pads and slices back, inference.py:645-687,634): clip
+        if (z + oz >= p.Dd || y + oy >= p.Hd || x + ox >= p.Wd || z + oz < 0 || y + oy < 0 || x + ox < 0) continue;
+        const size_t vout = ((size_t)(z + oz) * p.Hd + (y + oy)) * p.Wd + (x + ox);
+        const size_t nb = p.dst_single ? 0 : (size_t)n;
+        if (p.out_mode == 2) {
+            int best = 0; float bv = acc[0];
+#pragma unroll
+            for (int co = 1; co < kHeadMaxCo; co++) if (co < p.Co && acc[co] > bv) { bv = acc[co]; best = co; }
+            reinterpret_cast<uint8_t*>(p.dst)[nb * Sd + vout] = (uint8_t)best;
+        } else {
+            if (p.out_mode == 1) {
+                float mx = acc[0];
+#pragma unroll
+                for (int co = 1; co < kHeadMaxCo; co++) if (co < p.Co) mx = fmaxf(mx, acc[co]);
+                float sum = 0.f;
+#pragma unroll
+                for (int co = 0; co < kHeadMaxCo; co++) if (co < p.Co) { acc[co] = expf(acc[co] - mx); sum += acc[co]; }
+                const float inv = 1.f / sum;
+#pragma unroll
+                for (int co = 0; co < kHeadMaxCo; co++) acc[co] *= inv;
+            }
+            float* d = reinterpret_cast<float*>(p.dst);
+#pragma unroll
+            for (int co = 0; co < kHeadMaxCo; co++)
+                if (co < p.Co) d[(nb * p.Co + co) * Sd + vout] = acc[co];
+        }
+    }
+}
+
+// da[v][c] = sum_co dl[v][co] * w[co][c]
+__global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restrict__ dl, const float* __restrict__ w,
+                                                            float4* __restrict__ da, int N, int C, int Cq, int Co, size_t S)
+{
+    extern __shared__ float sw[];
+    const int Cp = Cq * 4;
+    for (int i = threadIdx.x; i < Co * Cp; i += blockDim.x) {
+        const int co = i / Cp, c = i % Cp;
+        sw[i] = c < C ? w[co * C + c] : 0.f;
+    }
+    __syncthreads();
+    const size_t total = (size_t)N * S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = i / S, v = i % S;
+        float g[kHeadMaxCo];
+#pragma unroll
+        for (int co = 0; co < kHeadMaxCo; co++) g[co] = co < Co ? dl[(n * Co + co) * S + v] : 0.f;
+        for (int cq = 0; cq < Cq; cq++) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int co = 0; co < kHeadMaxCo; co++) {
+                if (co < Co) {
+                    const float* wr = sw + co * Cp + cq * 4;
+                    o.x = fmaf(g[co], wr[0], o.x); o.y = fmaf(g[co], wr[1], o.y);
+                    o.z = fmaf(g[co], wr[2], o.z); o.w = fmaf(g[co], wr[3], o.w);
+                }
+            }
+            da[(n * Cq + cq) * S + v] = o;
+        }
+    }
+}
+
+// ws[co][c] += sum_v dl[v][co]*a[v][c] ; ws[Co*Cp + co] += sum_v dl[v][co].   grid (chunks, Cq)
+__global__ void __launch_bounds__(256) head_bwd_w_kernel(const float* __restrict__ dl, const float4* __restrict__ a,
+                                                         double* __restrict__ ws, int N, int Cq, int Co, size_t S)
+{
+    const int cq = blockIdx.y, Cp = Cq * 4;
+    const size_t total = (size_t)N * S;
+    __shared__ float red[8][4];
+    for (int co = 0; co < Co; co++) {
+        float s[4] = {0, 0, 0, 0}, sb = 0.f;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            const size_t n = i / S, v = i % S;
+            const float g = dl[(n * Co + co) * S + v];
+            const float4 av = a[(n * Cq + cq) * S + v];
+            s[0] = fmaf(g, av.x, s[0]); s[1] = fmaf(g, av.y, s[1]); s[2] = fmaf(g, av.z, s[2]); s[3] = fmaf(g, av.w, s[3]);
+            sb += g;
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        __syncthreads();
+        if (lane == 0) { for (int j = 0; j < 4; j++) red[warp][j] = s[j]; }
+        __shared__ float redb[8];
+        if (lane == 0) redb[warp] = sb;
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += (double)red[w][threadIdx.x];
+            atomicAdd(ws + (size_t)co * Cp + cq * 4 + threadIdx.x, t);
+        }
+        if (threadIdx.x == 4 && cq == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += (double)redb[w];
+            atomicAdd(ws + (size_t)Co * Cp + co, t);
+        }
+    }
+}
+
+__global__ void head_bwd_finish_kernel(const double* __restrict__ ws, float* __restrict__ dw, float* __restrict__ db, int C,
+                                       int Cp, int Co)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Co * C) dw[i] = (float)ws[(size_t)(i / C) * Cp + (i % C)];
+    if (i < Co) db[i] = (float)ws[(size_t)Co * Cp + i];
+}
+
+}  // namespace e3b
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace e3b;
+
+extern "C" {
+
+int e3b_pack_ncdhw(const float* src, float* dst_qp, int N, int C, int D, int H, int W, int Dv, int Hv, int Wv, int z0,
+                   int y0, int x0, void* stream)
+{
+    if (N <= 0 || C <= 0) return set_error("pack: empty tensor");
+    const int Cq = cpad8(C) / 4;
+    const size_t total = (size_t)N * Cq * D * H * W;
+    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, nullptr, reinterpret_cast<float4*>(dst_qp), N, C,
+                                                                        Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0);
+    return check_launch("pack_ncdhw");
+}
+
+int e3b_gather_tiles(const float* vol, const int32_t* origins, float* dst_qp, int B, int C, int D, int H, int W, int Dv,
+                     int Hv, int Wv, void* stream)
+{
+    if (B <= 0 || C <= 0) return set_error("gather: empty batch");
+    const int Cq = cpad8(C) / 4;
+    const size_t total = (size_t)B * Cq * D * H * W;
+    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vol, origins, reinterpret_cast<float4*>(dst_qp), B, C,
+                                                                        Cq, D, H, W, Dv, Hv, Wv, 0, 0, 0, 1);
+    return check_launch("gather_tiles");
+}
+
+int e3b_unpack_qp(const float* src_qp, float* dst, int N, int C, int D, int H, int W, void* stream)
+{
+    const size_t S = (size_t)D * H * W;
+    unpack_kernel<<<grid_for((size_t)N * C * S, 256), 256, 0, (cudaStream_t)stream>>>(src_qp, dst, N, C, cpad8(C) / 4, S);
+    return check_launch("unpack_qp");
+}
+
+int64_t e3b_packed_weight_floats(int mode, int C0, int C1, int Co, int kd, int kh, int kw)
+{
+    if (mode < 0 || mode > 3) return -1;
+    PackDims d = pack_dims(mode, C0, C1, Co, kd, kh, kw);
+    if (d.NT <= 0) return -1;
+    return (int64_t)d.ktot * d.ntot * d.taps;
+}
+
+int e3b_pack_weights(int mode, const float* w, const float* scale, float* dst, int C0, int C1, int Co, int kd, int kh,
+                     int kw, void* stream)
+{
+    if (mode < 0 || mode > 3) return set_error("pack_weights: bad mode %d", mode);
+    PackDims d = pack_dims(mode, C0, C1, Co, kd, kh, kw);
+    if (d.NT <= 0) return set_error("pack_weights: unsupported output width %d", d.ntot);
+    const size_t total = (size_t)d.ktot * d.ntot * d.taps;
+    pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mode, w, scale, dst, C0, C1, Co,
+                                                                                kd * kh * kw, d);
+    return check_launch("pack_weights");
+}
+
+int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_t S, const float* gamma, const float* beta,
+                      float eps, float* running_mean, float* running_var, float momentum, float* scale, float* shift,
+                      float* mean, float* rstd, void* stream)
+{
+    if (mode == 1 && (G <= 0 || C % G)) return set_error("norm: num_channels %d not divisible by num_groups %d", C, G);
+    if (mode == 3 && (!running_mean || !running_var)) return set_error("norm: eval-mode batch norm needs running stats");
+    const int Cp = cpad8(C);
+    norm_finalize_kernel<<<(N * Cp + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        stats, mode, G, N, C, Cp, (double)S, gamma, beta, eps, running_mean, running_var, momentum, scale, shift, mean, rstd);
+    return check_launch("norm_finalize");
+}
+
+int e3b_norm_act(const float* y, const float* scale, const float* shift, float* a, float* pooled, int N, int C, int D,
+                 int H, int W, int pk_d, int pk_h, int pk_w, int relu, void* stream)
+{
+    if (!pooled) { pk_d = pk_h = pk_w = 1; }
+    if (pk_d * pk_h * pk_w > 8) return set_error("norm_act: pooling window > 8 voxels");
+    const int Cq = cpad8(C) / 4;
+    const size_t total = (size_t)N * Cq * ((D + pk_d - 1) / pk_d) * ((H + pk_h - 1) / pk_h) * ((W + pk_w - 1) / pk_w);
+    norm_act_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(pooled), N,
+        Cq, D, H, W, pk_d, pk_h, pk_w, relu);
+    return check_launch("norm_act");
+}
+
+static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)
+{
+    p.a = reinterpret_cast<const float4*>(a->a); p.y = reinterpret_cast<const float4*>(a->y);
+    p.g0 = reinterpret_cast<const float4*>(a->g0); p.g1 = reinterpret_cast<const float4*>(a->g1);
+    p.gp = reinterpret_cast<const float4*>(a->gp);
+    p.N = a->N; p.C = a->C; p.Cq = cpad8(a->C) / 4; p.D = a->D; p.H = a->H; p.W = a->W;
+    p.wd = p.wh = p.ww = 1;
+    if (a->gp && a->s2d) return set_error("norm_bwd: pooled gradient and space-to-depth output are exclusive");
+    if (a->gp) { p.wd = a->pk_d; p.wh = a->pk_h; p.ww = a->pk_w; }
+    if (a->s2d) { p.wd = a->sd; p.wh = a->sh; p.ww = a->sw; }
+    if (p.wd * p.wh * p.ww > 8) return set_error("norm_bwd: window > 8 voxels");
+    p.Dw = (a->D + p.wd - 1) / p.wd; p.Hw = (a->H + p.wh - 1) / p.wh; p.Ww = (a->W + p.ww - 1) / p.ww;
+    p.relu = a->relu; p.s2d = a->s2d;
+    p.gamma = (a->mode == 0) ? nullptr : a->gamma;
+    p.mean = a->mean; p.rstd = a->rstd; p.m1 = a->m1; p.m2 = a->m2;
+    p.sums = a->sums; p.dy = reinterpret_cast<float4*>(a->dy);
+    return 0;
+}
+
+int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* a, void* stream)
+{
+    NormBwdDev p;
+    if (fill_bwd(a, p)) return 1;
+    const int Cp = p.Cq * 4;
+    cudaError_t e = cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * (size_t)a->N * Cp, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
+    const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
+    int bx = (int)((wins + 255) / 256);
+    int cap = (8 * num_sms()) / (p.Cq * a->N); if (cap < 1) cap = 1;
+    if (bx > cap) bx = cap;
+    norm_bwd_reduce_kernel<<<dim3(bx, p.Cq, a->N), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("norm_bwd_reduce");
+}
+
+int e3b_norm_bwd_finalize(const e3b_norm_bwd_args* a, void* stream)
+{
+    const int Cp = cpad8(a->C);
+    if (a->mode == 1 && (a->G <= 0 || a->C % a->G)) return set_error("norm_bwd: bad group count");
+    if (a->dbias && (a->mode == 1 || a->mode == 2) && !a->fwd_stats) return set_error("norm_bwd: dbias needs fwd_stats");
+    norm_bwd_finalize_kernel<<<(a->N * Cp + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        a->sums, a->fwd_stats, a->mode, a->G, a->N, a->C, Cp, (double)a->D * a->H * a->W, a->gamma, a->mean, a->rstd, a->m1,
+        a->m2, a->dgamma, a->dbeta, a->dbias);
+    return check_launch("norm_bwd_finalize");
+}
+
+int e3b_norm_bwd_apply(const e3b_norm_bwd_args* a, void* stream)
+{
+    NormBwdDev p;
+    if (fill_bwd(a, p)) return 1;
+    const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
+    int bx = (int)((wins + 255) / 256);
+    int cap = (16 * num_sms()) / (p.Cq * a->N); if (cap < 1) cap = 1;
+    if (bx > cap) bx = cap;
+    norm_bwd_apply_kernel<<<dim3(bx, p.Cq, a->N), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("norm_bwd_apply");
+}
+
+int e3b_head(const e3b_head_args* a, void* stream)
+{
+    if (a->Co > kHeadMaxCo) return set_error("head: out_channels %d > %d not supported", a->Co, kHeadMaxCo);
+    if (a->out_mode < 0 || a->out_mode > 2) return set_error("head: bad out_mode");
+    const int Cq = cpad8(a->C) / 4;
+    const size_t total = (size_t)a->N * a->cn_d * a->cn_h * a->cn_w;
+    const size_t smem = sizeof(float) * ((size_t)a->Co * Cq * 4 + a->Co);
+    head_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(*a, Cq);
+    return check_launch("head");
+}
+
+int e3b_head_bwd(const float* dl, const float* a, const float* w, float* da, float* dw, float* db, double* workspace, int N,
+                 int C, int Co, int D, int H, int W, void* stream)
+{
+    if (Co > kHeadMaxCo) return set_error("head_bwd: out_channels %d > %d not supported", Co, kHeadMaxCo);
+    const int Cq = cpad8(C) / 4, Cp = Cq * 4;
+    const size_t S = (size_t)D * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (da) {
+        head_bwd_data_kernel<<<grid_for((size_t)N * S, 256), 256, sizeof(float) * Co * Cp, st>>>(
+            dl, w, reinterpret_cast<float4*>(da), N, C, Cq, Co, S);
+        if (check_launch("head_bwd_data")) return 1;
+    }
+    cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(double) * ((size_t)Co * Cp + Co), st);
+    if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
+    int bx = (2 * num_sms()) / Cq; if (bx < 1) bx = 1;
+    head_bwd_w_kernel<<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const float4*>(a), workspace, N, Cq, Co, S);
+    if (check_launch("head_bwd_w")) return 1;
+    head_bwd_finish_kernel<<<(Co * C + 127) / 128 + 1, 128, 0, st>>>(workspace, dw, db, C, Cp, Co);
+    return check_launch("head_bwd_finish");
+}
+
+}  // extern "C"

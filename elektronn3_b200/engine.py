@@ -1,0 +1,624 @@
+"""Host-side orchestration of the sm_100a kernels (libe3b.so) for the UNet forward / backward.
+
+This is the glue between the reference-shaped ``torch.nn.Module`` (elektronn3_b200/unet.py) and the
+C ABI (include/e3b.h): it owns no arithmetic.  PyTorch is used for device memory (caching allocator),
+the current stream and the parameter tensors only.
+
+Activations live in the QP layout (see csrc/common.cuh): float32 ``(N, ceil8(C)/4, D, H, W, 4)``.
+The sequence of operations follows the reference ``UNet.forward`` (models/unet.py:894-916),
+``DownConv.forward`` (:244-253) and ``UpConv.forward`` (:384-408); the backward is what autograd
+derives from them.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def cpad8(c):
+    return (c + 7) & ~7
+
+
+def cpad16(c):
+    return (c + 15) & ~15
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class QP:
+    """A float32 activation tensor in quad-planar layout."""
+    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W')
+
+    def __init__(self, t, N, C, D, H, W):
+        self.t, self.N, self.C, self.D, self.H, self.W = t, N, C, D, H, W
+
+    @staticmethod
+    def empty(N, C, D, H, W, device):
+        return QP(torch.empty((N, cpad8(C) // 4, D, H, W, 4), dtype=torch.float32, device=device), N, C, D, H, W)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+    @property
+    def spatial(self):
+        return (self.D, self.H, self.W)
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f'elektronn3_b200: {what} must be a CUDA tensor (this path has no CPU implementation)')
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'elektronn3_b200: {what} must be float32, got {t.dtype}')
+
+
+# ------------------------------------------------------------------------------------------ layout
+def pack_input(x5):
+    """NCDHW float32 -> QP (reference: the tensor `Trainer._train_step` moves to the device, trainer.py:515)"""
+    _require_cuda(x5, 'input')
+    x5 = x5.contiguous()
+    N, C, D, H, W = x5.shape
+    q = QP.empty(N, C, D, H, W, x5.device)
+    L.check(L.lib().e3b_pack_ncdhw(x5.data_ptr(), q.ptr, N, C, D, H, W, D, H, W, 0, 0, 0, _stream()), 'pack_ncdhw')
+    return q
+
+
+def unpack(q):
+    out = torch.empty((q.N, q.C, q.D, q.H, q.W), dtype=torch.float32, device=q.t.device)
+    L.check(L.lib().e3b_unpack_qp(q.ptr, out.data_ptr(), q.N, q.C, q.D, q.H, q.W, _stream()), 'unpack_qp')
+    return out
+
+
+def gather_tiles(vol, origins, B, C, tile):
+    """Predictor tile gather (inference.py:179-189): vol (C, Dv, Hv, Wv) device tensor, origins int32 (B,3)."""
+    D, H, W = tile
+    q = QP.empty(B, C, D, H, W, vol.device)
+    L.check(L.lib().e3b_gather_tiles(vol.data_ptr(), origins.data_ptr(), q.ptr, B, C, D, H, W,
+                                     vol.shape[-3], vol.shape[-2], vol.shape[-1], _stream()), 'gather_tiles')
+    return q
+
+
+# ------------------------------------------------------------------------------------------ weights
+def pack_weights(mode, w, scale, C0, C1, Co, k):
+    n = L.lib().e3b_packed_weight_floats(mode, C0, C1, Co, *k)
+    if n <= 0:
+        raise RuntimeError(f'elektronn3_b200: unsupported channel configuration C0={C0} C1={C1} Co={Co}')
+    dst = torch.empty((n,), dtype=torch.float32, device=w.device)
+    wc = w.detach()
+    if not wc.is_contiguous():
+        wc = wc.contiguous()
+    L.check(L.lib().e3b_pack_weights(mode, wc.data_ptr(), _p(scale), dst.data_ptr(), C0, C1, Co, *k, _stream()),
+            'pack_weights')
+    return dst
+
+
+class WeightCache:
+    """Packed-weight images keyed by (parameter identity, mode); invalidated by the parameter's
+    in-place version counter (optimizer steps, load_state_dict) or a moved storage (.to(device))."""
+
+    def __init__(self):
+        self.d = {}
+
+    def get(self, key, params, make):
+        sig = tuple((p.data_ptr(), p._version) for p in params if p is not None)
+        hit = self.d.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        val = make()
+        self.d[key] = (sig, val)
+        return val
+
+
+# ------------------------------------------------------------------------------------------ conv
+def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), bias=None, relu=False,
+                 stats_channels=0, dst1_C=0, scatter=None, out_spatial=None, force_tz=0):
+    """One launch of the implicit-GEMM kernel.  Returns (dst0, dst1, stats)."""
+    a = L.ConvArgs()
+    dev = src0.t.device
+    a.src0, a.C0 = src0.ptr, src0.C
+    a.N, a.D, a.H, a.W = src0.N, src0.D, src0.H, src0.W
+    if src1 is not None:
+        a.src1, a.C1 = src1.ptr, src1.C
+        a.D1, a.H1, a.W1 = src1.D, src1.H, src1.W
+        a.off1_d, a.off1_h, a.off1_w = off1
+    a.kd, a.kh, a.kw = k
+    a.pd, a.ph, a.pw = pad
+    a.wpk = wpk.data_ptr()
+    if bias is not None:
+        a.bias, a.n_bias = bias.data_ptr(), bias.numel()
+    a.n_total = n_total
+    if scatter is None:
+        Do, Ho, Wo = (src0.D + 2 * pad[0] - k[0] + 1, src0.H + 2 * pad[1] - k[1] + 1, src0.W + 2 * pad[2] - k[2] + 1)
+    else:
+        Do, Ho, Wo = out_spatial
+        a.scatter = 1
+        a.sd, a.sh, a.sw = scatter
+        a.Ds, a.Hs, a.Ws = out_spatial
+    dst0 = QP.empty(src0.N, Co, Do, Ho, Wo, dev)
+    a.dst0, a.Cd0 = dst0.ptr, Co
+    dst1 = None
+    if dst1_C:
+        dst1 = QP.empty(src0.N, dst1_C, Do, Ho, Wo, dev)
+        a.dst1, a.Cd1 = dst1.ptr, dst1_C
+    a.relu = 1 if relu else 0
+    stats = None
+    if stats_channels:
+        stats = torch.empty((src0.N, stats_channels, 2), dtype=torch.float64, device=dev)
+        a.stats, a.stats_channels = stats.data_ptr(), stats_channels
+    a.force_tz = force_tz
+    L.check(L.lib().e3b_conv(ctypes.byref(a), _stream()), 'conv')
+    return dst0, dst1, stats
+
+
+def wgrad(src0, dy, Co, k, pad, dw_shape, *, src1=None, off1=(0, 0, 0), layout=0, up_taps=0, up_co=0):
+    a = L.WgradArgs()
+    dev = src0.t.device
+    a.src0, a.C0 = src0.ptr, src0.C
+    a.N, a.D, a.H, a.W = src0.N, src0.D, src0.H, src0.W
+    if src1 is not None:
+        a.src1, a.C1 = src1.ptr, src1.C
+        a.D1, a.H1, a.W1 = src1.D, src1.H, src1.W
+        a.off1_d, a.off1_h, a.off1_w = off1
+    a.dy, a.Co = dy.ptr, Co
+    a.kd, a.kh, a.kw = k
+    a.pd, a.ph, a.pw = pad
+    dw = torch.empty(dw_shape, dtype=torch.float32, device=dev)
+    a.dw, a.layout, a.up_taps, a.up_co = dw.data_ptr(), layout, up_taps, up_co
+    n = L.lib().e3b_wgrad_workspace_floats(ctypes.byref(a))
+    if n <= 0:
+        L.check(1, 'wgrad_workspace_floats')
+    ws = torch.empty((n,), dtype=torch.float32, device=dev)
+    a.workspace = ws.data_ptr()
+    L.check(L.lib().e3b_wgrad(ctypes.byref(a), _stream()), 'wgrad')
+    return dw
+
+
+# ------------------------------------------------------------------------------------------ norm
+MODE_NONE, MODE_GROUP, MODE_BATCH, MODE_BATCH_EVAL = 0, 1, 2, 3
+
+
+class NormState:
+    __slots__ = ('scale', 'shift', 'mean', 'rstd')
+
+
+def norm_finalize(stats, mode, G, N, C, S, gamma, beta, eps, rm, rv, momentum, device):
+    Cp = cpad8(C)
+    buf = torch.empty((4, N, Cp), dtype=torch.float32, device=device)
+    st = NormState()
+    st.scale, st.shift, st.mean, st.rstd = buf[0], buf[1], buf[2], buf[3]
+    L.check(L.lib().e3b_norm_finalize(_p(stats), mode, G, N, C, S, _p(gamma), _p(beta), eps, _p(rm), _p(rv), momentum,
+                                      st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
+                                      st.rstd.data_ptr(), _stream()), 'norm_finalize')
+    return st
+
+
+def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True):
+    """a = relu(y*scale+shift) and optionally the ceil-mode max-pooled tensor."""
+    dev = y.t.device
+    a = QP.empty(y.N, y.C, y.D, y.H, y.W, dev) if write_a else None
+    pooled = None
+    pk = (1, 1, 1)
+    if pool is not None:
+        pk = pool
+        pooled = QP.empty(y.N, y.C, -(-y.D // pk[0]), -(-y.H // pk[1]), -(-y.W // pk[2]), dev)
+    L.check(L.lib().e3b_norm_act(y.ptr, _p(scale), _p(shift), a.ptr if a else None, pooled.ptr if pooled else None,
+                                 y.N, y.C, y.D, y.H, y.W, pk[0], pk[1], pk[2], 1 if relu else 0, _stream()), 'norm_act')
+    return a, pooled
+
+
+# ------------------------------------------------------------------------------------------ network description
+class ConvSpec:
+    """A conv3 layer (models/unet.py:131-149) + the norm/activation that follows it."""
+
+    def __init__(self, name, conv, norm, C0, C1):
+        self.name, self.conv, self.norm = name, conv, norm
+        w = conv.weight
+        self.Co = w.shape[0]
+        self.C0, self.C1 = C0, C1
+        ks = tuple(w.shape[2:])
+        pads = tuple(conv.padding)
+        if len(ks) == 2:
+            ks, pads = (1,) + ks, (0,) + pads
+        self.k, self.pad = ks, pads
+        self.n_total = cpad16(self.Co)
+        self.n_total_dgrad = cpad16(cpad8(C0) + (cpad8(C1) if C1 else 0))
+
+    def w5(self):
+        w = self.conv.weight
+        return w
+
+
+class UpSpec:
+    """upconv2 'transpose' (models/unet.py:152-165) + norm0/act0 of UpConv"""
+
+    def __init__(self, name, up, norm):
+        self.name, self.up, self.norm = name, up, norm
+        w = up.weight
+        self.Ci, self.Co = w.shape[0], w.shape[1]
+        s = tuple(w.shape[2:])
+        if len(s) == 2:
+            s = (1,) + s
+        self.s = s
+        self.taps = s[0] * s[1] * s[2]
+        self.n_total = self.taps * cpad16(self.Co)
+
+
+def norm_mode(norm, training):
+    """-> (mode, G) for a module produced by get_normalization (models/unet.py:77-111)"""
+    import torch.nn as nn
+    if norm is None or isinstance(norm, nn.Identity):
+        return MODE_NONE, 1
+    if isinstance(norm, nn.GroupNorm):
+        return MODE_GROUP, norm.num_groups
+    if isinstance(norm, nn.modules.instancenorm._InstanceNorm):
+        if norm.track_running_stats:
+            raise NotImplementedError('InstanceNorm with running stats is not supported')
+        return MODE_GROUP, norm.num_features
+    if isinstance(norm, nn.modules.batchnorm._BatchNorm):
+        use_batch = training or (norm.running_mean is None)
+        return (MODE_BATCH if use_batch else MODE_BATCH_EVAL), 1
+    raise NotImplementedError(f'normalization module {type(norm).__name__} is not supported')
+
+
+class Unit:
+    """Everything one conv -> norm -> relu [-> pool] stage leaves behind for the backward pass."""
+    __slots__ = ('spec', 'src0', 'src1', 'off1', 'y', 'a', 'pooled', 'pool', 'mode', 'G', 'nstate', 'stats', 'dec')
+
+
+class Net:
+    """Flat description of a UNet instance (built by elektronn3_b200.unet.UNet)."""
+
+    def __init__(self, down, up, final_conv, dim, cache):
+        self.down, self.up, self.final, self.dim, self.cache = down, up, final_conv, dim, cache
+
+
+def _bn_fold(conv, norm):
+    """eval-mode BatchNorm folded into the conv that precedes it: per-channel
+    scale for the weights and the new bias.  O(C) torch ops, cached with the packed weights."""
+    s = torch.rsqrt(norm.running_var.detach() + norm.eps)
+    if norm.weight is not None:
+        s = s * norm.weight.detach()
+    b = conv.bias.detach() if conv.bias is not None else torch.zeros_like(s)
+    b = (b - norm.running_mean.detach()) * s
+    if norm.bias is not None:
+        b = b + norm.bias.detach()
+    return s.contiguous(), b.contiguous()
+
+
+def _conv_weights(net, spec, mode, training):
+    """-> (wpk, bias) for forward; BN-eval folding applied when the following norm allows it"""
+    nm, _ = norm_mode(spec.norm, training)
+    conv = spec.conv
+    if nm == MODE_BATCH_EVAL:
+        n = spec.norm
+        params = (conv.weight, conv.bias, n.weight, n.bias, n.running_mean, n.running_var)
+
+        def make():
+            s, b = _bn_fold(conv, n)
+            return pack_weights(0, conv.weight, s, spec.C0, spec.C1, spec.Co, spec.k), b
+        return net.cache.get((spec.name, 'fwd_fold'), params, make)
+    wpk = net.cache.get((spec.name, 'fwd'), (conv.weight,),
+                        lambda: pack_weights(0, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k))
+    return wpk, (conv.bias.detach() if conv.bias is not None else None)
+
+
+def _run_unit(net, spec, src0, src1, off1, pool, training, save):
+    """conv -> norm -> relu [-> pool]  (DownConv.forward models/unet.py:244-253, UpConv :402-407)"""
+    mode, G = norm_mode(spec.norm, training)
+    wpk, bias = _conv_weights(net, spec, 0, training)
+    u = Unit()
+    u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G = spec, src0, src1, off1, pool, mode, G
+    u.pooled = u.nstate = u.stats = u.dec = None
+    if mode in (MODE_NONE, MODE_BATCH_EVAL):
+        a, _, _ = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
+                               relu=True)
+        u.y = u.a = a
+        if pool is not None:
+            _, u.pooled = norm_act(a, None, None, write_a=False, pool=pool)
+    else:
+        n = spec.norm
+        y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1,
+                                   bias=bias, stats_channels=spec.Co)
+        S = y.D * y.H * y.W
+        rm = rv = None
+        mom = 0.0
+        if mode == MODE_BATCH:
+            rm, rv, mom = _bn_running(n, training)
+        u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, S, _affine(n, 'weight'), _affine(n, 'bias'), n.eps,
+                                 rm, rv, mom, y.t.device)
+        u.y, u.stats = y, stats
+        u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool)
+    if not save:
+        u.y = u.src0 = u.src1 = None
+    return u
+
+
+def _affine(n, name):
+    t = getattr(n, name, None)
+    return None if t is None else t.detach()
+
+
+def _bn_running(n, training):
+    """BatchNorm train-mode side effects (running stats, num_batches_tracked): torch semantics"""
+    if not training or n.running_mean is None or not n.track_running_stats:
+        return None, None, 0.0
+    if n.momentum is None:
+        raise NotImplementedError('BatchNorm(momentum=None) (cumulative average) is not supported')
+    if n.num_batches_tracked is not None:
+        n.num_batches_tracked.add_(1)
+    return n.running_mean, n.running_var, float(n.momentum)
+
+
+def _run_up(net, spec, dec, enc, training, save):
+    """upconv -> autocrop -> norm0 -> act0  (UpConv.forward models/unet.py:385-398)"""
+    mode, G = norm_mode(spec.norm, training)
+    up = spec.up
+    full = (dec.D * spec.s[0], dec.H * spec.s[1], dec.W * spec.s[2])
+    # autocrop (unet.py:294-301): from_up loses one voxel where (u - d) is odd
+    out_sp = tuple(u_ - ((u_ - d_) % 2) for u_, d_ in zip(full, enc.spatial))
+    for u_, d_ in zip(out_sp, enc.spatial):
+        if u_ > d_:
+            raise RuntimeError(f'autocrop: upsampled extent {out_sp} exceeds the skip tensor {enc.spatial} '
+                               '(models/unet.py:303-324 cannot crop from_down to a larger shape)')
+    off1 = tuple((d_ - u_) // 2 for u_, d_ in zip(out_sp, enc.spatial))
+    u = Unit()
+    u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G = spec, dec, None, (0, 0, 0), None, mode, G
+    u.pooled = u.nstate = u.stats = None
+    u.dec = dec
+    bias = up.bias.detach() if up.bias is not None else None
+    if mode == MODE_BATCH_EVAL:
+        n = spec.norm
+        params = (up.weight, up.bias, n.weight, n.bias, n.running_mean, n.running_var)
+
+        def make():
+            s, b = _bn_fold(up, n)
+            # the transposed-conv weight is (Ci, Co, ...): scale its output channel axis on the host
+            shape = (1, -1) + (1,) * (up.weight.dim() - 2)
+            return pack_weights(2, (up.weight.detach() * s.view(shape)).contiguous(), None, spec.Ci, 0, spec.Co,
+                                spec.s), b
+        wpk, bias = net.cache.get((spec.name, 'up_fold'), params, make)
+    else:
+        wpk = net.cache.get((spec.name, 'up'), (up.weight,),
+                            lambda: pack_weights(2, up.weight, None, spec.Ci, 0, spec.Co, spec.s))
+    if mode in (MODE_NONE, MODE_BATCH_EVAL):
+        a, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias, relu=True,
+                               scatter=spec.s, out_spatial=out_sp)
+        u.y = u.a = a
+    else:
+        n = spec.norm
+        y, _, stats = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias,
+                                   stats_channels=spec.Co, scatter=spec.s, out_spatial=out_sp)
+        rm = rv = None
+        mom = 0.0
+        if mode == MODE_BATCH:
+            rm, rv, mom = _bn_running(n, training)
+        u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, y.D * y.H * y.W, _affine(n, 'weight'),
+                                 _affine(n, 'bias'), n.eps, rm, rv, mom, y.t.device)
+        u.y, u.stats = y, stats
+        u.a, _ = norm_act(y, u.nstate.scale, u.nstate.shift)
+    if not save:
+        u.y = u.dec = u.src0 = None
+    return u, off1
+
+
+class Tape:
+    __slots__ = ('down', 'up', 'final_in', 'in_shape', 'squeeze')
+
+
+def forward_features(net, x, training, save):
+    """Everything up to (not including) conv_final.  x: (N,C,D,H,W) or (N,C,H,W) float32 CUDA.
+    Returns (QP features, Tape)."""
+    squeeze = x.dim() == 4
+    x5 = x.unsqueeze(2) if squeeze else x
+    if x5.dim() != 5:
+        raise RuntimeError(f'expected a {net.dim + 2}-dimensional input, got shape {tuple(x.shape)}')
+    cin = net.down[0][0].C0
+    if x5.shape[1] != cin:
+        raise RuntimeError(f'expected {cin} input channels, got {x5.shape[1]}')
+    cur = pack_input(x5)
+    return forward_features_qp(net, cur, training, save, squeeze, tuple(x.shape))
+
+
+def forward_features_qp(net, cur, training, save, squeeze=False, in_shape=None):
+    tape = Tape()
+    tape.down, tape.up, tape.squeeze, tape.in_shape = [], [], squeeze, in_shape
+    enc = []
+    for c1, c2, pool in net.down:
+        u1 = _run_unit(net, c1, cur, None, (0, 0, 0), None, training, save)
+        u2 = _run_unit(net, c2, u1.a, None, (0, 0, 0), pool, training, save)
+        enc.append(u2.a)
+        cur = u2.pooled if pool is not None else u2.a
+        tape.down.append((u1, u2))
+    for i, (ups, c1, c2) in enumerate(net.up):
+        e = enc[-(i + 2)]
+        u0, off1 = _run_up(net, ups, cur, e, training, save)
+        u1 = _run_unit(net, c1, u0.a, e, off1, None, training, save)
+        u2 = _run_unit(net, c2, u1.a, None, (0, 0, 0), None, training, save)
+        cur = u2.a
+        tape.up.append((u0, u1, u2, len(net.down) - 2 - i))
+    tape.final_in = cur
+    return cur, tape
+
+
+def head(feat, conv_final, out_mode=0, dst=None, crop=None, dst_origin=None, dst_single=False):
+    """conv_final (models/unet.py:881,912) [+ Softmax(1) / Argmax of Predictor, inference.py:443-456] and
+    the Predictor's crop-and-place.  out_mode 0 logits, 1 softmax, 2 argmax(uint8)."""
+    w, b = conv_final.weight.detach(), conv_final.bias
+    Co = w.shape[0]
+    a = L.HeadArgs()
+    a.a, a.N, a.C, a.D, a.H, a.W = feat.ptr, feat.N, feat.C, feat.D, feat.H, feat.W
+    a.w, a.b, a.Co = w.data_ptr(), _p(b.detach() if b is not None else None), Co
+    a.out_mode = out_mode
+    if crop is None:
+        crop = ((0, 0, 0), feat.spatial)
+    (a.c0_d, a.c0_h, a.c0_w), (a.cn_d, a.cn_h, a.cn_w) = crop
+    if dst is None:
+        oc = 1 if out_mode == 2 else Co
+        dst = torch.empty((feat.N, oc) + tuple(crop[1]), dtype=torch.uint8 if out_mode == 2 else torch.float32,
+                          device=feat.t.device)
+    a.dst = dst.data_ptr()
+    a.Dd, a.Hd, a.Wd = dst.shape[-3], dst.shape[-2], dst.shape[-1]
+    a.dst_origin = _p(dst_origin)
+    a.dst_single = 1 if dst_single else 0
+    L.check(L.lib().e3b_head(ctypes.byref(a), _stream()), 'head')
+    return dst
+
+
+def forward(net, x, training, save):
+    feat, tape = forward_features(net, x, training, save)
+    logits = head(feat, net.final)
+    if tape.squeeze:
+        logits = logits.squeeze(2)
+    return logits, tape
+
+
+# ------------------------------------------------------------------------------------------ backward
+def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True):
+    """Backward of norm -> relu [-> pool] for unit `u`; returns (dy QP or s2d QP, dgamma, dbeta, dbias)."""
+    if u.mode == MODE_BATCH_EVAL:
+        raise NotImplementedError('backward through eval-mode BatchNorm is not on the accelerated path '
+                                  '(call model.train() or wrap evaluation in torch.no_grad())')
+    a = u.a
+    dev = a.t.device
+    N, Cp = a.N, cpad8(C)
+    args = L.NormBwdArgs()
+    args.a, args.y = a.ptr, u.y.ptr
+    args.g0, args.g1, args.gp = (g0.ptr if g0 is not None else None, g1.ptr if g1 is not None else None,
+                                 gp.ptr if gp is not None else None)
+    args.N, args.C, args.D, args.H, args.W = N, C, a.D, a.H, a.W
+    if gp is not None:
+        args.pk_d, args.pk_h, args.pk_w = u.pool
+    args.mode, args.G = u.mode, u.G
+    n = u.spec.norm
+    args.eps = float(getattr(n, 'eps', 0.0) or 0.0)
+    gamma = _affine(n, 'weight') if u.mode != MODE_NONE else None
+    args.gamma = _p(gamma)
+    if u.nstate is None:       # mode none: identity statistics
+        ident = torch.zeros((2, N, Cp), dtype=torch.float32, device=dev)
+        ident[1].fill_(1.0)
+        mean, rstd = ident[0], ident[1]
+    else:
+        mean, rstd = u.nstate.mean, u.nstate.rstd
+    args.mean, args.rstd = mean.data_ptr(), rstd.data_ptr()
+    args.fwd_stats = _p(u.stats)
+    sums = torch.empty((N, Cp, 2), dtype=torch.float64, device=dev)
+    m = torch.empty((2, N, Cp), dtype=torch.float32, device=dev)
+    args.sums, args.m1, args.m2 = sums.data_ptr(), m[0].data_ptr(), m[1].data_ptr()
+    pg = torch.empty((3, C), dtype=torch.float32, device=dev)
+    has_affine = gamma is not None
+    args.dgamma = pg[0].data_ptr() if has_affine else None
+    args.dbeta = pg[1].data_ptr() if has_affine else None
+    args.dbias = pg[2].data_ptr() if want_bias else None
+    if s2d is not None:
+        args.s2d = 1
+        args.sd, args.sh, args.sw = s2d
+        nsl = s2d[0] * s2d[1] * s2d[2]
+        Dw, Hw, Ww = -(-a.D // s2d[0]), -(-a.H // s2d[1]), -(-a.W // s2d[2])
+        dy = QP(torch.empty((N, nsl * (Cp // 4), Dw, Hw, Ww, 4), dtype=torch.float32, device=dev), N, nsl * Cp, Dw, Hw,
+                Ww)
+    else:
+        dy = QP.empty(N, C, a.D, a.H, a.W, dev)
+    args.dy = dy.ptr
+    args.relu = 1
+    lib = L.lib()
+    st = _stream()
+    L.check(lib.e3b_norm_bwd_reduce(ctypes.byref(args), st), 'norm_bwd_reduce')
+    L.check(lib.e3b_norm_bwd_finalize(ctypes.byref(args), st), 'norm_bwd_finalize')
+    L.check(lib.e3b_norm_bwd_apply(ctypes.byref(args), st), 'norm_bwd_apply')
+    return dy, (pg[0] if has_affine else None), (pg[1] if has_affine else None), (pg[2] if want_bias else None)
+
+
+def _put(grads, param, val):
+    if param is not None and param.requires_grad:
+        grads[id(param)] = val.view(param.shape) if val.shape != param.shape else val
+
+
+def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
+    """Backward of one conv -> norm -> relu [-> pool] unit: returns (dsrc0, dsrc1)."""
+    spec = u.spec
+    conv, n = spec.conv, spec.norm
+    dy, dgamma, dbeta, dbias = _norm_bwd(u, spec.Co, g0, g1, gp, want_bias=conv.bias is not None)
+    if dgamma is not None:
+        _put(grads, n.weight, dgamma)
+        _put(grads, n.bias, dbeta)
+    if conv.bias is not None:
+        _put(grads, conv.bias, dbias)
+    if conv.weight.requires_grad:
+        dw = wgrad(u.src0, dy, spec.Co, spec.k, spec.pad, tuple(conv.weight.shape), src1=u.src1, off1=u.off1)
+        _put(grads, conv.weight, dw)
+    if not need_dx:
+        return None, None
+    if u.src1 is not None and (u.off1 != (0, 0, 0) or u.src1.spatial != u.src0.spatial):
+        raise NotImplementedError('backward through a centre-cropped skip connection (conv_mode="valid") '
+                                  'is not on the accelerated path yet')
+    wpk = net.cache.get((spec.name, 'dgrad'), (conv.weight,),
+                        lambda: pack_weights(1, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k))
+    dpad = tuple(kk - 1 - pp for kk, pp in zip(spec.k, spec.pad))
+    d0, d1, _ = conv_forward(dy, wpk, spec.n_total_dgrad, spec.C0, spec.k, dpad,
+                             dst1_C=spec.C1 if u.src1 is not None else 0)
+    return d0, d1
+
+
+def backward(net, tape, dlogits, need_dx):
+    """-> (dict id(param) -> grad tensor, dx or None)"""
+    grads = {}
+    _require_cuda(dlogits, 'grad_output')
+    dl = dlogits.unsqueeze(2) if tape.squeeze else dlogits
+    dl = dl.contiguous()
+    feat = tape.final_in
+    fc = net.final
+    Co = fc.weight.shape[0]
+    dev = dl.device
+    da = QP.empty(feat.N, feat.C, feat.D, feat.H, feat.W, dev)
+    dw = torch.empty((Co, feat.C), dtype=torch.float32, device=dev)
+    db = torch.empty((Co,), dtype=torch.float32, device=dev)
+    ws = torch.empty((Co * cpad8(feat.C) + Co,), dtype=torch.float64, device=dev)
+    L.check(L.lib().e3b_head_bwd(dl.data_ptr(), feat.ptr, fc.weight.detach().data_ptr(), da.ptr, dw.data_ptr(),
+                                 db.data_ptr(), ws.data_ptr(), feat.N, feat.C, Co, feat.D, feat.H, feat.W, _stream()),
+            'head_bwd')
+    _put(grads, fc.weight, dw)
+    _put(grads, fc.bias, db)
+
+    g = da
+    skip = {}
+    for (u0, u1, u2, enc_index), (ups, c1, c2) in zip(reversed(tape.up), reversed(net.up)):
+        g, _ = _conv_unit_bwd(net, u2, g, None, None, grads, True)
+        du, denc = _conv_unit_bwd(net, u1, g, None, None, grads, True)
+        skip[enc_index] = denc
+        # norm0/act0 backward, written space-to-depth for the transposed conv's GEMMs
+        up = ups.up
+        dy, dgamma, dbeta, dbias = _norm_bwd(u0, ups.Co, du, s2d=ups.s, want_bias=up.bias is not None)
+        if dgamma is not None:
+            _put(grads, ups.norm.weight, dgamma)
+            _put(grads, ups.norm.bias, dbeta)
+        if up.bias is not None:
+            _put(grads, up.bias, dbias)
+        dec = u0.dec
+        if up.weight.requires_grad:
+            dwu = wgrad(dec, dy, dy.C, (1, 1, 1), (0, 0, 0), tuple(up.weight.shape), layout=1, up_taps=ups.taps,
+                        up_co=ups.Co)
+            _put(grads, up.weight, dwu)
+        wpk = net.cache.get((ups.name, 'up_dgrad'), (up.weight,),
+                            lambda: pack_weights(3, up.weight, None, ups.Ci, 0, ups.Co, ups.s))
+        g, _, _ = conv_forward(dy, wpk, cpad16(ups.Ci), ups.Ci, (1, 1, 1), (0, 0, 0))
+    nd = len(net.down)
+    dx = None
+    for i in range(nd - 1, -1, -1):
+        u1, u2 = tape.down[i]
+        if u2.pool is not None:
+            g, _ = _conv_unit_bwd(net, u2, skip.get(i), None, g, grads, True)
+        else:
+            g, _ = _conv_unit_bwd(net, u2, g, skip.get(i), None, grads, True)
+        g, _ = _conv_unit_bwd(net, u1, g, None, None, grads, i > 0 or need_dx)
+    if need_dx:
+        dx = unpack(g)
+        if tape.squeeze:
+            dx = dx.squeeze(2)
+    return grads, dx

@@ -1,0 +1,168 @@
+/*
+ * e3b.h -- C ABI of libe3b.so: the B200-native (sm_100a) kernels behind the elektronn3 UNet /
+ * Predictor hot path.
+ *
+ * The reference has no FFI of its own: its seam is the torch.nn.Module protocol, and the arithmetic
+ * is delegated to torch ATen/cuDNN at the call sites cited on each entry point below (paths relative
+ * to the reference root).  This library replaces those library calls.  It is bound from Python with
+ * ctypes (elektronn3_b200/_lib.py); INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C, no torch types: raw device pointers, int sizes, a cudaStream_t passed as void*.
+ *  - no allocation, no ownership transfer: the caller (PyTorch's allocator) owns every buffer.
+ *  - every function returns 0 on success, non-zero on error; e3b_last_error() returns the message of
+ *    the calling thread's last error.  Nothing throws, nothing calls exit().
+ *  - all functions only ENQUEUE work on `stream` (asynchronous w.r.t. the host) and are re-entrant.
+ *  - internal activation layout "QP" (quad-planar): float32 (N, Cq, D, H, W, 4), Cq = ceil8(C)/4,
+ *    channel c -> plane c/4, lane c%4, padding channels exactly 0.  2D data uses D = 1.
+ */
+#ifndef E3B_H
+#define E3B_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E3B_VERSION 100
+
+int e3b_version(void);
+const char* e3b_last_error(void);
+/* number of kernels launched by this library since load (all threads); bench.py's gpu_launches */
+int64_t e3b_launch_count(void);
+
+/* ---- layout conversion at the module boundary ------------------------------------------------
+ * NCDHW float32 <-> QP.  Used for the network input (reference: trainer.py:515 `inp.to(device)`)
+ * and by tests.  src may be a sub-box of a larger volume (Predictor tiles, inference.py:179-189):
+ * (Dv,Hv,Wv) are the extents of the allocation, (z0,y0,x0) the origin of the box inside it (may be
+ * negative / overhanging: out-of-volume voxels read as 0, which is tiled_apply's zero padding). */
+int e3b_pack_ncdhw(const float* src, float* dst_qp, int N, int C, int D, int H, int W,
+                   int Dv, int Hv, int Wv, int z0, int y0, int x0, void* stream);
+int e3b_unpack_qp(const float* src_qp, float* dst, int N, int C, int D, int H, int W, void* stream);
+
+/* Predictor tile gather (inference.py:179-189): tile b of the batch is the box of a single-sample
+ * volume (Cv, Dv, Hv, Wv) whose origin is origins[3*b..3*b+2] (device int32, may overhang -> 0). */
+int e3b_gather_tiles(const float* vol, const int32_t* origins, float* dst_qp, int B, int C,
+                     int D, int H, int W, int Dv, int Hv, int Wv, void* stream);
+
+/* ---- weight packing ---------------------------------------------------------------------------
+ * torch parameter layouts -> the K-major no-swizzle shared-memory image the conv kernel streams.
+ *   mode 0: conv forward.  w (Co, C0+C1, kd,kh,kw); K space = [pad8(C0) | pad8(C1)], N space = pad16(Co)
+ *   mode 1: conv dgrad.    K space = pad8(Co); N space = [pad8(C0) | pad8(C1)] padded to 16; taps flipped
+ *   mode 2: transposed conv k=s forward. w (Ci, Co, sd,sh,sw); K = pad8(Ci), N = taps * pad16(Co)
+ *   mode 3: transposed conv dgrad on the space-to-depth gradient: K = taps * pad8(Co), N = pad16(Ci)
+ * `scale` (optional, [Co]) multiplies output channel co (eval-mode BatchNorm folding, mode 0 only).
+ * e3b_packed_weight_floats() returns the size of `dst` in floats. */
+int64_t e3b_packed_weight_floats(int mode, int C0, int C1, int Co, int kd, int kh, int kw);
+int e3b_pack_weights(int mode, const float* w, const float* scale, float* dst, int C0, int C1, int Co,
+                     int kd, int kh, int kw, void* stream);
+
+/* ---- convolution ------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (TF32 multiply, fp32 accumulate).
+ * Replaces nn.Conv3d/Conv2d behind conv3 (models/unet.py:131-149) incl. its dgrad, the virtual
+ * torch.cat((updec, enc), 1) in front of UpConv.conv1 (unet.py:399), and nn.ConvTranspose3d/2d
+ * behind upconv2 (unet.py:152-165, scatter=1). */
+typedef struct e3b_conv_args {
+    const float* src0; int32_t C0;             /* QP source 0 (N, C0, D, H, W) */
+    const float* src1; int32_t C1;             /* optional QP source 1 = channels after source 0 */
+    int32_t N, D, H, W;                        /* extents of source 0 */
+    int32_t D1, H1, W1;                        /* extents of source 1 (>= source 0's) */
+    int32_t off1_d, off1_h, off1_w;            /* autocrop centre-crop offset into source 1 (unet.py:303-324) */
+    int32_t kd, kh, kw;                        /* taps per dim: 1 or 3 */
+    int32_t pd, ph, pw;                        /* zero padding per dim (0..2) */
+    const float* wpk;                          /* e3b_pack_weights image */
+    const float* bias; int32_t n_bias;         /* bias[n_bias] per output channel (columns >= n_bias get 0) or NULL */
+    int32_t n_total;                           /* padded N space (multiple of 16) */
+    float* dst0; int32_t Cd0;                  /* QP output, channels [0, Cd0) */
+    float* dst1; int32_t Cd1;                  /* optional 2nd output: channels after pad8(Cd0) */
+    int32_t relu;                              /* fuse ReLU (eval-mode BN folded into weights) */
+    double* stats; int32_t stats_channels;     /* optional [N][stats_channels][2] sum/sumsq of the output (fp64;
+                                                  zeroed by this call) for the following Group/BatchNorm */
+    int32_t scatter, sd, sh, sw;               /* transposed conv: column = tap*pad16(Cd0)+co -> fine voxel */
+    int32_t Ds, Hs, Ws;                        /* scatter: (cropped) fine output extents (autocrop :294-301) */
+    int32_t force_tz;                          /* 0 = auto; tests only */
+} e3b_conv_args;
+int e3b_conv(const e3b_conv_args* args, void* stream);
+
+/* Weight gradient: dW[tap][ci][co] = sum_voxels x[v + tap - pad][ci] * dy[v][co]  (conv backward-filter
+ * of nn.Conv3d at unet.py:131-149; with taps=1 on (x, space-to-depth dy) also ConvTranspose's).
+ * x = [src0 | src1] (QP, extents D,H,W), dy QP (N, Co, Do,Ho,Wo).  Result is written in torch layout:
+ *   layout 0: dw (Co, C0+C1, kd, kh, kw)        (Conv)
+ *   layout 1: dw (C0, Co/ntap_up, sd, sh, sw) with dy channels = tap*pad8(Co_up)+co  (ConvTranspose)
+ * `workspace` holds split-K partials: e3b_wgrad_workspace_floats() floats. */
+typedef struct e3b_wgrad_args {
+    const float* src0; int32_t C0;
+    const float* src1; int32_t C1;
+    int32_t N, D, H, W;
+    int32_t D1, H1, W1, off1_d, off1_h, off1_w;
+    const float* dy; int32_t Co;
+    int32_t kd, kh, kw, pd, ph, pw;
+    float* dw; int32_t layout; int32_t up_taps; int32_t up_co;
+    float* workspace;
+} e3b_wgrad_args;
+int64_t e3b_wgrad_workspace_floats(const e3b_wgrad_args* args);
+int e3b_wgrad(const e3b_wgrad_args* args, void* stream);
+
+/* ---- normalisation + activation (+ pooling) -----------------------------------------------------
+ * get_normalization (unet.py:77-111) + get_activation 'relu' (:183-186) + MaxPool(ceil_mode) (:225-229).
+ * mode: 0 none, 1 group/instance (G groups), 2 batch (training: batch stats + running update),
+ *       3 batch eval (running stats).
+ * finalize: stats [N][C][2] (from e3b_conv) -> per-(n,c) scale/shift and mean/rstd ([N][pad8(C)]). */
+int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_t S,
+                      const float* gamma, const float* beta, float eps,
+                      float* running_mean, float* running_var, float momentum,
+                      float* scale, float* shift, float* mean, float* rstd, void* stream);
+/* a = relu(y*scale+shift) (QP); if pooled != NULL also pooled = maxpool_{(pk_d,pk_h,pk_w), ceil}(a).
+ * scale/shift NULL = identity; a NULL = only the pooled tensor is written (eval path: y is already
+ * activated by the conv epilogue). */
+int e3b_norm_act(const float* y, const float* scale, const float* shift, float* a, float* pooled,
+                 int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, void* stream);
+
+/* backward of conv -> norm -> relu [-> pool] as autograd derives it:
+ *   dr  = (g0 + g1 + unpool(gp)) * [a > 0]          g0,g1: same extents as a (either may be NULL)
+ *   reduce:   sums[n][c] = (sum dr, sum dr*xhat)                      (fp64 atomics, [N][pad8(C)][2])
+ *   finalize: m1,m2 per (n,c); dgamma, dbeta, dbias (conv bias grad)
+ *   apply:    dy = rstd * (gamma*dr - m1 - xhat*m2)      written QP, or space-to-depth (s2d=1:
+ *             channel = tap*pad8(C)+c on the grid (ceil(D/sd),..)) for the transposed conv backward. */
+typedef struct e3b_norm_bwd_args {
+    const float* a; const float* y;
+    const float* g0; const float* g1; const float* gp;
+    int32_t N, C, D, H, W;
+    int32_t pk_d, pk_h, pk_w;                  /* pooling kernel of gp (if gp) */
+    int32_t mode, G; float eps;
+    const float* gamma; const float* mean; const float* rstd;   /* mean/rstd [N][pad8(C)] */
+    const double* fwd_stats;                   /* [N][C][2] forward sums (for dbias) */
+    double* sums;                              /* [N][pad8(C)][2] */
+    float* m1; float* m2;                      /* [N][pad8(C)] */
+    float* dgamma; float* dbeta; float* dbias; /* [C] each; may be NULL */
+    float* dy; int32_t s2d, sd, sh, sw;        /* output */
+    int32_t relu;
+} e3b_norm_bwd_args;
+int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* args, void* stream);
+int e3b_norm_bwd_finalize(const e3b_norm_bwd_args* args, void* stream);
+int e3b_norm_bwd_apply(const e3b_norm_bwd_args* args, void* stream);
+
+/* ---- 1x1x1 head --------------------------------------------------------------------------------
+ * conv_final (unet.py:881,912) fused with Predictor's Softmax(1) / Argmax (inference.py:443-456,202-212).
+ * out_mode 0: logits float NCDHW; 1: softmax float NCDHW; 2: argmax uint8 (N,1,D,H,W).
+ * Writes only the box [c0, c0+cn) per dim of each sample into a destination of extents (Dd,Hd,Wd) at
+ * origin dst_origin[3*n..] (device int32; NULL = 0): the Predictor's crop-and-place
+ * (inference.py:147-151,188-197).  Destination batch index = dst_n[n] (NULL = n). */
+typedef struct e3b_head_args {
+    const float* a; int32_t N, C, D, H, W;     /* QP input */
+    const float* w; const float* b; int32_t Co;/* torch (Co, C, 1,1,1) */
+    int32_t out_mode;
+    void* dst; int32_t Dd, Hd, Wd;
+    int32_t c0_d, c0_h, c0_w, cn_d, cn_h, cn_w;
+    const int32_t* dst_origin;
+    int32_t dst_single;                        /* 1: all tiles write into sample 0 of dst */
+} e3b_head_args;
+int e3b_head(const e3b_head_args* args, void* stream);
+/* backward: dl NCDHW (N,Co,D,H,W) -> da QP; dw (Co,C), db (Co) via workspace double[Co*(C+1)] (zeroed here) */
+int e3b_head_bwd(const float* dl, const float* a, const float* w, float* da, float* dw, float* db,
+                 double* workspace, int N, int C, int Co, int D, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,400 @@
+"""Per-kernel parity tests of libe3b.so through the C ABI (ctypes) on a B200.
+
+Inputs are small dyadic rationals (k/8), exactly representable in TF32, so that tensor-core products
+are exact and the comparison against a float64 torch evaluation of the same operator is tight: any
+indexing / layout / pipeline bug shows up as an O(1) error instead of hiding under TF32 noise.
+Real-valued inputs (TF32 tolerance) are covered by the golden-vector tests in test_unet_gpu.py.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from elektronn3_b200 import engine
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return engine
+
+
+def dyadic(shape, seed, scale=8, lo=-8, hi=9):
+    rs = np.random.RandomState(seed)
+    return torch.from_numpy(rs.randint(lo, hi, size=shape).astype(np.float32) / scale).cuda()
+
+
+def to_qp_ref(x):
+    """pure-torch NCDHW -> QP (test-side restatement of the layout in csrc/common.cuh)"""
+    N, C, D, H, W = x.shape
+    Cp = (C + 7) & ~7
+    xp = torch.zeros((N, Cp, D, H, W), dtype=x.dtype, device=x.device)
+    xp[:, :C] = x
+    return xp.view(N, Cp // 4, 4, D, H, W).permute(0, 1, 3, 4, 5, 2).contiguous()
+
+
+def from_qp_ref(t, C):
+    N, Cq, D, H, W, _ = t.shape
+    return t.permute(0, 1, 5, 2, 3, 4).reshape(N, Cq * 4, D, H, W)[:, :C].contiguous()
+
+
+def qp(eng, x):
+    N, C, D, H, W = x.shape
+    return eng.QP(to_qp_ref(x), N, C, D, H, W)
+
+
+def assert_close(got, ref, tol, what=''):
+    ref = ref.to(torch.float64)
+    err = (got.to(torch.float64) - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1e-6)
+    assert err / scale < tol, f'{what}: max err {err:.3e} (scale {scale:.3e})'
+
+
+def test_pack_unpack_layout(eng):
+    x = dyadic((2, 5, 3, 6, 7), 0)
+    q = eng.pack_input(x)
+    assert torch.equal(q.t, to_qp_ref(x))
+    assert torch.equal(eng.unpack(q), x)
+    x1 = dyadic((1, 1, 4, 4, 9), 1)
+    assert torch.equal(eng.pack_input(x1).t, to_qp_ref(x1))
+
+
+CONV_CASES = [
+    # N, C0, Co, (D,H,W), k, pad
+    (1, 8, 16, (4, 16, 8), (3, 3, 3), (1, 1, 1)),
+    (1, 8, 16, (4, 16, 8), (1, 1, 1), (0, 0, 0)),
+    (2, 1, 32, (16, 16, 16), (3, 3, 3), (1, 1, 1)),
+    (1, 32, 32, (16, 18, 20), (3, 3, 3), (1, 1, 1)),
+    (1, 64, 64, (8, 16, 16), (3, 3, 3), (1, 1, 1)),
+    (1, 128, 128, (6, 8, 8), (3, 3, 3), (1, 1, 1)),
+    (1, 256, 256, (4, 8, 8), (3, 3, 3), (1, 1, 1)),
+    (1, 16, 24, (5, 32, 32), (1, 3, 3), (0, 1, 1)),       # planar
+    (2, 8, 8, (1, 40, 24), (1, 3, 3), (0, 1, 1)),         # 2D
+    (1, 3, 8, (11, 13, 18), (3, 3, 3), (1, 1, 1)),        # odd extents, ragged channels
+    (1, 8, 8, (12, 20, 20), (3, 3, 3), (0, 0, 0)),        # VALID
+    (1, 40, 48, (6, 10, 10), (3, 3, 3), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=[str(c) for c in CONV_CASES])
+def test_conv_forward_bias_relu_stats(eng, case):
+    N, C0, Co, sp, k, pad = case
+    x = dyadic((N, C0) + sp, 1, scale=4, lo=-4, hi=5)
+    w = dyadic((Co, C0) + k, 2, scale=4, lo=-2, hi=3)
+    b = dyadic((Co,), 3)
+    wpk = eng.pack_weights(0, w, None, C0, 0, Co, k)
+    ref = F.conv3d(x.double(), w.double(), b.double(), padding=pad)
+    y, _, stats = eng.conv_forward(qp(eng, x), wpk, eng.cpad16(Co), Co, k, pad, bias=b, stats_channels=Co)
+    torch.cuda.synchronize()
+    got = from_qp_ref(y.t, Co)
+    assert got.shape == ref.shape
+    assert_close(got, ref, 1e-6, 'conv')
+    # padding channels must be exactly zero
+    Cp = (Co + 7) & ~7
+    if Cp != Co:
+        full = y.t.permute(0, 1, 5, 2, 3, 4).reshape(N, Cp, *ref.shape[2:])
+        assert full[:, Co:].abs().max().item() == 0.0
+    assert_close(stats[:, :, 0], ref.sum(dim=(2, 3, 4)), 1e-6, 'sum')
+    assert_close(stats[:, :, 1], (ref * ref).sum(dim=(2, 3, 4)), 1e-6, 'sumsq')
+    yr, _, _ = eng.conv_forward(qp(eng, x), wpk, eng.cpad16(Co), Co, k, pad, bias=b, relu=True)
+    assert_close(from_qp_ref(yr.t, Co), ref.clamp_min(0), 1e-6, 'conv+relu')
+
+
+@pytest.mark.parametrize('tz', [1, 2, 3, 4])
+def test_conv_forward_tile_depths(eng, tz):
+    N, C0, Co, sp, k, pad = 1, 16, 32, (7, 20, 12), (3, 3, 3), (1, 1, 1)
+    x = dyadic((N, C0) + sp, 5, scale=4, lo=-4, hi=5)
+    w = dyadic((Co, C0) + k, 6, scale=4, lo=-2, hi=3)
+    wpk = eng.pack_weights(0, w, None, C0, 0, Co, k)
+    ref = F.conv3d(x.double(), w.double(), None, padding=pad)
+    y, _, _ = eng.conv_forward(qp(eng, x), wpk, eng.cpad16(Co), Co, k, pad, force_tz=tz)
+    assert_close(from_qp_ref(y.t, Co), ref, 1e-6, f'conv tz={tz}')
+
+
+def test_conv_many_tiles_persistent(eng):
+    """more tiles than SMs: exercises the persistent loop, smem ring wrap-around and TMEM ping-pong"""
+    N, C0, Co, sp = 2, 32, 32, (40, 48, 40)
+    x = dyadic((N, C0) + sp, 7, scale=4, lo=-4, hi=5)
+    w = dyadic((Co, C0, 3, 3, 3), 8, scale=4, lo=-2, hi=3)
+    wpk = eng.pack_weights(0, w, None, C0, 0, Co, (3, 3, 3))
+    ref = F.conv3d(x.double(), w.double(), None, padding=1)
+    y, _, _ = eng.conv_forward(qp(eng, x), wpk, eng.cpad16(Co), Co, (3, 3, 3), (1, 1, 1))
+    assert_close(from_qp_ref(y.t, Co), ref, 1e-6, 'conv persistent')
+
+
+@pytest.mark.parametrize('crop', [(0, 0, 0), (1, 2, 3)])
+def test_conv_virtual_concat(eng, crop):
+    """torch.cat((updec, enc), 1) -> conv (unet.py:399-402) with the skip tensor centre-cropped (autocrop)"""
+    N, C0, C1, Co, sp = 1, 16, 16, 16, (6, 16, 16)
+    x0 = dyadic((N, C0) + sp, 9, scale=4, lo=-4, hi=5)
+    big = tuple(s + 2 * c for s, c in zip(sp, crop))
+    x1 = dyadic((N, C1) + big, 10, scale=4, lo=-4, hi=5)
+    w = dyadic((Co, C0 + C1, 3, 3, 3), 11, scale=4, lo=-2, hi=3)
+    x1c = x1[:, :, crop[0]:crop[0] + sp[0], crop[1]:crop[1] + sp[1], crop[2]:crop[2] + sp[2]]
+    ref = F.conv3d(torch.cat((x0, x1c), 1).double(), w.double(), None, padding=1)
+    wpk = eng.pack_weights(0, w, None, C0, C1, Co, (3, 3, 3))
+    y, _, _ = eng.conv_forward(qp(eng, x0), wpk, eng.cpad16(Co), Co, (3, 3, 3), (1, 1, 1), src1=qp(eng, x1), off1=crop)
+    assert_close(from_qp_ref(y.t, Co), ref, 1e-6, 'concat conv')
+
+
+@pytest.mark.parametrize('case', [(1, 16, 8, (4, 8, 8), (2, 2, 2), None), (2, 32, 16, (3, 8, 16), (1, 2, 2), None),
+                                  (1, 64, 32, (3, 5, 6), (2, 2, 2), (5, 9, 12)), (1, 128, 64, (4, 8, 8), (2, 2, 2), None),
+                                  (1, 8, 3, (2, 8, 8), (2, 2, 2), None)])
+def test_transposed_conv_scatter(eng, case):
+    """ConvTranspose k=s (unet.py:152-165) incl. the autocrop of from_up (unet.py:294-301)"""
+    N, Ci, Co, sp, s, crop_to = case
+    x = dyadic((N, Ci) + sp, 12, scale=4, lo=-4, hi=5)
+    w = dyadic((Ci, Co) + s, 13, scale=4, lo=-2, hi=3)
+    b = dyadic((Co,), 14)
+    ref = F.conv_transpose3d(x.double(), w.double(), b.double(), stride=s)
+    out_sp = tuple(ref.shape[2:]) if crop_to is None else crop_to
+    ref = ref[:, :, :out_sp[0], :out_sp[1], :out_sp[2]]
+    wpk = eng.pack_weights(2, w, None, Ci, 0, Co, s)
+    taps = s[0] * s[1] * s[2]
+    y, _, stats = eng.conv_forward(qp(eng, x), wpk, taps * eng.cpad16(Co), Co, (1, 1, 1), (0, 0, 0), bias=b,
+                                   stats_channels=Co, scatter=s, out_spatial=out_sp)
+    assert_close(from_qp_ref(y.t, Co), ref, 1e-6, 'convT')
+    assert_close(stats[:, :, 0], ref.sum(dim=(2, 3, 4)), 1e-6, 'convT sum')
+    assert_close(stats[:, :, 1], (ref * ref).sum(dim=(2, 3, 4)), 1e-6, 'convT sumsq')
+
+
+@pytest.mark.parametrize('case', [(1, 16, 16, (4, 16, 8), (3, 3, 3), (1, 1, 1)), (2, 32, 64, (5, 10, 12), (3, 3, 3), (1, 1, 1)),
+                                  (1, 8, 24, (3, 16, 16), (1, 3, 3), (0, 1, 1)), (1, 8, 8, (8, 12, 12), (3, 3, 3), (0, 0, 0)),
+                                  (1, 128, 128, (4, 8, 8), (3, 3, 3), (1, 1, 1))])
+def test_conv_dgrad(eng, case):
+    N, C0, Co, sp, k, pad = case
+    x = dyadic((N, C0) + sp, 15, scale=4, lo=-4, hi=5).double().requires_grad_(True)
+    w = dyadic((Co, C0) + k, 16, scale=4, lo=-2, hi=3)
+    y = F.conv3d(x, w.double(), None, padding=pad)
+    dy = dyadic(tuple(y.shape), 17, scale=4, lo=-4, hi=5)
+    y.backward(dy.double())
+    wpk = eng.pack_weights(1, w, None, C0, 0, Co, k)
+    dpad = tuple(kk - 1 - pp for kk, pp in zip(k, pad))
+    dx, _, _ = eng.conv_forward(qp(eng, dy), wpk, eng.cpad16(eng.cpad8(C0)), C0, k, dpad)
+    assert_close(from_qp_ref(dx.t, C0), x.grad, 1e-6, 'dgrad')
+
+
+def test_conv_dgrad_concat_split(eng):
+    N, C0, C1, Co, sp = 1, 16, 24, 32, (4, 16, 8)
+    w = dyadic((Co, C0 + C1, 3, 3, 3), 18, scale=4, lo=-2, hi=3)
+    x = dyadic((N, C0 + C1) + sp, 19, scale=4, lo=-4, hi=5).double().requires_grad_(True)
+    y = F.conv3d(x, w.double(), None, padding=1)
+    dy = dyadic(tuple(y.shape), 20, scale=4, lo=-4, hi=5)
+    y.backward(dy.double())
+    wpk = eng.pack_weights(1, w, None, C0, C1, Co, (3, 3, 3))
+    d0, d1, _ = eng.conv_forward(qp(eng, dy), wpk, eng.cpad16(eng.cpad8(C0) + eng.cpad8(C1)), C0, (3, 3, 3), (1, 1, 1),
+                                 dst1_C=C1)
+    assert_close(from_qp_ref(d0.t, C0), x.grad[:, :C0], 1e-6, 'dgrad split 0')
+    assert_close(from_qp_ref(d1.t, C1), x.grad[:, C0:], 1e-6, 'dgrad split 1')
+
+
+WGRAD_CASES = [
+    (1, 8, 0, 16, (4, 16, 8), (3, 3, 3), (1, 1, 1)),
+    (2, 32, 0, 32, (6, 20, 18), (3, 3, 3), (1, 1, 1)),
+    (1, 1, 0, 32, (8, 16, 16), (3, 3, 3), (1, 1, 1)),
+    (1, 64, 0, 64, (4, 8, 8), (3, 3, 3), (1, 1, 1)),
+    (1, 16, 16, 16, (4, 16, 8), (3, 3, 3), (1, 1, 1)),     # virtual concat
+    (1, 8, 0, 24, (3, 16, 16), (1, 3, 3), (0, 1, 1)),      # planar
+    (1, 8, 0, 8, (8, 12, 12), (3, 3, 3), (0, 0, 0)),       # VALID
+    (1, 160, 0, 16, (3, 8, 8), (3, 3, 3), (1, 1, 1)),      # > 128 input channels: two M chunks
+    (1, 3, 0, 5, (5, 7, 9), (3, 3, 3), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES, ids=[str(c) for c in WGRAD_CASES])
+def test_conv_wgrad(eng, case):
+    N, C0, C1, Co, sp, k, pad = case
+    x = dyadic((N, C0 + C1) + sp, 21, scale=2, lo=-2, hi=3)
+    w = torch.zeros((Co, C0 + C1) + k, dtype=torch.float64, device='cuda', requires_grad=True)
+    y = F.conv3d(x.double(), w, None, padding=pad)
+    dy = dyadic(tuple(y.shape), 22, scale=2, lo=-2, hi=3)
+    y.backward(dy.double())
+    src0 = qp(eng, x[:, :C0].contiguous())
+    src1 = qp(eng, x[:, C0:].contiguous()) if C1 else None
+    dw = eng.wgrad(src0, qp(eng, dy), Co, k, pad, tuple(w.shape), src1=src1)
+    assert_close(dw, w.grad, 1e-6, 'wgrad')
+
+
+@pytest.mark.parametrize('case', [(1, 16, 8, (4, 8, 8), (2, 2, 2)), (2, 32, 16, (3, 8, 16), (1, 2, 2)),
+                                  (1, 64, 32, (2, 8, 8), (2, 2, 2))])
+def test_transposed_conv_backward(eng, case):
+    """dx and dW of ConvTranspose k=s via the space-to-depth gradient"""
+    N, Ci, Co, sp, s = case
+    x = dyadic((N, Ci) + sp, 23, scale=2, lo=-2, hi=3).double().requires_grad_(True)
+    w = dyadic((Ci, Co) + s, 24, scale=2, lo=-2, hi=3).double().requires_grad_(True)
+    y = F.conv_transpose3d(x, w, None, stride=s)
+    dy = dyadic(tuple(y.shape), 25, scale=2, lo=-2, hi=3)
+    y.backward(dy.double())
+    # space-to-depth of dy: channel = tap * pad8(Co) + co on the coarse grid
+    taps = s[0] * s[1] * s[2]
+    Cp = eng.cpad8(Co)
+    D, H, W = sp
+    d = dy.view(N, Co, D, s[0], H, s[1], W, s[2]).permute(0, 3, 5, 7, 1, 2, 4, 6).reshape(N, taps, Co, D, H, W)
+    dpad = torch.zeros((N, taps, Cp, D, H, W), device='cuda')
+    dpad[:, :, :Co] = d
+    dyq = qp(eng, dpad.view(N, taps * Cp, D, H, W))
+    wpk = eng.pack_weights(3, w.detach().float(), None, Ci, 0, Co, s)
+    dx, _, _ = eng.conv_forward(dyq, wpk, eng.cpad16(Ci), Ci, (1, 1, 1), (0, 0, 0))
+    assert_close(from_qp_ref(dx.t, Ci), x.grad, 1e-6, 'convT dgrad')
+    dw = eng.wgrad(qp(eng, x.detach().float()), dyq, taps * Cp, (1, 1, 1), (0, 0, 0), tuple(w.shape), layout=1,
+                   up_taps=taps, up_co=Co)
+    assert_close(dw, w.grad, 1e-6, 'convT wgrad')
+
+
+# ---------------------------------------------------------------------------------------- norm / act / pool
+def _norm_ref(y, mode, G, gamma, beta, rm, rv, eps=1e-5):
+    if mode == 1:
+        return F.group_norm(y, G, gamma, beta, eps)
+    if mode == 2:
+        return F.batch_norm(y, rm, rv, gamma, beta, True, 0.1, eps)
+    return y
+
+
+@pytest.mark.parametrize('mode,G,C,sp,pool', [(1, 8, 32, (6, 8, 10), None), (1, 8, 16, (5, 7, 9), (2, 2, 2)),
+                                              (2, 1, 8, (4, 6, 8), (2, 2, 2)), (2, 1, 24, (3, 9, 8), (1, 2, 2)),
+                                              (0, 1, 8, (4, 6, 8), (2, 2, 2)), (1, 3, 3, (4, 4, 4), None)])
+def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
+    N = 2
+    rs = np.random.RandomState(31)
+    y = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
+    gamma = torch.from_numpy((1 + 0.2 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    beta = torch.from_numpy((0.1 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    rm = torch.zeros(C, device='cuda')
+    rv = torch.ones(C, device='cuda')
+    S = sp[0] * sp[1] * sp[2]
+    yd = y.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rmd, rvd = rm.double().clone(), rv.double().clone()
+    a_ref = F.relu(_norm_ref(yd, mode, G, gd if mode else None, bd if mode else None, rmd, rvd))
+    outs = [a_ref]
+    if pool is not None:
+        outs.append(F.max_pool3d(a_ref, pool, pool, ceil_mode=True))
+    # forward through the kernels
+    yq = qp(eng, y)
+    stats = torch.stack((y.double().sum(dim=(2, 3, 4)), (y.double() ** 2).sum(dim=(2, 3, 4))), dim=-1).contiguous()
+    if mode == 0:
+        a, pooled = eng.norm_act(yq, None, None, pool=pool)
+        nstate = None
+    else:
+        nstate = eng.norm_finalize(stats, mode, G, N, C, S, gamma, beta, 1e-5, rm if mode == 2 else None,
+                                   rv if mode == 2 else None, 0.1, y.device)
+        a, pooled = eng.norm_act(yq, nstate.scale, nstate.shift, pool=pool)
+    assert_close(from_qp_ref(a.t, C), a_ref, 1e-5, 'norm+relu')
+    if pool is not None:
+        assert_close(from_qp_ref(pooled.t, C), outs[1], 1e-5, 'pool')
+    if mode == 2:
+        assert_close(rm, rmd, 1e-5, 'running_mean')
+        assert_close(rv, rvd, 1e-5, 'running_var')
+    # backward: g0 on a, gp on pooled
+    g0 = torch.from_numpy(rs.standard_normal(tuple(a_ref.shape)).astype(np.float32)).cuda()
+    loss = (a_ref * g0.double()).sum()
+    gpq = None
+    if pool is not None:
+        gp = torch.from_numpy(rs.standard_normal(tuple(outs[1].shape)).astype(np.float32)).cuda()
+        loss = loss + (outs[1] * gp.double()).sum()
+        gpq = qp(eng, gp)
+    loss.backward()
+
+    class Spec:
+        pass
+    u = eng.Unit()
+    u.spec = Spec()
+    u.spec.norm = torch.nn.GroupNorm(1, 1) if mode else None
+    if mode:
+        u.spec.norm.weight = torch.nn.Parameter(gamma)
+        u.spec.norm.eps = 1e-5
+    u.a, u.y, u.pool, u.mode, u.G, u.nstate, u.stats = a, yq, pool, mode, G, nstate, (stats if mode else None)
+    dy, dgamma, dbeta, dbias = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq)
+    assert_close(from_qp_ref(dy.t, C), yd.grad, 2e-4, 'norm bwd dy')
+    if mode:
+        assert_close(dgamma, gd.grad, 2e-4, 'dgamma')
+        assert_close(dbeta, bd.grad, 2e-4, 'dbeta')
+    ref_dbias = yd.grad.sum(dim=(0, 2, 3, 4))
+    scale = max(yd.grad.abs().sum(dim=(0, 2, 3, 4)).max().item(), 1e-6)
+    assert (dbias.double() - ref_dbias).abs().max().item() / scale < 1e-4
+
+
+def test_norm_backward_space_to_depth(eng):
+    """norm0/act0 backward of UpConv written tap-major for the transposed conv's dgrad GEMM, cropped fine grid"""
+    N, C, fine, s = 1, 8, (5, 7, 8), (2, 2, 2)
+    rs = np.random.RandomState(5)
+    y = torch.from_numpy(rs.standard_normal((N, C) + fine).astype(np.float32)).cuda()
+    g0 = torch.from_numpy(rs.standard_normal((N, C) + fine).astype(np.float32)).cuda()
+    yd = y.double().requires_grad_(True)
+    a_ref = F.relu(yd)
+    (a_ref * g0.double()).sum().backward()
+    a, _ = eng.norm_act(qp(eng, y), None, None)
+    u = eng.Unit()
+
+    class Spec:
+        norm = None
+    u.spec = Spec()
+    u.a, u.y, u.pool, u.mode, u.G, u.nstate, u.stats = a, a, None, 0, 1, None, None
+    dy, _, _, dbias = eng._norm_bwd(u, C, qp(eng, g0), s2d=s)
+    coarse = tuple(-(-f // k) for f, k in zip(fine, s))
+    full = torch.zeros((N, C) + tuple(c * k for c, k in zip(coarse, s)), dtype=torch.float64, device='cuda')
+    full[:, :, :fine[0], :fine[1], :fine[2]] = yd.grad
+    D, H, W = coarse
+    ref = full.view(N, C, D, 2, H, 2, W, 2).permute(0, 3, 5, 7, 1, 2, 4, 6).reshape(N, 8 * C, D, H, W)
+    assert_close(from_qp_ref(dy.t, 8 * C), ref, 1e-6, 's2d')
+
+
+# ---------------------------------------------------------------------------------------- head
+@pytest.mark.parametrize('C,Co', [(32, 2), (8, 4), (64, 3)])
+def test_head_modes_and_backward(eng, C, Co):
+    N, sp = 2, (5, 6, 7)
+    rs = np.random.RandomState(41)
+    a = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
+    conv = torch.nn.Conv3d(C, Co, 1).cuda()
+    ad = a.double().requires_grad_(True)
+    wd, bd = conv.weight.detach().double().requires_grad_(True), conv.bias.detach().double().requires_grad_(True)
+    ref = F.conv3d(ad, wd, bd)
+    aq = qp(eng, a)
+    assert_close(eng.head(aq, conv, 0), ref, 1e-5, 'logits')
+    assert_close(eng.head(aq, conv, 1), ref.softmax(1), 1e-5, 'softmax')
+    am = eng.head(aq, conv, 2)
+    assert am.dtype == torch.uint8 and am.shape == (N, 1) + sp
+    top2 = ref.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 1e-4
+    assert torch.equal(am[:, 0][decided].long(), ref.argmax(1)[decided])
+    # crop-and-place (inference.py:147-151,188-197)
+    dst = torch.full((1, Co, 9, 9, 9), -1.0, device='cuda')
+    org = torch.tensor([[0, 0, 0], [3, 4, 1]], dtype=torch.int32, device='cuda')
+    eng.head(aq, conv, 0, dst=dst, crop=((1, 1, 2), (3, 4, 4)), dst_origin=org, dst_single=True)
+    assert_close(dst[0, :, 3:6, 4:8, 1:5], ref[1, :, 1:4, 1:5, 2:6], 1e-5, 'placed tile 1')
+    assert_close(dst[0, :, 0:3, 0:4, 0:4], ref[0, :, 1:4, 1:5, 2:6], 1e-5, 'placed tile 0')
+    assert dst[0, :, 6:, :, :].eq(-1).all()
+    # backward
+    dl = torch.from_numpy(rs.standard_normal(tuple(ref.shape)).astype(np.float32)).cuda()
+    ref.backward(dl.double())
+    da = eng.QP.empty(N, C, *sp, a.device)
+    dw = torch.empty((Co, C), device='cuda')
+    db = torch.empty((Co,), device='cuda')
+    ws = torch.empty((Co * eng.cpad8(C) + Co,), dtype=torch.float64, device='cuda')
+    from elektronn3_b200 import _lib as L
+    L.check(L.lib().e3b_head_bwd(dl.data_ptr(), aq.ptr, conv.weight.detach().data_ptr(), da.ptr, dw.data_ptr(),
+                                 db.data_ptr(), ws.data_ptr(), N, C, Co, *sp, torch.cuda.current_stream().cuda_stream))
+    assert_close(from_qp_ref(da.t, C), ad.grad, 1e-5, 'head da')
+    assert_close(dw, wd.grad.view(Co, C), 1e-5, 'head dw')
+    assert_close(db, bd.grad, 1e-5, 'head db')
+
+
+def test_gather_tiles_zero_padding(eng):
+    vol = dyadic((2, 6, 7, 8), 51)
+    org = torch.tensor([[-2, -1, -3], [3, 4, 5], [0, 0, 0]], dtype=torch.int32, device='cuda')
+    q = eng.gather_tiles(vol, org, 3, 2, (5, 6, 7))
+    pad = F.pad(vol, (8, 8, 8, 8, 8, 8))
+    for b, (z, y, x) in enumerate(org.tolist()):
+        ref = pad[:, z + 8:z + 13, y + 8:y + 14, x + 8:x + 15]
+        assert torch.equal(from_qp_ref(q.t[b:b + 1], 2)[0], ref)
+
+
+def test_errors_surface_as_exceptions(eng):
+    x = dyadic((1, 8, 4, 8, 8), 61)
+    w = dyadic((8, 8, 5, 5, 5), 62)
+    with pytest.raises(RuntimeError):
+        eng.conv_forward(qp(eng, x), w.flatten(), 16, 8, (5, 5, 5), (2, 2, 2))
