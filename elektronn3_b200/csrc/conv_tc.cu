@@ -118,8 +118,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                                     (x0 - p.pw) * 4, y0 - p.ph, z0 - p.pd, c * 2, n);
                     else
                         tma_load_5d(a_base + (size_t)sa * p.a_stage_bytes, &tmap1, &a_full[sa],
-                                    (x0 - p.pw + p.off1_w) * 4, y0 - p.ph + p.off1_h, z0 - p.pd + p.off1_d,
-                                    (c - p.chunks0) * 2, n);
+                                    (x0 - p.pw) * 4, y0 - p.ph, z0 - p.pd, (c - p.chunks0) * 2, n);
                     if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
                     for (int g = 0; g < ngroups; g++) {
                         mbar_wait(&b_empty[sb], pb ^ 1);
@@ -314,15 +313,18 @@ static PFN_encodeTiled get_encode()
     return fn;
 }
 
-// QP tensor (N, Cq, D, H, W, 4) viewed as 5D (W*4, H, D, Cq, N); box = (bx*4, by, bz, 2, 1)
-int make_qp_tensor_map(CUtensorMap* map, const float* ptr, int N, int Cq, int D, int H, int W, int bx, int by,
-                       int bz, int bcq)
+// QP tensor (N, Cq, Da, Ha, Wa, 4) viewed as 5D (W*4, H, D, Cq, N); box = (bx*4, by, bz, bcq, 1).
+// (D, H, W) are the extents of the VIEW starting at `ptr` (a centre-cropped skip tensor is a sub-box of
+// its allocation: out-of-view voxels read as 0, exactly like zero padding of the cropped tensor);
+// (Da, Ha, Wa) are the extents of the allocation and give the strides.
+int make_qp_tensor_map(CUtensorMap* map, const float* ptr, int N, int Cq, int D, int H, int W, int Da, int Ha, int Wa,
+                       int bx, int by, int bz, int bcq)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[5] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)Cq, (cuuint64_t)N};
-    cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)W * H * 16, (cuuint64_t)W * H * D * 16,
-                             (cuuint64_t)W * H * D * 16 * Cq};
+    cuuint64_t strides[4] = {(cuuint64_t)Wa * 16, (cuuint64_t)Wa * Ha * 16, (cuuint64_t)Wa * Ha * Da * 16,
+                             (cuuint64_t)Wa * Ha * Da * 16 * Cq};
     cuuint32_t box[5] = {(cuuint32_t)bx * 4, (cuuint32_t)by, (cuuint32_t)bz, (cuuint32_t)bcq, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (box[0] > 256 || box[1] > 256 || box[2] > 256) return set_error("TMA box dimension > 256");
@@ -414,10 +416,12 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
     p.wpk = a->wpk;
 
     CUtensorMap m0, m1;
-    int rc = make_qp_tensor_map(&m0, a->src0, a->N, p.chunks0 * 2, a->D, a->H, a->W, p.HX, p.HY, p.HZ, 2);
+    int rc = make_qp_tensor_map(&m0, a->src0, a->N, p.chunks0 * 2, a->D, a->H, a->W, a->D, a->H, a->W, p.HX, p.HY,
+                                p.HZ, 2);
     if (rc) return rc;
     if (a->src1) {
-        rc = make_qp_tensor_map(&m1, a->src1, a->N, p.chunks1 * 2, a->D1, a->H1, a->W1, p.HX, p.HY, p.HZ, 2);
+        const float* v1 = a->src1 + (((size_t)a->off1_d * a->H1 + a->off1_h) * a->W1 + a->off1_w) * 4;
+        rc = make_qp_tensor_map(&m1, v1, a->N, p.chunks1 * 2, a->D, a->H, a->W, a->D1, a->H1, a->W1, p.HX, p.HY, p.HZ, 2);
         if (rc) return rc;
     } else {
         m1 = m0;

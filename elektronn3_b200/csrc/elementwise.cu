@@ -174,10 +174,57 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, int mode,
 // a = relu(y*scale+shift)  [+ pooled = maxpool(a), kernel (pkd,pkh,pkw), ceil mode]
 // one thread per pooling window (or voxel) per 4-channel plane
 // ------------------------------------------------------------------------------------------------
+// Z-PLANAR (N, D, C, H, Wp) float32 copy of a QP quad (Wp = ceil4(W)): the K-major operand layout of the
+// wgrad kernel (a line of 32 x-voxels of one channel = one 128-byte swizzle row).
+E3B_DEVINL void store_planar(float* __restrict__ pl, const float4& v, int n, int cq, int C, int D, int H, int Wp, int z,
+                             int y, int x)
+{
+    const size_t plane = (size_t)H * Wp;
+    const size_t o = (((size_t)n * D + z) * C + cq * 4) * plane + (size_t)y * Wp + x;
+    const int c = cq * 4;
+    if (c < C) pl[o] = v.x;
+    if (c + 1 < C) pl[o + plane] = v.y;
+    if (c + 2 < C) pl[o + 2 * plane] = v.z;
+    if (c + 3 < C) pl[o + 3 * plane] = v.w;
+}
+
+// The x-shifted gradient copies the wgrad kernel contracts against: (N, D, kw, C, H, Wxp) with
+//   dy3[n][z][dxi][c][y][xs] = dy[n][c][z][y][xs - (dxi - pw)]   (0 outside), xs in [0, Wx), Wx = conv input width.
+// A TMA box cannot start at a voxel offset that is not 16-byte aligned, so the stencil's x shift is
+// materialised here, by the kernel that produces dy anyway (each thread scatters its own value).
+E3B_DEVINL void store_planar_shifted(float* __restrict__ pl, const float4& v, int n, int cq, int C, int D, int H, int W,
+                                     int z, int y, int x, int kw, int pw, int Wx)
+{
+    const int Wxp = (Wx + 3) & ~3;
+    const size_t plane = (size_t)H * Wxp;
+    const int c = cq * 4;
+    for (int dxi = 0; dxi < kw; dxi++) {
+        const int sh = dxi - pw;
+        const size_t base = ((((size_t)n * D + z) * kw + dxi) * C + c) * plane + (size_t)y * Wxp;
+        const int xs = x + sh;
+        if (xs >= 0 && xs < Wx) {
+            if (c < C) pl[base + xs] = v.x;
+            if (c + 1 < C) pl[base + plane + xs] = v.y;
+            if (c + 2 < C) pl[base + 2 * plane + xs] = v.z;
+            if (c + 3 < C) pl[base + 3 * plane + xs] = v.w;
+        }
+        // columns no dy voxel maps to are zero: [0, sh) by the thread at x == 0, [W + sh, Wx) by x == W-1
+        int z0 = 0, z1 = 0;
+        if (x == 0 && sh > 0) { z0 = 0; z1 = sh < Wx ? sh : Wx; }
+        if (z1 > z0) for (int q = z0; q < z1; q++) for (int k = 0; k < 4; k++) if (c + k < C) pl[base + k * plane + q] = 0.f;
+        if (x == W - 1) {
+            int r0 = W + sh; if (r0 < 0) r0 = 0;
+            for (int q = r0; q < Wx; q++) for (int k = 0; k < 4; k++) if (c + k < C) pl[base + k * plane + q] = 0.f;
+        }
+    }
+}
+
 __global__ void norm_act_kernel(const float4* __restrict__ y, const float* __restrict__ scale,
                                 const float* __restrict__ shift, float4* __restrict__ a, float4* __restrict__ pooled,
+                                float* __restrict__ a_pl, float* __restrict__ pooled_pl, int C,
                                 int N, int Cq, int D, int H, int W, int pkd, int pkh, int pkw, int relu)
 {
+    const int Wpl = (W + 3) & ~3;
     const int Dp = (D + pkd - 1) / pkd, Hp = (H + pkh - 1) / pkh, Wp = (W + pkw - 1) / pkw;
     const size_t total = (size_t)N * Cq * Dp * Hp * Wp;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -206,11 +253,13 @@ __global__ void norm_act_kernel(const float4* __restrict__ y, const float* __res
                     v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
                     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                     if (a) a[o] = v;
+                    if (a_pl) store_planar(a_pl, v, n, cq, C, D, H, Wpl, z, yy, x);
                     m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
                 }
             }
         }
         if (pooled) pooled[i] = m;
+        if (pooled_pl) store_planar(pooled_pl, m, n, cq, C, Dp, Hp, (Wp + 3) & ~3, zp, yp, xp);
     }
 }
 
@@ -225,6 +274,8 @@ struct NormBwdDev {
     const float *gamma, *mean, *rstd, *m1, *m2;
     double* sums;
     float4* dy;
+    float* dy_pl;
+    int pl_kw, pl_pw, pl_Wx;
 };
 
 // loads one window, returns dr (masked upstream gradient) and xhat for up to 8 voxels
@@ -411,6 +462,24 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
             o.w = rs.w * (ga.w * dr[j].w - m1.w - xh[j].w * m2.w);
             if (p.s2d) p.dy[(((size_t)n * nslots + slot[j]) * p.Cq + cq) * wins + i] = o;
             else p.dy[offs[j]] = o;
+            if (p.dy_pl) {
+                if (p.s2d) {
+                    // (N, Dw, 1, nslots*Cp, Hw, Wwp): channel = slot*Cp + c on the coarse grid
+                    store_planar(p.dy_pl, o, n, slot[j] * p.Cq + cq, nslots * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
+                } else {
+                    const int sz = slot[j] / (p.wh * p.ww), sy = (slot[j] / p.ww) % p.wh, sx = slot[j] % p.ww;
+                    store_planar_shifted(p.dy_pl, o, n, cq, p.C, p.D, p.H, p.W, zw * p.wd + sz, yw * p.wh + sy,
+                                         xw * p.ww + sx, p.pl_kw, p.pl_pw, p.pl_Wx);
+                }
+            }
+        }
+        if (p.s2d && p.dy_pl) {
+            // fine voxels cropped away by autocrop (absent slots): their planar entries must be 0
+            bool present[8] = {false, false, false, false, false, false, false, false};
+            for (int j = 0; j < cnt; j++) present[slot[j]] = true;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < nslots; s++)
+                if (!present[s]) store_planar(p.dy_pl, z4, n, s * p.Cq + cq, nslots * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
         }
     }
 }
@@ -637,16 +706,17 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
     return check_launch("norm_finalize");
 }
 
-int e3b_norm_act(const float* y, const float* scale, const float* shift, float* a, float* pooled, int N, int C, int D,
-                 int H, int W, int pk_d, int pk_h, int pk_w, int relu, void* stream)
+int e3b_norm_act(const float* y, const float* scale, const float* shift, float* a, float* pooled, float* a_planar,
+                 float* pooled_planar, int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu,
+                 void* stream)
 {
-    if (!pooled) { pk_d = pk_h = pk_w = 1; }
+    if (!pooled && !pooled_planar) { pk_d = pk_h = pk_w = 1; }
     if (pk_d * pk_h * pk_w > 8) return set_error("norm_act: pooling window > 8 voxels");
     const int Cq = cpad8(C) / 4;
     const size_t total = (size_t)N * Cq * ((D + pk_d - 1) / pk_d) * ((H + pk_h - 1) / pk_h) * ((W + pk_w - 1) / pk_w);
     norm_act_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(pooled), N,
-        Cq, D, H, W, pk_d, pk_h, pk_w, relu);
+        reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(pooled),
+        a_planar, pooled_planar, C, N, Cq, D, H, W, pk_d, pk_h, pk_w, relu);
     return check_launch("norm_act");
 }
 
@@ -665,7 +735,8 @@ static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)
     p.relu = a->relu; p.s2d = a->s2d;
     p.gamma = (a->mode == 0) ? nullptr : a->gamma;
     p.mean = a->mean; p.rstd = a->rstd; p.m1 = a->m1; p.m2 = a->m2;
-    p.sums = a->sums; p.dy = reinterpret_cast<float4*>(a->dy);
+    p.sums = a->sums; p.dy = reinterpret_cast<float4*>(a->dy); p.dy_pl = a->dy_planar;
+    p.pl_kw = a->planar_kw > 0 ? a->planar_kw : 1; p.pl_pw = a->planar_pw; p.pl_Wx = a->planar_W > 0 ? a->planar_W : a->W;
     return 0;
 }
 

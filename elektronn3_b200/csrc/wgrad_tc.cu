@@ -5,84 +5,102 @@
 // (the backward-filter of nn.Conv3d at elektronn3 models/unet.py:131-149; with one tap on
 // (x, space-to-depth(dy)) also nn.ConvTranspose3d's, unet.py:152-165).
 //
-// GEMM view: M = input channels (128 TMEM lanes per CTA), N = output channels, K = voxels.  Both
-// operands are read straight from QP tiles as MN-major no-swizzle UMMA operands: 8 consecutive
-// x-voxels of a 4-channel plane are exactly one canonical core matrix with K (voxels) 16 bytes apart,
-// so one tf32 MMA (K = 8) consumes one 8-voxel row, and the (kh,kw) stencil taps are the same x halo
-// tile read through shifted descriptor start addresses.  Each tap owns its own TMEM accumulator
-// (TG taps x N columns <= 512).  The contraction over voxels is split over CTAs (split-K); partials go
-// to a workspace and a deterministic second kernel reduces them into the torch weight layout.
+// GEMM view: M = input channels, N = output channels, K = voxels.  kind::tf32 accepts MN-major operands
+// only in the SW128_32B layout, so both operands are read K-major from Z-PLANAR copies of the tensors
+// (N, D, C, H, Wp) float32, Wp = ceil4(W): a TMA box of 32 consecutive x-voxels x CB channels x rows lands
+// in shared memory as the canonical 128-byte-swizzled K-major tile (one 128 B line = 32 voxels of one
+// channel; 8 channels = one 1024 B swizzle atom).
+//  * the (kw) x-shifts of the stencil cannot be TMA coordinates (a box must start 16-byte aligned: a
+//    1-voxel shift of a 4-byte element is an illegal instruction) nor descriptor offsets, so the kernel
+//    that produces dy also writes it as kw x-shifted copies (N, D, kw, Co, H, Wp); the copies are stacked
+//    in the MMA's N dimension: one MMA of N = kw*NTW columns serves all x taps;
+//  * the (kh) y-shifts are STACKED IN M: a stage holds the rows [y][c][32 vox] contiguously, so an
+//    M = 128 operand starting at row r covers rows r .. r+RS-1 (RS = 128 / CB, CB = 8/16/32 channels per
+//    unit): accumulator rows [j*CB, (j+1)*CB) are tap dy = j.  With CB = 32 one MMA serves all three dy
+//    taps (75 % of the M rows useful instead of 25 %);
+//  * the (kd) z-shifts pair the x plane z with dy planes z+pd-kd: either all inside one CTA (narrow N)
+//    or split over CTAs;
+//  * every (kd, dx) tap pair owns a TMEM accumulator (columns <= 512); the contraction over voxels is
+//    split over CTAs (split-K), partials go to a workspace and a deterministic second kernel reduces
+//    them into the torch weight layout.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace e3b {
 
 static constexpr int kWgThreads = 192;
+static constexpr int kSeg = 32;              // voxels per 128-byte line
 
 struct WgradParams {
-    int N, D, H, W;              // x extents
+    int N, D, H, W;              // x extents (source 0 / the cropped view of source 1)
+    int D1;                      // planes per sample in the allocation of source 1
     int Do, Ho, Wo;              // dy extents
     int kd, kh, kw, pd, ph, pw;
     int off1_d, off1_h, off1_w;
-    int TYW, HX, HYW;            // rows per stage, halo extents
+    int CB, RS;                  // channels per M unit, rows stacked in M
+    int TY, TYA, rows_alloc;     // dy rows per stage, x rows loaded, x rows addressed by the MMAs
     int tiles_x, tiles_y, total_vt;
-    int cq0, cq1;                // planes in source 0 / 1
-    int mchunks0, mchunks;       // 128-channel M chunks in source 0 / total
+    int mchunks0, mchunks;       // CB-channel chunks in source 0 / total
     int NTW, nchunks_n;          // N columns per CTA, number of N chunks
-    int TG, nsub;                // taps per CTA (of the kh*kw in-plane taps), subgroups
-    int units, S;                // work units, split-K factor
-    int stages;
-    uint32_t a_plane, a_region, b_plane, b_bytes, stage_bytes;
-    int box_planes0, box_planes1, box_planes_dy;   // planes actually moved by each TMA box
-    int kpad_total, npad_total;  // padded K (= Cin) and N (= Cout) spaces
-    float* part;                 // [S][ntaps][kpad_total][npad_total]
+    int kdn, kd_units;           // kd taps per CTA, CTAs along kd
+    int units, S, stages;
+    uint32_t a_load_bytes, a_bytes, b_plane_bytes, b_bytes, stage_bytes;
+    int ktot, npad_total;        // partial-sum row / column space
+    float* part;                 // [S][ntaps][ktot][npad_total]
 };
 
-struct WgUnit { int kdi, sg, mc, nc; };
+struct WgUnit { int ku, mc, nc; };
 
 E3B_DEVINL WgUnit decode_unit(const WgradParams& p, int u) {
     WgUnit r;
     r.nc = u % p.nchunks_n; u /= p.nchunks_n;
     r.mc = u % p.mchunks; u /= p.mchunks;
-    r.sg = u % p.nsub; u /= p.nsub;
-    r.kdi = u;
+    r.ku = u;
     return r;
 }
 
-E3B_DEVINL bool decode_vt(const WgradParams& p, int vt, int kdi, int& n, int& z, int& y0, int& x0, int& zi) {
+E3B_DEVINL void decode_vt(const WgradParams& p, int vt, int& n, int& zi, int& y0, int& x0) {
     int xt = vt % p.tiles_x; vt /= p.tiles_x;
     int yt = vt % p.tiles_y; vt /= p.tiles_y;
-    z = vt % p.Do;
-    n = vt / p.Do;
-    x0 = xt * 8; y0 = yt * p.TYW;
-    zi = z + kdi - p.pd;
-    return zi >= 0 && zi < p.D;
+    zi = vt % p.D;
+    n = vt / p.D;
+    x0 = xt * kSeg; y0 = yt * p.TY;
+}
+
+// K-major, 128-byte swizzle: 8-row groups 1024 B apart; the K advance inside a line is added to the start
+// address (tiles are 1024 B aligned, so the swizzle phase bits [7,10) are untouched by offsets < 128 B).
+E3B_DEVINL uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                       // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // SBO
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmx1,
                 const __grid_constant__ CUtensorMap tmdy, const WgradParams p)
 {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128 B swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + p.stages;
     uint64_t* done = empty + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    volatile uint32_t* started_slot = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int unit = blockIdx.x / p.S, split = blockIdx.x % p.S;
     const WgUnit u = decode_unit(p, unit);
     const bool src1 = u.mc >= p.mchunks0;
     const int mc_local = src1 ? u.mc - p.mchunks0 : u.mc;
-    const int cq_src = src1 ? p.cq1 : p.cq0;
-    int planes = cq_src - mc_local * 32; if (planes > 32) planes = 32;   // real planes in this M chunk
-    const uint32_t a_bytes = (uint32_t)(src1 ? p.box_planes1 : p.box_planes0) * p.a_plane;
-    const uint32_t b_tx = (uint32_t)p.box_planes_dy * p.b_plane;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(done, 1);
+        mbar_init(done, 2);                      // tcgen05.commit + the issuer's own (releasing) arrive
         fence_barrier_init();
         tma_prefetch_desc(src1 ? &tmx1 : &tmx0);
         tma_prefetch_desc(&tmdy);
@@ -96,79 +114,99 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {
             uint32_t st = 0, ph = 0;
+            const CUtensorMap* mx = src1 ? &tmx1 : &tmx0;
+            const int ox = src1 ? p.off1_w : 0, oy = src1 ? p.off1_h : 0, oz = src1 ? p.off1_d : 0;
+            const int Dsrc = src1 ? p.D1 : p.D;      // planes per sample in the source's allocation
             for (int vt = split; vt < p.total_vt; vt += p.S) {
-                int n, z, y0, x0, zi;
-                if (!decode_vt(p, vt, u.kdi, n, z, y0, x0, zi)) continue;
+                int n, zi, y0, x0;
+                decode_vt(p, vt, n, zi, y0, x0);
                 mbar_wait(&empty[st], ph ^ 1);
                 uint8_t* sA = smem + (size_t)st * p.stage_bytes;
-                uint8_t* sB = sA + p.a_region;
-                mbar_arrive_expect_tx(&full[st], a_bytes + b_tx);
-                if (!src1)
-                    tma_load_5d(sA, &tmx0, &full[st], (x0 - p.pw) * 4, y0 - p.ph, zi, mc_local * 32, n);
-                else
-                    tma_load_5d(sA, &tmx1, &full[st], (x0 - p.pw + p.off1_w) * 4, y0 - p.ph + p.off1_h,
-                                zi + p.off1_d, mc_local * 32, n);
-                tma_load_5d(sB, &tmdy, &full[st], x0 * 4, y0, z, u.nc * (p.NTW / 4), n);
+                uint8_t* sB = sA + p.a_bytes;
+                int nb = 0;
+                for (int kj = 0; kj < p.kdn; kj++) {
+                    const int z = zi + p.pd - (u.ku * p.kdn + kj);
+                    nb += (z >= 0 && z < p.Do);
+                }
+                mbar_arrive_expect_tx(&full[st], p.a_load_bytes + (uint32_t)nb * p.b_plane_bytes);
+                // x: dims (x, c, y, n*D + z)
+                tma_load_4d(sA, mx, &full[st], x0 + ox, mc_local * p.CB, y0 - p.ph + oy, n * Dsrc + zi + oz);
+                for (int kj = 0; kj < p.kdn; kj++) {
+                    const int z = zi + p.pd - (u.ku * p.kdn + kj);
+                    // dy: dims (x, co, dxi, y, n*Do + z); planes outside the gradient are skipped, not loaded
+                    if (z >= 0 && z < p.Do)
+                        tma_load_5d(sB + (size_t)kj * p.b_plane_bytes, &tmdy, &full[st], x0, u.nc * p.NTW, 0, y0,
+                                    n * p.Do + z);
+                }
                 if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(p.NTW, 1, 1);
+            const uint32_t idesc = umma_idesc_tf32(p.kw * p.NTW, 0, 0);
             uint32_t st = 0, ph = 0;
-            bool first = true;
+            uint32_t started = 0;                        // bit kj: accumulator kj has been written once
+            const uint32_t a_row = (uint32_t)p.CB * 128u, b_row = (uint32_t)(p.kw * p.NTW) * 128u;
             for (int vt = split; vt < p.total_vt; vt += p.S) {
-                int n, z, y0, x0, zi;
-                if (!decode_vt(p, vt, u.kdi, n, z, y0, x0, zi)) continue;
+                int n, zi, y0, x0;
+                decode_vt(p, vt, n, zi, y0, x0);
                 mbar_wait(&full[st], ph);
                 tc_fence_after();
                 const uint32_t sA = smem_u32(smem + (size_t)st * p.stage_bytes);
-                const uint32_t sB = sA + p.a_region;
-                for (int tg = 0; tg < p.TG; tg++) {
-                    const int tap2 = u.sg * p.TG + tg;          // in-plane tap index
-                    const int dy = tap2 / p.kw, dx = tap2 % p.kw;
-                    for (int yy = 0; yy < p.TYW; yy++) {
-                        const uint64_t ad = umma_desc(sA + (uint32_t)((yy + dy) * p.HX + dx) * 16u, 128, p.a_plane);
-                        const uint64_t bd = umma_desc(sB + (uint32_t)(yy * 8) * 16u, 128, p.b_plane);
-                        umma_tf32(tmem_base + (uint32_t)(tg * p.NTW), ad, bd, idesc, (first && yy == 0) ? 0u : 1u);
+                const uint32_t sB = sA + p.a_bytes;
+                for (int kj = 0; kj < p.kdn; kj++) {
+                    const int z = zi + p.pd - (u.ku * p.kdn + kj);
+                    if (z < 0 || z >= p.Do) continue;
+                    const uint32_t acc = tmem_base + (uint32_t)(kj * p.kw * p.NTW);
+                    const uint32_t b0 = sB + (uint32_t)kj * p.b_plane_bytes;
+                    for (int yy = 0; yy < p.TY; yy++) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint32_t accum = ((started >> kj) & 1u) | (uint32_t)(yy | ks);
+                            umma_tf32(acc, umma_desc_sw128(sA + (uint32_t)yy * a_row + ks * 32u),
+                                      umma_desc_sw128(b0 + (uint32_t)yy * b_row + ks * 32u), idesc, accum ? 1u : 0u);
+                        }
                     }
+                    started |= 1u << kj;
                 }
-                first = false;
                 umma_commit(&empty[st]);
                 if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
             }
+            // accumulators that never received a plane (tiny volumes) are reported to the epilogue as empty
+            *started_slot = started;
+            mbar_arrive(done);
             umma_commit(done);
         }
     } else {
-        // epilogue: TMEM -> split-K partial
-        bool any = false;
-        for (int vt = split; vt < p.total_vt && !any; vt += p.S) {
-            int n, z, y0, x0, zi;
-            any = decode_vt(p, vt, u.kdi, n, z, y0, x0, zi);
-        }
+        // epilogue: TMEM -> split-K partial.  Accumulator row r = j*CB + c  <->  tap dy = j, channel c.
         mbar_wait(done, 0);
         tc_fence_after();
+        const uint32_t started = *started_slot;
         const int q = warp & 3;
-        const int row = q * 32 + lane;                       // M row = channel inside the chunk
+        const int row = q * 32 + lane;
+        const int j = row / p.CB, c = row % p.CB;
         const int ntaps = p.kd * p.kh * p.kw;
-        const int kbase = (src1 ? p.cq0 * 4 : 0) + mc_local * 128;
-        const bool row_ok = row < planes * 4;
-        for (int tg = 0; tg < p.TG; tg++) {
-            const int tap = u.kdi * (p.kh * p.kw) + u.sg * p.TG + tg;
-            for (int cb = 0; cb < p.NTW; cb += 16) {
-                float v[16];
-                if (any) {
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tg * p.NTW + cb), v);
-                } else {
+        const bool row_ok = j < p.kh;
+        for (int kj = 0; kj < p.kdn; kj++) {
+            const int kdi = u.ku * p.kdn + kj;
+            const bool any = (started >> kj) & 1u;
+            for (int dxi = 0; dxi < p.kw; dxi++) {
+                const int tap = (kdi * p.kh + j) * p.kw + dxi;
+                for (int cb = 0; cb < p.NTW; cb += 16) {
+                    float v[16];
+                    if (any) {
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kj * p.kw + dxi) * p.NTW + cb), v);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] = 0.f;
-                }
-                if (row_ok) {
-                    float* o = p.part + (((size_t)split * ntaps + tap) * p.kpad_total + kbase + row) * p.npad_total +
-                               u.nc * p.NTW + cb;
+                        for (int i = 0; i < 16; i++) v[i] = 0.f;
+                    }
+                    if (row_ok) {
+                        float* o = p.part + (((size_t)split * ntaps + tap) * p.ktot + (size_t)u.mc * p.CB + c) * p.npad_total +
+                                   u.nc * p.NTW + cb;
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; j4++)
-                        reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                        for (int j4 = 0; j4 < 4; j4++)
+                            reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                    }
                 }
             }
         }
@@ -179,82 +217,128 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
 }
 
 // deterministic split-K reduction + scatter into the torch parameter layout
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int S, int ntaps,
-                                    int kpad_total, int npad_total, int C0, int C0pad, int C1, int Co, int layout,
-                                    int up_taps, int up_co, int up_copad)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int S, int ntaps, int ktot,
+                                    int npad_total, int CB, int mchunks0, int C0, int C1, int Co, int layout, int up_taps,
+                                    int up_co, int up_copad)
 {
-    const size_t total = (size_t)ntaps * kpad_total * npad_total;
+    const size_t total = (size_t)ntaps * ktot * npad_total;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int nn = (int)(i % npad_total);
-        const int kk = (int)((i / npad_total) % kpad_total);
-        const int tap = (int)(i / ((size_t)npad_total * kpad_total));
+        const int kk = (int)((i / npad_total) % ktot);
+        const int tap = (int)(i / ((size_t)npad_total * ktot));
         int ci;
-        if (kk < C0pad) { if (kk >= C0) continue; ci = kk; }
-        else { if (kk - C0pad >= C1) continue; ci = C0 + kk - C0pad; }
+        if (kk < mchunks0 * CB) { if (kk >= C0) continue; ci = kk; }
+        else { const int k1 = kk - mchunks0 * CB; if (k1 >= C1) continue; ci = C0 + k1; }
+        if (layout == 0) { if (nn >= Co) continue; }
+        else { if (nn / up_copad >= up_taps || nn % up_copad >= up_co) continue; }
         float s = 0.f;
         for (int sp = 0; sp < S; sp++) s += part[(size_t)sp * total + i];
-        if (layout == 0) {
-            if (nn >= Co) continue;
-            dw[((size_t)nn * (C0 + C1) + ci) * ntaps + tap] = s;
-        } else {
-            const int t = nn / up_copad, co = nn % up_copad;
-            if (t >= up_taps || co >= up_co) continue;
-            dw[((size_t)ci * up_co + co) * up_taps + t] = s;
-        }
+        if (layout == 0) dw[((size_t)nn * (C0 + C1) + ci) * ntaps + tap] = s;
+        else dw[((size_t)ci * up_co + nn % up_copad) * up_taps + nn / up_copad] = s;
     }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_enc()
+{
+    static PFN_encodeTiled enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        enc = reinterpret_cast<PFN_encodeTiled>(fp);
+    }
+    return enc;
+}
+
+// z-planar activation (N, D, C, H, Wp) viewed as 4D (x: W, c: C, y: H, zn: N*D); box (32, bc, by, 1), 128 B swizzle
+static int make_x_map(CUtensorMap* map, const float* ptr, int N, int C, int D, int H, int W, int bc, int by)
+{
+    PFN_encodeTiled enc = get_enc();
+    if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t Wp = (cuuint64_t)((W + 3) & ~3);
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)N * D};
+    cuuint64_t strides[3] = {(cuuint64_t)H * Wp * 4, Wp * 4, (cuuint64_t)C * H * Wp * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kSeg, (cuuint32_t)bc, (cuuint32_t)by, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (box[1] > 256 || box[2] > 256) return set_error("wgrad: TMA box dimension > 256");
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+    return 0;
+}
+
+// shifted gradient copies (N, Do, kw, Co, Ho, Wxp) viewed as 5D (x: Wx, co: Co, dxi: kw, y: Ho, zn: N*Do);
+// box (32, NTW, kw, TY, 1)
+static int make_dy_map(CUtensorMap* map, const float* ptr, int N, int Co, int kw, int Do, int Ho, int Wx, int bn, int by)
+{
+    PFN_encodeTiled enc = get_enc();
+    if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t Wp = (cuuint64_t)((Wx + 3) & ~3);
+    cuuint64_t dims[5] = {(cuuint64_t)Wx, (cuuint64_t)Co, (cuuint64_t)kw, (cuuint64_t)Ho, (cuuint64_t)N * Do};
+    cuuint64_t strides[4] = {(cuuint64_t)Ho * Wp * 4, (cuuint64_t)Co * Ho * Wp * 4, Wp * 4, (cuuint64_t)kw * Co * Ho * Wp * 4};
+    cuuint32_t box[5] = {(cuuint32_t)kSeg, (cuuint32_t)bn, (cuuint32_t)kw, (cuuint32_t)by, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (box[1] > 256 || box[3] > 256) return set_error("wgrad: TMA box dimension > 256");
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("wgrad: cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
+    return 0;
 }
 
 static int plan_wgrad(const e3b_wgrad_args* a, WgradParams& p)
 {
     memset(&p, 0, sizeof(p));
     p.N = a->N; p.D = a->D; p.H = a->H; p.W = a->W;
+    p.D1 = a->D1;
     p.kd = a->kd; p.kh = a->kh; p.kw = a->kw; p.pd = a->pd; p.ph = a->ph; p.pw = a->pw;
     p.Do = a->D + 2 * a->pd - a->kd + 1; p.Ho = a->H + 2 * a->ph - a->kh + 1; p.Wo = a->W + 2 * a->pw - a->kw + 1;
+    if (p.Do <= 0 || p.Ho <= 0 || p.Wo <= 0) return set_error("wgrad: empty output");
     p.off1_d = a->off1_d; p.off1_h = a->off1_h; p.off1_w = a->off1_w;
-    p.cq0 = cpad8(a->C0) / 4;
-    p.cq1 = a->src1 ? cpad8(a->C1) / 4 : 0;
-    p.mchunks0 = (p.cq0 + 31) / 32;
-    p.mchunks = p.mchunks0 + (p.cq1 + 31) / 32;
-    p.kpad_total = (p.cq0 + p.cq1) * 4;
-    const int copad8 = cpad8(a->Co);          // dy tensor planes
-    p.npad_total = cpad16(a->Co);
-    p.NTW = conv_ntile_width(p.npad_total);
-    if (p.NTW <= 0) return set_error("wgrad: unsupported output width %d", p.npad_total);
-    (void)copad8;
-    p.nchunks_n = p.npad_total / p.NTW;
-    const int inplane = a->kh * a->kw;
-    int tg = inplane;
-    while (tg > 1 && tg * p.NTW > 512) tg /= 3;
-    if (tg * p.NTW > 512) return set_error("wgrad: N tile too wide");
-    p.TG = tg; p.nsub = inplane / tg;
-    p.units = a->kd * p.nsub * p.mchunks * p.nchunks_n;
-    p.HX = 8 + a->kw - 1;
-    const size_t budget = 227 * 1024 - 1024 - 256;
-    int tyw = 16;
-    for (;; tyw >>= 1) {
-        p.TYW = tyw; p.HYW = tyw + a->kh - 1;
-        p.a_plane = (uint32_t)(p.HX * p.HYW * 16);
-        p.a_region = 32u * p.a_plane;
-        p.b_plane = (uint32_t)(8 * tyw * 16);
-        p.b_bytes = p.b_plane * (uint32_t)(p.NTW / 4);
-        p.stage_bytes = p.a_region + p.b_bytes;
-        int st = (int)(budget / p.stage_bytes);
-        if (st >= 3 || (st >= 2 && tyw == 1)) { p.stages = st > 4 ? 4 : st; break; }
-        if (tyw == 1) return set_error("wgrad: stage does not fit shared memory");
+    const int C1 = a->src1 ? a->C1 : 0;
+    const int cmax = a->C0 > C1 ? a->C0 : C1;
+    p.CB = cmax > 16 ? 32 : (cmax > 8 ? 16 : 8);
+    p.RS = 128 / p.CB;
+    p.mchunks0 = (a->C0 + p.CB - 1) / p.CB;
+    p.mchunks = p.mchunks0 + (C1 + p.CB - 1) / p.CB;
+    p.ktot = p.mchunks * p.CB;
+    // N columns per CTA: one MMA covers the kw shifted copies, N = kw*NTW <= 256
+    const int npad = cpad16(a->Co);
+    const int ntw_max = a->kw == 1 ? 128 : 80;
+    p.NTW = npad <= ntw_max ? npad : (npad % 64 == 0 ? 64 : (npad % 48 == 0 ? 48 : 32));
+    p.nchunks_n = (npad + p.NTW - 1) / p.NTW;
+    p.npad_total = p.nchunks_n * p.NTW;
+    p.kdn = (a->kd * a->kw * p.NTW <= 512) ? a->kd : 1;
+    p.kd_units = a->kd / p.kdn;
+    p.units = p.kd_units * p.mchunks * p.nchunks_n;
+    const size_t budget = 227 * 1024 - 2048 - 256;
+    int ty = 8;
+    for (;; ty >>= 1) {
+        p.TY = ty; p.TYA = ty + a->kh - 1; p.rows_alloc = ty + p.RS - 1;
+        if (p.rows_alloc < p.TYA) p.rows_alloc = p.TYA;
+        p.a_load_bytes = (uint32_t)(p.TYA * p.CB * 128);
+        p.a_bytes = (uint32_t)(p.rows_alloc * p.CB * 128);
+        p.b_plane_bytes = (uint32_t)(ty * a->kw * p.NTW * 128);
+        p.b_bytes = (uint32_t)p.kdn * p.b_plane_bytes;
+        p.stage_bytes = p.a_bytes + p.b_bytes;
+        const int st = (int)(budget / p.stage_bytes);
+        const bool small_enough = ty == 1 || ty / 2 < p.Ho;      // do not carry rows a small volume does not have
+        if (st >= 2 && small_enough) { p.stages = st > 4 ? 4 : st; break; }
+        if (ty == 1) {
+            if (st >= 1) { p.stages = 1; break; }
+            return set_error("wgrad: stage does not fit shared memory");
+        }
     }
-    while (p.TYW > 1 && p.TYW / 2 >= p.Ho) { p.TYW >>= 1; }   // do not carry rows a small volume does not have
-    if (p.TYW != tyw) {
-        p.HYW = p.TYW + a->kh - 1;
-        p.a_plane = (uint32_t)(p.HX * p.HYW * 16); p.a_region = 32u * p.a_plane;
-        p.b_plane = (uint32_t)(8 * p.TYW * 16); p.b_bytes = p.b_plane * (uint32_t)(p.NTW / 4);
-        p.stage_bytes = p.a_region + p.b_bytes;
-        int st = (int)(budget / p.stage_bytes); p.stages = st > 4 ? 4 : st;
-    }
-    p.box_planes0 = p.cq0 < 32 ? p.cq0 : 32;
-    p.box_planes1 = p.cq1 < 32 ? p.cq1 : 32;
-    { const int cqdy = cpad8(a->Co) / 4; p.box_planes_dy = cqdy < p.NTW / 4 ? cqdy : p.NTW / 4; }
-    p.tiles_x = (p.Wo + 7) / 8; p.tiles_y = (p.Ho + p.TYW - 1) / p.TYW;
-    p.total_vt = p.tiles_x * p.tiles_y * p.Do * a->N;
+    // tiles cover the conv INPUT width (the shifted gradient copies are indexed by the input x)
+    p.tiles_x = (a->W + kSeg - 1) / kSeg; p.tiles_y = (p.Ho + p.TY - 1) / p.TY;
+    p.total_vt = p.tiles_x * p.tiles_y * p.D * a->N;
     int S = (2 * num_sms()) / p.units; if (S < 1) S = 1;
     if (S > p.total_vt) S = p.total_vt;
     if (S > 64) S = 64;
@@ -266,7 +350,7 @@ int64_t wgrad_workspace_floats(const e3b_wgrad_args* a)
 {
     WgradParams p;
     if (plan_wgrad(a, p)) return -1;
-    return (int64_t)p.S * a->kd * a->kh * a->kw * p.kpad_total * p.npad_total;
+    return (int64_t)p.S * a->kd * a->kh * a->kw * p.ktot * p.npad_total;
 }
 
 int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
@@ -276,15 +360,18 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     if (rc) return rc;
     p.part = a->workspace;
     CUtensorMap mx0, mx1, mdy;
-    rc = make_qp_tensor_map(&mx0, a->src0, a->N, p.cq0, a->D, a->H, a->W, p.HX, p.HYW, 1, p.box_planes0);
+    rc = make_x_map(&mx0, a->src0, a->N, a->C0, a->D, a->H, a->W, p.CB, p.TYA);
     if (rc) return rc;
     if (a->src1) {
-        rc = make_qp_tensor_map(&mx1, a->src1, a->N, p.cq1, a->D1, a->H1, a->W1, p.HX, p.HYW, 1, p.box_planes1);
+        if ((a->off1_d | a->off1_h | a->off1_w) && (a->pd | a->ph | a->pw))
+            return set_error("wgrad: a centre-cropped second source requires zero padding (VALID convolution)");
+        if (a->off1_w & 3) return set_error("wgrad: the x crop offset of the second source must be a multiple of 4");
+        rc = make_x_map(&mx1, a->src1, a->N, a->C1, a->D1, a->H1, a->W1, p.CB, p.TYA);
         if (rc) return rc;
     } else mx1 = mx0;
-    rc = make_qp_tensor_map(&mdy, a->dy, a->N, cpad8(a->Co) / 4, p.Do, p.Ho, p.Wo, 8, p.TYW, 1, p.box_planes_dy);
+    rc = make_dy_map(&mdy, a->dy, a->N, a->Co, a->kw, p.Do, p.Ho, a->W, p.NTW, p.TY);
     if (rc) return rc;
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -295,11 +382,11 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     rc = check_launch("wgrad_tc");
     if (rc) return rc;
     const int ntaps = a->kd * a->kh * a->kw;
-    const size_t total = (size_t)ntaps * p.kpad_total * p.npad_total;
+    const size_t total = (size_t)ntaps * p.ktot * p.npad_total;
     int blocks = (int)((total + 255) / 256); if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.part, a->dw, p.S, ntaps, p.kpad_total, p.npad_total, a->C0,
-                                                    cpad8(a->C0), a->src1 ? a->C1 : 0, a->Co, a->layout, a->up_taps,
-                                                    a->up_co, cpad8(a->up_co));
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.part, a->dw, p.S, ntaps, p.ktot, p.npad_total, p.CB, p.mchunks0,
+                                                    a->C0, a->src1 ? a->C1 : 0, a->Co, a->layout, a->up_taps, a->up_co,
+                                                    cpad8(a->up_co));
     return check_launch("wgrad_reduce");
 }
 

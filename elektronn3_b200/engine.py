@@ -32,12 +32,28 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-class QP:
-    """A float32 activation tensor in quad-planar layout."""
-    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W')
+def planar_empty(N, C, D, H, W, device, kw=None):
+    """Z-PLANAR layout of the wgrad operands: float32 (N, D, C, H, ceil4(W)); with kw: the x-shifted
+    gradient copies (N, D, kw, C, H, ceil4(W)) (include/e3b.h)"""
+    shape = (N, D, C, H, (W + 3) & ~3) if kw is None else (N, D, kw, C, H, (W + 3) & ~3)
+    return torch.empty(shape, dtype=torch.float32, device=device)
 
-    def __init__(self, t, N, C, D, H, W):
-        self.t, self.N, self.C, self.D, self.H, self.W = t, N, C, D, H, W
+
+def planar_from_ncdhw(x5):
+    """NCDHW -> z-planar (a view when C == 1 and W % 4 == 0, e.g. the network input)"""
+    W = x5.shape[-1]
+    t = x5.permute(0, 2, 1, 3, 4)
+    if W % 4:
+        t = torch.nn.functional.pad(t, (0, (-W) % 4))
+    return t.contiguous()
+
+
+class QP:
+    """A float32 activation tensor in quad-planar layout (+ optionally its planar copy `pl`)."""
+    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W', 'pl')
+
+    def __init__(self, t, N, C, D, H, W, pl=None):
+        self.t, self.N, self.C, self.D, self.H, self.W, self.pl = t, N, C, D, H, W, pl
 
     @staticmethod
     def empty(N, C, D, H, W, device):
@@ -60,12 +76,14 @@ def _require_cuda(t, what):
 
 
 # ------------------------------------------------------------------------------------------ layout
-def pack_input(x5):
+def pack_input(x5, planar=False):
     """NCDHW float32 -> QP (reference: the tensor `Trainer._train_step` moves to the device, trainer.py:515)"""
     _require_cuda(x5, 'input')
     x5 = x5.contiguous()
     N, C, D, H, W = x5.shape
     q = QP.empty(N, C, D, H, W, x5.device)
+    if planar:
+        q.pl = planar_from_ncdhw(x5)
     L.check(L.lib().e3b_pack_ncdhw(x5.data_ptr(), q.ptr, N, C, D, H, W, D, H, W, 0, 0, 0, _stream()), 'pack_ncdhw')
     return q
 
@@ -160,13 +178,15 @@ def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), b
 def wgrad(src0, dy, Co, k, pad, dw_shape, *, src1=None, off1=(0, 0, 0), layout=0, up_taps=0, up_co=0):
     a = L.WgradArgs()
     dev = src0.t.device
-    a.src0, a.C0 = src0.ptr, src0.C
+    if src0.pl is None or dy.pl is None or (src1 is not None and src1.pl is None):
+        raise RuntimeError('wgrad: operands need their planar copies (forward was run without save=True?)')
+    a.src0, a.C0 = src0.pl.data_ptr(), src0.C
     a.N, a.D, a.H, a.W = src0.N, src0.D, src0.H, src0.W
     if src1 is not None:
-        a.src1, a.C1 = src1.ptr, src1.C
+        a.src1, a.C1 = src1.pl.data_ptr(), src1.C
         a.D1, a.H1, a.W1 = src1.D, src1.H, src1.W
         a.off1_d, a.off1_h, a.off1_w = off1
-    a.dy, a.Co = dy.ptr, Co
+    a.dy, a.Co = dy.pl.data_ptr(), Co
     a.kd, a.kh, a.kw = k
     a.pd, a.ph, a.pw = pad
     dw = torch.empty(dw_shape, dtype=torch.float32, device=dev)
@@ -199,8 +219,10 @@ def norm_finalize(stats, mode, G, N, C, S, gamma, beta, eps, rm, rv, momentum, d
     return st
 
 
-def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True):
-    """a = relu(y*scale+shift) and optionally the ceil-mode max-pooled tensor."""
+def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, planar=False):
+    """a = relu(y*scale+shift) and optionally the ceil-mode max-pooled tensor.  planar=True also writes the
+    planar copies the weight-gradient kernel reads (training).  With write_a=False the QP tensor `y` is
+    already the activation; its planar copy (if requested) is attached to `y` itself."""
     dev = y.t.device
     a = QP.empty(y.N, y.C, y.D, y.H, y.W, dev) if write_a else None
     pooled = None
@@ -208,8 +230,15 @@ def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True):
     if pool is not None:
         pk = pool
         pooled = QP.empty(y.N, y.C, -(-y.D // pk[0]), -(-y.H // pk[1]), -(-y.W // pk[2]), dev)
+    a_pl = p_pl = None
+    if planar:
+        a_pl = planar_empty(y.N, y.C, y.D, y.H, y.W, dev)
+        (a if a is not None else y).pl = a_pl
+        if pooled is not None:
+            p_pl = pooled.pl = planar_empty(pooled.N, pooled.C, pooled.D, pooled.H, pooled.W, dev)
     L.check(L.lib().e3b_norm_act(y.ptr, _p(scale), _p(shift), a.ptr if a else None, pooled.ptr if pooled else None,
-                                 y.N, y.C, y.D, y.H, y.W, pk[0], pk[1], pk[2], 1 if relu else 0, _stream()), 'norm_act')
+                                 _p(a_pl), _p(p_pl), y.N, y.C, y.D, y.H, y.W, pk[0], pk[1], pk[2], 1 if relu else 0,
+                                 _stream()), 'norm_act')
     return a, pooled
 
 
@@ -320,8 +349,8 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save):
         a, _, _ = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
                                relu=True)
         u.y = u.a = a
-        if pool is not None:
-            _, u.pooled = norm_act(a, None, None, write_a=False, pool=pool)
+        if pool is not None or save:
+            _, u.pooled = norm_act(a, None, None, write_a=False, pool=pool, planar=save)
     else:
         n = spec.norm
         y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1,
@@ -334,7 +363,7 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save):
         u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, S, _affine(n, 'weight'), _affine(n, 'bias'), n.eps,
                                  rm, rv, mom, y.t.device)
         u.y, u.stats = y, stats
-        u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool)
+        u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, planar=save)
     if not save:
         u.y = u.src0 = u.src1 = None
     return u
@@ -391,6 +420,8 @@ def _run_up(net, spec, dec, enc, training, save):
         a, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias, relu=True,
                                scatter=spec.s, out_spatial=out_sp)
         u.y = u.a = a
+        if save:
+            norm_act(a, None, None, write_a=False, planar=True)
     else:
         n = spec.norm
         y, _, stats = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias,
@@ -402,7 +433,7 @@ def _run_up(net, spec, dec, enc, training, save):
         u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, y.D * y.H * y.W, _affine(n, 'weight'),
                                  _affine(n, 'bias'), n.eps, rm, rv, mom, y.t.device)
         u.y, u.stats = y, stats
-        u.a, _ = norm_act(y, u.nstate.scale, u.nstate.shift)
+        u.a, _ = norm_act(y, u.nstate.scale, u.nstate.shift, planar=save)
     if not save:
         u.y = u.dec = u.src0 = None
     return u, off1
@@ -422,7 +453,7 @@ def forward_features(net, x, training, save):
     cin = net.down[0][0].C0
     if x5.shape[1] != cin:
         raise RuntimeError(f'expected {cin} input channels, got {x5.shape[1]}')
-    cur = pack_input(x5)
+    cur = pack_input(x5, planar=save)
     return forward_features_qp(net, cur, training, save, squeeze, tuple(x.shape))
 
 
@@ -480,7 +511,7 @@ def forward(net, x, training, save):
 
 
 # ------------------------------------------------------------------------------------------ backward
-def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True):
+def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True, planar=True, conv_geom=None):
     """Backward of norm -> relu [-> pool] for unit `u`; returns (dy QP or s2d QP, dgamma, dbeta, dbias)."""
     if u.mode == MODE_BATCH_EVAL:
         raise NotImplementedError('backward through eval-mode BatchNorm is not on the accelerated path '
@@ -526,6 +557,14 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True):
     else:
         dy = QP.empty(N, C, a.D, a.H, a.W, dev)
     args.dy = dy.ptr
+    if planar:
+        if s2d is not None or conv_geom is None:
+            kw_, pw_, wx_ = 1, 0, dy.W
+        else:
+            kw_, pw_, wx_ = conv_geom
+        dy.pl = planar_empty(dy.N, dy.C, dy.D, dy.H, wx_, dev, kw=kw_)
+        args.dy_planar = dy.pl.data_ptr()
+        args.planar_kw, args.planar_pw, args.planar_W = kw_, pw_, wx_
     args.relu = 1
     lib = L.lib()
     st = _stream()
@@ -544,7 +583,9 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
     """Backward of one conv -> norm -> relu [-> pool] unit: returns (dsrc0, dsrc1)."""
     spec = u.spec
     conv, n = spec.conv, spec.norm
-    dy, dgamma, dbeta, dbias = _norm_bwd(u, spec.Co, g0, g1, gp, want_bias=conv.bias is not None)
+    dy, dgamma, dbeta, dbias = _norm_bwd(u, spec.Co, g0, g1, gp, want_bias=conv.bias is not None,
+                                         planar=conv.weight.requires_grad,
+                                         conv_geom=(spec.k[2], spec.pad[2], u.src0.W))
     if dgamma is not None:
         _put(grads, n.weight, dgamma)
         _put(grads, n.bias, dbeta)

@@ -86,7 +86,10 @@ int e3b_conv(const e3b_conv_args* args, void* stream);
 
 /* Weight gradient: dW[tap][ci][co] = sum_voxels x[v + tap - pad][ci] * dy[v][co]  (conv backward-filter
  * of nn.Conv3d at unet.py:131-149; with taps=1 on (x, space-to-depth dy) also ConvTranspose's).
- * x = [src0 | src1] (QP, extents D,H,W), dy QP (N, Co, Do,Ho,Wo).  Result is written in torch layout:
+ * Operands are Z-PLANAR float32 tensors (row pitch padded to 16 bytes), written by e3b_norm_act /
+ * e3b_norm_bwd_apply:  src0 (N, D, C0, H, ceil4(W));  src1 (N, D1, C1, H1, ceil4(W1)) read at offset off1
+ * (only with zero padding);  dy (N, Do, kw, Co, Ho, ceil4(W)) = the kw x-shifted copies described at
+ * e3b_norm_bwd_args.dy_planar.  Result is written in torch layout:
  *   layout 0: dw (Co, C0+C1, kd, kh, kw)        (Conv)
  *   layout 1: dw (C0, Co/ntap_up, sd, sh, sw) with dy channels = tap*pad8(Co_up)+co  (ConvTranspose)
  * `workspace` holds split-K partials: e3b_wgrad_workspace_floats() floats. */
@@ -114,8 +117,11 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
                       float* scale, float* shift, float* mean, float* rstd, void* stream);
 /* a = relu(y*scale+shift) (QP); if pooled != NULL also pooled = maxpool_{(pk_d,pk_h,pk_w), ceil}(a).
  * scale/shift NULL = identity; a NULL = only the pooled tensor is written (eval path: y is already
- * activated by the conv epilogue). */
+ * activated by the conv epilogue).
+ * a_planar / pooled_planar (optional): the same tensors as Z-PLANAR (N, D, C, H, ceil4(W)) float32 copies, the
+ * operand layout of e3b_wgrad. */
 int e3b_norm_act(const float* y, const float* scale, const float* shift, float* a, float* pooled,
+                 float* a_planar, float* pooled_planar,
                  int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, void* stream);
 
 /* backward of conv -> norm -> relu [-> pool] as autograd derives it:
@@ -136,6 +142,11 @@ typedef struct e3b_norm_bwd_args {
     float* m1; float* m2;                      /* [N][pad8(C)] */
     float* dgamma; float* dbeta; float* dbias; /* [C] each; may be NULL */
     float* dy; int32_t s2d, sd, sh, sw;        /* output */
+    float* dy_planar;                          /* optional: dy in the layout e3b_wgrad contracts against,
+                                                  (N, D, kw, C, H, ceil4(Wx)) with the stencil's x shift applied:
+                                                  [n][z][dxi][c][y][xs] = dy[n][c][z][y][xs - (dxi - pw)];
+                                                  s2d: (N, Dw, 1, taps*pad8(C), Hw, ceil4(Ww)) */
+    int32_t planar_kw, planar_pw, planar_W;    /* kw, pw and input width Wx of the conv dy belongs to (0 -> 1,0,W) */
     int32_t relu;
 } e3b_norm_bwd_args;
 int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* args, void* stream);

@@ -44,7 +44,26 @@ def from_qp_ref(t, C):
 
 def qp(eng, x):
     N, C, D, H, W = x.shape
-    return eng.QP(to_qp_ref(x), N, C, D, H, W)
+    return eng.QP(to_qp_ref(x), N, C, D, H, W, pl=eng.planar_from_ncdhw(x))
+
+
+def shifted_planar(eng, dy, kw, pw, Wx):
+    """test-side restatement of e3b_norm_bwd_args.dy_planar: (N, D, kw, C, H, ceil4(Wx)) x-shifted copies"""
+    N, C, D, H, W = dy.shape
+    out = torch.zeros((N, D, kw, C, H, (Wx + 3) & ~3), device=dy.device)
+    src = dy.permute(0, 2, 1, 3, 4)
+    for dxi in range(kw):
+        sh = dxi - pw
+        lo, hi = max(sh, 0), min(W + sh, Wx)
+        if hi > lo:
+            out[:, :, dxi, :, :, lo:hi] = src[..., lo - sh:hi - sh]
+    return out
+
+
+def qp_dy(eng, dy, kw, pw, Wx):
+    q = qp(eng, dy)
+    q.pl = shifted_planar(eng, dy, kw, pw, Wx)
+    return q
 
 
 def assert_close(got, ref, tol, what=''):
@@ -215,7 +234,7 @@ def test_conv_wgrad(eng, case):
     y.backward(dy.double())
     src0 = qp(eng, x[:, :C0].contiguous())
     src1 = qp(eng, x[:, C0:].contiguous()) if C1 else None
-    dw = eng.wgrad(src0, qp(eng, dy), Co, k, pad, tuple(w.shape), src1=src1)
+    dw = eng.wgrad(src0, qp_dy(eng, dy, k[2], pad[2], sp[2]), Co, k, pad, tuple(w.shape), src1=src1)
     assert_close(dw, w.grad, 1e-6, 'wgrad')
 
 
@@ -236,7 +255,7 @@ def test_transposed_conv_backward(eng, case):
     d = dy.view(N, Co, D, s[0], H, s[1], W, s[2]).permute(0, 3, 5, 7, 1, 2, 4, 6).reshape(N, taps, Co, D, H, W)
     dpad = torch.zeros((N, taps, Cp, D, H, W), device='cuda')
     dpad[:, :, :Co] = d
-    dyq = qp(eng, dpad.view(N, taps * Cp, D, H, W))
+    dyq = qp_dy(eng, dpad.view(N, taps * Cp, D, H, W), 1, 0, W)
     wpk = eng.pack_weights(3, w.detach().float(), None, Ci, 0, Co, s)
     dx, _, _ = eng.conv_forward(dyq, wpk, eng.cpad16(Ci), Ci, (1, 1, 1), (0, 0, 0))
     assert_close(from_qp_ref(dx.t, Ci), x.grad, 1e-6, 'convT dgrad')
@@ -277,12 +296,12 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
     yq = qp(eng, y)
     stats = torch.stack((y.double().sum(dim=(2, 3, 4)), (y.double() ** 2).sum(dim=(2, 3, 4))), dim=-1).contiguous()
     if mode == 0:
-        a, pooled = eng.norm_act(yq, None, None, pool=pool)
+        a, pooled = eng.norm_act(yq, None, None, pool=pool, planar=True)
         nstate = None
     else:
         nstate = eng.norm_finalize(stats, mode, G, N, C, S, gamma, beta, 1e-5, rm if mode == 2 else None,
                                    rv if mode == 2 else None, 0.1, y.device)
-        a, pooled = eng.norm_act(yq, nstate.scale, nstate.shift, pool=pool)
+        a, pooled = eng.norm_act(yq, nstate.scale, nstate.shift, pool=pool, planar=True)
     assert_close(from_qp_ref(a.t, C), a_ref, 1e-5, 'norm+relu')
     if pool is not None:
         assert_close(from_qp_ref(pooled.t, C), outs[1], 1e-5, 'pool')
@@ -310,6 +329,14 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
     u.a, u.y, u.pool, u.mode, u.G, u.nstate, u.stats = a, yq, pool, mode, G, nstate, (stats if mode else None)
     dy, dgamma, dbeta, dbias = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq)
     assert_close(from_qp_ref(dy.t, C), yd.grad, 2e-4, 'norm bwd dy')
+    # z-planar copies for the wgrad kernel
+    assert torch.equal(a.pl[..., :sp[2]], from_qp_ref(a.t, C).permute(0, 2, 1, 3, 4))
+    if pool is not None:
+        assert torch.equal(pooled.pl[..., :pooled.W], from_qp_ref(pooled.t, C).permute(0, 2, 1, 3, 4))
+    dy3, _, _, _ = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq, conv_geom=(3, 1, sp[2]))
+    assert torch.equal(dy3.pl, shifted_planar(eng, from_qp_ref(dy3.t, C), 3, 1, sp[2]))
+    dy3v, _, _, _ = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq, conv_geom=(3, 0, sp[2] + 2))
+    assert torch.equal(dy3v.pl, shifted_planar(eng, from_qp_ref(dy3v.t, C), 3, 0, sp[2] + 2))
     if mode:
         assert_close(dgamma, gd.grad, 2e-4, 'dgamma')
         assert_close(dbeta, bd.grad, 2e-4, 'dbeta')
@@ -341,6 +368,7 @@ def test_norm_backward_space_to_depth(eng):
     D, H, W = coarse
     ref = full.view(N, C, D, 2, H, 2, W, 2).permute(0, 3, 5, 7, 1, 2, 4, 6).reshape(N, 8 * C, D, H, W)
     assert_close(from_qp_ref(dy.t, 8 * C), ref, 1e-6, 's2d')
+    assert torch.equal(dy.pl[:, :, 0, :, :, :W], from_qp_ref(dy.t, 8 * C).permute(0, 2, 1, 3, 4))
 
 
 # ---------------------------------------------------------------------------------------- head
