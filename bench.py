@@ -120,6 +120,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-steps', type=int, default=0,
+                    help='run only this many train steps after one warm-up and exit (for ncu; prints no bench line)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -187,6 +189,11 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    if args.profile_steps:
+        for _ in range(1 + args.profile_steps):
+            step(x_dev, t_dev)
+        torch.cuda.synchronize()
+        return
     for _ in range(max(args.warmup, 3)):
         step(x_dev, t_dev)
     with ClockSampler(local_rank) as clocks:

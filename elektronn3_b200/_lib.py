@@ -27,7 +27,7 @@ class ConvArgs(ctypes.Structure):
         ('n_total', c_i32),
         ('dst0', c_void_p), ('Cd0', c_i32),
         ('dst1', c_void_p), ('Cd1', c_i32),
-        ('relu', c_i32),
+        ('relu', c_i32), ('round_tf32', c_i32),
         ('stats', c_void_p), ('stats_channels', c_i32),
         ('scatter', c_i32), ('sd', c_i32), ('sh', c_i32), ('sw', c_i32),
         ('Ds', c_i32), ('Hs', c_i32), ('Ws', c_i32),

@@ -157,6 +157,14 @@ E3B_DEVINL void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// round-to-nearest fp32 -> tf32 (10 explicit mantissa bits).  The tensor core ignores the low 13 bits of
+// its fp32 operands (truncation, biased); tensors that feed an MMA are stored pre-rounded instead.
+E3B_DEVINL float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
 E3B_DEVINL bool elect_one() {
     uint32_t pred;
     asm volatile(

@@ -48,6 +48,7 @@ struct ConvTcParams {
     float* dst1;                 // ... the rest to dst1 (dgrad of a virtual-concat conv)
     int cq0_alloc, cq1_alloc;    // planes allocated in dst0 / dst1
     int relu;
+    int round_tf32;              // round the stored output to TF32 (it feeds the next MMA unrounded otherwise)
     double* stats;               // [N][Cstat][2] sum / sumsq (fp64 atomics) or null
     int Cstat;
     int scatter;                 // 1: k=s transposed conv, column n = tap*Cup + co, dst is the fine grid
@@ -56,6 +57,20 @@ struct ConvTcParams {
     int Ds, Hs, Ws;              // (scatter) cropped fine-grid output extents
     const float* wpk;
 };
+
+static constexpr int kStatSlots = 256;
+
+// per-CTA statistics accumulators -> global [N][Cstat][2] (fp64 atomics: a few hundred per CTA, not per tile)
+E3B_DEVINL void flush_stats(const ConvTcParams& p, double* cta_stats, int n, int nt, int etid) {
+    const int nslots = p.scatter ? (p.Cup < kStatSlots ? p.Cup : kStatSlots) : (p.NT < kStatSlots ? p.NT : kStatSlots);
+    for (int i = etid; i < nslots * 2; i += 128) {
+        const int si = i >> 1;
+        const int ch = p.scatter ? si : nt * p.NT + si;
+        const double v = cta_stats[i];
+        cta_stats[i] = 0.0;
+        if (ch < p.Cstat && v != 0.0) atomicAdd(p.stats + ((size_t)n * p.Cstat + ch) * 2 + (i & 1), v);
+    }
+}
 
 E3B_DEVINL void decode_tile(const ConvTcParams& p, int t, int& nt, int& n, int& z0, int& y0, int& x0) {
     int xt = t % p.tiles_x; t /= p.tiles_x;
@@ -82,6 +97,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     uint64_t* acc_full = b_empty + p.SB;  // [2]
     uint64_t* acc_empty = acc_full + 2;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    __shared__ double cta_stats[kStatSlots * 2];
+    for (int i = threadIdx.x; i < kStatSlots * 2; i += blockDim.x) cta_stats[i] = 0.0;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -133,79 +150,114 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(p.NT, 0, 0);
-            const uint32_t a_lbo = (uint32_t)(p.HX * p.HY * p.HZ * 16);  // between the two 4-channel planes
-            const uint32_t a_sbo = (uint32_t)(p.HX * 16);                // next y row (8-row group)
-            const uint32_t b_lbo = (uint32_t)(p.NT * 16);
-            const uint32_t b_sbo = 128;
-            uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it++) {
-                const uint32_t buf = it & 1, use = it >> 1;
-                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+        // The whole warp runs the loop (warp-uniform control flow keeps the descriptor arithmetic on the
+        // uniform datapath); one elected lane issues the MMAs and the commits.
+        const uint32_t idesc = umma_idesc_tf32(p.NT, 0, 0);
+        // descriptor templates with a zero address field; one voxel == 16 B == one address unit
+        const uint64_t a_tmpl = umma_desc(0, (uint32_t)(p.HX * p.HY * p.HZ * 16), (uint32_t)(p.HX * 16));
+        const uint64_t b_tmpl = umma_desc(0, (uint32_t)(p.NT * 16), 128);
+        const uint32_t plane_step = (uint32_t)(p.HY * p.HX);
+        const uint32_t tap_step_b = (uint32_t)(2 * p.NT);
+        const bool leader = elect_one();
+        uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it++) {
+            const uint32_t buf = it & 1, use = it >> 1;
+            mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + buf * 256;
+            for (int c = 0; c < nchunks; c++) {
+                mbar_wait(&a_full[sa], pa);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + buf * 256;
-                for (int c = 0; c < nchunks; c++) {
-                    mbar_wait(&a_full[sa], pa);
+                const uint32_t a16 = smem_u32(a_base + (size_t)sa * p.a_stage_bytes) >> 4;
+                int dz = 0, dy = 0, dx = 0;
+                for (int g = 0; g < ngroups; g++) {
+                    mbar_wait(&b_full[sb], pb);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(a_base + (size_t)sa * p.a_stage_bytes);
-                    int tap = 0;
-                    for (int g = 0; g < ngroups; g++) {
-                        mbar_wait(&b_full[sb], pb);
-                        tc_fence_after();
-                        const uint32_t b_addr = smem_u32(b_base + (size_t)sb * p.b_stage_bytes);
-                        for (int tg = 0; tg < p.TG; tg++, tap++) {
-                            const int dz = tap / (p.kh * p.kw);
-                            const int dy = (tap / p.kw) % p.kh;
-                            const int dx = tap % p.kw;
-                            const uint64_t bdesc = umma_desc(b_addr + (uint32_t)tg * (2u * p.NT * 16u), b_lbo, b_sbo);
-                            const uint32_t accum = (c | tap) ? 1u : 0u;
+                    const uint32_t b16 = smem_u32(b_base + (size_t)sb * p.b_stage_bytes) >> 4;
+                    if (leader) {
+                        uint64_t bd = b_tmpl + b16;
+                        for (int tg = 0; tg < p.TG; tg++) {
+                            uint64_t ad = a_tmpl + (a16 + (uint32_t)((dz * p.HY + dy) * p.HX + dx));
+                            uint32_t d = acc;
+                            const uint32_t accum = (c | g | tg) ? 1u : 0u;
                             for (int pl = 0; pl < p.TZ; pl++) {
-                                const uint32_t off = (uint32_t)(((pl + dz) * p.HY + dy) * p.HX + dx) * 16u;
-                                umma_tf32(acc + (uint32_t)(pl * p.NT), umma_desc(a_addr + off, a_lbo, a_sbo), bdesc,
-                                          idesc, accum);
+                                umma_tf32(d, ad, bd, idesc, accum);
+                                ad += plane_step;
+                                d += (uint32_t)p.NT;
                             }
+                            bd += tap_step_b;
+                            if (++dx == p.kw) { dx = 0; if (++dy == p.kh) { dy = 0; ++dz; } }
                         }
                         umma_commit(&b_empty[sb]);
-                        if (++sb == (uint32_t)p.SB) { sb = 0; pb ^= 1; }
                     }
-                    umma_commit(&a_empty[sa]);
-                    if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
+                    __syncwarp();
+                    if (++sb == (uint32_t)p.SB) { sb = 0; pb ^= 1; }
                 }
-                umma_commit(&acc_full[buf]);
+                if (leader) umma_commit(&a_empty[sa]);
+                __syncwarp();
+                if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
             }
+            if (leader) umma_commit(&acc_full[buf]);
+            __syncwarp();
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;          // GEMM row inside the tile
         const int ry = row >> 3, rx = row & 7;
+        const int etid = threadIdx.x - 64;      // 0..127
+        // butterfly transpose-reduce leaves column (bit-reversed low nibble of the lane) in lanes 0..15
+        const int bcol = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
+        int cur_n = -1, cur_nt = -1;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it++) {
             const uint32_t buf = it & 1, use = it >> 1;
             int nt, n, z0, y0, x0;
             decode_tile(p, t, nt, n, z0, y0, x0);
+            if (p.stats && (n != cur_n || (!p.scatter && nt != cur_nt))) {
+                // the per-CTA statistics accumulators belong to one (sample, N tile): flush on change
+                named_bar_sync(1, 128);
+                if (cur_n >= 0) flush_stats(p, cta_stats, cur_n, cur_nt, etid);
+                named_bar_sync(1, 128);
+                cur_n = n; cur_nt = nt;
+            }
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after();
             const int y = y0 + ry, x = x0 + rx;
-            const bool in_xy = (y < p.Ho) && (x < p.Wo);
-            for (int pl = 0; pl < p.TZ; pl++) {
-                const int z = z0 + pl;
-                if (z >= p.Do) break;           // warp-uniform
-                const bool valid = in_xy;
-                for (int cb = 0; cb < p.NT; cb += 16) {
+            const bool valid = (y < p.Ho) && (x < p.Wo);
+            const int npl = (p.Do - z0) < p.TZ ? (p.Do - z0) : p.TZ;
+            for (int cb = 0; cb < p.NT; cb += 16) {
+                const int ncol = nt * p.NT + cb;     // first global N column of this group
+                float bias_v[16];
+                {
+                    const int b0 = p.scatter ? (ncol % p.Cup) : ncol;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) bias_v[j] = (p.bias && b0 + j < p.n_bias) ? __ldg(p.bias + b0 + j) : 0.f;
+                }
+                // scatter geometry of this column group (one tap per 16-column group: Cup % 16 == 0)
+                int ti = 0, tj = 0, tk = 0, co = ncol;
+                if (p.scatter) {
+                    const int tapi = ncol / p.Cup; co = ncol % p.Cup;
+                    ti = tapi / (p.sh * p.sw); tj = (tapi / p.sw) % p.sh; tk = tapi % p.sw;
+                }
+                float s[16], ss[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) { s[j] = 0.f; ss[j] = 0.f; }
+                for (int pl = 0; pl < npl; pl++) {
+                    const int z = z0 + pl;
                     float v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)(pl * p.NT + cb), v);
-                    const int ncol = nt * p.NT + cb;     // first global N column of this group
-                    if (p.bias) {
-                        const int b0 = p.scatter ? (ncol % p.Cup) : ncol;
 #pragma unroll
-                        for (int j = 0; j < 16; j++) v[j] += (b0 + j < p.n_bias) ? __ldg(p.bias + b0 + j) : 0.f;
-                    }
+                    for (int j = 0; j < 16; j++) v[j] += bias_v[j];
                     if (p.relu) {
 #pragma unroll
                         for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], 0.f);
                     }
+                    if (p.round_tf32) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = tf32_rn(v[j]);
+                    }
+                    bool sv = valid;
                     if (!p.scatter) {
                         if (valid) {
 #pragma unroll
@@ -223,10 +275,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                         }
                     } else {
                         // column = tap * Cup + co ; fine voxel = (z*sd+i, y*sh+j, x*sw+k)
-                        const int tapi = ncol / p.Cup, co = ncol % p.Cup;
-                        const int ti = tapi / (p.sh * p.sw), tj = (tapi / p.sw) % p.sh, tk = tapi % p.sw;
                         const int fz = z * p.sd + ti, fy = y * p.sh + tj, fx = x * p.sw + tk;
-                        if (valid && fz < p.Ds && fy < p.Hs && fx < p.Ws) {
+                        sv = valid && fz < p.Ds && fy < p.Hs && fx < p.Ws;
+                        if (sv) {
 #pragma unroll
                             for (int j4 = 0; j4 < 4; j4++) {
                                 int cq = (co >> 2) + j4;
@@ -238,41 +289,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                             }
                         }
                     }
-                    if (p.stats) {
-                        // per-channel sum / sumsq over the warp's 32 rows: 16-value butterfly transpose-reduce
-                        bool sv = valid;
-                        if (p.scatter) {
-                            const int tapi = ncol / p.Cup;
-                            const int ti = tapi / (p.sh * p.sw), tj = (tapi / p.sw) % p.sh, tk = tapi % p.sw;
-                            sv = valid && (z * p.sd + ti < p.Ds) && (y * p.sh + tj < p.Hs) && (x * p.sw + tk < p.Ws);
+                    if (p.stats && sv) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
+                    }
+                }
+                if (p.stats) {
+                    // per-channel sum / sumsq over the warp's 32 rows x npl planes: 16-value butterfly
+#pragma unroll
+                    for (int step = 0; step < 4; step++) {
+                        const int half = 8 >> step;           // 8,4,2,1 values kept
+                        const int bit = 1 << step;            // exchange partner lane bit
+                        const bool upper = (lane & bit) != 0;
+#pragma unroll
+                        for (int j = 0; j < half; j++) {
+                            float send_s = upper ? s[j] : s[j + half];
+                            float send_q = upper ? ss[j] : ss[j + half];
+                            float keep_s = upper ? s[j + half] : s[j];
+                            float keep_q = upper ? ss[j + half] : ss[j];
+                            s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                            ss[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
                         }
-                        float s[16], ss[16];
-#pragma unroll
-                        for (int j = 0; j < 16; j++) { float a = sv ? v[j] : 0.f; s[j] = a; ss[j] = a * a; }
-                        // after the 4 halving steps lane L holds column (L & 15)'s partial over 2 rows-halves
-#pragma unroll
-                        for (int step = 0; step < 4; step++) {
-                            const int half = 8 >> step;           // 8,4,2,1 values kept
-                            const int bit = 1 << step;            // exchange partner lane bit
-                            const bool upper = (lane & bit) != 0;
-#pragma unroll
-                            for (int j = 0; j < half; j++) {
-                                float send_s = upper ? s[j] : s[j + half];
-                                float send_q = upper ? ss[j] : ss[j + half];
-                                float keep_s = upper ? s[j + half] : s[j];
-                                float keep_q = upper ? ss[j + half] : ss[j];
-                                s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-                                ss[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
-                            }
-                        }
-                        float fs = s[0] + __shfl_xor_sync(0xffffffffu, s[0], 16);
-                        float fq = ss[0] + __shfl_xor_sync(0xffffffffu, ss[0], 16);
-                        if (lane < 16) {
-                            // column index recovered from the butterfly: bit k of the column = lane bit (3-k)? no:
-                            // step 0 split on value-index bit 3 by lane bit 0, step 1 bit 2 by lane bit 1, ...
-                            const int col = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
-                            int ch = ncol + col;
-                            if (p.scatter) ch = ch % p.Cup;
+                    }
+                    const float fs = s[0] + __shfl_xor_sync(0xffffffffu, s[0], 16);
+                    const float fq = ss[0] + __shfl_xor_sync(0xffffffffu, ss[0], 16);
+                    if (lane < 16) {
+                        const int si = p.scatter ? (co + bcol) : (cb + bcol);     // accumulator slot
+                        if (si < kStatSlots) {
+                            atomicAdd(&cta_stats[si * 2], (double)fs);
+                            atomicAdd(&cta_stats[si * 2 + 1], (double)fq);
+                        } else {
+                            const int ch = p.scatter ? si : ncol + bcol;
                             if (ch < p.Cstat) {
                                 atomicAdd(p.stats + ((size_t)n * p.Cstat + ch) * 2, (double)fs);
                                 atomicAdd(p.stats + ((size_t)n * p.Cstat + ch) * 2 + 1, (double)fq);
@@ -284,6 +331,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (p.stats) {
+            named_bar_sync(1, 128);
+            if (cur_n >= 0) flush_stats(p, cta_stats, cur_n, cur_nt, etid);
         }
     }
 
@@ -390,7 +441,7 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
     while (tg > 1 && (size_t)tg * 2 * p.NT * 16 > 40 * 1024) tg /= 3;
     p.TG = tg;
     p.b_stage_bytes = (uint32_t)(tg * 2 * p.NT * 16);
-    const size_t budget = 227 * 1024 - 1024 - 256;
+    const size_t budget = 227 * 1024 - 1024 - 256 - sizeof(double) * 2 * kStatSlots - 64;   // static cta_stats
     int sa = 2, sb = 2;
     // grow depth while it fits (A first up to 4, then B up to 4)
     for (;;) {
@@ -407,7 +458,7 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
     p.cq0_alloc = e3b_cpad(a->Cd0) / 4;
     p.cq1_alloc = a->dst1 ? e3b_cpad(a->Cd1) / 4 : 0;
     p.cq0 = a->dst1 ? p.cq0_alloc : (1 << 30);
-    p.relu = a->relu;
+    p.relu = a->relu; p.round_tf32 = a->round_tf32;
     p.stats = a->stats; p.Cstat = a->stats_channels;
     p.scatter = a->scatter; p.sd = a->sd; p.sh = a->sh; p.sw = a->sw;
     p.Cup = a->scatter ? e3b_cpad(a->Cd0) : 1;

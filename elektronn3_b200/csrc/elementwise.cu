@@ -45,7 +45,7 @@ __global__ void pack_kernel(const float* __restrict__ src, const int32_t* __rest
                 if (c < C) v[j] = __ldg(src + nb + (size_t)c * plane + vox);
             }
         }
-        dst[i] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[i] = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
     }
 }
 
@@ -115,7 +115,7 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, const
             const int t = k / Cop8, co = k % Cop8;
             if (n < C0 && co < Co) v = w[((size_t)n * Co + co) * tu + t];
         }
-        dst[i] = v;
+        dst[i] = tf32_rn(v);
     }
 }
 
@@ -252,6 +252,8 @@ __global__ void norm_act_kernel(const float4* __restrict__ y, const float* __res
                     v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
                     v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
                     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    // activations are MMA operands of the next conv: store them rounded to TF32
+                    v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
                     if (a) a[o] = v;
                     if (a_pl) store_planar(a_pl, v, n, cq, C, D, H, Wpl, z, yy, x);
                     m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
@@ -460,6 +462,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
             o.y = rs.y * (ga.y * dr[j].y - m1.y - xh[j].y * m2.y);
             o.z = rs.z * (ga.z * dr[j].z - m1.z - xh[j].z * m2.z);
             o.w = rs.w * (ga.w * dr[j].w - m1.w - xh[j].w * m2.w);
+            // dy is the MMA operand of dgrad and wgrad: store it rounded to TF32
+            o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
             if (p.s2d) p.dy[(((size_t)n * nslots + slot[j]) * p.Cq + cq) * wins + i] = o;
             else p.dy[offs[j]] = o;
             if (p.dy_pl) {

@@ -136,7 +136,7 @@ class WeightCache:
 
 # ------------------------------------------------------------------------------------------ conv
 def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), bias=None, relu=False,
-                 stats_channels=0, dst1_C=0, scatter=None, out_spatial=None, force_tz=0):
+                 stats_channels=0, dst1_C=0, scatter=None, out_spatial=None, force_tz=0, round_tf32=False):
     """One launch of the implicit-GEMM kernel.  Returns (dst0, dst1, stats)."""
     a = L.ConvArgs()
     dev = src0.t.device
@@ -166,6 +166,7 @@ def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), b
         dst1 = QP.empty(src0.N, dst1_C, Do, Ho, Wo, dev)
         a.dst1, a.Cd1 = dst1.ptr, dst1_C
     a.relu = 1 if relu else 0
+    a.round_tf32 = 1 if round_tf32 else 0
     stats = None
     if stats_channels:
         stats = torch.empty((src0.N, stats_channels, 2), dtype=torch.float64, device=dev)
@@ -347,7 +348,7 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save):
     u.pooled = u.nstate = u.stats = u.dec = None
     if mode in (MODE_NONE, MODE_BATCH_EVAL):
         a, _, _ = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
-                               relu=True)
+                               relu=True, round_tf32=True)
         u.y = u.a = a
         if pool is not None or save:
             _, u.pooled = norm_act(a, None, None, write_a=False, pool=pool, planar=save)
@@ -418,7 +419,7 @@ def _run_up(net, spec, dec, enc, training, save):
                             lambda: pack_weights(2, up.weight, None, spec.Ci, 0, spec.Co, spec.s))
     if mode in (MODE_NONE, MODE_BATCH_EVAL):
         a, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias, relu=True,
-                               scatter=spec.s, out_spatial=out_sp)
+                               scatter=spec.s, out_spatial=out_sp, round_tf32=True)
         u.y = u.a = a
         if save:
             norm_act(a, None, None, write_a=False, planar=True)

@@ -76,6 +76,8 @@ typedef struct e3b_conv_args {
     float* dst0; int32_t Cd0;                  /* QP output, channels [0, Cd0) */
     float* dst1; int32_t Cd1;                  /* optional 2nd output: channels after pad8(Cd0) */
     int32_t relu;                              /* fuse ReLU (eval-mode BN folded into weights) */
+    int32_t round_tf32;                        /* store the output rounded to TF32 (round-to-nearest): set when
+                                                  the output is the operand of another MMA */
     double* stats; int32_t stats_channels;     /* optional [N][stats_channels][2] sum/sumsq of the output (fp64;
                                                   zeroed by this call) for the following Group/BatchNorm */
     int32_t scatter, sd, sh, sw;               /* transposed conv: column = tap*pad16(Cd0)+co -> fine voxel */

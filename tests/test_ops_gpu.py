@@ -302,9 +302,10 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
         nstate = eng.norm_finalize(stats, mode, G, N, C, S, gamma, beta, 1e-5, rm if mode == 2 else None,
                                    rv if mode == 2 else None, 0.1, y.device)
         a, pooled = eng.norm_act(yq, nstate.scale, nstate.shift, pool=pool, planar=True)
-    assert_close(from_qp_ref(a.t, C), a_ref, 1e-5, 'norm+relu')
+    # activations / gradients that feed an MMA are stored rounded to TF32 (2^-11 relative)
+    assert_close(from_qp_ref(a.t, C), a_ref, 6e-4, 'norm+relu')
     if pool is not None:
-        assert_close(from_qp_ref(pooled.t, C), outs[1], 1e-5, 'pool')
+        assert_close(from_qp_ref(pooled.t, C), outs[1], 6e-4, 'pool')
     if mode == 2:
         assert_close(rm, rmd, 1e-5, 'running_mean')
         assert_close(rv, rvd, 1e-5, 'running_var')
@@ -328,15 +329,15 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
         u.spec.norm.eps = 1e-5
     u.a, u.y, u.pool, u.mode, u.G, u.nstate, u.stats = a, yq, pool, mode, G, nstate, (stats if mode else None)
     dy, dgamma, dbeta, dbias = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq)
-    assert_close(from_qp_ref(dy.t, C), yd.grad, 2e-4, 'norm bwd dy')
+    assert_close(from_qp_ref(dy.t, C), yd.grad, 1e-3, 'norm bwd dy')
     # z-planar copies for the wgrad kernel
     assert torch.equal(a.pl[..., :sp[2]], from_qp_ref(a.t, C).permute(0, 2, 1, 3, 4))
     if pool is not None:
         assert torch.equal(pooled.pl[..., :pooled.W], from_qp_ref(pooled.t, C).permute(0, 2, 1, 3, 4))
     dy3, _, _, _ = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq, conv_geom=(3, 1, sp[2]))
-    assert torch.equal(dy3.pl, shifted_planar(eng, from_qp_ref(dy3.t, C), 3, 1, sp[2]))
+    assert torch.equal(dy3.pl[..., :sp[2]], shifted_planar(eng, from_qp_ref(dy3.t, C), 3, 1, sp[2])[..., :sp[2]])
     dy3v, _, _, _ = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq, conv_geom=(3, 0, sp[2] + 2))
-    assert torch.equal(dy3v.pl, shifted_planar(eng, from_qp_ref(dy3v.t, C), 3, 0, sp[2] + 2))
+    assert torch.equal(dy3v.pl[..., :sp[2] + 2], shifted_planar(eng, from_qp_ref(dy3v.t, C), 3, 0, sp[2] + 2)[..., :sp[2] + 2])
     if mode:
         assert_close(dgamma, gd.grad, 2e-4, 'dgamma')
         assert_close(dbeta, bd.grad, 2e-4, 'dbeta')
@@ -367,7 +368,7 @@ def test_norm_backward_space_to_depth(eng):
     full[:, :, :fine[0], :fine[1], :fine[2]] = yd.grad
     D, H, W = coarse
     ref = full.view(N, C, D, 2, H, 2, W, 2).permute(0, 3, 5, 7, 1, 2, 4, 6).reshape(N, 8 * C, D, H, W)
-    assert_close(from_qp_ref(dy.t, 8 * C), ref, 1e-6, 's2d')
+    assert_close(from_qp_ref(dy.t, 8 * C), ref, 6e-4, 's2d')
     assert torch.equal(dy.pl[:, :, 0, :, :, :W], from_qp_ref(dy.t, 8 * C).permute(0, 2, 1, 3, 4))
 
 
