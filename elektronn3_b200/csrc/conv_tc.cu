@@ -478,11 +478,13 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
         m1 = m0;
     }
     const size_t smem = (size_t)sa * p.a_stage_bytes + (size_t)sb * p.b_stage_bytes + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    static bool configured = false;
+    if (!configured) {
+        // static shared memory (cta_stats) counts against the 227 KB per-CTA limit
+        const int max_dyn = 227 * 1024 - (int)(sizeof(double) * 2 * kStatSlots) - 64;
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
         if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = 227 * 1024;
+        configured = true;
     }
     if (p.stats) {
         cudaError_t e = cudaMemsetAsync(p.stats, 0, sizeof(double) * 2 * (size_t)a->N * p.Cstat, stream);
