@@ -54,7 +54,7 @@ class WgradArgs(ctypes.Structure):
 class NormBwdArgs(ctypes.Structure):
     """struct e3b_norm_bwd_args"""
     _fields_ = [
-        ('a', c_void_p), ('y', c_void_p),
+        ('y', c_void_p), ('scale', c_void_p), ('shift', c_void_p),
         ('g0', c_void_p), ('g1', c_void_p), ('gp', c_void_p),
         ('N', c_i32), ('C', c_i32), ('D', c_i32), ('H', c_i32), ('W', c_i32),
         ('pk_d', c_i32), ('pk_h', c_i32), ('pk_w', c_i32),

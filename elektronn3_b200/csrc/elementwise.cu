@@ -269,7 +269,8 @@ __global__ void norm_act_kernel(const float4* __restrict__ y, const float* __res
 // backward of norm -> relu [-> pool]
 // ------------------------------------------------------------------------------------------------
 struct NormBwdDev {
-    const float4 *a, *y, *g0, *g1, *gp;
+    const float4 *y, *g0, *g1, *gp;
+    const float *scale, *shift;              // forward affine (nullptr: y already is the activation)
     int N, Cq, C, D, H, W, wd, wh, ww;     // window = pooling kernel (gp) or s2d stride, else 1
     int Dw, Hw, Ww;
     int relu, s2d;
@@ -280,78 +281,106 @@ struct NormBwdDev {
     int pl_kw, pl_pw, pl_Wx;
 };
 
-// loads one window, returns dr (masked upstream gradient) and xhat for up to 8 voxels
-E3B_DEVINL int load_window(const NormBwdDev& p, int n, int cq, int zw, int yw, int xw, const float4& mu, const float4& rs,
-                           float4* dr, float4* xh, size_t* offs, int* slot)
+// One pooling / space-to-depth window (WD x WH x WW voxels, compile-time so everything stays in
+// registers): the masked upstream gradient dr and xhat of every slot.
+//   dr = (g0 + g1 + unpool(gp)) * [a > 0]
+// `a` is not read from memory: it is recomputed bit-exactly from y (a = tf32_rn(relu(y*scale+shift)), the
+// arithmetic of norm_act_kernel), or y itself is the activation (scale == nullptr).
+template <int WD, int WH, int WW>
+struct Window {
+    static constexpr int N = WD * WH * WW;
+    float4 dr[N], xh[N];
+    bool ok[N];
+};
+
+template <int WD, int WH, int WW>
+E3B_DEVINL void load_window(const NormBwdDev& p, int n, int cq, int zw, int yw, int xw, const float4& mu, const float4& rs,
+                            const float4& sc, const float4& sh, Window<WD, WH, WW>& w)
 {
+    constexpr int NS = WD * WH * WW;
     const size_t base = ((size_t)n * p.Cq + cq) * p.D;
-    float4 av[8];
-    int cnt = 0;
-    for (int dz = 0; dz < p.wd; dz++) {
-        const int z = zw * p.wd + dz;
-        for (int dyy = 0; dyy < p.wh; dyy++) {
-            const int yy = yw * p.wh + dyy;
-            for (int dx = 0; dx < p.ww; dx++) {
-                const int x = xw * p.ww + dx;
-                if (z >= p.D || yy >= p.H || x >= p.W) continue;
-                const size_t o = ((base + z) * p.H + yy) * p.W + x;
-                offs[cnt] = o;
-                slot[cnt] = (dz * p.wh + dyy) * p.ww + dx;
-                av[cnt] = p.a[o];
-                const float4 yv = p.y[o];
-                xh[cnt] = make_float4((yv.x - mu.x) * rs.x, (yv.y - mu.y) * rs.y, (yv.z - mu.z) * rs.z, (yv.w - mu.w) * rs.w);
-                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.g0) g = p.g0[o];
-                if (p.g1) { const float4 t = p.g1[o]; g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w; }
-                dr[cnt] = g;
-                cnt++;
+    float4 av[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        const int dz = j / (WH * WW), dyy = (j / WW) % WH, dx = j % WW;
+        const int z = zw * WD + dz, yy = yw * WH + dyy, x = xw * WW + dx;
+        w.ok[j] = (z < p.D) && (yy < p.H) && (x < p.W);
+        w.dr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.xh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        av[j] = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
+        if (w.ok[j]) {
+            const size_t o = ((base + z) * p.H + yy) * p.W + x;
+            const float4 yv = p.y[o];
+            float4 a = yv;
+            if (p.scale) {
+                a.x = fmaf(yv.x, sc.x, sh.x); a.y = fmaf(yv.y, sc.y, sh.y);
+                a.z = fmaf(yv.z, sc.z, sh.z); a.w = fmaf(yv.w, sc.w, sh.w);
+                if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+                a.x = tf32_rn(a.x); a.y = tf32_rn(a.y); a.z = tf32_rn(a.z); a.w = tf32_rn(a.w);
             }
+            av[j] = a;
+            w.xh[j] = make_float4((yv.x - mu.x) * rs.x, (yv.y - mu.y) * rs.y, (yv.z - mu.z) * rs.z, (yv.w - mu.w) * rs.w);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.g0) g = p.g0[o];
+            if (p.g1) { const float4 t = p.g1[o]; g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w; }
+            w.dr[j] = g;
         }
     }
     if (p.gp) {
         // route the pooled gradient to the first maximum in (d,h,w) scan order (torch max_pool backward)
         const float4 gpv = p.gp[((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw];
         int bx = 0, by = 0, bz = 0, bw = 0;
-        for (int j = 1; j < cnt; j++) {
-            if (av[j].x > av[bx].x) bx = j;
-            if (av[j].y > av[by].y) by = j;
-            if (av[j].z > av[bz].z) bz = j;
-            if (av[j].w > av[bw].w) bw = j;
+        float4 best = av[0];
+#pragma unroll
+        for (int j = 1; j < NS; j++) {
+            if (av[j].x > best.x) { best.x = av[j].x; bx = j; }
+            if (av[j].y > best.y) { best.y = av[j].y; by = j; }
+            if (av[j].z > best.z) { best.z = av[j].z; bz = j; }
+            if (av[j].w > best.w) { best.w = av[j].w; bw = j; }
         }
-        for (int j = 0; j < cnt; j++) {
-            if (j == bx) dr[j].x += gpv.x;
-            if (j == by) dr[j].y += gpv.y;
-            if (j == bz) dr[j].z += gpv.z;
-            if (j == bw) dr[j].w += gpv.w;
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            if (j == bx) w.dr[j].x += gpv.x;
+            if (j == by) w.dr[j].y += gpv.y;
+            if (j == bz) w.dr[j].z += gpv.z;
+            if (j == bw) w.dr[j].w += gpv.w;
         }
     }
     if (p.relu) {
-        for (int j = 0; j < cnt; j++) {
-            if (!(av[j].x > 0.f)) dr[j].x = 0.f;
-            if (!(av[j].y > 0.f)) dr[j].y = 0.f;
-            if (!(av[j].z > 0.f)) dr[j].z = 0.f;
-            if (!(av[j].w > 0.f)) dr[j].w = 0.f;
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            if (!(av[j].x > 0.f)) w.dr[j].x = 0.f;
+            if (!(av[j].y > 0.f)) w.dr[j].y = 0.f;
+            if (!(av[j].z > 0.f)) w.dr[j].z = 0.f;
+            if (!(av[j].w > 0.f)) w.dr[j].w = 0.f;
         }
     }
-    return cnt;
+}
+
+E3B_DEVINL void load_nc4(const float* p, size_t nc, float4& v, float dflt) {
+    v = p ? *reinterpret_cast<const float4*>(p + nc) : make_float4(dflt, dflt, dflt, dflt);
 }
 
 // grid: (blocks per plane, Cq, N)
+template <int WD, int WH, int WW>
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p)
 {
     const int cq = blockIdx.y, n = blockIdx.z;
     const size_t nc = ((size_t)n * p.Cq + cq) * 4;
-    const float4 mu = *reinterpret_cast<const float4*>(p.mean + nc);
-    const float4 rs = *reinterpret_cast<const float4*>(p.rstd + nc);
+    float4 mu, rs, sc, sh;
+    load_nc4(p.mean, nc, mu, 0.f); load_nc4(p.rstd, nc, rs, 1.f);
+    load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
     const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < wins; i += (size_t)gridDim.x * blockDim.x) {
         const int xw = (int)(i % p.Ww), yw = (int)((i / p.Ww) % p.Hw), zw = (int)(i / ((size_t)p.Ww * p.Hw));
-        float4 dr[8], xh[8]; size_t offs[8]; int slot[8];
-        const int cnt = load_window(p, n, cq, zw, yw, xw, mu, rs, dr, xh, offs, slot);
-        for (int j = 0; j < cnt; j++) {
-            s1[0] += dr[j].x; s1[1] += dr[j].y; s1[2] += dr[j].z; s1[3] += dr[j].w;
-            s2[0] += dr[j].x * xh[j].x; s2[1] += dr[j].y * xh[j].y; s2[2] += dr[j].z * xh[j].z; s2[3] += dr[j].w * xh[j].w;
+        Window<WD, WH, WW> w;
+        load_window<WD, WH, WW>(p, n, cq, zw, yw, xw, mu, rs, sc, sh, w);
+#pragma unroll
+        for (int j = 0; j < WD * WH * WW; j++) {
+            s1[0] += w.dr[j].x; s1[1] += w.dr[j].y; s1[2] += w.dr[j].z; s1[3] += w.dr[j].w;
+            s2[0] += w.dr[j].x * w.xh[j].x; s2[1] += w.dr[j].y * w.xh[j].y;
+            s2[2] += w.dr[j].z * w.xh[j].z; s2[3] += w.dr[j].w * w.xh[j].w;
         }
     }
     __shared__ float red[8][8];
@@ -431,14 +460,16 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ sums, const 
     if (dbias) dbias[c] = (float)dbi;
 }
 
+template <int WD, int WH, int WW>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
 {
+    constexpr int NS = WD * WH * WW;
     const int cq = blockIdx.y, n = blockIdx.z;
     const size_t nc = ((size_t)n * p.Cq + cq) * 4;
-    const float4 mu = *reinterpret_cast<const float4*>(p.mean + nc);
-    const float4 rs = *reinterpret_cast<const float4*>(p.rstd + nc);
-    const float4 m1 = *reinterpret_cast<const float4*>(p.m1 + nc);
-    const float4 m2 = *reinterpret_cast<const float4*>(p.m2 + nc);
+    float4 mu, rs, sc, sh, m1, m2;
+    load_nc4(p.mean, nc, mu, 0.f); load_nc4(p.rstd, nc, rs, 1.f);
+    load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
+    load_nc4(p.m1, nc, m1, 0.f); load_nc4(p.m2, nc, m2, 0.f);
     float4 ga = make_float4(1.f, 1.f, 1.f, 1.f);
     if (p.gamma) {
         const int c = cq * 4;
@@ -446,44 +477,32 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
         ga.z = c + 2 < p.C ? p.gamma[c + 2] : 0.f; ga.w = c + 3 < p.C ? p.gamma[c + 3] : 0.f;
     }
     const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
-    const int nslots = p.wd * p.wh * p.ww;
+    const size_t base = ((size_t)n * p.Cq + cq) * p.D;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < wins; i += (size_t)gridDim.x * blockDim.x) {
         const int xw = (int)(i % p.Ww), yw = (int)((i / p.Ww) % p.Hw), zw = (int)(i / ((size_t)p.Ww * p.Hw));
-        float4 dr[8], xh[8]; size_t offs[8]; int slot[8];
-        const int cnt = load_window(p, n, cq, zw, yw, xw, mu, rs, dr, xh, offs, slot);
-        if (p.s2d) {
-            // every tap plane of the coarse voxel is written (absent fine voxels -> 0)
-            for (int s = 0; s < nslots; s++)
-                p.dy[(((size_t)n * nslots + s) * p.Cq + cq) * wins + i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int j = 0; j < cnt; j++) {
-            float4 o;
-            o.x = rs.x * (ga.x * dr[j].x - m1.x - xh[j].x * m2.x);
-            o.y = rs.y * (ga.y * dr[j].y - m1.y - xh[j].y * m2.y);
-            o.z = rs.z * (ga.z * dr[j].z - m1.z - xh[j].z * m2.z);
-            o.w = rs.w * (ga.w * dr[j].w - m1.w - xh[j].w * m2.w);
-            // dy is the MMA operand of dgrad and wgrad: store it rounded to TF32
-            o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
-            if (p.s2d) p.dy[(((size_t)n * nslots + slot[j]) * p.Cq + cq) * wins + i] = o;
-            else p.dy[offs[j]] = o;
-            if (p.dy_pl) {
-                if (p.s2d) {
-                    // (N, Dw, 1, nslots*Cp, Hw, Wwp): channel = slot*Cp + c on the coarse grid
-                    store_planar(p.dy_pl, o, n, slot[j] * p.Cq + cq, nslots * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
-                } else {
-                    const int sz = slot[j] / (p.wh * p.ww), sy = (slot[j] / p.ww) % p.wh, sx = slot[j] % p.ww;
-                    store_planar_shifted(p.dy_pl, o, n, cq, p.C, p.D, p.H, p.W, zw * p.wd + sz, yw * p.wh + sy,
-                                         xw * p.ww + sx, p.pl_kw, p.pl_pw, p.pl_Wx);
-                }
+        Window<WD, WH, WW> w;
+        load_window<WD, WH, WW>(p, n, cq, zw, yw, xw, mu, rs, sc, sh, w);
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (w.ok[j]) {
+                o.x = rs.x * (ga.x * w.dr[j].x - m1.x - w.xh[j].x * m2.x);
+                o.y = rs.y * (ga.y * w.dr[j].y - m1.y - w.xh[j].y * m2.y);
+                o.z = rs.z * (ga.z * w.dr[j].z - m1.z - w.xh[j].z * m2.z);
+                o.w = rs.w * (ga.w * w.dr[j].w - m1.w - w.xh[j].w * m2.w);
+                // dy is the MMA operand of dgrad and wgrad: store it rounded to TF32
+                o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
             }
-        }
-        if (p.s2d && p.dy_pl) {
-            // fine voxels cropped away by autocrop (absent slots): their planar entries must be 0
-            bool present[8] = {false, false, false, false, false, false, false, false};
-            for (int j = 0; j < cnt; j++) present[slot[j]] = true;
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < nslots; s++)
-                if (!present[s]) store_planar(p.dy_pl, z4, n, s * p.Cq + cq, nslots * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
+            const int dz = j / (WH * WW), dyy = (j / WW) % WH, dx = j % WW;
+            if (p.s2d) {
+                // every tap plane of the coarse voxel is written (fine voxels cropped away by autocrop -> 0)
+                p.dy[(((size_t)n * NS + j) * p.Cq + cq) * wins + i] = o;
+                if (p.dy_pl) store_planar(p.dy_pl, o, n, j * p.Cq + cq, NS * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
+            } else if (w.ok[j]) {
+                const int z = zw * WD + dz, yy = yw * WH + dyy, x = xw * WW + dx;
+                p.dy[((base + z) * p.H + yy) * p.W + x] = o;
+                if (p.dy_pl) store_planar_shifted(p.dy_pl, o, n, cq, p.C, p.D, p.H, p.W, z, yy, x, p.pl_kw, p.pl_pw, p.pl_Wx);
+            }
         }
     }
 }
@@ -726,7 +745,9 @@ int e3b_norm_act(const float* y, const float* scale, const float* shift, float* 
 
 static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)
 {
-    p.a = reinterpret_cast<const float4*>(a->a); p.y = reinterpret_cast<const float4*>(a->y);
+    p.y = reinterpret_cast<const float4*>(a->y);
+    p.scale = a->scale; p.shift = a->shift;
+    if ((a->scale == nullptr) != (a->shift == nullptr)) return set_error("norm_bwd: scale and shift go together");
     p.g0 = reinterpret_cast<const float4*>(a->g0); p.g1 = reinterpret_cast<const float4*>(a->g1);
     p.gp = reinterpret_cast<const float4*>(a->gp);
     p.N = a->N; p.C = a->C; p.Cq = cpad8(a->C) / 4; p.D = a->D; p.H = a->H; p.W = a->W;
@@ -755,7 +776,12 @@ int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* a, void* stream)
     int bx = (int)((wins + 255) / 256);
     int cap = (8 * num_sms()) / (p.Cq * a->N); if (cap < 1) cap = 1;
     if (bx > cap) bx = cap;
-    norm_bwd_reduce_kernel<<<dim3(bx, p.Cq, a->N), 256, 0, (cudaStream_t)stream>>>(p);
+    const dim3 grid(bx, p.Cq, a->N);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.wd == 1 && p.wh == 1 && p.ww == 1) norm_bwd_reduce_kernel<1, 1, 1><<<grid, 256, 0, st>>>(p);
+    else if (p.wd == 2 && p.wh == 2 && p.ww == 2) norm_bwd_reduce_kernel<2, 2, 2><<<grid, 256, 0, st>>>(p);
+    else if (p.wd == 1 && p.wh == 2 && p.ww == 2) norm_bwd_reduce_kernel<1, 2, 2><<<grid, 256, 0, st>>>(p);
+    else return set_error("norm_bwd: unsupported window %dx%dx%d", p.wd, p.wh, p.ww);
     return check_launch("norm_bwd_reduce");
 }
 
@@ -778,7 +804,12 @@ int e3b_norm_bwd_apply(const e3b_norm_bwd_args* a, void* stream)
     int bx = (int)((wins + 255) / 256);
     int cap = (16 * num_sms()) / (p.Cq * a->N); if (cap < 1) cap = 1;
     if (bx > cap) bx = cap;
-    norm_bwd_apply_kernel<<<dim3(bx, p.Cq, a->N), 256, 0, (cudaStream_t)stream>>>(p);
+    const dim3 grid(bx, p.Cq, a->N);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.wd == 1 && p.wh == 1 && p.ww == 1) norm_bwd_apply_kernel<1, 1, 1><<<grid, 256, 0, st>>>(p);
+    else if (p.wd == 2 && p.wh == 2 && p.ww == 2) norm_bwd_apply_kernel<2, 2, 2><<<grid, 256, 0, st>>>(p);
+    else if (p.wd == 1 && p.wh == 2 && p.ww == 2) norm_bwd_apply_kernel<1, 2, 2><<<grid, 256, 0, st>>>(p);
+    else return set_error("norm_bwd: unsupported window %dx%dx%d", p.wd, p.wh, p.ww);
     return check_launch("norm_bwd_apply");
 }
 

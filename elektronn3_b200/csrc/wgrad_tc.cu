@@ -339,9 +339,8 @@ static int plan_wgrad(const e3b_wgrad_args* a, WgradParams& p)
     // tiles cover the conv INPUT width (the shifted gradient copies are indexed by the input x)
     p.tiles_x = (a->W + kSeg - 1) / kSeg; p.tiles_y = (p.Ho + p.TY - 1) / p.TY;
     p.total_vt = p.tiles_x * p.tiles_y * p.D * a->N;
-    int S = (2 * num_sms()) / p.units; if (S < 1) S = 1;
+    int S = (2 * num_sms()) / p.units; if (S < 1) S = 1;       // ~2 CTAs per SM (smem allows one resident: two waves)
     if (S > p.total_vt) S = p.total_vt;
-    if (S > 64) S = 64;
     p.S = S;
     return 0;
 }

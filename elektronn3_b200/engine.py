@@ -521,7 +521,9 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True, planar=True,
     dev = a.t.device
     N, Cp = a.N, cpad8(C)
     args = L.NormBwdArgs()
-    args.a, args.y = a.ptr, u.y.ptr
+    args.y = u.y.ptr
+    if u.nstate is not None:
+        args.scale, args.shift = u.nstate.scale.data_ptr(), u.nstate.shift.data_ptr()
     args.g0, args.g1, args.gp = (g0.ptr if g0 is not None else None, g1.ptr if g1 is not None else None,
                                  gp.ptr if gp is not None else None)
     args.N, args.C, args.D, args.H, args.W = N, C, a.D, a.H, a.W

@@ -127,13 +127,15 @@ int e3b_norm_act(const float* y, const float* scale, const float* shift, float* 
                  int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, void* stream);
 
 /* backward of conv -> norm -> relu [-> pool] as autograd derives it:
- *   dr  = (g0 + g1 + unpool(gp)) * [a > 0]          g0,g1: same extents as a (either may be NULL)
+ *   dr  = (g0 + g1 + unpool(gp)) * [a > 0]          g0,g1: same extents as y (either may be NULL)
  *   reduce:   sums[n][c] = (sum dr, sum dr*xhat)                      (fp64 atomics, [N][pad8(C)][2])
  *   finalize: m1,m2 per (n,c); dgamma, dbeta, dbias (conv bias grad)
  *   apply:    dy = rstd * (gamma*dr - m1 - xhat*m2)      written QP, or space-to-depth (s2d=1:
  *             channel = tap*pad8(C)+c on the grid (ceil(D/sd),..)) for the transposed conv backward. */
 typedef struct e3b_norm_bwd_args {
-    const float* a; const float* y;
+    const float* y;                            /* conv output (pre-norm); with scale == NULL: the activation itself */
+    const float* scale; const float* shift;    /* forward affine [N][pad8(C)] from e3b_norm_finalize: the activation
+                                                  a = tf32(relu(y*scale+shift)) is recomputed, not re-read */
     const float* g0; const float* g1; const float* gp;
     int32_t N, C, D, H, W;
     int32_t pk_d, pk_h, pk_w;                  /* pooling kernel of gp (if gp) */
