@@ -612,42 +612,51 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restr
 }
 
 // ws[co][c] += sum_v dl[v][co]*a[v][c] ; ws[Co*Cp + co] += sum_v dl[v][co].   grid (chunks, Cq)
+// One pass over the activations: every thread keeps all Co partial sums of its 4 channels.
+template <int CO>
 __global__ void __launch_bounds__(256) head_bwd_w_kernel(const float* __restrict__ dl, const float4* __restrict__ a,
                                                          double* __restrict__ ws, int N, int Cq, int Co, size_t S)
 {
     const int cq = blockIdx.y, Cp = Cq * 4;
     const size_t total = (size_t)N * S;
-    __shared__ float red[8][4];
-    for (int co = 0; co < Co; co++) {
-        float s[4] = {0, 0, 0, 0}, sb = 0.f;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-            const size_t n = i / S, v = i % S;
-            const float g = dl[(n * Co + co) * S + v];
-            const float4 av = a[(n * Cq + cq) * S + v];
-            s[0] = fmaf(g, av.x, s[0]); s[1] = fmaf(g, av.y, s[1]); s[2] = fmaf(g, av.z, s[2]); s[3] = fmaf(g, av.w, s[3]);
-            sb += g;
+    float acc[CO][4], sb[CO];
+#pragma unroll
+    for (int co = 0; co < CO; co++) { acc[co][0] = acc[co][1] = acc[co][2] = acc[co][3] = 0.f; sb[co] = 0.f; }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = i / S, v = i % S;
+        const float4 av = a[(n * Cq + cq) * S + v];
+#pragma unroll
+        for (int co = 0; co < CO; co++) {
+            if (co < Co) {
+                const float g = dl[(n * Co + co) * S + v];
+                acc[co][0] = fmaf(g, av.x, acc[co][0]); acc[co][1] = fmaf(g, av.y, acc[co][1]);
+                acc[co][2] = fmaf(g, av.z, acc[co][2]); acc[co][3] = fmaf(g, av.w, acc[co][3]);
+                sb[co] += g;
+            }
         }
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    }
+    __shared__ float red[8][CO * 5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int co = 0; co < CO; co++) {
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            for (int j = 0; j < 4; j++) acc[co][j] += __shfl_xor_sync(0xffffffffu, acc[co][j], o);
+            sb[co] += __shfl_xor_sync(0xffffffffu, sb[co], o);
         }
-        __syncthreads();
-        if (lane == 0) { for (int j = 0; j < 4; j++) red[warp][j] = s[j]; }
-        __shared__ float redb[8];
-        if (lane == 0) redb[warp] = sb;
-        __syncthreads();
-        if (threadIdx.x < 4) {
-            double t = 0.0;
-            for (int w = 0; w < 8; w++) t += (double)red[w][threadIdx.x];
-            atomicAdd(ws + (size_t)co * Cp + cq * 4 + threadIdx.x, t);
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) red[warp][co * 5 + j] = acc[co][j];
+            red[warp][co * 5 + 4] = sb[co];
         }
-        if (threadIdx.x == 4 && cq == 0) {
-            double t = 0.0;
-            for (int w = 0; w < 8; w++) t += (double)redb[w];
-            atomicAdd(ws + (size_t)Co * Cp + co, t);
-        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < Co * 5; t += blockDim.x) {
+        double sum = 0.0;
+        for (int w = 0; w < 8; w++) sum += (double)red[w][t];
+        const int co = t / 5, j = t % 5;
+        if (j < 4) atomicAdd(ws + (size_t)co * Cp + cq * 4 + j, sum);
+        else if (cq == 0) atomicAdd(ws + (size_t)Co * Cp + co, sum);
     }
 }
 
@@ -838,8 +847,9 @@ int e3b_head_bwd(const float* dl, const float* a, const float* w, float* da, flo
     }
     cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(double) * ((size_t)Co * Cp + Co), st);
     if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
-    int bx = (2 * num_sms()) / Cq; if (bx < 1) bx = 1;
-    head_bwd_w_kernel<<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const float4*>(a), workspace, N, Cq, Co, S);
+    int bx = (8 * num_sms()) / Cq; if (bx < 1) bx = 1;
+    if (Co <= 4) head_bwd_w_kernel<4><<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const float4*>(a), workspace, N, Cq, Co, S);
+    else head_bwd_w_kernel<kHeadMaxCo><<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const float4*>(a), workspace, N, Cq, Co, S);
     if (check_launch("head_bwd_w")) return 1;
     head_bwd_finish_kernel<<<(Co * C + 127) / 128 + 1, 128, 0, st>>>(workspace, dw, db, C, Cp, Co);
     return check_launch("head_bwd_finish");
