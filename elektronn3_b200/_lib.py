@@ -56,6 +56,7 @@ class NormBwdArgs(ctypes.Structure):
     _fields_ = [
         ('y', c_void_p), ('scale', c_void_p), ('shift', c_void_p),
         ('g0', c_void_p), ('g1', c_void_p), ('gp', c_void_p),
+        ('pool_idx', c_void_p),
         ('N', c_i32), ('C', c_i32), ('D', c_i32), ('H', c_i32), ('W', c_i32),
         ('pk_d', c_i32), ('pk_h', c_i32), ('pk_w', c_i32),
         ('mode', c_i32), ('G', c_i32), ('eps', c_float),
@@ -96,11 +97,12 @@ SIGNATURES = {
     'e3b_packed_weight_floats': (c_i64, [c_int] * 7),
     'e3b_pack_weights': (c_int, [c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     'e3b_conv': (c_int, [ctypes.POINTER(ConvArgs), c_void_p]),
+    'e3b_debug_conv_counters': (c_int, [c_void_p, c_int]),
     'e3b_wgrad_workspace_floats': (c_i64, [ctypes.POINTER(WgradArgs)]),
     'e3b_wgrad': (c_int, [ctypes.POINTER(WgradArgs), c_void_p]),
     'e3b_norm_finalize': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_i64, c_void_p, c_void_p, c_float,
                                   c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    'e3b_norm_act': (c_int, [c_void_p] * 7 + [c_int] * 9 + [c_void_p]),
+    'e3b_norm_act': (c_int, [c_void_p] * 8 + [c_int] * 9 + [c_void_p]),
     'e3b_norm_bwd_reduce': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_finalize': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_apply': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),

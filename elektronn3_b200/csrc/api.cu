@@ -57,6 +57,8 @@ int e3b_conv(const e3b_conv_args* a, void* stream)
     return launch_conv_tc(a, (cudaStream_t)stream);
 }
 
+int e3b_debug_conv_counters(unsigned long long* out16, int reset) { return conv_debug_read(out16, reset); }
+
 int64_t e3b_wgrad_workspace_floats(const e3b_wgrad_args* a)
 {
     if (!a) return -1;

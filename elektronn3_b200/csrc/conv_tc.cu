@@ -21,6 +21,7 @@
 //    of tile i overlaps the MMAs of tile i+1.  CTAs are persistent over a static tile schedule.
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace e3b {
 
@@ -48,6 +49,7 @@ struct ConvTcParams {
     float* dst1;                 // ... the rest to dst1 (dgrad of a virtual-concat conv)
     int cq0_alloc, cq1_alloc;    // planes allocated in dst0 / dst1
     int relu;
+    int debug;                   // accumulate role timings into g_conv_dbg
     int round_tf32;              // round the stored output to TF32 (it feeds the next MMA unrounded otherwise)
     double* stats;               // [N][Cstat][2] sum / sumsq (fp64 atomics) or null
     int Cstat;
@@ -60,6 +62,11 @@ struct ConvTcParams {
 
 static constexpr int kStatSlots = 256;
 
+// Optional cycle accounting of the pipeline roles (scripts/conv_pipeline_debug.py): enabled per launch.
+__device__ unsigned long long g_conv_dbg[16];
+#define DBG_T0(var) long long var = 0; if (p.debug) var = clock64()
+#define DBG_ACC(slot, var) if (p.debug) dbg[slot] += (unsigned long long)(clock64() - var)
+
 // per-CTA statistics accumulators -> global [N][Cstat][2] (fp64 atomics: a few hundred per CTA, not per tile)
 E3B_DEVINL void flush_stats(const ConvTcParams& p, double* cta_stats, int n, int nt, int etid) {
     const int nslots = p.scatter ? (p.Cup < kStatSlots ? p.Cup : kStatSlots) : (p.NT < kStatSlots ? p.NT : kStatSlots);
@@ -69,6 +76,30 @@ E3B_DEVINL void flush_stats(const ConvTcParams& p, double* cta_stats, int n, int
         const double v = cta_stats[i];
         cta_stats[i] = 0.0;
         if (ch < p.Cstat && v != 0.0) atomicAdd(p.stats + ((size_t)n * p.Cstat + ch) * 2 + (i & 1), v);
+    }
+}
+
+// Issue the TZ plane MMAs of one stencil tap (fully unrolled: two uniform adds per MMA).
+template <int TZ>
+E3B_DEVINL void issue_tap_planes(uint32_t acc, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accum, uint32_t plane_step,
+                                 uint32_t nt)
+{
+#pragma unroll
+    for (int pl = 0; pl < TZ; pl++) umma_tf32(acc + (uint32_t)pl * nt, ad + (uint64_t)((uint32_t)pl * plane_step), bd, idesc, accum);
+}
+
+E3B_DEVINL void issue_tap(int tz, uint32_t acc, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accum, uint32_t plane_step,
+                          uint32_t nt)
+{
+    switch (tz) {
+    case 1: issue_tap_planes<1>(acc, ad, bd, idesc, accum, plane_step, nt); break;
+    case 2: issue_tap_planes<2>(acc, ad, bd, idesc, accum, plane_step, nt); break;
+    case 3: issue_tap_planes<3>(acc, ad, bd, idesc, accum, plane_step, nt); break;
+    case 4: issue_tap_planes<4>(acc, ad, bd, idesc, accum, plane_step, nt); break;
+    case 5: issue_tap_planes<5>(acc, ad, bd, idesc, accum, plane_step, nt); break;
+    case 6: issue_tap_planes<6>(acc, ad, bd, idesc, accum, plane_step, nt); break;
+    case 7: issue_tap_planes<7>(acc, ad, bd, idesc, accum, plane_step, nt); break;
+    default: issue_tap_planes<8>(acc, ad, bd, idesc, accum, plane_step, nt); break;
     }
 }
 
@@ -98,6 +129,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     uint64_t* acc_empty = acc_full + 2;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     __shared__ double cta_stats[kStatSlots * 2];
+    __shared__ uint32_t tap_off[27];         // halo-tile offset of every stencil tap, in 16-byte (voxel) units
+    if (threadIdx.x < 27) {
+        const int tp = threadIdx.x;
+        tap_off[tp] = (uint32_t)(((tp / (p.kh * p.kw)) * p.HY + (tp / p.kw) % p.kh) * p.HX + tp % p.kw);
+    }
     for (int i = threadIdx.x; i < kStatSlots * 2; i += blockDim.x) cta_stats[i] = 0.0;
 
     const int warp = threadIdx.x >> 5;
@@ -123,12 +159,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            unsigned long long dbg[16] = {0};
+            DBG_T0(t_all);
             uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 int nt, n, z0, y0, x0;
                 decode_tile(p, t, nt, n, z0, y0, x0);
                 for (int c = 0; c < nchunks; c++) {
+                    DBG_T0(t0);
                     mbar_wait(&a_empty[sa], pa ^ 1);
+                    DBG_ACC(0, t0);
                     mbar_arrive_expect_tx(&a_full[sa], p.a_stage_bytes);
                     if (c < p.chunks0)
                         tma_load_5d(a_base + (size_t)sa * p.a_stage_bytes, &tmap0, &a_full[sa],
@@ -138,7 +178,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                                     (x0 - p.pw) * 4, y0 - p.ph, z0 - p.pd, (c - p.chunks0) * 2, n);
                     if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
                     for (int g = 0; g < ngroups; g++) {
+                        DBG_T0(t1);
                         mbar_wait(&b_empty[sb], pb ^ 1);
+                        DBG_ACC(1, t1);
                         mbar_arrive_expect_tx(&b_full[sb], p.b_stage_bytes);
                         const float* src = p.wpk + ((size_t)(nt * nchunks + c) * ntaps + (size_t)g * p.TG) *
                                                        (size_t)(2 * p.NT * 4);
@@ -147,6 +189,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                     }
                 }
             }
+            DBG_ACC(2, t_all);
+            if (p.debug) for (int i = 0; i < 3; i++) atomicAdd(&g_conv_dbg[i], dbg[i]);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -159,38 +203,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         const uint32_t plane_step = (uint32_t)(p.HY * p.HX);
         const uint32_t tap_step_b = (uint32_t)(2 * p.NT);
         const bool leader = elect_one();
+        unsigned long long dbg[16] = {0};
+        DBG_T0(t_all);
         uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it++) {
             const uint32_t buf = it & 1, use = it >> 1;
+            DBG_T0(t0);
             mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+            DBG_ACC(3, t0);
             tc_fence_after();
             const uint32_t acc = tmem_base + buf * 256;
             for (int c = 0; c < nchunks; c++) {
+                DBG_T0(t1);
                 mbar_wait(&a_full[sa], pa);
+                DBG_ACC(4, t1);
                 tc_fence_after();
                 const uint32_t a16 = smem_u32(a_base + (size_t)sa * p.a_stage_bytes) >> 4;
-                int dz = 0, dy = 0, dx = 0;
+                int tap = 0;
                 for (int g = 0; g < ngroups; g++) {
+                    DBG_T0(t2);
                     mbar_wait(&b_full[sb], pb);
+                    DBG_ACC(5, t2);
                     tc_fence_after();
+                    DBG_T0(t3);
                     const uint32_t b16 = smem_u32(b_base + (size_t)sb * p.b_stage_bytes) >> 4;
                     if (leader) {
                         uint64_t bd = b_tmpl + b16;
-                        for (int tg = 0; tg < p.TG; tg++) {
-                            uint64_t ad = a_tmpl + (a16 + (uint32_t)((dz * p.HY + dy) * p.HX + dx));
-                            uint32_t d = acc;
-                            const uint32_t accum = (c | g | tg) ? 1u : 0u;
-                            for (int pl = 0; pl < p.TZ; pl++) {
-                                umma_tf32(d, ad, bd, idesc, accum);
-                                ad += plane_step;
-                                d += (uint32_t)p.NT;
-                            }
+                        const uint64_t a_stage = a_tmpl + a16;
+                        for (int tg = 0; tg < p.TG; tg++, tap++) {
+                            issue_tap(p.TZ, acc, a_stage + tap_off[tap], bd, idesc, (c | tap) ? 1u : 0u, plane_step, (uint32_t)p.NT);
                             bd += tap_step_b;
-                            if (++dx == p.kw) { dx = 0; if (++dy == p.kh) { dy = 0; ++dz; } }
                         }
                         umma_commit(&b_empty[sb]);
                     }
                     __syncwarp();
+                    DBG_ACC(6, t3);
                     if (++sb == (uint32_t)p.SB) { sb = 0; pb ^= 1; }
                 }
                 if (leader) umma_commit(&a_empty[sa]);
@@ -200,6 +247,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             if (leader) umma_commit(&acc_full[buf]);
             __syncwarp();
         }
+        DBG_ACC(7, t_all);
+        if (p.debug && leader) for (int i = 3; i < 8; i++) atomicAdd(&g_conv_dbg[i], dbg[i]);
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -210,6 +259,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         const int bcol = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
         int cur_n = -1, cur_nt = -1;
         uint32_t it = 0;
+        unsigned long long dbg[16] = {0};
+        DBG_T0(t_all);
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it++) {
             const uint32_t buf = it & 1, use = it >> 1;
             int nt, n, z0, y0, x0;
@@ -221,7 +272,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                 named_bar_sync(1, 128);
                 cur_n = n; cur_nt = nt;
             }
+            DBG_T0(t0);
             mbar_wait(&acc_full[buf], use & 1);
+            DBG_ACC(8, t0);
             tc_fence_after();
             const int y = y0 + ry, x = x0 + rx;
             const bool valid = (y < p.Ho) && (x < p.Wo);
@@ -332,6 +385,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        DBG_ACC(9, t_all);
+        if (p.debug && etid == 0) for (int i = 8; i < 10; i++) atomicAdd(&g_conv_dbg[i], dbg[i]);
         if (p.stats) {
             named_bar_sync(1, 128);
             if (cur_n >= 0) flush_stats(p, cta_stats, cur_n, cur_nt, etid);
@@ -407,6 +462,29 @@ int num_sms()
     return g_num_sms;
 }
 
+int conv_debug_read(unsigned long long* out16, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out16, g_conv_dbg, sizeof(unsigned long long) * 16);
+    if (e != cudaSuccess) return set_error("conv_debug_read: %s", cudaGetErrorString(e));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_conv_dbg, z, sizeof(z));
+    }
+    return 0;
+}
+
+// dynamic shared memory the kernel may request: the 227 KB opt-in limit minus its static shared memory
+static int conv_max_dyn_smem()
+{
+    static int v = 0;
+    if (!v) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, conv_tc_kernel) != cudaSuccess) return 0;
+        v = 227 * 1024 - (int)fa.sharedSizeBytes;
+    }
+    return v;
+}
+
 int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
 {
     ConvTcParams p;
@@ -441,7 +519,8 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
     while (tg > 1 && (size_t)tg * 2 * p.NT * 16 > 40 * 1024) tg /= 3;
     p.TG = tg;
     p.b_stage_bytes = (uint32_t)(tg * 2 * p.NT * 16);
-    const size_t budget = 227 * 1024 - 1024 - 256 - sizeof(double) * 2 * kStatSlots - 64;   // static cta_stats
+    if (conv_max_dyn_smem() <= 0) return set_error("conv: cudaFuncGetAttributes failed");
+    const size_t budget = (size_t)conv_max_dyn_smem() - 1024 - 256;     // barriers + alignment slack
     int sa = 2, sb = 2;
     // grow depth while it fits (A first up to 4, then B up to 4)
     for (;;) {
@@ -459,6 +538,7 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
     p.cq1_alloc = a->dst1 ? e3b_cpad(a->Cd1) / 4 : 0;
     p.cq0 = a->dst1 ? p.cq0_alloc : (1 << 30);
     p.relu = a->relu; p.round_tf32 = a->round_tf32;
+    p.debug = getenv("E3B_CONV_DEBUG") != nullptr;
     p.stats = a->stats; p.Cstat = a->stats_channels;
     p.scatter = a->scatter; p.sd = a->sd; p.sh = a->sh; p.sw = a->sw;
     p.Cup = a->scatter ? e3b_cpad(a->Cd0) : 1;
@@ -481,7 +561,7 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
     static bool configured = false;
     if (!configured) {
         // static shared memory (cta_stats) counts against the 227 KB per-CTA limit
-        const int max_dyn = 227 * 1024 - (int)(sizeof(double) * 2 * kStatSlots) - 64;
+        const int max_dyn = conv_max_dyn_smem();
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
         if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;

@@ -219,60 +219,108 @@ E3B_DEVINL void store_planar_shifted(float* __restrict__ pl, const float4& v, in
     }
 }
 
-__global__ void norm_act_kernel(const float4* __restrict__ y, const float* __restrict__ scale,
-                                const float* __restrict__ shift, float4* __restrict__ a, float4* __restrict__ pooled,
-                                float* __restrict__ a_pl, float* __restrict__ pooled_pl, int C,
-                                int N, int Cq, int D, int H, int W, int pkd, int pkh, int pkw, int relu)
+// grid: (planes * chunks-per-plane, Cq, N): one block works inside one (n, 4-channel plane, z) slice, so
+// the per-(n,c) constants are loaded once and only one integer division per thread is needed.
+struct NormActDev {
+    const float4* y; const float* scale; const float* shift;
+    float4* a; float4* pooled; float* a_pl; float* pooled_pl; uchar4* pool_idx;
+    int C, N, Cq, D, H, W, pkd, pkh, pkw, relu;
+    int Dp, Hp, Wp;
+};
+
+E3B_DEVINL float4 norm_relu_round(const float4& yv, const float4& sc, const float4& sh, bool affine, int relu)
 {
-    const int Wpl = (W + 3) & ~3;
-    const int Dp = (D + pkd - 1) / pkd, Hp = (H + pkh - 1) / pkh, Wp = (W + pkw - 1) / pkw;
-    const size_t total = (size_t)N * Cq * Dp * Hp * Wp;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        size_t r = i;
-        const int xp = (int)(r % Wp); r /= Wp;
-        const int yp = (int)(r % Hp); r /= Hp;
-        const int zp = (int)(r % Dp); r /= Dp;
-        const int cq = (int)(r % Cq);
-        const int n = (int)(r / Cq);
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (scale) {
-            sc = *reinterpret_cast<const float4*>(scale + ((size_t)n * Cq + cq) * 4);
-            sh = *reinterpret_cast<const float4*>(shift + ((size_t)n * Cq + cq) * 4);
-        }
-        float4 m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
-        const size_t base = ((size_t)n * Cq + cq) * D;
-        for (int dz = 0; dz < pkd; dz++) {
-            const int z = zp * pkd + dz; if (z >= D) break;
-            for (int dy = 0; dy < pkh; dy++) {
-                const int yy = yp * pkh + dy; if (yy >= H) break;
-                for (int dx = 0; dx < pkw; dx++) {
-                    const int x = xp * pkw + dx; if (x >= W) break;
-                    const size_t o = ((base + z) * H + yy) * W + x;
-                    float4 v = y[o];
-                    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                    // activations are MMA operands of the next conv: store them rounded to TF32
-                    v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
-                    if (a) a[o] = v;
-                    if (a_pl) store_planar(a_pl, v, n, cq, C, D, H, Wpl, z, yy, x);
-                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-                }
+    float4 v = yv;
+    if (affine) {
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    }
+    // activations are MMA operands of the next conv: store them rounded to TF32
+    v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
+    return v;
+}
+
+E3B_DEVINL void load_nc4(const float* p, size_t nc, float4& v, float dflt) {
+    v = p ? *reinterpret_cast<const float4*>(p + nc) : make_float4(dflt, dflt, dflt, dflt);
+}
+
+// a = tf32(relu(y*scale+shift)), no pooling: one voxel per thread
+__global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
+{
+    const int cq = blockIdx.y, n = blockIdx.z;
+    const int chunks = (p.H * p.W + 255) / 256;
+    const int z = blockIdx.x / chunks;
+    const int hw = (blockIdx.x % chunks) * 256 + threadIdx.x;
+    if (hw >= p.H * p.W) return;
+    const int yy = hw / p.W, x = hw % p.W;
+    const size_t nc = ((size_t)n * p.Cq + cq) * 4;
+    float4 sc, sh;
+    load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
+    const size_t o = ((((size_t)n * p.Cq + cq) * p.D + z) * p.H + yy) * p.W + x;
+    const float4 v = norm_relu_round(p.y[o], sc, sh, p.scale != nullptr, p.relu);
+    if (p.a) p.a[o] = v;
+    if (p.a_pl) store_planar(p.a_pl, v, n, cq, p.C, p.D, p.H, (p.W + 3) & ~3, z, yy, x);
+}
+
+// ... + ceil-mode max pooling: one pooling window per thread.  pool_idx records, per channel, the window
+// slot ((dz*pkh + dy)*pkw + dx) of the FIRST maximum in scan order (torch max_pool backward semantics), so
+// that the backward pass is a per-voxel kernel that never re-examines the window.
+__global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
+{
+    const int cq = blockIdx.y, n = blockIdx.z;
+    const int chunks = (p.Hp * p.Wp + 255) / 256;
+    const int zp = blockIdx.x / chunks;
+    const int hw = (blockIdx.x % chunks) * 256 + threadIdx.x;
+    if (hw >= p.Hp * p.Wp) return;
+    const int yp = hw / p.Wp, xp = hw % p.Wp;
+    const size_t nc = ((size_t)n * p.Cq + cq) * 4;
+    float4 sc, sh;
+    load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
+    const size_t base = ((size_t)n * p.Cq + cq) * p.D;
+    const int Wpl = (p.W + 3) & ~3;
+    float4 m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
+    uchar4 idx = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++) {
+        const int z = zp * p.pkd + dz;
+        if (dz >= p.pkd || z >= p.D) continue;
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++) {
+            const int yy = yp * p.pkh + dy;
+            if (dy >= p.pkh || yy >= p.H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                const int x = xp * p.pkw + dx;
+                if (dx >= p.pkw || x >= p.W) continue;
+                const size_t o = ((base + z) * p.H + yy) * p.W + x;
+                const float4 v = norm_relu_round(p.y[o], sc, sh, p.scale != nullptr, p.relu);
+                if (p.a) p.a[o] = v;
+                if (p.a_pl) store_planar(p.a_pl, v, n, cq, p.C, p.D, p.H, Wpl, z, yy, x);
+                const unsigned char slot = (unsigned char)((dz * p.pkh + dy) * p.pkw + dx);
+                if (v.x > m.x) { m.x = v.x; idx.x = slot; }
+                if (v.y > m.y) { m.y = v.y; idx.y = slot; }
+                if (v.z > m.z) { m.z = v.z; idx.z = slot; }
+                if (v.w > m.w) { m.w = v.w; idx.w = slot; }
             }
         }
-        if (pooled) pooled[i] = m;
-        if (pooled_pl) store_planar(pooled_pl, m, n, cq, C, Dp, Hp, (Wp + 3) & ~3, zp, yp, xp);
     }
+    const size_t op = ((((size_t)n * p.Cq + cq) * p.Dp + zp) * p.Hp + yp) * p.Wp + xp;
+    if (p.pooled) p.pooled[op] = m;
+    if (p.pool_idx) p.pool_idx[op] = idx;
+    if (p.pooled_pl) store_planar(p.pooled_pl, m, n, cq, p.C, p.Dp, p.Hp, (p.Wp + 3) & ~3, zp, yp, xp);
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward of norm -> relu [-> pool]
+// backward of norm -> relu [-> pool]: per-voxel kernels
 // ------------------------------------------------------------------------------------------------
 struct NormBwdDev {
     const float4 *y, *g0, *g1, *gp;
+    const uchar4* pool_idx;
     const float *scale, *shift;              // forward affine (nullptr: y already is the activation)
-    int N, Cq, C, D, H, W, wd, wh, ww;     // window = pooling kernel (gp) or s2d stride, else 1
+    int N, Cq, C, D, H, W, wd, wh, ww;       // window = pooling kernel (gp) or s2d stride, else 1
     int Dw, Hw, Ww;
+    int Dg, Hg, Wg;                          // extents of the thread grid (s2d: the un-cropped fine grid)
     int relu, s2d;
     const float *gamma, *mean, *rstd, *m1, *m2;
     double* sums;
@@ -281,88 +329,39 @@ struct NormBwdDev {
     int pl_kw, pl_pw, pl_Wx;
 };
 
-// One pooling / space-to-depth window (WD x WH x WW voxels, compile-time so everything stays in
-// registers): the masked upstream gradient dr and xhat of every slot.
-//   dr = (g0 + g1 + unpool(gp)) * [a > 0]
-// `a` is not read from memory: it is recomputed bit-exactly from y (a = tf32_rn(relu(y*scale+shift)), the
-// arithmetic of norm_act_kernel), or y itself is the activation (scale == nullptr).
-template <int WD, int WH, int WW>
-struct Window {
-    static constexpr int N = WD * WH * WW;
-    float4 dr[N], xh[N];
-    bool ok[N];
-};
-
-template <int WD, int WH, int WW>
-E3B_DEVINL void load_window(const NormBwdDev& p, int n, int cq, int zw, int yw, int xw, const float4& mu, const float4& rs,
-                            const float4& sc, const float4& sh, Window<WD, WH, WW>& w)
+// the masked upstream gradient dr = (g0 + g1 + unpool(gp)) * [a > 0] and xhat of one voxel.
+// `a` is recomputed bit-exactly from y (the arithmetic of norm_act_kernel), never read.
+E3B_DEVINL void voxel_grad(const NormBwdDev& p, size_t o, int n, int cq, int z, int yy, int x, const float4& mu,
+                           const float4& rs, const float4& sc, const float4& sh, float4& dr, float4& xh)
 {
-    constexpr int NS = WD * WH * WW;
-    const size_t base = ((size_t)n * p.Cq + cq) * p.D;
-    float4 av[NS];
-#pragma unroll
-    for (int j = 0; j < NS; j++) {
-        const int dz = j / (WH * WW), dyy = (j / WW) % WH, dx = j % WW;
-        const int z = zw * WD + dz, yy = yw * WH + dyy, x = xw * WW + dx;
-        w.ok[j] = (z < p.D) && (yy < p.H) && (x < p.W);
-        w.dr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        w.xh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        av[j] = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
-        if (w.ok[j]) {
-            const size_t o = ((base + z) * p.H + yy) * p.W + x;
-            const float4 yv = p.y[o];
-            float4 a = yv;
-            if (p.scale) {
-                a.x = fmaf(yv.x, sc.x, sh.x); a.y = fmaf(yv.y, sc.y, sh.y);
-                a.z = fmaf(yv.z, sc.z, sh.z); a.w = fmaf(yv.w, sc.w, sh.w);
-                if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-                a.x = tf32_rn(a.x); a.y = tf32_rn(a.y); a.z = tf32_rn(a.z); a.w = tf32_rn(a.w);
-            }
-            av[j] = a;
-            w.xh[j] = make_float4((yv.x - mu.x) * rs.x, (yv.y - mu.y) * rs.y, (yv.z - mu.z) * rs.z, (yv.w - mu.w) * rs.w);
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.g0) g = p.g0[o];
-            if (p.g1) { const float4 t = p.g1[o]; g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w; }
-            w.dr[j] = g;
-        }
-    }
+    const float4 yv = p.y[o];
+    float4 a = yv;
+    if (p.scale) a = norm_relu_round(yv, sc, sh, true, p.relu);
+    xh = make_float4((yv.x - mu.x) * rs.x, (yv.y - mu.y) * rs.y, (yv.z - mu.z) * rs.z, (yv.w - mu.w) * rs.w);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.g0) g = p.g0[o];
+    if (p.g1) { const float4 t = p.g1[o]; g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w; }
     if (p.gp) {
-        // route the pooled gradient to the first maximum in (d,h,w) scan order (torch max_pool backward)
-        const float4 gpv = p.gp[((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw];
-        int bx = 0, by = 0, bz = 0, bw = 0;
-        float4 best = av[0];
-#pragma unroll
-        for (int j = 1; j < NS; j++) {
-            if (av[j].x > best.x) { best.x = av[j].x; bx = j; }
-            if (av[j].y > best.y) { best.y = av[j].y; by = j; }
-            if (av[j].z > best.z) { best.z = av[j].z; bz = j; }
-            if (av[j].w > best.w) { best.w = av[j].w; bw = j; }
-        }
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-            if (j == bx) w.dr[j].x += gpv.x;
-            if (j == by) w.dr[j].y += gpv.y;
-            if (j == bz) w.dr[j].z += gpv.z;
-            if (j == bw) w.dr[j].w += gpv.w;
-        }
+        const int zw = z / p.wd, yw = yy / p.wh, xw = x / p.ww;
+        const unsigned char slot = (unsigned char)(((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww));
+        const size_t ow = ((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw;
+        const uchar4 idx = p.pool_idx[ow];
+        const float4 gpv = p.gp[ow];
+        if (idx.x == slot) g.x += gpv.x;
+        if (idx.y == slot) g.y += gpv.y;
+        if (idx.z == slot) g.z += gpv.z;
+        if (idx.w == slot) g.w += gpv.w;
     }
     if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-            if (!(av[j].x > 0.f)) w.dr[j].x = 0.f;
-            if (!(av[j].y > 0.f)) w.dr[j].y = 0.f;
-            if (!(av[j].z > 0.f)) w.dr[j].z = 0.f;
-            if (!(av[j].w > 0.f)) w.dr[j].w = 0.f;
-        }
+        if (!(a.x > 0.f)) g.x = 0.f;
+        if (!(a.y > 0.f)) g.y = 0.f;
+        if (!(a.z > 0.f)) g.z = 0.f;
+        if (!(a.w > 0.f)) g.w = 0.f;
     }
+    dr = g;
 }
 
-E3B_DEVINL void load_nc4(const float* p, size_t nc, float4& v, float dflt) {
-    v = p ? *reinterpret_cast<const float4*>(p + nc) : make_float4(dflt, dflt, dflt, dflt);
-}
-
-// grid: (blocks per plane, Cq, N)
-template <int WD, int WH, int WW>
+// grid: (D * chunks-per-plane, Cq, N)
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p)
 {
     const int cq = blockIdx.y, n = blockIdx.z;
@@ -370,18 +369,17 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p
     float4 mu, rs, sc, sh;
     load_nc4(p.mean, nc, mu, 0.f); load_nc4(p.rstd, nc, rs, 1.f);
     load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
-    const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
+    const int HW = p.H * p.W;
+    const int total = p.D * HW;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < wins; i += (size_t)gridDim.x * blockDim.x) {
-        const int xw = (int)(i % p.Ww), yw = (int)((i / p.Ww) % p.Hw), zw = (int)(i / ((size_t)p.Ww * p.Hw));
-        Window<WD, WH, WW> w;
-        load_window<WD, WH, WW>(p, n, cq, zw, yw, xw, mu, rs, sc, sh, w);
-#pragma unroll
-        for (int j = 0; j < WD * WH * WW; j++) {
-            s1[0] += w.dr[j].x; s1[1] += w.dr[j].y; s1[2] += w.dr[j].z; s1[3] += w.dr[j].w;
-            s2[0] += w.dr[j].x * w.xh[j].x; s2[1] += w.dr[j].y * w.xh[j].y;
-            s2[2] += w.dr[j].z * w.xh[j].z; s2[3] += w.dr[j].w * w.xh[j].w;
-        }
+    const size_t base = ((size_t)n * p.Cq + cq) * (size_t)total;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += gridDim.x * blockDim.x) {
+        const int z = v / HW, r = v - z * HW, yy = r / p.W, x = r - yy * p.W;
+        float4 dr, xh;
+        voxel_grad(p, base + v, n, cq, z, yy, x, mu, rs, sc, sh, dr, xh);
+        s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
+        s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]);
+        s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
     }
     __shared__ float red[8][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -460,10 +458,9 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ sums, const 
     if (dbias) dbias[c] = (float)dbi;
 }
 
-template <int WD, int WH, int WW>
+// grid: (Dg * chunks-per-plane, Cq, N); (Dg,Hg,Wg) = (D,H,W), or the un-cropped fine grid for s2d output
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
 {
-    constexpr int NS = WD * WH * WW;
     const int cq = blockIdx.y, n = blockIdx.z;
     const size_t nc = ((size_t)n * p.Cq + cq) * 4;
     float4 mu, rs, sc, sh, m1, m2;
@@ -476,34 +473,37 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
         ga.x = c < p.C ? p.gamma[c] : 0.f; ga.y = c + 1 < p.C ? p.gamma[c + 1] : 0.f;
         ga.z = c + 2 < p.C ? p.gamma[c + 2] : 0.f; ga.w = c + 3 < p.C ? p.gamma[c + 3] : 0.f;
     }
-    const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
-    const size_t base = ((size_t)n * p.Cq + cq) * p.D;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < wins; i += (size_t)gridDim.x * blockDim.x) {
-        const int xw = (int)(i % p.Ww), yw = (int)((i / p.Ww) % p.Hw), zw = (int)(i / ((size_t)p.Ww * p.Hw));
-        Window<WD, WH, WW> w;
-        load_window<WD, WH, WW>(p, n, cq, zw, yw, xw, mu, rs, sc, sh, w);
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (w.ok[j]) {
-                o.x = rs.x * (ga.x * w.dr[j].x - m1.x - w.xh[j].x * m2.x);
-                o.y = rs.y * (ga.y * w.dr[j].y - m1.y - w.xh[j].y * m2.y);
-                o.z = rs.z * (ga.z * w.dr[j].z - m1.z - w.xh[j].z * m2.z);
-                o.w = rs.w * (ga.w * w.dr[j].w - m1.w - w.xh[j].w * m2.w);
-                // dy is the MMA operand of dgrad and wgrad: store it rounded to TF32
-                o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
-            }
-            const int dz = j / (WH * WW), dyy = (j / WW) % WH, dx = j % WW;
-            if (p.s2d) {
-                // every tap plane of the coarse voxel is written (fine voxels cropped away by autocrop -> 0)
-                p.dy[(((size_t)n * NS + j) * p.Cq + cq) * wins + i] = o;
-                if (p.dy_pl) store_planar(p.dy_pl, o, n, j * p.Cq + cq, NS * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
-            } else if (w.ok[j]) {
-                const int z = zw * WD + dz, yy = yw * WH + dyy, x = xw * WW + dx;
-                p.dy[((base + z) * p.H + yy) * p.W + x] = o;
-                if (p.dy_pl) store_planar_shifted(p.dy_pl, o, n, cq, p.C, p.D, p.H, p.W, z, yy, x, p.pl_kw, p.pl_pw, p.pl_Wx);
-            }
+    const int chunks = (p.Hg * p.Wg + 255) / 256;
+    const int z = blockIdx.x / chunks;
+    const int hw = (blockIdx.x % chunks) * 256 + threadIdx.x;
+    if (hw >= p.Hg * p.Wg) return;
+    const int yy = hw / p.Wg, x = hw - yy * p.Wg;
+    const bool inside = z < p.D && yy < p.H && x < p.W;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) {
+        const size_t ov = ((((size_t)n * p.Cq + cq) * p.D + z) * p.H + yy) * p.W + x;
+        float4 dr, xh;
+        voxel_grad(p, ov, n, cq, z, yy, x, mu, rs, sc, sh, dr, xh);
+        o.x = rs.x * (ga.x * dr.x - m1.x - xh.x * m2.x);
+        o.y = rs.y * (ga.y * dr.y - m1.y - xh.y * m2.y);
+        o.z = rs.z * (ga.z * dr.z - m1.z - xh.z * m2.z);
+        o.w = rs.w * (ga.w * dr.w - m1.w - xh.w * m2.w);
+        // dy is the MMA operand of dgrad and wgrad: store it rounded to TF32
+        o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
+        if (!p.s2d) {
+            p.dy[ov] = o;
+            if (p.dy_pl) store_planar_shifted(p.dy_pl, o, n, cq, p.C, p.D, p.H, p.W, z, yy, x, p.pl_kw, p.pl_pw, p.pl_Wx);
         }
+    }
+    if (p.s2d) {
+        // space-to-depth: channel = slot*Cp + c on the coarse grid; fine voxels cropped away by autocrop -> 0
+        const int zw = z / p.wd, yw = yy / p.wh, xw = x / p.ww;
+        const int slot = ((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww);
+        const int NS = p.wd * p.wh * p.ww;
+        const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
+        const size_t iw = ((size_t)zw * p.Hw + yw) * p.Ww + xw;
+        p.dy[(((size_t)n * NS + slot) * p.Cq + cq) * wins + iw] = o;
+        if (p.dy_pl) store_planar(p.dy_pl, o, n, slot * p.Cq + cq, NS * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
     }
 }
 
@@ -739,16 +739,27 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
 }
 
 int e3b_norm_act(const float* y, const float* scale, const float* shift, float* a, float* pooled, float* a_planar,
-                 float* pooled_planar, int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu,
-                 void* stream)
+                 float* pooled_planar, uint8_t* pool_idx, int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w,
+                 int relu, void* stream)
 {
-    if (!pooled && !pooled_planar) { pk_d = pk_h = pk_w = 1; }
-    if (pk_d * pk_h * pk_w > 8) return set_error("norm_act: pooling window > 8 voxels");
-    const int Cq = cpad8(C) / 4;
-    const size_t total = (size_t)N * Cq * ((D + pk_d - 1) / pk_d) * ((H + pk_h - 1) / pk_h) * ((W + pk_w - 1) / pk_w);
-    norm_act_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(y), scale, shift, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(pooled),
-        a_planar, pooled_planar, C, N, Cq, D, H, W, pk_d, pk_h, pk_w, relu);
+    const bool pooling = pooled || pooled_planar || pool_idx;
+    if (!pooling) { pk_d = pk_h = pk_w = 1; }
+    if (pk_d < 1 || pk_h < 1 || pk_w < 1 || pk_d > 2 || pk_h > 2 || pk_w > 2) return set_error("norm_act: pooling kernel must be 1 or 2 per dim");
+    if ((scale == nullptr) != (shift == nullptr)) return set_error("norm_act: scale and shift go together");
+    NormActDev p;
+    p.y = reinterpret_cast<const float4*>(y); p.scale = scale; p.shift = shift;
+    p.a = reinterpret_cast<float4*>(a); p.pooled = reinterpret_cast<float4*>(pooled);
+    p.a_pl = a_planar; p.pooled_pl = pooled_planar; p.pool_idx = reinterpret_cast<uchar4*>(pool_idx);
+    p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu;
+    p.Dp = (D + pk_d - 1) / pk_d; p.Hp = (H + pk_h - 1) / pk_h; p.Wp = (W + pk_w - 1) / pk_w;
+    if (p.Cq > 65535 || N > 65535) return set_error("norm_act: too many channels / samples for the launch grid");
+    if (pooling) {
+        const dim3 grid((unsigned)(p.Dp * ((p.Hp * p.Wp + 255) / 256)), p.Cq, N);
+        norm_act_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    } else {
+        const dim3 grid((unsigned)(D * ((H * W + 255) / 256)), p.Cq, N);
+        norm_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    }
     return check_launch("norm_act");
 }
 
@@ -759,18 +770,23 @@ static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)
     if ((a->scale == nullptr) != (a->shift == nullptr)) return set_error("norm_bwd: scale and shift go together");
     p.g0 = reinterpret_cast<const float4*>(a->g0); p.g1 = reinterpret_cast<const float4*>(a->g1);
     p.gp = reinterpret_cast<const float4*>(a->gp);
+    p.pool_idx = reinterpret_cast<const uchar4*>(a->pool_idx);
+    if (a->gp && !a->pool_idx) return set_error("norm_bwd: a pooled gradient needs the forward pool_idx");
     p.N = a->N; p.C = a->C; p.Cq = cpad8(a->C) / 4; p.D = a->D; p.H = a->H; p.W = a->W;
     p.wd = p.wh = p.ww = 1;
     if (a->gp && a->s2d) return set_error("norm_bwd: pooled gradient and space-to-depth output are exclusive");
     if (a->gp) { p.wd = a->pk_d; p.wh = a->pk_h; p.ww = a->pk_w; }
     if (a->s2d) { p.wd = a->sd; p.wh = a->sh; p.ww = a->sw; }
-    if (p.wd * p.wh * p.ww > 8) return set_error("norm_bwd: window > 8 voxels");
+    if (p.wd < 1 || p.wh < 1 || p.ww < 1 || p.wd * p.wh * p.ww > 8) return set_error("norm_bwd: window > 8 voxels");
     p.Dw = (a->D + p.wd - 1) / p.wd; p.Hw = (a->H + p.wh - 1) / p.wh; p.Ww = (a->W + p.ww - 1) / p.ww;
+    p.Dg = a->D; p.Hg = a->H; p.Wg = a->W;
+    if (a->s2d) { p.Dg = p.Dw * p.wd; p.Hg = p.Hw * p.wh; p.Wg = p.Ww * p.ww; }
     p.relu = a->relu; p.s2d = a->s2d;
     p.gamma = (a->mode == 0) ? nullptr : a->gamma;
     p.mean = a->mean; p.rstd = a->rstd; p.m1 = a->m1; p.m2 = a->m2;
     p.sums = a->sums; p.dy = reinterpret_cast<float4*>(a->dy); p.dy_pl = a->dy_planar;
     p.pl_kw = a->planar_kw > 0 ? a->planar_kw : 1; p.pl_pw = a->planar_pw; p.pl_Wx = a->planar_W > 0 ? a->planar_W : a->W;
+    if (p.Cq > 65535 || a->N > 65535) return set_error("norm_bwd: too many channels / samples for the launch grid");
     return 0;
 }
 
@@ -781,16 +797,11 @@ int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* a, void* stream)
     const int Cp = p.Cq * 4;
     cudaError_t e = cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * (size_t)a->N * Cp, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
-    const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
-    int bx = (int)((wins + 255) / 256);
-    int cap = (8 * num_sms()) / (p.Cq * a->N); if (cap < 1) cap = 1;
+    const size_t vox = (size_t)p.D * p.H * p.W;
+    int bx = (int)((vox + 255) / 256);
+    int cap = (16 * num_sms()) / (p.Cq * a->N); if (cap < 1) cap = 1;
     if (bx > cap) bx = cap;
-    const dim3 grid(bx, p.Cq, a->N);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (p.wd == 1 && p.wh == 1 && p.ww == 1) norm_bwd_reduce_kernel<1, 1, 1><<<grid, 256, 0, st>>>(p);
-    else if (p.wd == 2 && p.wh == 2 && p.ww == 2) norm_bwd_reduce_kernel<2, 2, 2><<<grid, 256, 0, st>>>(p);
-    else if (p.wd == 1 && p.wh == 2 && p.ww == 2) norm_bwd_reduce_kernel<1, 2, 2><<<grid, 256, 0, st>>>(p);
-    else return set_error("norm_bwd: unsupported window %dx%dx%d", p.wd, p.wh, p.ww);
+    norm_bwd_reduce_kernel<<<dim3(bx, p.Cq, a->N), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("norm_bwd_reduce");
 }
 
@@ -809,16 +820,8 @@ int e3b_norm_bwd_apply(const e3b_norm_bwd_args* a, void* stream)
 {
     NormBwdDev p;
     if (fill_bwd(a, p)) return 1;
-    const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
-    int bx = (int)((wins + 255) / 256);
-    int cap = (16 * num_sms()) / (p.Cq * a->N); if (cap < 1) cap = 1;
-    if (bx > cap) bx = cap;
-    const dim3 grid(bx, p.Cq, a->N);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (p.wd == 1 && p.wh == 1 && p.ww == 1) norm_bwd_apply_kernel<1, 1, 1><<<grid, 256, 0, st>>>(p);
-    else if (p.wd == 2 && p.wh == 2 && p.ww == 2) norm_bwd_apply_kernel<2, 2, 2><<<grid, 256, 0, st>>>(p);
-    else if (p.wd == 1 && p.wh == 2 && p.ww == 2) norm_bwd_apply_kernel<1, 2, 2><<<grid, 256, 0, st>>>(p);
-    else return set_error("norm_bwd: unsupported window %dx%dx%d", p.wd, p.wh, p.ww);
+    const dim3 grid((unsigned)(p.Dg * ((p.Hg * p.Wg + 255) / 256)), p.Cq, a->N);
+    norm_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("norm_bwd_apply");
 }
 

@@ -17,6 +17,7 @@ int num_sms();
 int conv_ntile_width(int npad_total);
 int make_qp_tensor_map(CUtensorMap* map, const float* ptr, int N, int Cq, int D, int H, int W, int Da, int Ha, int Wa,
                        int bx, int by, int bz, int bcq);
+int conv_debug_read(unsigned long long* out16, int reset);
 int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream);
 int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream);
 int64_t wgrad_workspace_floats(const e3b_wgrad_args* a);

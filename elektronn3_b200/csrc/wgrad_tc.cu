@@ -142,41 +142,49 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(p.kw * p.NTW, 0, 0);
-            uint32_t st = 0, ph = 0;
-            uint32_t started = 0;                        // bit kj: accumulator kj has been written once
-            const uint32_t a_row = (uint32_t)p.CB * 128u, b_row = (uint32_t)(p.kw * p.NTW) * 128u;
-            for (int vt = split; vt < p.total_vt; vt += p.S) {
-                int n, zi, y0, x0;
-                decode_vt(p, vt, n, zi, y0, x0);
-                mbar_wait(&full[st], ph);
-                tc_fence_after();
-                const uint32_t sA = smem_u32(smem + (size_t)st * p.stage_bytes);
-                const uint32_t sB = sA + p.a_bytes;
-                for (int kj = 0; kj < p.kdn; kj++) {
-                    const int z = zi + p.pd - (u.ku * p.kdn + kj);
-                    if (z < 0 || z >= p.Do) continue;
+        // whole warp runs the loop (uniform control flow); one elected lane issues
+        const uint32_t idesc = umma_idesc_tf32(p.kw * p.NTW, 0, 0);
+        const bool leader = elect_one();
+        uint32_t st = 0, ph = 0;
+        uint32_t started = 0;                        // bit kj: accumulator kj has been written once
+        const uint32_t a_row16 = (uint32_t)p.CB * 8u, b_row16 = (uint32_t)(p.kw * p.NTW) * 8u;   // 16-byte units
+        const uint64_t tmpl = umma_desc_sw128(0);
+        for (int vt = split; vt < p.total_vt; vt += p.S) {
+            int n, zi, y0, x0;
+            decode_vt(p, vt, n, zi, y0, x0);
+            mbar_wait(&full[st], ph);
+            tc_fence_after();
+            const uint32_t sA16 = smem_u32(smem + (size_t)st * p.stage_bytes) >> 4;
+            const uint32_t sB16 = sA16 + (p.a_bytes >> 4);
+            for (int kj = 0; kj < p.kdn; kj++) {
+                const int z = zi + p.pd - (u.ku * p.kdn + kj);
+                if (z < 0 || z >= p.Do) continue;
+                if (leader) {
                     const uint32_t acc = tmem_base + (uint32_t)(kj * p.kw * p.NTW);
-                    const uint32_t b0 = sB + (uint32_t)kj * p.b_plane_bytes;
+                    uint64_t ad = tmpl + sA16;
+                    uint64_t bd = tmpl + (sB16 + (uint32_t)kj * (p.b_plane_bytes >> 4));
+                    const uint32_t first = ((started >> kj) & 1u) ? 1u : 0u;
                     for (int yy = 0; yy < p.TY; yy++) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            const uint32_t accum = ((started >> kj) & 1u) | (uint32_t)(yy | ks);
-                            umma_tf32(acc, umma_desc_sw128(sA + (uint32_t)yy * a_row + ks * 32u),
-                                      umma_desc_sw128(b0 + (uint32_t)yy * b_row + ks * 32u), idesc, accum ? 1u : 0u);
-                        }
+                        umma_tf32(acc, ad, bd, idesc, first | (uint32_t)yy);
+                        umma_tf32(acc, ad + 2, bd + 2, idesc, 1u);
+                        umma_tf32(acc, ad + 4, bd + 4, idesc, 1u);
+                        umma_tf32(acc, ad + 6, bd + 6, idesc, 1u);
+                        ad += a_row16; bd += b_row16;
                     }
-                    started |= 1u << kj;
                 }
-                umma_commit(&empty[st]);
-                if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
+                started |= 1u << kj;
             }
+            if (leader) umma_commit(&empty[st]);
+            __syncwarp();
+            if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
+        }
+        if (leader) {
             // accumulators that never received a plane (tiny volumes) are reported to the epilogue as empty
             *started_slot = started;
             mbar_arrive(done);
             umma_commit(done);
         }
+        __syncwarp();
     } else {
         // epilogue: TMEM -> split-K partial.  Accumulator row r = j*CB + c  <->  tap dy = j, channel c.
         mbar_wait(done, 0);

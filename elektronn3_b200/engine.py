@@ -50,10 +50,11 @@ def planar_from_ncdhw(x5):
 
 class QP:
     """A float32 activation tensor in quad-planar layout (+ optionally its planar copy `pl`)."""
-    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W', 'pl')
+    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W', 'pl', 'idx')
 
     def __init__(self, t, N, C, D, H, W, pl=None):
         self.t, self.N, self.C, self.D, self.H, self.W, self.pl = t, N, C, D, H, W, pl
+        self.idx = None            # pooled tensors: arg-max slots of the pooling windows (uint8)
 
     @staticmethod
     def empty(N, C, D, H, W, device):
@@ -231,15 +232,17 @@ def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, planar=Fals
     if pool is not None:
         pk = pool
         pooled = QP.empty(y.N, y.C, -(-y.D // pk[0]), -(-y.H // pk[1]), -(-y.W // pk[2]), dev)
-    a_pl = p_pl = None
+    a_pl = p_pl = pidx = None
     if planar:
         a_pl = planar_empty(y.N, y.C, y.D, y.H, y.W, dev)
         (a if a is not None else y).pl = a_pl
         if pooled is not None:
             p_pl = pooled.pl = planar_empty(pooled.N, pooled.C, pooled.D, pooled.H, pooled.W, dev)
+            # arg-max slots for the backward pass (what MaxPool(return_indices=True) keeps in the reference)
+            pidx = pooled.idx = torch.empty(pooled.t.shape, dtype=torch.uint8, device=dev)
     L.check(L.lib().e3b_norm_act(y.ptr, _p(scale), _p(shift), a.ptr if a else None, pooled.ptr if pooled else None,
-                                 _p(a_pl), _p(p_pl), y.N, y.C, y.D, y.H, y.W, pk[0], pk[1], pk[2], 1 if relu else 0,
-                                 _stream()), 'norm_act')
+                                 _p(a_pl), _p(p_pl), _p(pidx), y.N, y.C, y.D, y.H, y.W, pk[0], pk[1], pk[2],
+                                 1 if relu else 0, _stream()), 'norm_act')
     return a, pooled
 
 
@@ -529,6 +532,9 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True, planar=True,
     args.N, args.C, args.D, args.H, args.W = N, C, a.D, a.H, a.W
     if gp is not None:
         args.pk_d, args.pk_h, args.pk_w = u.pool
+        if u.pooled is None or u.pooled.idx is None:
+            raise RuntimeError('norm backward: the forward pass kept no pooling indices')
+        args.pool_idx = u.pooled.idx.data_ptr()
     args.mode, args.G = u.mode, u.G
     n = u.spec.norm
     args.eps = float(getattr(n, 'eps', 0.0) or 0.0)

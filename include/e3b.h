@@ -85,6 +85,9 @@ typedef struct e3b_conv_args {
     int32_t force_tz;                          /* 0 = auto; tests only */
 } e3b_conv_args;
 int e3b_conv(const e3b_conv_args* args, void* stream);
+/* Developer aid: with the environment variable E3B_CONV_DEBUG set, e3b_conv accumulates per-role cycle
+ * counters (producer / MMA issuer / epilogue barrier waits); this reads (and optionally resets) them. */
+int e3b_debug_conv_counters(unsigned long long* out16, int reset);
 
 /* Weight gradient: dW[tap][ci][co] = sum_voxels x[v + tap - pad][ci] * dy[v][co]  (conv backward-filter
  * of nn.Conv3d at unet.py:131-149; with taps=1 on (x, space-to-depth dy) also ConvTranspose's).
@@ -121,9 +124,12 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
  * scale/shift NULL = identity; a NULL = only the pooled tensor is written (eval path: y is already
  * activated by the conv epilogue).
  * a_planar / pooled_planar (optional): the same tensors as Z-PLANAR (N, D, C, H, ceil4(W)) float32 copies, the
- * operand layout of e3b_wgrad. */
+ * operand layout of e3b_wgrad.
+ * pool_idx (optional, uint8 (N, pad8(C)/4, Dp, Hp, Wp, 4)): per pooled voxel and channel the window slot
+ * ((dz*pk_h+dy)*pk_w+dx) of the first maximum -- what nn.MaxPool3d(return_indices) would give; consumed by
+ * e3b_norm_bwd_*. */
 int e3b_norm_act(const float* y, const float* scale, const float* shift, float* a, float* pooled,
-                 float* a_planar, float* pooled_planar,
+                 float* a_planar, float* pooled_planar, uint8_t* pool_idx,
                  int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, void* stream);
 
 /* backward of conv -> norm -> relu [-> pool] as autograd derives it:
@@ -137,6 +143,7 @@ typedef struct e3b_norm_bwd_args {
     const float* scale; const float* shift;    /* forward affine [N][pad8(C)] from e3b_norm_finalize: the activation
                                                   a = tf32(relu(y*scale+shift)) is recomputed, not re-read */
     const float* g0; const float* g1; const float* gp;
+    const uint8_t* pool_idx;                   /* forward arg-max slots of the pooling (required with gp) */
     int32_t N, C, D, H, W;
     int32_t pk_d, pk_h, pk_w;                  /* pooling kernel of gp (if gp) */
     int32_t mode, G; float eps;

@@ -328,6 +328,7 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
         u.spec.norm.weight = torch.nn.Parameter(gamma)
         u.spec.norm.eps = 1e-5
     u.a, u.y, u.pool, u.mode, u.G, u.nstate, u.stats = a, yq, pool, mode, G, nstate, (stats if mode else None)
+    u.pooled = pooled
     dy, dgamma, dbeta, dbias = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq)
     assert_close(from_qp_ref(dy.t, C), yd.grad, 1e-3, 'norm bwd dy')
     # z-planar copies for the wgrad kernel
