@@ -91,7 +91,7 @@ SIGNATURES = {
     'e3b_version': (c_int, []),
     'e3b_last_error': (ctypes.c_char_p, []),
     'e3b_launch_count': (c_i64, []),
-    'e3b_pack_ncdhw': (c_int, [c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
+    'e3b_pack_ncdhw': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
     'e3b_unpack_qp': (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     'e3b_gather_tiles': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     'e3b_packed_weight_floats': (c_i64, [c_int] * 7),

@@ -16,12 +16,26 @@ static inline int grid_for(size_t total, int block, int max_waves = 8)
     return (int)b;
 }
 
+// Z-PLANAR (N, D, C, H, Wp) float32 copy of a QP quad (Wp = ceil4(W)): the K-major operand layout of the
+// wgrad kernel (a line of 32 x-voxels of one channel = one 128-byte swizzle row).
+E3B_DEVINL void store_planar(float* __restrict__ pl, const float4& v, int n, int cq, int C, int D, int H, int Wp, int z,
+                             int y, int x)
+{
+    const size_t plane = (size_t)H * Wp;
+    const size_t o = (((size_t)n * D + z) * C + cq * 4) * plane + (size_t)y * Wp + x;
+    const int c = cq * 4;
+    if (c < C) pl[o] = v.x;
+    if (c + 1 < C) pl[o + plane] = v.y;
+    if (c + 2 < C) pl[o + 2 * plane] = v.z;
+    if (c + 3 < C) pl[o + 3 * plane] = v.w;
+}
+
 // ------------------------------------------------------------------------------------------------
 // NCDHW box -> QP   (network input, Predictor tile gather)
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const float* __restrict__ src, const int32_t* __restrict__ origins, float4* __restrict__ dst,
-                            int N, int C, int Cq, int D, int H, int W, int Dv, int Hv, int Wv, int z0, int y0, int x0,
-                            int single)
+                            float* __restrict__ dst_pl, int N, int C, int Cq, int D, int H, int W, int Dv, int Hv, int Wv,
+                            int z0, int y0, int x0, int single)
 {
     const size_t total = (size_t)N * Cq * D * H * W;
     const size_t plane = (size_t)Dv * Hv * Wv;
@@ -45,7 +59,9 @@ __global__ void pack_kernel(const float* __restrict__ src, const int32_t* __rest
                 if (c < C) v[j] = __ldg(src + nb + (size_t)c * plane + vox);
             }
         }
-        dst[i] = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
+        const float4 q = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
+        dst[i] = q;
+        if (dst_pl) store_planar(dst_pl, q, n, cq, C, D, H, (W + 3) & ~3, z, y, x);
     }
 }
 
@@ -174,20 +190,6 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, int mode,
 // a = relu(y*scale+shift)  [+ pooled = maxpool(a), kernel (pkd,pkh,pkw), ceil mode]
 // one thread per pooling window (or voxel) per 4-channel plane
 // ------------------------------------------------------------------------------------------------
-// Z-PLANAR (N, D, C, H, Wp) float32 copy of a QP quad (Wp = ceil4(W)): the K-major operand layout of the
-// wgrad kernel (a line of 32 x-voxels of one channel = one 128-byte swizzle row).
-E3B_DEVINL void store_planar(float* __restrict__ pl, const float4& v, int n, int cq, int C, int D, int H, int Wp, int z,
-                             int y, int x)
-{
-    const size_t plane = (size_t)H * Wp;
-    const size_t o = (((size_t)n * D + z) * C + cq * 4) * plane + (size_t)y * Wp + x;
-    const int c = cq * 4;
-    if (c < C) pl[o] = v.x;
-    if (c + 1 < C) pl[o + plane] = v.y;
-    if (c + 2 < C) pl[o + 2 * plane] = v.z;
-    if (c + 3 < C) pl[o + 3 * plane] = v.w;
-}
-
 // The x-shifted gradient copies the wgrad kernel contracts against: (N, D, kw, C, H, Wxp) with
 //   dy3[n][z][dxi][c][y][xs] = dy[n][c][z][y][xs - (dxi - pw)]   (0 outside), xs in [0, Wx), Wx = conv input width.
 // A TMA box cannot start at a voxel offset that is not 16-byte aligned, so the stencil's x shift is
@@ -234,8 +236,8 @@ E3B_DEVINL float4 norm_relu_round(const float4& yv, const float4& sc, const floa
     if (affine) {
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
         v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     // activations are MMA operands of the next conv: store them rounded to TF32
     v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
     return v;
@@ -677,14 +679,14 @@ using namespace e3b;
 
 extern "C" {
 
-int e3b_pack_ncdhw(const float* src, float* dst_qp, int N, int C, int D, int H, int W, int Dv, int Hv, int Wv, int z0,
-                   int y0, int x0, void* stream)
+int e3b_pack_ncdhw(const float* src, float* dst_qp, float* dst_planar, int N, int C, int D, int H, int W, int Dv, int Hv,
+                   int Wv, int z0, int y0, int x0, void* stream)
 {
     if (N <= 0 || C <= 0) return set_error("pack: empty tensor");
     const int Cq = cpad8(C) / 4;
     const size_t total = (size_t)N * Cq * D * H * W;
-    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, nullptr, reinterpret_cast<float4*>(dst_qp), N, C,
-                                                                        Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0);
+    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, nullptr, reinterpret_cast<float4*>(dst_qp),
+                                                                        dst_planar, N, C, Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0);
     return check_launch("pack_ncdhw");
 }
 
@@ -694,8 +696,8 @@ int e3b_gather_tiles(const float* vol, const int32_t* origins, float* dst_qp, in
     if (B <= 0 || C <= 0) return set_error("gather: empty batch");
     const int Cq = cpad8(C) / 4;
     const size_t total = (size_t)B * Cq * D * H * W;
-    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vol, origins, reinterpret_cast<float4*>(dst_qp), B, C,
-                                                                        Cq, D, H, W, Dv, Hv, Wv, 0, 0, 0, 1);
+    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vol, origins, reinterpret_cast<float4*>(dst_qp), nullptr,
+                                                                        B, C, Cq, D, H, W, Dv, Hv, Wv, 0, 0, 0, 1);
     return check_launch("gather_tiles");
 }
 

@@ -84,8 +84,9 @@ def pack_input(x5, planar=False):
     N, C, D, H, W = x5.shape
     q = QP.empty(N, C, D, H, W, x5.device)
     if planar:
-        q.pl = planar_from_ncdhw(x5)
-    L.check(L.lib().e3b_pack_ncdhw(x5.data_ptr(), q.ptr, N, C, D, H, W, D, H, W, 0, 0, 0, _stream()), 'pack_ncdhw')
+        q.pl = planar_empty(N, C, D, H, W, x5.device)
+    L.check(L.lib().e3b_pack_ncdhw(x5.data_ptr(), q.ptr, _p(q.pl), N, C, D, H, W, D, H, W, 0, 0, 0, _stream()),
+            'pack_ncdhw')
     return q
 
 

@@ -35,8 +35,10 @@ int64_t e3b_launch_count(void);
  * NCDHW float32 <-> QP.  Used for the network input (reference: trainer.py:515 `inp.to(device)`)
  * and by tests.  src may be a sub-box of a larger volume (Predictor tiles, inference.py:179-189):
  * (Dv,Hv,Wv) are the extents of the allocation, (z0,y0,x0) the origin of the box inside it (may be
- * negative / overhanging: out-of-volume voxels read as 0, which is tiled_apply's zero padding). */
-int e3b_pack_ncdhw(const float* src, float* dst_qp, int N, int C, int D, int H, int W,
+ * negative / overhanging: out-of-volume voxels read as 0, which is tiled_apply's zero padding).
+ * Values are stored rounded to TF32 (they are MMA operands).  dst_planar (optional): the z-planar copy
+ * (N, D, C, H, ceil4(W)) that e3b_wgrad reads. */
+int e3b_pack_ncdhw(const float* src, float* dst_qp, float* dst_planar, int N, int C, int D, int H, int W,
                    int Dv, int Hv, int Wv, int z0, int y0, int x0, void* stream);
 int e3b_unpack_qp(const float* src_qp, float* dst, int N, int C, int D, int H, int W, void* stream);
 

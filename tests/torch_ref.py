@@ -13,14 +13,60 @@ def _norm(n, t):
     return t if isinstance(n, nn.Identity) else n(t)
 
 
-def unet_forward(m, x):
-    conv = F.conv3d if m.dim == 3 else F.conv2d
-    convT = F.conv_transpose3d if m.dim == 3 else F.conv_transpose2d
+def tf32_round(t):
+    """round-to-nearest (ties away, like cvt.rna) fp32 -> tf32, as a float32 tensor"""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _RoundSTE(torch.autograd.Function):
+    """forward: round to TF32; backward: identity (the kernels do not differentiate the rounding)"""
+
+    @staticmethod
+    def forward(ctx, t):
+        return tf32_round(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundGrad(torch.autograd.Function):
+    """forward: identity; backward: round the gradient to TF32 (dy is stored rounded: it is an MMA operand)"""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return tf32_round(g)
+
+
+def unet_forward(m, x, emulate=False):
+    """emulate=True reproduces the ARITHMETIC of the sm_100a kernels in fp32 torch ops: every MMA operand
+    (network input, activations, weights, conv-output gradients) is rounded to TF32 where the kernels store
+    it rounded, products are then exact and accumulation is fp32 -- so the result should agree with
+    libe3b to ~1e-5 (logits) and isolates implementation bugs from TF32 noise."""
+    conv_ = F.conv3d if m.dim == 3 else F.conv2d
+    convT_ = F.conv_transpose3d if m.dim == 3 else F.conv_transpose2d
     pool = F.max_pool3d if m.dim == 3 else F.max_pool2d
+    rs = _RoundSTE.apply if emulate else (lambda t: t)
+    rg = _RoundGrad.apply if emulate else (lambda t: t)
+
+    def conv(t, w, b, **kw):
+        return rg(conv_(t, rs(w), b, **kw))
+
+    def convT(t, w, b, **kw):
+        return rg(convT_(t, rs(w), b, **kw))
+
+    def act(t):
+        return rs(F.relu(t))
+    x = rs(x)
     enc = []
     for b in m.down_convs:
-        y = F.relu(_norm(b.norm0, conv(x, b.conv1.weight, b.conv1.bias, padding=b.conv1.padding)))
-        y = F.relu(_norm(b.norm1, conv(y, b.conv2.weight, b.conv2.bias, padding=b.conv2.padding)))
+        y = act(_norm(b.norm0, conv(x, b.conv1.weight, b.conv1.bias, padding=b.conv1.padding)))
+        y = act(_norm(b.norm1, conv(y, b.conv2.weight, b.conv2.bias, padding=b.conv2.padding)))
         enc.append(y)
         x = pool(y, b.pool.kernel_size, ceil_mode=True) if b.pooling else y
     for i, b in enumerate(m.up_convs):
@@ -32,21 +78,22 @@ def unet_forward(m, x):
             u = u[(slice(None), slice(None)) + tuple(slice(0, a - ((a - d) % 2)) for a, d in zip(us, ds))]
             us = u.shape[2:]
             e = e[(slice(None), slice(None)) + tuple(slice((d - a) // 2, (d + a) // 2) for a, d in zip(us, ds))]
-        u = F.relu(_norm(b.norm0, u))
-        y = F.relu(_norm(b.norm1, conv(torch.cat((u, e), 1), b.conv1.weight, b.conv1.bias, padding=b.conv1.padding)))
-        x = F.relu(_norm(b.norm2, conv(y, b.conv2.weight, b.conv2.bias, padding=b.conv2.padding)))
-    return conv(x, m.conv_final.weight, m.conv_final.bias)
+        u = act(_norm(b.norm0, u))
+        y = act(_norm(b.norm1, conv(torch.cat((u, e), 1), b.conv1.weight, b.conv1.bias, padding=b.conv1.padding)))
+        x = act(_norm(b.norm2, conv(y, b.conv2.weight, b.conv2.bias, padding=b.conv2.padding)))
+    return conv_(x, m.conv_final.weight, m.conv_final.bias)      # the 1x1x1 head runs in fp32 on CUDA cores
 
 
 def grads_with(m, x, dlogits, mode):
-    """parameter gradients of the functional forward; mode 'fp32' | 'tf32' (cuDNN conv math)"""
+    """parameter gradients of the functional forward; mode 'fp32' | 'tf32' (cuDNN conv math) |
+    'emulate' (fp32 math on TF32-rounded operands: the kernels' arithmetic)"""
     import copy
     m = copy.deepcopy(m)          # keeps BatchNorm running statistics of the caller untouched
     m.zero_grad()
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = mode == 'tf32'
     try:
-        out = unet_forward(m, x)
+        out = unet_forward(m, x, emulate=(mode == 'emulate'))
         out.backward(dlogits)
     finally:
         torch.backends.cudnn.allow_tf32 = old
