@@ -25,10 +25,18 @@ m2 = copy.deepcopy(m)
 out = m2(x); out.backward(dl)
 ours = {k: p.grad for k, p in m2.named_parameters()}
 print('logits: ours vs emulation %.3e' % ((out.detach() - outem).abs().max() / outem.abs().max()).item())
-print('logits rel err: tf32 %.3e ours %.3e' % (((outtf - out32).abs().max() / out32.abs().max()).item(), ((out.detach() - out32).abs().max() / out32.abs().max()).item()))
+print('logits rel err: emulation %.3e tf32 %.3e ours %.3e' % (((outem - out32).abs().max() / out32.abs().max()).item(), ((outtf - out32).abs().max() / out32.abs().max()).item(), ((out.detach() - out32).abs().max() / out32.abs().max()).item()))
+def rms(a, b):
+    return ((a - b).double().pow(2).sum().sqrt() / b.double().pow(2).sum().sqrt()).item()
+print('logits RMS: ours-vs-emulation %.3e   tf32-vs-fp32 %.3e   ours-vs-fp32 %.3e' % (rms(out.detach(), outem), rms(outtf, out32), rms(out.detach(), out32)))
+worst = max((rms(ours[k], gem[k]) / max(rms(gtf[k], g32[k]), 1e-12), k) for k in g32 if g32[k].abs().max() > 1e-3 * max(v.abs().max().item() for v in g32.values()))
+print('grads: worst RMS(ours-vs-emulation)/RMS(tf32 noise) = %.3f at %s' % worst)
+for k in list(g32)[:6] + list(g32)[-6:]:
+    print(f'   {k:32s} rms ours-vs-emu {rms(ours[k], gem[k]):.2e}  tf32 noise {rms(gtf[k], g32[k]):.2e}  ours-vs-fp32 {rms(ours[k], g32[k]):.2e}')
 gmax = max(v.abs().max().item() for v in g32.values())
 for k, ref in g32.items():
     sc = max(ref.abs().max().item(), 1e-2 * gmax)
     e_t = ((gtf[k] - ref).abs().max() / sc).item(); e_o = ((ours[k] - ref).abs().max() / sc).item()
     e_e = ((ours[k] - gem[k]).abs().max() / sc).item()
-    print(f'{k:32s} tf32 {e_t:.2e}  ours {e_o:.2e}  ours-vs-emulation {e_e:.2e}' + ('  <<<<' if e_e > 1e-2 else ''))
+    e_m = ((gem[k] - ref).abs().max() / sc).item()
+    print(f'{k:32s} tf32 {e_t:.2e}  emulation {e_m:.2e}  ours {e_o:.2e}  ours-vs-emulation {e_e:.2e}' + ('  <<<<' if e_o > 3 * max(e_t, e_m) + 5e-3 else ''))
