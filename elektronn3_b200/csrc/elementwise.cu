@@ -247,22 +247,37 @@ E3B_DEVINL void load_nc4(const float* p, size_t nc, float4& v, float dflt) {
     v = p ? *reinterpret_cast<const float4*>(p + nc) : make_float4(dflt, dflt, dflt, dflt);
 }
 
-// a = tf32(relu(y*scale+shift)), no pooling: one voxel per thread
+// a = tf32(relu(y*scale+shift)), no pooling.  Each thread owns kVpt voxels (a block covers kVpt*256
+// consecutive voxels of one (n, 4-channel plane) slab) and issues all its loads before the first use:
+// ~64 B in flight per thread is what it takes to cover the HBM latency at 50 % occupancy.
+static constexpr int kVpt = 4;
 __global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
 {
     const int cq = blockIdx.y, n = blockIdx.z;
-    const int chunks = (p.H * p.W + 255) / 256;
-    const int z = blockIdx.x / chunks;
-    const int hw = (blockIdx.x % chunks) * 256 + threadIdx.x;
-    if (hw >= p.H * p.W) return;
-    const int yy = hw / p.W, x = hw % p.W;
+    const int HW = p.H * p.W, S = p.D * HW;
+    const int v0 = blockIdx.x * (256 * kVpt) + threadIdx.x;
     const size_t nc = ((size_t)n * p.Cq + cq) * 4;
     float4 sc, sh;
     load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
-    const size_t o = ((((size_t)n * p.Cq + cq) * p.D + z) * p.H + yy) * p.W + x;
-    const float4 v = norm_relu_round(p.y[o], sc, sh, p.scale != nullptr, p.relu);
-    if (p.a) p.a[o] = v;
-    if (p.a_pl) store_planar(p.a_pl, v, n, cq, p.C, p.D, p.H, (p.W + 3) & ~3, z, yy, x);
+    const size_t base = ((size_t)n * p.Cq + cq) * (size_t)S;
+    float4 yv[kVpt];
+#pragma unroll
+    for (int j = 0; j < kVpt; j++) {
+        const int v = v0 + j * 256;
+        if (v < S) yv[j] = __ldcs(p.y + base + v);
+    }
+    const int Wpl = (p.W + 3) & ~3;
+#pragma unroll
+    for (int j = 0; j < kVpt; j++) {
+        const int v = v0 + j * 256;
+        if (v >= S) continue;
+        const float4 r = norm_relu_round(yv[j], sc, sh, p.scale != nullptr, p.relu);
+        if (p.a) p.a[base + v] = r;
+        if (p.a_pl) {
+            const int z = v / HW, hw = v - z * HW, yy = hw / p.W, x = hw - yy * p.W;
+            store_planar(p.a_pl, r, n, cq, p.C, p.D, p.H, Wpl, z, yy, x);
+        }
+    }
 }
 
 // ... + ceil-mode max pooling: one pooling window per thread.  pool_idx records, per channel, the window
@@ -331,28 +346,45 @@ struct NormBwdDev {
     int pl_kw, pl_pw, pl_Wx;
 };
 
+// Inputs of one voxel of the backward pass, loaded up front (several voxels per thread are in flight
+// before the first one is used).
+struct VoxIn {
+    float4 y, g0, g1, gp;
+    uchar4 idx;
+    unsigned char slot;
+};
+
+E3B_DEVINL void load_vox(const NormBwdDev& p, size_t o, int n, int cq, int z, int yy, int x, VoxIn& in)
+{
+    in.y = p.y[o];
+    if (p.g0) in.g0 = __ldcs(p.g0 + o);
+    if (p.g1) in.g1 = __ldcs(p.g1 + o);
+    if (p.gp) {
+        const int zw = z / p.wd, yw = yy / p.wh, xw = x / p.ww;
+        in.slot = (unsigned char)(((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww));
+        const size_t ow = ((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw;
+        in.idx = p.pool_idx[ow];
+        in.gp = p.gp[ow];
+    }
+}
+
 // the masked upstream gradient dr = (g0 + g1 + unpool(gp)) * [a > 0] and xhat of one voxel.
 // `a` is recomputed bit-exactly from y (the arithmetic of norm_act_kernel), never read.
-E3B_DEVINL void voxel_grad(const NormBwdDev& p, size_t o, int n, int cq, int z, int yy, int x, const float4& mu,
-                           const float4& rs, const float4& sc, const float4& sh, float4& dr, float4& xh)
+E3B_DEVINL void voxel_grad(const NormBwdDev& p, const VoxIn& in, const float4& mu, const float4& rs, const float4& sc,
+                           const float4& sh, float4& dr, float4& xh)
 {
-    const float4 yv = p.y[o];
+    const float4 yv = in.y;
     float4 a = yv;
     if (p.scale) a = norm_relu_round(yv, sc, sh, true, p.relu);
     xh = make_float4((yv.x - mu.x) * rs.x, (yv.y - mu.y) * rs.y, (yv.z - mu.z) * rs.z, (yv.w - mu.w) * rs.w);
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.g0) g = p.g0[o];
-    if (p.g1) { const float4 t = p.g1[o]; g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w; }
+    if (p.g0) g = in.g0;
+    if (p.g1) { g.x += in.g1.x; g.y += in.g1.y; g.z += in.g1.z; g.w += in.g1.w; }
     if (p.gp) {
-        const int zw = z / p.wd, yw = yy / p.wh, xw = x / p.ww;
-        const unsigned char slot = (unsigned char)(((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww));
-        const size_t ow = ((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw;
-        const uchar4 idx = p.pool_idx[ow];
-        const float4 gpv = p.gp[ow];
-        if (idx.x == slot) g.x += gpv.x;
-        if (idx.y == slot) g.y += gpv.y;
-        if (idx.z == slot) g.z += gpv.z;
-        if (idx.w == slot) g.w += gpv.w;
+        if (in.idx.x == in.slot) g.x += in.gp.x;
+        if (in.idx.y == in.slot) g.y += in.gp.y;
+        if (in.idx.z == in.slot) g.z += in.gp.z;
+        if (in.idx.w == in.slot) g.w += in.gp.w;
     }
     if (p.relu) {
         if (!(a.x > 0.f)) g.x = 0.f;
@@ -363,7 +395,8 @@ E3B_DEVINL void voxel_grad(const NormBwdDev& p, size_t o, int n, int cq, int z, 
     dr = g;
 }
 
-// grid: (D * chunks-per-plane, Cq, N)
+// grid: (chunks, Cq, N); a block strides over the voxels of one (n, 4-channel plane) slab, kRedVpt at a time
+static constexpr int kRedVpt = 1;
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p)
 {
     const int cq = blockIdx.y, n = blockIdx.z;
@@ -375,13 +408,26 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p
     const int total = p.D * HW;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     const size_t base = ((size_t)n * p.Cq + cq) * (size_t)total;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += gridDim.x * blockDim.x) {
-        const int z = v / HW, r = v - z * HW, yy = r / p.W, x = r - yy * p.W;
-        float4 dr, xh;
-        voxel_grad(p, base + v, n, cq, z, yy, x, mu, rs, sc, sh, dr, xh);
-        s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
-        s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]);
-        s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
+    const int stride = gridDim.x * blockDim.x;
+    for (int v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += kRedVpt * stride) {
+        VoxIn in[kRedVpt];
+#pragma unroll
+        for (int j = 0; j < kRedVpt; j++) {
+            const int v = v0 + j * stride;
+            if (v < total) {
+                const int z = v / HW, r = v - z * HW, yy = r / p.W, x = r - yy * p.W;
+                load_vox(p, base + v, n, cq, z, yy, x, in[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kRedVpt; j++) {
+            if (v0 + j * stride >= total) continue;
+            float4 dr, xh;
+            voxel_grad(p, in[j], mu, rs, sc, sh, dr, xh);
+            s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
+            s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]);
+            s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
+        }
     }
     __shared__ float red[8][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -460,7 +506,9 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ sums, const 
     if (dbias) dbias[c] = (float)dbi;
 }
 
-// grid: (Dg * chunks-per-plane, Cq, N); (Dg,Hg,Wg) = (D,H,W), or the un-cropped fine grid for s2d output
+// grid: (chunks, Cq, N) over the flat thread grid (Dg,Hg,Wg) = (D,H,W), or the un-cropped fine grid for
+// s2d output; kAppVpt voxels per thread, all loads issued before the first use.
+static constexpr int kAppVpt = 1;
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
 {
     const int cq = blockIdx.y, n = blockIdx.z;
@@ -475,37 +523,214 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
         ga.x = c < p.C ? p.gamma[c] : 0.f; ga.y = c + 1 < p.C ? p.gamma[c + 1] : 0.f;
         ga.z = c + 2 < p.C ? p.gamma[c + 2] : 0.f; ga.w = c + 3 < p.C ? p.gamma[c + 3] : 0.f;
     }
-    const int chunks = (p.Hg * p.Wg + 255) / 256;
-    const int z = blockIdx.x / chunks;
-    const int hw = (blockIdx.x % chunks) * 256 + threadIdx.x;
-    if (hw >= p.Hg * p.Wg) return;
-    const int yy = hw / p.Wg, x = hw - yy * p.Wg;
-    const bool inside = z < p.D && yy < p.H && x < p.W;
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (inside) {
-        const size_t ov = ((((size_t)n * p.Cq + cq) * p.D + z) * p.H + yy) * p.W + x;
-        float4 dr, xh;
-        voxel_grad(p, ov, n, cq, z, yy, x, mu, rs, sc, sh, dr, xh);
-        o.x = rs.x * (ga.x * dr.x - m1.x - xh.x * m2.x);
-        o.y = rs.y * (ga.y * dr.y - m1.y - xh.y * m2.y);
-        o.z = rs.z * (ga.z * dr.z - m1.z - xh.z * m2.z);
-        o.w = rs.w * (ga.w * dr.w - m1.w - xh.w * m2.w);
-        // dy is the MMA operand of dgrad and wgrad: store it rounded to TF32
-        o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
-        if (!p.s2d) {
-            p.dy[ov] = o;
-            if (p.dy_pl) store_planar_shifted(p.dy_pl, o, n, cq, p.C, p.D, p.H, p.W, z, yy, x, p.pl_kw, p.pl_pw, p.pl_Wx);
+    const int HWg = p.Hg * p.Wg, Sg = p.Dg * HWg;
+    const int v0 = blockIdx.x * (256 * kAppVpt) + threadIdx.x;
+    VoxIn in[kAppVpt];
+    int zs[kAppVpt], ys[kAppVpt], xs[kAppVpt];
+#pragma unroll
+    for (int j = 0; j < kAppVpt; j++) {
+        const int v = v0 + j * 256;
+        zs[j] = v / HWg;
+        const int hw = v - zs[j] * HWg;
+        ys[j] = hw / p.Wg; xs[j] = hw - ys[j] * p.Wg;
+        if (v < Sg && zs[j] < p.D && ys[j] < p.H && xs[j] < p.W) {
+            const size_t ov = ((((size_t)n * p.Cq + cq) * p.D + zs[j]) * p.H + ys[j]) * p.W + xs[j];
+            load_vox(p, ov, n, cq, zs[j], ys[j], xs[j], in[j]);
         }
     }
-    if (p.s2d) {
-        // space-to-depth: channel = slot*Cp + c on the coarse grid; fine voxels cropped away by autocrop -> 0
-        const int zw = z / p.wd, yw = yy / p.wh, xw = x / p.ww;
-        const int slot = ((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww);
-        const int NS = p.wd * p.wh * p.ww;
-        const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
-        const size_t iw = ((size_t)zw * p.Hw + yw) * p.Ww + xw;
-        p.dy[(((size_t)n * NS + slot) * p.Cq + cq) * wins + iw] = o;
-        if (p.dy_pl) store_planar(p.dy_pl, o, n, slot * p.Cq + cq, NS * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
+#pragma unroll
+    for (int j = 0; j < kAppVpt; j++) {
+        const int v = v0 + j * 256;
+        if (v >= Sg) continue;
+        const int z = zs[j], yy = ys[j], x = xs[j];
+        const bool inside = z < p.D && yy < p.H && x < p.W;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (inside) {
+            const size_t ov = ((((size_t)n * p.Cq + cq) * p.D + z) * p.H + yy) * p.W + x;
+            float4 dr, xh;
+            voxel_grad(p, in[j], mu, rs, sc, sh, dr, xh);
+            o.x = rs.x * (ga.x * dr.x - m1.x - xh.x * m2.x);
+            o.y = rs.y * (ga.y * dr.y - m1.y - xh.y * m2.y);
+            o.z = rs.z * (ga.z * dr.z - m1.z - xh.z * m2.z);
+            o.w = rs.w * (ga.w * dr.w - m1.w - xh.w * m2.w);
+            // dy is the MMA operand of dgrad and wgrad: store it rounded to TF32
+            o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
+            if (!p.s2d) {
+                p.dy[ov] = o;
+                if (p.dy_pl) store_planar_shifted(p.dy_pl, o, n, cq, p.C, p.D, p.H, p.W, z, yy, x, p.pl_kw, p.pl_pw, p.pl_Wx);
+            }
+        }
+        if (p.s2d) {
+            // space-to-depth: channel = slot*Cp + c on the coarse grid; fine voxels cropped away by autocrop -> 0
+            const int zw = z / p.wd, yw = yy / p.wh, xw = x / p.ww;
+            const int slot = ((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww);
+            const int NS = p.wd * p.wh * p.ww;
+            const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
+            const size_t iw = ((size_t)zw * p.Hw + yw) * p.Ww + xw;
+            p.dy[(((size_t)n * NS + slot) * p.Cq + cq) * wins + iw] = o;
+            if (p.dy_pl) store_planar(p.dy_pl, o, n, slot * p.Cq + cq, NS * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vector ("x4") variants for W % 4 == 0: one thread owns 4 consecutive x voxels of one row, so the
+// index arithmetic is paid once per 4 voxels and the planar copies are written with aligned 16-byte
+// stores (the scalar kernels above are instruction-issue bound, not HBM bound: ~27 issue slots per
+// voxel quad are available at full HBM rate).  The +-1 x-shifted gradient copies take their edge
+// value from the neighbouring lane.
+// ------------------------------------------------------------------------------------------------
+E3B_DEVINL float comp(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+E3B_DEVINL float4 apply_formula(const float4& dr, const float4& xh, const float4& rs, const float4& ga, const float4& m1,
+                                const float4& m2)
+{
+    float4 o;
+    o.x = tf32_rn(rs.x * (ga.x * dr.x - m1.x - xh.x * m2.x));
+    o.y = tf32_rn(rs.y * (ga.y * dr.y - m1.y - xh.y * m2.y));
+    o.z = tf32_rn(rs.z * (ga.z * dr.z - m1.z - xh.z * m2.z));
+    o.w = tf32_rn(rs.w * (ga.w * dr.w - m1.w - xh.w * m2.w));
+    return o;
+}
+
+struct BwdConsts { float4 mu, rs, sc, sh, m1, m2, ga; };
+
+E3B_DEVINL void load_bwd_consts(const NormBwdDev& p, int n, int cq, BwdConsts& c, bool with_m)
+{
+    const size_t nc = ((size_t)n * p.Cq + cq) * 4;
+    load_nc4(p.mean, nc, c.mu, 0.f); load_nc4(p.rstd, nc, c.rs, 1.f);
+    load_nc4(p.scale, nc, c.sc, 1.f); load_nc4(p.shift, nc, c.sh, 0.f);
+    c.m1 = c.m2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (with_m) { load_nc4(p.m1, nc, c.m1, 0.f); load_nc4(p.m2, nc, c.m2, 0.f); }
+    c.ga = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.gamma) {
+        const int ch = cq * 4;
+        c.ga.x = ch < p.C ? p.gamma[ch] : 0.f; c.ga.y = ch + 1 < p.C ? p.gamma[ch + 1] : 0.f;
+        c.ga.z = ch + 2 < p.C ? p.gamma[ch + 2] : 0.f; c.ga.w = ch + 3 < p.C ? p.gamma[ch + 3] : 0.f;
+    }
+}
+
+// dy of a single voxel (slow path of the x4 kernel: the neighbour across a warp boundary)
+E3B_DEVINL float4 single_dy(const NormBwdDev& p, const BwdConsts& c, int n, int cq, int z, int yy, int x)
+{
+    VoxIn in;
+    const size_t ov = ((((size_t)n * p.Cq + cq) * p.D + z) * p.H + yy) * p.W + x;
+    load_vox(p, ov, n, cq, z, yy, x, in);
+    float4 dr, xh;
+    voxel_grad(p, in, c.mu, c.rs, c.sc, c.sh, dr, xh);
+    return apply_formula(dr, xh, c.rs, c.ga, c.m1, c.m2);
+}
+
+// grid: (chunks of 256 x-groups, Cq, N).  KW = 1: one planar copy; KW = 3 (pw = 1, Wx == W): three.
+template <int KW>
+__global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev p)
+{
+    const int cq = blockIdx.y, n = blockIdx.z;
+    BwdConsts c;
+    load_bwd_consts(p, n, cq, c, true);
+    const int Wg = p.W >> 2;
+    const int total = p.D * p.H * Wg;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const bool active = t < total;
+    const int row = active ? t / Wg : 0;
+    const int xg = active ? t - row * Wg : 0;
+    const int z = row / p.H, yy = row - z * p.H, x0 = xg * 4;
+    const size_t ov = (((size_t)n * p.Cq + cq) * p.D * p.H + row) * (size_t)p.W + x0;
+    float4 o[4];
+    if (active) {
+        VoxIn in[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) load_vox(p, ov + j, n, cq, z, yy, x0 + j, in[j]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float4 dr, xh;
+            voxel_grad(p, in[j], c.mu, c.rs, c.sc, c.sh, dr, xh);
+            o[j] = apply_formula(dr, xh, c.rs, c.ga, c.m1, c.m2);
+            p.dy[ov + j] = o[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (!p.dy_pl) return;                     // (uniform over the grid)
+    float4 left = make_float4(0.f, 0.f, 0.f, 0.f), right = left;
+    if (KW == 3) {
+        const int lane = threadIdx.x & 31;
+        left.x = __shfl_up_sync(0xffffffffu, o[3].x, 1); left.y = __shfl_up_sync(0xffffffffu, o[3].y, 1);
+        left.z = __shfl_up_sync(0xffffffffu, o[3].z, 1); left.w = __shfl_up_sync(0xffffffffu, o[3].w, 1);
+        right.x = __shfl_down_sync(0xffffffffu, o[0].x, 1); right.y = __shfl_down_sync(0xffffffffu, o[0].y, 1);
+        right.z = __shfl_down_sync(0xffffffffu, o[0].z, 1); right.w = __shfl_down_sync(0xffffffffu, o[0].w, 1);
+        if (active) {
+            if (xg == 0) left = make_float4(0.f, 0.f, 0.f, 0.f);
+            else if (lane == 0) left = single_dy(p, c, n, cq, z, yy, x0 - 1);
+            if (xg == Wg - 1) right = make_float4(0.f, 0.f, 0.f, 0.f);
+            else if (lane == 31) right = single_dy(p, c, n, cq, z, yy, x0 + 4);
+        }
+    }
+    if (!active) return;
+    const size_t plane = (size_t)p.H * p.W;                 // Wxp == W (W % 4 == 0, Wx == W)
+    const int ch0 = cq * 4;
+    float* pl0 = p.dy_pl + ((((size_t)n * p.D + z) * KW) * p.C + ch0) * plane + (size_t)yy * p.W + x0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (ch0 + k >= p.C) break;
+        const float a0 = comp(o[0], k), a1 = comp(o[1], k), a2 = comp(o[2], k), a3 = comp(o[3], k);
+        float* q = pl0 + (size_t)k * plane;
+        if (KW == 1) {
+            *reinterpret_cast<float4*>(q) = make_float4(a0, a1, a2, a3);
+        } else {
+            const size_t cstride = (size_t)p.C * plane;       // between the dxi copies
+            // dxi = 0: shift -1: out[xs] = dy[xs + 1];  dxi = 1: unshifted;  dxi = 2: shift +1: out[xs] = dy[xs - 1]
+            *reinterpret_cast<float4*>(q) = make_float4(a1, a2, a3, comp(right, k));
+            *reinterpret_cast<float4*>(q + cstride) = make_float4(a0, a1, a2, a3);
+            *reinterpret_cast<float4*>(q + 2 * cstride) = make_float4(comp(left, k), a0, a1, a2);
+        }
+    }
+}
+
+// statistics pass, 4 consecutive voxels per thread and iteration.  grid: (chunks, Cq, N)
+__global__ void __launch_bounds__(256) norm_bwd_reduce_x4_kernel(const NormBwdDev p)
+{
+    const int cq = blockIdx.y, n = blockIdx.z;
+    BwdConsts c;
+    load_bwd_consts(p, n, cq, c, false);
+    const int Wg = p.W >> 2;
+    const int total = p.D * p.H * Wg;
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    const size_t base = ((size_t)n * p.Cq + cq) * (size_t)p.D * p.H * p.W;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        int z = 0, yy = 0, x0 = 0;
+        if (p.gp) { const int row = t / Wg; x0 = (t - row * Wg) * 4; z = row / p.H; yy = row - z * p.H; }
+        VoxIn in[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) load_vox(p, base + (size_t)t * 4 + j, n, cq, z, yy, x0 + j, in[j]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float4 dr, xh;
+            voxel_grad(p, in[j], c.mu, c.rs, c.sc, c.sh, dr, xh);
+            s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
+            s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]);
+            s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
+        }
+    }
+    __shared__ float red[8][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+    }
+    if (lane == 0) {
+        for (int j = 0; j < 4; j++) { red[warp][j] = s1[j]; red[warp][4 + j] = s2[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double tt = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) tt += (double)red[w][threadIdx.x];
+        const int j = threadIdx.x & 3, which = threadIdx.x >> 2;
+        atomicAdd(p.sums + (((size_t)n * p.Cq + cq) * 4 + j) * 2 + which, tt);
     }
 }
 
@@ -759,7 +984,8 @@ int e3b_norm_act(const float* y, const float* scale, const float* shift, float* 
         const dim3 grid((unsigned)(p.Dp * ((p.Hp * p.Wp + 255) / 256)), p.Cq, N);
         norm_act_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     } else {
-        const dim3 grid((unsigned)(D * ((H * W + 255) / 256)), p.Cq, N);
+        const size_t S = (size_t)D * H * W;
+        const dim3 grid((unsigned)((S + 256 * kVpt - 1) / (256 * kVpt)), p.Cq, N);
         norm_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     }
     return check_launch("norm_act");
@@ -800,9 +1026,15 @@ int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* a, void* stream)
     cudaError_t e = cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * (size_t)a->N * Cp, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
     const size_t vox = (size_t)p.D * p.H * p.W;
-    int bx = (int)((vox + 255) / 256);
+    int bx = (int)((vox + 256 * kRedVpt - 1) / (256 * kRedVpt));
     int cap = (16 * num_sms()) / (p.Cq * a->N); if (cap < 1) cap = 1;
     if (bx > cap) bx = cap;
+    if (false && p.W % 4 == 0) {      // measured slower than the scalar kernel (128 registers): kept for reference
+        bx = (int)((vox / 4 + 255) / 256);
+        if (bx > cap) bx = cap;
+        norm_bwd_reduce_x4_kernel<<<dim3(bx, p.Cq, a->N), 256, 0, (cudaStream_t)stream>>>(p);
+        return check_launch("norm_bwd_reduce_x4");
+    }
     norm_bwd_reduce_kernel<<<dim3(bx, p.Cq, a->N), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("norm_bwd_reduce");
 }
@@ -822,7 +1054,18 @@ int e3b_norm_bwd_apply(const e3b_norm_bwd_args* a, void* stream)
 {
     NormBwdDev p;
     if (fill_bwd(a, p)) return 1;
-    const dim3 grid((unsigned)(p.Dg * ((p.Hg * p.Wg + 255) / 256)), p.Cq, a->N);
+    // vector path: rows of 4-voxel groups, SAME-padded stencil (the gradient is as wide as the conv input)
+    const bool x4 = !p.s2d && (p.W % 4 == 0) && (!p.dy_pl || (p.pl_Wx == p.W && ((p.pl_kw == 1 && p.pl_pw == 0) ||
+                                                                               (p.pl_kw == 3 && p.pl_pw == 1))));
+    if (x4) {
+        const size_t groups = (size_t)p.D * p.H * (p.W / 4);
+        const dim3 grid((unsigned)((groups + 255) / 256), p.Cq, a->N);
+        if (p.dy_pl && p.pl_kw == 3) norm_bwd_apply_x4_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        else norm_bwd_apply_x4_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        return check_launch("norm_bwd_apply_x4");
+    }
+    const size_t Sg = (size_t)p.Dg * p.Hg * p.Wg;
+    const dim3 grid((unsigned)((Sg + 256 * kAppVpt - 1) / (256 * kAppVpt)), p.Cq, a->N);
     norm_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("norm_bwd_apply");
 }

@@ -275,7 +275,8 @@ def _norm_ref(y, mode, G, gamma, beta, rm, rv, eps=1e-5):
 
 @pytest.mark.parametrize('mode,G,C,sp,pool', [(1, 8, 32, (6, 8, 10), None), (1, 8, 16, (5, 7, 9), (2, 2, 2)),
                                               (2, 1, 8, (4, 6, 8), (2, 2, 2)), (2, 1, 24, (3, 9, 8), (1, 2, 2)),
-                                              (0, 1, 8, (4, 6, 8), (2, 2, 2)), (1, 3, 3, (4, 4, 4), None)])
+                                              (0, 1, 8, (4, 6, 8), (2, 2, 2)), (1, 3, 3, (4, 4, 4), None),
+                                              (1, 4, 8, (2, 3, 136), None), (2, 1, 8, (2, 4, 132), (1, 2, 2))])
 def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
     N = 2
     rs = np.random.RandomState(31)
