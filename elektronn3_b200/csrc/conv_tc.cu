@@ -279,76 +279,81 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             const int y = y0 + ry, x = x0 + rx;
             const bool valid = (y < p.Ho) && (x < p.Wo);
             const int npl = (p.Do - z0) < p.TZ ? (p.Do - z0) : p.TZ;
-            for (int cb = 0; cb < p.NT; cb += 16) {
-                const int ncol = nt * p.NT + cb;     // first global N column of this group
-                float bias_v[16];
-                {
-                    const int b0 = p.scatter ? (ncol % p.Cup) : ncol;
-#pragma unroll
-                    for (int j = 0; j < 16; j++) bias_v[j] = (p.bias && b0 + j < p.n_bias) ? __ldg(p.bias + b0 + j) : 0.f;
-                }
-                // scatter geometry of this column group (one tap per 16-column group: Cup % 16 == 0)
-                int ti = 0, tj = 0, tk = 0, co = ncol;
-                if (p.scatter) {
-                    const int tapi = ncol / p.Cup; co = ncol % p.Cup;
-                    ti = tapi / (p.sh * p.sw); tj = (tapi / p.sw) % p.sh; tk = tapi % p.sw;
-                }
+            // Column groups of 16.  In scatter mode the columns of one tile are [tap][channel]: the groups are
+            // visited channel-major so that the statistics of a channel group are reduced once for all taps.
+            const int cspan = (p.scatter && p.Cup < p.NT) ? p.Cup : p.NT;      // columns per tap inside this tile
+            const int ntp = p.NT / cspan;                                      // taps inside this tile
+            for (int cg = 0; cg < cspan; cg += 16) {
                 float s[16], ss[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++) { s[j] = 0.f; ss[j] = 0.f; }
-                for (int pl = 0; pl < npl; pl++) {
-                    const int z = z0 + pl;
-                    float v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)(pl * p.NT + cb), v);
+                const int co = p.scatter ? ((nt * p.NT + cg) % p.Cup) : (nt * p.NT + cg);   // first channel of the group
+                float bias_v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] += bias_v[j];
-                    if (p.relu) {
-#pragma unroll
-                        for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], 0.f);
+                for (int j = 0; j < 16; j++) bias_v[j] = (p.bias && co + j < p.n_bias) ? __ldg(p.bias + co + j) : 0.f;
+                for (int tp = 0; tp < ntp; tp++) {
+                    const int cb = tp * cspan + cg;
+                    const int ncol = nt * p.NT + cb;     // first global N column of this group
+                    // scatter geometry of this column group (one tap per 16-column group: Cup % 16 == 0)
+                    int ti = 0, tj = 0, tk = 0;
+                    if (p.scatter) {
+                        const int tapi = ncol / p.Cup;
+                        ti = tapi / (p.sh * p.sw); tj = (tapi / p.sw) % p.sh; tk = tapi % p.sw;
                     }
-                    if (p.round_tf32) {
+                    for (int pl = 0; pl < npl; pl++) {
+                        const int z = z0 + pl;
+                        float v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)(pl * p.NT + cb), v);
 #pragma unroll
-                        for (int j = 0; j < 16; j++) v[j] = tf32_rn(v[j]);
-                    }
-                    bool sv = valid;
-                    if (!p.scatter) {
-                        if (valid) {
+                        for (int j = 0; j < 16; j++) v[j] += bias_v[j];
+                        if (p.relu) {
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; j4++) {
-                                int cq = (ncol >> 2) + j4;
-                                float* base; int cqa;
-                                if (cq < p.cq0) { base = p.dst0; cqa = p.cq0_alloc; }
-                                else { base = p.dst1; cq -= p.cq0; cqa = p.cq1_alloc; }
-                                if (base != nullptr && cq < cqa) {
-                                    size_t o = ((((size_t)n * cqa + cq) * p.Do + z) * p.Ho + y) * (size_t)p.Wo + x;
-                                    reinterpret_cast<float4*>(base)[o] =
-                                        make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                            for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], 0.f);
+                        }
+                        if (p.round_tf32) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) v[j] = tf32_rn(v[j]);
+                        }
+                        bool sv = valid;
+                        if (!p.scatter) {
+                            if (valid) {
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; j4++) {
+                                    int cq = (ncol >> 2) + j4;
+                                    float* base; int cqa;
+                                    if (cq < p.cq0) { base = p.dst0; cqa = p.cq0_alloc; }
+                                    else { base = p.dst1; cq -= p.cq0; cqa = p.cq1_alloc; }
+                                    if (base != nullptr && cq < cqa) {
+                                        size_t o = ((((size_t)n * cqa + cq) * p.Do + z) * p.Ho + y) * (size_t)p.Wo + x;
+                                        reinterpret_cast<float4*>(base)[o] =
+                                            make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                                    }
+                                }
+                            }
+                        } else {
+                            // column = tap * Cup + co ; fine voxel = (z*sd+i, y*sh+j, x*sw+k)
+                            const int fz = z * p.sd + ti, fy = y * p.sh + tj, fx = x * p.sw + tk;
+                            sv = valid && fz < p.Ds && fy < p.Hs && fx < p.Ws;
+                            if (sv) {
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; j4++) {
+                                    int cq = (co >> 2) + j4;
+                                    if (cq < p.cq0_alloc) {
+                                        size_t o = ((((size_t)n * p.cq0_alloc + cq) * p.Ds + fz) * p.Hs + fy) * (size_t)p.Ws + fx;
+                                        reinterpret_cast<float4*>(p.dst0)[o] =
+                                            make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                                    }
                                 }
                             }
                         }
-                    } else {
-                        // column = tap * Cup + co ; fine voxel = (z*sd+i, y*sh+j, x*sw+k)
-                        const int fz = z * p.sd + ti, fy = y * p.sh + tj, fx = x * p.sw + tk;
-                        sv = valid && fz < p.Ds && fy < p.Hs && fx < p.Ws;
-                        if (sv) {
+                        if (p.stats && sv) {
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; j4++) {
-                                int cq = (co >> 2) + j4;
-                                if (cq < p.cq0_alloc) {
-                                    size_t o = ((((size_t)n * p.cq0_alloc + cq) * p.Ds + fz) * p.Hs + fy) * (size_t)p.Ws + fx;
-                                    reinterpret_cast<float4*>(p.dst0)[o] =
-                                        make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                                }
-                            }
+                            for (int j = 0; j < 16; j++) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
                         }
-                    }
-                    if (p.stats && sv) {
-#pragma unroll
-                        for (int j = 0; j < 16; j++) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
                     }
                 }
                 if (p.stats) {
-                    // per-channel sum / sumsq over the warp's 32 rows x npl planes: 16-value butterfly
+                    // per-channel sum / sumsq over the warp's 32 rows x npl planes (x taps): 16-value butterfly
 #pragma unroll
                     for (int step = 0; step < 4; step++) {
                         const int half = 8 >> step;           // 8,4,2,1 values kept
@@ -367,12 +372,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                     const float fs = s[0] + __shfl_xor_sync(0xffffffffu, s[0], 16);
                     const float fq = ss[0] + __shfl_xor_sync(0xffffffffu, ss[0], 16);
                     if (lane < 16) {
-                        const int si = p.scatter ? (co + bcol) : (cb + bcol);     // accumulator slot
+                        const int si = p.scatter ? (co + bcol) : (cg + bcol);     // accumulator slot
                         if (si < kStatSlots) {
                             atomicAdd(&cta_stats[si * 2], (double)fs);
                             atomicAdd(&cta_stats[si * 2 + 1], (double)fq);
                         } else {
-                            const int ch = p.scatter ? si : ncol + bcol;
+                            const int ch = p.scatter ? si : nt * p.NT + cg + bcol;
                             if (ch < p.Cstat) {
                                 atomicAdd(p.stats + ((size_t)n * p.Cstat + ch) * 2, (double)fs);
                                 atomicAdd(p.stats + ((size_t)n * p.Cstat + ch) * 2 + 1, (double)fq);
@@ -505,6 +510,19 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
     p.n_ntiles = npad_total / p.NT;
     // accumulator planes per tile: two ping-pong sets of <= 256 TMEM columns
     int tz = 256 / p.NT; if (tz > 8) tz = 8; if (tz > p.Do) tz = p.Do; if (tz < 1) tz = 1;
+    // tile depth: minimise (waves of the persistent schedule) x (cost of a tile ~ tz planes + fixed part)
+    {
+        const long long txy = (long long)((p.Wo + kTX - 1) / kTX) * ((p.Ho + kTY - 1) / kTY) * p.n_ntiles * a->N;
+        double best = 1e30;
+        int best_tz = tz;
+        for (int t = tz; t >= 1; t--) {
+            const long long tiles = txy * ((p.Do + t - 1) / t);
+            const long long waves = (tiles + num_sms() - 1) / num_sms();
+            const double cost = (double)waves * (t + 0.5);
+            if (cost < best - 1e-9) { best = cost; best_tz = t; }
+        }
+        tz = best_tz;
+    }
     if (a->force_tz > 0) tz = a->force_tz;
     p.TZ = tz;
     p.HX = kTX + a->kw - 1; p.HY = kTY + a->kh - 1; p.HZ = tz + a->kd - 1;

@@ -18,13 +18,16 @@
 //    M = 128 operand starting at row r covers rows r .. r+RS-1 (RS = 128 / CB, CB = 8/16/32 channels per
 //    unit): accumulator rows [j*CB, (j+1)*CB) are tap dy = j.  With CB = 32 one MMA serves all three dy
 //    taps (75 % of the M rows useful instead of 25 %);
-//  * the (kd) z-shifts pair the x plane z with dy planes z+pd-kd: either all inside one CTA (narrow N)
-//    or split over CTAs;
+//  * the (kd) z-shifts pair the x plane z with the dy planes z+pd-kd+1 .. z+pd: either all inside one CTA
+//    (narrow N) or split over CTAs.  A CTA walks a contiguous run of x planes of one (n, y tile, x tile)
+//    column, so the dy planes live in their own shared-memory ring and every plane is staged ONCE for
+//    the kd x-planes that use it (a sliding window along z) instead of once per x plane;
 //  * every (kd, dx) tap pair owns a TMEM accumulator (columns <= 512); the contraction over voxels is
 //    split over CTAs (split-K), partials go to a workspace and a deterministic second kernel reduces
 //    them into the torch weight layout.
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace e3b {
 
@@ -39,12 +42,13 @@ struct WgradParams {
     int off1_d, off1_h, off1_w;
     int CB, RS;                  // channels per M unit, rows stacked in M
     int TY, TYA, rows_alloc;     // dy rows per stage, x rows loaded, x rows addressed by the MMAs
-    int tiles_x, tiles_y, total_vt;
+    int tiles_x, tiles_y;
     int mchunks0, mchunks;       // CB-channel chunks in source 0 / total
     int NTW, nchunks_n;          // N columns per CTA, number of N chunks
     int kdn, kd_units;           // kd taps per CTA, CTAs along kd
-    int units, S, stages;
-    uint32_t a_load_bytes, a_bytes, b_plane_bytes, b_bytes, stage_bytes;
+    int units, S, SA, SB;        // CTAs = units * S; depth of the x-tile ring and of the dy-plane ring
+    int total_L;                 // linear work items: (column = (n, y tile, x tile)) x (x plane z)
+    uint32_t a_load_bytes, a_bytes, b_plane_bytes;
     int ktot, npad_total;        // partial-sum row / column space
     float* part;                 // [S][ntaps][ktot][npad_total]
 };
@@ -59,12 +63,30 @@ E3B_DEVINL WgUnit decode_unit(const WgradParams& p, int u) {
     return r;
 }
 
-E3B_DEVINL void decode_vt(const WgradParams& p, int vt, int& n, int& zi, int& y0, int& x0) {
-    int xt = vt % p.tiles_x; vt /= p.tiles_x;
-    int yt = vt % p.tiles_y; vt /= p.tiles_y;
-    zi = vt % p.D;
-    n = vt / p.D;
+// column index -> sample and tile origin
+E3B_DEVINL void decode_col(const WgradParams& p, int col, int& n, int& y0, int& x0) {
+    int xt = col % p.tiles_x; col /= p.tiles_x;
+    int yt = col % p.tiles_y;
+    n = col / p.tiles_y;
     x0 = xt * kSeg; y0 = yt * p.TY;
+}
+
+// The run of work of one CTA, cut into per-column segments.  Producer and MMA issuer walk it in lock step.
+struct WgSeg {
+    int col, za, zb;             // x planes [za, zb) of column col
+    int blo, bhi;                // dy planes [blo, bhi] staged for this segment (may be empty: blo > bhi)
+};
+// dy planes used by x plane zi: [lo, hi]  (all kdn taps of this CTA)
+E3B_DEVINL int wg_lo(const WgradParams& p, int ku, int zi) { return zi + p.pd - (ku * p.kdn + p.kdn - 1); }
+E3B_DEVINL int wg_hi(const WgradParams& p, int ku, int zi) { return zi + p.pd - ku * p.kdn; }
+E3B_DEVINL WgSeg wg_segment(const WgradParams& p, int ku, int L, int L1) {
+    WgSeg g;
+    g.col = L / p.D; g.za = L - g.col * p.D;
+    const int left = L1 - L;
+    g.zb = g.za + left < p.D ? g.za + left : p.D;
+    g.blo = wg_lo(p, ku, g.za); if (g.blo < 0) g.blo = 0;
+    g.bhi = wg_hi(p, ku, g.zb - 1); if (g.bhi > p.Do - 1) g.bhi = p.Do - 1;
+    return g;
 }
 
 // K-major, 128-byte swizzle: 8-row groups 1024 B apart; the K advance inside a line is added to the start
@@ -85,10 +107,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128 B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + p.stages;
-    uint64_t* done = empty + p.stages;
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + (size_t)p.SA * p.a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.SB * p.b_plane_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + p.SA;
+    uint64_t* b_full = a_empty + p.SA;
+    uint64_t* b_empty = b_full + p.SB;
+    uint64_t* done = b_empty + p.SB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     volatile uint32_t* started_slot = tmem_slot + 1;
 
@@ -97,9 +123,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
     const WgUnit u = decode_unit(p, unit);
     const bool src1 = u.mc >= p.mchunks0;
     const int mc_local = src1 ? u.mc - p.mchunks0 : u.mc;
+    // this CTA's contiguous run of the linear (column, z) work space
+    const int L0 = (int)(((long long)p.total_L * split) / p.S), L1 = (int)(((long long)p.total_L * (split + 1)) / p.S);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < p.SA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < p.SB; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_init(done, 2);                      // tcgen05.commit + the issuer's own (releasing) arrive
         fence_barrier_init();
         tma_prefetch_desc(src1 ? &tmx1 : &tmx0);
@@ -113,70 +142,90 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t st = 0, ph = 0;
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
             const CUtensorMap* mx = src1 ? &tmx1 : &tmx0;
             const int ox = src1 ? p.off1_w : 0, oy = src1 ? p.off1_h : 0, oz = src1 ? p.off1_d : 0;
             const int Dsrc = src1 ? p.D1 : p.D;      // planes per sample in the source's allocation
-            for (int vt = split; vt < p.total_vt; vt += p.S) {
-                int n, zi, y0, x0;
-                decode_vt(p, vt, n, zi, y0, x0);
-                mbar_wait(&empty[st], ph ^ 1);
-                uint8_t* sA = smem + (size_t)st * p.stage_bytes;
-                uint8_t* sB = sA + p.a_bytes;
-                int nb = 0;
-                for (int kj = 0; kj < p.kdn; kj++) {
-                    const int z = zi + p.pd - (u.ku * p.kdn + kj);
-                    nb += (z >= 0 && z < p.Do);
+            for (int L = L0; L < L1;) {
+                const WgSeg g = wg_segment(p, u.ku, L, L1);
+                int n, y0, x0;
+                decode_col(p, g.col, n, y0, x0);
+                int bnext = g.blo;
+                for (int zi = g.za; zi < g.zb; zi++) {
+                    int need = wg_hi(p, u.ku, zi); if (need > g.bhi) need = g.bhi;
+                    for (; bnext <= need; bnext++) {
+                        // dy: dims (x, co, dxi, y, n*Do + z)
+                        mbar_wait(&b_empty[sb], pb ^ 1);
+                        mbar_arrive_expect_tx(&b_full[sb], p.b_plane_bytes);
+                        tma_load_5d(b_ring + (size_t)sb * p.b_plane_bytes, &tmdy, &b_full[sb], x0, u.nc * p.NTW, 0, y0,
+                                    n * p.Do + bnext);
+                        if (++sb == (uint32_t)p.SB) { sb = 0; pb ^= 1; }
+                    }
+                    // x: dims (x, c, y, n*D + z)
+                    mbar_wait(&a_empty[sa], pa ^ 1);
+                    mbar_arrive_expect_tx(&a_full[sa], p.a_load_bytes);
+                    tma_load_4d(a_ring + (size_t)sa * p.a_bytes, mx, &a_full[sa], x0 + ox, mc_local * p.CB, y0 - p.ph + oy,
+                                n * Dsrc + zi + oz);
+                    if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
                 }
-                mbar_arrive_expect_tx(&full[st], p.a_load_bytes + (uint32_t)nb * p.b_plane_bytes);
-                // x: dims (x, c, y, n*D + z)
-                tma_load_4d(sA, mx, &full[st], x0 + ox, mc_local * p.CB, y0 - p.ph + oy, n * Dsrc + zi + oz);
-                for (int kj = 0; kj < p.kdn; kj++) {
-                    const int z = zi + p.pd - (u.ku * p.kdn + kj);
-                    // dy: dims (x, co, dxi, y, n*Do + z); planes outside the gradient are skipped, not loaded
-                    if (z >= 0 && z < p.Do)
-                        tma_load_5d(sB + (size_t)kj * p.b_plane_bytes, &tmdy, &full[st], x0, u.nc * p.NTW, 0, y0,
-                                    n * p.Do + z);
-                }
-                if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
+                L += g.zb - g.za;
             }
         }
     } else if (warp == 1) {
         // whole warp runs the loop (uniform control flow); one elected lane issues
         const uint32_t idesc = umma_idesc_tf32(p.kw * p.NTW, 0, 0);
         const bool leader = elect_one();
-        uint32_t st = 0, ph = 0;
+        uint32_t sa = 0, pa = 0;
+        uint32_t wb = 0, wpb = 0;                    // next dy-plane slot to wait for
+        uint32_t rb = 0;                             // next dy-plane slot to release
         uint32_t started = 0;                        // bit kj: accumulator kj has been written once
         const uint32_t a_row16 = (uint32_t)p.CB * 8u, b_row16 = (uint32_t)(p.kw * p.NTW) * 8u;   // 16-byte units
         const uint64_t tmpl = umma_desc_sw128(0);
-        for (int vt = split; vt < p.total_vt; vt += p.S) {
-            int n, zi, y0, x0;
-            decode_vt(p, vt, n, zi, y0, x0);
-            mbar_wait(&full[st], ph);
-            tc_fence_after();
-            const uint32_t sA16 = smem_u32(smem + (size_t)st * p.stage_bytes) >> 4;
-            const uint32_t sB16 = sA16 + (p.a_bytes >> 4);
-            for (int kj = 0; kj < p.kdn; kj++) {
-                const int z = zi + p.pd - (u.ku * p.kdn + kj);
-                if (z < 0 || z >= p.Do) continue;
-                if (leader) {
-                    const uint32_t acc = tmem_base + (uint32_t)(kj * p.kw * p.NTW);
-                    uint64_t ad = tmpl + sA16;
-                    uint64_t bd = tmpl + (sB16 + (uint32_t)kj * (p.b_plane_bytes >> 4));
-                    const uint32_t first = ((started >> kj) & 1u) ? 1u : 0u;
-                    for (int yy = 0; yy < p.TY; yy++) {
-                        umma_tf32(acc, ad, bd, idesc, first | (uint32_t)yy);
-                        umma_tf32(acc, ad + 2, bd + 2, idesc, 1u);
-                        umma_tf32(acc, ad + 4, bd + 4, idesc, 1u);
-                        umma_tf32(acc, ad + 6, bd + 6, idesc, 1u);
-                        ad += a_row16; bd += b_row16;
-                    }
+        const uint32_t a16 = smem_u32(a_ring) >> 4, b16 = smem_u32(b_ring) >> 4;
+        for (int L = L0; L < L1;) {
+            const WgSeg g = wg_segment(p, u.ku, L, L1);
+            const uint32_t slot0 = wb;               // ring slot of dy plane g.blo
+            int bwaited = g.blo, brel = g.blo;
+            for (int zi = g.za; zi < g.zb; zi++) {
+                int need = wg_hi(p, u.ku, zi); if (need > g.bhi) need = g.bhi;
+                for (; bwaited <= need; bwaited++) {
+                    mbar_wait(&b_full[wb], wpb);
+                    if (++wb == (uint32_t)p.SB) { wb = 0; wpb ^= 1; }
                 }
-                started |= 1u << kj;
+                mbar_wait(&a_full[sa], pa);
+                tc_fence_after();
+                const uint32_t sA16 = a16 + (uint32_t)sa * (p.a_bytes >> 4);
+                for (int kj = 0; kj < p.kdn; kj++) {
+                    const int z = zi + p.pd - (u.ku * p.kdn + kj);
+                    if (z < 0 || z >= p.Do) continue;
+                    if (leader) {
+                        const uint32_t slot = (slot0 + (uint32_t)(z - g.blo)) % (uint32_t)p.SB;
+                        const uint32_t acc = tmem_base + (uint32_t)(kj * p.kw * p.NTW);
+                        uint64_t ad = tmpl + sA16;
+                        uint64_t bd = tmpl + (b16 + slot * (p.b_plane_bytes >> 4));
+                        const uint32_t first = ((started >> kj) & 1u) ? 1u : 0u;
+                        for (int yy = 0; yy < p.TY; yy++) {
+                            umma_tf32(acc, ad, bd, idesc, first | (uint32_t)yy);
+                            umma_tf32(acc, ad + 2, bd + 2, idesc, 1u);
+                            umma_tf32(acc, ad + 4, bd + 4, idesc, 1u);
+                            umma_tf32(acc, ad + 6, bd + 6, idesc, 1u);
+                            ad += a_row16; bd += b_row16;
+                        }
+                    }
+                    started |= 1u << kj;
+                }
+                if (leader) umma_commit(&a_empty[sa]);
+                if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
+                // dy planes no later x plane of this segment uses are handed back to the producer
+                int relupto = g.bhi + 1;
+                if (zi + 1 < g.zb) { relupto = wg_lo(p, u.ku, zi + 1); if (relupto > g.bhi + 1) relupto = g.bhi + 1; }
+                for (; brel < relupto; brel++) {
+                    if (leader) umma_commit(&b_empty[rb]);
+                    if (++rb == (uint32_t)p.SB) rb = 0;
+                }
+                __syncwarp();
             }
-            if (leader) umma_commit(&empty[st]);
-            __syncwarp();
-            if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
+            L += g.zb - g.za;
         }
         if (leader) {
             // accumulators that never received a plane (tiny volumes) are reported to the epilogue as empty
@@ -326,29 +375,40 @@ static int plan_wgrad(const e3b_wgrad_args* a, WgradParams& p)
     p.kdn = (a->kd * a->kw * p.NTW <= 512) ? a->kd : 1;
     p.kd_units = a->kd / p.kdn;
     p.units = p.kd_units * p.mchunks * p.nchunks_n;
-    const size_t budget = 227 * 1024 - 2048 - 256;
+    const size_t budget = 227 * 1024 - 2048 - 512;
     int ty = 8;
+    // developer overrides for tuning runs (scripts/layer_bench.py): E3B_WGRAD_TY / _SA / _SB
+    const char* e_ty = getenv("E3B_WGRAD_TY"); const char* e_sa = getenv("E3B_WGRAD_SA"); const char* e_sb = getenv("E3B_WGRAD_SB");
+    if (e_ty) ty = atoi(e_ty);
     for (;; ty >>= 1) {
         p.TY = ty; p.TYA = ty + a->kh - 1; p.rows_alloc = ty + p.RS - 1;
         if (p.rows_alloc < p.TYA) p.rows_alloc = p.TYA;
         p.a_load_bytes = (uint32_t)(p.TYA * p.CB * 128);
         p.a_bytes = (uint32_t)(p.rows_alloc * p.CB * 128);
         p.b_plane_bytes = (uint32_t)(ty * a->kw * p.NTW * 128);
-        p.b_bytes = (uint32_t)p.kdn * p.b_plane_bytes;
-        p.stage_bytes = p.a_bytes + p.b_bytes;
-        const int st = (int)(budget / p.stage_bytes);
+        // rings: the dy window holds kdn live planes; +2 lets the producer run ahead.  x tiles: 2..4 deep.
         const bool small_enough = ty == 1 || ty / 2 < p.Ho;      // do not carry rows a small volume does not have
-        if (st >= 2 && small_enough) { p.stages = st > 4 ? 4 : st; break; }
-        if (ty == 1) {
-            if (st >= 1) { p.stages = 1; break; }
-            return set_error("wgrad: stage does not fit shared memory");
+        int sa = 2, sb = p.kdn + 1;
+        const bool fits = (size_t)sa * p.a_bytes + (size_t)sb * p.b_plane_bytes <= budget;
+        if (fits && (small_enough || ty == 1)) {
+            for (;;) {
+                bool grew = false;
+                if (sb < p.kdn + 3 && (size_t)sa * p.a_bytes + (size_t)(sb + 1) * p.b_plane_bytes <= budget) { sb++; grew = true; }
+                if (sa < 4 && (size_t)(sa + 1) * p.a_bytes + (size_t)sb * p.b_plane_bytes <= budget) { sa++; grew = true; }
+                if (!grew) break;
+            }
+            p.SA = sa; p.SB = sb;
+            if (e_sa && atoi(e_sa) >= 2 && atoi(e_sa) <= sa) p.SA = atoi(e_sa);
+            if (e_sb && atoi(e_sb) >= p.kdn + 1 && atoi(e_sb) <= sb) p.SB = atoi(e_sb);
+            break;
         }
+        if (ty == 1) return set_error("wgrad: stage does not fit shared memory");
     }
     // tiles cover the conv INPUT width (the shifted gradient copies are indexed by the input x)
     p.tiles_x = (a->W + kSeg - 1) / kSeg; p.tiles_y = (p.Ho + p.TY - 1) / p.TY;
-    p.total_vt = p.tiles_x * p.tiles_y * p.D * a->N;
-    int S = (2 * num_sms()) / p.units; if (S < 1) S = 1;       // ~2 CTAs per SM (smem allows one resident: two waves)
-    if (S > p.total_vt) S = p.total_vt;
+    p.total_L = p.tiles_x * p.tiles_y * a->N * p.D;
+    int S = num_sms() / p.units; if (S < 1) S = 1;             // one resident CTA per SM, a single wave
+    if (S > p.total_L) S = p.total_L;
     p.S = S;
     return 0;
 }
@@ -378,7 +438,7 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     } else mx1 = mx0;
     rc = make_dy_map(&mdy, a->dy, a->N, a->Co, a->kw, p.Do, p.Ho, a->W, p.NTW, p.TY);
     if (rc) return rc;
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 1024;
+    const size_t smem = (size_t)p.SA * p.a_bytes + (size_t)p.SB * p.b_plane_bytes + 1024 + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
