@@ -211,8 +211,8 @@ def main():
 
         # dominant kernel alone: conv_tc_kernel on the up_convs.1.conv1 shape, CUDA events on the launch stream
         d = DOM
-        q0 = engine.QP.empty(d['N'], d['C0'], d['S'], d['S'], d['S'], dev)
-        q1 = engine.QP.empty(d['N'], d['C1'], d['S'], d['S'], d['S'], dev)
+        q0 = engine.QP.empty_half(d['N'], d['C0'], d['S'], d['S'], d['S'], dev)
+        q1 = engine.QP.empty_half(d['N'], d['C1'], d['S'], d['S'], d['S'], dev)
         q0.t.normal_(), q1.t.normal_()
         w = torch.randn(d['Co'], d['C0'] + d['C1'], 3, 3, 3, device=dev) * 0.05
         wpk = engine.pack_weights(0, w, None, d['C0'], d['C1'], d['Co'], (3, 3, 3))

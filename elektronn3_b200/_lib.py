@@ -27,7 +27,8 @@ class ConvArgs(ctypes.Structure):
         ('n_total', c_i32),
         ('dst0', c_void_p), ('Cd0', c_i32),
         ('dst1', c_void_p), ('Cd1', c_i32),
-        ('relu', c_i32), ('round_tf32', c_i32),
+        ('relu', c_i32), ('half_out', c_i32),
+        ('out_scale', c_void_p),
         ('stats', c_void_p), ('stats_channels', c_i32),
         ('scatter', c_i32), ('sd', c_i32), ('sh', c_i32), ('sw', c_i32),
         ('Ds', c_i32), ('Hs', c_i32), ('Ws', c_i32),
@@ -63,6 +64,7 @@ class NormBwdArgs(ctypes.Structure):
         ('gamma', c_void_p), ('mean', c_void_p), ('rstd', c_void_p),
         ('fwd_stats', c_void_p),
         ('sums', c_void_p),
+        ('amax', c_void_p), ('dy_scale', c_void_p),
         ('m1', c_void_p), ('m2', c_void_p),
         ('dgamma', c_void_p), ('dbeta', c_void_p), ('dbias', c_void_p),
         ('dy', c_void_p), ('s2d', c_i32), ('sd', c_i32), ('sh', c_i32), ('sw', c_i32),
@@ -102,7 +104,7 @@ SIGNATURES = {
     'e3b_wgrad': (c_int, [ctypes.POINTER(WgradArgs), c_void_p]),
     'e3b_norm_finalize': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_i64, c_void_p, c_void_p, c_float,
                                   c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    'e3b_norm_act': (c_int, [c_void_p] * 8 + [c_int] * 9 + [c_void_p]),
+    'e3b_norm_act': (c_int, [c_void_p] * 8 + [c_int] * 10 + [c_void_p]),
     'e3b_norm_bwd_reduce': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_finalize': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_apply': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),

@@ -2,6 +2,7 @@
 // Hand-written inline PTX; no CUTLASS dependency.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -15,6 +16,15 @@
 // MN-major operand (K = voxels: wgrad), and (b) a spatial shift by one voxel is a +16 B shift of the
 // shared-memory start address, which is what lets all 27 taps of a 3x3x3 stencil read ONE halo tile.
 __host__ __device__ inline int e3b_cpad(int c) { return (c + 7) & ~7; }
+
+// "QH" (operand layout): the tensors the forward / dgrad MMAs read -- network input, activations, pooled
+// activations, conv-output gradients -- are stored as fp16 (N, Ch, D, H, W, 8) with Ch = ceil16(C) / 8:
+// channel c lives in plane c / 8, lane c % 8; again one voxel of one plane is a 16-byte unit, so every
+// statement above about core matrices and +16 B tap shifts holds unchanged, and one MMA (kind::f16, K = 16)
+// consumes two planes.  fp16 carries the same 10 explicit mantissa bits as TF32 (the reference's GPU
+// arithmetic): inside the fp16 normal range the stored operand is bit-for-bit the TF32-rounded value.
+// Gradients are kept in range by a per-tensor power-of-two scale (e3b_norm_bwd_*), undone in the dgrad epilogue.
+__host__ __device__ inline int e3b_cpad16(int c) { return (c + 15) & ~15; }
 
 namespace e3b {
 
@@ -134,6 +144,21 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int n, int a_mn_major, int b
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// Instruction descriptor for kind::f16 with fp16 operands (a_format = b_format = 0), fp32 accumulate, M = 128.
+__host__ __device__ inline uint32_t umma_idesc_f16(int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(128 >> 4) << 24);
+}
+
+E3B_DEVINL void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 E3B_DEVINL void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -163,6 +188,20 @@ E3B_DEVINL float tf32_rn(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
+}
+
+// 4 floats -> 4 halves (round to nearest even) packed in 8 bytes
+E3B_DEVINL uint2 pack_half4(float a, float b, float c, float d) {
+    const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&lo);
+    r.y = *reinterpret_cast<const uint32_t*>(&hi);
+    return r;
+}
+E3B_DEVINL float4 unpack_half4(const uint2& u) {
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 E3B_DEVINL bool elect_one() {

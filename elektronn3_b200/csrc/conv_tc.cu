@@ -5,10 +5,11 @@
 // (:178-180) and `upconv2` (:152-165).
 //
 // Design ("halo-tile implicit GEMM"):
-//  * activations are QP tensors (see common.cuh).  A CTA tile is 8(x) x 16(y) x TZ(z) output voxels =
-//    TZ accumulators of M=128 rows x N columns in TMEM.
-//  * per 8 input channels ONE TMA box load brings the (8+kw-1) x (16+kh-1) x (TZ+kd-1) halo tile of
-//    those channels into shared memory (zero fill outside the volume == conv zero padding).  Because
+//  * the operand is a QH tensor (fp16, 8 channels per 16-byte voxel unit, see common.cuh); the output an
+//    fp32 QP tensor (or QH again when the epilogue already produces the next layer's operand).  A CTA tile
+//    is 8(x) x 16(y) x TZ(z) output voxels = TZ accumulators of M=128 rows x N columns in TMEM.
+//  * per 16 input channels (two 16-byte planes = the K of one kind::f16 MMA) ONE TMA box load brings the
+//    (8+kw-1) x (16+kh-1) x (TZ+kd-1) halo tile of those channels into shared memory (zero fill outside the volume == conv zero padding).  Because
 //    one voxel is a 16-byte quad in the no-swizzle canonical UMMA layout, every stencil tap is the
 //    same tile read through a descriptor whose start address is shifted by
 //    ((dz*HY + dy)*HX + dx) * 16 B: 27 taps x TZ planes of MMAs are issued per loaded tile, so L2->smem
@@ -36,7 +37,7 @@ struct ConvTcParams {
     int TZ;                      // output planes per tile
     int HX, HY, HZ;              // halo tile extents
     int tiles_x, tiles_y, tiles_z, n_ntiles, total_tiles;
-    int chunks0, chunks1;        // 8-channel K chunks from source 0 / source 1
+    int chunks0, chunks1;        // 16-channel K chunks from source 0 / source 1
     int off1_d, off1_h, off1_w;  // crop offset into source 1
     int NT;                      // columns per N tile (multiple of 16, <= 256)
     int TG;                      // taps per weight stage
@@ -50,7 +51,8 @@ struct ConvTcParams {
     int cq0_alloc, cq1_alloc;    // planes allocated in dst0 / dst1
     int relu;
     int debug;                   // accumulate role timings into g_conv_dbg
-    int round_tf32;              // round the stored output to TF32 (it feeds the next MMA unrounded otherwise)
+    int half_out;                // store the output as a QH (fp16) operand tensor: it feeds the next MMA
+    const float* out_scale;      // optional device scalar multiplied into the accumulator (gradient un-scaling)
     double* stats;               // [N][Cstat][2] sum / sumsq (fp64 atomics) or null
     int Cstat;
     int scatter;                 // 1: k=s transposed conv, column n = tap*Cup + co, dst is the fine grid
@@ -85,7 +87,7 @@ E3B_DEVINL void issue_tap_planes(uint32_t acc, uint64_t ad, uint64_t bd, uint32_
                                  uint32_t nt)
 {
 #pragma unroll
-    for (int pl = 0; pl < TZ; pl++) umma_tf32(acc + (uint32_t)pl * nt, ad + (uint64_t)((uint32_t)pl * plane_step), bd, idesc, accum);
+    for (int pl = 0; pl < TZ; pl++) umma_f16(acc + (uint32_t)pl * nt, ad + (uint64_t)((uint32_t)pl * plane_step), bd, idesc, accum);
 }
 
 E3B_DEVINL void issue_tap(int tz, uint32_t acc, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accum, uint32_t plane_step,
@@ -196,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         // ===================== MMA issuer =====================
         // The whole warp runs the loop (warp-uniform control flow keeps the descriptor arithmetic on the
         // uniform datapath); one elected lane issues the MMAs and the commits.
-        const uint32_t idesc = umma_idesc_tf32(p.NT, 0, 0);
+        const uint32_t idesc = umma_idesc_f16(p.NT, 0, 0);
         // descriptor templates with a zero address field; one voxel == 16 B == one address unit
         const uint64_t a_tmpl = umma_desc(0, (uint32_t)(p.HX * p.HY * p.HZ * 16), (uint32_t)(p.HX * 16));
         const uint64_t b_tmpl = umma_desc(0, (uint32_t)(p.NT * 16), 128);
@@ -261,6 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         uint32_t it = 0;
         unsigned long long dbg[16] = {0};
         DBG_T0(t_all);
+        const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.f;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it++) {
             const uint32_t buf = it & 1, use = it >> 1;
             int nt, n, z0, y0, x0;
@@ -305,17 +308,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                         float v[16];
                         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)(pl * p.NT + cb), v);
 #pragma unroll
-                        for (int j = 0; j < 16; j++) v[j] += bias_v[j];
+                        for (int j = 0; j < 16; j++) v[j] = fmaf(v[j], oscale, bias_v[j]);
                         if (p.relu) {
 #pragma unroll
                             for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], 0.f);
                         }
-                        if (p.round_tf32) {
-#pragma unroll
-                            for (int j = 0; j < 16; j++) v[j] = tf32_rn(v[j]);
-                        }
                         bool sv = valid;
-                        if (!p.scatter) {
+                        if (p.half_out) {
+                            // operand tensor (QH): 16 columns = two 16-byte units (planes ncol/8 and ncol/8 + 1)
+                            int fz = z, fy = y, fx = x, hd = p.Do, hh = p.Ho, hw = p.Wo, hp = ncol >> 3;
+                            if (p.scatter) {
+                                fz = z * p.sd + ti; fy = y * p.sh + tj; fx = x * p.sw + tk;
+                                hd = p.Ds; hh = p.Hs; hw = p.Ws; hp = co >> 3;
+                                sv = valid && fz < p.Ds && fy < p.Hs && fx < p.Ws;
+                            }
+                            if (sv) {
+#pragma unroll
+                                for (int j8 = 0; j8 < 2; j8++) {
+                                    const int hpl = hp + j8;
+                                    if (hpl < p.cq0_alloc) {
+                                        const uint2 lo = pack_half4(v[j8 * 8], v[j8 * 8 + 1], v[j8 * 8 + 2], v[j8 * 8 + 3]);
+                                        const uint2 hi = pack_half4(v[j8 * 8 + 4], v[j8 * 8 + 5], v[j8 * 8 + 6], v[j8 * 8 + 7]);
+                                        size_t o = ((((size_t)n * p.cq0_alloc + hpl) * hd + fz) * hh + fy) * (size_t)hw + fx;
+                                        reinterpret_cast<uint4*>(p.dst0)[o] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+                                    }
+                                }
+                            }
+                        } else if (!p.scatter) {
                             if (valid) {
 #pragma unroll
                                 for (int j4 = 0; j4 < 4; j4++) {
@@ -356,15 +375,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                     // per-channel sum / sumsq over the warp's 32 rows x npl planes (x taps): 16-value butterfly
 #pragma unroll
                     for (int step = 0; step < 4; step++) {
-                        const int half = 8 >> step;           // 8,4,2,1 values kept
+                        const int keepn = 8 >> step;          // 8,4,2,1 values kept
                         const int bit = 1 << step;            // exchange partner lane bit
                         const bool upper = (lane & bit) != 0;
 #pragma unroll
-                        for (int j = 0; j < half; j++) {
-                            float send_s = upper ? s[j] : s[j + half];
-                            float send_q = upper ? ss[j] : ss[j + half];
-                            float keep_s = upper ? s[j + half] : s[j];
-                            float keep_q = upper ? ss[j + half] : ss[j];
+                        for (int j = 0; j < keepn; j++) {
+                            float send_s = upper ? s[j] : s[j + keepn];
+                            float send_q = upper ? ss[j] : ss[j + keepn];
+                            float keep_s = upper ? s[j + keepn] : s[j];
+                            float keep_q = upper ? ss[j + keepn] : ss[j];
                             s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
                             ss[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
                         }
@@ -528,8 +547,8 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
     p.HX = kTX + a->kw - 1; p.HY = kTY + a->kh - 1; p.HZ = tz + a->kd - 1;
     p.tiles_x = (p.Wo + kTX - 1) / kTX; p.tiles_y = (p.Ho + kTY - 1) / kTY; p.tiles_z = (p.Do + tz - 1) / tz;
     p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_z * p.n_ntiles * a->N;
-    p.chunks0 = e3b_cpad(a->C0) / 8;
-    p.chunks1 = a->src1 ? e3b_cpad(a->C1) / 8 : 0;
+    p.chunks0 = e3b_cpad16(a->C0) / 16;
+    p.chunks1 = a->src1 ? e3b_cpad16(a->C1) / 16 : 0;
     p.off1_d = a->off1_d; p.off1_h = a->off1_h; p.off1_w = a->off1_w;
     p.a_stage_bytes = (uint32_t)(p.HX * p.HY * p.HZ * 16 * 2);
     // weight stage: largest tap group (27, 9, 3, 1) that fits 40 KB
@@ -551,25 +570,26 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
         return set_error("conv: tile does not fit shared memory");
     p.SA = sa; p.SB = sb;
     p.bias = a->bias; p.n_bias = a->n_bias;
-    p.dst0 = a->dst0; p.dst1 = a->dst1;
-    p.cq0_alloc = e3b_cpad(a->Cd0) / 4;
+    p.dst0 = reinterpret_cast<float*>(a->dst0); p.dst1 = a->dst1;
+    p.cq0_alloc = a->half_out ? e3b_cpad16(a->Cd0) / 8 : e3b_cpad(a->Cd0) / 4;      // 16-byte planes in dst0
     p.cq1_alloc = a->dst1 ? e3b_cpad(a->Cd1) / 4 : 0;
     p.cq0 = a->dst1 ? p.cq0_alloc : (1 << 30);
-    p.relu = a->relu; p.round_tf32 = a->round_tf32;
+    p.relu = a->relu; p.half_out = a->half_out; p.out_scale = a->out_scale;
+    if (a->half_out && a->dst1) return set_error("conv: the fp16 operand output has a single destination");
+    if (a->half_out && a->stats) return set_error("conv: statistics are taken from an fp32 output");
     p.debug = getenv("E3B_CONV_DEBUG") != nullptr;
     p.stats = a->stats; p.Cstat = a->stats_channels;
     p.scatter = a->scatter; p.sd = a->sd; p.sh = a->sh; p.sw = a->sw;
-    p.Cup = a->scatter ? e3b_cpad(a->Cd0) : 1;
-    if (a->scatter && p.Cup % 16) p.Cup = (p.Cup + 15) & ~15;
+    p.Cup = a->scatter ? e3b_cpad16(a->Cd0) : 1;
     p.Ds = a->Ds; p.Hs = a->Hs; p.Ws = a->Ws;
-    p.wpk = a->wpk;
+    p.wpk = reinterpret_cast<const float*>(a->wpk);
 
     CUtensorMap m0, m1;
-    int rc = make_qp_tensor_map(&m0, a->src0, a->N, p.chunks0 * 2, a->D, a->H, a->W, a->D, a->H, a->W, p.HX, p.HY,
+    int rc = make_qp_tensor_map(&m0, reinterpret_cast<const float*>(a->src0), a->N, p.chunks0 * 2, a->D, a->H, a->W, a->D, a->H, a->W, p.HX, p.HY,
                                 p.HZ, 2);
     if (rc) return rc;
     if (a->src1) {
-        const float* v1 = a->src1 + (((size_t)a->off1_d * a->H1 + a->off1_h) * a->W1 + a->off1_w) * 4;
+        const float* v1 = reinterpret_cast<const float*>(a->src1) + (((size_t)a->off1_d * a->H1 + a->off1_h) * a->W1 + a->off1_w) * 4;
         rc = make_qp_tensor_map(&m1, v1, a->N, p.chunks1 * 2, a->D, a->H, a->W, a->D1, a->H1, a->W1, p.HX, p.HY, p.HZ, 2);
         if (rc) return rc;
     } else {

@@ -30,14 +30,23 @@ E3B_DEVINL void store_planar(float* __restrict__ pl, const float4& v, int n, int
     if (c + 3 < C) pl[o + 3 * plane] = v.w;
 }
 
+// fp16 operand tensor (QH): (N, Ch, S voxels, 8 halves), Ch = ceil16(C)/8.  The fp32 quad `cq` (channels
+// 4cq..4cq+3) of voxel v is the 8-byte half (cq & 1) of unit ((n*Ch + cq/2)*S + v).
+E3B_DEVINL size_t qh_index(int n, int Ch, int cq, size_t S, size_t v) { return (((size_t)n * Ch + (cq >> 1)) * S + v) * 2 + (cq & 1); }
+E3B_DEVINL void store_qh(uint2* __restrict__ qh, const float4& v, int n, int Ch, int cq, size_t S, size_t vox) {
+    qh[qh_index(n, Ch, cq, S, vox)] = pack_half4(v.x, v.y, v.z, v.w);
+}
+
 // ------------------------------------------------------------------------------------------------
-// NCDHW box -> QP   (network input, Predictor tile gather)
+// NCDHW box -> QH   (network input, Predictor tile gather)
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_kernel(const float* __restrict__ src, const int32_t* __restrict__ origins, float4* __restrict__ dst,
+__global__ void pack_kernel(const float* __restrict__ src, const int32_t* __restrict__ origins, uint2* __restrict__ dst,
                             float* __restrict__ dst_pl, int N, int C, int Cq, int D, int H, int W, int Dv, int Hv, int Wv,
                             int z0, int y0, int x0, int single)
 {
+    // Cq = ceil16(C)/4 fp32 quads per voxel: the padding channels of the 16-channel chunks are written as 0
     const size_t total = (size_t)N * Cq * D * H * W;
+    const size_t S = (size_t)D * H * W;
     const size_t plane = (size_t)Dv * Hv * Wv;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
@@ -60,8 +69,8 @@ __global__ void pack_kernel(const float* __restrict__ src, const int32_t* __rest
             }
         }
         const float4 q = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
-        dst[i] = q;
-        if (dst_pl) store_planar(dst_pl, q, n, cq, C, D, H, (W + 3) & ~3, z, y, x);
+        store_qh(dst, q, n, Cq >> 1, cq, S, ((size_t)z * H + y) * W + x);
+        if (dst_pl && cq * 4 < C) store_planar(dst_pl, q, n, cq, C, D, H, (W + 3) & ~3, z, y, x);
     }
 }
 
@@ -77,7 +86,7 @@ __global__ void unpack_kernel(const float* __restrict__ src, float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight packing: torch layout -> [ntile][chunk8][tap][kq 2][NT][4] (K-major no-swizzle smem image)
+// weight packing: torch layout -> fp16 [ntile][chunk16][tap][kq 2][NT][8] (K-major no-swizzle smem image)
 // ------------------------------------------------------------------------------------------------
 struct PackDims { int ktot, ntot, taps, NT; };
 
@@ -85,53 +94,56 @@ static PackDims pack_dims(int mode, int C0, int C1, int Co, int kd, int kh, int 
 {
     PackDims d;
     const int t = kd * kh * kw;
-    const int cin = cpad8(C0) + (C1 > 0 ? cpad8(C1) : 0);
     switch (mode) {
-    case 0: d.ktot = cin; d.ntot = cpad16(Co); d.taps = t; break;
-    case 1: d.ktot = cpad8(Co); d.ntot = cpad16(cin); d.taps = t; break;
-    case 2: d.ktot = cpad8(C0); d.ntot = t * cpad16(Co); d.taps = 1; break;
-    default: d.ktot = t * cpad8(Co); d.ntot = cpad16(C0); d.taps = 1; break;
+    case 0: d.ktot = cpad16(C0) + (C1 > 0 ? cpad16(C1) : 0); d.ntot = cpad16(Co); d.taps = t; break;
+    case 1: d.ktot = cpad16(Co); d.ntot = cpad16(cpad8(C0) + (C1 > 0 ? cpad8(C1) : 0)); d.taps = t; break;
+    case 2: d.ktot = cpad16(C0); d.ntot = t * cpad16(Co); d.taps = 1; break;
+    default: d.ktot = cpad16(t * cpad8(Co)); d.ntot = cpad16(C0); d.taps = 1; break;
     }
     d.NT = conv_ntile_width(d.ntot);
     return d;
 }
 
 __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, const float* __restrict__ scale,
-                                    float* __restrict__ dst, int C0, int C1, int Co, int tu, PackDims d)
+                                    __half* __restrict__ dst, int C0, int C1, int Co, int tu, PackDims d)
 {
     const size_t total = (size_t)d.ktot * d.ntot * d.taps;
-    const int C0p = cpad8(C0), Cop8 = cpad8(Co), Cop16 = cpad16(Co);
-    const int nchunks = d.ktot / 8;
+    const int C0p16 = cpad16(C0), C0p8 = cpad8(C0), Cop8 = cpad8(Co), Cop16 = cpad16(Co);
+    const int nchunks = d.ktot / 16;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
-        const int k4 = (int)(r % 4); r /= 4;
+        const int k8 = (int)(r % 8); r /= 8;
         const int nn = (int)(r % d.NT); r /= d.NT;
         const int kq = (int)(r % 2); r /= 2;
         const int tap = (int)(r % d.taps); r /= d.taps;
         const int chunk = (int)(r % nchunks);
         const int nt = (int)(r / nchunks);
-        const int k = chunk * 8 + kq * 4 + k4;
+        const int k = chunk * 16 + kq * 8 + k8;
         const int n = nt * d.NT + nn;
         float v = 0.f;
-        if (mode == 0 || mode == 1) {
-            const int kc = mode == 0 ? k : n;      // index into the [pad8(C0) | pad8(C1)] channel space
-            const int oc = mode == 0 ? n : k;      // output channel of the torch weight
+        if (mode == 0) {
+            // K space [pad16(C0) | pad16(C1)] (the operand tensors of the two sources), N = output channel
             int ci = -1;
-            if (kc < C0p) { if (kc < C0) ci = kc; }
-            else if (kc - C0p < C1) ci = C0 + kc - C0p;
-            if (ci >= 0 && oc < Co) {
-                const int tp = mode == 0 ? tap : d.taps - 1 - tap;
-                v = w[((size_t)oc * (C0 + C1) + ci) * d.taps + tp];
-                if (scale && mode == 0) v *= scale[oc];
+            if (k < C0p16) { if (k < C0) ci = k; }
+            else if (k - C0p16 < C1) ci = C0 + k - C0p16;
+            if (ci >= 0 && n < Co) {
+                v = w[((size_t)n * (C0 + C1) + ci) * d.taps + tap];
+                if (scale) v *= scale[n];
             }
+        } else if (mode == 1) {
+            // K = output channel of the forward conv, N space [pad8(C0) | pad8(C1)] (the fp32 QP gradient outputs)
+            int ci = -1;
+            if (n < C0p8) { if (n < C0) ci = n; }
+            else if (n - C0p8 < C1) ci = C0 + n - C0p8;
+            if (ci >= 0 && k < Co) v = w[((size_t)k * (C0 + C1) + ci) * d.taps + (d.taps - 1 - tap)];
         } else if (mode == 2) {
             const int t = n / Cop16, co = n % Cop16;
             if (k < C0 && co < Co) v = w[((size_t)k * Co + co) * tu + t];
         } else {
             const int t = k / Cop8, co = k % Cop8;
-            if (n < C0 && co < Co) v = w[((size_t)n * Co + co) * tu + t];
+            if (t < tu && n < C0 && co < Co) v = w[((size_t)n * Co + co) * tu + t];
         }
-        dst[i] = tf32_rn(v);
+        dst[i] = __float2half_rn(v);
     }
 }
 
@@ -225,8 +237,10 @@ E3B_DEVINL void store_planar_shifted(float* __restrict__ pl, const float4& v, in
 // the per-(n,c) constants are loaded once and only one integer division per thread is needed.
 struct NormActDev {
     const float4* y; const float* scale; const float* shift;
-    float4* a; float4* pooled; float* a_pl; float* pooled_pl; uchar4* pool_idx;
-    int C, N, Cq, D, H, W, pkd, pkh, pkw, relu;
+    const uint2* yh;             // y_half: the input is itself a QH operand tensor (eval path: pooling only)
+    uint2* a; uint2* pooled;     // QH outputs
+    float* a_pl; float* pooled_pl; uchar4* pool_idx;
+    int C, N, Cq, Ch, D, H, W, pkd, pkh, pkw, relu;
     int Dp, Hp, Wp;
 };
 
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
         const int v = v0 + j * 256;
         if (v >= S) continue;
         const float4 r = norm_relu_round(yv[j], sc, sh, p.scale != nullptr, p.relu);
-        if (p.a) p.a[base + v] = r;
+        if (p.a) store_qh(p.a, r, n, p.Ch, cq, (size_t)S, (size_t)v);
         if (p.a_pl) {
             const int z = v / HW, hw = v - z * HW, yy = hw / p.W, x = hw - yy * p.W;
             store_planar(p.a_pl, r, n, cq, p.C, p.D, p.H, Wpl, z, yy, x);
@@ -295,6 +309,7 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
     float4 sc, sh;
     load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
     const size_t base = ((size_t)n * p.Cq + cq) * p.D;
+    const size_t S = (size_t)p.D * p.H * p.W;
     const int Wpl = (p.W + 3) & ~3;
     float4 m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
     uchar4 idx = make_uchar4(0, 0, 0, 0);
@@ -310,9 +325,11 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
             for (int dx = 0; dx < 2; dx++) {
                 const int x = xp * p.pkw + dx;
                 if (dx >= p.pkw || x >= p.W) continue;
-                const size_t o = ((base + z) * p.H + yy) * p.W + x;
-                const float4 v = norm_relu_round(p.y[o], sc, sh, p.scale != nullptr, p.relu);
-                if (p.a) p.a[o] = v;
+                const size_t vox = ((size_t)z * p.H + yy) * p.W + x;
+                float4 v;
+                if (p.yh) v = unpack_half4(p.yh[qh_index(n, p.Ch, cq, S, vox)]);
+                else v = norm_relu_round(p.y[base * p.H * p.W + vox], sc, sh, p.scale != nullptr, p.relu);
+                if (p.a) store_qh(p.a, v, n, p.Ch, cq, S, vox);
                 if (p.a_pl) store_planar(p.a_pl, v, n, cq, p.C, p.D, p.H, Wpl, z, yy, x);
                 const unsigned char slot = (unsigned char)((dz * p.pkh + dy) * p.pkw + dx);
                 if (v.x > m.x) { m.x = v.x; idx.x = slot; }
@@ -323,7 +340,7 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
         }
     }
     const size_t op = ((((size_t)n * p.Cq + cq) * p.Dp + zp) * p.Hp + yp) * p.Wp + xp;
-    if (p.pooled) p.pooled[op] = m;
+    if (p.pooled) store_qh(p.pooled, m, n, p.Ch, cq, (size_t)p.Dp * p.Hp * p.Wp, ((size_t)zp * p.Hp + yp) * p.Wp + xp);
     if (p.pool_idx) p.pool_idx[op] = idx;
     if (p.pooled_pl) store_planar(p.pooled_pl, m, n, cq, p.C, p.Dp, p.Hp, (p.Wp + 3) & ~3, zp, yp, xp);
 }
@@ -341,10 +358,21 @@ struct NormBwdDev {
     int relu, s2d;
     const float *gamma, *mean, *rstd, *m1, *m2;
     double* sums;
-    float4* dy;
+    unsigned int* amax;                      // [N][pad8(C)][2] max |dr|, max |xhat| (float bits; reduce pass)
+    float* dy_scale;                         // [0] bound on |dy| (float bits), [1] 2^k, [2] 2^-k
+    uint2* dy;                               // QH output, scaled by 2^k
+    int Ch;                                  // 16-byte planes of dy
     float* dy_pl;
     int pl_kw, pl_pw, pl_Wx;
 };
+
+// power-of-two scale that brings a tensor bounded by `bound` to at most 2^14 (fp16 max is 2^16)
+E3B_DEVINL float dy_scale_from_bound(float bound) {
+    if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+    int e = 14 - (int)ceilf(log2f(bound));
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    return exp2f((float)e);
+}
 
 // Inputs of one voxel of the backward pass, loaded up front (several voxels per thread are in flight
 // before the first one is used).
@@ -407,6 +435,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p
     const int HW = p.H * p.W;
     const int total = p.D * HW;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float md[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};       // max |dr|, max |xhat|: bound for the fp16 scale of dy
     const size_t base = ((size_t)n * p.Cq + cq) * (size_t)total;
     const int stride = gridDim.x * blockDim.x;
     for (int v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += kRedVpt * stride) {
@@ -427,19 +456,25 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p
             s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
             s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]);
             s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
+            md[0] = fmaxf(md[0], fabsf(dr.x)); md[1] = fmaxf(md[1], fabsf(dr.y));
+            md[2] = fmaxf(md[2], fabsf(dr.z)); md[3] = fmaxf(md[3], fabsf(dr.w));
+            mx[0] = fmaxf(mx[0], fabsf(xh.x)); mx[1] = fmaxf(mx[1], fabsf(xh.y));
+            mx[2] = fmaxf(mx[2], fabsf(xh.z)); mx[3] = fmaxf(mx[3], fabsf(xh.w));
         }
     }
-    __shared__ float red[8][8];
+    __shared__ float red[8][16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         for (int o = 16; o > 0; o >>= 1) {
             s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
             s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+            md[j] = fmaxf(md[j], __shfl_xor_sync(0xffffffffu, md[j], o));
+            mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
         }
     }
     if (lane == 0) {
-        for (int j = 0; j < 4; j++) { red[warp][j] = s1[j]; red[warp][4 + j] = s2[j]; }
+        for (int j = 0; j < 4; j++) { red[warp][j] = s1[j]; red[warp][4 + j] = s2[j]; red[warp][8 + j] = md[j]; red[warp][12 + j] = mx[j]; }
     }
     __syncthreads();
     if (threadIdx.x < 8) {
@@ -447,6 +482,12 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += (double)red[w][threadIdx.x];
         const int j = threadIdx.x & 3, which = threadIdx.x >> 2;
         atomicAdd(p.sums + (nc + j) * 2 + which, t);
+    } else if (threadIdx.x < 16 && p.amax) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t = fmaxf(t, red[w][threadIdx.x]);
+        const int j = threadIdx.x & 3, which = (threadIdx.x >> 2) - 2;
+        if (!(t < 3.0e38f)) t = 3.0e38f;                     // inf / nan: the scale falls back to 1
+        atomicMax(p.amax + (nc + j) * 2 + which, __float_as_uint(t));   // non-negative floats order like their bits
     }
 }
 
@@ -454,7 +495,8 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ sums, const 
                                          int G, int N, int C, int Cp, double S, const float* __restrict__ gamma,
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          float* __restrict__ m1o, float* __restrict__ m2o, float* __restrict__ dgamma,
-                                         float* __restrict__ dbeta, float* __restrict__ dbias)
+                                         float* __restrict__ dbeta, float* __restrict__ dbias,
+                                         const unsigned int* __restrict__ amax, float* __restrict__ dy_scale)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * Cp) return;
@@ -476,6 +518,14 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ sums, const 
         m1 *= ga / (S * N); m2 *= ga / (S * N);
     }
     m1o[i] = (float)m1; m2o[i] = (float)m2;
+    if (amax && dy_scale) {
+        // |dy| = |rstd (gamma dr - m1 - xhat m2)| <= rstd (|gamma| max|dr| + |m1| + max|xhat| |m2|)
+        const float ga = (gamma && mode != 0) ? fabsf(gamma[c]) : 1.f;
+        const float r = rstd ? rstd[i] : 1.f;
+        const float bound = r * (ga * __uint_as_float(amax[(size_t)i * 2]) + fabsf((float)m1) +
+                                 __uint_as_float(amax[(size_t)i * 2 + 1]) * fabsf((float)m2));
+        atomicMax(reinterpret_cast<unsigned int*>(dy_scale), __float_as_uint(bound < 3.0e38f ? bound : 3.0e38f));
+    }
     if (n != 0) return;
     // per-channel parameter gradients (loop over the batch; for group mode m1/m2 differ per sample)
     double dg = 0.0, db = 0.0, dbi = 0.0;
@@ -525,6 +575,9 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
     }
     const int HWg = p.Hg * p.Wg, Sg = p.Dg * HWg;
     const int v0 = blockIdx.x * (256 * kAppVpt) + threadIdx.x;
+    // fp16 range: dy is stored multiplied by 2^k (undone by the dgrad epilogue through dy_scale[2])
+    const float dscale = dy_scale_from_bound(p.dy_scale[0]);
+    if (blockIdx.x == 0 && cq == 0 && n == 0 && threadIdx.x == 0) { p.dy_scale[1] = dscale; p.dy_scale[2] = 1.f / dscale; }
     VoxIn in[kAppVpt];
     int zs[kAppVpt], ys[kAppVpt], xs[kAppVpt];
 #pragma unroll
@@ -546,7 +599,6 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
         const bool inside = z < p.D && yy < p.H && x < p.W;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (inside) {
-            const size_t ov = ((((size_t)n * p.Cq + cq) * p.D + z) * p.H + yy) * p.W + x;
             float4 dr, xh;
             voxel_grad(p, in[j], mu, rs, sc, sh, dr, xh);
             o.x = rs.x * (ga.x * dr.x - m1.x - xh.x * m2.x);
@@ -556,7 +608,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
             // dy is the MMA operand of dgrad and wgrad: store it rounded to TF32
             o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
             if (!p.s2d) {
-                p.dy[ov] = o;
+                const float4 os = make_float4(o.x * dscale, o.y * dscale, o.z * dscale, o.w * dscale);
+                store_qh(p.dy, os, n, p.Ch, cq, (size_t)p.D * p.H * p.W, ((size_t)z * p.H + yy) * p.W + x);
                 if (p.dy_pl) store_planar_shifted(p.dy_pl, o, n, cq, p.C, p.D, p.H, p.W, z, yy, x, p.pl_kw, p.pl_pw, p.pl_Wx);
             }
         }
@@ -567,7 +620,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
             const int NS = p.wd * p.wh * p.ww;
             const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
             const size_t iw = ((size_t)zw * p.Hw + yw) * p.Ww + xw;
-            p.dy[(((size_t)n * NS + slot) * p.Cq + cq) * wins + iw] = o;
+            const float4 os = make_float4(o.x * dscale, o.y * dscale, o.z * dscale, o.w * dscale);
+            store_qh(p.dy, os, n, p.Ch, slot * p.Cq + cq, wins, iw);
             if (p.dy_pl) store_planar(p.dy_pl, o, n, slot * p.Cq + cq, NS * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
         }
     }
@@ -636,6 +690,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev
     const int xg = active ? t - row * Wg : 0;
     const int z = row / p.H, yy = row - z * p.H, x0 = xg * 4;
     const size_t ov = (((size_t)n * p.Cq + cq) * p.D * p.H + row) * (size_t)p.W + x0;
+    const float dscale = dy_scale_from_bound(p.dy_scale[0]);
+    if (blockIdx.x == 0 && cq == 0 && n == 0 && threadIdx.x == 0) { p.dy_scale[1] = dscale; p.dy_scale[2] = 1.f / dscale; }
     float4 o[4];
     if (active) {
         VoxIn in[4];
@@ -646,7 +702,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev
             float4 dr, xh;
             voxel_grad(p, in[j], c.mu, c.rs, c.sc, c.sh, dr, xh);
             o[j] = apply_formula(dr, xh, c.rs, c.ga, c.m1, c.m2);
-            p.dy[ov + j] = o[j];
+            const float4 os = make_float4(o[j].x * dscale, o[j].y * dscale, o[j].z * dscale, o[j].w * dscale);
+            store_qh(p.dy, os, n, p.Ch, cq, (size_t)p.D * p.H * p.W, (size_t)row * p.W + x0 + j);
         }
     } else {
 #pragma unroll
@@ -688,52 +745,6 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev
     }
 }
 
-// statistics pass, 4 consecutive voxels per thread and iteration.  grid: (chunks, Cq, N)
-__global__ void __launch_bounds__(256) norm_bwd_reduce_x4_kernel(const NormBwdDev p)
-{
-    const int cq = blockIdx.y, n = blockIdx.z;
-    BwdConsts c;
-    load_bwd_consts(p, n, cq, c, false);
-    const int Wg = p.W >> 2;
-    const int total = p.D * p.H * Wg;
-    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-    const size_t base = ((size_t)n * p.Cq + cq) * (size_t)p.D * p.H * p.W;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-        int z = 0, yy = 0, x0 = 0;
-        if (p.gp) { const int row = t / Wg; x0 = (t - row * Wg) * 4; z = row / p.H; yy = row - z * p.H; }
-        VoxIn in[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) load_vox(p, base + (size_t)t * 4 + j, n, cq, z, yy, x0 + j, in[j]);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float4 dr, xh;
-            voxel_grad(p, in[j], c.mu, c.rs, c.sc, c.sh, dr, xh);
-            s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
-            s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]);
-            s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
-        }
-    }
-    __shared__ float red[8][8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        for (int o = 16; o > 0; o >>= 1) {
-            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
-            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
-        }
-    }
-    if (lane == 0) {
-        for (int j = 0; j < 4; j++) { red[warp][j] = s1[j]; red[warp][4 + j] = s2[j]; }
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        double tt = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) tt += (double)red[w][threadIdx.x];
-        const int j = threadIdx.x & 3, which = threadIdx.x >> 2;
-        atomicAdd(p.sums + (((size_t)n * p.Cq + cq) * 4 + j) * 2 + which, tt);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // 1x1x1 head (+ softmax / argmax, crop-and-place)
 // ------------------------------------------------------------------------------------------------
@@ -749,7 +760,8 @@ __global__ void __launch_bounds__(256) head_kernel(const e3b_head_args p, int Cq
     }
     for (int i = threadIdx.x; i < p.Co; i += blockDim.x) sw[p.Co * Cp + i] = p.b ? p.b[i] : 0.f;
     __syncthreads();
-    const float4* a = reinterpret_cast<const float4*>(p.a);
+    const uint2* a = reinterpret_cast<const uint2*>(p.a);      // QH operand tensor
+    const int Ch = cpad16(p.C) / 8;
     const size_t box = (size_t)p.cn_d * p.cn_h * p.cn_w;
     const size_t total = (size_t)p.N * box;
     const size_t S = (size_t)p.D * p.H * p.W;
@@ -765,7 +777,7 @@ __global__ void __launch_bounds__(256) head_kernel(const e3b_head_args p, int Cq
 #pragma unroll
         for (int co = 0; co < kHeadMaxCo; co++) acc[co] = co < p.Co ? sw[p.Co * Cp + co] : 0.f;
         for (int cq = 0; cq < Cq; cq++) {
-            const float4 v = a[((size_t)n * Cq + cq) * S + vin];
+            const float4 v = unpack_half4(a[qh_index(n, Ch, cq, S, vin)]);
 #pragma unroll
             for (int co = 0; co < kHeadMaxCo; co++) {
                 if (co < p.Co) {
@@ -841,8 +853,8 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restr
 // ws[co][c] += sum_v dl[v][co]*a[v][c] ; ws[Co*Cp + co] += sum_v dl[v][co].   grid (chunks, Cq)
 // One pass over the activations: every thread keeps all Co partial sums of its 4 channels.
 template <int CO>
-__global__ void __launch_bounds__(256) head_bwd_w_kernel(const float* __restrict__ dl, const float4* __restrict__ a,
-                                                         double* __restrict__ ws, int N, int Cq, int Co, size_t S)
+__global__ void __launch_bounds__(256) head_bwd_w_kernel(const float* __restrict__ dl, const uint2* __restrict__ a,
+                                                         double* __restrict__ ws, int N, int Cq, int Ch, int Co, size_t S)
 {
     const int cq = blockIdx.y, Cp = Cq * 4;
     const size_t total = (size_t)N * S;
@@ -851,7 +863,7 @@ __global__ void __launch_bounds__(256) head_bwd_w_kernel(const float* __restrict
     for (int co = 0; co < CO; co++) { acc[co][0] = acc[co][1] = acc[co][2] = acc[co][3] = 0.f; sb[co] = 0.f; }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t n = i / S, v = i % S;
-        const float4 av = a[(n * Cq + cq) * S + v];
+        const float4 av = unpack_half4(a[qh_index((int)n, Ch, cq, S, v)]);
 #pragma unroll
         for (int co = 0; co < CO; co++) {
             if (co < Co) {
@@ -904,24 +916,24 @@ using namespace e3b;
 
 extern "C" {
 
-int e3b_pack_ncdhw(const float* src, float* dst_qp, float* dst_planar, int N, int C, int D, int H, int W, int Dv, int Hv,
+int e3b_pack_ncdhw(const float* src, void* dst_qp, float* dst_planar, int N, int C, int D, int H, int W, int Dv, int Hv,
                    int Wv, int z0, int y0, int x0, void* stream)
 {
     if (N <= 0 || C <= 0) return set_error("pack: empty tensor");
-    const int Cq = cpad8(C) / 4;
+    const int Cq = cpad16(C) / 4;
     const size_t total = (size_t)N * Cq * D * H * W;
-    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, nullptr, reinterpret_cast<float4*>(dst_qp),
+    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, nullptr, reinterpret_cast<uint2*>(dst_qp),
                                                                         dst_planar, N, C, Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0);
     return check_launch("pack_ncdhw");
 }
 
-int e3b_gather_tiles(const float* vol, const int32_t* origins, float* dst_qp, int B, int C, int D, int H, int W, int Dv,
+int e3b_gather_tiles(const float* vol, const int32_t* origins, void* dst_qp, int B, int C, int D, int H, int W, int Dv,
                      int Hv, int Wv, void* stream)
 {
     if (B <= 0 || C <= 0) return set_error("gather: empty batch");
-    const int Cq = cpad8(C) / 4;
+    const int Cq = cpad16(C) / 4;
     const size_t total = (size_t)B * Cq * D * H * W;
-    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vol, origins, reinterpret_cast<float4*>(dst_qp), nullptr,
+    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vol, origins, reinterpret_cast<uint2*>(dst_qp), nullptr,
                                                                         B, C, Cq, D, H, W, Dv, Hv, Wv, 0, 0, 0, 1);
     return check_launch("gather_tiles");
 }
@@ -938,17 +950,17 @@ int64_t e3b_packed_weight_floats(int mode, int C0, int C1, int Co, int kd, int k
     if (mode < 0 || mode > 3) return -1;
     PackDims d = pack_dims(mode, C0, C1, Co, kd, kh, kw);
     if (d.NT <= 0) return -1;
-    return (int64_t)d.ktot * d.ntot * d.taps;
+    return (int64_t)d.ktot * d.ntot * d.taps / 2;        // fp16 elements, counted in floats
 }
 
-int e3b_pack_weights(int mode, const float* w, const float* scale, float* dst, int C0, int C1, int Co, int kd, int kh,
+int e3b_pack_weights(int mode, const float* w, const float* scale, void* dst, int C0, int C1, int Co, int kd, int kh,
                      int kw, void* stream)
 {
     if (mode < 0 || mode > 3) return set_error("pack_weights: bad mode %d", mode);
     PackDims d = pack_dims(mode, C0, C1, Co, kd, kh, kw);
     if (d.NT <= 0) return set_error("pack_weights: unsupported output width %d", d.ntot);
     const size_t total = (size_t)d.ktot * d.ntot * d.taps;
-    pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mode, w, scale, dst, C0, C1, Co,
+    pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mode, w, scale, reinterpret_cast<__half*>(dst), C0, C1, Co,
                                                                                 kd * kh * kw, d);
     return check_launch("pack_weights");
 }
@@ -965,19 +977,21 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
     return check_launch("norm_finalize");
 }
 
-int e3b_norm_act(const float* y, const float* scale, const float* shift, float* a, float* pooled, float* a_planar,
+int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled, float* a_planar,
                  float* pooled_planar, uint8_t* pool_idx, int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w,
-                 int relu, void* stream)
+                 int relu, int y_is_half, void* stream)
 {
     const bool pooling = pooled || pooled_planar || pool_idx;
+    if (y_is_half && (!pooling || scale || a)) return set_error("norm_act: an fp16 input is only pooled (eval path)");
     if (!pooling) { pk_d = pk_h = pk_w = 1; }
     if (pk_d < 1 || pk_h < 1 || pk_w < 1 || pk_d > 2 || pk_h > 2 || pk_w > 2) return set_error("norm_act: pooling kernel must be 1 or 2 per dim");
     if ((scale == nullptr) != (shift == nullptr)) return set_error("norm_act: scale and shift go together");
     NormActDev p;
-    p.y = reinterpret_cast<const float4*>(y); p.scale = scale; p.shift = shift;
-    p.a = reinterpret_cast<float4*>(a); p.pooled = reinterpret_cast<float4*>(pooled);
+    p.y = y_is_half ? nullptr : reinterpret_cast<const float4*>(y); p.scale = scale; p.shift = shift;
+    p.yh = y_is_half ? reinterpret_cast<const uint2*>(y) : nullptr;
+    p.a = reinterpret_cast<uint2*>(a); p.pooled = reinterpret_cast<uint2*>(pooled);
     p.a_pl = a_planar; p.pooled_pl = pooled_planar; p.pool_idx = reinterpret_cast<uchar4*>(pool_idx);
-    p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu;
+    p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu;
     p.Dp = (D + pk_d - 1) / pk_d; p.Hp = (H + pk_h - 1) / pk_h; p.Wp = (W + pk_w - 1) / pk_w;
     if (p.Cq > 65535 || N > 65535) return set_error("norm_act: too many channels / samples for the launch grid");
     if (pooling) {
@@ -1012,7 +1026,9 @@ static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)
     p.relu = a->relu; p.s2d = a->s2d;
     p.gamma = (a->mode == 0) ? nullptr : a->gamma;
     p.mean = a->mean; p.rstd = a->rstd; p.m1 = a->m1; p.m2 = a->m2;
-    p.sums = a->sums; p.dy = reinterpret_cast<float4*>(a->dy); p.dy_pl = a->dy_planar;
+    p.sums = a->sums; p.dy = reinterpret_cast<uint2*>(a->dy); p.dy_pl = a->dy_planar;
+    p.amax = a->amax; p.dy_scale = a->dy_scale;
+    p.Ch = a->s2d ? cpad16(p.wd * p.wh * p.ww * p.Cq * 4) / 8 : cpad16(a->C) / 8;
     p.pl_kw = a->planar_kw > 0 ? a->planar_kw : 1; p.pl_pw = a->planar_pw; p.pl_Wx = a->planar_W > 0 ? a->planar_W : a->W;
     if (p.Cq > 65535 || a->N > 65535) return set_error("norm_bwd: too many channels / samples for the launch grid");
     return 0;
@@ -1025,16 +1041,14 @@ int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* a, void* stream)
     const int Cp = p.Cq * 4;
     cudaError_t e = cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * (size_t)a->N * Cp, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
+    if (!a->amax || !a->dy_scale) return set_error("norm_bwd: amax / dy_scale buffers are required");
+    e = cudaMemsetAsync(a->amax, 0, sizeof(unsigned int) * 2 * (size_t)a->N * Cp, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a->dy_scale, 0, sizeof(float) * 4, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
     const size_t vox = (size_t)p.D * p.H * p.W;
     int bx = (int)((vox + 256 * kRedVpt - 1) / (256 * kRedVpt));
     int cap = (16 * num_sms()) / (p.Cq * a->N); if (cap < 1) cap = 1;
     if (bx > cap) bx = cap;
-    if (false && p.W % 4 == 0) {      // measured slower than the scalar kernel (128 registers): kept for reference
-        bx = (int)((vox / 4 + 255) / 256);
-        if (bx > cap) bx = cap;
-        norm_bwd_reduce_x4_kernel<<<dim3(bx, p.Cq, a->N), 256, 0, (cudaStream_t)stream>>>(p);
-        return check_launch("norm_bwd_reduce_x4");
-    }
     norm_bwd_reduce_kernel<<<dim3(bx, p.Cq, a->N), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("norm_bwd_reduce");
 }
@@ -1046,7 +1060,7 @@ int e3b_norm_bwd_finalize(const e3b_norm_bwd_args* a, void* stream)
     if (a->dbias && (a->mode == 1 || a->mode == 2) && !a->fwd_stats) return set_error("norm_bwd: dbias needs fwd_stats");
     norm_bwd_finalize_kernel<<<(a->N * Cp + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         a->sums, a->fwd_stats, a->mode, a->G, a->N, a->C, Cp, (double)a->D * a->H * a->W, a->gamma, a->mean, a->rstd, a->m1,
-        a->m2, a->dgamma, a->dbeta, a->dbias);
+        a->m2, a->dgamma, a->dbeta, a->dbias, a->amax, a->dy_scale);
     return check_launch("norm_bwd_finalize");
 }
 
@@ -1081,7 +1095,7 @@ int e3b_head(const e3b_head_args* a, void* stream)
     return check_launch("head");
 }
 
-int e3b_head_bwd(const float* dl, const float* a, const float* w, float* da, float* dw, float* db, double* workspace, int N,
+int e3b_head_bwd(const float* dl, const void* a, const float* w, float* da, float* dw, float* db, double* workspace, int N,
                  int C, int Co, int D, int H, int W, void* stream)
 {
     if (Co > kHeadMaxCo) return set_error("head_bwd: out_channels %d > %d not supported", Co, kHeadMaxCo);
@@ -1096,8 +1110,9 @@ int e3b_head_bwd(const float* dl, const float* a, const float* w, float* da, flo
     cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(double) * ((size_t)Co * Cp + Co), st);
     if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
     int bx = (8 * num_sms()) / Cq; if (bx < 1) bx = 1;
-    if (Co <= 4) head_bwd_w_kernel<4><<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const float4*>(a), workspace, N, Cq, Co, S);
-    else head_bwd_w_kernel<kHeadMaxCo><<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const float4*>(a), workspace, N, Cq, Co, S);
+    const int Ch = cpad16(C) / 8;
+    if (Co <= 4) head_bwd_w_kernel<4><<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const uint2*>(a), workspace, N, Cq, Ch, Co, S);
+    else head_bwd_w_kernel<kHeadMaxCo><<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const uint2*>(a), workspace, N, Cq, Ch, Co, S);
     if (check_launch("head_bwd_w")) return 1;
     head_bwd_finish_kernel<<<(Co * C + 127) / 128 + 1, 128, 0, st>>>(workspace, dw, db, C, Cp, Co);
     return check_launch("head_bwd_finish");

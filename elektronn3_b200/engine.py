@@ -4,7 +4,9 @@ This is the glue between the reference-shaped ``torch.nn.Module`` (elektronn3_b2
 C ABI (include/e3b.h): it owns no arithmetic.  PyTorch is used for device memory (caching allocator),
 the current stream and the parameter tensors only.
 
-Activations live in the QP layout (see csrc/common.cuh): float32 ``(N, ceil8(C)/4, D, H, W, 4)``.
+fp32 tensors (conv outputs, activation gradients) live in the QP layout (see csrc/common.cuh): float32
+``(N, ceil8(C)/4, D, H, W, 4)``; everything an MMA reads (input, activations, conv-output gradients) lives in
+the QH operand layout: float16 ``(N, ceil16(C)/8, D, H, W, 8)``.
 The sequence of operations follows the reference ``UNet.forward`` (models/unet.py:894-916),
 ``DownConv.forward`` (:244-253) and ``UpConv.forward`` (:384-408); the backward is what autograd
 derives from them.
@@ -49,16 +51,25 @@ def planar_from_ncdhw(x5):
 
 
 class QP:
-    """A float32 activation tensor in quad-planar layout (+ optionally its planar copy `pl`)."""
-    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W', 'pl', 'idx')
+    """A device tensor in quad-planar layout (+ optionally its planar copy `pl`): float32 QP, or -- when
+    ``half`` -- the float16 QH operand layout."""
+    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W', 'pl', 'idx', 'half', 'scale')
 
     def __init__(self, t, N, C, D, H, W, pl=None):
         self.t, self.N, self.C, self.D, self.H, self.W, self.pl = t, N, C, D, H, W, pl
         self.idx = None            # pooled tensors: arg-max slots of the pooling windows (uint8)
+        self.half = t.dtype == torch.float16
+        self.scale = None          # gradients: device float[4] (bound bits, 2^k, 2^-k, -) of the fp16 scale
 
     @staticmethod
     def empty(N, C, D, H, W, device):
         return QP(torch.empty((N, cpad8(C) // 4, D, H, W, 4), dtype=torch.float32, device=device), N, C, D, H, W)
+
+    @staticmethod
+    def empty_half(N, C, D, H, W, device):
+        """QH operand tensor; padding planes that no kernel writes (C % 16 in 1..8) must read as zero"""
+        alloc = torch.zeros if cpad16(C) != cpad8(C) else torch.empty
+        return QP(alloc((N, cpad16(C) // 8, D, H, W, 8), dtype=torch.float16, device=device), N, C, D, H, W)
 
     @property
     def ptr(self):
@@ -82,7 +93,7 @@ def pack_input(x5, planar=False):
     _require_cuda(x5, 'input')
     x5 = x5.contiguous()
     N, C, D, H, W = x5.shape
-    q = QP.empty(N, C, D, H, W, x5.device)
+    q = QP.empty_half(N, C, D, H, W, x5.device)
     if planar:
         q.pl = planar_empty(N, C, D, H, W, x5.device)
     L.check(L.lib().e3b_pack_ncdhw(x5.data_ptr(), q.ptr, _p(q.pl), N, C, D, H, W, D, H, W, 0, 0, 0, _stream()),
@@ -91,6 +102,8 @@ def pack_input(x5, planar=False):
 
 
 def unpack(q):
+    if q.half:
+        raise RuntimeError('unpack: expects a float32 QP tensor')
     out = torch.empty((q.N, q.C, q.D, q.H, q.W), dtype=torch.float32, device=q.t.device)
     L.check(L.lib().e3b_unpack_qp(q.ptr, out.data_ptr(), q.N, q.C, q.D, q.H, q.W, _stream()), 'unpack_qp')
     return out
@@ -99,7 +112,7 @@ def unpack(q):
 def gather_tiles(vol, origins, B, C, tile):
     """Predictor tile gather (inference.py:179-189): vol (C, Dv, Hv, Wv) device tensor, origins int32 (B,3)."""
     D, H, W = tile
-    q = QP.empty(B, C, D, H, W, vol.device)
+    q = QP.empty_half(B, C, D, H, W, vol.device)
     L.check(L.lib().e3b_gather_tiles(vol.data_ptr(), origins.data_ptr(), q.ptr, B, C, D, H, W,
                                      vol.shape[-3], vol.shape[-2], vol.shape[-1], _stream()), 'gather_tiles')
     return q
@@ -138,10 +151,16 @@ class WeightCache:
 
 # ------------------------------------------------------------------------------------------ conv
 def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), bias=None, relu=False,
-                 stats_channels=0, dst1_C=0, scatter=None, out_spatial=None, force_tz=0, round_tf32=False):
-    """One launch of the implicit-GEMM kernel.  Returns (dst0, dst1, stats)."""
+                 stats_channels=0, dst1_C=0, scatter=None, out_spatial=None, force_tz=0, half_out=False):
+    """One launch of the implicit-GEMM kernel.  Sources are QH operand tensors; the output is float32 QP, or
+    QH again with half_out (it is the next layer's operand).  A scaled gradient source (src0.scale) is
+    un-scaled in the epilogue.  Returns (dst0, dst1, stats)."""
     a = L.ConvArgs()
     dev = src0.t.device
+    if not src0.half or (src1 is not None and not src1.half):
+        raise RuntimeError('conv: sources must be float16 QH operand tensors')
+    if src0.scale is not None:
+        a.out_scale = src0.scale.data_ptr() + 8
     a.src0, a.C0 = src0.ptr, src0.C
     a.N, a.D, a.H, a.W = src0.N, src0.D, src0.H, src0.W
     if src1 is not None:
@@ -161,14 +180,14 @@ def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), b
         a.scatter = 1
         a.sd, a.sh, a.sw = scatter
         a.Ds, a.Hs, a.Ws = out_spatial
-    dst0 = QP.empty(src0.N, Co, Do, Ho, Wo, dev)
+    dst0 = (QP.empty_half if half_out else QP.empty)(src0.N, Co, Do, Ho, Wo, dev)
     a.dst0, a.Cd0 = dst0.ptr, Co
     dst1 = None
     if dst1_C:
         dst1 = QP.empty(src0.N, dst1_C, Do, Ho, Wo, dev)
         a.dst1, a.Cd1 = dst1.ptr, dst1_C
     a.relu = 1 if relu else 0
-    a.round_tf32 = 1 if round_tf32 else 0
+    a.half_out = 1 if half_out else 0
     stats = None
     if stats_channels:
         stats = torch.empty((src0.N, stats_channels, 2), dtype=torch.float64, device=dev)
@@ -223,16 +242,18 @@ def norm_finalize(stats, mode, G, N, C, S, gamma, beta, eps, rm, rv, momentum, d
 
 
 def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, planar=False):
-    """a = relu(y*scale+shift) and optionally the ceil-mode max-pooled tensor.  planar=True also writes the
-    planar copies the weight-gradient kernel reads (training).  With write_a=False the QP tensor `y` is
-    already the activation; its planar copy (if requested) is attached to `y` itself."""
+    """a = relu(y*scale+shift) (QH) and optionally the ceil-mode max-pooled tensor (QH).  planar=True also
+    writes the planar copies the weight-gradient kernel reads (training).  With write_a=False `y` is already
+    a QH activation (eval path) and is only pooled."""
     dev = y.t.device
-    a = QP.empty(y.N, y.C, y.D, y.H, y.W, dev) if write_a else None
+    if write_a == y.half:
+        raise RuntimeError('norm_act: y must be float32 QP when a is written, a QH activation otherwise')
+    a = QP.empty_half(y.N, y.C, y.D, y.H, y.W, dev) if write_a else None
     pooled = None
     pk = (1, 1, 1)
     if pool is not None:
         pk = pool
-        pooled = QP.empty(y.N, y.C, -(-y.D // pk[0]), -(-y.H // pk[1]), -(-y.W // pk[2]), dev)
+        pooled = QP.empty_half(y.N, y.C, -(-y.D // pk[0]), -(-y.H // pk[1]), -(-y.W // pk[2]), dev)
     a_pl = p_pl = pidx = None
     if planar:
         a_pl = planar_empty(y.N, y.C, y.D, y.H, y.W, dev)
@@ -243,7 +264,7 @@ def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, planar=Fals
             pidx = pooled.idx = torch.empty(pooled.t.shape, dtype=torch.uint8, device=dev)
     L.check(L.lib().e3b_norm_act(y.ptr, _p(scale), _p(shift), a.ptr if a else None, pooled.ptr if pooled else None,
                                  _p(a_pl), _p(p_pl), _p(pidx), y.N, y.C, y.D, y.H, y.W, pk[0], pk[1], pk[2],
-                                 1 if relu else 0, _stream()), 'norm_act')
+                                 1 if relu else 0, 1 if y.half else 0, _stream()), 'norm_act')
     return a, pooled
 
 
@@ -350,12 +371,18 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save):
     u = Unit()
     u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G = spec, src0, src1, off1, pool, mode, G
     u.pooled = u.nstate = u.stats = u.dec = None
-    if mode in (MODE_NONE, MODE_BATCH_EVAL):
+    if mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save):
+        # inference: the conv epilogue (folded BN, bias, ReLU) writes the next layer's operand directly
         a, _, _ = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
-                               relu=True, round_tf32=True)
+                               relu=True, half_out=True)
         u.y = u.a = a
-        if pool is not None or save:
-            _, u.pooled = norm_act(a, None, None, write_a=False, pool=pool, planar=save)
+        if pool is not None:
+            _, u.pooled = norm_act(a, None, None, write_a=False, pool=pool)
+    elif mode == MODE_NONE:
+        # training without normalisation: y is kept in float32 for the backward pass (identity affine)
+        y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias)
+        u.y = y
+        u.a, u.pooled = norm_act(y, None, None, pool=pool, planar=save)
     else:
         n = spec.norm
         y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1,
@@ -421,12 +448,15 @@ def _run_up(net, spec, dec, enc, training, save):
     else:
         wpk = net.cache.get((spec.name, 'up'), (up.weight,),
                             lambda: pack_weights(2, up.weight, None, spec.Ci, 0, spec.Co, spec.s))
-    if mode in (MODE_NONE, MODE_BATCH_EVAL):
+    if mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save):
         a, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias, relu=True,
-                               scatter=spec.s, out_spatial=out_sp, round_tf32=True)
+                               scatter=spec.s, out_spatial=out_sp, half_out=True)
         u.y = u.a = a
-        if save:
-            norm_act(a, None, None, write_a=False, planar=True)
+    elif mode == MODE_NONE:
+        y, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias,
+                               scatter=spec.s, out_spatial=out_sp)
+        u.y = y
+        u.a, _ = norm_act(y, None, None, planar=save)
     else:
         n = spec.norm
         y, _, stats = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias,
@@ -552,6 +582,9 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True, planar=True,
     sums = torch.empty((N, Cp, 2), dtype=torch.float64, device=dev)
     m = torch.empty((2, N, Cp), dtype=torch.float32, device=dev)
     args.sums, args.m1, args.m2 = sums.data_ptr(), m[0].data_ptr(), m[1].data_ptr()
+    amax = torch.empty((N, Cp, 2), dtype=torch.int32, device=dev)
+    dy_scale = torch.empty((4,), dtype=torch.float32, device=dev)
+    args.amax, args.dy_scale = amax.data_ptr(), dy_scale.data_ptr()
     pg = torch.empty((3, C), dtype=torch.float32, device=dev)
     has_affine = gamma is not None
     args.dgamma = pg[0].data_ptr() if has_affine else None
@@ -562,10 +595,10 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True, planar=True,
         args.sd, args.sh, args.sw = s2d
         nsl = s2d[0] * s2d[1] * s2d[2]
         Dw, Hw, Ww = -(-a.D // s2d[0]), -(-a.H // s2d[1]), -(-a.W // s2d[2])
-        dy = QP(torch.empty((N, nsl * (Cp // 4), Dw, Hw, Ww, 4), dtype=torch.float32, device=dev), N, nsl * Cp, Dw, Hw,
-                Ww)
+        dy = QP.empty_half(N, nsl * Cp, Dw, Hw, Ww, dev)
     else:
-        dy = QP.empty(N, C, a.D, a.H, a.W, dev)
+        dy = QP.empty_half(N, C, a.D, a.H, a.W, dev)
+    dy.scale = dy_scale            # the tensor holds 2^k * dy; conv_forward undoes it through dy_scale[2]
     args.dy = dy.ptr
     if planar:
         if s2d is not None or conv_geom is None:

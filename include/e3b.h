@@ -13,8 +13,13 @@
  *  - every function returns 0 on success, non-zero on error; e3b_last_error() returns the message of
  *    the calling thread's last error.  Nothing throws, nothing calls exit().
  *  - all functions only ENQUEUE work on `stream` (asynchronous w.r.t. the host) and are re-entrant.
- *  - internal activation layout "QP" (quad-planar): float32 (N, Cq, D, H, W, 4), Cq = ceil8(C)/4,
+ *  - internal fp32 layout "QP" (quad-planar): float32 (N, Cq, D, H, W, 4), Cq = ceil8(C)/4,
  *    channel c -> plane c/4, lane c%4, padding channels exactly 0.  2D data uses D = 1.
+ *    Carries convolution outputs and gradients w.r.t. activations (what the elementwise kernels read).
+ *  - operand layout "QH": float16 (N, Ch, D, H, W, 8), Ch = ceil16(C)/8, channel c -> plane c/8, lane c%8,
+ *    padding channels exactly 0.  Carries everything a forward / dgrad MMA reads: the network input,
+ *    activations, pooled activations and conv-output gradients.  fp16 has TF32's 10 explicit mantissa
+ *    bits (the reference's GPU arithmetic); gradients are stored times a per-tensor power of two.
  */
 #ifndef E3B_H
 #define E3B_H
@@ -24,7 +29,7 @@
 extern "C" {
 #endif
 
-#define E3B_VERSION 100
+#define E3B_VERSION 200
 
 int e3b_version(void);
 const char* e3b_last_error(void);
@@ -32,54 +37,54 @@ const char* e3b_last_error(void);
 int64_t e3b_launch_count(void);
 
 /* ---- layout conversion at the module boundary ------------------------------------------------
- * NCDHW float32 <-> QP.  Used for the network input (reference: trainer.py:515 `inp.to(device)`)
+ * NCDHW float32 -> QH (e3b_pack_ncdhw, e3b_gather_tiles) and QP -> NCDHW float32 (e3b_unpack_qp).  Used for the network input (reference: trainer.py:515 `inp.to(device)`)
  * and by tests.  src may be a sub-box of a larger volume (Predictor tiles, inference.py:179-189):
  * (Dv,Hv,Wv) are the extents of the allocation, (z0,y0,x0) the origin of the box inside it (may be
  * negative / overhanging: out-of-volume voxels read as 0, which is tiled_apply's zero padding).
- * Values are stored rounded to TF32 (they are MMA operands).  dst_planar (optional): the z-planar copy
- * (N, D, C, H, ceil4(W)) that e3b_wgrad reads. */
-int e3b_pack_ncdhw(const float* src, float* dst_qp, float* dst_planar, int N, int C, int D, int H, int W,
+ * dst_planar (optional): the z-planar float32 copy (N, D, C, H, ceil4(W)), rounded to TF32, that e3b_wgrad reads. */
+int e3b_pack_ncdhw(const float* src, void* dst_qh, float* dst_planar, int N, int C, int D, int H, int W,
                    int Dv, int Hv, int Wv, int z0, int y0, int x0, void* stream);
 int e3b_unpack_qp(const float* src_qp, float* dst, int N, int C, int D, int H, int W, void* stream);
 
 /* Predictor tile gather (inference.py:179-189): tile b of the batch is the box of a single-sample
  * volume (Cv, Dv, Hv, Wv) whose origin is origins[3*b..3*b+2] (device int32, may overhang -> 0). */
-int e3b_gather_tiles(const float* vol, const int32_t* origins, float* dst_qp, int B, int C,
+int e3b_gather_tiles(const float* vol, const int32_t* origins, void* dst_qh, int B, int C,
                      int D, int H, int W, int Dv, int Hv, int Wv, void* stream);
 
 /* ---- weight packing ---------------------------------------------------------------------------
- * torch parameter layouts -> the K-major no-swizzle shared-memory image the conv kernel streams.
- *   mode 0: conv forward.  w (Co, C0+C1, kd,kh,kw); K space = [pad8(C0) | pad8(C1)], N space = pad16(Co)
- *   mode 1: conv dgrad.    K space = pad8(Co); N space = [pad8(C0) | pad8(C1)] padded to 16; taps flipped
- *   mode 2: transposed conv k=s forward. w (Ci, Co, sd,sh,sw); K = pad8(Ci), N = taps * pad16(Co)
- *   mode 3: transposed conv dgrad on the space-to-depth gradient: K = taps * pad8(Co), N = pad16(Ci)
+ * torch parameter layouts -> the fp16 K-major no-swizzle shared-memory image the conv kernel streams.
+ *   mode 0: conv forward.  w (Co, C0+C1, kd,kh,kw); K space = [pad16(C0) | pad16(C1)], N space = pad16(Co)
+ *   mode 1: conv dgrad.    K space = pad16(Co); N space = [pad8(C0) | pad8(C1)] padded to 16; taps flipped
+ *   mode 2: transposed conv k=s forward. w (Ci, Co, sd,sh,sw); K = pad16(Ci), N = taps * pad16(Co)
+ *   mode 3: transposed conv dgrad on the space-to-depth gradient: K = pad16(taps * pad8(Co)), N = pad16(Ci)
  * `scale` (optional, [Co]) multiplies output channel co (eval-mode BatchNorm folding, mode 0 only).
- * e3b_packed_weight_floats() returns the size of `dst` in floats. */
+ * e3b_packed_weight_floats() returns the size of `dst` in units of 4 bytes. */
 int64_t e3b_packed_weight_floats(int mode, int C0, int C1, int Co, int kd, int kh, int kw);
-int e3b_pack_weights(int mode, const float* w, const float* scale, float* dst, int C0, int C1, int Co,
+int e3b_pack_weights(int mode, const float* w, const float* scale, void* dst, int C0, int C1, int Co,
                      int kd, int kh, int kw, void* stream);
 
 /* ---- convolution ------------------------------------------------------------------------------
- * Implicit-GEMM convolution on tcgen05 tensor cores (TF32 multiply, fp32 accumulate).
+ * Implicit-GEMM convolution on tcgen05 tensor cores (kind::f16: fp16 operands, fp32 accumulate).
  * Replaces nn.Conv3d/Conv2d behind conv3 (models/unet.py:131-149) incl. its dgrad, the virtual
  * torch.cat((updec, enc), 1) in front of UpConv.conv1 (unet.py:399), and nn.ConvTranspose3d/2d
  * behind upconv2 (unet.py:152-165, scatter=1). */
 typedef struct e3b_conv_args {
-    const float* src0; int32_t C0;             /* QP source 0 (N, C0, D, H, W) */
-    const float* src1; int32_t C1;             /* optional QP source 1 = channels after source 0 */
+    const void* src0; int32_t C0;              /* QH source 0 (N, C0, D, H, W) */
+    const void* src1; int32_t C1;              /* optional QH source 1 = channels after source 0 */
     int32_t N, D, H, W;                        /* extents of source 0 */
     int32_t D1, H1, W1;                        /* extents of source 1 (>= source 0's) */
     int32_t off1_d, off1_h, off1_w;            /* autocrop centre-crop offset into source 1 (unet.py:303-324) */
     int32_t kd, kh, kw;                        /* taps per dim: 1 or 3 */
     int32_t pd, ph, pw;                        /* zero padding per dim (0..2) */
-    const float* wpk;                          /* e3b_pack_weights image */
+    const void* wpk;                           /* e3b_pack_weights image */
     const float* bias; int32_t n_bias;         /* bias[n_bias] per output channel (columns >= n_bias get 0) or NULL */
     int32_t n_total;                           /* padded N space (multiple of 16) */
-    float* dst0; int32_t Cd0;                  /* QP output, channels [0, Cd0) */
-    float* dst1; int32_t Cd1;                  /* optional 2nd output: channels after pad8(Cd0) */
+    void* dst0; int32_t Cd0;                   /* QP (fp32) output, channels [0, Cd0); QH with half_out */
+    float* dst1; int32_t Cd1;                  /* optional 2nd QP output: channels after pad8(Cd0) */
     int32_t relu;                              /* fuse ReLU (eval-mode BN folded into weights) */
-    int32_t round_tf32;                        /* store the output rounded to TF32 (round-to-nearest): set when
-                                                  the output is the operand of another MMA */
+    int32_t half_out;                          /* write dst0 as a QH operand tensor: the output feeds the next MMA */
+    const float* out_scale;                    /* optional device scalar multiplied into the accumulators before the
+                                                  bias (e3b_norm_bwd_args.dy_scale + 2: undoes the gradient scale) */
     double* stats; int32_t stats_channels;     /* optional [N][stats_channels][2] sum/sumsq of the output (fp64;
                                                   zeroed by this call) for the following Group/BatchNorm */
     int32_t scatter, sd, sh, sw;               /* transposed conv: column = tap*pad16(Cd0)+co -> fine voxel */
@@ -93,8 +98,8 @@ int e3b_debug_conv_counters(unsigned long long* out16, int reset);
 
 /* Weight gradient: dW[tap][ci][co] = sum_voxels x[v + tap - pad][ci] * dy[v][co]  (conv backward-filter
  * of nn.Conv3d at unet.py:131-149; with taps=1 on (x, space-to-depth dy) also ConvTranspose's).
- * Operands are Z-PLANAR float32 tensors (row pitch padded to 16 bytes), written by e3b_norm_act /
- * e3b_norm_bwd_apply:  src0 (N, D, C0, H, ceil4(W));  src1 (N, D1, C1, H1, ceil4(W1)) read at offset off1
+ * TF32 multiply, fp32 accumulate.  Operands are Z-PLANAR float32 tensors (row pitch padded to 16 bytes,
+ * values rounded to TF32), written by e3b_norm_act / e3b_norm_bwd_apply:  src0 (N, D, C0, H, ceil4(W));  src1 (N, D1, C1, H1, ceil4(W1)) read at offset off1
  * (only with zero padding);  dy (N, Do, kw, Co, Ho, ceil4(W)) = the kw x-shifted copies described at
  * e3b_norm_bwd_args.dy_planar.  Result is written in torch layout:
  *   layout 0: dw (Co, C0+C1, kd, kh, kw)        (Conv)
@@ -122,24 +127,26 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
                       const float* gamma, const float* beta, float eps,
                       float* running_mean, float* running_var, float momentum,
                       float* scale, float* shift, float* mean, float* rstd, void* stream);
-/* a = relu(y*scale+shift) (QP); if pooled != NULL also pooled = maxpool_{(pk_d,pk_h,pk_w), ceil}(a).
- * scale/shift NULL = identity; a NULL = only the pooled tensor is written (eval path: y is already
- * activated by the conv epilogue).
+/* a = relu(y*scale+shift): y QP (fp32), a QH; if pooled != NULL also pooled = maxpool_{(pk_d,pk_h,pk_w), ceil}(a) (QH).
+ * scale/shift NULL = identity; a NULL = only the pooled tensor is written.  y_is_half: y is itself a QH
+ * activation (eval path: the conv epilogue already activated it) and is only pooled.
  * a_planar / pooled_planar (optional): the same tensors as Z-PLANAR (N, D, C, H, ceil4(W)) float32 copies, the
  * operand layout of e3b_wgrad.
  * pool_idx (optional, uint8 (N, pad8(C)/4, Dp, Hp, Wp, 4)): per pooled voxel and channel the window slot
  * ((dz*pk_h+dy)*pk_w+dx) of the first maximum -- what nn.MaxPool3d(return_indices) would give; consumed by
  * e3b_norm_bwd_*. */
-int e3b_norm_act(const float* y, const float* scale, const float* shift, float* a, float* pooled,
+int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled,
                  float* a_planar, float* pooled_planar, uint8_t* pool_idx,
-                 int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, void* stream);
+                 int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, int y_is_half, void* stream);
 
 /* backward of conv -> norm -> relu [-> pool] as autograd derives it:
  *   dr  = (g0 + g1 + unpool(gp)) * [a > 0]          g0,g1: same extents as y (either may be NULL)
- *   reduce:   sums[n][c] = (sum dr, sum dr*xhat)                      (fp64 atomics, [N][pad8(C)][2])
- *   finalize: m1,m2 per (n,c); dgamma, dbeta, dbias (conv bias grad)
- *   apply:    dy = rstd * (gamma*dr - m1 - xhat*m2)      written QP, or space-to-depth (s2d=1:
- *             channel = tap*pad8(C)+c on the grid (ceil(D/sd),..)) for the transposed conv backward. */
+ *   reduce:   sums[n][c] = (sum dr, sum dr*xhat)   (fp64 atomics, [N][pad8(C)][2]);  amax = (max|dr|, max|xhat|)
+ *   finalize: m1,m2 per (n,c); dgamma, dbeta, dbias (conv bias grad); a bound on |dy| -> dy_scale[0]
+ *   apply:    dy = rstd * (gamma*dr - m1 - xhat*m2), written as the QH operand 2^k * dy (k from the bound so
+ *             that |2^k dy| <= 2^14; 2^k -> dy_scale[1], 2^-k -> dy_scale[2]), or space-to-depth (s2d=1:
+ *             channel = tap*pad8(C)+c on the grid (ceil(D/sd),..)) for the transposed conv backward.
+ *             The planar float32 copies for e3b_wgrad are unscaled. */
 typedef struct e3b_norm_bwd_args {
     const float* y;                            /* conv output (pre-norm); with scale == NULL: the activation itself */
     const float* scale; const float* shift;    /* forward affine [N][pad8(C)] from e3b_norm_finalize: the activation
@@ -152,9 +159,11 @@ typedef struct e3b_norm_bwd_args {
     const float* gamma; const float* mean; const float* rstd;   /* mean/rstd [N][pad8(C)] */
     const double* fwd_stats;                   /* [N][C][2] forward sums (for dbias) */
     double* sums;                              /* [N][pad8(C)][2] */
+    uint32_t* amax;                            /* [N][pad8(C)][2] workspace (float bits) */
+    float* dy_scale;                           /* [4]: bound bits, 2^k, 2^-k, unused */
     float* m1; float* m2;                      /* [N][pad8(C)] */
     float* dgamma; float* dbeta; float* dbias; /* [C] each; may be NULL */
-    float* dy; int32_t s2d, sd, sh, sw;        /* output */
+    void* dy; int32_t s2d, sd, sh, sw;         /* QH output (scaled) */
     float* dy_planar;                          /* optional: dy in the layout e3b_wgrad contracts against,
                                                   (N, D, kw, C, H, ceil4(Wx)) with the stencil's x shift applied:
                                                   [n][z][dxi][c][y][xs] = dy[n][c][z][y][xs - (dxi - pw)];
@@ -173,7 +182,7 @@ int e3b_norm_bwd_apply(const e3b_norm_bwd_args* args, void* stream);
  * origin dst_origin[3*n..] (device int32; NULL = 0): the Predictor's crop-and-place
  * (inference.py:147-151,188-197).  Destination batch index = dst_n[n] (NULL = n). */
 typedef struct e3b_head_args {
-    const float* a; int32_t N, C, D, H, W;     /* QP input */
+    const void* a; int32_t N, C, D, H, W;      /* QH input */
     const float* w; const float* b; int32_t Co;/* torch (Co, C, 1,1,1) */
     int32_t out_mode;
     void* dst; int32_t Dd, Hd, Wd;
@@ -182,8 +191,8 @@ typedef struct e3b_head_args {
     int32_t dst_single;                        /* 1: all tiles write into sample 0 of dst */
 } e3b_head_args;
 int e3b_head(const e3b_head_args* args, void* stream);
-/* backward: dl NCDHW (N,Co,D,H,W) -> da QP; dw (Co,C), db (Co) via workspace double[Co*(C+1)] (zeroed here) */
-int e3b_head_bwd(const float* dl, const float* a, const float* w, float* da, float* dw, float* db,
+/* backward: dl NCDHW (N,Co,D,H,W), a QH -> da QP; dw (Co,C), db (Co) via workspace double[Co*(C+1)] (zeroed here) */
+int e3b_head_bwd(const float* dl, const void* a, const float* w, float* da, float* dw, float* db,
                  double* workspace, int N, int C, int Co, int D, int H, int W, void* stream);
 
 #ifdef __cplusplus

@@ -17,10 +17,10 @@ names = ['prod:a_empty', 'prod:b_empty', 'prod:total', 'mma:acc_empty', 'mma:a_f
 cases = [(4, 32, 0, 32, 64), (4, 32, 32, 32, 64), (4, 64, 0, 64, 32), (4, 64, 64, 64, 32), (4, 128, 0, 128, 16), (4, 1, 0, 32, 64)]
 for (N, C0, C1, Co, S) in cases:
     dev = 'cuda'
-    q0 = eng.QP.empty(N, C0, S, S, S, dev); q0.t.normal_()
+    q0 = eng.QP.empty_half(N, C0, S, S, S, dev); q0.t.normal_()
     q1 = None
     if C1:
-        q1 = eng.QP.empty(N, C1, S, S, S, dev); q1.t.normal_()
+        q1 = eng.QP.empty_half(N, C1, S, S, S, dev); q1.t.normal_()
     w = torch.randn(Co, C0 + C1, 3, 3, 3, device=dev) * 0.05
     wpk = eng.pack_weights(0, w, None, C0, C1, Co, (3, 3, 3))
     for stats in (0, Co):

@@ -1,6 +1,6 @@
 """Per-kernel parity tests of libe3b.so through the C ABI (ctypes) on a B200.
 
-Inputs are small dyadic rationals (k/8), exactly representable in TF32, so that tensor-core products
+Inputs are small dyadic rationals (k/8), exactly representable in fp16 / TF32, so that tensor-core products
 are exact and the comparison against a float64 torch evaluation of the same operator is tight: any
 indexing / layout / pipeline bug shows up as an O(1) error instead of hiding under TF32 noise.
 Real-valued inputs (TF32 tolerance) are covered by the golden-vector tests in test_unet_gpu.py.
@@ -42,9 +42,35 @@ def from_qp_ref(t, C):
     return t.permute(0, 1, 5, 2, 3, 4).reshape(N, Cq * 4, D, H, W)[:, :C].contiguous()
 
 
-def qp(eng, x):
+def to_qh_ref(x):
+    """pure-torch NCDHW -> QH, the fp16 operand layout (N, ceil16(C)/8, D, H, W, 8) of csrc/common.cuh"""
     N, C, D, H, W = x.shape
-    return eng.QP(to_qp_ref(x), N, C, D, H, W, pl=eng.planar_from_ncdhw(x))
+    Cp = (C + 15) & ~15
+    xp = torch.zeros((N, Cp, D, H, W), dtype=torch.float16, device=x.device)
+    xp[:, :C] = x.to(torch.float16)
+    return xp.view(N, Cp // 8, 8, D, H, W).permute(0, 1, 3, 4, 5, 2).contiguous()
+
+
+def from_qh_ref(q, C):
+    """QH operand tensor -> float32 NCDHW; a scaled gradient (q.scale) is un-scaled"""
+    t = q.t
+    N, Ch, D, H, W, _ = t.shape
+    out = t.permute(0, 1, 5, 2, 3, 4).reshape(N, Ch * 8, D, H, W)[:, :C].float().contiguous()
+    if q.scale is not None:
+        out = out * q.scale[2]
+    return out
+
+
+def qp(eng, x):
+    """MMA operand (QH) + its planar float32 copy for the weight-gradient kernel"""
+    N, C, D, H, W = x.shape
+    return eng.QP(to_qh_ref(x), N, C, D, H, W, pl=eng.planar_from_ncdhw(x))
+
+
+def qp32(eng, x):
+    """float32 QP tensor (conv outputs, gradients w.r.t. activations)"""
+    N, C, D, H, W = x.shape
+    return eng.QP(to_qp_ref(x), N, C, D, H, W)
 
 
 def shifted_planar(eng, dy, kw, pw, Wx):
@@ -66,6 +92,12 @@ def qp_dy(eng, dy, kw, pw, Wx):
     return q
 
 
+def same_operand(pl, q):
+    """planar float32 copy (TF32-rounded) vs fp16 operand: equal up to the fp16 subnormal spacing (values below
+    6e-5) and the tie-breaking rule of the two round-to-nearest conversions"""
+    return bool(((pl - q).abs() <= 1e-3 * q.abs() + 1e-7).all())
+
+
 def assert_close(got, ref, tol, what=''):
     ref = ref.to(torch.float64)
     err = (got.to(torch.float64) - ref).abs().max().item()
@@ -76,10 +108,14 @@ def assert_close(got, ref, tol, what=''):
 def test_pack_unpack_layout(eng):
     x = dyadic((2, 5, 3, 6, 7), 0)
     q = eng.pack_input(x)
-    assert torch.equal(q.t, to_qp_ref(x))
-    assert torch.equal(eng.unpack(q), x)
+    assert q.half and torch.equal(q.t, to_qh_ref(x))
+    assert torch.equal(eng.unpack(qp32(eng, x)), x)
     x1 = dyadic((1, 1, 4, 4, 9), 1)
-    assert torch.equal(eng.pack_input(x1).t, to_qp_ref(x1))
+    assert torch.equal(eng.pack_input(x1).t, to_qh_ref(x1))
+    x2 = dyadic((2, 19, 3, 4, 5), 2)                      # two 16-channel chunks, the second one ragged
+    qq = eng.pack_input(x2, planar=True)
+    assert torch.equal(qq.t, to_qh_ref(x2))
+    assert torch.equal(qq.pl[..., :5], x2.permute(0, 2, 1, 3, 4))
 
 
 CONV_CASES = [
@@ -121,6 +157,12 @@ def test_conv_forward_bias_relu_stats(eng, case):
     assert_close(stats[:, :, 1], (ref * ref).sum(dim=(2, 3, 4)), 1e-6, 'sumsq')
     yr, _, _ = eng.conv_forward(qp(eng, x), wpk, eng.cpad16(Co), Co, k, pad, bias=b, relu=True)
     assert_close(from_qp_ref(yr.t, Co), ref.clamp_min(0), 1e-6, 'conv+relu')
+    # the same, written directly as the next layer's fp16 operand (eval path)
+    yh, _, _ = eng.conv_forward(qp(eng, x), wpk, eng.cpad16(Co), Co, k, pad, bias=b, relu=True, half_out=True)
+    assert yh.half and yh.t.shape[1] == eng.cpad16(Co) // 8
+    assert_close(from_qh_ref(yh, Co), ref.clamp_min(0), 1e-3, 'conv+relu -> QH')
+    if eng.cpad16(Co) != Co:
+        assert from_qh_ref(yh, eng.cpad16(Co))[:, Co:].abs().max().item() == 0.0
 
 
 @pytest.mark.parametrize('tz', [1, 2, 3, 4])
@@ -294,7 +336,7 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
     if pool is not None:
         outs.append(F.max_pool3d(a_ref, pool, pool, ceil_mode=True))
     # forward through the kernels
-    yq = qp(eng, y)
+    yq = qp32(eng, y)
     stats = torch.stack((y.double().sum(dim=(2, 3, 4)), (y.double() ** 2).sum(dim=(2, 3, 4))), dim=-1).contiguous()
     if mode == 0:
         a, pooled = eng.norm_act(yq, None, None, pool=pool, planar=True)
@@ -304,9 +346,12 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
                                    rv if mode == 2 else None, 0.1, y.device)
         a, pooled = eng.norm_act(yq, nstate.scale, nstate.shift, pool=pool, planar=True)
     # activations / gradients that feed an MMA are stored rounded to TF32 (2^-11 relative)
-    assert_close(from_qp_ref(a.t, C), a_ref, 6e-4, 'norm+relu')
+    assert a.half and a.t.shape[1] == eng.cpad16(C) // 8
+    assert_close(from_qh_ref(a, C), a_ref, 6e-4, 'norm+relu')
+    if eng.cpad16(C) != C:
+        assert from_qh_ref(a, eng.cpad16(C))[:, C:].abs().max().item() == 0.0
     if pool is not None:
-        assert_close(from_qp_ref(pooled.t, C), outs[1], 6e-4, 'pool')
+        assert_close(from_qh_ref(pooled, C), outs[1], 6e-4, 'pool')
     if mode == 2:
         assert_close(rm, rmd, 1e-5, 'running_mean')
         assert_close(rv, rvd, 1e-5, 'running_var')
@@ -317,7 +362,7 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
     if pool is not None:
         gp = torch.from_numpy(rs.standard_normal(tuple(outs[1].shape)).astype(np.float32)).cuda()
         loss = loss + (outs[1] * gp.double()).sum()
-        gpq = qp(eng, gp)
+        gpq = qp32(eng, gp)
     loss.backward()
 
     class Spec:
@@ -330,16 +375,21 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
         u.spec.norm.eps = 1e-5
     u.a, u.y, u.pool, u.mode, u.G, u.nstate, u.stats = a, yq, pool, mode, G, nstate, (stats if mode else None)
     u.pooled = pooled
-    dy, dgamma, dbeta, dbias = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq)
-    assert_close(from_qp_ref(dy.t, C), yd.grad, 1e-3, 'norm bwd dy')
-    # z-planar copies for the wgrad kernel
-    assert torch.equal(a.pl[..., :sp[2]], from_qp_ref(a.t, C).permute(0, 2, 1, 3, 4))
+    dy, dgamma, dbeta, dbias = eng._norm_bwd(u, C, qp32(eng, g0), gp=gpq)
+    assert dy.half and dy.scale is not None
+    assert_close(from_qh_ref(dy, C), yd.grad, 1e-3, 'norm bwd dy')
+    # the fp16 scale is a power of two that brings the largest |dy| into (2^10, 2^14]
+    k = torch.log2(dy.scale[1]).item()
+    assert k == round(k) and abs(dy.scale[1].item() * dy.scale[2].item() - 1.0) < 1e-6
+    assert 2.0 ** 10 < dy.t.float().abs().max().item() <= 2.0 ** 14
+    # z-planar float32 copies for the wgrad kernel: the same values as the fp16 operand (both carry 10 mantissa bits)
+    assert same_operand(a.pl[..., :sp[2]], from_qh_ref(a, C).permute(0, 2, 1, 3, 4))
     if pool is not None:
-        assert torch.equal(pooled.pl[..., :pooled.W], from_qp_ref(pooled.t, C).permute(0, 2, 1, 3, 4))
-    dy3, _, _, _ = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq, conv_geom=(3, 1, sp[2]))
-    assert torch.equal(dy3.pl[..., :sp[2]], shifted_planar(eng, from_qp_ref(dy3.t, C), 3, 1, sp[2])[..., :sp[2]])
-    dy3v, _, _, _ = eng._norm_bwd(u, C, qp(eng, g0), gp=gpq, conv_geom=(3, 0, sp[2] + 2))
-    assert torch.equal(dy3v.pl[..., :sp[2] + 2], shifted_planar(eng, from_qp_ref(dy3v.t, C), 3, 0, sp[2] + 2)[..., :sp[2] + 2])
+        assert same_operand(pooled.pl[..., :pooled.W], from_qh_ref(pooled, C).permute(0, 2, 1, 3, 4))
+    dy3, _, _, _ = eng._norm_bwd(u, C, qp32(eng, g0), gp=gpq, conv_geom=(3, 1, sp[2]))
+    assert same_operand(dy3.pl[..., :sp[2]], shifted_planar(eng, from_qh_ref(dy3, C), 3, 1, sp[2])[..., :sp[2]])
+    dy3v, _, _, _ = eng._norm_bwd(u, C, qp32(eng, g0), gp=gpq, conv_geom=(3, 0, sp[2] + 2))
+    assert same_operand(dy3v.pl[..., :sp[2] + 2], shifted_planar(eng, from_qh_ref(dy3v, C), 3, 0, sp[2] + 2)[..., :sp[2] + 2])
     if mode:
         assert_close(dgamma, gd.grad, 2e-4, 'dgamma')
         assert_close(dbeta, bd.grad, 2e-4, 'dbeta')
@@ -357,21 +407,22 @@ def test_norm_backward_space_to_depth(eng):
     yd = y.double().requires_grad_(True)
     a_ref = F.relu(yd)
     (a_ref * g0.double()).sum().backward()
-    a, _ = eng.norm_act(qp(eng, y), None, None)
+    yq = qp32(eng, y)
+    a, _ = eng.norm_act(yq, None, None)
     u = eng.Unit()
 
     class Spec:
         norm = None
     u.spec = Spec()
-    u.a, u.y, u.pool, u.mode, u.G, u.nstate, u.stats = a, a, None, 0, 1, None, None
-    dy, _, _, dbias = eng._norm_bwd(u, C, qp(eng, g0), s2d=s)
+    u.a, u.y, u.pool, u.mode, u.G, u.nstate, u.stats = a, yq, None, 0, 1, None, None
+    dy, _, _, dbias = eng._norm_bwd(u, C, qp32(eng, g0), s2d=s)
     coarse = tuple(-(-f // k) for f, k in zip(fine, s))
     full = torch.zeros((N, C) + tuple(c * k for c, k in zip(coarse, s)), dtype=torch.float64, device='cuda')
     full[:, :, :fine[0], :fine[1], :fine[2]] = yd.grad
     D, H, W = coarse
     ref = full.view(N, C, D, 2, H, 2, W, 2).permute(0, 3, 5, 7, 1, 2, 4, 6).reshape(N, 8 * C, D, H, W)
-    assert_close(from_qp_ref(dy.t, 8 * C), ref, 6e-4, 's2d')
-    assert torch.equal(dy.pl[:, :, 0, :, :, :W], from_qp_ref(dy.t, 8 * C).permute(0, 2, 1, 3, 4))
+    assert_close(from_qh_ref(dy, 8 * C), ref, 6e-4, 's2d')
+    assert same_operand(dy.pl[:, :, 0, :, :, :W], from_qh_ref(dy, 8 * C).permute(0, 2, 1, 3, 4))
 
 
 # ---------------------------------------------------------------------------------------- head
@@ -379,7 +430,7 @@ def test_norm_backward_space_to_depth(eng):
 def test_head_modes_and_backward(eng, C, Co):
     N, sp = 2, (5, 6, 7)
     rs = np.random.RandomState(41)
-    a = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
+    a = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda().half().float()   # features are fp16
     conv = torch.nn.Conv3d(C, Co, 1).cuda()
     ad = a.double().requires_grad_(True)
     wd, bd = conv.weight.detach().double().requires_grad_(True), conv.bias.detach().double().requires_grad_(True)
@@ -421,7 +472,7 @@ def test_gather_tiles_zero_padding(eng):
     pad = F.pad(vol, (8, 8, 8, 8, 8, 8))
     for b, (z, y, x) in enumerate(org.tolist()):
         ref = pad[:, z + 8:z + 13, y + 8:y + 14, x + 8:x + 15]
-        assert torch.equal(from_qp_ref(q.t[b:b + 1], 2)[0], ref)
+        assert torch.equal(from_qh_ref(eng.QP(q.t[b:b + 1], 1, 2, 5, 6, 7), 2)[0], ref)
 
 
 def test_errors_surface_as_exceptions(eng):
