@@ -49,6 +49,7 @@ class WgradArgs(ctypes.Structure):
         ('pd', c_i32), ('ph', c_i32), ('pw', c_i32),
         ('dw', c_void_p), ('layout', c_i32), ('up_taps', c_i32), ('up_co', c_i32),
         ('workspace', c_void_p),
+        ('dy_unscale', c_void_p),
     ]
 
 

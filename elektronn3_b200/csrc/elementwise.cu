@@ -16,18 +16,19 @@ static inline int grid_for(size_t total, int block, int max_waves = 8)
     return (int)b;
 }
 
-// Z-PLANAR (N, D, C, H, Wp) float32 copy of a QP quad (Wp = ceil4(W)): the K-major operand layout of the
-// wgrad kernel (a line of 32 x-voxels of one channel = one 128-byte swizzle row).
-E3B_DEVINL void store_planar(float* __restrict__ pl, const float4& v, int n, int cq, int C, int D, int H, int Wp, int z,
+// Z-PLANAR (N, D, C, H, Wp) fp16 copy of a quad (Wp = ceil8(W): 16-byte row pitch): the K-major operand
+// layout of the wgrad kernel (a line of 64 x-voxels of one channel = one 128-byte swizzle row).
+__host__ __device__ static inline int wpitch(int W) { return (W + 7) & ~7; }
+E3B_DEVINL void store_planar(__half* __restrict__ pl, const float4& v, int n, int cq, int C, int D, int H, int Wp, int z,
                              int y, int x)
 {
     const size_t plane = (size_t)H * Wp;
     const size_t o = (((size_t)n * D + z) * C + cq * 4) * plane + (size_t)y * Wp + x;
     const int c = cq * 4;
-    if (c < C) pl[o] = v.x;
-    if (c + 1 < C) pl[o + plane] = v.y;
-    if (c + 2 < C) pl[o + 2 * plane] = v.z;
-    if (c + 3 < C) pl[o + 3 * plane] = v.w;
+    if (c < C) pl[o] = __float2half_rn(v.x);
+    if (c + 1 < C) pl[o + plane] = __float2half_rn(v.y);
+    if (c + 2 < C) pl[o + 2 * plane] = __float2half_rn(v.z);
+    if (c + 3 < C) pl[o + 3 * plane] = __float2half_rn(v.w);
 }
 
 // fp16 operand tensor (QH): (N, Ch, S voxels, 8 halves), Ch = ceil16(C)/8.  The fp32 quad `cq` (channels
@@ -41,7 +42,7 @@ E3B_DEVINL void store_qh(uint2* __restrict__ qh, const float4& v, int n, int Ch,
 // NCDHW box -> QH   (network input, Predictor tile gather)
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const float* __restrict__ src, const int32_t* __restrict__ origins, uint2* __restrict__ dst,
-                            float* __restrict__ dst_pl, int N, int C, int Cq, int D, int H, int W, int Dv, int Hv, int Wv,
+                            __half* __restrict__ dst_pl, int N, int C, int Cq, int D, int H, int W, int Dv, int Hv, int Wv,
                             int z0, int y0, int x0, int single)
 {
     // Cq = ceil16(C)/4 fp32 quads per voxel: the padding channels of the 16-channel chunks are written as 0
@@ -70,7 +71,7 @@ __global__ void pack_kernel(const float* __restrict__ src, const int32_t* __rest
         }
         const float4 q = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
         store_qh(dst, q, n, Cq >> 1, cq, S, ((size_t)z * H + y) * W + x);
-        if (dst_pl && cq * 4 < C) store_planar(dst_pl, q, n, cq, C, D, H, (W + 3) & ~3, z, y, x);
+        if (dst_pl && cq * 4 < C) store_planar(dst_pl, q, n, cq, C, D, H, wpitch(W), z, y, x);
     }
 }
 
@@ -206,29 +207,31 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, int mode,
 //   dy3[n][z][dxi][c][y][xs] = dy[n][c][z][y][xs - (dxi - pw)]   (0 outside), xs in [0, Wx), Wx = conv input width.
 // A TMA box cannot start at a voxel offset that is not 16-byte aligned, so the stencil's x shift is
 // materialised here, by the kernel that produces dy anyway (each thread scatters its own value).
-E3B_DEVINL void store_planar_shifted(float* __restrict__ pl, const float4& v, int n, int cq, int C, int D, int H, int W,
+E3B_DEVINL void store_planar_shifted(__half* __restrict__ pl, const float4& v, int n, int cq, int C, int D, int H, int W,
                                      int z, int y, int x, int kw, int pw, int Wx)
 {
-    const int Wxp = (Wx + 3) & ~3;
+    const int Wxp = wpitch(Wx);
     const size_t plane = (size_t)H * Wxp;
     const int c = cq * 4;
+    const __half hz = __float2half_rn(0.f);
+    const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
     for (int dxi = 0; dxi < kw; dxi++) {
         const int sh = dxi - pw;
         const size_t base = ((((size_t)n * D + z) * kw + dxi) * C + c) * plane + (size_t)y * Wxp;
         const int xs = x + sh;
         if (xs >= 0 && xs < Wx) {
-            if (c < C) pl[base + xs] = v.x;
-            if (c + 1 < C) pl[base + plane + xs] = v.y;
-            if (c + 2 < C) pl[base + 2 * plane + xs] = v.z;
-            if (c + 3 < C) pl[base + 3 * plane + xs] = v.w;
+            if (c < C) pl[base + xs] = h0;
+            if (c + 1 < C) pl[base + plane + xs] = h1;
+            if (c + 2 < C) pl[base + 2 * plane + xs] = h2;
+            if (c + 3 < C) pl[base + 3 * plane + xs] = h3;
         }
         // columns no dy voxel maps to are zero: [0, sh) by the thread at x == 0, [W + sh, Wx) by x == W-1
         int z0 = 0, z1 = 0;
         if (x == 0 && sh > 0) { z0 = 0; z1 = sh < Wx ? sh : Wx; }
-        if (z1 > z0) for (int q = z0; q < z1; q++) for (int k = 0; k < 4; k++) if (c + k < C) pl[base + k * plane + q] = 0.f;
+        if (z1 > z0) for (int q = z0; q < z1; q++) for (int k = 0; k < 4; k++) if (c + k < C) pl[base + k * plane + q] = hz;
         if (x == W - 1) {
             int r0 = W + sh; if (r0 < 0) r0 = 0;
-            for (int q = r0; q < Wx; q++) for (int k = 0; k < 4; k++) if (c + k < C) pl[base + k * plane + q] = 0.f;
+            for (int q = r0; q < Wx; q++) for (int k = 0; k < 4; k++) if (c + k < C) pl[base + k * plane + q] = hz;
         }
     }
 }
@@ -239,7 +242,7 @@ struct NormActDev {
     const float4* y; const float* scale; const float* shift;
     const uint2* yh;             // y_half: the input is itself a QH operand tensor (eval path: pooling only)
     uint2* a; uint2* pooled;     // QH outputs
-    float* a_pl; float* pooled_pl; uchar4* pool_idx;
+    __half* a_pl; __half* pooled_pl; uchar4* pool_idx;
     int C, N, Cq, Ch, D, H, W, pkd, pkh, pkw, relu;
     int Dp, Hp, Wp;
 };
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
         const int v = v0 + j * 256;
         if (v < S) yv[j] = __ldcs(p.y + base + v);
     }
-    const int Wpl = (p.W + 3) & ~3;
+    const int Wpl = wpitch(p.W);
 #pragma unroll
     for (int j = 0; j < kVpt; j++) {
         const int v = v0 + j * 256;
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
     load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
     const size_t base = ((size_t)n * p.Cq + cq) * p.D;
     const size_t S = (size_t)p.D * p.H * p.W;
-    const int Wpl = (p.W + 3) & ~3;
+    const int Wpl = wpitch(p.W);
     float4 m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
     uchar4 idx = make_uchar4(0, 0, 0, 0);
 #pragma unroll
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
     const size_t op = ((((size_t)n * p.Cq + cq) * p.Dp + zp) * p.Hp + yp) * p.Wp + xp;
     if (p.pooled) store_qh(p.pooled, m, n, p.Ch, cq, (size_t)p.Dp * p.Hp * p.Wp, ((size_t)zp * p.Hp + yp) * p.Wp + xp);
     if (p.pool_idx) p.pool_idx[op] = idx;
-    if (p.pooled_pl) store_planar(p.pooled_pl, m, n, cq, p.C, p.Dp, p.Hp, (p.Wp + 3) & ~3, zp, yp, xp);
+    if (p.pooled_pl) store_planar(p.pooled_pl, m, n, cq, p.C, p.Dp, p.Hp, wpitch(p.Wp), zp, yp, xp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -362,7 +365,7 @@ struct NormBwdDev {
     float* dy_scale;                         // [0] bound on |dy| (float bits), [1] 2^k, [2] 2^-k
     uint2* dy;                               // QH output, scaled by 2^k
     int Ch;                                  // 16-byte planes of dy
-    float* dy_pl;
+    __half* dy_pl;                           // planar copies carry the same 2^k scale as dy
     int pl_kw, pl_pw, pl_Wx;
 };
 
@@ -610,7 +613,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
             if (!p.s2d) {
                 const float4 os = make_float4(o.x * dscale, o.y * dscale, o.z * dscale, o.w * dscale);
                 store_qh(p.dy, os, n, p.Ch, cq, (size_t)p.D * p.H * p.W, ((size_t)z * p.H + yy) * p.W + x);
-                if (p.dy_pl) store_planar_shifted(p.dy_pl, o, n, cq, p.C, p.D, p.H, p.W, z, yy, x, p.pl_kw, p.pl_pw, p.pl_Wx);
+                if (p.dy_pl) store_planar_shifted(p.dy_pl, os, n, cq, p.C, p.D, p.H, p.W, z, yy, x, p.pl_kw, p.pl_pw, p.pl_Wx);
             }
         }
         if (p.s2d) {
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
             const size_t iw = ((size_t)zw * p.Hw + yw) * p.Ww + xw;
             const float4 os = make_float4(o.x * dscale, o.y * dscale, o.z * dscale, o.w * dscale);
             store_qh(p.dy, os, n, p.Ch, slot * p.Cq + cq, wins, iw);
-            if (p.dy_pl) store_planar(p.dy_pl, o, n, slot * p.Cq + cq, NS * p.Cq * 4, p.Dw, p.Hw, (p.Ww + 3) & ~3, zw, yw, xw);
+            if (p.dy_pl) store_planar(p.dy_pl, os, n, slot * p.Cq + cq, NS * p.Cq * 4, p.Dw, p.Hw, wpitch(p.Ww), zw, yw, xw);
         }
     }
 }
@@ -725,22 +728,25 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev
         }
     }
     if (!active) return;
-    const size_t plane = (size_t)p.H * p.W;                 // Wxp == W (W % 4 == 0, Wx == W)
+    const int Wp = wpitch(p.W);                             // Wx == W; 16-byte row pitch
+    const size_t plane = (size_t)p.H * Wp;
     const int ch0 = cq * 4;
-    float* pl0 = p.dy_pl + ((((size_t)n * p.D + z) * KW) * p.C + ch0) * plane + (size_t)yy * p.W + x0;
+    __half* pl0 = p.dy_pl + ((((size_t)n * p.D + z) * KW) * p.C + ch0) * plane + (size_t)yy * Wp + x0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if (ch0 + k >= p.C) break;
-        const float a0 = comp(o[0], k), a1 = comp(o[1], k), a2 = comp(o[2], k), a3 = comp(o[3], k);
-        float* q = pl0 + (size_t)k * plane;
+        // (the planar copies carry the same power-of-two scale as the QH tensor)
+        const float a0 = comp(o[0], k) * dscale, a1 = comp(o[1], k) * dscale, a2 = comp(o[2], k) * dscale,
+                    a3 = comp(o[3], k) * dscale;
+        __half* q = pl0 + (size_t)k * plane;
         if (KW == 1) {
-            *reinterpret_cast<float4*>(q) = make_float4(a0, a1, a2, a3);
+            *reinterpret_cast<uint2*>(q) = pack_half4(a0, a1, a2, a3);
         } else {
             const size_t cstride = (size_t)p.C * plane;       // between the dxi copies
             // dxi = 0: shift -1: out[xs] = dy[xs + 1];  dxi = 1: unshifted;  dxi = 2: shift +1: out[xs] = dy[xs - 1]
-            *reinterpret_cast<float4*>(q) = make_float4(a1, a2, a3, comp(right, k));
-            *reinterpret_cast<float4*>(q + cstride) = make_float4(a0, a1, a2, a3);
-            *reinterpret_cast<float4*>(q + 2 * cstride) = make_float4(comp(left, k), a0, a1, a2);
+            *reinterpret_cast<uint2*>(q) = pack_half4(a1, a2, a3, comp(right, k) * dscale);
+            *reinterpret_cast<uint2*>(q + cstride) = pack_half4(a0, a1, a2, a3);
+            *reinterpret_cast<uint2*>(q + 2 * cstride) = pack_half4(comp(left, k) * dscale, a0, a1, a2);
         }
     }
 }
@@ -916,14 +922,14 @@ using namespace e3b;
 
 extern "C" {
 
-int e3b_pack_ncdhw(const float* src, void* dst_qp, float* dst_planar, int N, int C, int D, int H, int W, int Dv, int Hv,
+int e3b_pack_ncdhw(const float* src, void* dst_qp, void* dst_planar, int N, int C, int D, int H, int W, int Dv, int Hv,
                    int Wv, int z0, int y0, int x0, void* stream)
 {
     if (N <= 0 || C <= 0) return set_error("pack: empty tensor");
     const int Cq = cpad16(C) / 4;
     const size_t total = (size_t)N * Cq * D * H * W;
     pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, nullptr, reinterpret_cast<uint2*>(dst_qp),
-                                                                        dst_planar, N, C, Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0);
+                                                                        reinterpret_cast<__half*>(dst_planar), N, C, Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0);
     return check_launch("pack_ncdhw");
 }
 
@@ -977,8 +983,8 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
     return check_launch("norm_finalize");
 }
 
-int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled, float* a_planar,
-                 float* pooled_planar, uint8_t* pool_idx, int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w,
+int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled, void* a_planar,
+                 void* pooled_planar, uint8_t* pool_idx, int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w,
                  int relu, int y_is_half, void* stream)
 {
     const bool pooling = pooled || pooled_planar || pool_idx;
@@ -990,7 +996,7 @@ int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a,
     p.y = y_is_half ? nullptr : reinterpret_cast<const float4*>(y); p.scale = scale; p.shift = shift;
     p.yh = y_is_half ? reinterpret_cast<const uint2*>(y) : nullptr;
     p.a = reinterpret_cast<uint2*>(a); p.pooled = reinterpret_cast<uint2*>(pooled);
-    p.a_pl = a_planar; p.pooled_pl = pooled_planar; p.pool_idx = reinterpret_cast<uchar4*>(pool_idx);
+    p.a_pl = reinterpret_cast<__half*>(a_planar); p.pooled_pl = reinterpret_cast<__half*>(pooled_planar); p.pool_idx = reinterpret_cast<uchar4*>(pool_idx);
     p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu;
     p.Dp = (D + pk_d - 1) / pk_d; p.Hp = (H + pk_h - 1) / pk_h; p.Wp = (W + pk_w - 1) / pk_w;
     if (p.Cq > 65535 || N > 65535) return set_error("norm_act: too many channels / samples for the launch grid");
@@ -1026,7 +1032,7 @@ static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)
     p.relu = a->relu; p.s2d = a->s2d;
     p.gamma = (a->mode == 0) ? nullptr : a->gamma;
     p.mean = a->mean; p.rstd = a->rstd; p.m1 = a->m1; p.m2 = a->m2;
-    p.sums = a->sums; p.dy = reinterpret_cast<uint2*>(a->dy); p.dy_pl = a->dy_planar;
+    p.sums = a->sums; p.dy = reinterpret_cast<uint2*>(a->dy); p.dy_pl = reinterpret_cast<__half*>(a->dy_planar);
     p.amax = a->amax; p.dy_scale = a->dy_scale;
     p.Ch = a->s2d ? cpad16(p.wd * p.wh * p.ww * p.Cq * 4) / 8 : cpad16(a->C) / 8;
     p.pl_kw = a->planar_kw > 0 ? a->planar_kw : 1; p.pl_pw = a->planar_pw; p.pl_Wx = a->planar_W > 0 ? a->planar_W : a->W;

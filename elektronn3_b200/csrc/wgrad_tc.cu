@@ -5,13 +5,14 @@
 // (the backward-filter of nn.Conv3d at elektronn3 models/unet.py:131-149; with one tap on
 // (x, space-to-depth(dy)) also nn.ConvTranspose3d's, unet.py:152-165).
 //
-// GEMM view: M = input channels, N = output channels, K = voxels.  kind::tf32 accepts MN-major operands
-// only in the SW128_32B layout, so both operands are read K-major from Z-PLANAR copies of the tensors
-// (N, D, C, H, Wp) float32, Wp = ceil4(W): a TMA box of 32 consecutive x-voxels x CB channels x rows lands
-// in shared memory as the canonical 128-byte-swizzled K-major tile (one 128 B line = 32 voxels of one
-// channel; 8 channels = one 1024 B swizzle atom).
+// GEMM view: M = input channels, N = output channels, K = voxels.  Both operands are read K-major from
+// Z-PLANAR fp16 copies of the tensors (N, D, C, H, Wp), Wp = ceil8(W) (kind::f16, fp32 accumulate; fp16
+// carries TF32's 10 mantissa bits, the gradient copies carry the power-of-two scale of e3b_norm_bwd_*, undone
+// in the split-K reduction): a TMA box of 64 consecutive x-voxels x CB channels x rows lands in shared
+// memory as the canonical 128-byte-swizzled K-major tile (one 128 B line = 64 voxels of one channel;
+// 8 channels = one 1024 B swizzle atom).
 //  * the (kw) x-shifts of the stencil cannot be TMA coordinates (a box must start 16-byte aligned: a
-//    1-voxel shift of a 4-byte element is an illegal instruction) nor descriptor offsets, so the kernel
+//    1-voxel shift of a 2-byte element is an illegal instruction) nor descriptor offsets, so the kernel
 //    that produces dy also writes it as kw x-shifted copies (N, D, kw, Co, H, Wp); the copies are stacked
 //    in the MMA's N dimension: one MMA of N = kw*NTW columns serves all x taps;
 //  * the (kh) y-shifts are STACKED IN M: a stage holds the rows [y][c][32 vox] contiguously, so an
@@ -32,7 +33,7 @@
 namespace e3b {
 
 static constexpr int kWgThreads = 192;
-static constexpr int kSeg = 32;              // voxels per 128-byte line
+static constexpr int kSeg = 64;              // voxels per 128-byte line
 
 struct WgradParams {
     int N, D, H, W;              // x extents (source 0 / the cropped view of source 1)
@@ -173,7 +174,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
         }
     } else if (warp == 1) {
         // whole warp runs the loop (uniform control flow); one elected lane issues
-        const uint32_t idesc = umma_idesc_tf32(p.kw * p.NTW, 0, 0);
+        const uint32_t idesc = umma_idesc_f16(p.kw * p.NTW, 0, 0);
         const bool leader = elect_one();
         uint32_t sa = 0, pa = 0;
         uint32_t wb = 0, wpb = 0;                    // next dy-plane slot to wait for
@@ -205,10 +206,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
                         uint64_t bd = tmpl + (b16 + slot * (p.b_plane_bytes >> 4));
                         const uint32_t first = ((started >> kj) & 1u) ? 1u : 0u;
                         for (int yy = 0; yy < p.TY; yy++) {
-                            umma_tf32(acc, ad, bd, idesc, first | (uint32_t)yy);
-                            umma_tf32(acc, ad + 2, bd + 2, idesc, 1u);
-                            umma_tf32(acc, ad + 4, bd + 4, idesc, 1u);
-                            umma_tf32(acc, ad + 6, bd + 6, idesc, 1u);
+                            umma_f16(acc, ad, bd, idesc, first | (uint32_t)yy);
+                            umma_f16(acc, ad + 2, bd + 2, idesc, 1u);
+                            umma_f16(acc, ad + 4, bd + 4, idesc, 1u);
+                            umma_f16(acc, ad + 6, bd + 6, idesc, 1u);
                             ad += a_row16; bd += b_row16;
                         }
                     }
@@ -276,9 +277,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
 // deterministic split-K reduction + scatter into the torch parameter layout
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int S, int ntaps, int ktot,
                                     int npad_total, int CB, int mchunks0, int C0, int C1, int Co, int layout, int up_taps,
-                                    int up_co, int up_copad)
+                                    int up_co, int up_copad, const float* __restrict__ dy_unscale)
 {
     const size_t total = (size_t)ntaps * ktot * npad_total;
+    const float unscale = dy_unscale ? __ldg(dy_unscale) : 1.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int nn = (int)(i % npad_total);
         const int kk = (int)((i / npad_total) % ktot);
@@ -290,6 +292,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
         else { if (nn / up_copad >= up_taps || nn % up_copad >= up_co) continue; }
         float s = 0.f;
         for (int sp = 0; sp < S; sp++) s += part[(size_t)sp * total + i];
+        s *= unscale;
         if (layout == 0) dw[((size_t)nn * (C0 + C1) + ci) * ntaps + tap] = s;
         else dw[((size_t)ci * up_co + nn % up_copad) * up_taps + nn / up_copad] = s;
     }
@@ -313,18 +316,18 @@ static PFN_encodeTiled get_enc()
     return enc;
 }
 
-// z-planar activation (N, D, C, H, Wp) viewed as 4D (x: W, c: C, y: H, zn: N*D); box (32, bc, by, 1), 128 B swizzle
-static int make_x_map(CUtensorMap* map, const float* ptr, int N, int C, int D, int H, int W, int bc, int by)
+// z-planar fp16 activation (N, D, C, H, Wp) viewed as 4D (x: W, c: C, y: H, zn: N*D); box (64, bc, by, 1), 128 B swizzle
+static int make_x_map(CUtensorMap* map, const void* ptr, int N, int C, int D, int H, int W, int bc, int by)
 {
     PFN_encodeTiled enc = get_enc();
     if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
-    const cuuint64_t Wp = (cuuint64_t)((W + 3) & ~3);
+    const cuuint64_t Wp = (cuuint64_t)((W + 7) & ~7);
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)N * D};
-    cuuint64_t strides[3] = {(cuuint64_t)H * Wp * 4, Wp * 4, (cuuint64_t)C * H * Wp * 4};
+    cuuint64_t strides[3] = {(cuuint64_t)H * Wp * 2, Wp * 2, (cuuint64_t)C * H * Wp * 2};
     cuuint32_t box[4] = {(cuuint32_t)kSeg, (cuuint32_t)bc, (cuuint32_t)by, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (box[1] > 256 || box[2] > 256) return set_error("wgrad: TMA box dimension > 256");
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
@@ -333,17 +336,17 @@ static int make_x_map(CUtensorMap* map, const float* ptr, int N, int C, int D, i
 
 // shifted gradient copies (N, Do, kw, Co, Ho, Wxp) viewed as 5D (x: Wx, co: Co, dxi: kw, y: Ho, zn: N*Do);
 // box (32, NTW, kw, TY, 1)
-static int make_dy_map(CUtensorMap* map, const float* ptr, int N, int Co, int kw, int Do, int Ho, int Wx, int bn, int by)
+static int make_dy_map(CUtensorMap* map, const void* ptr, int N, int Co, int kw, int Do, int Ho, int Wx, int bn, int by)
 {
     PFN_encodeTiled enc = get_enc();
     if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
-    const cuuint64_t Wp = (cuuint64_t)((Wx + 3) & ~3);
+    const cuuint64_t Wp = (cuuint64_t)((Wx + 7) & ~7);
     cuuint64_t dims[5] = {(cuuint64_t)Wx, (cuuint64_t)Co, (cuuint64_t)kw, (cuuint64_t)Ho, (cuuint64_t)N * Do};
-    cuuint64_t strides[4] = {(cuuint64_t)Ho * Wp * 4, (cuuint64_t)Co * Ho * Wp * 4, Wp * 4, (cuuint64_t)kw * Co * Ho * Wp * 4};
+    cuuint64_t strides[4] = {(cuuint64_t)Ho * Wp * 2, (cuuint64_t)Co * Ho * Wp * 2, Wp * 2, (cuuint64_t)kw * Co * Ho * Wp * 2};
     cuuint32_t box[5] = {(cuuint32_t)kSeg, (cuuint32_t)bn, (cuuint32_t)kw, (cuuint32_t)by, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (box[1] > 256 || box[3] > 256) return set_error("wgrad: TMA box dimension > 256");
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, box, estr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("wgrad: cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
@@ -432,7 +435,7 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     if (a->src1) {
         if ((a->off1_d | a->off1_h | a->off1_w) && (a->pd | a->ph | a->pw))
             return set_error("wgrad: a centre-cropped second source requires zero padding (VALID convolution)");
-        if (a->off1_w & 3) return set_error("wgrad: the x crop offset of the second source must be a multiple of 4");
+        if (a->off1_w & 7) return set_error("wgrad: the x crop offset of the second source must be a multiple of 8");
         rc = make_x_map(&mx1, a->src1, a->N, a->C1, a->D1, a->H1, a->W1, p.CB, p.TYA);
         if (rc) return rc;
     } else mx1 = mx0;
@@ -453,7 +456,7 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     int blocks = (int)((total + 255) / 256); if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
     wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.part, a->dw, p.S, ntaps, p.ktot, p.npad_total, p.CB, p.mchunks0,
                                                     a->C0, a->src1 ? a->C1 : 0, a->Co, a->layout, a->up_taps, a->up_co,
-                                                    cpad8(a->up_co));
+                                                    cpad8(a->up_co), a->dy_unscale);
     return check_launch("wgrad_reduce");
 }
 

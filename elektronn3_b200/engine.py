@@ -35,18 +35,18 @@ def _stream():
 
 
 def planar_empty(N, C, D, H, W, device, kw=None):
-    """Z-PLANAR layout of the wgrad operands: float32 (N, D, C, H, ceil4(W)); with kw: the x-shifted
-    gradient copies (N, D, kw, C, H, ceil4(W)) (include/e3b.h)"""
-    shape = (N, D, C, H, (W + 3) & ~3) if kw is None else (N, D, kw, C, H, (W + 3) & ~3)
-    return torch.empty(shape, dtype=torch.float32, device=device)
+    """Z-PLANAR layout of the wgrad operands: float16 (N, D, C, H, ceil8(W)); with kw: the x-shifted
+    gradient copies (N, D, kw, C, H, ceil8(W)) (include/e3b.h)"""
+    shape = (N, D, C, H, (W + 7) & ~7) if kw is None else (N, D, kw, C, H, (W + 7) & ~7)
+    return torch.empty(shape, dtype=torch.float16, device=device)
 
 
 def planar_from_ncdhw(x5):
-    """NCDHW -> z-planar (a view when C == 1 and W % 4 == 0, e.g. the network input)"""
+    """NCDHW -> z-planar float16 (test helper: the kernels write these copies themselves)"""
     W = x5.shape[-1]
-    t = x5.permute(0, 2, 1, 3, 4)
-    if W % 4:
-        t = torch.nn.functional.pad(t, (0, (-W) % 4))
+    t = x5.permute(0, 2, 1, 3, 4).to(torch.float16)
+    if W % 8:
+        t = torch.nn.functional.pad(t, (0, (-W) % 8))
     return t.contiguous()
 
 
@@ -218,6 +218,8 @@ def wgrad(src0, dy, Co, k, pad, dw_shape, *, src1=None, off1=(0, 0, 0), layout=0
         L.check(1, 'wgrad_workspace_floats')
     ws = torch.empty((n,), dtype=torch.float32, device=dev)
     a.workspace = ws.data_ptr()
+    if dy.scale is not None:
+        a.dy_unscale = dy.scale.data_ptr() + 8          # the planar gradient copies hold 2^k * dy
     L.check(L.lib().e3b_wgrad(ctypes.byref(a), _stream()), 'wgrad')
     return dw
 

@@ -41,8 +41,8 @@ int64_t e3b_launch_count(void);
  * and by tests.  src may be a sub-box of a larger volume (Predictor tiles, inference.py:179-189):
  * (Dv,Hv,Wv) are the extents of the allocation, (z0,y0,x0) the origin of the box inside it (may be
  * negative / overhanging: out-of-volume voxels read as 0, which is tiled_apply's zero padding).
- * dst_planar (optional): the z-planar float32 copy (N, D, C, H, ceil4(W)), rounded to TF32, that e3b_wgrad reads. */
-int e3b_pack_ncdhw(const float* src, void* dst_qh, float* dst_planar, int N, int C, int D, int H, int W,
+ * dst_planar (optional): the z-planar float16 copy (N, D, C, H, ceil8(W)) that e3b_wgrad reads. */
+int e3b_pack_ncdhw(const float* src, void* dst_qh, void* dst_planar, int N, int C, int D, int H, int W,
                    int Dv, int Hv, int Wv, int z0, int y0, int x0, void* stream);
 int e3b_unpack_qp(const float* src_qp, float* dst, int N, int C, int D, int H, int W, void* stream);
 
@@ -98,22 +98,24 @@ int e3b_debug_conv_counters(unsigned long long* out16, int reset);
 
 /* Weight gradient: dW[tap][ci][co] = sum_voxels x[v + tap - pad][ci] * dy[v][co]  (conv backward-filter
  * of nn.Conv3d at unet.py:131-149; with taps=1 on (x, space-to-depth dy) also ConvTranspose's).
- * TF32 multiply, fp32 accumulate.  Operands are Z-PLANAR float32 tensors (row pitch padded to 16 bytes,
- * values rounded to TF32), written by e3b_norm_act / e3b_norm_bwd_apply:  src0 (N, D, C0, H, ceil4(W));  src1 (N, D1, C1, H1, ceil4(W1)) read at offset off1
- * (only with zero padding);  dy (N, Do, kw, Co, Ho, ceil4(W)) = the kw x-shifted copies described at
+ * fp16 operands (kind::f16), fp32 accumulate.  Operands are Z-PLANAR float16 tensors (row pitch padded to
+ * 16 bytes = ceil8(W) elements), written by e3b_norm_act / e3b_norm_bwd_apply:  src0 (N, D, C0, H, ceil8(W));  src1 (N, D1, C1, H1, ceil8(W1)) read at offset off1
+ * (only with zero padding);  dy (N, Do, kw, Co, Ho, ceil8(W)) = the kw x-shifted copies described at
  * e3b_norm_bwd_args.dy_planar.  Result is written in torch layout:
  *   layout 0: dw (Co, C0+C1, kd, kh, kw)        (Conv)
  *   layout 1: dw (C0, Co/ntap_up, sd, sh, sw) with dy channels = tap*pad8(Co_up)+co  (ConvTranspose)
  * `workspace` holds split-K partials: e3b_wgrad_workspace_floats() floats. */
 typedef struct e3b_wgrad_args {
-    const float* src0; int32_t C0;
-    const float* src1; int32_t C1;
+    const void* src0; int32_t C0;
+    const void* src1; int32_t C1;
     int32_t N, D, H, W;
     int32_t D1, H1, W1, off1_d, off1_h, off1_w;
-    const float* dy; int32_t Co;
+    const void* dy; int32_t Co;
     int32_t kd, kh, kw, pd, ph, pw;
     float* dw; int32_t layout; int32_t up_taps; int32_t up_co;
     float* workspace;
+    const float* dy_unscale;                   /* optional device scalar multiplied into dw: 2^-k of the scaled gradient
+                                                  copies (e3b_norm_bwd_args.dy_scale + 2) */
 } e3b_wgrad_args;
 int64_t e3b_wgrad_workspace_floats(const e3b_wgrad_args* args);
 int e3b_wgrad(const e3b_wgrad_args* args, void* stream);
@@ -130,13 +132,13 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
 /* a = relu(y*scale+shift): y QP (fp32), a QH; if pooled != NULL also pooled = maxpool_{(pk_d,pk_h,pk_w), ceil}(a) (QH).
  * scale/shift NULL = identity; a NULL = only the pooled tensor is written.  y_is_half: y is itself a QH
  * activation (eval path: the conv epilogue already activated it) and is only pooled.
- * a_planar / pooled_planar (optional): the same tensors as Z-PLANAR (N, D, C, H, ceil4(W)) float32 copies, the
+ * a_planar / pooled_planar (optional): the same tensors as Z-PLANAR (N, D, C, H, ceil8(W)) float16 copies, the
  * operand layout of e3b_wgrad.
  * pool_idx (optional, uint8 (N, pad8(C)/4, Dp, Hp, Wp, 4)): per pooled voxel and channel the window slot
  * ((dz*pk_h+dy)*pk_w+dx) of the first maximum -- what nn.MaxPool3d(return_indices) would give; consumed by
  * e3b_norm_bwd_*. */
 int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled,
-                 float* a_planar, float* pooled_planar, uint8_t* pool_idx,
+                 void* a_planar, void* pooled_planar, uint8_t* pool_idx,
                  int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, int y_is_half, void* stream);
 
 /* backward of conv -> norm -> relu [-> pool] as autograd derives it:
@@ -164,10 +166,10 @@ typedef struct e3b_norm_bwd_args {
     float* m1; float* m2;                      /* [N][pad8(C)] */
     float* dgamma; float* dbeta; float* dbias; /* [C] each; may be NULL */
     void* dy; int32_t s2d, sd, sh, sw;         /* QH output (scaled) */
-    float* dy_planar;                          /* optional: dy in the layout e3b_wgrad contracts against,
-                                                  (N, D, kw, C, H, ceil4(Wx)) with the stencil's x shift applied:
+    void* dy_planar;                           /* optional: 2^k * dy (float16) in the layout e3b_wgrad contracts against,
+                                                  (N, D, kw, C, H, ceil8(Wx)) with the stencil's x shift applied:
                                                   [n][z][dxi][c][y][xs] = dy[n][c][z][y][xs - (dxi - pw)];
-                                                  s2d: (N, Dw, 1, taps*pad8(C), Hw, ceil4(Ww)) */
+                                                  s2d: (N, Dw, 1, taps*pad8(C), Hw, ceil8(Ww)) */
     int32_t planar_kw, planar_pw, planar_W;    /* kw, pw and input width Wx of the conv dy belongs to (0 -> 1,0,W) */
     int32_t relu;
 } e3b_norm_bwd_args;

@@ -74,10 +74,10 @@ def qp32(eng, x):
 
 
 def shifted_planar(eng, dy, kw, pw, Wx):
-    """test-side restatement of e3b_norm_bwd_args.dy_planar: (N, D, kw, C, H, ceil4(Wx)) x-shifted copies"""
+    """test-side restatement of e3b_norm_bwd_args.dy_planar: float16 (N, D, kw, C, H, ceil8(Wx)) x-shifted copies"""
     N, C, D, H, W = dy.shape
-    out = torch.zeros((N, D, kw, C, H, (Wx + 3) & ~3), device=dy.device)
-    src = dy.permute(0, 2, 1, 3, 4)
+    out = torch.zeros((N, D, kw, C, H, (Wx + 7) & ~7), device=dy.device, dtype=torch.float16)
+    src = dy.permute(0, 2, 1, 3, 4).to(torch.float16)
     for dxi in range(kw):
         sh = dxi - pw
         lo, hi = max(sh, 0), min(W + sh, Wx)
@@ -92,10 +92,12 @@ def qp_dy(eng, dy, kw, pw, Wx):
     return q
 
 
-def same_operand(pl, q):
-    """planar float32 copy (TF32-rounded) vs fp16 operand: equal up to the fp16 subnormal spacing (values below
-    6e-5) and the tie-breaking rule of the two round-to-nearest conversions"""
-    return bool(((pl - q).abs() <= 1e-3 * q.abs() + 1e-7).all())
+def same_operand(pl, q, scale=None):
+    """planar fp16 copy vs the QH operand: the same fp16 values (a gradient's planar copies carry its scale)"""
+    pl = pl.float()
+    if scale is not None:
+        pl = pl * scale[2]
+    return bool(((pl - q.float()).abs() <= 1e-3 * q.float().abs() + 1e-7).all())
 
 
 def assert_close(got, ref, tol, what=''):
@@ -115,7 +117,7 @@ def test_pack_unpack_layout(eng):
     x2 = dyadic((2, 19, 3, 4, 5), 2)                      # two 16-channel chunks, the second one ragged
     qq = eng.pack_input(x2, planar=True)
     assert torch.equal(qq.t, to_qh_ref(x2))
-    assert torch.equal(qq.pl[..., :5], x2.permute(0, 2, 1, 3, 4))
+    assert qq.pl.dtype == torch.float16 and torch.equal(qq.pl[..., :5].float(), x2.permute(0, 2, 1, 3, 4))
 
 
 CONV_CASES = [
@@ -387,9 +389,9 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
     if pool is not None:
         assert same_operand(pooled.pl[..., :pooled.W], from_qh_ref(pooled, C).permute(0, 2, 1, 3, 4))
     dy3, _, _, _ = eng._norm_bwd(u, C, qp32(eng, g0), gp=gpq, conv_geom=(3, 1, sp[2]))
-    assert same_operand(dy3.pl[..., :sp[2]], shifted_planar(eng, from_qh_ref(dy3, C), 3, 1, sp[2])[..., :sp[2]])
+    assert same_operand(dy3.pl[..., :sp[2]], shifted_planar(eng, from_qh_ref(dy3, C), 3, 1, sp[2])[..., :sp[2]], dy3.scale)
     dy3v, _, _, _ = eng._norm_bwd(u, C, qp32(eng, g0), gp=gpq, conv_geom=(3, 0, sp[2] + 2))
-    assert same_operand(dy3v.pl[..., :sp[2] + 2], shifted_planar(eng, from_qh_ref(dy3v, C), 3, 0, sp[2] + 2)[..., :sp[2] + 2])
+    assert same_operand(dy3v.pl[..., :sp[2] + 2], shifted_planar(eng, from_qh_ref(dy3v, C), 3, 0, sp[2] + 2)[..., :sp[2] + 2], dy3v.scale)
     if mode:
         assert_close(dgamma, gd.grad, 2e-4, 'dgamma')
         assert_close(dbeta, bd.grad, 2e-4, 'dbeta')
@@ -422,7 +424,7 @@ def test_norm_backward_space_to_depth(eng):
     D, H, W = coarse
     ref = full.view(N, C, D, 2, H, 2, W, 2).permute(0, 3, 5, 7, 1, 2, 4, 6).reshape(N, 8 * C, D, H, W)
     assert_close(from_qh_ref(dy, 8 * C), ref, 6e-4, 's2d')
-    assert same_operand(dy.pl[:, :, 0, :, :, :W], from_qh_ref(dy, 8 * C).permute(0, 2, 1, 3, 4))
+    assert same_operand(dy.pl[:, :, 0, :, :, :W], from_qh_ref(dy, 8 * C).permute(0, 2, 1, 3, 4), dy.scale)
 
 
 # ---------------------------------------------------------------------------------------- head
