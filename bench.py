@@ -30,6 +30,7 @@ FWD_BWD_GFLOP = 1175.75          # algorithmic, SURVEY.md 8(d) / BASELINE.md 2.3
 # dominant kernel for the roofline: conv_tc_kernel on up_convs.1.conv1 (virtual concat 64 -> 32 at 64^3)
 DOM = dict(N=4, C0=32, C1=32, Co=32, S=64)
 DOM_GFLOP = 2 * 4 * 64 ** 3 * 32 * (64 * 27) / 1e9     # 115.96
+DOM_TRAFFIC = None               # dram bytes per launch of that kernel from the ncu --set full capture (profiles/)
 
 
 def dice_loss(logits, target, eps=1e-4):
@@ -223,16 +224,15 @@ def main():
             dom()
         reps = 10
         ms_dom = timed(dom, reps) / reps
-        # TF32 dense peak the way MEASURED_PEAKS.json measured bf16: cuBLAS matmul burst
-        torch.backends.cuda.matmul.allow_tf32 = True
-        a = torch.randn(8192, 8192, device=dev)
-        b = torch.randn(8192, 8192, device=dev)
+        # fp16 dense peak the way MEASURED_PEAKS.json measured bf16: cuBLAS matmul burst
+        a = torch.randn(8192, 8192, device=dev, dtype=torch.float16)
+        b = torch.randn(8192, 8192, device=dev, dtype=torch.float16)
         for _ in range(3):
             a @ b
         best = 1e9
         for _ in range(5):
             best = min(best, timed(lambda: a @ b, 1))
-        tf32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        f16_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
         del a, b
     total_voxels = voxels * world
     value = total_voxels / (ms / args.steps * 1e-3)
@@ -249,16 +249,17 @@ def main():
         pass
     bf16_peak = peaks.get('bf16_tflops', 1590.0)
     achieved = DOM_GFLOP / ms_dom            # GFLOP / ms == TFLOP/s
-    roofline = dict(bound='tensor', kernel='conv_tc_kernel (up_convs.1.conv1: virtual concat 32+32 -> 32 @ 4x64^3)',
-                    achieved=achieved, peak=bf16_peak / 2, unit='TFLOP/s', frac=achieved / (bf16_peak / 2),
-                    traffic=None, ms_per_launch=ms_dom,
-                    peak_note=('kind::tf32 runs at half the bf16 rate: peak = MEASURED_PEAKS.json bf16_tflops / 2'
-                               if peaks else 'fallback 1.59 PF bf16 / 2'),
-                    tf32_cublas_tflops_measured_here=tf32_peak,
-                    step_tensor_frac=FWD_BWD_GFLOP / (ms / args.steps) / (bf16_peak / 2))
+    roofline = dict(bound='tensor', kernel='conv kernel of up_convs.1.conv1 (virtual concat 32+32 -> 32 @ 4x64^3)',
+                    achieved=achieved, peak=bf16_peak, unit='TFLOP/s', frac=achieved / bf16_peak,
+                    traffic=DOM_TRAFFIC, ms_per_launch=ms_dom,
+                    peak_note=('tcgen05 kind::f16 (fp16 operands, fp32 accumulate) runs at the bf16 rate: peak = '
+                               'MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)'
+                               if peaks else 'fallback 1.59 PF dense bf16 (B200_PROFILING.md)'),
+                    f16_cublas_tflops_measured_here=f16_peak,
+                    step_tensor_frac=FWD_BWD_GFLOP / (ms / args.steps) / bf16_peak)
     line = dict(metric='voxels/s', value=value, unit='voxels/s', n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak',
-                vs_baseline=None, dtype='tf32', data='synthetic',
+                vs_baseline=None, dtype='f16 operands / f32 accumulate (TF32-equivalent mantissa), f32 storage', data='synthetic',
                 config=dict(workload=WORKLOAD, global_batch=BATCH[0] * world,
                             parallelism=f'dp{world}' if world > 1 else 'single',
                             l2='per-step working set (>3 GB of fp32 activations) exceeds the 126 MB L2; no flush needed'),
