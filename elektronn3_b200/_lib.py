@@ -33,6 +33,7 @@ class ConvArgs(ctypes.Structure):
         ('scatter', c_i32), ('sd', c_i32), ('sh', c_i32), ('sw', c_i32),
         ('Ds', c_i32), ('Hs', c_i32), ('Ws', c_i32),
         ('force_tz', c_i32),
+        ('variant', c_i32),
     ]
 
 
@@ -100,6 +101,9 @@ SIGNATURES = {
     'e3b_packed_weight_floats': (c_i64, [c_int] * 7),
     'e3b_pack_weights': (c_int, [c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     'e3b_conv': (c_int, [ctypes.POINTER(ConvArgs), c_void_p]),
+    'e3b_conv_variant': (c_int, [c_int] * 7),
+    'e3b_debug_zs_read': (c_int, [c_void_p, c_int]),
+    'e3b_debug_zs_prof': (c_int, [c_void_p, c_int]),
     'e3b_debug_conv_counters': (c_int, [c_void_p, c_int]),
     'e3b_wgrad_workspace_floats': (c_i64, [ctypes.POINTER(WgradArgs)]),
     'e3b_wgrad': (c_int, [ctypes.POINTER(WgradArgs), c_void_p]),

@@ -54,9 +54,22 @@ int e3b_conv(const e3b_conv_args* a, void* stream)
     }
     if (((uintptr_t)a->src0 | (uintptr_t)a->dst0 | (uintptr_t)a->wpk | (uintptr_t)a->src1 | (uintptr_t)a->dst1) & 15)
         return set_error("conv: pointers must be 16-byte aligned");
+    if (a->variant == 1) {
+        if (!conv_zs_supported(a->C0, a->src1 ? a->C1 : 0, a->n_total, a->kd, a->kh, a->kw, a->scatter))
+            return set_error("conv: variant 1 (z-stacked) does not support this configuration");
+        return launch_conv_zs(a, (cudaStream_t)stream);
+    }
+    if (a->variant != 0) return set_error("conv: unknown variant %d", a->variant);
     return launch_conv_tc(a, (cudaStream_t)stream);
 }
 
+int e3b_conv_variant(int C0, int C1, int n_total, int kd, int kh, int kw, int scatter)
+{
+    return conv_zs_supported(C0, C1, n_total, kd, kh, kw, scatter);
+}
+
+int e3b_debug_zs_read(uint32_t* out, int n) { return conv_zs_debug_read(out, n); }
+int e3b_debug_zs_prof(unsigned long long* out16, int reset) { return conv_zs_prof_read(out16, reset); }
 int e3b_debug_conv_counters(unsigned long long* out16, int reset) { return conv_debug_read(out16, reset); }
 
 int64_t e3b_wgrad_workspace_floats(const e3b_wgrad_args* a)

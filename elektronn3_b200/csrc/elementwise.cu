@@ -96,6 +96,8 @@ static PackDims pack_dims(int mode, int C0, int C1, int Co, int kd, int kh, int 
     PackDims d;
     const int t = kd * kh * kw;
     switch (mode) {
+    case 4: d.ktot = cpad16(C0) + (C1 > 0 ? cpad16(C1) : 0); d.ntot = cpad16(Co); d.taps = t; d.NT = d.ntot; return d;
+    case 5: d.ktot = cpad16(Co); d.ntot = cpad16(cpad8(C0) + (C1 > 0 ? cpad8(C1) : 0)); d.taps = t; d.NT = d.ntot; return d;
     case 0: d.ktot = cpad16(C0) + (C1 > 0 ? cpad16(C1) : 0); d.ntot = cpad16(Co); d.taps = t; break;
     case 1: d.ktot = cpad16(Co); d.ntot = cpad16(cpad8(C0) + (C1 > 0 ? cpad8(C1) : 0)); d.taps = t; break;
     case 2: d.ktot = cpad16(C0); d.ntot = t * cpad16(Co); d.taps = 1; break;
@@ -114,15 +116,26 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, const
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
         const int k8 = (int)(r % 8); r /= 8;
-        const int nn = (int)(r % d.NT); r /= d.NT;
-        const int kq = (int)(r % 2); r /= 2;
-        const int tap = (int)(r % d.taps); r /= d.taps;
-        const int chunk = (int)(r % nchunks);
-        const int nt = (int)(r / nchunks);
+        int nn, kq, tap, chunk, nt = 0;
+        if (mode >= 4) {
+            // z-stacked image (conv_zs.cu): [chunk16][tap (dy,dx) 9][kq 2][N3 = (j, n)][8], block j holds z tap dz = 2 - j
+            const int n3 = (int)(r % (3 * d.NT)); r /= (size_t)(3 * d.NT);
+            kq = (int)(r % 2); r /= 2;
+            const int t9 = (int)(r % 9);
+            chunk = (int)(r / 9);
+            nn = n3 % d.NT;
+            tap = (2 - n3 / d.NT) * 9 + t9;
+        } else {
+            nn = (int)(r % d.NT); r /= d.NT;
+            kq = (int)(r % 2); r /= 2;
+            tap = (int)(r % d.taps); r /= d.taps;
+            chunk = (int)(r % nchunks);
+            nt = (int)(r / nchunks);
+        }
         const int k = chunk * 16 + kq * 8 + k8;
         const int n = nt * d.NT + nn;
         float v = 0.f;
-        if (mode == 0) {
+        if (mode == 0 || mode == 4) {
             // K space [pad16(C0) | pad16(C1)] (the operand tensors of the two sources), N = output channel
             int ci = -1;
             if (k < C0p16) { if (k < C0) ci = k; }
@@ -131,7 +144,7 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, const
                 v = w[((size_t)n * (C0 + C1) + ci) * d.taps + tap];
                 if (scale) v *= scale[n];
             }
-        } else if (mode == 1) {
+        } else if (mode == 1 || mode == 5) {
             // K = output channel of the forward conv, N space [pad8(C0) | pad8(C1)] (the fp32 QP gradient outputs)
             int ci = -1;
             if (n < C0p8) { if (n < C0) ci = n; }
@@ -951,20 +964,27 @@ int e3b_unpack_qp(const float* src_qp, float* dst, int N, int C, int D, int H, i
     return check_launch("unpack_qp");
 }
 
+static bool pack_mode_ok(int mode, const PackDims& d, int kd, int kh, int kw)
+{
+    if (mode < 0 || mode > 5 || d.NT <= 0) return false;
+    if (mode >= 4 && (kd != 3 || kh != 3 || kw != 3 || d.ntot > 80)) return false;
+    return true;
+}
+
 int64_t e3b_packed_weight_floats(int mode, int C0, int C1, int Co, int kd, int kh, int kw)
 {
-    if (mode < 0 || mode > 3) return -1;
+    if (mode < 0 || mode > 5) return -1;
     PackDims d = pack_dims(mode, C0, C1, Co, kd, kh, kw);
-    if (d.NT <= 0) return -1;
+    if (!pack_mode_ok(mode, d, kd, kh, kw)) return -1;
     return (int64_t)d.ktot * d.ntot * d.taps / 2;        // fp16 elements, counted in floats
 }
 
 int e3b_pack_weights(int mode, const float* w, const float* scale, void* dst, int C0, int C1, int Co, int kd, int kh,
                      int kw, void* stream)
 {
-    if (mode < 0 || mode > 3) return set_error("pack_weights: bad mode %d", mode);
+    if (mode < 0 || mode > 5) return set_error("pack_weights: bad mode %d", mode);
     PackDims d = pack_dims(mode, C0, C1, Co, kd, kh, kw);
-    if (d.NT <= 0) return set_error("pack_weights: unsupported output width %d", d.ntot);
+    if (!pack_mode_ok(mode, d, kd, kh, kw)) return set_error("pack_weights: mode %d does not support output width %d / these taps", mode, d.ntot);
     const size_t total = (size_t)d.ktot * d.ntot * d.taps;
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mode, w, scale, reinterpret_cast<__half*>(dst), C0, C1, Co,
                                                                                 kd * kh * kw, d);

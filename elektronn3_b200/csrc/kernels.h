@@ -19,6 +19,10 @@ int make_qp_tensor_map(CUtensorMap* map, const float* ptr, int N, int Cq, int D,
                        int bx, int by, int bz, int bcq);
 int conv_debug_read(unsigned long long* out16, int reset);
 int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream);
+int conv_zs_supported(int C0, int C1, int n_total, int kd, int kh, int kw, int scatter);
+int conv_zs_debug_read(uint32_t* out, int n);
+int conv_zs_prof_read(unsigned long long* out16, int reset);
+int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream);
 int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream);
 int64_t wgrad_workspace_floats(const e3b_wgrad_args* a);
 

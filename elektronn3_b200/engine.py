@@ -132,6 +132,11 @@ def pack_weights(mode, w, scale, C0, C1, Co, k):
     return dst
 
 
+def conv_variant(C0, C1, n_total, k):
+    """1 if the z-stacked kernel serves this convolution (weights then packed with mode 4/5), else 0"""
+    return int(L.lib().e3b_conv_variant(C0, C1 or 0, n_total, k[0], k[1], k[2], 0))
+
+
 class WeightCache:
     """Packed-weight images keyed by (parameter identity, mode); invalidated by the parameter's
     in-place version counter (optimizer steps, load_state_dict) or a moved storage (.to(device))."""
@@ -151,7 +156,7 @@ class WeightCache:
 
 # ------------------------------------------------------------------------------------------ conv
 def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), bias=None, relu=False,
-                 stats_channels=0, dst1_C=0, scatter=None, out_spatial=None, force_tz=0, half_out=False):
+                 stats_channels=0, dst1_C=0, scatter=None, out_spatial=None, force_tz=0, half_out=False, variant=0):
     """One launch of the implicit-GEMM kernel.  Sources are QH operand tensors; the output is float32 QP, or
     QH again with half_out (it is the next layer's operand).  A scaled gradient source (src0.scale) is
     un-scaled in the epilogue.  Returns (dst0, dst1, stats)."""
@@ -193,6 +198,7 @@ def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), b
         stats = torch.empty((src0.N, stats_channels, 2), dtype=torch.float64, device=dev)
         a.stats, a.stats_channels = stats.data_ptr(), stats_channels
     a.force_tz = force_tz
+    a.variant = variant            # must match the mode `wpk` was packed with (conv_variant)
     L.check(L.lib().e3b_conv(ctypes.byref(a), _stream()), 'conv')
     return dst0, dst1, stats
 
@@ -286,6 +292,15 @@ class ConvSpec:
         self.k, self.pad = ks, pads
         self.n_total = cpad16(self.Co)
         self.n_total_dgrad = cpad16(cpad8(C0) + (cpad8(C1) if C1 else 0))
+        self._variants = None
+
+    @property
+    def variants(self):
+        """(forward, dgrad) kernel variant: asked once from the library (it knows its shared-memory plans)"""
+        if self._variants is None:
+            self._variants = (conv_variant(self.C0, self.C1, self.n_total, self.k),
+                              conv_variant(self.Co, 0, self.n_total_dgrad, self.k))
+        return self._variants
 
     def w5(self):
         w = self.conv.weight
@@ -353,16 +368,17 @@ def _conv_weights(net, spec, mode, training):
     """-> (wpk, bias) for forward; BN-eval folding applied when the following norm allows it"""
     nm, _ = norm_mode(spec.norm, training)
     conv = spec.conv
+    pmode = 4 if spec.variants[0] else 0
     if nm == MODE_BATCH_EVAL:
         n = spec.norm
         params = (conv.weight, conv.bias, n.weight, n.bias, n.running_mean, n.running_var)
 
         def make():
             s, b = _bn_fold(conv, n)
-            return pack_weights(0, conv.weight, s, spec.C0, spec.C1, spec.Co, spec.k), b
+            return pack_weights(pmode, conv.weight, s, spec.C0, spec.C1, spec.Co, spec.k), b
         return net.cache.get((spec.name, 'fwd_fold'), params, make)
     wpk = net.cache.get((spec.name, 'fwd'), (conv.weight,),
-                        lambda: pack_weights(0, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k))
+                        lambda: pack_weights(pmode, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k))
     return wpk, (conv.bias.detach() if conv.bias is not None else None)
 
 
@@ -373,22 +389,24 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save):
     u = Unit()
     u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G = spec, src0, src1, off1, pool, mode, G
     u.pooled = u.nstate = u.stats = u.dec = None
+    var = spec.variants[0]
     if mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save):
         # inference: the conv epilogue (folded BN, bias, ReLU) writes the next layer's operand directly
         a, _, _ = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
-                               relu=True, half_out=True)
+                               relu=True, half_out=True, variant=var)
         u.y = u.a = a
         if pool is not None:
             _, u.pooled = norm_act(a, None, None, write_a=False, pool=pool)
     elif mode == MODE_NONE:
         # training without normalisation: y is kept in float32 for the backward pass (identity affine)
-        y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias)
+        y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
+                                   variant=var)
         u.y = y
         u.a, u.pooled = norm_act(y, None, None, pool=pool, planar=save)
     else:
         n = spec.norm
         y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1,
-                                   bias=bias, stats_channels=spec.Co)
+                                   bias=bias, stats_channels=spec.Co, variant=var)
         S = y.D * y.H * y.W
         rm = rv = None
         mom = 0.0
@@ -644,11 +662,12 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
     if u.src1 is not None and (u.off1 != (0, 0, 0) or u.src1.spatial != u.src0.spatial):
         raise NotImplementedError('backward through a centre-cropped skip connection (conv_mode="valid") '
                                   'is not on the accelerated path yet')
+    dvar = spec.variants[1]
     wpk = net.cache.get((spec.name, 'dgrad'), (conv.weight,),
-                        lambda: pack_weights(1, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k))
+                        lambda: pack_weights(5 if dvar else 1, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k))
     dpad = tuple(kk - 1 - pp for kk, pp in zip(spec.k, spec.pad))
     d0, d1, _ = conv_forward(dy, wpk, spec.n_total_dgrad, spec.C0, spec.k, dpad,
-                             dst1_C=spec.C1 if u.src1 is not None else 0)
+                             dst1_C=spec.C1 if u.src1 is not None else 0, variant=dvar)
     return d0, d1
 
 

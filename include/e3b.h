@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define E3B_VERSION 200
+#define E3B_VERSION 210
 
 int e3b_version(void);
 const char* e3b_last_error(void);
@@ -57,6 +57,8 @@ int e3b_gather_tiles(const float* vol, const int32_t* origins, void* dst_qh, int
  *   mode 1: conv dgrad.    K space = pad16(Co); N space = [pad8(C0) | pad8(C1)] padded to 16; taps flipped
  *   mode 2: transposed conv k=s forward. w (Ci, Co, sd,sh,sw); K = pad16(Ci), N = taps * pad16(Co)
  *   mode 3: transposed conv dgrad on the space-to-depth gradient: K = pad16(taps * pad8(Co)), N = pad16(Ci)
+ *   mode 4 / 5: the contents of mode 0 / 1 as the image of the z-stacked kernel (e3b_conv_args.variant = 1):
+ *           [chunk16][(dy,dx) tap][k half][3 z taps x N][8], 3x3x3 taps and N <= 80 only
  * `scale` (optional, [Co]) multiplies output channel co (eval-mode BatchNorm folding, mode 0 only).
  * e3b_packed_weight_floats() returns the size of `dst` in units of 4 bytes. */
 int64_t e3b_packed_weight_floats(int mode, int C0, int C1, int Co, int kd, int kh, int kw);
@@ -90,11 +92,24 @@ typedef struct e3b_conv_args {
     int32_t scatter, sd, sh, sw;               /* transposed conv: column = tap*pad16(Cd0)+co -> fine voxel */
     int32_t Ds, Hs, Ws;                        /* scatter: (cropped) fine output extents (autocrop :294-301) */
     int32_t force_tz;                          /* 0 = auto; tests only */
+    int32_t variant;                           /* 0: halo-tile kernel (wpk packed with mode 0..3);
+                                                  1: z-stacked kernel (wpk packed with mode 4/5), see e3b_conv_variant */
 } e3b_conv_args;
 int e3b_conv(const e3b_conv_args* args, void* stream);
+/* Which kernel serves a convolution best: 1 = the z-stacked kernel (3x3x3 taps, n_total <= 80, weight image
+ * resident in shared memory: the three z taps are stacked in the MMA's N so that narrow layers are not
+ * operand-fetch bound), else 0.  The caller packs the weights accordingly (mode 4/5 vs 0/1) and passes the same
+ * value in e3b_conv_args.variant.  Both kernels compute the same function. */
+int e3b_conv_variant(int C0, int C1, int n_total, int kd, int kh, int kw, int scatter);
 /* Developer aid: with the environment variable E3B_CONV_DEBUG set, e3b_conv accumulates per-role cycle
  * counters (producer / MMA issuer / epilogue barrier waits); this reads (and optionally resets) them. */
 int e3b_debug_conv_counters(unsigned long long* out16, int reset);
+/* Developer aid (environment variable E3B_ZS_DEBUG): progress words of the z-stacked kernel's roles, 16 per CTA,
+ * kept in host-mapped memory so that they can be read after a trapped launch. */
+int e3b_debug_zs_read(uint32_t* out, int n);
+/* Developer aid (E3B_ZS_PROF): per-role cycle counters of the z-stacked kernel summed over CTAs (producer total /
+ * wait, issuer total / waits / issue, epilogue total / wait / load / store / statistics / release). */
+int e3b_debug_zs_prof(unsigned long long* out16, int reset);
 
 /* Weight gradient: dW[tap][ci][co] = sum_voxels x[v + tap - pad][ci] * dy[v][co]  (conv backward-filter
  * of nn.Conv3d at unet.py:131-149; with taps=1 on (x, space-to-depth dy) also ConvTranspose's).

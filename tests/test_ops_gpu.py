@@ -167,6 +167,82 @@ def test_conv_forward_bias_relu_stats(eng, case):
         assert from_qh_ref(yh, eng.cpad16(Co))[:, Co:].abs().max().item() == 0.0
 
 
+ZS_CASES = [
+    # N, C0, C1, Co, (D,H,W), pad       -- the z-stacked kernel (csrc/conv_zs.cu, e3b_conv_args.variant = 1)
+    (1, 8, 0, 16, (4, 16, 8), (1, 1, 1)),
+    (2, 1, 0, 32, (16, 16, 16), (1, 1, 1)),
+    (1, 32, 0, 32, (16, 18, 20), (1, 1, 1)),
+    (1, 32, 32, 32, (9, 16, 16), (1, 1, 1)),              # virtual concat
+    (1, 16, 24, 16, (5, 16, 8), (1, 1, 1)),               # virtual concat, ragged second source
+    (1, 3, 0, 8, (11, 13, 18), (1, 1, 1)),                # odd extents, ragged channels
+    (1, 8, 0, 8, (12, 20, 20), (0, 0, 0)),                # VALID
+    (1, 8, 0, 8, (6, 12, 12), (2, 2, 2)),                 # full correlation (the dgrad geometry of VALID)
+    (1, 40, 0, 48, (6, 10, 10), (1, 1, 1)),
+    (1, 32, 0, 64, (8, 16, 16), (1, 1, 1)),
+    (2, 16, 0, 80, (3, 8, 8), (1, 1, 1)),
+    (1, 16, 0, 16, (70, 8, 8), (1, 1, 1)),                # one chain longer than the 32-block TMEM ring
+    (1, 16, 0, 16, (1, 8, 8), (1, 1, 1)),                 # a single plane
+    (2, 32, 0, 32, (40, 48, 40), (1, 1, 1)),              # more work than SMs: runs cut mid-chain, ring wrap-around
+]
+
+
+@pytest.mark.parametrize('case', ZS_CASES, ids=[str(c) for c in ZS_CASES])
+def test_conv_zstacked_forward_bias_relu_stats(eng, case):
+    N, C0, C1, Co, sp, pad = case
+    k = (3, 3, 3)
+    assert eng.conv_variant(C0, C1, eng.cpad16(Co), k) == 1
+    x0 = dyadic((N, C0) + sp, 31, scale=4, lo=-4, hi=5)
+    x1 = dyadic((N, C1) + sp, 32, scale=4, lo=-4, hi=5) if C1 else None
+    w = dyadic((Co, C0 + C1) + k, 33, scale=4, lo=-2, hi=3)
+    b = dyadic((Co,), 34)
+    xin = x0 if x1 is None else torch.cat((x0, x1), 1)
+    ref = F.conv3d(xin.double(), w.double(), b.double(), padding=pad)
+    wpk = eng.pack_weights(4, w, None, C0, C1, Co, k)
+    src1 = qp(eng, x1) if C1 else None
+    y, _, stats = eng.conv_forward(qp(eng, x0), wpk, eng.cpad16(Co), Co, k, pad, src1=src1, bias=b, stats_channels=Co, variant=1)
+    torch.cuda.synchronize()
+    got = from_qp_ref(y.t, Co)
+    assert got.shape == ref.shape
+    assert_close(got, ref, 1e-6, 'conv')
+    Cp = (Co + 7) & ~7
+    if Cp != Co:
+        full = y.t.permute(0, 1, 5, 2, 3, 4).reshape(N, Cp, *ref.shape[2:])
+        assert full[:, Co:].abs().max().item() == 0.0
+    assert_close(stats[:, :, 0], ref.sum(dim=(2, 3, 4)), 1e-6, 'sum')
+    assert_close(stats[:, :, 1], (ref * ref).sum(dim=(2, 3, 4)), 1e-6, 'sumsq')
+    # the halo-tile kernel computes the same function
+    y0, _, _ = eng.conv_forward(qp(eng, x0), eng.pack_weights(0, w, None, C0, C1, Co, k), eng.cpad16(Co), Co, k, pad, src1=src1,
+                                bias=b)
+    assert torch.equal(y0.t, y.t)
+    yh, _, _ = eng.conv_forward(qp(eng, x0), wpk, eng.cpad16(Co), Co, k, pad, src1=src1, bias=b, relu=True, half_out=True,
+                                variant=1)
+    assert yh.half and yh.t.shape[1] == eng.cpad16(Co) // 8
+    assert_close(from_qh_ref(yh, Co), ref.clamp_min(0), 1e-3, 'conv+relu -> QH')
+    if eng.cpad16(Co) != Co:
+        assert from_qh_ref(yh, eng.cpad16(Co))[:, Co:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize('case', [(1, 16, 0, 16, (4, 16, 8), (1, 1, 1)), (2, 32, 0, 64, (5, 10, 12), (1, 1, 1)),
+                                  (1, 8, 0, 8, (8, 12, 12), (0, 0, 0)), (1, 16, 24, 32, (4, 16, 8), (1, 1, 1)),
+                                  (1, 32, 32, 32, (20, 24, 16), (1, 1, 1))])
+def test_conv_zstacked_dgrad(eng, case):
+    N, C0, C1, Co, sp, pad = case
+    k = (3, 3, 3)
+    nt = eng.cpad16(eng.cpad8(C0) + (eng.cpad8(C1) if C1 else 0))
+    assert eng.conv_variant(Co, 0, nt, k) == 1
+    x = dyadic((N, C0 + C1) + sp, 35, scale=4, lo=-4, hi=5).double().requires_grad_(True)
+    w = dyadic((Co, C0 + C1) + k, 36, scale=4, lo=-2, hi=3)
+    y = F.conv3d(x, w.double(), None, padding=pad)
+    dy = dyadic(tuple(y.shape), 37, scale=4, lo=-4, hi=5)
+    y.backward(dy.double())
+    wpk = eng.pack_weights(5, w, None, C0, C1, Co, k)
+    dpad = tuple(2 - pp for pp in pad)
+    d0, d1, _ = eng.conv_forward(qp(eng, dy), wpk, nt, C0, k, dpad, dst1_C=C1, variant=1)
+    assert_close(from_qp_ref(d0.t, C0), x.grad[:, :C0], 1e-6, 'dgrad 0')
+    if C1:
+        assert_close(from_qp_ref(d1.t, C1), x.grad[:, C0:], 1e-6, 'dgrad 1')
+
+
 @pytest.mark.parametrize('tz', [1, 2, 3, 4])
 def test_conv_forward_tile_depths(eng, tz):
     N, C0, Co, sp, k, pad = 1, 16, 32, (7, 20, 12), (3, 3, 3), (1, 1, 1)
