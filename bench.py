@@ -30,7 +30,7 @@ FWD_BWD_GFLOP = 1175.75          # algorithmic, SURVEY.md 8(d) / BASELINE.md 2.3
 # dominant kernel for the roofline: conv_tc_kernel on up_convs.1.conv1 (virtual concat 64 -> 32 at 64^3)
 DOM = dict(N=4, C0=32, C1=32, Co=32, S=64)
 DOM_GFLOP = 2 * 4 * 64 ** 3 * 32 * (64 * 27) / 1e9     # 115.96
-DOM_TRAFFIC = None               # dram bytes per launch of that kernel from the ncu --set full capture (profiles/)
+DOM_TRAFFIC = 372.551e6          # dram__bytes_read + write of that launch, ncu --set full (profiles/r01_ncu_full_step_zs.csv)
 
 
 def dice_loss(logits, target, eps=1e-4):

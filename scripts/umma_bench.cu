@@ -63,6 +63,17 @@ int main()
         double avg = 0; for (int i = 0; i < 148; i++) avg += h[i]; avg /= 148;
         printf("N=%3d nacc=%d %-50s %.1f cycles/MMA (ideal %d)\n", c.N, c.nacc, name, avg / iters, c.N / 2);
     };
+    // x / y tap shifts of the halo tile: A start += 16 B (one voxel in x) or 160 B (one row)
+    for (int N : {32, 96, 192}) {
+        const int nacc = 512 / N > 4 ? 4 : 512 / N;
+        run("halo tile A, A start += 0", Cfg{N, 0, 2880, 160, 0, (uint32_t)N * 16, 128, 0, nacc});
+        run("halo tile A, A start += 16 B per MMA (x taps)", Cfg{N, 0, 2880, 160, 0, (uint32_t)N * 16, 128, 16, nacc});
+        run("halo tile A, A start += 32 B per MMA", Cfg{N, 0, 2880, 160, 0, (uint32_t)N * 16, 128, 32, nacc});
+        run("halo tile A, A start += 160 B per MMA (y taps)", Cfg{N, 0, 2880, 160, 0, (uint32_t)N * 16, 128, 160, nacc});
+        run("halo tile A (SBO=128 dense rows), A start += 16 B", Cfg{N, 0, 2880, 128, 0, (uint32_t)N * 16, 128, 16, nacc});
+        run("halo tile A (SBO=256), A start += 16 B", Cfg{N, 0, 5760, 256, 0, (uint32_t)N * 16, 128, 16, nacc});
+        run("halo tile A (SBO=256), A start += 0 B", Cfg{N, 0, 5760, 256, 0, (uint32_t)N * 16, 128, 0, nacc});
+    }
     const int Ns[] = {32, 64, 128, 256};
     for (int N : Ns) {
         for (int nacc = 1; nacc <= 8 && nacc * N <= 512; nacc *= 2) {
