@@ -154,11 +154,28 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(1234 + rank)
     model = e3.UNet(**MODEL_KW).to(dev).train()
-    step_model = model
-    if world > 1:
-        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
     voxels = BATCH[0] * BATCH[2] * BATCH[3] * BATCH[4]
+    use_graph = os.environ.get('E3B_BENCH_GRAPH', '1') != '0'
+
+    def grad_sync(params):
+        # data-parallel gradient average: one flat NCCL all-reduce (what DDP's bucketed all-reduce computes)
+        grads = [p.grad for p in params]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat)
+        flat.div_(world)
+        torch._foreach_copy_(grads, torch._utils._unflatten_dense_tensors(flat, grads))
+
+    gstep = None
+    step_model = model
+    if use_graph:
+        if world > 1:                          # same initial weights on every rank (DDP broadcasts them at construction)
+            for p in model.parameters():
+                dist.broadcast(p.data, 0)
+        gstep = e3.GraphedTrainStep(model, dice_loss, opt, BATCH, (BATCH[0],) + BATCH[2:],
+                                    grad_sync=grad_sync if world > 1 else None)
+    elif world > 1:
+        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
 
     x_dev = torch.randn(BATCH, device=dev)
     t_dev = torch.randint(0, 2, (BATCH[0],) + BATCH[2:], device=dev)
@@ -166,6 +183,8 @@ def main():
     t_host = torch.randint(0, 2, (BATCH[0],) + BATCH[2:]).pin_memory()
 
     def step(x, t):
+        if gstep is not None:                  # the same launches, replayed as one CUDA graph (elektronn3_b200/graph.py)
+            return gstep(x, t)[0]
         opt.zero_grad(set_to_none=True)
         loss = dice_loss(step_model(x), t)
         loss.backward()
@@ -201,8 +220,12 @@ def main():
         l0 = _lib.launch_count()
         ms = timed(lambda: step(x_dev, t_dev), args.steps)
         launches = _lib.launch_count() - l0
+        if gstep is not None:                  # kernels inside the replayed graph are not re-counted by the library
+            launches = gstep.launches_per_step * args.steps
 
         def e2e_step():
+            if gstep is not None:              # pinned host batch -> the graph's static buffers (H2D), replay, loss read
+                return float(gstep(x_host, t_host)[0])
             x = x_host.to(dev, non_blocking=True)
             t = t_host.to(dev, non_blocking=True)
             return float(step(x, t))             # D2H read of the loss, like trainer.py:575
@@ -263,6 +286,8 @@ def main():
                 vs_baseline=None, dtype='f16 operands / f32 accumulate (TF32-equivalent mantissa), f32 storage', data='synthetic',
                 config=dict(workload=WORKLOAD, global_batch=BATCH[0] * world,
                             parallelism=f'dp{world}' if world > 1 else 'single',
+                            launch=('whole step replayed as one CUDA graph (GraphedTrainStep)' if gstep is not None
+                                    else 'eager launches'),
                             l2='per-step working set (>3 GB of fp32 activations) exceeds the 126 MB L2; no flush needed'),
                 e2e=dict(value=e2e_value, unit='voxels/s', ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=(x_host.numel() * 4 + t_host.numel() * 8), d2h_bytes_per_step=4),

@@ -1065,11 +1065,17 @@ int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* a, void* stream)
     NormBwdDev p;
     if (fill_bwd(a, p)) return 1;
     const int Cp = p.Cq * 4;
-    cudaError_t e = cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * (size_t)a->N * Cp, (cudaStream_t)stream);
-    if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
     if (!a->amax || !a->dy_scale) return set_error("norm_bwd: amax / dy_scale buffers are required");
-    e = cudaMemsetAsync(a->amax, 0, sizeof(unsigned int) * 2 * (size_t)a->N * Cp, (cudaStream_t)stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(a->dy_scale, 0, sizeof(float) * 4, (cudaStream_t)stream);
+    const size_t sums_b = sizeof(double) * 2 * (size_t)a->N * Cp, amax_b = sizeof(unsigned int) * 2 * (size_t)a->N * Cp;
+    cudaError_t e;
+    if ((char*)a->amax == (char*)a->sums + sums_b && (char*)a->dy_scale == (char*)a->amax + amax_b) {
+        // the three accumulators sit back to back (engine.py allocates them so): one memset node instead of three
+        e = cudaMemsetAsync(a->sums, 0, sums_b + amax_b + sizeof(float) * 4, (cudaStream_t)stream);
+    } else {
+        e = cudaMemsetAsync(a->sums, 0, sums_b, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(a->amax, 0, amax_b, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(a->dy_scale, 0, sizeof(float) * 4, (cudaStream_t)stream);
+    }
     if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
     const size_t vox = (size_t)p.D * p.H * p.W;
     int bx = (int)((vox + 256 * kRedVpt - 1) / (256 * kRedVpt));

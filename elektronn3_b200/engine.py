@@ -599,11 +599,13 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True, planar=True,
         mean, rstd = u.nstate.mean, u.nstate.rstd
     args.mean, args.rstd = mean.data_ptr(), rstd.data_ptr()
     args.fwd_stats = _p(u.stats)
-    sums = torch.empty((N, Cp, 2), dtype=torch.float64, device=dev)
+    # sums (fp64), amax (u32), dy_scale (4 floats) back to back: e3b_norm_bwd_reduce clears them with one memset
+    acc = torch.empty((N * Cp * 2 * 8 + N * Cp * 2 * 4 + 16,), dtype=torch.uint8, device=dev)
+    sums = acc[:N * Cp * 16].view(torch.float64)
+    amax = acc[N * Cp * 16:N * Cp * 24].view(torch.int32)
+    dy_scale = acc[N * Cp * 24:].view(torch.float32)
     m = torch.empty((2, N, Cp), dtype=torch.float32, device=dev)
     args.sums, args.m1, args.m2 = sums.data_ptr(), m[0].data_ptr(), m[1].data_ptr()
-    amax = torch.empty((N, Cp, 2), dtype=torch.int32, device=dev)
-    dy_scale = torch.empty((4,), dtype=torch.float32, device=dev)
     args.amax, args.dy_scale = amax.data_ptr(), dy_scale.data_ptr()
     pg = torch.empty((3, C), dtype=torch.float32, device=dev)
     has_affine = gamma is not None

@@ -1,0 +1,81 @@
+"""The core training step captured ONCE in a CUDA graph and replayed.
+
+What is captured is exactly the device work of ``Trainer._train_step`` (training/trainer.py:509-543):
+forward, criterion, backward, optimizer step, ``zero_grad(set_to_none=True)`` -- about 170 kernel launches
+and 30 memset nodes per step for BASELINE cfg 2.  Launched one by one from Python they leave the GPU idle
+for ~8 % of the step (more when the host synchronises on the loss every step, as ``Trainer`` does at
+trainer.py:575); replayed as one graph they do not.  The kernels, their order and their arithmetic are those
+of the eager path (tests/test_unet_gpu.py::test_graphed_train_step_matches_eager).
+
+    step = GraphedTrainStep(model, criterion, optimizer, inp_shape, target_shape)
+    dloss, dout = step(batch['inp'], batch['target'])      # host (pinned) or device tensors
+
+This is an optional accelerator next to the ``nn.Module`` drop-in: ``Trainer`` keeps working unchanged with
+the plain module (a maintainer would replace the body of ``_train_step`` by the call above).
+"""
+import torch
+
+
+class GraphedTrainStep:
+    """forward + criterion + backward + optimizer.step of a fixed-shape batch as one CUDA graph.
+
+    ``model``: an ``elektronn3_b200.UNet`` in train mode on a CUDA device; ``criterion(dout, dtarget)`` any
+    capturable torch loss (the reference's ``DiceLoss`` / ``CombinedLoss`` are: pure tensor ops);
+    ``optimizer``: a capturable torch optimizer (``SGD``; ``Adam(capturable=True)``)."""
+
+    def __init__(self, model, criterion, optimizer, inp_shape, target_shape, target_dtype=torch.int64, warmup=3,
+                 grad_sync=None):
+        """grad_sync (optional): callable(list of parameters) run between backward and optimizer.step, inside the
+        graph -- the data-parallel gradient all-reduce of a multi-GPU job (NCCL collectives are capturable)"""
+        dev = next(model.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('elektronn3_b200: GraphedTrainStep needs the model on a CUDA device')
+        self.model, self.criterion, self.optimizer, self.grad_sync = model, criterion, optimizer, grad_sync
+        from . import _lib
+        self.inp = torch.zeros(inp_shape, dtype=torch.float32, device=dev)
+        self.target = torch.zeros(target_shape, dtype=target_dtype, device=dev)
+        # warm-up on a side stream (lazy initialisation of kernels, allocator and optimizer state happens here,
+        # not under capture); the parameters move, which is what training steps do
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)          # gradients are then allocated from the graph's pool
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.dout = model(self.inp)
+            self.dloss = criterion(self.dout, self.target)
+            self.dloss.backward()
+            if grad_sync is not None:
+                grad_sync([p for p in model.parameters() if p.grad is not None])
+            optimizer.step()
+        self.launches_per_step = _lib.launch_count() - l0      # libe3b.so kernels inside one replay
+        self._invalidate()
+
+    def _eager_step(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.criterion(self.model(self.inp), self.target)
+        loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync([p for p in self.model.parameters() if p.grad is not None])
+        self.optimizer.step()
+
+    def _invalidate(self):
+        # the replay rewrites the parameters without bumping their Python-side version counters: drop the packed
+        # weight images keyed on them, so that an eager call of the module (validation) re-packs
+        net = self.model.__dict__.get('_e3b_net')
+        if net is not None:
+            net.cache.d.clear()
+
+    def __call__(self, inp, target):
+        """copy the batch into the graph's static buffers (H2D when they are host tensors), replay.
+        Returns (dloss, dout): static device tensors, overwritten by the next call."""
+        self.inp.copy_(inp, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+        self.graph.replay()
+        self._invalidate()
+        return self.dloss, self.dout
