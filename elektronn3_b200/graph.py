@@ -25,8 +25,9 @@ class GraphedTrainStep:
 
     def __init__(self, model, criterion, optimizer, inp_shape, target_shape, target_dtype=torch.int64, warmup=3,
                  grad_sync=None):
-        """grad_sync (optional): callable(list of parameters) run between backward and optimizer.step, inside the
-        graph -- the data-parallel gradient all-reduce of a multi-GPU job (NCCL collectives are capturable)"""
+        """grad_sync (optional, EXPERIMENTAL -- not validated on hardware yet): callable(list of parameters) run between
+        backward and optimizer.step inside the graph, e.g. a data-parallel gradient all-reduce.  With it the capture
+        uses the thread-local error mode, because NCCL's watchdog thread issues CUDA calls of its own."""
         dev = next(model.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('elektronn3_b200: GraphedTrainStep needs the model on a CUDA device')
@@ -46,7 +47,8 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         optimizer.zero_grad(set_to_none=True)          # gradients are then allocated from the graph's pool
         l0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
+        mode = {} if grad_sync is None else {'capture_error_mode': 'thread_local'}
+        with torch.cuda.graph(self.graph, **mode):
             self.dout = model(self.inp)
             self.dloss = criterion(self.dout, self.target)
             self.dloss.backward()
