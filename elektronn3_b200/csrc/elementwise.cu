@@ -572,6 +572,73 @@ __global__ void norm_bwd_finalize_kernel(const double* __restrict__ sums, const 
     if (dbias) dbias[c] = (float)dbi;
 }
 
+// The same finalisation for problems that fit ONE block (N * pad8(C) <= 1024, i.e. every BASELINE layer): thread
+// (n, c) computes the means of its sample and leaves its share of the parameter gradients in shared memory; the
+// threads of sample 0 then add the shares in sample order (deterministic).  The general kernel above spends ~8 us
+// in the serial N x (C/G) fp64 loops of the sample-0 threads; this one ~3 us.
+__global__ void __launch_bounds__(1024) norm_bwd_finalize_block_kernel(
+    const double* __restrict__ sums, const double* __restrict__ fwd_stats, int mode, int G, int N, int C, int Cp, double S,
+    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ m1o,
+    float* __restrict__ m2o, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+    const unsigned int* __restrict__ amax, float* __restrict__ dy_scale)
+{
+    extern __shared__ double share[];            // [N * Cp][3]: S2 (dgamma), S1 (dbeta), dbias share of sample n
+    __shared__ unsigned int bound_bits;
+    const int i = threadIdx.x;
+    if (i == 0) bound_bits = 0u;
+    __syncthreads();
+    const bool on = i < N * Cp;
+    const int n = on ? i / Cp : 0, c = on ? i % Cp : 0;
+    double m1 = 0.0, m2 = 0.0;
+    if (on && c < C) {
+        if (mode == 1) {
+            const int cg = C / G, g = c / cg;
+            for (int j = 0; j < cg; j++) {
+                const int cc = g * cg + j;
+                const double ga = gamma ? (double)gamma[cc] : 1.0;
+                m1 += ga * sums[((size_t)n * Cp + cc) * 2];
+                m2 += ga * sums[((size_t)n * Cp + cc) * 2 + 1];
+            }
+            m1 /= S * cg; m2 /= S * cg;
+        } else if (mode == 2) {
+            const double ga = gamma ? (double)gamma[c] : 1.0;
+            for (int j = 0; j < N; j++) { m1 += sums[((size_t)j * Cp + c) * 2]; m2 += sums[((size_t)j * Cp + c) * 2 + 1]; }
+            m1 *= ga / (S * N); m2 *= ga / (S * N);
+        }
+        const double S1 = sums[(size_t)i * 2], S2 = sums[(size_t)i * 2 + 1];
+        double dbi = 0.0;
+        if (dbias) {
+            const double ga = (gamma && mode != 0) ? (double)gamma[c] : 1.0;
+            const double r = (double)rstd[i], mu = (double)mean[i];
+            double sum_xhat = 0.0;
+            if (mode == 1 || mode == 2) sum_xhat = r * (fwd_stats[((size_t)n * C + c) * 2] - S * mu);
+            dbi = r * (ga * S1 - S * m1 - m2 * sum_xhat);
+        }
+        share[i * 3] = S2; share[i * 3 + 1] = S1; share[i * 3 + 2] = dbi;
+        if (amax && dy_scale) {
+            // |dy| = |rstd (gamma dr - m1 - xhat m2)| <= rstd (|gamma| max|dr| + |m1| + max|xhat| |m2|)
+            const float ga = (gamma && mode != 0) ? fabsf(gamma[c]) : 1.f;
+            const float r = rstd ? rstd[i] : 1.f;
+            const float bound = r * (ga * __uint_as_float(amax[(size_t)i * 2]) + fabsf((float)m1) +
+                                     __uint_as_float(amax[(size_t)i * 2 + 1]) * fabsf((float)m2));
+            atomicMax(&bound_bits, __float_as_uint(bound < 3.0e38f ? bound : 3.0e38f));
+        }
+    }
+    if (on) { m1o[i] = (float)m1; m2o[i] = (float)m2; }
+    __syncthreads();
+    if (i == 0 && amax && dy_scale) atomicMax(reinterpret_cast<unsigned int*>(dy_scale), bound_bits);
+    if (on && n == 0 && c < C) {
+        double dg = 0.0, db = 0.0, dbi = 0.0;
+        for (int j = 0; j < N; j++) {
+            const double* sh = share + ((size_t)j * Cp + c) * 3;
+            dg += sh[0]; db += sh[1]; dbi += sh[2];
+        }
+        if (dgamma) dgamma[c] = (float)dg;
+        if (dbeta) dbeta[c] = (float)db;
+        if (dbias) dbias[c] = (float)dbi;
+    }
+}
+
 // grid: (chunks, Cq, N) over the flat thread grid (Dg,Hg,Wg) = (D,H,W), or the un-cropped fine grid for
 // s2d output; kAppVpt voxels per thread, all loads issued before the first use.
 static constexpr int kAppVpt = 1;
@@ -1090,7 +1157,15 @@ int e3b_norm_bwd_finalize(const e3b_norm_bwd_args* a, void* stream)
     const int Cp = cpad8(a->C);
     if (a->mode == 1 && (a->G <= 0 || a->C % a->G)) return set_error("norm_bwd: bad group count");
     if (a->dbias && (a->mode == 1 || a->mode == 2) && !a->fwd_stats) return set_error("norm_bwd: dbias needs fwd_stats");
-    norm_bwd_finalize_kernel<<<(a->N * Cp + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    const int nt = a->N * Cp;
+    if (nt <= 1024) {
+        const int threads = (nt + 31) & ~31;
+        norm_bwd_finalize_block_kernel<<<1, threads, sizeof(double) * 3 * (size_t)nt, (cudaStream_t)stream>>>(
+            a->sums, a->fwd_stats, a->mode, a->G, a->N, a->C, Cp, (double)a->D * a->H * a->W, a->gamma, a->mean, a->rstd,
+            a->m1, a->m2, a->dgamma, a->dbeta, a->dbias, a->amax, a->dy_scale);
+        return check_launch("norm_bwd_finalize");
+    }
+    norm_bwd_finalize_kernel<<<(nt + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         a->sums, a->fwd_stats, a->mode, a->G, a->N, a->C, Cp, (double)a->D * a->H * a->W, a->gamma, a->mean, a->rstd, a->m1,
         a->m2, a->dgamma, a->dbeta, a->dbias, a->amax, a->dy_scale);
     return check_launch("norm_bwd_finalize");
