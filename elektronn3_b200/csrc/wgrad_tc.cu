@@ -316,6 +316,30 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
 }
 
+// one thread per element, walking all S partials: for layers whose contraction is split over fewer than 64 CTAs
+__global__ void wgrad_reduce_flat_kernel(const float* __restrict__ part, float* __restrict__ dw, int S, int ntaps, int ktot,
+                                         int npad_total, int CB, int mchunks0, int C0, int C1, int Co, int layout, int up_taps,
+                                         int up_co, int up_copad, const float* __restrict__ dy_unscale)
+{
+    const size_t total = (size_t)ntaps * ktot * npad_total;
+    const float unscale = dy_unscale ? __ldg(dy_unscale) : 1.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int nn = (int)(i % npad_total);
+        const int kk = (int)((i / npad_total) % ktot);
+        const int tap = (int)(i / ((size_t)npad_total * ktot));
+        int ci;
+        if (kk < mchunks0 * CB) { if (kk >= C0) continue; ci = kk; }
+        else { const int k1 = kk - mchunks0 * CB; if (k1 >= C1) continue; ci = C0 + k1; }
+        if (layout == 0) { if (nn >= Co) continue; }
+        else { if (nn / up_copad >= up_taps || nn % up_copad >= up_co) continue; }
+        float s = 0.f;
+        for (int sp = 0; sp < S; sp++) s += part[(size_t)sp * total + i];
+        s *= unscale;
+        if (layout == 0) dw[((size_t)nn * (C0 + C1) + ci) * ntaps + tap] = s;
+        else dw[((size_t)ci * up_co + nn % up_copad) * up_taps + nn / up_copad] = s;
+    }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -471,10 +495,17 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     if (rc) return rc;
     const int ntaps = a->kd * a->kh * a->kw;
     const size_t total = (size_t)ntaps * p.ktot * p.npad_total;
-    int blocks = (int)((total + 31) / 32); if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.part, a->dw, p.S, ntaps, p.ktot, p.npad_total, p.CB, p.mchunks0,
-                                                    a->C0, a->src1 ? a->C1 : 0, a->Co, a->layout, a->up_taps, a->up_co,
-                                                    cpad8(a->up_co), a->dy_unscale);
+    if (p.S >= 64) {
+        int blocks = (int)((total + 31) / 32); if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+        wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.part, a->dw, p.S, ntaps, p.ktot, p.npad_total, p.CB, p.mchunks0,
+                                                        a->C0, a->src1 ? a->C1 : 0, a->Co, a->layout, a->up_taps, a->up_co,
+                                                        cpad8(a->up_co), a->dy_unscale);
+    } else {
+        int blocks = (int)((total + 255) / 256); if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+        wgrad_reduce_flat_kernel<<<blocks, 256, 0, stream>>>(p.part, a->dw, p.S, ntaps, p.ktot, p.npad_total, p.CB, p.mchunks0,
+                                                             a->C0, a->src1 ? a->C1 : 0, a->Co, a->layout, a->up_taps, a->up_co,
+                                                             cpad8(a->up_co), a->dy_unscale);
+    }
     return check_launch("wgrad_reduce");
 }
 
