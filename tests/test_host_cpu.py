@@ -212,3 +212,30 @@ def test_single_rank_identity_tiling_equals_reference_tiled_apply():
     out = orc.tiled_apply(lambda t, c: t[c] if c is not None else t, vol[None, None],
                           (8, 8, 8), (4, 4, 4), None, (1, 1, 16, 24, 16))
     assert np.array_equal(out[0, 0], slab)
+
+
+def test_conv_kernel_selection_and_weight_image_sizes():
+    """e3b_conv_variant is pure host logic (shared-memory plan of the z-stacked kernel): 3x3x3 taps, narrow
+    outputs, weight image resident.  The packed-weight sizes of modes 4/5 equal those of modes 0/1."""
+    from elektronn3_b200 import _lib
+    lib = _lib.lib()
+    v = lambda C0, C1, nt, k=(3, 3, 3), sc=0: lib.e3b_conv_variant(C0, C1, nt, k[0], k[1], k[2], sc)
+    assert v(32, 0, 32) == 1 and v(32, 32, 32) == 1 and v(1, 0, 32) == 1      # cfg-2 full-resolution layers
+    assert v(32, 0, 64) == 1 and v(64, 0, 32) == 1                            # 32 -> 64 and its dgrad
+    assert v(64, 0, 64) == 0 and v(128, 0, 64) == 0                           # weight image does not fit
+    assert v(32, 0, 96) == 0 and v(128, 0, 128) == 0                          # N = 3 * n_total > 256
+    assert v(32, 0, 32, (1, 3, 3)) == 0 and v(32, 0, 32, (1, 1, 1)) == 0      # planar / 1x1x1: halo-tile kernel
+    assert v(32, 0, 32, (3, 3, 3), 1) == 0                                    # transposed conv (scatter)
+    f = lib.e3b_packed_weight_floats
+    for (C0, C1, Co) in [(32, 0, 32), (32, 32, 32), (3, 0, 8), (40, 0, 48)]:
+        assert f(4, C0, C1, Co, 3, 3, 3) == f(0, C0, C1, Co, 3, 3, 3) > 0
+        assert f(5, C0, C1, Co, 3, 3, 3) == f(1, C0, C1, Co, 3, 3, 3) > 0
+    assert f(4, 32, 0, 32, 1, 3, 3) == -1 and f(4, 32, 0, 128, 3, 3, 3) == -1
+
+
+def test_graphed_train_step_needs_cuda():
+    import elektronn3_b200 as e3
+    m = e3.UNet(n_blocks=2, start_filts=8)
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    with pytest.raises(RuntimeError):
+        e3.GraphedTrainStep(m, torch.nn.functional.cross_entropy, opt, (1, 1, 8, 8, 8), (1, 8, 8, 8))
