@@ -167,16 +167,28 @@ def main():
     model = e3.UNet(**MODEL_KW).to(dev).train()
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
     voxels = BATCH[0] * BATCH[2] * BATCH[3] * BATCH[4]
-    # N = 1: the whole step is replayed as one CUDA graph (elektronn3_b200/graph.py).  N > 1: eager launches around
-    # stock DistributedDataParallel -- capturing the NCCL all-reduce inside the graph hung on the
-    # 2-GPU box in round 1 and is left for a later round.
-    use_graph = world == 1 and os.environ.get('E3B_BENCH_GRAPH', '1') != '0'
+    # N = 1: the whole step is replayed as one CUDA graph (elektronn3_b200/graph.py).  N > 1: the graph ends after
+    # backward; the data-parallel gradient average (one flat NCCL all-reduce: what DDP's buckets compute) and the
+    # optimizer step run eagerly, so that no NCCL call is captured (capturing it hung on the 2-GPU box).
+    # E3B_BENCH_GRAPH=0: eager launches, N > 1 around stock DistributedDataParallel.
+    use_graph = os.environ.get('E3B_BENCH_GRAPH', '1') != '0'
     gstep = None
     step_model = model
+    params = [p for p in model.parameters()]
     if use_graph:
-        gstep = e3.GraphedTrainStep(model, dice_loss, opt, BATCH, (BATCH[0],) + BATCH[2:])
+        if world > 1:                          # same initial weights on every rank (DDP broadcasts them at construction)
+            for p in params:
+                dist.broadcast(p.data, 0)
+        gstep = e3.GraphedTrainStep(model, dice_loss, opt if world == 1 else None, BATCH, (BATCH[0],) + BATCH[2:])
     elif world > 1:
         step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
+
+    def grad_sync():
+        grads = [p.grad for p in params]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat)
+        flat.div_(world)
+        torch._foreach_copy_(grads, torch._utils._unflatten_dense_tensors(flat, grads))
 
     x_dev = torch.randn(BATCH, device=dev)
     t_dev = torch.randint(0, 2, (BATCH[0],) + BATCH[2:], device=dev)
@@ -185,7 +197,11 @@ def main():
 
     def step(x, t):
         if gstep is not None:                  # the same launches, replayed as one CUDA graph (elektronn3_b200/graph.py)
-            return gstep(x, t)[0]
+            loss = gstep(x, t)[0]
+            if world > 1:
+                grad_sync()
+                opt.step()
+            return loss
         opt.zero_grad(set_to_none=True)
         loss = dice_loss(step_model(x), t)
         loss.backward()
@@ -226,7 +242,7 @@ def main():
 
         def e2e_step():
             if gstep is not None:              # pinned host batch -> the graph's static buffers (H2D), replay, loss read
-                return float(gstep(x_host, t_host)[0])
+                return float(step(x_host, t_host))
             x = x_host.to(dev, non_blocking=True)
             t = t_host.to(dev, non_blocking=True)
             return float(step(x, t))             # D2H read of the loss, like trainer.py:575
@@ -287,8 +303,10 @@ def main():
                 vs_baseline=None, dtype='f16 operands / f32 accumulate (TF32-equivalent mantissa), f32 storage', data='synthetic',
                 config=dict(workload=WORKLOAD, global_batch=BATCH[0] * world,
                             parallelism=f'dp{world}' if world > 1 else 'single',
-                            launch=('whole step replayed as one CUDA graph (GraphedTrainStep)' if gstep is not None
-                                    else 'eager launches'),
+                            launch=('eager launches' if gstep is None else
+                                    'whole step replayed as one CUDA graph (GraphedTrainStep)' if world == 1 else
+                                    'forward+loss+backward replayed as one CUDA graph, flat NCCL all-reduce and '
+                                    'optimizer step eager'),
                             l2='per-step working set (>3 GB of fp32 activations) exceeds the 126 MB L2; no flush needed'),
                 e2e=dict(value=e2e_value, unit='voxels/s', ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=(x_host.numel() * 4 + t_host.numel() * 8), d2h_bytes_per_step=4),

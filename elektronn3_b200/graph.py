@@ -21,7 +21,9 @@ class GraphedTrainStep:
 
     ``model``: an ``elektronn3_b200.UNet`` in train mode on a CUDA device; ``criterion(dout, dtarget)`` any
     capturable torch loss (the reference's ``DiceLoss`` / ``CombinedLoss`` are: pure tensor ops);
-    ``optimizer``: a capturable torch optimizer (``SGD``; ``Adam(capturable=True)``)."""
+    ``optimizer``: a capturable torch optimizer (``SGD``; ``Adam(capturable=True)``), or ``None``: the graph then ends
+    after backward, the gradients stay in the parameters' static ``.grad`` tensors and the caller all-reduces them
+    and steps the optimizer eagerly (the multi-GPU form: no NCCL call is captured)."""
 
     def __init__(self, model, criterion, optimizer, inp_shape, target_shape, target_dtype=torch.int64, warmup=3,
                  grad_sync=None):
@@ -45,7 +47,9 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        optimizer.zero_grad(set_to_none=True)          # gradients are then allocated from the graph's pool
+        for p in model.parameters():                   # gradients are then allocated from the graph's pool
+            p.grad = None
+        self._invalidate()                             # the weight re-packing kernels must be part of the graph
         l0 = _lib.launch_count()
         mode = {} if grad_sync is None else {'capture_error_mode': 'thread_local'}
         with torch.cuda.graph(self.graph, **mode):
@@ -54,17 +58,20 @@ class GraphedTrainStep:
             self.dloss.backward()
             if grad_sync is not None:
                 grad_sync([p for p in model.parameters() if p.grad is not None])
-            optimizer.step()
+            if optimizer is not None:
+                optimizer.step()
         self.launches_per_step = _lib.launch_count() - l0      # libe3b.so kernels inside one replay
         self._invalidate()
 
     def _eager_step(self):
-        self.optimizer.zero_grad(set_to_none=True)
+        for p in self.model.parameters():
+            p.grad = None
         loss = self.criterion(self.model(self.inp), self.target)
         loss.backward()
         if self.grad_sync is not None:
             self.grad_sync([p for p in self.model.parameters() if p.grad is not None])
-        self.optimizer.step()
+        if self.optimizer is not None:
+            self.optimizer.step()
 
     def _invalidate(self):
         # the replay rewrites the parameters without bumping their Python-side version counters: drop the packed
