@@ -9,7 +9,8 @@ tail -15 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench rc=$?" | tee -a gpurun_out/round_summary.txt
 cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
+# (eager launches for the launch list: one warm-up step + one listed step)
+E3B_BENCH_GRAPH=0 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
   python bench.py --profile-steps 1 > gpurun_out/ncu_launch.log 2>&1
 echo "ncu rc=$?" | tee -a gpurun_out/round_summary.txt
-python scripts/launch_summary.py gpurun_out/launches.csv 2>&1 | tail -40
+python scripts/launch_summary.py gpurun_out/launches.csv 2 2>&1 | tail -40
