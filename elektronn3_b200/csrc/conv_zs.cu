@@ -271,7 +271,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                 ZP_ACC(3, t);
                 zs_wait(&a_full[sa], pa, p.dbg, 16 * blockIdx.x + 2, 0x300000u | (sa << 8) | (uint32_t)zp);
                 ZP_ACC(4, t);
-                if (!(p.skip & 32)) tc_fence_after();
+                tc_fence_after();
                 const int nb = ohi - olo + 1;
                 const uint32_t j_lo = (uint32_t)(olo - (zp + p.pd - 2));
                 int n1 = (int)(R - s_lo); if (n1 > nb) n1 = nb;
@@ -318,7 +318,6 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                 // unpredicated UTCBAR that the non-elected lanes executed too -> double arrival)
                 ZP_ACC(13, t);
                 if (leader) umma_commit(&a_empty[sa]);
-                if ((p.skip & 16) && leader) { umma_commit(w_full); umma_commit(w_full); umma_commit(w_full); umma_commit(w_full); }   // tuning: what does a commit cost?
                 // output planes whose last contributing input plane (min(z - pd + 2, D - 1)) has now been issued
                 for (; next_commit < g.zb; next_commit++) {
                     int last = next_commit - p.pd + 2; if (last > p.D - 1) last = p.D - 1;
