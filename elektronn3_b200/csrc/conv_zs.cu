@@ -3,10 +3,11 @@
 // models/unet.py:131-149, incl. the virtual torch.cat of unet.py:399 and the dgrad of both), different GEMM
 // shape.
 //
-// Why: tcgen05.mma with both operands in shared memory fetches (128 + N) x 32 B per M=128, K=16
-// instruction at 128 B/clk, i.e. (128 + N)/4 clocks, while the math takes N/2 clocks.  With N = Cout = 32
-// (the layers that hold most of the FLOPs of a UNet with start_filts=32) the halo-tile kernel of conv_tc.cu
-// is operand-fetch bound at 16/40 = 40 % of the tensor peak.  Here the three z taps are STACKED IN N:
+// Why: tcgen05.mma with both operands in shared memory fetches (128 + N) x 32 B per M=128, K=16 instruction;
+// measured on B200 (scripts/umma_bench.cu) that costs 44 clocks at N = 32, 48 at N = 64, 56 at N = 96, 64 at
+// N = 128, while the math takes N/2 clocks.  With N = Cout = 32 (the layers that hold most of the FLOPs of a
+// UNet with start_filts=32) the halo-tile kernel of conv_tc.cu is operand-fetch bound at 16/44 = 36 % of the
+// tensor peak.  Here the three z taps are STACKED IN N:
 //
 //     acc[v, (j, co)] += sum_{dy,dx,ci} x[z', v + (dy,dx), ci] * w[dz = 2 - j, dy, dx][ci][co]
 //
@@ -19,9 +20,9 @@
 // exactly once per run (no z halo re-reads), the complete weight image stays resident in shared memory.
 //
 // Roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..9 epilogue (two warpgroups taking
-// alternate output planes).  The epilogue drains an
-// output plane as soon as its last input plane has been applied (tcgen05.commit -> mbarrier), then clears
-// the block with tcgen05.st so that every MMA can accumulate, and hands it back to the issuer.
+// alternate output planes).  The epilogue drains an output plane as soon as its last input plane has been
+// applied (tcgen05.commit -> mbarrier), clears the block with tcgen05.st so that every MMA can accumulate,
+// and hands it back to the issuer.
 #include "common.cuh"
 #include "kernels.h"
 #include <stdlib.h>
