@@ -91,7 +91,8 @@ class Predictor:
         self.batch_size = batch_size
         self.out_dtype = out_dtype
         if float16:
-            raise NotImplementedError('float16=True is not on the B200 path (kernels compute TF32/fp32)')
+            raise NotImplementedError('float16=True is not on the B200 path (the kernels already multiply fp16 operands with fp32 '
+                                      'accumulation; a .half() module is not needed)')
         if augmentations is not None:
             raise NotImplementedError('test-time augmentations are not on the B200 path yet')
         if argmax_with_threshold is not None:

@@ -274,7 +274,7 @@ class UNet(nn.Module):
             raise RuntimeError(f'Expected {self.dim + 2}D input (N, C{", D" if self.dim == 3 else ""}, H, W), '
                                f'got shape {tuple(x.shape)}')
         if torch.is_autocast_enabled():
-            x = x.float()                        # kernels compute in TF32 / fp32 accumulate regardless of autocast
+            x = x.float()                        # fp16 operands / fp32 accumulate regardless of autocast
         with torch.autocast(device_type='cuda', enabled=False):
             return _UNetFunction.apply(self, x, *self.parameters())
 
