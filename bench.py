@@ -5,7 +5,10 @@
 A "step" is one pass of the hot path over one synthetic batch: forward of
 UNet(n_blocks=3,start_filts=32,normalization='group') on (4,1,64,64,64) fp32, Dice loss
 (the reference's DiceLoss formula, modules/loss.py:165-233, in plain torch: a boundary consumer that
-stays torch), backward, SGD step.  N>1 (torchrun): one process per GPU, weak scaling, DDP all-reduce.
+stays torch), backward, SGD step.  The launches of a step are captured once in a CUDA graph and replayed
+(elektronn3_b200.GraphedTrainStep; E3B_BENCH_GRAPH=0 launches them eagerly).  N>1 (torchrun): one process per GPU,
+weak scaling; the graph ends after backward, then one flat NCCL all-reduce of the gradients and the optimizer step
+(E3B_BENCH_GRAPH=0: stock DistributedDataParallel).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = through the public
 module API with pinned HOST input/target copied in and the loss read back every step.
