@@ -73,6 +73,8 @@ class NormBwdArgs(ctypes.Structure):
         ('dy_planar', c_void_p),
         ('planar_kw', c_i32), ('planar_pw', c_i32), ('planar_W', c_i32),
         ('relu', c_i32),
+        ('g1_crop', c_i32),
+        ('g1_od', c_i32), ('g1_oh', c_i32), ('g1_ow', c_i32), ('g1_D', c_i32), ('g1_H', c_i32), ('g1_W', c_i32),
     ]
 
 

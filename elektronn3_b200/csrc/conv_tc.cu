@@ -474,16 +474,25 @@ int conv_ntile_width(int npad_total)
     return -1;
 }
 
-static int g_num_sms = 0;
+// Per-device state: kernel attributes (cudaFuncSetAttribute) and the SM count belong to a DEVICE, not to the
+// process: a second device used from the same process (nn.DataParallel replicas, model.to('cuda:1')) needs its own.
+int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 int num_sms()
 {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    static int sms[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (!sms[dev]) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = v > 0 ? v : 148;
     }
-    return g_num_sms;
+    return sms[dev];
 }
 
 int conv_debug_read(unsigned long long* out16, int reset)
@@ -596,13 +605,13 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
         m1 = m0;
     }
     const size_t smem = (size_t)sa * p.a_stage_bytes + (size_t)sb * p.b_stage_bytes + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {false};
+    if (!configured[current_device()]) {
         // static shared memory (cta_stats) counts against the 227 KB per-CTA limit
         const int max_dyn = conv_max_dyn_smem();
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
         if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured[current_device()] = true;
     }
     if (p.stats) {
         cudaError_t e = cudaMemsetAsync(p.stats, 0, sizeof(double) * 2 * (size_t)a->N * p.Cstat, stream);

@@ -582,13 +582,13 @@ int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream)
         m1 = m0;
     }
     const size_t smem = (size_t)p.w_bytes + (size_t)p.SA * p.a_stage_bytes + kZsBarrierBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {false};
+    if (!configured[current_device()]) {
         const int max_dyn = zs_max_dyn_smem();
         if (max_dyn <= 0) return set_error("conv(z-stacked): cudaFuncGetAttributes failed");
         cudaError_t e = cudaFuncSetAttribute(conv_zs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
         if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured[current_device()] = true;
     }
     if (p.stats) {
         cudaError_t e = cudaMemsetAsync(p.stats, 0, sizeof(double) * 2 * (size_t)a->N * p.Cstat, stream);

@@ -380,6 +380,7 @@ struct NormBwdDev {
     int Ch;                                  // 16-byte planes of dy
     __half* dy_pl;                           // planar copies carry the same 2^k scale as dy
     int pl_kw, pl_pw, pl_Wx;
+    int g1_crop, g1_od, g1_oh, g1_ow, g1_D, g1_H, g1_W;   // g1 = gradient of a centre-cropped view (zero outside the box)
 };
 
 // power-of-two scale that brings a tensor bounded by `bound` to at most 2^14 (fp16 max is 2^16)
@@ -402,7 +403,17 @@ E3B_DEVINL void load_vox(const NormBwdDev& p, size_t o, int n, int cq, int z, in
 {
     in.y = p.y[o];
     if (p.g0) in.g0 = __ldcs(p.g0 + o);
-    if (p.g1) in.g1 = __ldcs(p.g1 + o);
+    if (p.g1) {
+        if (!p.g1_crop) {
+            in.g1 = __ldcs(p.g1 + o);
+        } else {
+            // backward of autocrop's slice of the skip tensor: zero outside the cropped box
+            const int zc = z - p.g1_od, yc = yy - p.g1_oh, xc = x - p.g1_ow;
+            in.g1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (zc >= 0 && zc < p.g1_D && yc >= 0 && yc < p.g1_H && xc >= 0 && xc < p.g1_W)
+                in.g1 = __ldcs(p.g1 + ((((size_t)n * p.Cq + cq) * p.g1_D + zc) * p.g1_H + yc) * p.g1_W + xc);
+        }
+    }
     if (p.gp) {
         const int zw = z / p.wd, yw = yy / p.wh, xw = x / p.ww;
         in.slot = (unsigned char)(((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww));
@@ -1123,6 +1134,11 @@ static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)
     p.amax = a->amax; p.dy_scale = a->dy_scale;
     p.Ch = a->s2d ? cpad16(p.wd * p.wh * p.ww * p.Cq * 4) / 8 : cpad16(a->C) / 8;
     p.pl_kw = a->planar_kw > 0 ? a->planar_kw : 1; p.pl_pw = a->planar_pw; p.pl_Wx = a->planar_W > 0 ? a->planar_W : a->W;
+    p.g1_crop = a->g1_crop; p.g1_od = a->g1_od; p.g1_oh = a->g1_oh; p.g1_ow = a->g1_ow;
+    p.g1_D = a->g1_D; p.g1_H = a->g1_H; p.g1_W = a->g1_W;
+    if (a->g1_crop && (!a->g1 || a->g1_od < 0 || a->g1_oh < 0 || a->g1_ow < 0 || a->g1_od + a->g1_D > a->D ||
+                       a->g1_oh + a->g1_H > a->H || a->g1_ow + a->g1_W > a->W))
+        return set_error("norm_bwd: the cropped skip gradient box does not fit the tensor");
     if (p.Cq > 65535 || a->N > 65535) return set_error("norm_bwd: too many channels / samples for the launch grid");
     return 0;
 }

@@ -13,7 +13,9 @@ int set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);
 
-int num_sms();
+static constexpr int kMaxDevices = 64;
+int current_device();     // cudaGetDevice(), clamped to [0, kMaxDevices)
+int num_sms();            // of the current device
 int conv_ntile_width(int npad_total);
 int make_qp_tensor_map(CUtensorMap* map, const float* ptr, int N, int Cq, int D, int H, int W, int Da, int Ha, int Wa,
                        int bx, int by, int bz, int bcq);

@@ -484,11 +484,11 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     rc = make_dy_map(&mdy, a->dy, a->N, a->Co, a->kw, p.Do, p.Ho, a->W, p.NTW, p.TY);
     if (rc) return rc;
     const size_t smem = (size_t)p.SA * p.a_bytes + (size_t)p.SB * p.b_plane_bytes + 1024 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {false};
+    if (!configured[current_device()]) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
+        configured[current_device()] = true;
     }
     wgrad_tc_kernel<<<p.units * p.S, kWgThreads, smem, stream>>>(mx0, mx1, mdy, p);
     rc = check_launch("wgrad_tc");

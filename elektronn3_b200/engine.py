@@ -53,13 +53,14 @@ def planar_from_ncdhw(x5):
 class QP:
     """A device tensor in quad-planar layout (+ optionally its planar copy `pl`): float32 QP, or -- when
     ``half`` -- the float16 QH operand layout."""
-    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W', 'pl', 'idx', 'half', 'scale')
+    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W', 'pl', 'idx', 'half', 'scale', 'crop_off')
 
     def __init__(self, t, N, C, D, H, W, pl=None):
         self.t, self.N, self.C, self.D, self.H, self.W, self.pl = t, N, C, D, H, W, pl
         self.idx = None            # pooled tensors: arg-max slots of the pooling windows (uint8)
         self.half = t.dtype == torch.float16
         self.scale = None          # gradients: device float[4] (bound bits, 2^k, 2^-k, -) of the fp16 scale
+        self.crop_off = None       # gradient of a centre-cropped view: offset of the view inside the full tensor
 
     @staticmethod
     def empty(N, C, D, H, W, device):
@@ -138,14 +139,29 @@ def conv_variant(C0, C1, n_total, k):
 
 
 class WeightCache:
-    """Packed-weight images keyed by (parameter identity, mode); invalidated by the parameter's
-    in-place version counter (optimizer steps, load_state_dict) or a moved storage (.to(device))."""
+    """Packed-weight images of one UNet instance.
+
+    Training mode: NEVER served from the cache.  Parameters change every step, and the reference's own code
+    writes them in ways no version counter sees (``p.data.copy_`` in training/swa.py:201 ``swap_swa_sgd``,
+    ``p.data.addcdiv_`` in training/padam.py:94), so every training forward / backward re-packs (23 small launches
+    for cfg 2 -- what an optimizer step cost before, too).
+    Eval mode: an image is reused while (storage, version) of every tensor that entered it AND the cache epoch are
+    unchanged.  The epoch moves on every training-mode forward (BatchNorm running statistics are written through raw
+    pointers by e3b_norm_finalize), on ``train()`` / ``eval()``, ``load_state_dict`` and ``_apply`` of the module,
+    and once per ``Predictor.predict`` call."""
 
     def __init__(self):
         self.d = {}
+        self.epoch = 0
 
-    def get(self, key, params, make):
-        sig = tuple((p.data_ptr(), p._version) for p in params if p is not None)
+    def invalidate(self):
+        self.epoch += 1
+        self.d.clear()
+
+    def get(self, key, params, make, training=False):
+        if training:
+            return make()
+        sig = (self.epoch,) + tuple((p.data_ptr(), p._version) for p in params if p is not None)
         hit = self.d.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
@@ -376,9 +392,9 @@ def _conv_weights(net, spec, mode, training):
         def make():
             s, b = _bn_fold(conv, n)
             return pack_weights(pmode, conv.weight, s, spec.C0, spec.C1, spec.Co, spec.k), b
-        return net.cache.get((spec.name, 'fwd_fold'), params, make)
+        return net.cache.get((spec.name, 'fwd_fold'), params, make, training)
     wpk = net.cache.get((spec.name, 'fwd'), (conv.weight,),
-                        lambda: pack_weights(pmode, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k))
+                        lambda: pack_weights(pmode, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k), training)
     return wpk, (conv.bias.detach() if conv.bias is not None else None)
 
 
@@ -464,10 +480,10 @@ def _run_up(net, spec, dec, enc, training, save):
             shape = (1, -1) + (1,) * (up.weight.dim() - 2)
             return pack_weights(2, (up.weight.detach() * s.view(shape)).contiguous(), None, spec.Ci, 0, spec.Co,
                                 spec.s), b
-        wpk, bias = net.cache.get((spec.name, 'up_fold'), params, make)
+        wpk, bias = net.cache.get((spec.name, 'up_fold'), params, make, training)
     else:
         wpk = net.cache.get((spec.name, 'up'), (up.weight,),
-                            lambda: pack_weights(2, up.weight, None, spec.Ci, 0, spec.Co, spec.s))
+                            lambda: pack_weights(2, up.weight, None, spec.Ci, 0, spec.Co, spec.s), training)
     if mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save):
         a, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias, relu=True,
                                scatter=spec.s, out_spatial=out_sp, half_out=True)
@@ -558,8 +574,14 @@ def head(feat, conv_final, out_mode=0, dst=None, crop=None, dst_origin=None, dst
 
 
 def forward(net, x, training, save):
-    feat, tape = forward_features(net, x, training, save)
-    logits = head(feat, net.final)
+    _require_cuda(x, 'input')
+    # the kernels are launched on the CURRENT device's current stream: make that the tensor's device
+    # (model.to('cuda:1') without torch.cuda.set_device(1), nn.DataParallel replica threads)
+    with torch.cuda.device(x.device):
+        if training:
+            net.cache.invalidate()       # eval-mode images (folded BatchNorm statistics) are stale after this pass
+        feat, tape = forward_features(net, x, training, save)
+        logits = head(feat, net.final)
     if tape.squeeze:
         logits = logits.squeeze(2)
     return logits, tape
@@ -567,7 +589,9 @@ def forward(net, x, training, save):
 
 # ------------------------------------------------------------------------------------------ backward
 def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True, planar=True, conv_geom=None):
-    """Backward of norm -> relu [-> pool] for unit `u`; returns (dy QP or s2d QP, dgamma, dbeta, dbias)."""
+    """Backward of norm -> relu [-> pool] for unit `u`; returns (dy QP or s2d QP, dgamma, dbeta, dbias).
+    g1 may be the gradient of a centre-cropped view of this unit's activation (``g1.crop_off`` set by
+    _conv_unit_bwd): it is then added inside that box only (the backward of autocrop's slice is a zero pad)."""
     if u.mode == MODE_BATCH_EVAL:
         raise NotImplementedError('backward through eval-mode BatchNorm is not on the accelerated path '
                                   '(call model.train() or wrap evaluation in torch.no_grad())')
@@ -581,6 +605,10 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True, planar=True,
     args.g0, args.g1, args.gp = (g0.ptr if g0 is not None else None, g1.ptr if g1 is not None else None,
                                  gp.ptr if gp is not None else None)
     args.N, args.C, args.D, args.H, args.W = N, C, a.D, a.H, a.W
+    if g1 is not None and (g1.crop_off is not None or g1.spatial != a.spatial):
+        args.g1_crop = 1
+        args.g1_od, args.g1_oh, args.g1_ow = g1.crop_off or (0, 0, 0)
+        args.g1_D, args.g1_H, args.g1_W = g1.spatial
     if gp is not None:
         args.pk_d, args.pk_h, args.pk_w = u.pool
         if u.pooled is None or u.pooled.idx is None:
@@ -656,27 +684,48 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
         _put(grads, n.bias, dbeta)
     if conv.bias is not None:
         _put(grads, conv.bias, dbias)
+    cropped = u.src1 is not None and (tuple(u.off1) != (0, 0, 0) or u.src1.spatial != u.src0.spatial)
     if conv.weight.requires_grad:
-        dw = wgrad(u.src0, dy, spec.Co, spec.k, spec.pad, tuple(conv.weight.shape), src1=u.src1, off1=u.off1)
+        src1, off1 = u.src1, u.off1
+        if cropped and (any(spec.pad) or off1[2] % 8):
+            # the weight-gradient kernel reads a cropped second source in place only for un-padded convolutions and
+            # 16-byte aligned x offsets; otherwise hand it the cropped view as a tensor of its own (memory plumbing
+            # of an off-default configuration: VALID-mode training)
+            src1, off1 = _cropped_planar(u.src1, u.off1, u.src0.spatial), (0, 0, 0)
+        dw = wgrad(u.src0, dy, spec.Co, spec.k, spec.pad, tuple(conv.weight.shape), src1=src1, off1=off1)
         _put(grads, conv.weight, dw)
     if not need_dx:
         return None, None
-    if u.src1 is not None and (u.off1 != (0, 0, 0) or u.src1.spatial != u.src0.spatial):
-        raise NotImplementedError('backward through a centre-cropped skip connection (conv_mode="valid") '
-                                  'is not on the accelerated path yet')
     dvar = spec.variants[1]
     wpk = net.cache.get((spec.name, 'dgrad'), (conv.weight,),
-                        lambda: pack_weights(5 if dvar else 1, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k))
+                        lambda: pack_weights(5 if dvar else 1, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k), True)
     dpad = tuple(kk - 1 - pp for kk, pp in zip(spec.k, spec.pad))
     d0, d1, _ = conv_forward(dy, wpk, spec.n_total_dgrad, spec.C0, spec.k, dpad,
                              dst1_C=spec.C1 if u.src1 is not None else 0, variant=dvar)
+    if cropped:
+        d1.crop_off = tuple(u.off1)       # gradient of autocrop's slice of the skip tensor (models/unet.py:303-324)
     return d0, d1
+
+
+def _cropped_planar(src, off, spatial):
+    """The centre-cropped view of a tensor's z-planar copy (N, D, C, H, ceil8(W)) as a contiguous planar tensor."""
+    D, H, W = spatial
+    pl = src.pl[:, off[0]:off[0] + D, :, off[1]:off[1] + H, off[2]:off[2] + W]
+    if W % 8:
+        pl = torch.nn.functional.pad(pl, (0, (-W) % 8))
+    q = QP(src.t, src.N, src.C, D, H, W, pl=pl.contiguous())
+    return q
 
 
 def backward(net, tape, dlogits, need_dx):
     """-> (dict id(param) -> grad tensor, dx or None)"""
-    grads = {}
     _require_cuda(dlogits, 'grad_output')
+    with torch.cuda.device(dlogits.device):
+        return _backward(net, tape, dlogits, need_dx)
+
+
+def _backward(net, tape, dlogits, need_dx):
+    grads = {}
     dl = dlogits.unsqueeze(2) if tape.squeeze else dlogits
     dl = dl.contiguous()
     feat = tape.final_in
@@ -713,14 +762,15 @@ def backward(net, tape, dlogits, need_dx):
                         up_co=ups.Co)
             _put(grads, up.weight, dwu)
         wpk = net.cache.get((ups.name, 'up_dgrad'), (up.weight,),
-                            lambda: pack_weights(3, up.weight, None, ups.Ci, 0, ups.Co, ups.s))
+                            lambda: pack_weights(3, up.weight, None, ups.Ci, 0, ups.Co, ups.s), True)
         g, _, _ = conv_forward(dy, wpk, cpad16(ups.Ci), ups.Ci, (1, 1, 1), (0, 0, 0))
     nd = len(net.down)
     dx = None
     for i in range(nd - 1, -1, -1):
         u1, u2 = tape.down[i]
+        # (the skip gradient always travels as g1: it may be the gradient of a centre-cropped view)
         if u2.pool is not None:
-            g, _ = _conv_unit_bwd(net, u2, skip.get(i), None, g, grads, True)
+            g, _ = _conv_unit_bwd(net, u2, None, skip.get(i), g, grads, True)
         else:
             g, _ = _conv_unit_bwd(net, u2, g, skip.get(i), None, grads, True)
         g, _ = _conv_unit_bwd(net, u1, g, None, None, grads, i > 0 or need_dx)

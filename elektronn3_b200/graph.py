@@ -37,8 +37,11 @@ class GraphedTrainStep:
         from . import _lib
         self.inp = torch.zeros(inp_shape, dtype=torch.float32, device=dev)
         self.target = torch.zeros(target_shape, dtype=target_dtype, device=dev)
-        # warm-up on a side stream (lazy initialisation of kernels, allocator and optimizer state happens here,
-        # not under capture); the parameters move, which is what training steps do
+        # Warm-up on a side stream: lazy initialisation of kernels, allocator and optimizer state happens here, not
+        # under capture.  The warm-up steps run on an all-zero batch and must leave NO trace: parameters, BatchNorm
+        # statistics / counters and optimizer state are snapshotted and restored IN PLACE afterwards (the graph keeps
+        # the addresses), so the first replay starts from exactly the state the caller handed in.
+        snap = self._snapshot()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -61,7 +64,38 @@ class GraphedTrainStep:
             if optimizer is not None:
                 optimizer.step()
         self.launches_per_step = _lib.launch_count() - l0      # libe3b.so kernels inside one replay
+        self._restore(snap)
         self._invalidate()
+
+    def _snapshot(self):
+        model_t = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        opt_t, opt_py = {}, {}
+        if self.optimizer is not None:
+            for p, st in self.optimizer.state.items():
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        opt_t[(id(p), k)] = v.detach().clone()
+                    else:
+                        opt_py[(id(p), k)] = v
+        return model_t, opt_t, opt_py
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        model_t, opt_t, opt_py = snap
+        for k, v in self.model.state_dict().items():
+            v.copy_(model_t[k])
+        if self.optimizer is not None:
+            for p, st in self.optimizer.state.items():
+                for k, v in list(st.items()):
+                    if torch.is_tensor(v):
+                        # state created by the warm-up (momentum buffers, Adam moments / step) is zeroed in place: for
+                        # SGD and Adam a zero state is the state of a fresh optimizer
+                        old = opt_t.get((id(p), k))
+                        v.copy_(old) if old is not None else v.zero_()
+                    elif (id(p), k) in opt_py:
+                        st[k] = opt_py[(id(p), k)]
+                    elif isinstance(v, (int, float)):
+                        st[k] = type(v)(0)
 
     def _eager_step(self):
         for p in self.model.parameters():
@@ -76,9 +110,7 @@ class GraphedTrainStep:
     def _invalidate(self):
         # the replay rewrites the parameters without bumping their Python-side version counters: drop the packed
         # weight images keyed on them, so that an eager call of the module (validation) re-packs
-        net = self.model.__dict__.get('_e3b_net')
-        if net is not None:
-            net.cache.d.clear()
+        self.model.invalidate_weight_cache()
 
     def __call__(self, inp, target):
         """copy the batch into the graph's static buffers (H2D when they are host tensors), replay.

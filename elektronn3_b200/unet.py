@@ -128,11 +128,12 @@ class _UNetFunction(torch.autograd.Function):
     backward launches dgrad / wgrad / norm-backward kernels and returns per-parameter gradients."""
 
     @staticmethod
-    def forward(ctx, model, x, *params):
+    def forward(ctx, model, save, x, *params):
+        # `save` is decided by the caller: grad mode is always off in here, and ctx.needs_input_grad reflects
+        # requires_grad of the inputs whatever the grad mode (so it is True under torch.no_grad(), too)
         net = model._net()
-        need_grad = any(ctx.needs_input_grad)      # all False under torch.no_grad()
-        logits, tape = engine.forward(net, x.detach(), model.training, save=need_grad)
-        ctx.model, ctx.tape, ctx.params = model, (tape if need_grad else None), params
+        logits, tape = engine.forward(net, x.detach(), model.training, save=save)
+        ctx.model, ctx.tape, ctx.params = model, (tape if save else None), params
         ctx.need_dx = x.requires_grad
         return logits
 
@@ -142,7 +143,7 @@ class _UNetFunction(torch.autograd.Function):
             raise RuntimeError('backward called on a forward that saved no activations')
         grads, dx = engine.backward(ctx.model._net(), ctx.tape, dlogits, ctx.need_dx)
         ctx.tape = None
-        return (None, dx) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
+        return (None, None, dx) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
 
 
 class UNet(nn.Module):
@@ -269,14 +270,47 @@ class UNet(nn.Module):
         self.__dict__.pop('_e3b_net', None)      # parameters may be re-created (.to(), .half(), ...)
         return super()._apply(fn, *args, **kwargs)
 
+    def invalidate_weight_cache(self):
+        """Drop the packed weight images (eval mode keeps them between calls).  Needed only after writing parameters
+        or BatchNorm statistics through ``.data`` / raw pointers while staying in eval mode; ``train()``, ``eval()``,
+        ``load_state_dict`` and every training-mode forward do it themselves."""
+        net = self.__dict__.get('_e3b_net')
+        if net is not None:
+            net.cache.invalidate()
+
+    def train(self, mode: bool = True):
+        self.invalidate_weight_cache()
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate_weight_cache()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _param_tensors(self):
+        """The tensors autograd must see as inputs of the network node, in a fixed order.  On an ``nn.DataParallel``
+        replica ``parameters()`` is empty (``Module._replicate_for_data_parallel`` clears ``_parameters``): the broadcast
+        copies hang on the submodules as plain attributes / ``_former_parameters`` (torch/nn/parallel/replicate.py), and
+        gradients flow through them back to the real parameters."""
+        if not getattr(self, '_is_replica', False):
+            return list(self.parameters())
+        out = []
+        for mod in self.modules():
+            former = getattr(mod, '_former_parameters', None)
+            if former:
+                out.extend(t for t in former.values() if t is not None)
+        return out
+
     def forward(self, x):
         if x.dim() != self.dim + 2:
             raise RuntimeError(f'Expected {self.dim + 2}D input (N, C{", D" if self.dim == 3 else ""}, H, W), '
                                f'got shape {tuple(x.shape)}')
         if torch.is_autocast_enabled():
             x = x.float()                        # fp16 operands / fp32 accumulate regardless of autocast
+        params = self._param_tensors()
+        # activations (fp32 conv outputs, planar copies, pooling indices) are kept only when a backward can follow
+        save = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         with torch.autocast(device_type='cuda', enabled=False):
-            return _UNetFunction.apply(self, x, *self.parameters())
+            return _UNetFunction.apply(self, save, x, *params)
 
     @torch.jit.unused
     def forward_gradcp(self, x):

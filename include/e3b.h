@@ -187,6 +187,10 @@ typedef struct e3b_norm_bwd_args {
                                                   s2d: (N, Dw, 1, taps*pad8(C), Hw, ceil8(Ww)) */
     int32_t planar_kw, planar_pw, planar_W;    /* kw, pw and input width Wx of the conv dy belongs to (0 -> 1,0,W) */
     int32_t relu;
+    int32_t g1_crop;                           /* 1: g1 is the gradient of a CENTRE-CROPPED view of this tensor (autocrop,
+                                                  unet.py:303-324; the backward of the slice is a zero pad): it has extents
+                                                  (g1_D,g1_H,g1_W) and is added inside the box starting at (g1_od,g1_oh,g1_ow) */
+    int32_t g1_od, g1_oh, g1_ow, g1_D, g1_H, g1_W;
 } e3b_norm_bwd_args;
 int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* args, void* stream);
 int e3b_norm_bwd_finalize(const e3b_norm_bwd_args* args, void* stream);
