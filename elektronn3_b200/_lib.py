@@ -29,6 +29,7 @@ class ConvArgs(ctypes.Structure):
         ('dst1', c_void_p), ('Cd1', c_i32),
         ('relu', c_i32), ('half_out', c_i32),
         ('out_scale', c_void_p),
+        ('w_unscale', c_void_p),
         ('stats', c_void_p), ('stats_channels', c_i32),
         ('scatter', c_i32), ('sd', c_i32), ('sh', c_i32), ('sw', c_i32),
         ('Ds', c_i32), ('Hs', c_i32), ('Ws', c_i32),
@@ -89,6 +90,10 @@ class HeadArgs(ctypes.Structure):
         ('cn_d', c_i32), ('cn_h', c_i32), ('cn_w', c_i32),
         ('dst_origin', c_void_p),
         ('dst_single', c_i32),
+        ('flip', c_i32),
+        ('accumulate', c_i32), ('acc_scale', c_float),
+        ('use_threshold', c_i32), ('threshold', c_float),
+        ('round_half', c_i32),
     ]
 
 
@@ -99,9 +104,9 @@ SIGNATURES = {
     'e3b_launch_count': (c_i64, []),
     'e3b_pack_ncdhw': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
     'e3b_unpack_qp': (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
-    'e3b_gather_tiles': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    'e3b_gather_tiles': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
     'e3b_packed_weight_floats': (c_i64, [c_int] * 7),
-    'e3b_pack_weights': (c_int, [c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    'e3b_pack_weights': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     'e3b_conv': (c_int, [ctypes.POINTER(ConvArgs), c_void_p]),
     'e3b_conv_variant': (c_int, [c_int] * 7),
     'e3b_debug_zs_read': (c_int, [c_void_p, c_int]),
@@ -116,6 +121,7 @@ SIGNATURES = {
     'e3b_norm_bwd_finalize': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_apply': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_head': (c_int, [ctypes.POINTER(HeadArgs), c_void_p]),
+    'e3b_prob_argmax': (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_float, c_void_p]),
     'e3b_head_bwd': (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),
 }
 

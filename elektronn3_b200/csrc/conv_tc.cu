@@ -53,6 +53,7 @@ struct ConvTcParams {
     int debug;                   // accumulate role timings into g_conv_dbg
     int half_out;                // store the output as a QH (fp16) operand tensor: it feeds the next MMA
     const float* out_scale;      // optional device scalar multiplied into the accumulator (gradient un-scaling)
+    const float* w_unscale;      // optional second one (un-scaling of power-of-two scaled weights)
     double* stats;               // [N][Cstat][2] sum / sumsq (fp64 atomics) or null
     int Cstat;
     int scatter;                 // 1: k=s transposed conv, column n = tap*Cup + co, dst is the fine grid
@@ -263,7 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         uint32_t it = 0;
         unsigned long long dbg[16] = {0};
         DBG_T0(t_all);
-        const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.f;
+        const float oscale = (p.out_scale ? __ldg(p.out_scale) : 1.f) * (p.w_unscale ? __ldg(p.w_unscale) : 1.f);
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it++) {
             const uint32_t buf = it & 1, use = it >> 1;
             int nt, n, z0, y0, x0;
@@ -583,7 +584,7 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
     p.cq0_alloc = a->half_out ? e3b_cpad16(a->Cd0) / 8 : e3b_cpad(a->Cd0) / 4;      // 16-byte planes in dst0
     p.cq1_alloc = a->dst1 ? e3b_cpad(a->Cd1) / 4 : 0;
     p.cq0 = a->dst1 ? p.cq0_alloc : (1 << 30);
-    p.relu = a->relu; p.half_out = a->half_out; p.out_scale = a->out_scale;
+    p.relu = a->relu; p.half_out = a->half_out; p.out_scale = a->out_scale; p.w_unscale = a->w_unscale;
     if (a->half_out && a->dst1) return set_error("conv: the fp16 operand output has a single destination");
     if (a->half_out && a->stats) return set_error("conv: statistics are taken from an fp32 output");
     p.debug = getenv("E3B_CONV_DEBUG") != nullptr;

@@ -84,7 +84,7 @@ struct ConvZsParams {
     const float* bias; int n_bias;
     float* dst0; int cq0; float* dst1; int cq0_alloc, cq1_alloc;
     int relu, half_out;
-    const float* out_scale;
+    const float* out_scale; const float* w_unscale;
     double* stats; int Cstat;
     const uint8_t* wpk;
     uint32_t* dbg;               // host-mapped debug words or null
@@ -355,7 +355,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         named_bar_sync(1, 256);                 // bias_s visible to the epilogue warps
         if (eg == 0 && lane == 0) for (int b = 0; b < p.R; b++) mbar_arrive(&blk_free[b]);
 
-        const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.f;
+        const float oscale = (p.out_scale ? __ldg(p.out_scale) : 1.f) * (p.w_unscale ? __ldg(p.w_unscale) : 1.f);
         const bool reg_stats = p.stats != nullptr && p.NTW <= 32;     // per-thread partial sums over a whole run
         float rs[32], rq[32];
 #pragma unroll
@@ -564,7 +564,7 @@ int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream)
     p.cq0_alloc = a->half_out ? cpad16(a->Cd0) / 8 : cpad8(a->Cd0) / 4;
     p.cq1_alloc = a->dst1 ? cpad8(a->Cd1) / 4 : 0;
     p.cq0 = a->dst1 ? p.cq0_alloc : (1 << 30);
-    p.relu = a->relu; p.half_out = a->half_out; p.out_scale = a->out_scale;
+    p.relu = a->relu; p.half_out = a->half_out; p.out_scale = a->out_scale; p.w_unscale = a->w_unscale;
     if (a->half_out && a->dst1) return set_error("conv: the fp16 operand output has a single destination");
     if (a->half_out && a->stats) return set_error("conv: statistics are taken from an fp32 output");
     p.stats = a->stats; p.Cstat = a->stats_channels;

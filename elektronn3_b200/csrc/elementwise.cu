@@ -43,7 +43,7 @@ E3B_DEVINL void store_qh(uint2* __restrict__ qh, const float4& v, int n, int Ch,
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const float* __restrict__ src, const int32_t* __restrict__ origins, uint2* __restrict__ dst,
                             __half* __restrict__ dst_pl, int N, int C, int Cq, int D, int H, int W, int Dv, int Hv, int Wv,
-                            int z0, int y0, int x0, int single)
+                            int z0, int y0, int x0, int single, int flip)
 {
     // Cq = ceil16(C)/4 fp32 quads per voxel: the padding channels of the 16-channel chunks are written as 0
     const size_t total = (size_t)N * Cq * D * H * W;
@@ -58,7 +58,9 @@ __global__ void pack_kernel(const float* __restrict__ src, const int32_t* __rest
         const int n = (int)(r / Cq);
         int oz = z0, oy = y0, ox = x0;
         if (origins) { oz = origins[3 * n]; oy = origins[3 * n + 1]; ox = origins[3 * n + 2]; }
-        const int sz = z + oz, sy = y + oy, sx = x + ox;
+        // (flip: the tile is mirrored while it is gathered -- FlipAugment.forward of the Predictor's TTA)
+        const int sz = ((flip & 1) ? D - 1 - z : z) + oz, sy = ((flip & 2) ? H - 1 - y : y) + oy,
+                  sx = ((flip & 4) ? W - 1 - x : x) + ox;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (sz >= 0 && sz < Dv && sy >= 0 && sy < Hv && sx >= 0 && sx < Wv) {
             const size_t vox = ((size_t)sz * Hv + sy) * Wv + sx;
@@ -108,8 +110,10 @@ static PackDims pack_dims(int mode, int C0, int C1, int Co, int kd, int kh, int 
 }
 
 __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, const float* __restrict__ scale,
-                                    __half* __restrict__ dst, int C0, int C1, int Co, int tu, PackDims d)
+                                    const float* __restrict__ wscale, __half* __restrict__ dst, int C0, int C1, int Co, int tu,
+                                    PackDims d)
 {
+    const float ws = wscale ? __ldg(wscale) : 1.f;       // power of two: max|w| -> [1, 2), undone in the conv epilogue
     const size_t total = (size_t)d.ktot * d.ntot * d.taps;
     const int C0p16 = cpad16(C0), C0p8 = cpad8(C0), Cop8 = cpad8(Co), Cop16 = cpad16(Co);
     const int nchunks = d.ktot / 16;
@@ -157,7 +161,7 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, const
             const int t = k / Cop8, co = k % Cop8;
             if (t < tu && n < C0 && co < Co) v = w[((size_t)n * Co + co) * tu + t];
         }
-        dst[i] = __float2half_rn(v);
+        dst[i] = __float2half_rn(v * ws);
     }
 }
 
@@ -869,7 +873,10 @@ __global__ void __launch_bounds__(256) head_kernel(const e3b_head_args p, int Cq
         const int x = (int)(r % p.cn_w); r /= p.cn_w;
         const int y = (int)(r % p.cn_h);
         const int z = (int)(r / p.cn_h);
-        const size_t vin = ((size_t)(z + p.c0_d) * p.H + (y + p.c0_h)) * p.W + (x + p.c0_w);
+        // (flip: the features are the network output on a mirrored tile -- FlipAugment.backward of the TTA)
+        const int zi = (p.flip & 1) ? p.D - 1 - (z + p.c0_d) : z + p.c0_d, yi = (p.flip & 2) ? p.H - 1 - (y + p.c0_h) : y + p.c0_h,
+                  xi = (p.flip & 4) ? p.W - 1 - (x + p.c0_w) : x + p.c0_w;
+        const size_t vin = ((size_t)zi * p.H + yi) * p.W + xi;
         float acc[kHeadMaxCo];
 #pragma unroll
         for (int co = 0; co < kHeadMaxCo; co++) acc[co] = co < p.Co ? sw[p.Co * Cp + co] : 0.f;
@@ -890,28 +897,56 @@ __global__ void __launch_bounds__(256) head_kernel(const e3b_head_args p, int Cq
         if (z + oz >= p.Dd || y + oy >= p.Hd || x + ox >= p.Wd || z + oz < 0 || y + oy < 0 || x + ox < 0) continue;
         const size_t vout = ((size_t)(z + oz) * p.Hd + (y + oy)) * p.Wd + (x + ox);
         const size_t nb = p.dst_single ? 0 : (size_t)n;
+        if (p.out_mode == 1 || (p.out_mode == 2 && p.use_threshold)) {
+            float mx = acc[0];
+#pragma unroll
+            for (int co = 1; co < kHeadMaxCo; co++) if (co < p.Co) mx = fmaxf(mx, acc[co]);
+            float sum = 0.f;
+#pragma unroll
+            for (int co = 0; co < kHeadMaxCo; co++) if (co < p.Co) { acc[co] = expf(acc[co] - mx); sum += acc[co]; }
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int co = 0; co < kHeadMaxCo; co++) acc[co] *= inv;
+        }
         if (p.out_mode == 2) {
+            if (p.use_threshold) {
+#pragma unroll
+                for (int co = 0; co < kHeadMaxCo; co++) if (co < p.Co && !(acc[co] > p.threshold)) acc[co] = 0.f;
+            }
             int best = 0; float bv = acc[0];
 #pragma unroll
             for (int co = 1; co < kHeadMaxCo; co++) if (co < p.Co && acc[co] > bv) { bv = acc[co]; best = co; }
             reinterpret_cast<uint8_t*>(p.dst)[nb * Sd + vout] = (uint8_t)best;
         } else {
-            if (p.out_mode == 1) {
-                float mx = acc[0];
-#pragma unroll
-                for (int co = 1; co < kHeadMaxCo; co++) if (co < p.Co) mx = fmaxf(mx, acc[co]);
-                float sum = 0.f;
-#pragma unroll
-                for (int co = 0; co < kHeadMaxCo; co++) if (co < p.Co) { acc[co] = expf(acc[co] - mx); sum += acc[co]; }
-                const float inv = 1.f / sum;
-#pragma unroll
-                for (int co = 0; co < kHeadMaxCo; co++) acc[co] *= inv;
-            }
             float* d = reinterpret_cast<float*>(p.dst);
+            const float scl = p.acc_scale != 0.f ? p.acc_scale : 1.f;
 #pragma unroll
             for (int co = 0; co < kHeadMaxCo; co++)
-                if (co < p.Co) d[(nb * p.Co + co) * Sd + vout] = acc[co];
+                if (co < p.Co) {
+                    float v = acc[co];
+                    if (p.round_half) v = __half2float(__float2half_rn(v));
+                    float* o = d + (nb * p.Co + co) * Sd + vout;
+                    *o = p.accumulate ? fmaf(scl, v, *o) : scl * v;
+                }
         }
+    }
+}
+
+// argmax over the channels of a probability volume, optional threshold (the Predictor's deferred argmax after the
+// test-time-augmentation mean, inference.py:519-523)
+__global__ void __launch_bounds__(256) prob_argmax_kernel(const float* __restrict__ prob, uint8_t* __restrict__ dst, int N, int C,
+                                                          size_t S, int use_threshold, float threshold)
+{
+    const size_t total = (size_t)N * S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = i / S, v = i % S;
+        int best = 0; float bv = 0.f;
+        for (int c = 0; c < C; c++) {
+            float x = prob[(n * C + c) * S + v];
+            if (use_threshold && !(x > threshold)) x = 0.f;
+            if (c == 0 || x > bv) { bv = x; best = c; }
+        }
+        dst[i] = (uint8_t)best;
     }
 }
 
@@ -1020,18 +1055,18 @@ int e3b_pack_ncdhw(const float* src, void* dst_qp, void* dst_planar, int N, int 
     const int Cq = cpad16(C) / 4;
     const size_t total = (size_t)N * Cq * D * H * W;
     pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, nullptr, reinterpret_cast<uint2*>(dst_qp),
-                                                                        reinterpret_cast<__half*>(dst_planar), N, C, Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0);
+                                                                        reinterpret_cast<__half*>(dst_planar), N, C, Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0, 0);
     return check_launch("pack_ncdhw");
 }
 
 int e3b_gather_tiles(const float* vol, const int32_t* origins, void* dst_qp, int B, int C, int D, int H, int W, int Dv,
-                     int Hv, int Wv, void* stream)
+                     int Hv, int Wv, int flip, void* stream)
 {
     if (B <= 0 || C <= 0) return set_error("gather: empty batch");
     const int Cq = cpad16(C) / 4;
     const size_t total = (size_t)B * Cq * D * H * W;
     pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vol, origins, reinterpret_cast<uint2*>(dst_qp), nullptr,
-                                                                        B, C, Cq, D, H, W, Dv, Hv, Wv, 0, 0, 0, 1);
+                                                                        B, C, Cq, D, H, W, Dv, Hv, Wv, 0, 0, 0, 1, flip);
     return check_launch("gather_tiles");
 }
 
@@ -1057,15 +1092,15 @@ int64_t e3b_packed_weight_floats(int mode, int C0, int C1, int Co, int kd, int k
     return (int64_t)d.ktot * d.ntot * d.taps / 2;        // fp16 elements, counted in floats
 }
 
-int e3b_pack_weights(int mode, const float* w, const float* scale, void* dst, int C0, int C1, int Co, int kd, int kh,
-                     int kw, void* stream)
+int e3b_pack_weights(int mode, const float* w, const float* scale, const float* wscale, void* dst, int C0, int C1, int Co,
+                     int kd, int kh, int kw, void* stream)
 {
     if (mode < 0 || mode > 5) return set_error("pack_weights: bad mode %d", mode);
     PackDims d = pack_dims(mode, C0, C1, Co, kd, kh, kw);
     if (!pack_mode_ok(mode, d, kd, kh, kw)) return set_error("pack_weights: mode %d does not support output width %d / these taps", mode, d.ntot);
     const size_t total = (size_t)d.ktot * d.ntot * d.taps;
-    pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mode, w, scale, reinterpret_cast<__half*>(dst), C0, C1, Co,
-                                                                                kd * kh * kw, d);
+    pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mode, w, scale, wscale, reinterpret_cast<__half*>(dst), C0,
+                                                                                C1, Co, kd * kh * kw, d);
     return check_launch("pack_weights");
 }
 
@@ -1211,11 +1246,19 @@ int e3b_head(const e3b_head_args* a, void* stream)
 {
     if (a->Co > kHeadMaxCo) return set_error("head: out_channels %d > %d not supported", a->Co, kHeadMaxCo);
     if (a->out_mode < 0 || a->out_mode > 2) return set_error("head: bad out_mode");
+    if (a->out_mode == 2 && (a->accumulate || a->round_half)) return set_error("head: accumulate / round_half apply to float outputs");
     const int Cq = cpad8(a->C) / 4;
     const size_t total = (size_t)a->N * a->cn_d * a->cn_h * a->cn_w;
     const size_t smem = sizeof(float) * ((size_t)a->Co * Cq * 4 + a->Co);
     head_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(*a, Cq);
     return check_launch("head");
+}
+
+int e3b_prob_argmax(const float* prob, uint8_t* dst, int N, int C, int64_t S, int use_threshold, float threshold, void* stream)
+{
+    if (N <= 0 || C <= 0 || C > 255 || S <= 0) return set_error("prob_argmax: bad extents");
+    prob_argmax_kernel<<<grid_for((size_t)N * S, 256), 256, 0, (cudaStream_t)stream>>>(prob, dst, N, C, (size_t)S, use_threshold, threshold);
+    return check_launch("prob_argmax");
 }
 
 int e3b_head_bwd(const float* dl, const void* a, const float* w, float* da, float* dw, float* db, double* workspace, int N,

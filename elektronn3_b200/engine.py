@@ -110,17 +110,20 @@ def unpack(q):
     return out
 
 
-def gather_tiles(vol, origins, B, C, tile):
-    """Predictor tile gather (inference.py:179-189): vol (C, Dv, Hv, Wv) device tensor, origins int32 (B,3)."""
+def gather_tiles(vol, origins, B, C, tile, flip=0):
+    """Predictor tile gather (inference.py:179-189): vol (C, Dv, Hv, Wv) device tensor, origins int32 (B,3).
+    flip: bit mask (D, H, W) of the test-time-augmentation mirror applied while gathering (inference.py:215-223)."""
     D, H, W = tile
     q = QP.empty_half(B, C, D, H, W, vol.device)
     L.check(L.lib().e3b_gather_tiles(vol.data_ptr(), origins.data_ptr(), q.ptr, B, C, D, H, W,
-                                     vol.shape[-3], vol.shape[-2], vol.shape[-1], _stream()), 'gather_tiles')
+                                     vol.shape[-3], vol.shape[-2], vol.shape[-1], flip, _stream()), 'gather_tiles')
     return q
 
 
 # ------------------------------------------------------------------------------------------ weights
-def pack_weights(mode, w, scale, C0, C1, Co, k):
+def pack_weights(mode, w, scale, C0, C1, Co, k, wscale=None):
+    """wscale: optional WeightScale -- the image is packed times its power of two 2^k (undone by the conv epilogue
+    through conv_forward(w_unscale=...)), so that tiny / huge weights keep their 10 mantissa bits in fp16."""
     n = L.lib().e3b_packed_weight_floats(mode, C0, C1, Co, *k)
     if n <= 0:
         raise RuntimeError(f'elektronn3_b200: unsupported channel configuration C0={C0} C1={C1} Co={Co}')
@@ -128,9 +131,48 @@ def pack_weights(mode, w, scale, C0, C1, Co, k):
     wc = w.detach()
     if not wc.is_contiguous():
         wc = wc.contiguous()
-    L.check(L.lib().e3b_pack_weights(mode, wc.data_ptr(), _p(scale), dst.data_ptr(), C0, C1, Co, *k, _stream()),
-            'pack_weights')
+    L.check(L.lib().e3b_pack_weights(mode, wc.data_ptr(), _p(scale), wscale.up_ptr if wscale is not None else None,
+                                     dst.data_ptr(), C0, C1, Co, *k, _stream()), 'pack_weights')
     return dst
+
+
+class WeightScale:
+    """One row (2^k, 2^-k) of a device table of per-tensor power-of-two weight scales."""
+    __slots__ = ('table', 'row')
+
+    def __init__(self, table, row):
+        self.table, self.row = table, row
+
+    @property
+    def up_ptr(self):
+        return self.table.data_ptr() + 8 * self.row
+
+    @property
+    def down_ptr(self):
+        return self.table.data_ptr() + 8 * self.row + 4
+
+
+def weight_scale_table(weights, channel_scales=None):
+    """(P, 2) float32 device table: for every weight tensor the power of two 2^k that brings max|w| into [1, 2) and its
+    inverse.  A handful of multi-tensor torch kernels for ALL tensors of the network (no host synchronisation).
+    channel_scales: optional per-tensor (factors [Co], output-channel axis) folded into the weights at pack time
+    (eval-mode BatchNorm); those tensors are measured after the fold."""
+    ws = [w.detach() for w in weights]
+    if channel_scales is not None and any(c is not None for c in channel_scales):
+        amaxes = []
+        for w, c in zip(ws, channel_scales):
+            if c is None:
+                amaxes.append(w.abs().max())
+            else:
+                f, axis = c
+                per_channel = w.abs().amax([d for d in range(w.dim()) if d != axis])
+                amaxes.append((per_channel * f.abs()).max())
+        amax = torch.stack(amaxes)
+    else:
+        amax = torch.stack(torch._foreach_norm(ws, float('inf')))
+    k = -torch.floor(torch.log2(amax.clamp_min(1e-37)))
+    k = torch.where((amax > 0) & torch.isfinite(amax), k, torch.zeros_like(k)).clamp_(-100.0, 100.0)
+    return torch.stack((torch.exp2(k), torch.exp2(-k)), 1).contiguous()
 
 
 def conv_variant(C0, C1, n_total, k):
@@ -172,7 +214,8 @@ class WeightCache:
 
 # ------------------------------------------------------------------------------------------ conv
 def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), bias=None, relu=False,
-                 stats_channels=0, dst1_C=0, scatter=None, out_spatial=None, force_tz=0, half_out=False, variant=0):
+                 stats_channels=0, dst1_C=0, scatter=None, out_spatial=None, force_tz=0, half_out=False, variant=0,
+                 w_unscale=None):
     """One launch of the implicit-GEMM kernel.  Sources are QH operand tensors; the output is float32 QP, or
     QH again with half_out (it is the next layer's operand).  A scaled gradient source (src0.scale) is
     un-scaled in the epilogue.  Returns (dst0, dst1, stats)."""
@@ -182,6 +225,8 @@ def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), b
         raise RuntimeError('conv: sources must be float16 QH operand tensors')
     if src0.scale is not None:
         a.out_scale = src0.scale.data_ptr() + 8
+    if w_unscale is not None:
+        a.w_unscale = w_unscale.down_ptr           # the image in `wpk` was packed times 2^k (WeightScale)
     a.src0, a.C0 = src0.ptr, src0.C
     a.N, a.D, a.H, a.W = src0.N, src0.D, src0.H, src0.W
     if src1 is not None:
@@ -360,11 +405,57 @@ class Unit:
     __slots__ = ('spec', 'src0', 'src1', 'off1', 'y', 'a', 'pooled', 'pool', 'mode', 'G', 'nstate', 'stats', 'dec')
 
 
+class WeightSet:
+    """What one forward (and the backward that follows it) needs besides the raw parameters: the per-tensor power-of-two
+    weight scales and, in eval mode, the folded BatchNorm factors."""
+    __slots__ = ('scales', 'folds')
+
+
 class Net:
     """Flat description of a UNet instance (built by elektronn3_b200.unet.UNet)."""
 
     def __init__(self, down, up, final_conv, dim, cache):
         self.down, self.up, self.final, self.dim, self.cache = down, up, final_conv, dim, cache
+        self.wset = None
+
+    def specs(self):
+        for c1, c2, _ in self.down:
+            yield c1
+            yield c2
+        for ups, c1, c2 in self.up:
+            yield ups
+            yield c1
+            yield c2
+
+
+def prepare_weights(net, training):
+    """-> WeightSet; cached like the packed images (never in training mode)."""
+    specs = list(net.specs())
+    params = []
+    for sp in specs:
+        mod = sp.conv if isinstance(sp, ConvSpec) else sp.up
+        n = sp.norm
+        params += [mod.weight, mod.bias, getattr(n, 'weight', None), getattr(n, 'bias', None),
+                   getattr(n, 'running_mean', None), getattr(n, 'running_var', None)]
+
+    def make():
+        ws = WeightSet()
+        ws.folds = {}
+        weights, cscales = [], []
+        for sp in specs:
+            is_conv = isinstance(sp, ConvSpec)
+            mod = sp.conv if is_conv else sp.up
+            weights.append(mod.weight)
+            if norm_mode(sp.norm, training)[0] == MODE_BATCH_EVAL:
+                f, b = _bn_fold(mod, sp.norm)
+                ws.folds[sp.name] = (f, b)
+                cscales.append((f, 0 if is_conv else 1))
+            else:
+                cscales.append(None)
+        table = weight_scale_table(weights, cscales)
+        ws.scales = {sp.name: WeightScale(table, i) for i, sp in enumerate(specs)}
+        return ws
+    return net.cache.get(('weightset',), params, make, training)
 
 
 def _bn_fold(conv, norm):
@@ -381,27 +472,27 @@ def _bn_fold(conv, norm):
 
 
 def _conv_weights(net, spec, mode, training):
-    """-> (wpk, bias) for forward; BN-eval folding applied when the following norm allows it"""
+    """-> (wpk, bias, WeightScale) for forward; BN-eval folding applied when the following norm allows it"""
     nm, _ = norm_mode(spec.norm, training)
     conv = spec.conv
     pmode = 4 if spec.variants[0] else 0
+    wsc = net.wset.scales[spec.name]
     if nm == MODE_BATCH_EVAL:
         n = spec.norm
         params = (conv.weight, conv.bias, n.weight, n.bias, n.running_mean, n.running_var)
-
-        def make():
-            s, b = _bn_fold(conv, n)
-            return pack_weights(pmode, conv.weight, s, spec.C0, spec.C1, spec.Co, spec.k), b
-        return net.cache.get((spec.name, 'fwd_fold'), params, make, training)
+        s, b = net.wset.folds[spec.name]
+        wpk = net.cache.get((spec.name, 'fwd_fold'), params,
+                            lambda: pack_weights(pmode, conv.weight, s, spec.C0, spec.C1, spec.Co, spec.k, wscale=wsc), training)
+        return wpk, b, wsc
     wpk = net.cache.get((spec.name, 'fwd'), (conv.weight,),
-                        lambda: pack_weights(pmode, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k), training)
-    return wpk, (conv.bias.detach() if conv.bias is not None else None)
+                        lambda: pack_weights(pmode, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k, wscale=wsc), training)
+    return wpk, (conv.bias.detach() if conv.bias is not None else None), wsc
 
 
 def _run_unit(net, spec, src0, src1, off1, pool, training, save):
     """conv -> norm -> relu [-> pool]  (DownConv.forward models/unet.py:244-253, UpConv :402-407)"""
     mode, G = norm_mode(spec.norm, training)
-    wpk, bias = _conv_weights(net, spec, 0, training)
+    wpk, bias, wsc = _conv_weights(net, spec, 0, training)
     u = Unit()
     u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G = spec, src0, src1, off1, pool, mode, G
     u.pooled = u.nstate = u.stats = u.dec = None
@@ -409,20 +500,20 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save):
     if mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save):
         # inference: the conv epilogue (folded BN, bias, ReLU) writes the next layer's operand directly
         a, _, _ = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
-                               relu=True, half_out=True, variant=var)
+                               relu=True, half_out=True, variant=var, w_unscale=wsc)
         u.y = u.a = a
         if pool is not None:
             _, u.pooled = norm_act(a, None, None, write_a=False, pool=pool)
     elif mode == MODE_NONE:
         # training without normalisation: y is kept in float32 for the backward pass (identity affine)
         y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
-                                   variant=var)
+                                   variant=var, w_unscale=wsc)
         u.y = y
         u.a, u.pooled = norm_act(y, None, None, pool=pool, planar=save)
     else:
         n = spec.norm
         y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1,
-                                   bias=bias, stats_channels=spec.Co, variant=var)
+                                   bias=bias, stats_channels=spec.Co, variant=var, w_unscale=wsc)
         S = y.D * y.H * y.W
         rm = rv = None
         mom = 0.0
@@ -470,33 +561,34 @@ def _run_up(net, spec, dec, enc, training, save):
     u.pooled = u.nstate = u.stats = None
     u.dec = dec
     bias = up.bias.detach() if up.bias is not None else None
+    wsc = net.wset.scales[spec.name]
     if mode == MODE_BATCH_EVAL:
         n = spec.norm
         params = (up.weight, up.bias, n.weight, n.bias, n.running_mean, n.running_var)
+        fs, bias = net.wset.folds[spec.name]
 
         def make():
-            s, b = _bn_fold(up, n)
             # the transposed-conv weight is (Ci, Co, ...): scale its output channel axis on the host
             shape = (1, -1) + (1,) * (up.weight.dim() - 2)
-            return pack_weights(2, (up.weight.detach() * s.view(shape)).contiguous(), None, spec.Ci, 0, spec.Co,
-                                spec.s), b
-        wpk, bias = net.cache.get((spec.name, 'up_fold'), params, make, training)
+            return pack_weights(2, (up.weight.detach() * fs.view(shape)).contiguous(), None, spec.Ci, 0, spec.Co,
+                                spec.s, wscale=wsc)
+        wpk = net.cache.get((spec.name, 'up_fold'), params, make, training)
     else:
         wpk = net.cache.get((spec.name, 'up'), (up.weight,),
-                            lambda: pack_weights(2, up.weight, None, spec.Ci, 0, spec.Co, spec.s), training)
+                            lambda: pack_weights(2, up.weight, None, spec.Ci, 0, spec.Co, spec.s, wscale=wsc), training)
     if mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save):
         a, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias, relu=True,
-                               scatter=spec.s, out_spatial=out_sp, half_out=True)
+                               scatter=spec.s, out_spatial=out_sp, half_out=True, w_unscale=wsc)
         u.y = u.a = a
     elif mode == MODE_NONE:
         y, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias,
-                               scatter=spec.s, out_spatial=out_sp)
+                               scatter=spec.s, out_spatial=out_sp, w_unscale=wsc)
         u.y = y
         u.a, _ = norm_act(y, None, None, planar=save)
     else:
         n = spec.norm
         y, _, stats = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias,
-                                   stats_channels=spec.Co, scatter=spec.s, out_spatial=out_sp)
+                                   stats_channels=spec.Co, scatter=spec.s, out_spatial=out_sp, w_unscale=wsc)
         rm = rv = None
         mom = 0.0
         if mode == MODE_BATCH:
@@ -511,7 +603,7 @@ def _run_up(net, spec, dec, enc, training, save):
 
 
 class Tape:
-    __slots__ = ('down', 'up', 'final_in', 'in_shape', 'squeeze')
+    __slots__ = ('down', 'up', 'final_in', 'in_shape', 'squeeze', 'wset')
 
 
 def forward_features(net, x, training, save):
@@ -531,6 +623,7 @@ def forward_features(net, x, training, save):
 def forward_features_qp(net, cur, training, save, squeeze=False, in_shape=None):
     tape = Tape()
     tape.down, tape.up, tape.squeeze, tape.in_shape = [], [], squeeze, in_shape
+    net.wset = tape.wset = prepare_weights(net, training)
     enc = []
     for c1, c2, pool in net.down:
         u1 = _run_unit(net, c1, cur, None, (0, 0, 0), None, training, save)
@@ -549,9 +642,11 @@ def forward_features_qp(net, cur, training, save, squeeze=False, in_shape=None):
     return cur, tape
 
 
-def head(feat, conv_final, out_mode=0, dst=None, crop=None, dst_origin=None, dst_single=False):
+def head(feat, conv_final, out_mode=0, dst=None, crop=None, dst_origin=None, dst_single=False, flip=0, accumulate=False,
+         acc_scale=1.0, threshold=None, round_half=False):
     """conv_final (models/unet.py:881,912) [+ Softmax(1) / Argmax of Predictor, inference.py:443-456] and
-    the Predictor's crop-and-place.  out_mode 0 logits, 1 softmax, 2 argmax(uint8)."""
+    the Predictor's crop-and-place.  out_mode 0 logits, 1 softmax, 2 argmax(uint8).  flip / accumulate / acc_scale:
+    test-time augmentation (un-mirror, mean); threshold: nn.Threshold before Argmax; round_half: float16=True."""
     w, b = conv_final.weight.detach(), conv_final.bias
     Co = w.shape[0]
     a = L.HeadArgs()
@@ -569,6 +664,10 @@ def head(feat, conv_final, out_mode=0, dst=None, crop=None, dst_origin=None, dst
     a.Dd, a.Hd, a.Wd = dst.shape[-3], dst.shape[-2], dst.shape[-1]
     a.dst_origin = _p(dst_origin)
     a.dst_single = 1 if dst_single else 0
+    a.flip, a.accumulate, a.acc_scale = flip, 1 if accumulate else 0, float(acc_scale)
+    if threshold is not None:
+        a.use_threshold, a.threshold = 1, float(threshold)
+    a.round_half = 1 if round_half else 0
     L.check(L.lib().e3b_head(ctypes.byref(a), _stream()), 'head')
     return dst
 
@@ -697,11 +796,13 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
     if not need_dx:
         return None, None
     dvar = spec.variants[1]
+    wsc = net.wset.scales[spec.name]
     wpk = net.cache.get((spec.name, 'dgrad'), (conv.weight,),
-                        lambda: pack_weights(5 if dvar else 1, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k), True)
+                        lambda: pack_weights(5 if dvar else 1, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k, wscale=wsc),
+                        True)
     dpad = tuple(kk - 1 - pp for kk, pp in zip(spec.k, spec.pad))
     d0, d1, _ = conv_forward(dy, wpk, spec.n_total_dgrad, spec.C0, spec.k, dpad,
-                             dst1_C=spec.C1 if u.src1 is not None else 0, variant=dvar)
+                             dst1_C=spec.C1 if u.src1 is not None else 0, variant=dvar, w_unscale=wsc)
     if cropped:
         d1.crop_off = tuple(u.off1)       # gradient of autocrop's slice of the skip tensor (models/unet.py:303-324)
     return d0, d1
@@ -726,6 +827,7 @@ def backward(net, tape, dlogits, need_dx):
 
 def _backward(net, tape, dlogits, need_dx):
     grads = {}
+    net.wset = tape.wset                # the weight scales of the forward this tape belongs to
     dl = dlogits.unsqueeze(2) if tape.squeeze else dlogits
     dl = dl.contiguous()
     feat = tape.final_in
@@ -761,9 +863,10 @@ def _backward(net, tape, dlogits, need_dx):
             dwu = wgrad(dec, dy, dy.C, (1, 1, 1), (0, 0, 0), tuple(up.weight.shape), layout=1, up_taps=ups.taps,
                         up_co=ups.Co)
             _put(grads, up.weight, dwu)
+        wsc = net.wset.scales[ups.name]
         wpk = net.cache.get((ups.name, 'up_dgrad'), (up.weight,),
-                            lambda: pack_weights(3, up.weight, None, ups.Ci, 0, ups.Co, ups.s), True)
-        g, _, _ = conv_forward(dy, wpk, cpad16(ups.Ci), ups.Ci, (1, 1, 1), (0, 0, 0))
+                            lambda: pack_weights(3, up.weight, None, ups.Ci, 0, ups.Co, ups.s, wscale=wsc), True)
+        g, _, _ = conv_forward(dy, wpk, cpad16(ups.Ci), ups.Ci, (1, 1, 1), (0, 0, 0), w_unscale=wsc)
     nd = len(net.down)
     dx = None
     for i in range(nd - 1, -1, -1):

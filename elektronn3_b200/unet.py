@@ -270,6 +270,41 @@ class UNet(nn.Module):
         self.__dict__.pop('_e3b_net', None)      # parameters may be re-created (.to(), .half(), ...)
         return super()._apply(fn, *args, **kwargs)
 
+    def output_spatial(self, in_spatial):
+        """Spatial extents of ``forward``'s result for an input of spatial extents ``in_spatial``: the layer arithmetic
+        of models/unet.py (conv3 :131-149, ceil-mode pooling :225-229, transposed conv :160-165, autocrop :256-325)
+        without running anything.  SAME nets return ``in_spatial``; VALID nets shrink (unet.py:714-753)."""
+        dim = self.dim
+        cur = [1] * (3 - dim) + [int(v) for v in in_spatial]
+        if len(cur) != 3:
+            raise ValueError(f'expected {dim} spatial extents, got {tuple(in_spatial)}')
+        pad = 1 if 'same' in self.conv_mode else 0
+
+        def conv2x(sp, planar):
+            lose = 2 * 2 * (1 - pad)                       # two 3-tap convolutions
+            out = [sp[0] - (0 if (planar or dim == 2) else lose), sp[1] - lose, sp[2] - lose]
+            if min(out) < 1:
+                raise RuntimeError(f'input extents {tuple(in_spatial)} are too small for this network')
+            return out
+        enc = []
+        for i, b in enumerate(self.down_convs):
+            planar = i in self.planar_blocks
+            cur = conv2x(cur, planar)
+            enc.append(list(cur))
+            if b.pooling:
+                k = b.pool_kernel()
+                cur = [-(-c // kk) for c, kk in zip(cur, k)]
+        for i, b in enumerate(self.up_convs):
+            planar = (self.n_blocks - 2 - i) in self.planar_blocks
+            s = (1, 2, 2) if (planar or dim == 2) else (2, 2, 2)
+            e = enc[-(i + 2)]
+            up = [c * ss for c, ss in zip(cur, s)]
+            up = [u - ((u - d) % 2) for u, d in zip(up, e)]
+            if any(u > d for u, d in zip(up, e)):
+                raise RuntimeError('autocrop: the upsampled tensor exceeds the skip tensor')
+            cur = conv2x(up, planar)
+        return tuple(cur[3 - dim:])
+
     def invalidate_weight_cache(self):
         """Drop the packed weight images (eval mode keeps them between calls).  Needed only after writing parameters
         or BatchNorm statistics through ``.data`` / raw pointers while staying in eval mode; ``train()``, ``eval()``,

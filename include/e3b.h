@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define E3B_VERSION 210
+#define E3B_VERSION 220
 
 int e3b_version(void);
 const char* e3b_last_error(void);
@@ -47,9 +47,11 @@ int e3b_pack_ncdhw(const float* src, void* dst_qh, void* dst_planar, int N, int 
 int e3b_unpack_qp(const float* src_qp, float* dst, int N, int C, int D, int H, int W, void* stream);
 
 /* Predictor tile gather (inference.py:179-189): tile b of the batch is the box of a single-sample
- * volume (Cv, Dv, Hv, Wv) whose origin is origins[3*b..3*b+2] (device int32, may overhang -> 0). */
+ * volume (Cv, Dv, Hv, Wv) whose origin is origins[3*b..3*b+2] (device int32, may overhang -> 0).
+ * flip (bit 0: D, bit 1: H, bit 2: W) mirrors the tile in those dims while gathering: the test-time
+ * augmentation FlipAugment.forward (inference.py:215-223) as an index transform instead of a torch.flip copy. */
 int e3b_gather_tiles(const float* vol, const int32_t* origins, void* dst_qh, int B, int C,
-                     int D, int H, int W, int Dv, int Hv, int Wv, void* stream);
+                     int D, int H, int W, int Dv, int Hv, int Wv, int flip, void* stream);
 
 /* ---- weight packing ---------------------------------------------------------------------------
  * torch parameter layouts -> the fp16 K-major no-swizzle shared-memory image the conv kernel streams.
@@ -60,9 +62,12 @@ int e3b_gather_tiles(const float* vol, const int32_t* origins, void* dst_qh, int
  *   mode 4 / 5: the contents of mode 0 / 1 as the image of the z-stacked kernel (e3b_conv_args.variant = 1):
  *           [chunk16][(dy,dx) tap][k half][3 z taps x N][8], 3x3x3 taps and N <= 80 only
  * `scale` (optional, [Co]) multiplies output channel co (eval-mode BatchNorm folding, mode 0 only).
+ * `wscale` (optional, device scalar): a power of two multiplied into every weight before the fp16 rounding, chosen by
+ * the caller so that max|w| lands in [1, 2): tiny (or huge) weights then keep TF32's 10 mantissa bits instead of falling
+ * into fp16's subnormal range; the convolution undoes it through e3b_conv_args.w_unscale.
  * e3b_packed_weight_floats() returns the size of `dst` in units of 4 bytes. */
 int64_t e3b_packed_weight_floats(int mode, int C0, int C1, int Co, int kd, int kh, int kw);
-int e3b_pack_weights(int mode, const float* w, const float* scale, void* dst, int C0, int C1, int Co,
+int e3b_pack_weights(int mode, const float* w, const float* scale, const float* wscale, void* dst, int C0, int C1, int Co,
                      int kd, int kh, int kw, void* stream);
 
 /* ---- convolution ------------------------------------------------------------------------------
@@ -87,6 +92,8 @@ typedef struct e3b_conv_args {
     int32_t half_out;                          /* write dst0 as a QH operand tensor: the output feeds the next MMA */
     const float* out_scale;                    /* optional device scalar multiplied into the accumulators before the
                                                   bias (e3b_norm_bwd_args.dy_scale + 2: undoes the gradient scale) */
+    const float* w_unscale;                    /* optional second device scalar, multiplied likewise: 2^-k of a weight image
+                                                  packed with the power-of-two scale 2^k (e3b_pack_weights wscale) */
     double* stats; int32_t stats_channels;     /* optional [N][stats_channels][2] sum/sumsq of the output (fp64;
                                                   zeroed by this call) for the following Group/BatchNorm */
     int32_t scatter, sd, sh, sw;               /* transposed conv: column = tap*pad16(Cd0)+co -> fine voxel */
@@ -210,8 +217,19 @@ typedef struct e3b_head_args {
     int32_t c0_d, c0_h, c0_w, cn_d, cn_h, cn_w;
     const int32_t* dst_origin;
     int32_t dst_single;                        /* 1: all tiles write into sample 0 of dst */
+    int32_t flip;                              /* bits D/H/W: `a` is the network output on a mirrored tile; voxel v of the box
+                                                  is read at its mirrored position (FlipAugment.backward, inference.py:225-226) */
+    int32_t accumulate; float acc_scale;       /* out_mode 0/1: dst = (accumulate ? dst : 0) + acc_scale * value (acc_scale 0
+                                                  is read as 1): the mean over test-time augmentations (inference.py:507-517) */
+    int32_t use_threshold; float threshold;    /* out_mode 2: probabilities <= threshold are zeroed before the argmax
+                                                  (nn.Threshold(t, 0) + Argmax, inference.py:448-453); implies softmax */
+    int32_t round_half;                        /* out_mode 0/1: values rounded through fp16 (Predictor(float16=True) returns what a
+                                                  .half() model computed, inference.py:402-408,445-446) */
 } e3b_head_args;
 int e3b_head(const e3b_head_args* args, void* stream);
+/* argmax over the channels of a probability volume (N, C, S) float -> uint8 (N, 1, S), with the optional threshold of
+ * e3b_head_args: the deferred argmax after the test-time-augmentation mean (inference.py:519-523). */
+int e3b_prob_argmax(const float* prob, uint8_t* dst, int N, int C, int64_t S, int use_threshold, float threshold, void* stream);
 /* backward: dl NCDHW (N,Co,D,H,W), a QH -> da QP; dw (Co,C), db (Co) via workspace double[Co*(C+1)] (zeroed here) */
 int e3b_head_bwd(const float* dl, const void* a, const float* w, float* da, float* dw, float* db,
                  double* workspace, int N, int C, int Co, int D, int H, int W, void* stream);

@@ -85,3 +85,63 @@ def test_convT_is_gemm_plus_pixel_shuffle():
     y = orc.convT_fwd(x, w, b)
     ref = np.einsum('ncdhw,coijk->nodihjwk', x, w).reshape(1, 5, 4, 6, 8) + b[None, :, None, None, None]
     assert rel_err(y, ref) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The plain-torch restatement (oracle/torch_ref.py: the comparator of the full-size GPU parity tests and the CPU /
+# cuDNN arms of bench.py) pinned against the same reference-generated goldens.
+def _torch_model(case, sd, train):
+    import torch
+    import elektronn3_b200 as e3
+    m = e3.UNet(**case['model'])
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    return m.train(train)
+
+
+@pytest.mark.parametrize('name', list(fx.CASES))
+def test_torch_restatement_matches_reference(name):
+    import torch
+    from oracle import torch_ref
+    case = fx.CASES[name]
+    g, sd = load_golden(name)
+    m = _torch_model(case, sd, case['train'])
+    x = torch.from_numpy(fx.make_input(case['x']))
+    if not case['train']:
+        with torch.no_grad():
+            assert rel_err(torch_ref.unet_forward(m, x).numpy(), g['logits']) < TOL
+        return
+    out = torch_ref.unet_forward(m, x)
+    assert rel_err(out.detach().numpy(), g['logits']) < TOL
+    out.backward(torch.from_numpy(g['dlogits']))
+    gmax = max(np.abs(v[:-3]).max() for k, v in g.items() if k.startswith('grad_digest/'))
+    for k, p in m.named_parameters():
+        if ('grad_digest/' + k) in g:
+            ref = g['grad_digest/' + k]
+            got = fx.digest(p.grad.numpy())
+            assert np.abs(got[:-3] - ref[:-3]).max() / max(np.abs(ref[:-3]).max(), 1e-2 * gmax) < 2e-4, k
+
+
+@pytest.mark.parametrize('name', list(fx.PRED_CASES))
+def test_torch_tiled_restatement_matches_reference(name):
+    import torch
+    from oracle import torch_ref
+    case = fx.PRED_CASES[name]
+    g, sd = load_golden(name)
+    m = _torch_model(case, sd, False)
+    vol = torch.from_numpy(fx.make_input(case['vol'], kind='neuro'))
+    with torch.no_grad():
+        out = torch_ref.tiled_apply(lambda t: torch_ref.unet_forward(m, t).softmax(1), vol, case['tile'], case['overlap'],
+                                    (vol.shape[0], case['out_channels'], *vol.shape[2:]))
+    assert rel_err(out.numpy(), g['softmax']) < TOL
+
+
+def test_torch_dice_restatement_matches_reference_formula():
+    """dice_loss of oracle/torch_ref.py against the closed form of modules/loss.py:165-233 on a case small enough
+    to evaluate by hand: perfect prediction -> loss ~ 0, uniform prediction with 2 balanced classes -> 0.5."""
+    import torch
+    from oracle import torch_ref
+    t = torch.tensor([[[0, 1], [1, 0]]])                        # (N=1, 2, 2)
+    big = torch.zeros(1, 2, 2, 2)
+    big.scatter_(1, t.unsqueeze(1), 50.0)
+    assert float(torch_ref.dice_loss(big, t)) < 1e-4
+    assert abs(float(torch_ref.dice_loss(torch.zeros(1, 2, 2, 2), t)) - 0.5) < 1e-4

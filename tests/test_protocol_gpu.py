@@ -1,0 +1,343 @@
+"""Module / Predictor protocol on the GPU box: what Trainer, SWA, DataParallel and Predictor callers do to the drop-in
+module, the reference's own shape matrix (models/unet.py:938-1016), VALID-mode training through the
+centre-cropped skips (unet.py:256-325), and the Predictor options (inference.py:215-243, 402-408, 445-456, 476-489)."""
+import copy
+import itertools
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def e3():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    import elektronn3_b200
+    return elektronn3_b200
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+def ref32(m, x):
+    from oracle import torch_ref
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        return torch_ref.unet_forward(m, x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def grads_close(m, mref, tol=0.3):
+    gmax = max(p.grad.abs().max().item() for p in mref.parameters())
+    for (k, p), (_, q) in zip(m.named_parameters(), mref.named_parameters()):
+        assert p.grad is not None, k
+        err = (p.grad - q.grad).abs().max().item() / max(q.grad.abs().max().item(), 1e-2 * gmax)
+        assert err < tol, (k, err)
+
+
+# ------------------------------------------------------------------------------------------------ reference shape matrix
+def _shape_cases():
+    cases = []
+    for n in range(1, 5):
+        cases.append((2, n, ()))
+        for k in range(n + 1):
+            for p in itertools.combinations(range(n), k):
+                cases.append((3, n, p))
+    return cases
+
+
+@pytest.mark.parametrize('dim,n_blocks,planar', _shape_cases())
+def test_reference_shape_matrix(e3, dim, n_blocks, planar):
+    """test_2d_config / test_planar_configs of models/unet.py:1001-1016: every n_blocks in 1..4 with every combination of
+    planar blocks on the minimal input (2^n_blocks per axis), forward + backward; here also compared with torch in fp32."""
+    torch.manual_seed(n_blocks * 10 + len(planar))
+    m = e3.UNet(n_blocks=n_blocks, planar_blocks=planar, dim=dim).cuda().train()
+    s = 2 ** n_blocks
+    shape = (2, 1, s, s) if dim == 2 else (2, 1, s // (2 ** len(planar)), s, s)
+    x = torch.randn(shape, device='cuda')
+    out = m(x)
+    assert tuple(out.shape) == (2, 2) + shape[2:]
+    out.sum().backward()
+    mref = copy.deepcopy(m)
+    mref.zero_grad()
+    o32 = ref32(mref, x)
+    o32.sum().backward()
+    assert rel(out.detach(), o32.detach()) < 6e-3
+    grads_close(m, mref, tol=0.35)
+
+
+# ------------------------------------------------------------------------------------------------ VALID-mode training
+@pytest.mark.parametrize('kw,shape', [
+    (dict(n_blocks=2, start_filts=16, normalization='group', conv_mode='valid'), (2, 1, 28, 36, 44)),
+    (dict(n_blocks=3, start_filts=8, normalization='batch', conv_mode='valid'), (1, 1, 52, 52, 60)),
+    (dict(n_blocks=3, start_filts=8, normalization='group', conv_mode='valid', planar_blocks=(0,)), (1, 1, 20, 60, 52)),
+    (dict(dim=2, n_blocks=3, start_filts=8, normalization='group', conv_mode='valid'), (2, 1, 68, 76)),
+])
+def test_valid_mode_training_through_cropped_skips(e3, kw, shape):
+    """backward through autocrop's centre crop of the skip tensors (the slice's gradient is a zero pad) and the weight
+    gradient of a conv whose second source is a cropped view: training with conv_mode='valid' (models/unet.py:714-753)"""
+    torch.manual_seed(3)
+    m = e3.UNet(**kw).cuda().train()
+    x = torch.randn(shape, device='cuda', requires_grad=True)
+    out = m(x)
+    assert tuple(out.shape[2:]) == tuple(m.output_spatial(shape[2:]))
+    g = torch.randn_like(out)
+    out.backward(g)
+    dx = x.grad.clone()
+    mref = copy.deepcopy(m)
+    mref.zero_grad()
+    x2 = x.detach().clone().requires_grad_(True)
+    o32 = ref32(mref, x2)
+    assert o32.shape == out.shape
+    o32.backward(g)
+    assert rel(out.detach(), o32.detach()) < 6e-3
+    grads_close(m, mref)
+    assert rel(dx, x2.grad) < 0.2
+
+
+def test_odd_shapes_train_with_same_convs(e3):
+    """ceil-mode pooling + autocrop of the up path (unet.py:294-301) in training"""
+    torch.manual_seed(4)
+    m = e3.UNet(n_blocks=3, start_filts=8, normalization='group').cuda().train()
+    x = torch.randn(1, 1, 11, 13, 18, device='cuda')
+    out = m(x)
+    out.square().mean().backward()
+    mref = copy.deepcopy(m)
+    mref.zero_grad()
+    o32 = ref32(mref, x)
+    o32.square().mean().backward()
+    assert rel(out.detach(), o32.detach()) < 6e-3
+    grads_close(m, mref)
+
+
+# ------------------------------------------------------------------------------------------------ weight cache
+def test_weight_cache_follows_data_writes_and_running_stats(e3):
+    """in-place writes through .data (training/swa.py:201 swap_swa_sgd, training/padam.py:94) bump no version counter;
+    BatchNorm running statistics are written by the kernels through raw pointers"""
+    torch.manual_seed(5)
+    m = e3.UNet(n_blocks=2, start_filts=8).cuda()
+    x = torch.randn(2, 1, 16, 16, 16, device='cuda')
+    m.train()
+    with torch.no_grad():
+        y0 = m(x)
+        for p in m.parameters():
+            p.data.mul_(1.5)                      # no _version bump
+        y1 = m(x)
+    assert not torch.allclose(y0, y1)
+    assert rel(y1, ref32_nograd(m, x)) < 6e-3
+    # eval images follow (a) the statistics written by the training-mode passes above, (b) .data writes + eval()
+    m.eval()
+    with torch.no_grad():
+        e0 = m(x)
+        assert rel(e0, ref32_nograd(m, x)) < 6e-3
+        m.train()
+        m(x)                                       # moves running_mean / running_var only
+        m.eval()
+        e1 = m(x)
+        assert not torch.allclose(e0, e1) and rel(e1, ref32_nograd(m, x)) < 6e-3
+        for p in m.parameters():
+            p.data.mul_(0.5)
+        m.eval()                                   # what Trainer._validate does after swap_swa_sgd
+        e2 = m(x)
+        assert rel(e2, ref32_nograd(m, x)) < 6e-3
+
+
+def ref32_nograd(m, x):
+    with torch.no_grad():
+        return ref32(copy.deepcopy(m), x)
+
+
+def test_no_grad_forward_keeps_no_training_buffers(e3, monkeypatch):
+    """validation under torch.no_grad() must not pay the training footprint (planar copies, pooling indices, fp32 y)"""
+    from elektronn3_b200 import engine
+    calls = []
+    real = engine.planar_empty
+    monkeypatch.setattr(engine, 'planar_empty', lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    m = e3.UNet(n_blocks=2, start_filts=8, normalization='group').cuda().train()
+    x = torch.randn(1, 1, 16, 16, 16, device='cuda')
+    with torch.no_grad():
+        m(x)
+    assert not calls
+    m(x).sum().backward()
+    assert calls
+
+
+# ------------------------------------------------------------------------------------------------ devices
+def test_data_parallel_forward_backward(e3):
+    """nn.DataParallel replicas (benchmark/train_benchmark.py:109-110, models/base.py:48-49): parameters() is empty on a
+    replica; gradients must reach the wrapped module's parameters"""
+    torch.manual_seed(6)
+    m = e3.UNet(n_blocks=2, start_filts=8, normalization='group').cuda().train()
+    ids = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    dp = torch.nn.DataParallel(m, device_ids=ids)
+    x = torch.randn(4, 1, 16, 16, 16, device='cuda:0')
+    out = dp(x)
+    assert out.shape == (4, 2, 16, 16, 16)
+    out.square().mean().backward()
+    mref = copy.deepcopy(m)
+    mref.zero_grad()
+    o32 = ref32(mref, x)
+    o32.square().mean().backward()
+    assert rel(out.detach(), o32.detach()) < 6e-3
+    grads_close(m, mref)
+
+
+def test_second_device_in_the_same_process(e3):
+    """model.to('cuda:1') without torch.cuda.set_device(1): kernels follow the tensor's device; kernel attributes
+    (dynamic shared memory opt-in) and the SM count are per device"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    torch.manual_seed(7)
+    m0 = e3.UNet(n_blocks=3, start_filts=32, normalization='group').to('cuda:0').train()
+    m1 = copy.deepcopy(m0).to('cuda:1')
+    x = torch.randn(1, 1, 32, 32, 32)
+    o0 = m0(x.to('cuda:0'))
+    o1 = m1(x.to('cuda:1'))                      # current device is still 0
+    assert o1.device == torch.device('cuda:1')
+    assert torch.allclose(o0.cpu(), o1.cpu(), rtol=1e-4, atol=1e-5)
+    o1.sum().backward()
+    assert all(p.grad is not None and p.grad.device == torch.device('cuda:1') for p in m1.parameters())
+    vol = torch.randn(1, 1, 32, 32, 32)
+    p1 = e3.Predictor(m1, device='cuda:1', tile_shape=(16, 16, 16), overlap_shape=(8, 8, 8), offset=(0, 0, 0), out_shape=(2, 32, 32, 32))
+    p0 = e3.Predictor(m0, device='cuda:0', tile_shape=(16, 16, 16), overlap_shape=(8, 8, 8), offset=(0, 0, 0), out_shape=(2, 32, 32, 32))
+    assert torch.allclose(p0.predict(vol), p1.predict(vol), rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ Predictor options
+def _pred_model(e3, **kw):
+    torch.manual_seed(8)
+    m = e3.UNet(**kw).cuda()
+    with torch.no_grad():
+        for k, b in m.named_buffers():
+            if k.endswith('running_var'):
+                b.copy_(0.5 + torch.rand_like(b))
+            elif k.endswith('running_mean'):
+                b.copy_(0.1 * torch.randn_like(b))
+    return m.eval()
+
+
+def _ref_tiled(m, vol, tile, ovl, fn):
+    from oracle import torch_ref
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            return torch_ref.tiled_apply(lambda t: fn(t.cuda()), vol, tile, ovl, (vol.shape[0], 2, *vol.shape[2:]))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_predictor_test_time_augmentation_and_threshold(e3):
+    """augmentations (inference.py:215-243,507-517): mean of the softmax maps over the identity and the flipped passes,
+    argmax deferred until after the mean (:519-523), argmax_with_threshold (:448-453)"""
+    from oracle import torch_ref
+    m = _pred_model(e3, n_blocks=2, start_filts=8)
+    vol = torch.randn(1, 1, 16, 32, 24)
+    tile, ovl = (8, 16, 8), (4, 4, 8)
+    kw = dict(device='cuda', tile_shape=tile, overlap_shape=ovl, offset=(0, 0, 0))
+    augs = [e3.inference.FlipAugment(d) for d in [(0,), (1,), (0, 1), (2,), (0, 1, 2)]]
+
+    def tta(t):
+        outs = [torch_ref.unet_forward(m, t).softmax(1)]
+        for a in augs:
+            outs.append(a.backward(torch_ref.unet_forward(m, a.forward(t)).softmax(1)))
+        return torch.stack(outs).mean(0)
+    ref = _ref_tiled(m, vol, tile, ovl, tta)
+    out = e3.Predictor(m, out_shape=(2, 16, 32, 24), augmentations=augs, **kw).predict(vol)
+    assert rel(out, ref) < 4e-3
+    lab = e3.Predictor(m, out_shape=(1, 16, 32, 24), augmentations=3, apply_argmax=True, **kw).predict(vol)
+    assert lab.dtype == torch.uint8 and lab.shape == (1, 1, 16, 32, 24)
+    # threshold without augmentations: nn.Threshold(t, 0) on the softmax map, then Argmax
+    thr = 0.7
+    ref1 = _ref_tiled(m, vol, tile, ovl, lambda t: torch_ref.unet_forward(m, t).softmax(1))
+    want = torch.where(ref1 > thr, ref1, torch.zeros_like(ref1)).argmax(1)
+    got = e3.Predictor(m, out_shape=(1, 16, 32, 24), argmax_with_threshold=thr, **kw).predict(vol)
+    assert got.dtype == torch.uint8
+    decided = ((ref1 - thr).abs() > 1e-2).all(1) & ((ref1[:, 0] - ref1[:, 1]).abs() > 1e-2)
+    assert torch.equal(got[:, 0].long()[decided], want[decided])
+    assert ((got[:, 0] == 0) | (ref1[:, 1] > thr - 1e-2)).all()      # below the threshold everything collapses to label 0
+    # threshold with augmentations
+    got2 = e3.Predictor(m, out_shape=(1, 16, 32, 24), augmentations=augs, argmax_with_threshold=thr, **kw).predict(vol)
+    want2 = torch.where(ref > thr, ref, torch.zeros_like(ref)).argmax(1)
+    decided2 = ((ref - thr).abs() > 1e-2).all(1) & ((ref[:, 0] - ref[:, 1]).abs() > 1e-2)
+    assert torch.equal(got2[:, 0].long()[decided2], want2[decided2])
+
+
+def test_predictor_float16_and_device_tensors(e3):
+    """float16=True (inference.py:402-408,445-446) returns what a .half() model returns: fp16 values (out_dtype follows
+    the input dtype, :613-614); return_device / CUDA input keep everything in HBM"""
+    from oracle import torch_ref
+    m = _pred_model(e3, n_blocks=2, start_filts=8)
+    vol = torch.randn(1, 1, 16, 16, 32)
+    kw = dict(device='cuda', tile_shape=(8, 8, 16), overlap_shape=(4, 4, 8), offset=(0, 0, 0), out_shape=(2, 16, 16, 32))
+    ref = _ref_tiled(m, vol, (8, 8, 16), (4, 4, 8), lambda t: torch_ref.unet_forward(m, t).softmax(1))
+    h = e3.Predictor(m, float16=True, **kw).predict(vol)
+    assert h.dtype == torch.float16 and rel(h.float(), ref) < 5e-3
+    d = e3.Predictor(m, return_device=True, **kw).predict(vol.cuda())
+    assert d.is_cuda and rel(d.cpu(), ref) < 4e-3
+
+
+def test_predictor_offset_tiling_of_a_valid_network(e3):
+    """offset != 0 (inference.py:476-489, tiled_apply :134-153): a VALID network maps tile + 2 * offset to the tile, the
+    input already carries the halo, nothing is cropped; offset=None derives it like data/utils.py:63-78"""
+    m = _pred_model(e3, n_blocks=2, start_filts=8, conv_mode='valid')       # (BatchNorm eval: position independent)
+    off = tuple((i - o) // 2 for i, o in zip((90, 90, 90), m.output_spatial((90, 90, 90))))
+    assert off == (8, 8, 8)
+    vol = torch.randn(1, 1, 48, 40, 56)
+    with torch.no_grad():
+        whole = ref32(m, vol.cuda()).softmax(1).cpu()             # VALID tiles are exact sub-blocks of the untiled result
+    for offset in (off, None):
+        p = e3.Predictor(m, device='cuda', tile_shape=(16, 8, 8), offset=offset, out_shape=(2, 48, 40, 56))
+        out = p.predict(vol)
+        assert tuple(out.shape) == (1, 2, 32, 24, 40)
+        assert rel(out, whole) < 4e-3
+    with pytest.raises(ValueError):          # an offset that is not the network's: the tile comes back with another shape
+        e3.Predictor(m, device='cuda', tile_shape=(16, 8, 8), offset=(6, 6, 6), out_shape=(2, 48, 40, 56)).predict(vol)
+
+
+def test_predictor_sharded_over_two_ranks(e3, tmp_path):
+    """the tile grid sharded over 2 ranks (one process per GPU, NCCL): slab + halo uploads, one gather, same result"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    script = tmp_path / 'shard.py'
+    script.write_text(f'''
+import os, sys
+sys.path.insert(0, {ROOT!r})
+import torch, torch.distributed as dist
+import elektronn3_b200 as e3
+lr = int(os.environ['LOCAL_RANK']); torch.cuda.set_device(lr)
+dist.init_process_group('nccl', device_id=torch.device('cuda', lr))
+torch.manual_seed(0)
+m = e3.UNet(n_blocks=2, start_filts=8).cuda().eval()
+for t in list(m.parameters()) + list(m.buffers()):
+    dist.broadcast(t.data, 0)
+vol = torch.randn(1, 1, 40, 24, 24)
+kw = dict(device=torch.device('cuda', lr), tile_shape=(8, 8, 8), overlap_shape=(4, 4, 4), offset=(0, 0, 0))
+for argmax in (False, True):
+    oc = 1 if argmax else 2
+    single = e3.Predictor(m, out_shape=(oc, 40, 24, 24), apply_argmax=argmax, distributed=False, **kw).predict(vol)
+    p = e3.Predictor(m, out_shape=(oc, 40, 24, 24), apply_argmax=argmax, **kw)
+    shard = p.predict(vol)
+    if dist.get_rank() == 0:
+        assert shard is not None and torch.equal(shard, single), 'sharded result differs'
+        assert p.last_stats['h2d_bytes'] < vol.numel() * 4, 'rank 0 uploaded the whole volume'
+    else:
+        assert shard is None
+    both = e3.Predictor(m, out_shape=(oc, 40, 24, 24), apply_argmax=argmax, result_on='all', **kw).predict(vol)
+    assert torch.equal(both, single)
+dist.destroy_process_group()
+print('SHARD_OK')
+''')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29571', str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count('SHARD_OK') == 2, r.stdout[-2000:] + r.stderr[-4000:]
