@@ -561,13 +561,17 @@ int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream)
     p.chunks1 = a->src1 ? e3b_cpad16(a->C1) / 16 : 0;
     p.off1_d = a->off1_d; p.off1_h = a->off1_h; p.off1_w = a->off1_w;
     p.a_stage_bytes = (uint32_t)(p.HX * p.HY * p.HZ * 16 * 2);
-    // weight stage: largest tap group (27, 9, 3, 1) that fits 40 KB
-    int tg = ntaps;
-    while (tg > 1 && (size_t)tg * 2 * p.NT * 16 > 40 * 1024) tg /= 3;
-    p.TG = tg;
-    p.b_stage_bytes = (uint32_t)(tg * 2 * p.NT * 16);
+    // weight stage: the largest tap group (27, 9, 3, 1) that still leaves room for two input and two weight stages.
+    // Every stage boundary costs the issuing thread an mbarrier wait (~116 cycles) and a tcgen05.commit (~190 cycles of
+    // pipe time; profiles/r02_umma_issue_queue_commit_wait.txt), so fewer, larger stages win as long as both rings stay
+    // double-buffered.
     if (conv_max_dyn_smem() <= 0) return set_error("conv: cudaFuncGetAttributes failed");
     const size_t budget = (size_t)conv_max_dyn_smem() - 1024 - 256;     // barriers + alignment slack
+    int tg = ntaps;
+    while (tg > 1 && 2 * (size_t)p.a_stage_bytes + 2 * ((size_t)tg * 2 * p.NT * 16) > budget) tg /= 3;
+    if (const char* e = getenv("E3B_CONV_TG")) { const int v = atoi(e); if (v >= 1 && v <= tg && ntaps % v == 0) tg = v; }     // tuning
+    p.TG = tg;
+    p.b_stage_bytes = (uint32_t)(tg * 2 * p.NT * 16);
     int sa = 2, sb = 2;
     // grow depth while it fits (A first up to 4, then B up to 4)
     for (;;) {

@@ -22,14 +22,26 @@
 // Roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..9 epilogue (two warpgroups taking
 // alternate output planes).  The epilogue drains an output plane as soon as its last input plane has been
 // applied (tcgen05.commit -> mbarrier), clears the block with tcgen05.st so that every MMA can accumulate,
-// and hands it back to the issuer.
+// and hands it back.
+//
+// The single issuing thread is the scarce resource (measured, profiles/r02_umma_issue_queue_commit_wait.txt: one
+// tcgen05.mma costs it ~46 cycles, one tcgen05.commit ~190 cycles of pipe time, one mbarrier wait on a complete
+// phase ~116 cycles, and the MMA queue only hides ~4 MMAs), so its per-plane bookkeeping is kept minimal:
+//  * a shared-memory stage holds ZB = 2 consecutive input planes (one TMA box, one full barrier, one release commit);
+//  * the issuer never waits for TMEM blocks: the PRODUCER waits for the blocks a stage's MMAs will newly touch
+//    (blk_free) and only then gives the stage's full barrier its second arrival, so "stage full" implies "blocks free";
+//  * for narrow planes (NTW <= 48) a CTA runs TWO independent chains side by side (CHAINS = 2: two producers, two
+//    issuers, one epilogue warpgroup each, half of the stages and half of the TMEM ring each, ONE shared weight image):
+//    while one issuer is busy with waits / commits / bookkeeping the other one keeps the tensor pipe fed.  Each chain is
+//    the same deterministic sequence of MMAs a single-chain CTA would issue for that part of the run.
 #include "common.cuh"
 #include "kernels.h"
 #include <stdlib.h>
 
 namespace e3b {
 
-static constexpr int kZsThreads = 320;            // TMA warp, MMA warp, two epilogue warpgroups
+static constexpr int kZsThreads1 = 320;           // one chain : TMA warp, MMA warp, two epilogue warpgroups
+static constexpr int kZsThreads2 = 384;           // two chains: 2 TMA warps, 2 MMA warps, one epilogue warpgroup per chain
 static constexpr int kZsTX = 8, kZsTY = 16;
 static constexpr int kZsMaxBlocks = 32;          // TMEM ring blocks (512 / NTW, NTW >= 16)
 static constexpr int kZsMaxStages = 8;
@@ -80,6 +92,7 @@ struct ConvZsParams {
     long long total_L;           // (n, y tile, x tile) chains x Do output planes
     int chunks0, chunks1;        // 16-channel K chunks of source 0 / 1
     int NTW, R, SA;              // columns per output plane, ring blocks, plane-tile stages
+    int ZB;                      // input planes per stage
     uint32_t a0_bytes, a_stage_bytes, w_bytes, w_piece_bytes;
     const float* bias; int n_bias;
     float* dst0; int cq0; float* dst1; int cq0_alloc, cq1_alloc;
@@ -89,7 +102,7 @@ struct ConvZsParams {
     const uint8_t* wpk;
     uint32_t* dbg;               // host-mapped debug words or null
     int prof;                    // accumulate role timings into g_zs_prof
-    int skip;                    // tuning aid (E3B_ZS_SKIP): 1 no global stores, 2 no statistics, 4 no MMAs, 8 no TMEM loads
+    int skip;                    // tuning aid (E3B_ZS_SKIP): 1 no global stores, 2 no statistics, 4 no MMAs
 };
 
 
@@ -162,76 +175,128 @@ E3B_DEVINL void zs_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* dbg, 
 
 E3B_DEVINL void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// TMEM -> registers without waiting: several loads are put in flight, then ONE tcgen05.wait::ld (tmem_ld_wait32)
+E3B_DEVINL void tmem_ld16_raw(uint32_t taddr, uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// wait for the loads, then pin the 32 destination registers behind the wait (the compiler must not consume them earlier)
+E3B_DEVINL void tmem_ld_wait32(uint32_t* r)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+    asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                      "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
+
 // Optional cycle accounting of the pipeline roles (E3B_ZS_PROF, scripts/zs_bench.py): summed over CTAs.
 __device__ unsigned long long g_zs_prof[16];
 #define ZP_T0(var) long long var = 0; if (p.prof) var = clock64()
 #define ZP_ACC(slot, var) if (p.prof) { const long long now_ = clock64(); prof[slot] += (unsigned long long)(now_ - var); var = now_; }
 
-__global__ void __launch_bounds__(kZsThreads, 1)
+template <int CHAINS>
+__global__ void __launch_bounds__(CHAINS == 2 ? kZsThreads2 : kZsThreads1, 1)
 conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, const ConvZsParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // carve: [weights][plane-tile stages][barriers]
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // roles: warps [0, CHAINS) TMA producers, [CHAINS, 2 CHAINS) MMA issuers, then 8 epilogue warps
+    const int role = warp < CHAINS ? 0 : (warp < 2 * CHAINS ? 1 : 2);
+    const int ew = warp - 2 * CHAINS;                                   // epilogue warp 0..7
+    const int chain = role == 0 ? warp : (role == 1 ? warp - CHAINS : (CHAINS == 2 ? ew >> 2 : 0));
+    // carve: [weights][plane-tile stages (SA per chain)][barriers]; p.SA and p.R are PER CHAIN
     uint8_t* w_base = smem;
-    uint8_t* a_base = smem + p.w_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(a_base + (size_t)p.SA * p.a_stage_bytes);
-    uint64_t* a_full = bars;                          // [kZsMaxStages]
-    uint64_t* a_empty = a_full + kZsMaxStages;        // [kZsMaxStages]
-    uint64_t* blk_full = a_empty + kZsMaxStages;      // [kZsMaxBlocks]
-    uint64_t* blk_free = blk_full + kZsMaxBlocks;     // [kZsMaxBlocks]
-    uint64_t* w_full = blk_free + kZsMaxBlocks;       // [1]
+    uint8_t* a_base = smem + p.w_bytes + (size_t)chain * p.SA * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.w_bytes + (size_t)CHAINS * p.SA * p.a_stage_bytes);
+    uint64_t* a_full = bars + chain * (kZsMaxStages / CHAINS);                          // [kZsMaxStages]
+    uint64_t* a_empty = bars + kZsMaxStages + chain * (kZsMaxStages / CHAINS);          // [kZsMaxStages]
+    uint64_t* blk_full = bars + 2 * kZsMaxStages + chain * (kZsMaxBlocks / CHAINS);     // [kZsMaxBlocks]
+    uint64_t* blk_free = bars + 2 * kZsMaxStages + kZsMaxBlocks + chain * (kZsMaxBlocks / CHAINS);   // [kZsMaxBlocks]
+    uint64_t* w_full = bars + 2 * kZsMaxStages + 2 * kZsMaxBlocks;                      // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
     __shared__ __align__(16) float bias_s[kZsMaxN];
 
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
     const int nchunks = p.chunks0 + p.chunks1;
     const int N3 = 3 * p.NTW;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.SA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < p.R; i++) { mbar_init(&blk_full[i], 1); mbar_init(&blk_free[i], 4); }
+        // a_full: the TMA transaction (arrive.expect_tx) + the producer's "output blocks are free" arrival
+        for (int c = 0; c < CHAINS; c++) {
+            for (int i = 0; i < p.SA; i++) {
+                mbar_init(&bars[c * (kZsMaxStages / CHAINS) + i], 2);
+                mbar_init(&bars[kZsMaxStages + c * (kZsMaxStages / CHAINS) + i], 1);
+            }
+            for (int i = 0; i < p.R; i++) {
+                mbar_init(&bars[2 * kZsMaxStages + c * (kZsMaxBlocks / CHAINS) + i], 1);
+                mbar_init(&bars[2 * kZsMaxStages + kZsMaxBlocks + c * (kZsMaxBlocks / CHAINS) + i], 4);
+            }
+        }
         mbar_init(w_full, 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmap0);
         if (p.chunks1) tma_prefetch_desc(&tmap1);
     }
-    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (warp == CHAINS) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot + (uint32_t)chain * (512u / CHAINS);      // this chain's half of the columns
 
-    // this CTA's contiguous run of the linear (chain, output plane) space
-    const long long L0 = p.total_L * blockIdx.x / gridDim.x, L1 = p.total_L * (blockIdx.x + 1) / gridDim.x;
+    // this CTA's contiguous run of the linear (chain, output plane) space, cut into one contiguous part per chain
+    const long long C0 = p.total_L * blockIdx.x / gridDim.x, C1 = p.total_L * (blockIdx.x + 1) / gridDim.x;
+    const long long L0 = C0 + (C1 - C0) * chain / CHAINS, L1 = C0 + (C1 - C0) * (chain + 1) / CHAINS;
 
-    if (warp == 0) {
+    if (role == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(w_full, p.w_bytes);
-            for (uint32_t o = 0; o < p.w_bytes; o += p.w_piece_bytes) bulk_load_1d(w_base + o, p.wpk + o, p.w_piece_bytes, w_full);
+            if (chain == 0) {                        // the weight image is shared by the chains
+                mbar_arrive_expect_tx(w_full, p.w_bytes);
+                for (uint32_t o = 0; o < p.w_bytes; o += p.w_piece_bytes) bulk_load_1d(w_base + o, p.wpk + o, p.w_piece_bytes, w_full);
+            }
             uint32_t sa = 0, pa = 0;
+            uint32_t ws = 0, free_par = 0;           // ring slot of the next output plane to acquire, its barriers' parities
             unsigned long long prof[16] = {0};
             ZP_T0(t_all); ZP_T0(t);
             for (long long L = L0; L < L1;) {
                 const ZsPiece g = zs_piece(p, L, L1);
                 const int zlo = zs_in_lo(p, g), zhi = zs_in_hi(p, g);
-                for (int zp = zlo; zp <= zhi; zp++) {
+                int next_wait = g.za;
+                for (int zp = zlo; zp <= zhi; zp += p.ZB) {
+                    const int zlast = zp + p.ZB - 1 < zhi ? zp + p.ZB - 1 : zhi;       // last input plane of this stage
                     ZP_ACC(15, t);
                     zs_wait(&a_empty[sa], pa ^ 1, p.dbg, 16 * blockIdx.x + 0, 0x100000u | (sa << 8) | (uint32_t)zp);
                     ZP_ACC(1, t);
+                    // (the box always spans ZB planes: a plane beyond the piece is loaded but not used, one beyond the
+                    // volume is zero-filled; either way the transaction is the full stage)
                     mbar_arrive_expect_tx(&a_full[sa], p.a_stage_bytes);
                     uint8_t* st = a_base + (size_t)sa * p.a_stage_bytes;
                     tma_load_5d(st, &tmap0, &a_full[sa], (g.x0 - p.pw) * 4, g.y0 - p.ph, zp, 0, g.n);
                     if (p.chunks1) tma_load_5d(st + p.a0_bytes, &tmap1, &a_full[sa], (g.x0 - p.pw) * 4, g.y0 - p.ph, zp, 0, g.n);
+                    // TMEM blocks of the output planes this stage's MMAs touch for the first time: wait here, on the
+                    // producer's time, so that the issuer never does
+                    int ohi = zlast + p.pd; if (ohi > g.zb - 1) ohi = g.zb - 1;
+                    for (; next_wait <= ohi; next_wait++) {
+                        zs_wait(&blk_free[ws], (free_par >> ws) & 1u, p.dbg, 16 * blockIdx.x + 1, 0x200000u | (ws << 8) | (uint32_t)zp);
+                        free_par ^= 1u << ws;
+                        if (++ws == (uint32_t)p.R) ws = 0;
+                    }
+                    ZP_ACC(3, t);
+                    mbar_arrive(&a_full[sa]);
                     if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
                 }
                 L += g.zb - g.za;
             }
             ZP_ACC(0, t_all);
-            if (p.prof) for (int i = 0; i < 2; i++) atomicAdd(&g_zs_prof[i], prof[i]);
+            if (p.prof) { for (int i = 0; i < 2; i++) atomicAdd(&g_zs_prof[i], prof[i]); atomicAdd(&g_zs_prof[3], prof[3]); }
         }
-    } else if (warp == 1) {
+    } else if (role == 1) {
         // ===================== MMA issuer =====================
         // The whole warp runs the loop with uniform control flow, so that all descriptor arithmetic stays on the
         // uniform datapath (32-bit adds on the low descriptor word: the address field cannot carry); one elected
@@ -239,94 +304,95 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         const bool leader = elect_one();
         const uint32_t idesc1 = umma_idesc_f16(p.NTW, 0, 0), idesc2 = umma_idesc_f16(2 * p.NTW, 0, 0),
                        idesc3 = umma_idesc_f16(3 * p.NTW, 0, 0);
-        const uint32_t plane16 = (uint32_t)(p.HX * p.HY);               // one 8-channel plane of the tile, 16-byte units
-        const uint64_t a_tmpl = umma_desc(0, plane16 * 16u, (uint32_t)(p.HX * 16));
+        const uint32_t plane16 = (uint32_t)(p.HX * p.HY);               // one 8-channel plane of one z plane, 16-byte units
+        const uint32_t ZB = (uint32_t)p.ZB;
+        const uint64_t a_tmpl = umma_desc(0, ZB * plane16 * 16u, (uint32_t)(p.HX * 16));
         const uint64_t b_tmpl = umma_desc(0, (uint32_t)(N3 * 16), 128);
         const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
         const uint32_t a_lo0 = (uint32_t)a_tmpl + (smem_u32(a_base) >> 4), b_lo0 = (uint32_t)b_tmpl + (smem_u32(w_base) >> 4);
         const uint32_t a_stage16 = p.a_stage_bytes >> 4;
         const uint32_t HX = (uint32_t)p.HX, NTW = (uint32_t)p.NTW, R = (uint32_t)p.R;
-        const uint32_t chunk_step_a = 2u * plane16, tap_step_b = (uint32_t)(2 * N3);
+        const uint32_t chunk_step_a = 2u * ZB * plane16, tap_step_b = (uint32_t)(2 * N3);
         zs_wait(w_full, 0, p.dbg, 16 * blockIdx.x + 14, 0x500000u);
         tc_fence_after();
-        uint32_t sa = 0, pa = 0, free_par = 0;
-        uint32_t ws = 0;                         // ring slot of the next output plane to acquire (== slot of the next piece's first plane at piece end)
+        uint32_t sa = 0, pa = 0;
+        uint32_t ws = 0;                         // ring slot of the next output plane to enter the window (== slot of the next piece's first plane at piece end)
         unsigned long long prof[16] = {0};
         ZP_T0(t_all); ZP_T0(t);
         for (long long L = L0; L < L1;) {
             const ZsPiece g = zs_piece(p, L, L1);
             const int zlo = zs_in_lo(p, g), zhi = zs_in_hi(p, g);
-            int next_wait = g.za, next_commit = g.za, olo_prev = g.za;
+            int next_in = g.za, next_commit = g.za, olo_prev = g.za;
             uint32_t cs = ws, s_lo = ws;         // slots of next_commit / of the lowest output plane fed by the current input plane
-            for (int zp = zlo; zp <= zhi; zp++) {
-                // output planes this input plane feeds: z = zp + pd - dz, dz = 0..2, inside the piece
-                int olo = zp + p.pd - 2; if (olo < g.za) olo = g.za;
-                int ohi = zp + p.pd; if (ohi > g.zb - 1) ohi = g.zb - 1;
-                if (olo != olo_prev) { olo_prev = olo; if (++s_lo == R) s_lo = 0; }      // olo advances by at most one per plane
+            for (int zp0 = zlo; zp0 <= zhi; zp0 += p.ZB) {
+                const int zlast = zp0 + p.ZB - 1 < zhi ? zp0 + p.ZB - 1 : zhi;
                 ZP_ACC(15, t);
-                for (; next_wait <= ohi; next_wait++) {
-                    zs_wait(&blk_free[ws], (free_par >> ws) & 1u, p.dbg, 16 * blockIdx.x + 1, 0x200000u | (ws << 8) | (uint32_t)zp);
-                    free_par ^= 1u << ws;
-                    if (++ws == R) ws = 0;
-                }
-                ZP_ACC(3, t);
-                zs_wait(&a_full[sa], pa, p.dbg, 16 * blockIdx.x + 2, 0x300000u | (sa << 8) | (uint32_t)zp);
+                // one wait per stage: the TMA has landed AND (second arrival, by the producer) the TMEM blocks of every
+                // output plane this stage touches are free
+                zs_wait(&a_full[sa], pa, p.dbg, 16 * blockIdx.x + 2, 0x300000u | (sa << 8) | (uint32_t)zp0);
                 ZP_ACC(4, t);
                 tc_fence_after();
-                const int nb = ohi - olo + 1;
-                const uint32_t j_lo = (uint32_t)(olo - (zp + p.pd - 2));
-                int n1 = (int)(R - s_lo); if (n1 > nb) n1 = nb;
-                const int n2 = nb - n1;
-                const uint32_t id1 = n1 == 3 ? idesc3 : (n1 == 2 ? idesc2 : idesc1);
-                const uint32_t id2 = n2 == 2 ? idesc2 : idesc1;
-                const uint32_t acc1 = tmem_base + s_lo * NTW;
-                uint32_t a_lo = a_lo0 + sa * a_stage16;
-                uint32_t b_lo = b_lo0 + j_lo * NTW;
-                const uint32_t b2_off = (uint32_t)n1 * NTW;
-                ZP_ACC(12, t);
-                if (nb > 0 && !(p.skip & 4)) {
-                    if (n2 == 0) {
-                        for (int c = 0; c < nchunks; c++) {
-                            if (leader) {
+                for (int zp = zp0; zp <= zlast; zp++) {
+                    // output planes this input plane feeds: z = zp + pd - dz, dz = 0..2, inside the piece
+                    int olo = zp + p.pd - 2; if (olo < g.za) olo = g.za;
+                    int ohi = zp + p.pd; if (ohi > g.zb - 1) ohi = g.zb - 1;
+                    if (olo != olo_prev) { olo_prev = olo; if (++s_lo == R) s_lo = 0; }      // olo advances by at most one per plane
+                    for (; next_in <= ohi; next_in++) { if (++ws == R) ws = 0; }
+                    const int nb = ohi - olo + 1;
+                    const uint32_t j_lo = (uint32_t)(olo - (zp + p.pd - 2));
+                    int n1 = (int)(R - s_lo); if (n1 > nb) n1 = nb;
+                    const int n2 = nb - n1;
+                    const uint32_t id1 = n1 == 3 ? idesc3 : (n1 == 2 ? idesc2 : idesc1);
+                    const uint32_t id2 = n2 == 2 ? idesc2 : idesc1;
+                    const uint32_t acc1 = tmem_base + s_lo * NTW;
+                    uint32_t a_lo = a_lo0 + sa * a_stage16 + (uint32_t)(zp - zp0) * plane16;
+                    uint32_t b_lo = b_lo0 + j_lo * NTW;
+                    const uint32_t b2_off = (uint32_t)n1 * NTW;
+                    ZP_ACC(12, t);
+                    if (nb > 0 && !(p.skip & 4)) {
+                        if (n2 == 0) {
+                            for (int c = 0; c < nchunks; c++) {
+                                if (leader) {
 #pragma unroll
-                                for (int ty = 0; ty < 3; ty++)
+                                    for (int ty = 0; ty < 3; ty++)
 #pragma unroll
-                                    for (int tx = 0; tx < 3; tx++)
-                                        umma_f16_lohi(acc1, a_lo + (uint32_t)ty * HX + (uint32_t)tx, a_hi,
-                                                      b_lo + (uint32_t)(ty * 3 + tx) * tap_step_b, b_hi, id1);
+                                        for (int tx = 0; tx < 3; tx++)
+                                            umma_f16_lohi(acc1, a_lo + (uint32_t)ty * HX + (uint32_t)tx, a_hi,
+                                                          b_lo + (uint32_t)(ty * 3 + tx) * tap_step_b, b_hi, id1);
+                                }
+                                a_lo += chunk_step_a; b_lo += 9u * tap_step_b;
                             }
-                            a_lo += chunk_step_a; b_lo += 9u * tap_step_b;
-                        }
-                    } else {
-                        // the three blocks wrap around the end of the TMEM ring: two MMAs per tap
-                        for (int c = 0; c < nchunks; c++) {
-                            if (leader) {
+                        } else {
+                            // the three blocks wrap around the end of the TMEM ring: two MMAs per tap
+                            for (int c = 0; c < nchunks; c++) {
+                                if (leader) {
 #pragma unroll
-                                for (int ty = 0; ty < 3; ty++)
+                                    for (int ty = 0; ty < 3; ty++)
 #pragma unroll
-                                    for (int tx = 0; tx < 3; tx++) {
-                                        const uint32_t al = a_lo + (uint32_t)ty * HX + (uint32_t)tx;
-                                        const uint32_t bl = b_lo + (uint32_t)(ty * 3 + tx) * tap_step_b;
-                                        umma_f16_lohi(acc1, al, a_hi, bl, b_hi, id1);
-                                        umma_f16_lohi(tmem_base, al, a_hi, bl + b2_off, b_hi, id2);
-                                    }
+                                        for (int tx = 0; tx < 3; tx++) {
+                                            const uint32_t al = a_lo + (uint32_t)ty * HX + (uint32_t)tx;
+                                            const uint32_t bl = b_lo + (uint32_t)(ty * 3 + tx) * tap_step_b;
+                                            umma_f16_lohi(acc1, al, a_hi, bl, b_hi, id1);
+                                            umma_f16_lohi(tmem_base, al, a_hi, bl + b2_off, b_hi, id2);
+                                        }
+                                }
+                                a_lo += chunk_step_a; b_lo += 9u * tap_step_b;
                             }
-                            a_lo += chunk_step_a; b_lo += 9u * tap_step_b;
                         }
                     }
+                    // (one commit site per barrier kind only: a second, `else if (leader)` copy of a commit was once
+                    // compiled to an unpredicated UTCBAR that the non-elected lanes executed too -> double arrival)
+                    ZP_ACC(13, t);
+                    // output planes whose last contributing input plane (min(z - pd + 2, D - 1)) has now been issued
+                    for (; next_commit < g.zb; next_commit++) {
+                        int last = next_commit - p.pd + 2; if (last > p.D - 1) last = p.D - 1;
+                        if (last > zp) break;
+                        if (leader) umma_commit(&blk_full[cs]);
+                        if (++cs == R) cs = 0;
+                    }
+                    ZP_ACC(14, t);
                 }
-                // (one commit site only: a second, `else if (leader)` copy of this commit was once compiled to an
-                // unpredicated UTCBAR that the non-elected lanes executed too -> double arrival)
-                ZP_ACC(13, t);
-                if (leader) umma_commit(&a_empty[sa]);
-                // output planes whose last contributing input plane (min(z - pd + 2, D - 1)) has now been issued
-                for (; next_commit < g.zb; next_commit++) {
-                    int last = next_commit - p.pd + 2; if (last > p.D - 1) last = p.D - 1;
-                    if (last > zp) break;
-                    if (leader) umma_commit(&blk_full[cs]);
-                    if (++cs == R) cs = 0;
-                }
-                ZP_ACC(14, t);
+                if (leader) umma_commit(&a_empty[sa]);          // the stage (all its planes) goes back to the producer
                 __syncwarp();
                 ZP_ACC(5, t);
                 if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
@@ -334,14 +400,16 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             L += g.zb - g.za;
         }
         ZP_ACC(2, t_all);
-        if (p.prof && leader) { for (int i = 2; i < 6; i++) atomicAdd(&g_zs_prof[i], prof[i]); for (int i = 12; i < 16; i++) atomicAdd(&g_zs_prof[i], prof[i]); }
+        if (p.prof && leader) { atomicAdd(&g_zs_prof[2], prof[2]); atomicAdd(&g_zs_prof[4], prof[4]); atomicAdd(&g_zs_prof[5], prof[5]); for (int i = 12; i < 16; i++) atomicAdd(&g_zs_prof[i], prof[i]); }
     } else {
-        // ===================== epilogue (warps 2..9: two warpgroups that take alternate output planes) =====================
-        const int eg = (warp - 2) >> 2;         // warpgroup: drains the output planes whose running count is eg (mod 2)
+        // ===================== epilogue: two warpgroups =====================
+        // one chain : they take alternate output planes (EG = 2);  two chains: one warpgroup per chain, every plane (EG = 1)
+        constexpr uint32_t EG = CHAINS == 2 ? 1u : 2u;
+        const int eg = CHAINS == 2 ? 0 : (ew >> 2);      // drains the output planes whose running count is eg (mod EG)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;          // GEMM row inside the tile
         const int ry = row >> 3, rx = row & 7;
-        const int etid = threadIdx.x - 64;      // 0..255
+        const int etid = threadIdx.x - 64 * CHAINS;      // 0..255
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         // butterfly transpose-reduce leaves column (bit-reversed low nibble of the lane) in lanes 0..15
         const int bcol = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
@@ -364,7 +432,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 5; i++) { acc_s[i] = 0.0; acc_q[i] = 0.0; }
         int cur_n = -1;
-        uint32_t s = 0, full_par = 0, cnt = 0;  // R is even: a ring slot always meets the same warpgroup
+        uint32_t s = 0, full_par = 0, cnt = 0;  // (EG = 2: R is even, a ring slot always meets the same warpgroup)
         const uint32_t R = (uint32_t)p.R;
         const size_t cstride = (size_t)p.Do * p.Ho * p.Wo;            // 16-byte units between channel planes of the output
         unsigned long long prof[16] = {0};
@@ -382,7 +450,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             const size_t vox = (size_t)y * p.Wo + x;
             const size_t o0 = (size_t)g.n * p.cq0_alloc * cstride + vox, o1 = (size_t)g.n * p.cq1_alloc * cstride + vox;
             for (int z = g.za; z < g.zb; z++, cnt++) {
-                if ((cnt & 1u) != (uint32_t)eg) { if (++s == R) s = 0; continue; }
+                if (EG == 2 && (cnt & 1u) != (uint32_t)eg) { if (++s == R) s = 0; continue; }
                 ZP_ACC(15, t);
                 zs_wait(&blk_full[s], (full_par >> s) & 1u, p.dbg, 16 * blockIdx.x + 3 + q, 0x400000u | (s << 8) | (uint32_t)z);
                 ZP_ACC(7, t);
@@ -391,16 +459,27 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                 const uint32_t blk = lane_base + s * (uint32_t)p.NTW;
                 const size_t zoff = (size_t)z * p.Ho * p.Wo;
 #pragma unroll
-                for (int i = 0; i < 5; i++) {
-                    const int cg = i * 16;
-                    if (cg < p.NTW) {
-                        float v[16];
-                        if (!(p.skip & 8)) tmem_ld16(blk + (uint32_t)cg, v);
-                        else {
+                for (int ip = 0; ip < 3; ip++) {
+                  // 32 columns at a time: both TMEM loads in flight before the one wait
+                  const int cg0 = ip * 32;
+                  if (cg0 < p.NTW) {
+                    const bool two = cg0 + 16 < p.NTW;
+                    uint32_t r[32];
 #pragma unroll
-                            for (int j = 0; j < 16; j++) v[j] = (float)(z + j);
-                        }
-                        tmem_st16_zero(blk + (uint32_t)cg);          // the block is clear again for its next output plane
+                    for (int j = 0; j < 32; j++) r[j] = 0u;
+                    tmem_ld16_raw(blk + (uint32_t)cg0, r);
+                    if (two) tmem_ld16_raw(blk + (uint32_t)cg0 + 16u, r + 16);
+                    tmem_ld_wait32(r);
+                    tmem_st16_zero(blk + (uint32_t)cg0);             // the block is clear again for its next output plane
+                    if (two) tmem_st16_zero(blk + (uint32_t)cg0 + 16u);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                      const int i = ip * 2 + h;
+                      const int cg = i * 16;
+                      if (h == 0 || two) {
+                        float v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[h * 16 + j]);
 #pragma unroll
                         for (int j4 = 0; j4 < 4; j4++) {
                             const float4 b = *reinterpret_cast<const float4*>(&bias_s[cg + j4 * 4]);
@@ -454,7 +533,9 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                             }
                         }
                         ZP_ACC(10, t);
+                      }
                     }
+                  }
                 }
                 tmem_wait_st();
                 tc_fence_before();
@@ -467,12 +548,12 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         }
         if (p.stats && cur_n >= 0) zs_flush_stats(p, cur_n, lane, bcol, reg_stats, rs, rq, acc_s, acc_q);
         ZP_ACC(6, t_all);
-        if (p.prof && warp == 2 && lane == 0) for (int i = 6; i < 12; i++) atomicAdd(&g_zs_prof[i], prof[i]);
+        if (p.prof && (ew & 3) == 0 && lane == 0) for (int i = 6; i < 12; i++) atomicAdd(&g_zs_prof[i], prof[i]);
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == CHAINS) { tc_fence_after(); tmem_dealloc(*tmem_slot, 512); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -483,7 +564,7 @@ static int zs_max_dyn_smem()
     static int v = 0;
     if (!v) {
         cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, conv_zs_kernel) != cudaSuccess) return 0;
+        if (cudaFuncGetAttributes(&fa, conv_zs_kernel<1>) != cudaSuccess) return 0;
         v = 227 * 1024 - (int)fa.sharedSizeBytes;
     }
     return v;
@@ -491,19 +572,50 @@ static int zs_max_dyn_smem()
 
 static const size_t kZsBarrierBytes = (size_t)(2 * kZsMaxStages + 2 * kZsMaxBlocks + 1) * 8 + 16;
 
-// shared-memory plan: resident weight image + SA plane-tile stages.  Returns SA (0: does not fit).
-static int zs_plan(int C0, int C1, int n_total, uint32_t* w_bytes, uint32_t* a_stage_bytes)
+// Shared-memory / TMEM plan: resident weight image + per chain SA stages of ZB input-plane tiles and R ring blocks.
+struct ZsPlan { int chains, zb, sa, r; uint32_t w_bytes, a_stage_bytes; };
+
+static int env_int(const char* name)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
+// ok = false: the weights (plus a minimal ring of stages) do not fit.
+static bool zs_plan(int C0, int C1, int n_total, ZsPlan* out)
 {
     const int chunks = cpad16(C0) / 16 + (C1 > 0 ? cpad16(C1) / 16 : 0);
     const size_t wb = (size_t)chunks * 9 * 2 * (3 * n_total) * 16;
-    const size_t ab = (size_t)(kZsTX + 2) * (kZsTY + 2) * 16 * 2 * chunks;
+    const size_t ab = (size_t)(kZsTX + 2) * (kZsTY + 2) * 16 * 2 * chunks;      // one input plane tile, all channels
     const size_t budget = 227 * 1024 - 2048 - kZsBarrierBytes;       // static smem (bias) and alignment slack: 1 KB each
-    if (wb + 3 * ab > budget) return 0;
-    size_t sa = (budget - wb) / ab;
-    if (sa > kZsMaxStages) sa = kZsMaxStages;
-    if (w_bytes) *w_bytes = (uint32_t)wb;
-    if (a_stage_bytes) *a_stage_bytes = (uint32_t)ab;
-    return (int)sa;
+    if (wb + 2 * ab > budget) return false;
+    const size_t room = budget - wb;
+    static int force_chains = -1, force_zb = -1;                      // tuning / tests: E3B_ZS_CHAINS, E3B_ZS_ZB
+    if (force_chains < 0) { force_chains = env_int("E3B_ZS_CHAINS"); force_zb = env_int("E3B_ZS_ZB"); }
+    ZsPlan pl;
+    pl.w_bytes = (uint32_t)wb;
+    // two chains: narrow planes only (each chain gets half of the 512 TMEM columns), at least two stages per chain
+    for (int chains = 2; chains >= 1; chains--) {
+        if (force_chains && chains != force_chains) continue;
+        if (chains == 2 && n_total > 48) continue;
+        int r = (512 / chains) / n_total;
+        if (r > kZsMaxBlocks / chains) r = kZsMaxBlocks / chains;
+        if (chains == 1) r &= ~1;                                     // the two warpgroups own alternate ring slots
+        for (int zb = 2; zb >= 1; zb--) {
+            if (force_zb && zb != force_zb) continue;
+            if (r < zb + 4) continue;                                 // zb + 2 blocks accumulate, the rest is slack for the epilogue
+            const size_t stage = ab * zb;
+            size_t sa = room / (stage * chains);
+            const size_t cap = zb == 2 ? 4 : (size_t)kZsMaxStages / chains;
+            if (sa > cap) sa = cap;
+            const size_t need = (chains == 1 && zb == 1) ? 3 : 2;      // single-plane stages of a lone chain: at least three
+            if (sa < need) continue;
+            pl.chains = chains; pl.zb = zb; pl.sa = (int)sa; pl.r = r; pl.a_stage_bytes = (uint32_t)stage;
+            if (out) *out = pl;
+            return true;
+        }
+    }
+    return false;
 }
 
 int conv_zs_supported(int C0, int C1, int n_total, int kd, int kh, int kw, int scatter)
@@ -514,7 +626,7 @@ int conv_zs_supported(int C0, int C1, int n_total, int kd, int kh, int kw, int s
     if (scatter || kd != 3 || kh != 3 || kw != 3) return 0;
     if (n_total % 16 || n_total < 16 || n_total > 80) return 0;
     if (C0 <= 0 || C1 < 0) return 0;
-    return zs_plan(C0, C1, n_total, nullptr, nullptr) >= 3 ? 1 : 0;
+    return zs_plan(C0, C1, n_total, nullptr) ? 1 : 0;
 }
 
 int conv_zs_prof_read(unsigned long long* out16, int reset)
@@ -547,17 +659,16 @@ int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream)
     p.pd = a->pd; p.ph = a->ph; p.pw = a->pw;
     p.NTW = a->n_total;
     if (p.NTW % 16 || p.NTW < 16 || p.NTW > 80) return set_error("conv(z-stacked): n_total %d not in 16..80", a->n_total);
-    p.R = 512 / p.NTW; if (p.R > kZsMaxBlocks) p.R = kZsMaxBlocks;
-    p.R &= ~1;                                   // even: the two epilogue warpgroups own alternate ring slots
     p.HX = kZsTX + 2; p.HY = kZsTY + 2;
     p.tiles_x = (p.Wo + kZsTX - 1) / kZsTX; p.tiles_y = (p.Ho + kZsTY - 1) / kZsTY;
     p.total_L = (long long)a->N * p.tiles_x * p.tiles_y * p.Do;
     p.chunks0 = cpad16(a->C0) / 16;
     p.chunks1 = a->src1 ? cpad16(a->C1) / 16 : 0;
-    p.SA = zs_plan(a->C0, a->src1 ? a->C1 : 0, p.NTW, &p.w_bytes, &p.a_stage_bytes);
-    if (p.SA < 3) return set_error("conv(z-stacked): weights do not fit shared memory");
+    ZsPlan pl;
+    if (!zs_plan(a->C0, a->src1 ? a->C1 : 0, p.NTW, &pl)) return set_error("conv(z-stacked): weights do not fit shared memory");
+    p.SA = pl.sa; p.ZB = pl.zb; p.R = pl.r; p.w_bytes = pl.w_bytes; p.a_stage_bytes = pl.a_stage_bytes;
     if (const char* e = getenv("E3B_ZS_SA")) { const int v = atoi(e); if (v >= 2 && v < p.SA) p.SA = v; }           // tuning / tests
-    p.a0_bytes = (uint32_t)(p.HX * p.HY * 16 * 2 * p.chunks0);
+    p.a0_bytes = (uint32_t)(p.HX * p.HY * 16 * 2 * p.chunks0 * p.ZB);
     p.w_piece_bytes = (uint32_t)(2 * 3 * p.NTW * 16);                 // one (chunk, tap) image
     p.bias = a->bias; p.n_bias = a->n_bias;
     p.dst0 = reinterpret_cast<float*>(a->dst0); p.dst1 = a->dst1;
@@ -572,21 +683,22 @@ int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream)
 
     CUtensorMap m0, m1;
     int rc = make_qp_tensor_map(&m0, reinterpret_cast<const float*>(a->src0), a->N, p.chunks0 * 2, a->D, a->H, a->W, a->D, a->H,
-                                a->W, p.HX, p.HY, 1, p.chunks0 * 2);
+                                a->W, p.HX, p.HY, p.ZB, p.chunks0 * 2);
     if (rc) return rc;
     if (a->src1) {
         const float* v1 = reinterpret_cast<const float*>(a->src1) + (((size_t)a->off1_d * a->H1 + a->off1_h) * a->W1 + a->off1_w) * 4;
-        rc = make_qp_tensor_map(&m1, v1, a->N, p.chunks1 * 2, a->D, a->H, a->W, a->D1, a->H1, a->W1, p.HX, p.HY, 1, p.chunks1 * 2);
+        rc = make_qp_tensor_map(&m1, v1, a->N, p.chunks1 * 2, a->D, a->H, a->W, a->D1, a->H1, a->W1, p.HX, p.HY, p.ZB, p.chunks1 * 2);
         if (rc) return rc;
     } else {
         m1 = m0;
     }
-    const size_t smem = (size_t)p.w_bytes + (size_t)p.SA * p.a_stage_bytes + kZsBarrierBytes + 1024;
+    const size_t smem = (size_t)p.w_bytes + (size_t)pl.chains * p.SA * p.a_stage_bytes + kZsBarrierBytes + 1024;
     static bool configured[kMaxDevices] = {false};
     if (!configured[current_device()]) {
         const int max_dyn = zs_max_dyn_smem();
         if (max_dyn <= 0) return set_error("conv(z-stacked): cudaFuncGetAttributes failed");
-        cudaError_t e = cudaFuncSetAttribute(conv_zs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+        cudaError_t e = cudaFuncSetAttribute(conv_zs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_zs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
         if (e != cudaSuccess) return set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured[current_device()] = true;
     }
@@ -607,7 +719,8 @@ int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream)
     }
     long long grid = p.total_L < num_sms() ? p.total_L : num_sms();
     if (const char* e = getenv("E3B_ZS_GRID")) { const int gcap = atoi(e); if (gcap > 0 && gcap < grid) grid = gcap; }   // tests: long runs on small volumes
-    conv_zs_kernel<<<(int)grid, kZsThreads, smem, stream>>>(m0, m1, p);
+    if (pl.chains == 2) conv_zs_kernel<2><<<(int)grid, kZsThreads2, smem, stream>>>(m0, m1, p);
+    else conv_zs_kernel<1><<<(int)grid, kZsThreads1, smem, stream>>>(m0, m1, p);
     return check_launch("conv_zs");
 }
 

@@ -383,7 +383,8 @@ class Predictor:
                 with torch.cuda.stream(cs):
                     for c0 in range(0, z_hi - z_lo, chunk0):
                         c1 = min(c0 + chunk0, z_hi - z_lo)
-                        dslab[n, :, c0:c1].copy_(inp5[n, :, z_lo + c0:z_lo + c1], non_blocking=True)
+                        for ch in range(C):        # (one contiguous block per channel: a strided host copy would be staged)
+                            dslab[n, ch, c0:c1].copy_(inp5[n, ch, z_lo + c0:z_lo + c1], non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(cs)
                         events.append(ev)
@@ -396,7 +397,8 @@ class Predictor:
                         ev.record(cur)
                         cs.wait_event(ev)
                         with torch.cuda.stream(cs):
-                            host[n, :, a:b].copy_(dout[n, :, a:b], non_blocking=True)
+                            for ch in range(oc):    # contiguous blocks: plain asynchronous DMA into the pinned result
+                                host[n, ch, a:b].copy_(dout[n, ch, a:b], non_blocking=True)
                 ntiles += self._predict_rows(dslab[n], z_lo, range(r0, r1), grid12, tile3, ovl3, src_shift, crop0, work_mode,
                                              dout[n], r0, events, chunk0, on_row)
             cur.wait_stream(cs)
