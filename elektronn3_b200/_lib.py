@@ -71,8 +71,6 @@ class NormBwdArgs(ctypes.Structure):
         ('m1', c_void_p), ('m2', c_void_p),
         ('dgamma', c_void_p), ('dbeta', c_void_p), ('dbias', c_void_p),
         ('dy', c_void_p), ('s2d', c_i32), ('sd', c_i32), ('sh', c_i32), ('sw', c_i32),
-        ('dy_planar', c_void_p),
-        ('planar_kw', c_i32), ('planar_pw', c_i32), ('planar_W', c_i32),
         ('relu', c_i32),
         ('g1_crop', c_i32),
         ('g1_od', c_i32), ('g1_oh', c_i32), ('g1_ow', c_i32), ('g1_D', c_i32), ('g1_H', c_i32), ('g1_W', c_i32),
@@ -102,7 +100,7 @@ SIGNATURES = {
     'e3b_version': (c_int, []),
     'e3b_last_error': (ctypes.c_char_p, []),
     'e3b_launch_count': (c_i64, []),
-    'e3b_pack_ncdhw': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
+    'e3b_pack_ncdhw': (c_int, [c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
     'e3b_unpack_qp': (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     'e3b_gather_tiles': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
     'e3b_packed_weight_floats': (c_i64, [c_int] * 7),
@@ -116,7 +114,7 @@ SIGNATURES = {
     'e3b_wgrad': (c_int, [ctypes.POINTER(WgradArgs), c_void_p]),
     'e3b_norm_finalize': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_i64, c_void_p, c_void_p, c_float,
                                   c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    'e3b_norm_act': (c_int, [c_void_p] * 8 + [c_int] * 10 + [c_void_p]),
+    'e3b_norm_act': (c_int, [c_void_p] * 6 + [c_int] * 10 + [c_void_p]),
     'e3b_norm_bwd_reduce': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_finalize': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_apply': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),

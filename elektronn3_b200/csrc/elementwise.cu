@@ -16,21 +16,6 @@ static inline int grid_for(size_t total, int block, int max_waves = 8)
     return (int)b;
 }
 
-// Z-PLANAR (N, D, C, H, Wp) fp16 copy of a quad (Wp = ceil8(W): 16-byte row pitch): the K-major operand
-// layout of the wgrad kernel (a line of 64 x-voxels of one channel = one 128-byte swizzle row).
-__host__ __device__ static inline int wpitch(int W) { return (W + 7) & ~7; }
-E3B_DEVINL void store_planar(__half* __restrict__ pl, const float4& v, int n, int cq, int C, int D, int H, int Wp, int z,
-                             int y, int x)
-{
-    const size_t plane = (size_t)H * Wp;
-    const size_t o = (((size_t)n * D + z) * C + cq * 4) * plane + (size_t)y * Wp + x;
-    const int c = cq * 4;
-    if (c < C) pl[o] = __float2half_rn(v.x);
-    if (c + 1 < C) pl[o + plane] = __float2half_rn(v.y);
-    if (c + 2 < C) pl[o + 2 * plane] = __float2half_rn(v.z);
-    if (c + 3 < C) pl[o + 3 * plane] = __float2half_rn(v.w);
-}
-
 // fp16 operand tensor (QH): (N, Ch, S voxels, 8 halves), Ch = ceil16(C)/8.  The fp32 quad `cq` (channels
 // 4cq..4cq+3) of voxel v is the 8-byte half (cq & 1) of unit ((n*Ch + cq/2)*S + v).
 E3B_DEVINL size_t qh_index(int n, int Ch, int cq, size_t S, size_t v) { return (((size_t)n * Ch + (cq >> 1)) * S + v) * 2 + (cq & 1); }
@@ -42,7 +27,7 @@ E3B_DEVINL void store_qh(uint2* __restrict__ qh, const float4& v, int n, int Ch,
 // NCDHW box -> QH   (network input, Predictor tile gather)
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const float* __restrict__ src, const int32_t* __restrict__ origins, uint2* __restrict__ dst,
-                            __half* __restrict__ dst_pl, int N, int C, int Cq, int D, int H, int W, int Dv, int Hv, int Wv,
+                            int N, int C, int Cq, int D, int H, int W, int Dv, int Hv, int Wv,
                             int z0, int y0, int x0, int single, int flip)
 {
     // Cq = ceil16(C)/4 fp32 quads per voxel: the padding channels of the 16-channel chunks are written as 0
@@ -73,7 +58,6 @@ __global__ void pack_kernel(const float* __restrict__ src, const int32_t* __rest
         }
         const float4 q = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
         store_qh(dst, q, n, Cq >> 1, cq, S, ((size_t)z * H + y) * W + x);
-        if (dst_pl && cq * 4 < C) store_planar(dst_pl, q, n, cq, C, D, H, wpitch(W), z, y, x);
     }
 }
 
@@ -220,46 +204,13 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, int mode,
 // a = relu(y*scale+shift)  [+ pooled = maxpool(a), kernel (pkd,pkh,pkw), ceil mode]
 // one thread per pooling window (or voxel) per 4-channel plane
 // ------------------------------------------------------------------------------------------------
-// The x-shifted gradient copies the wgrad kernel contracts against: (N, D, kw, C, H, Wxp) with
-//   dy3[n][z][dxi][c][y][xs] = dy[n][c][z][y][xs - (dxi - pw)]   (0 outside), xs in [0, Wx), Wx = conv input width.
-// A TMA box cannot start at a voxel offset that is not 16-byte aligned, so the stencil's x shift is
-// materialised here, by the kernel that produces dy anyway (each thread scatters its own value).
-E3B_DEVINL void store_planar_shifted(__half* __restrict__ pl, const float4& v, int n, int cq, int C, int D, int H, int W,
-                                     int z, int y, int x, int kw, int pw, int Wx)
-{
-    const int Wxp = wpitch(Wx);
-    const size_t plane = (size_t)H * Wxp;
-    const int c = cq * 4;
-    const __half hz = __float2half_rn(0.f);
-    const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
-    for (int dxi = 0; dxi < kw; dxi++) {
-        const int sh = dxi - pw;
-        const size_t base = ((((size_t)n * D + z) * kw + dxi) * C + c) * plane + (size_t)y * Wxp;
-        const int xs = x + sh;
-        if (xs >= 0 && xs < Wx) {
-            if (c < C) pl[base + xs] = h0;
-            if (c + 1 < C) pl[base + plane + xs] = h1;
-            if (c + 2 < C) pl[base + 2 * plane + xs] = h2;
-            if (c + 3 < C) pl[base + 3 * plane + xs] = h3;
-        }
-        // columns no dy voxel maps to are zero: [0, sh) by the thread at x == 0, [W + sh, Wx) by x == W-1
-        int z0 = 0, z1 = 0;
-        if (x == 0 && sh > 0) { z0 = 0; z1 = sh < Wx ? sh : Wx; }
-        if (z1 > z0) for (int q = z0; q < z1; q++) for (int k = 0; k < 4; k++) if (c + k < C) pl[base + k * plane + q] = hz;
-        if (x == W - 1) {
-            int r0 = W + sh; if (r0 < 0) r0 = 0;
-            for (int q = r0; q < Wx; q++) for (int k = 0; k < 4; k++) if (c + k < C) pl[base + k * plane + q] = hz;
-        }
-    }
-}
-
 // grid: (planes * chunks-per-plane, Cq, N): one block works inside one (n, 4-channel plane, z) slice, so
 // the per-(n,c) constants are loaded once and only one integer division per thread is needed.
 struct NormActDev {
     const float4* y; const float* scale; const float* shift;
     const uint2* yh;             // y_half: the input is itself a QH operand tensor (eval path: pooling only)
     uint2* a; uint2* pooled;     // QH outputs
-    __half* a_pl; __half* pooled_pl; uchar4* pool_idx;
+    uchar4* pool_idx;
     int C, N, Cq, Ch, D, H, W, pkd, pkh, pkw, relu;
     int Dp, Hp, Wp;
 };
@@ -288,7 +239,7 @@ static constexpr int kVpt = 4;
 __global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
 {
     const int cq = blockIdx.y, n = blockIdx.z;
-    const int HW = p.H * p.W, S = p.D * HW;
+    const int S = p.D * p.H * p.W;
     const int v0 = blockIdx.x * (256 * kVpt) + threadIdx.x;
     const size_t nc = ((size_t)n * p.Cq + cq) * 4;
     float4 sc, sh;
@@ -300,17 +251,12 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
         const int v = v0 + j * 256;
         if (v < S) yv[j] = __ldcs(p.y + base + v);
     }
-    const int Wpl = wpitch(p.W);
 #pragma unroll
     for (int j = 0; j < kVpt; j++) {
         const int v = v0 + j * 256;
         if (v >= S) continue;
         const float4 r = norm_relu_round(yv[j], sc, sh, p.scale != nullptr, p.relu);
         if (p.a) store_qh(p.a, r, n, p.Ch, cq, (size_t)S, (size_t)v);
-        if (p.a_pl) {
-            const int z = v / HW, hw = v - z * HW, yy = hw / p.W, x = hw - yy * p.W;
-            store_planar(p.a_pl, r, n, cq, p.C, p.D, p.H, Wpl, z, yy, x);
-        }
     }
 }
 
@@ -330,7 +276,6 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
     load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
     const size_t base = ((size_t)n * p.Cq + cq) * p.D;
     const size_t S = (size_t)p.D * p.H * p.W;
-    const int Wpl = wpitch(p.W);
     float4 m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
     uchar4 idx = make_uchar4(0, 0, 0, 0);
 #pragma unroll
@@ -350,7 +295,6 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
                 if (p.yh) v = unpack_half4(p.yh[qh_index(n, p.Ch, cq, S, vox)]);
                 else v = norm_relu_round(p.y[base * p.H * p.W + vox], sc, sh, p.scale != nullptr, p.relu);
                 if (p.a) store_qh(p.a, v, n, p.Ch, cq, S, vox);
-                if (p.a_pl) store_planar(p.a_pl, v, n, cq, p.C, p.D, p.H, Wpl, z, yy, x);
                 const unsigned char slot = (unsigned char)((dz * p.pkh + dy) * p.pkw + dx);
                 if (v.x > m.x) { m.x = v.x; idx.x = slot; }
                 if (v.y > m.y) { m.y = v.y; idx.y = slot; }
@@ -362,7 +306,6 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
     const size_t op = ((((size_t)n * p.Cq + cq) * p.Dp + zp) * p.Hp + yp) * p.Wp + xp;
     if (p.pooled) store_qh(p.pooled, m, n, p.Ch, cq, (size_t)p.Dp * p.Hp * p.Wp, ((size_t)zp * p.Hp + yp) * p.Wp + xp);
     if (p.pool_idx) p.pool_idx[op] = idx;
-    if (p.pooled_pl) store_planar(p.pooled_pl, m, n, cq, p.C, p.Dp, p.Hp, wpitch(p.Wp), zp, yp, xp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -382,8 +325,6 @@ struct NormBwdDev {
     float* dy_scale;                         // [0] bound on |dy| (float bits), [1] 2^k, [2] 2^-k
     uint2* dy;                               // QH output, scaled by 2^k
     int Ch;                                  // 16-byte planes of dy
-    __half* dy_pl;                           // planar copies carry the same 2^k scale as dy
-    int pl_kw, pl_pw, pl_Wx;
     int g1_crop, g1_od, g1_oh, g1_ow, g1_D, g1_H, g1_W;   // g1 = gradient of a centre-cropped view (zero outside the box)
 };
 
@@ -708,32 +649,25 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
             if (!p.s2d) {
                 const float4 os = make_float4(o.x * dscale, o.y * dscale, o.z * dscale, o.w * dscale);
                 store_qh(p.dy, os, n, p.Ch, cq, (size_t)p.D * p.H * p.W, ((size_t)z * p.H + yy) * p.W + x);
-                if (p.dy_pl) store_planar_shifted(p.dy_pl, os, n, cq, p.C, p.D, p.H, p.W, z, yy, x, p.pl_kw, p.pl_pw, p.pl_Wx);
             }
         }
         if (p.s2d) {
             // space-to-depth: channel = slot*Cp + c on the coarse grid; fine voxels cropped away by autocrop -> 0
             const int zw = z / p.wd, yw = yy / p.wh, xw = x / p.ww;
             const int slot = ((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww);
-            const int NS = p.wd * p.wh * p.ww;
             const size_t wins = (size_t)p.Dw * p.Hw * p.Ww;
             const size_t iw = ((size_t)zw * p.Hw + yw) * p.Ww + xw;
             const float4 os = make_float4(o.x * dscale, o.y * dscale, o.z * dscale, o.w * dscale);
             store_qh(p.dy, os, n, p.Ch, slot * p.Cq + cq, wins, iw);
-            if (p.dy_pl) store_planar(p.dy_pl, os, n, slot * p.Cq + cq, NS * p.Cq * 4, p.Dw, p.Hw, wpitch(p.Ww), zw, yw, xw);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Vector ("x4") variants for W % 4 == 0: one thread owns 4 consecutive x voxels of one row, so the
-// index arithmetic is paid once per 4 voxels and the planar copies are written with aligned 16-byte
-// stores (the scalar kernels above are instruction-issue bound, not HBM bound: ~27 issue slots per
-// voxel quad are available at full HBM rate).  The +-1 x-shifted gradient copies take their edge
-// value from the neighbouring lane.
+// Vector ("x4") variant for W % 4 == 0: one thread owns 4 consecutive x voxels of one row, so the index arithmetic is
+// paid once per 4 voxels (the scalar kernel above is instruction-issue bound, not HBM bound: ~27 issue slots per voxel
+// quad are available at full HBM rate).
 // ------------------------------------------------------------------------------------------------
-E3B_DEVINL float comp(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
-
 E3B_DEVINL float4 apply_formula(const float4& dr, const float4& xh, const float4& rs, const float4& ga, const float4& m1,
                                 const float4& m2)
 {
@@ -762,19 +696,7 @@ E3B_DEVINL void load_bwd_consts(const NormBwdDev& p, int n, int cq, BwdConsts& c
     }
 }
 
-// dy of a single voxel (slow path of the x4 kernel: the neighbour across a warp boundary)
-E3B_DEVINL float4 single_dy(const NormBwdDev& p, const BwdConsts& c, int n, int cq, int z, int yy, int x)
-{
-    VoxIn in;
-    const size_t ov = ((((size_t)n * p.Cq + cq) * p.D + z) * p.H + yy) * p.W + x;
-    load_vox(p, ov, n, cq, z, yy, x, in);
-    float4 dr, xh;
-    voxel_grad(p, in, c.mu, c.rs, c.sc, c.sh, dr, xh);
-    return apply_formula(dr, xh, c.rs, c.ga, c.m1, c.m2);
-}
-
-// grid: (chunks of 256 x-groups, Cq, N).  KW = 1: one planar copy; KW = 3 (pw = 1, Wx == W): three.
-template <int KW>
+// grid: (chunks of 256 x-groups, Cq, N)
 __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev p)
 {
     const int cq = blockIdx.y, n = blockIdx.z;
@@ -783,66 +705,23 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev
     const int Wg = p.W >> 2;
     const int total = p.D * p.H * Wg;
     const int t = blockIdx.x * 256 + threadIdx.x;
-    const bool active = t < total;
-    const int row = active ? t / Wg : 0;
-    const int xg = active ? t - row * Wg : 0;
-    const int z = row / p.H, yy = row - z * p.H, x0 = xg * 4;
-    const size_t ov = (((size_t)n * p.Cq + cq) * p.D * p.H + row) * (size_t)p.W + x0;
     const float dscale = dy_scale_from_bound(p.dy_scale[0]);
     if (blockIdx.x == 0 && cq == 0 && n == 0 && threadIdx.x == 0) { p.dy_scale[1] = dscale; p.dy_scale[2] = 1.f / dscale; }
-    float4 o[4];
-    if (active) {
-        VoxIn in[4];
+    if (t >= total) return;
+    const int row = t / Wg;
+    const int xg = t - row * Wg;
+    const int z = row / p.H, yy = row - z * p.H, x0 = xg * 4;
+    const size_t ov = (((size_t)n * p.Cq + cq) * p.D * p.H + row) * (size_t)p.W + x0;
+    VoxIn in[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) load_vox(p, ov + j, n, cq, z, yy, x0 + j, in[j]);
+    for (int j = 0; j < 4; j++) load_vox(p, ov + j, n, cq, z, yy, x0 + j, in[j]);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float4 dr, xh;
-            voxel_grad(p, in[j], c.mu, c.rs, c.sc, c.sh, dr, xh);
-            o[j] = apply_formula(dr, xh, c.rs, c.ga, c.m1, c.m2);
-            const float4 os = make_float4(o[j].x * dscale, o[j].y * dscale, o[j].z * dscale, o[j].w * dscale);
-            store_qh(p.dy, os, n, p.Ch, cq, (size_t)p.D * p.H * p.W, (size_t)row * p.W + x0 + j);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (!p.dy_pl) return;                     // (uniform over the grid)
-    float4 left = make_float4(0.f, 0.f, 0.f, 0.f), right = left;
-    if (KW == 3) {
-        const int lane = threadIdx.x & 31;
-        left.x = __shfl_up_sync(0xffffffffu, o[3].x, 1); left.y = __shfl_up_sync(0xffffffffu, o[3].y, 1);
-        left.z = __shfl_up_sync(0xffffffffu, o[3].z, 1); left.w = __shfl_up_sync(0xffffffffu, o[3].w, 1);
-        right.x = __shfl_down_sync(0xffffffffu, o[0].x, 1); right.y = __shfl_down_sync(0xffffffffu, o[0].y, 1);
-        right.z = __shfl_down_sync(0xffffffffu, o[0].z, 1); right.w = __shfl_down_sync(0xffffffffu, o[0].w, 1);
-        if (active) {
-            if (xg == 0) left = make_float4(0.f, 0.f, 0.f, 0.f);
-            else if (lane == 0) left = single_dy(p, c, n, cq, z, yy, x0 - 1);
-            if (xg == Wg - 1) right = make_float4(0.f, 0.f, 0.f, 0.f);
-            else if (lane == 31) right = single_dy(p, c, n, cq, z, yy, x0 + 4);
-        }
-    }
-    if (!active) return;
-    const int Wp = wpitch(p.W);                             // Wx == W; 16-byte row pitch
-    const size_t plane = (size_t)p.H * Wp;
-    const int ch0 = cq * 4;
-    __half* pl0 = p.dy_pl + ((((size_t)n * p.D + z) * KW) * p.C + ch0) * plane + (size_t)yy * Wp + x0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (ch0 + k >= p.C) break;
-        // (the planar copies carry the same power-of-two scale as the QH tensor)
-        const float a0 = comp(o[0], k) * dscale, a1 = comp(o[1], k) * dscale, a2 = comp(o[2], k) * dscale,
-                    a3 = comp(o[3], k) * dscale;
-        __half* q = pl0 + (size_t)k * plane;
-        if (KW == 1) {
-            *reinterpret_cast<uint2*>(q) = pack_half4(a0, a1, a2, a3);
-        } else {
-            const size_t cstride = (size_t)p.C * plane;       // between the dxi copies
-            // dxi = 0: shift -1: out[xs] = dy[xs + 1];  dxi = 1: unshifted;  dxi = 2: shift +1: out[xs] = dy[xs - 1]
-            *reinterpret_cast<uint2*>(q) = pack_half4(a1, a2, a3, comp(right, k) * dscale);
-            *reinterpret_cast<uint2*>(q + cstride) = pack_half4(a0, a1, a2, a3);
-            *reinterpret_cast<uint2*>(q + 2 * cstride) = pack_half4(comp(left, k) * dscale, a0, a1, a2);
-        }
+    for (int j = 0; j < 4; j++) {
+        float4 dr, xh;
+        voxel_grad(p, in[j], c.mu, c.rs, c.sc, c.sh, dr, xh);
+        const float4 o = apply_formula(dr, xh, c.rs, c.ga, c.m1, c.m2);
+        const float4 os = make_float4(o.x * dscale, o.y * dscale, o.z * dscale, o.w * dscale);
+        store_qh(p.dy, os, n, p.Ch, cq, (size_t)p.D * p.H * p.W, (size_t)row * p.W + x0 + j);
     }
 }
 
@@ -1048,14 +927,14 @@ using namespace e3b;
 
 extern "C" {
 
-int e3b_pack_ncdhw(const float* src, void* dst_qp, void* dst_planar, int N, int C, int D, int H, int W, int Dv, int Hv,
+int e3b_pack_ncdhw(const float* src, void* dst_qp, int N, int C, int D, int H, int W, int Dv, int Hv,
                    int Wv, int z0, int y0, int x0, void* stream)
 {
     if (N <= 0 || C <= 0) return set_error("pack: empty tensor");
     const int Cq = cpad16(C) / 4;
     const size_t total = (size_t)N * Cq * D * H * W;
     pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, nullptr, reinterpret_cast<uint2*>(dst_qp),
-                                                                        reinterpret_cast<__half*>(dst_planar), N, C, Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0, 0);
+                                                                        N, C, Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0, 0);
     return check_launch("pack_ncdhw");
 }
 
@@ -1065,7 +944,7 @@ int e3b_gather_tiles(const float* vol, const int32_t* origins, void* dst_qp, int
     if (B <= 0 || C <= 0) return set_error("gather: empty batch");
     const int Cq = cpad16(C) / 4;
     const size_t total = (size_t)B * Cq * D * H * W;
-    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vol, origins, reinterpret_cast<uint2*>(dst_qp), nullptr,
+    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vol, origins, reinterpret_cast<uint2*>(dst_qp),
                                                                         B, C, Cq, D, H, W, Dv, Hv, Wv, 0, 0, 0, 1, flip);
     return check_launch("gather_tiles");
 }
@@ -1116,11 +995,10 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
     return check_launch("norm_finalize");
 }
 
-int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled, void* a_planar,
-                 void* pooled_planar, uint8_t* pool_idx, int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w,
-                 int relu, int y_is_half, void* stream)
+int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled, uint8_t* pool_idx, int N, int C,
+                 int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, int y_is_half, void* stream)
 {
-    const bool pooling = pooled || pooled_planar || pool_idx;
+    const bool pooling = pooled || pool_idx;
     if (y_is_half && (!pooling || scale || a)) return set_error("norm_act: an fp16 input is only pooled (eval path)");
     if (!pooling) { pk_d = pk_h = pk_w = 1; }
     if (pk_d < 1 || pk_h < 1 || pk_w < 1 || pk_d > 2 || pk_h > 2 || pk_w > 2) return set_error("norm_act: pooling kernel must be 1 or 2 per dim");
@@ -1129,7 +1007,7 @@ int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a,
     p.y = y_is_half ? nullptr : reinterpret_cast<const float4*>(y); p.scale = scale; p.shift = shift;
     p.yh = y_is_half ? reinterpret_cast<const uint2*>(y) : nullptr;
     p.a = reinterpret_cast<uint2*>(a); p.pooled = reinterpret_cast<uint2*>(pooled);
-    p.a_pl = reinterpret_cast<__half*>(a_planar); p.pooled_pl = reinterpret_cast<__half*>(pooled_planar); p.pool_idx = reinterpret_cast<uchar4*>(pool_idx);
+    p.pool_idx = reinterpret_cast<uchar4*>(pool_idx);
     p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu;
     p.Dp = (D + pk_d - 1) / pk_d; p.Hp = (H + pk_h - 1) / pk_h; p.Wp = (W + pk_w - 1) / pk_w;
     if (p.Cq > 65535 || N > 65535) return set_error("norm_act: too many channels / samples for the launch grid");
@@ -1165,10 +1043,9 @@ static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)
     p.relu = a->relu; p.s2d = a->s2d;
     p.gamma = (a->mode == 0) ? nullptr : a->gamma;
     p.mean = a->mean; p.rstd = a->rstd; p.m1 = a->m1; p.m2 = a->m2;
-    p.sums = a->sums; p.dy = reinterpret_cast<uint2*>(a->dy); p.dy_pl = reinterpret_cast<__half*>(a->dy_planar);
+    p.sums = a->sums; p.dy = reinterpret_cast<uint2*>(a->dy);
     p.amax = a->amax; p.dy_scale = a->dy_scale;
     p.Ch = a->s2d ? cpad16(p.wd * p.wh * p.ww * p.Cq * 4) / 8 : cpad16(a->C) / 8;
-    p.pl_kw = a->planar_kw > 0 ? a->planar_kw : 1; p.pl_pw = a->planar_pw; p.pl_Wx = a->planar_W > 0 ? a->planar_W : a->W;
     p.g1_crop = a->g1_crop; p.g1_od = a->g1_od; p.g1_oh = a->g1_oh; p.g1_ow = a->g1_ow;
     p.g1_D = a->g1_D; p.g1_H = a->g1_H; p.g1_W = a->g1_W;
     if (a->g1_crop && (!a->g1 || a->g1_od < 0 || a->g1_oh < 0 || a->g1_ow < 0 || a->g1_od + a->g1_D > a->D ||
@@ -1226,14 +1103,11 @@ int e3b_norm_bwd_apply(const e3b_norm_bwd_args* a, void* stream)
 {
     NormBwdDev p;
     if (fill_bwd(a, p)) return 1;
-    // vector path: rows of 4-voxel groups, SAME-padded stencil (the gradient is as wide as the conv input)
-    const bool x4 = !p.s2d && (p.W % 4 == 0) && (!p.dy_pl || (p.pl_Wx == p.W && ((p.pl_kw == 1 && p.pl_pw == 0) ||
-                                                                               (p.pl_kw == 3 && p.pl_pw == 1))));
-    if (x4) {
+    // vector path: rows of 4-voxel groups
+    if (!p.s2d && (p.W % 4 == 0)) {
         const size_t groups = (size_t)p.D * p.H * (p.W / 4);
         const dim3 grid((unsigned)((groups + 255) / 256), p.Cq, a->N);
-        if (p.dy_pl && p.pl_kw == 3) norm_bwd_apply_x4_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-        else norm_bwd_apply_x4_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        norm_bwd_apply_x4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
         return check_launch("norm_bwd_apply_x4");
     }
     const size_t Sg = (size_t)p.Dg * p.Hg * p.Wg;

@@ -5,27 +5,23 @@
 // (the backward-filter of nn.Conv3d at elektronn3 models/unet.py:131-149; with one tap on
 // (x, space-to-depth(dy)) also nn.ConvTranspose3d's, unet.py:152-165).
 //
-// GEMM view: M = input channels, N = output channels, K = voxels.  Both operands are read K-major from
-// Z-PLANAR fp16 copies of the tensors (N, D, C, H, Wp), Wp = ceil8(W) (kind::f16, fp32 accumulate; fp16
-// carries TF32's 10 mantissa bits, the gradient copies carry the power-of-two scale of e3b_norm_bwd_*, undone
-// in the split-K reduction): a TMA box of 64 consecutive x-voxels x CB channels x rows lands in shared
-// memory as the canonical 128-byte-swizzled K-major tile (one 128 B line = 64 voxels of one channel;
-// 8 channels = one 1024 B swizzle atom).
-//  * the (kw) x-shifts of the stencil cannot be TMA coordinates (a box must start 16-byte aligned: a
-//    1-voxel shift of a 2-byte element is an illegal instruction) nor descriptor offsets, so the kernel
-//    that produces dy also writes it as kw x-shifted copies (N, D, kw, Co, H, Wp); the copies are stacked
-//    in the MMA's N dimension: one MMA of N = kw*NTW columns serves all x taps;
-//  * the (kh) y-shifts are STACKED IN M: a stage holds the rows [y][c][32 vox] contiguously, so an
-//    M = 128 operand starting at row r covers rows r .. r+RS-1 (RS = 128 / CB, CB = 8/16/32 channels per
-//    unit): accumulator rows [j*CB, (j+1)*CB) are tap dy = j.  With CB = 32 one MMA serves all three dy
-//    taps (75 % of the M rows useful instead of 25 %);
-//  * the (kd) z-shifts pair the x plane z with the dy planes z+pd-kd+1 .. z+pd: either all inside one CTA
-//    (narrow N) or split over CTAs.  A CTA walks a contiguous run of x planes of one (n, y tile, x tile)
-//    column, so the dy planes live in their own shared-memory ring and every plane is staged ONCE for
-//    the kd x-planes that use it (a sliding window along z) instead of once per x plane;
-//  * every (kd, dx) tap pair owns a TMEM accumulator (columns <= 512); the contraction over voxels is
-//    split over CTAs (split-K), partials go to a workspace and a deterministic second kernel reduces
-//    them into the torch weight layout.
+// GEMM view: M = input channels, N = output channels, K = voxels.  Both operands are read STRAIGHT from the QH operand
+// tensors the forward / dgrad kernels use (fp16, 8 channels per 16-byte voxel unit) as MN-major no-swizzle UMMA operands:
+// 8 consecutive x-voxels of an 8-channel plane are one canonical core matrix (8 K-rows of 16 bytes), so one kind::f16
+// MMA (K = 16) contracts 16 consecutive x-voxels, and -- because a voxel is a 16-byte unit -- every stencil shift is a
+// legal descriptor start address.  No K-major ("planar") copies of the activations or of the gradients exist any more:
+// round 1 wrote one planar copy of every activation and three x-shifted copies of every gradient (a TMA box of a
+// 2-byte type cannot start at an odd element, profiles/r02_tma_odd_coordinate.txt), 268 MB of extra HBM traffic per
+// full-resolution 32-channel layer.
+//  * x taps (kw): the x tile carries a halo, tap dx is a +16 B start address; one TMEM accumulator per dx;
+//  * y taps (kh) are STACKED IN M: the x tile lies in shared memory as [row][8-channel plane][x], so the 16 M groups of
+//    one MMA are (row j, plane): accumulator rows [j*CB, (j+1)*CB) are tap dy = j of the gradient row they meet
+//    (CB = 32 channels: 3 of the 4 stacked rows are useful);
+//  * z taps (kd) are STACKED IN N: the gradient tile holds the kd planes z+pd-kd+1 .. z+pd as [row][plane z][channel
+//    plane][x] (one TMA box; planes outside the volume are zero-filled = the convolution's zero padding), so the N groups
+//    of one MMA are (z plane, channel plane): N = kd * NTW columns, accumulator column block zs is tap dz = kd-1-zs.
+// One MMA of M = 128, N = 96, K = 16 therefore serves 9 taps of a 32 -> 32 layer; the contraction over voxels is split
+// over CTAs (split-K), partials go to a workspace and a deterministic second kernel reduces them into the torch layout.
 #include "common.cuh"
 #include "kernels.h"
 #include <stdlib.h>
@@ -33,72 +29,69 @@
 namespace e3b {
 
 static constexpr int kWgThreads = 192;
-static constexpr int kSeg = 64;              // voxels per 128-byte line
 
 struct WgradParams {
     int N, D, H, W;              // x extents (source 0 / the cropped view of source 1)
-    int D1;                      // planes per sample in the allocation of source 1
     int Do, Ho, Wo;              // dy extents
     int kd, kh, kw, pd, ph, pw;
-    int off1_d, off1_h, off1_w;
-    int CB, RS;                  // channels per M unit, rows stacked in M
-    int TY, TYA, rows_alloc;     // dy rows per stage, x rows loaded, x rows addressed by the MMAs
+    int CB, RS, PA, PB;          // channels per M block, rows stacked in M, 8-channel planes per x tile / per dy z-slot
+    int TY, TX, HXa, rows_a;     // dy rows and x-voxels per step, x tile width (TX + kw - 1) and rows (TY + RS - 1)
     int tiles_x, tiles_y;
     int mchunks0, mchunks;       // CB-channel chunks in source 0 / total
-    int NTW, nchunks_n;          // N columns per CTA, number of N chunks
-    int kdn, kd_units;           // kd taps per CTA, CTAs along kd
-    int units, S, SA, SB;        // CTAs = units * S; depth of the x-tile ring and of the dy-plane ring
+    int NTW, nchunks_n;          // N columns per z-slot and CTA, number of N chunks
+    int units, S, SA;            // CTAs = units * S; stage ring depth
     int total_L;                 // linear work items: (column = (n, y tile, x tile)) x (x plane z)
-    uint32_t a_load_bytes, a_bytes, b_plane_bytes;
+    uint32_t a_bytes, b_bytes, stage_bytes, tx_bytes;   // a_bytes: padded offset of the dy tile; tx_bytes: what the two TMA boxes move
     int ktot, npad_total;        // partial-sum row / column space
     float* part;                 // [S][ntaps][ktot][npad_total]
 };
 
-struct WgUnit { int ku, mc, nc; };
+struct WgUnit { int mc, nc; };
 
 E3B_DEVINL WgUnit decode_unit(const WgradParams& p, int u) {
     WgUnit r;
-    r.nc = u % p.nchunks_n; u /= p.nchunks_n;
-    r.mc = u % p.mchunks; u /= p.mchunks;
-    r.ku = u;
+    r.nc = u % p.nchunks_n;
+    r.mc = u / p.nchunks_n;
     return r;
 }
 
-// column index -> sample and tile origin
-E3B_DEVINL void decode_col(const WgradParams& p, int col, int& n, int& y0, int& x0) {
-    int xt = col % p.tiles_x; col /= p.tiles_x;
-    int yt = col % p.tiles_y;
+// linear work item -> sample, tile origin, x plane
+E3B_DEVINL void decode_item(const WgradParams& p, int L, int& n, int& y0, int& x0, int& zi) {
+    int col = L / p.D;
+    zi = L - col * p.D;
+    const int xt = col % p.tiles_x; col /= p.tiles_x;
+    const int yt = col % p.tiles_y;
     n = col / p.tiles_y;
-    x0 = xt * kSeg; y0 = yt * p.TY;
+    x0 = xt * p.TX; y0 = yt * p.TY;
 }
 
-// The run of work of one CTA, cut into per-column segments.  Producer and MMA issuer walk it in lock step.
-struct WgSeg {
-    int col, za, zb;             // x planes [za, zb) of column col
-    int blo, bhi;                // dy planes [blo, bhi] staged for this segment (may be empty: blo > bhi)
-};
-// dy planes used by x plane zi: [lo, hi]  (all kdn taps of this CTA)
-E3B_DEVINL int wg_lo(const WgradParams& p, int ku, int zi) { return zi + p.pd - (ku * p.kdn + p.kdn - 1); }
-E3B_DEVINL int wg_hi(const WgradParams& p, int ku, int zi) { return zi + p.pd - ku * p.kdn; }
-E3B_DEVINL WgSeg wg_segment(const WgradParams& p, int ku, int L, int L1) {
-    WgSeg g;
-    g.col = L / p.D; g.za = L - g.col * p.D;
-    const int left = L1 - L;
-    g.zb = g.za + left < p.D ? g.za + left : p.D;
-    g.blo = wg_lo(p, ku, g.za); if (g.blo < 0) g.blo = 0;
-    g.bhi = wg_hi(p, ku, g.zb - 1); if (g.bhi > p.Do - 1) g.bhi = p.Do - 1;
-    return g;
+// kind::f16 MMA with the descriptors given as (low, high) words (32-bit uniform adds advance the low words)
+E3B_DEVINL void umma_f16_lohi_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                  uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 
-// K-major, 128-byte swizzle: 8-row groups 1024 B apart; the K advance inside a line is added to the start
-// address (tiles are 1024 B aligned, so the swizzle phase bits [7,10) are untouched by offsets < 128 B).
-E3B_DEVINL uint64_t umma_desc_sw128(uint32_t saddr) {
-    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;                       // LBO (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;             // SBO
-    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-    return d;
+// the MMAs of one dy row: KW x taps (one accumulator each) x KS 16-voxel K steps, fully unrolled so that the UTCHMMAs issue
+// back to back (a loop with run-time bounds costs the single issuing thread more than an MMA takes to execute)
+template <int KW, int KS>
+E3B_DEVINL void wg_issue_row(uint32_t tmem_base, uint32_t acc_cols, uint32_t a_row, uint32_t a_hi, uint32_t b_row, uint32_t b_hi,
+                             uint32_t idesc, uint32_t acc_flag)
+{
+#pragma unroll
+    for (int dx = 0; dx < KW; dx++) {
+#pragma unroll
+        for (int k = 0; k < KS; k++)
+            umma_f16_lohi_acc(tmem_base + (uint32_t)dx * acc_cols, a_row + (uint32_t)(dx + 16 * k), a_hi, b_row + (uint32_t)(16 * k), b_hi,
+                              idesc, k == 0 ? acc_flag : 1u);
+    }
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -106,18 +99,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmdy, const WgradParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024-byte alignment is required by the 128 B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* a_ring = smem;
-    uint8_t* b_ring = smem + (size_t)p.SA * p.a_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.SB * p.b_plane_bytes);
-    uint64_t* a_full = bars;
-    uint64_t* a_empty = a_full + p.SA;
-    uint64_t* b_full = a_empty + p.SA;
-    uint64_t* b_empty = b_full + p.SB;
-    uint64_t* done = b_empty + p.SB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.SA * p.stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = full + p.SA;
+    uint64_t* done = empty + p.SA;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-    volatile uint32_t* started_slot = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int unit = blockIdx.x / p.S, split = blockIdx.x % p.S;
@@ -128,9 +115,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
     const int L0 = (int)(((long long)p.total_L * split) / p.S), L1 = (int)(((long long)p.total_L * (split + 1)) / p.S);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.SA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < p.SB; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        mbar_init(done, 2);                      // tcgen05.commit + the issuer's own (releasing) arrive
+        for (int i = 0; i < p.SA; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
         fence_barrier_init();
         tma_prefetch_desc(src1 ? &tmx1 : &tmx0);
         tma_prefetch_desc(&tmdy);
@@ -142,118 +128,81 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        // ===================== TMA producer: one x tile + one dy tile (kd planes) per stage =====================
         if (lane == 0) {
-            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+            uint32_t s = 0, par = 0;
             const CUtensorMap* mx = src1 ? &tmx1 : &tmx0;
-            const int ox = src1 ? p.off1_w : 0, oy = src1 ? p.off1_h : 0, oz = src1 ? p.off1_d : 0;
-            const int Dsrc = src1 ? p.D1 : p.D;      // planes per sample in the source's allocation
-            for (int L = L0; L < L1;) {
-                const WgSeg g = wg_segment(p, u.ku, L, L1);
-                int n, y0, x0;
-                decode_col(p, g.col, n, y0, x0);
-                int bnext = g.blo;
-                for (int zi = g.za; zi < g.zb; zi++) {
-                    int need = wg_hi(p, u.ku, zi); if (need > g.bhi) need = g.bhi;
-                    for (; bnext <= need; bnext++) {
-                        // dy: dims (x, co, dxi, y, n*Do + z)
-                        mbar_wait(&b_empty[sb], pb ^ 1);
-                        mbar_arrive_expect_tx(&b_full[sb], p.b_plane_bytes);
-                        tma_load_5d(b_ring + (size_t)sb * p.b_plane_bytes, &tmdy, &b_full[sb], x0, u.nc * p.NTW, 0, y0,
-                                    n * p.Do + bnext);
-                        if (++sb == (uint32_t)p.SB) { sb = 0; pb ^= 1; }
-                    }
-                    // x: dims (x, c, y, n*D + z)
-                    mbar_wait(&a_empty[sa], pa ^ 1);
-                    mbar_arrive_expect_tx(&a_full[sa], p.a_load_bytes);
-                    tma_load_4d(a_ring + (size_t)sa * p.a_bytes, mx, &a_full[sa], x0 + ox, mc_local * p.CB, y0 - p.ph + oy,
-                                n * Dsrc + zi + oz);
-                    if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
-                }
-                L += g.zb - g.za;
+            for (int L = L0; L < L1; L++) {
+                int n, y0, x0, zi;
+                decode_item(p, L, n, y0, x0, zi);
+                mbar_wait(&empty[s], par ^ 1);
+                mbar_arrive_expect_tx(&full[s], p.tx_bytes);
+                uint8_t* st = smem + (size_t)s * p.stage_bytes;
+                // x : dims (x*4, channel plane, y, z, n)       box (HXa*4, PA, rows_a, 1, 1)
+                tma_load_5d(st, mx, &full[s], (x0 - p.pw) * 4, mc_local * p.PA, y0 - p.ph, zi, n);
+                // dy: dims (x*4, channel plane, z, y, n)       box (TX*4, PB, kd, TY, 1)
+                tma_load_5d(st + p.a_bytes, &tmdy, &full[s], x0 * 4, u.nc * p.PB, zi + p.pd - (p.kd - 1), y0, n);
+                if (++s == (uint32_t)p.SA) { s = 0; par ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // whole warp runs the loop (uniform control flow); one elected lane issues
-        const uint32_t idesc = umma_idesc_f16(p.kw * p.NTW, 0, 0);
+        // ===================== MMA issuer (whole warp, uniform control flow; one elected lane issues) =====================
+        const uint32_t idesc = umma_idesc_f16(p.kd * p.NTW, 1, 1);        // both operands MN-major
         const bool leader = elect_one();
-        uint32_t sa = 0, pa = 0;
-        uint32_t wb = 0, wpb = 0;                    // next dy-plane slot to wait for
-        uint32_t rb = 0;                             // next dy-plane slot to release
-        uint32_t started = 0;                        // bit kj: accumulator kj has been written once
-        const uint32_t a_row16 = (uint32_t)p.CB * 8u, b_row16 = (uint32_t)(p.kw * p.NTW) * 8u;   // 16-byte units
-        const uint64_t tmpl = umma_desc_sw128(0);
-        const uint32_t a16 = smem_u32(a_ring) >> 4, b16 = smem_u32(b_ring) >> 4;
-        for (int L = L0; L < L1;) {
-            const WgSeg g = wg_segment(p, u.ku, L, L1);
-            const uint32_t slot0 = wb;               // ring slot of dy plane g.blo
-            int bwaited = g.blo, brel = g.blo;
-            for (int zi = g.za; zi < g.zb; zi++) {
-                int need = wg_hi(p, u.ku, zi); if (need > g.bhi) need = g.bhi;
-                for (; bwaited <= need; bwaited++) {
-                    mbar_wait(&b_full[wb], wpb);
-                    if (++wb == (uint32_t)p.SB) { wb = 0; wpb ^= 1; }
-                }
-                mbar_wait(&a_full[sa], pa);
-                tc_fence_after();
-                const uint32_t sA16 = a16 + (uint32_t)sa * (p.a_bytes >> 4);
-                for (int kj = 0; kj < p.kdn; kj++) {
-                    const int z = zi + p.pd - (u.ku * p.kdn + kj);
-                    if (z < 0 || z >= p.Do) continue;
-                    if (leader) {
-                        const uint32_t slot = (slot0 + (uint32_t)(z - g.blo)) % (uint32_t)p.SB;
-                        const uint32_t acc = tmem_base + (uint32_t)(kj * p.kw * p.NTW);
-                        uint64_t ad = tmpl + sA16;
-                        uint64_t bd = tmpl + (b16 + slot * (p.b_plane_bytes >> 4));
-                        const uint32_t first = ((started >> kj) & 1u) ? 1u : 0u;
-                        for (int yy = 0; yy < p.TY; yy++) {
-                            umma_f16(acc, ad, bd, idesc, first | (uint32_t)yy);
-                            umma_f16(acc, ad + 2, bd + 2, idesc, 1u);
-                            umma_f16(acc, ad + 4, bd + 4, idesc, 1u);
-                            umma_f16(acc, ad + 6, bd + 6, idesc, 1u);
-                            ad += a_row16; bd += b_row16;
-                        }
+        // MN-major, no swizzle: the two 8-voxel K halves of one MMA are 128 B apart (LBO), the 8-channel M / N groups one
+        // tile plane apart (SBO)
+        const uint64_t a_tmpl = umma_desc(0, 128, (uint32_t)(p.HXa * 16));
+        const uint64_t b_tmpl = umma_desc(0, 128, (uint32_t)(p.TX * 16));
+        const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
+        const uint32_t a_lo0 = (uint32_t)a_tmpl + (smem_u32(smem) >> 4);
+        const uint32_t b_lo0 = a_lo0 - (uint32_t)a_tmpl + (uint32_t)b_tmpl + (p.a_bytes >> 4);
+        const uint32_t stage16 = p.stage_bytes >> 4;
+        const uint32_t row_a16 = (uint32_t)(p.PA * p.HXa), row_b16 = (uint32_t)(p.kd * p.PB * p.TX);
+        const uint32_t acc_cols = (uint32_t)(p.kd * p.NTW);
+        const int ksteps = p.TX / 16;
+        uint32_t s = 0, par = 0, started = 0;
+        for (int L = L0; L < L1; L++) {
+            mbar_wait(&full[s], par);
+            tc_fence_after();
+            uint32_t a_row = a_lo0 + s * stage16, b_row = b_lo0 + s * stage16;
+            const int shape = (p.kw == 3 ? 2 : 0) + (ksteps == 2 ? 1 : 0);
+            for (int r = 0; r < p.TY; r++) {
+                const uint32_t flag = started | (uint32_t)r;          // 0 only for the very first row this CTA contracts
+                if (leader) {
+                    switch (shape) {
+                    case 3: wg_issue_row<3, 2>(tmem_base, acc_cols, a_row, a_hi, b_row, b_hi, idesc, flag); break;
+                    case 2: wg_issue_row<3, 1>(tmem_base, acc_cols, a_row, a_hi, b_row, b_hi, idesc, flag); break;
+                    case 1: wg_issue_row<1, 2>(tmem_base, acc_cols, a_row, a_hi, b_row, b_hi, idesc, flag); break;
+                    default: wg_issue_row<1, 1>(tmem_base, acc_cols, a_row, a_hi, b_row, b_hi, idesc, flag); break;
                     }
-                    started |= 1u << kj;
                 }
-                if (leader) umma_commit(&a_empty[sa]);
-                if (++sa == (uint32_t)p.SA) { sa = 0; pa ^= 1; }
-                // dy planes no later x plane of this segment uses are handed back to the producer
-                int relupto = g.bhi + 1;
-                if (zi + 1 < g.zb) { relupto = wg_lo(p, u.ku, zi + 1); if (relupto > g.bhi + 1) relupto = g.bhi + 1; }
-                for (; brel < relupto; brel++) {
-                    if (leader) umma_commit(&b_empty[rb]);
-                    if (++rb == (uint32_t)p.SB) rb = 0;
-                }
-                __syncwarp();
+                a_row += row_a16; b_row += row_b16;
             }
-            L += g.zb - g.za;
+            started = 1u;
+            if (leader) umma_commit(&empty[s]);
+            __syncwarp();
+            if (++s == (uint32_t)p.SA) { s = 0; par ^= 1; }
         }
-        if (leader) {
-            // accumulators that never received a plane (tiny volumes) are reported to the epilogue as empty
-            *started_slot = started;
-            mbar_arrive(done);
-            umma_commit(done);
-        }
+        if (leader) umma_commit(done);
         __syncwarp();
     } else {
-        // epilogue: TMEM -> split-K partial.  Accumulator row r = j*CB + c  <->  tap dy = j, channel c.
+        // ===================== epilogue: TMEM -> split-K partial =====================
+        // accumulator dx, row r = j*CB + c, column zs*NTW + co  <->  tap (dz = kd-1-zs, dy = j, dx), channels (c, co)
         mbar_wait(done, 0);
         tc_fence_after();
-        const uint32_t started = *started_slot;
+        const bool any = L1 > L0;
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int j = row / p.CB, c = row % p.CB;
         const int ntaps = p.kd * p.kh * p.kw;
         const bool row_ok = j < p.kh;
-        for (int kj = 0; kj < p.kdn; kj++) {
-            const int kdi = u.ku * p.kdn + kj;
-            const bool any = (started >> kj) & 1u;
-            for (int dxi = 0; dxi < p.kw; dxi++) {
-                const int tap = (kdi * p.kh + j) * p.kw + dxi;
+        for (int dx = 0; dx < p.kw; dx++) {
+            for (int zs = 0; zs < p.kd; zs++) {
+                const int tap = ((p.kd - 1 - zs) * p.kh + j) * p.kw + dx;
                 for (int cb = 0; cb < p.NTW; cb += 16) {
                     float v[16];
                     if (any) {
-                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kj * p.kw + dxi) * p.NTW + cb), v);
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((dx * p.kd + zs) * p.NTW + cb), v);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] = 0.f;
@@ -358,40 +307,34 @@ static PFN_encodeTiled get_enc()
     return enc;
 }
 
-// z-planar fp16 activation (N, D, C, H, Wp) viewed as 4D (x: W, c: C, y: H, zn: N*D); box (64, bc, by, 1), 128 B swizzle
-static int make_x_map(CUtensorMap* map, const void* ptr, int N, int C, int D, int H, int W, int bc, int by)
+// QH tensor (N, P, Da, Ha, Wa, 8 halves) seen as 16-byte voxel units of 4 floats: 5D map with the dims in the order the
+// shared-memory tile wants them.  zy_order 0: (x*4, plane, y, z, n)  [x tile: rows outermost];
+//                                 zy_order 1: (x*4, plane, z, y, n)  [dy tile: the kd planes of a row adjacent].
+// (D, H, W): extents of the VIEW starting at `ptr` (a centre-cropped skip tensor is a sub-box of its allocation: everything
+// outside the view reads as 0); (Da, Ha, Wa): extents of the allocation (strides).
+static int make_qh_map(CUtensorMap* map, const void* ptr, int N, int P, int D, int H, int W, int Da, int Ha, int Wa, int bx,
+                       int bp, int by, int bz, int zy_order)
 {
     PFN_encodeTiled enc = get_enc();
     if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
-    const cuuint64_t Wp = (cuuint64_t)((W + 7) & ~7);
-    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)N * D};
-    cuuint64_t strides[3] = {(cuuint64_t)H * Wp * 2, Wp * 2, (cuuint64_t)C * H * Wp * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kSeg, (cuuint32_t)bc, (cuuint32_t)by, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (box[1] > 256 || box[2] > 256) return set_error("wgrad: TMA box dimension > 256");
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    const cuuint64_t sy = (cuuint64_t)Wa * 16, sz = (cuuint64_t)Wa * Ha * 16, sp = (cuuint64_t)Wa * Ha * Da * 16, sn = sp * P;
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    dims[0] = (cuuint64_t)W * 4; box[0] = (cuuint32_t)bx * 4;
+    dims[1] = (cuuint64_t)P; strides[0] = sp; box[1] = (cuuint32_t)bp;
+    if (zy_order == 0) {
+        dims[2] = (cuuint64_t)H; strides[1] = sy; box[2] = (cuuint32_t)by;
+        dims[3] = (cuuint64_t)D; strides[2] = sz; box[3] = (cuuint32_t)bz;
+    } else {
+        dims[2] = (cuuint64_t)D; strides[1] = sz; box[2] = (cuuint32_t)bz;
+        dims[3] = (cuuint64_t)H; strides[2] = sy; box[3] = (cuuint32_t)by;
+    }
+    dims[4] = (cuuint64_t)N; strides[3] = sn; box[4] = 1;
+    for (int i = 0; i < 4; i++) if (box[i] > 256) return set_error("wgrad: TMA box dimension > 256");
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error("wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
-    return 0;
-}
-
-// shifted gradient copies (N, Do, kw, Co, Ho, Wxp) viewed as 5D (x: Wx, co: Co, dxi: kw, y: Ho, zn: N*Do);
-// box (32, NTW, kw, TY, 1)
-static int make_dy_map(CUtensorMap* map, const void* ptr, int N, int Co, int kw, int Do, int Ho, int Wx, int bn, int by)
-{
-    PFN_encodeTiled enc = get_enc();
-    if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
-    const cuuint64_t Wp = (cuuint64_t)((Wx + 7) & ~7);
-    cuuint64_t dims[5] = {(cuuint64_t)Wx, (cuuint64_t)Co, (cuuint64_t)kw, (cuuint64_t)Ho, (cuuint64_t)N * Do};
-    cuuint64_t strides[4] = {(cuuint64_t)Ho * Wp * 2, (cuuint64_t)Co * Ho * Wp * 2, Wp * 2, (cuuint64_t)kw * Co * Ho * Wp * 2};
-    cuuint32_t box[5] = {(cuuint32_t)kSeg, (cuuint32_t)bn, (cuuint32_t)kw, (cuuint32_t)by, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    if (box[1] > 256 || box[3] > 256) return set_error("wgrad: TMA box dimension > 256");
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error("wgrad: cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
+    if (r != CUDA_SUCCESS) return set_error("wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
 
@@ -399,58 +342,46 @@ static int plan_wgrad(const e3b_wgrad_args* a, WgradParams& p)
 {
     memset(&p, 0, sizeof(p));
     p.N = a->N; p.D = a->D; p.H = a->H; p.W = a->W;
-    p.D1 = a->D1;
     p.kd = a->kd; p.kh = a->kh; p.kw = a->kw; p.pd = a->pd; p.ph = a->ph; p.pw = a->pw;
     p.Do = a->D + 2 * a->pd - a->kd + 1; p.Ho = a->H + 2 * a->ph - a->kh + 1; p.Wo = a->W + 2 * a->pw - a->kw + 1;
     if (p.Do <= 0 || p.Ho <= 0 || p.Wo <= 0) return set_error("wgrad: empty output");
-    p.off1_d = a->off1_d; p.off1_h = a->off1_h; p.off1_w = a->off1_w;
     const int C1 = a->src1 ? a->C1 : 0;
-    const int cmax = a->C0 > C1 ? a->C0 : C1;
-    p.CB = cmax > 16 ? 32 : (cmax > 8 ? 16 : 8);
+    const int cmax = cpad16(a->C0 > C1 ? a->C0 : C1);
+    // channels per M block: with y taps, 32 (four rows stacked in M, three of them taps); without, as many as there are
+    p.CB = a->kh > 1 ? (cmax >= 32 ? 32 : 16) : (cmax >= 128 ? 128 : (cmax >= 64 ? 64 : (cmax >= 32 ? 32 : 16)));
     p.RS = 128 / p.CB;
-    p.mchunks0 = (a->C0 + p.CB - 1) / p.CB;
-    p.mchunks = p.mchunks0 + (C1 + p.CB - 1) / p.CB;
+    p.PA = p.CB / 8;
+    p.mchunks0 = (cpad16(a->C0) + p.CB - 1) / p.CB;
+    p.mchunks = p.mchunks0 + (C1 > 0 ? (cpad16(C1) + p.CB - 1) / p.CB : 0);
     p.ktot = p.mchunks * p.CB;
-    // N columns per CTA: one MMA covers the kw shifted copies, N = kw*NTW <= 256
+    // N columns per z-slot: kw accumulators of kd * NTW columns must fit the 512 TMEM columns, one MMA has N = kd * NTW <= 256
     const int npad = cpad16(a->Co);
-    const int ntw_max = a->kw == 1 ? 128 : 80;
-    p.NTW = npad <= ntw_max ? npad : (npad % 64 == 0 ? 64 : (npad % 48 == 0 ? 48 : 32));
+    int ntw_max = 512 / (a->kw * a->kd); if (ntw_max > 256 / a->kd) ntw_max = 256 / a->kd;
+    ntw_max &= ~15;
+    if (npad <= ntw_max) p.NTW = npad;
+    else { p.NTW = ntw_max; while (p.NTW > 16 && npad % p.NTW) p.NTW -= 16; }
+    p.PB = p.NTW / 8;
     p.nchunks_n = (npad + p.NTW - 1) / p.NTW;
     p.npad_total = p.nchunks_n * p.NTW;
-    p.kdn = (a->kd * a->kw * p.NTW <= 512) ? a->kd : 1;
-    p.kd_units = a->kd / p.kdn;
-    p.units = p.kd_units * p.mchunks * p.nchunks_n;
+    p.units = p.mchunks * p.nchunks_n;
+    p.TX = a->W > 16 ? 32 : 16;
+    p.HXa = p.TX + a->kw - 1;
     const size_t budget = 227 * 1024 - 2048 - 512;
     int ty = 8;
-    // developer overrides for tuning runs (scripts/layer_bench.py): E3B_WGRAD_TY / _SA / _SB
-    const char* e_ty = getenv("E3B_WGRAD_TY"); const char* e_sa = getenv("E3B_WGRAD_SA"); const char* e_sb = getenv("E3B_WGRAD_SB");
-    if (e_ty) ty = atoi(e_ty);
+    if (const char* e = getenv("E3B_WGRAD_TY")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) ty = v; }      // tuning
     for (;; ty >>= 1) {
-        p.TY = ty; p.TYA = ty + a->kh - 1; p.rows_alloc = ty + p.RS - 1;
-        if (p.rows_alloc < p.TYA) p.rows_alloc = p.TYA;
-        p.a_load_bytes = (uint32_t)(p.TYA * p.CB * 128);
-        p.a_bytes = (uint32_t)(p.rows_alloc * p.CB * 128);
-        p.b_plane_bytes = (uint32_t)(ty * a->kw * p.NTW * 128);
-        // rings: the dy window holds kdn live planes; +2 lets the producer run ahead.  x tiles: 2..4 deep.
+        p.TY = ty; p.rows_a = ty + p.RS - 1;
+        p.a_bytes = (uint32_t)(((size_t)p.rows_a * p.PA * p.HXa * 16 + 127) & ~(size_t)127);
+        p.b_bytes = (uint32_t)((size_t)ty * a->kd * p.PB * p.TX * 16);
+        p.stage_bytes = p.a_bytes + p.b_bytes;
+        p.tx_bytes = (uint32_t)((size_t)p.rows_a * p.PA * p.HXa * 16) + p.b_bytes;
         const bool small_enough = ty == 1 || ty / 2 < p.Ho;      // do not carry rows a small volume does not have
-        int sa = 2, sb = p.kdn + 1;
-        const bool fits = (size_t)sa * p.a_bytes + (size_t)sb * p.b_plane_bytes <= budget;
-        if (fits && (small_enough || ty == 1)) {
-            for (;;) {
-                bool grew = false;
-                if (sb < p.kdn + 3 && (size_t)sa * p.a_bytes + (size_t)(sb + 1) * p.b_plane_bytes <= budget) { sb++; grew = true; }
-                if (sa < 4 && (size_t)(sa + 1) * p.a_bytes + (size_t)sb * p.b_plane_bytes <= budget) { sa++; grew = true; }
-                if (!grew) break;
-            }
-            p.SA = sa; p.SB = sb;
-            if (e_sa && atoi(e_sa) >= 2 && atoi(e_sa) <= sa) p.SA = atoi(e_sa);
-            if (e_sb && atoi(e_sb) >= p.kdn + 1 && atoi(e_sb) <= sb) p.SB = atoi(e_sb);
-            break;
-        }
+        if ((size_t)2 * p.stage_bytes <= budget && small_enough) break;
         if (ty == 1) return set_error("wgrad: stage does not fit shared memory");
     }
-    // tiles cover the conv INPUT width (the shifted gradient copies are indexed by the input x)
-    p.tiles_x = (a->W + kSeg - 1) / kSeg; p.tiles_y = (p.Ho + p.TY - 1) / p.TY;
+    int sa = (int)(budget / p.stage_bytes); if (sa > 4) sa = 4;
+    p.SA = sa;
+    p.tiles_x = (p.Wo + p.TX - 1) / p.TX; p.tiles_y = (p.Ho + p.TY - 1) / p.TY;
     p.total_L = p.tiles_x * p.tiles_y * a->N * p.D;
     int S = num_sms() / p.units; if (S < 1) S = 1;             // one resident CTA per SM, a single wave
     if (S > p.total_L) S = p.total_L;
@@ -471,19 +402,20 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     int rc = plan_wgrad(a, p);
     if (rc) return rc;
     p.part = a->workspace;
+    if (((uintptr_t)a->src0 | (uintptr_t)a->src1 | (uintptr_t)a->dy) & 15) return set_error("wgrad: pointers must be 16-byte aligned");
     CUtensorMap mx0, mx1, mdy;
-    rc = make_x_map(&mx0, a->src0, a->N, a->C0, a->D, a->H, a->W, p.CB, p.TYA);
+    rc = make_qh_map(&mx0, a->src0, a->N, cpad16(a->C0) / 8, a->D, a->H, a->W, a->D, a->H, a->W, p.HXa, p.PA, p.rows_a, 1, 0);
     if (rc) return rc;
     if (a->src1) {
-        if ((a->off1_d | a->off1_h | a->off1_w) && (a->pd | a->ph | a->pw))
-            return set_error("wgrad: a centre-cropped second source requires zero padding (VALID convolution)");
-        if (a->off1_w & 7) return set_error("wgrad: the x crop offset of the second source must be a multiple of 8");
-        rc = make_x_map(&mx1, a->src1, a->N, a->C1, a->D1, a->H1, a->W1, p.CB, p.TYA);
+        // the centre-cropped view of the skip tensor (autocrop, unet.py:303-324): a voxel is a 16-byte unit, any offset is legal
+        const uint8_t* v1 = reinterpret_cast<const uint8_t*>(a->src1) +
+                            (((size_t)a->off1_d * a->H1 + a->off1_h) * a->W1 + a->off1_w) * 16;
+        rc = make_qh_map(&mx1, v1, a->N, cpad16(a->C1) / 8, a->D, a->H, a->W, a->D1, a->H1, a->W1, p.HXa, p.PA, p.rows_a, 1, 0);
         if (rc) return rc;
     } else mx1 = mx0;
-    rc = make_dy_map(&mdy, a->dy, a->N, a->Co, a->kw, p.Do, p.Ho, a->W, p.NTW, p.TY);
+    rc = make_qh_map(&mdy, a->dy, a->N, cpad16(a->Co) / 8, p.Do, p.Ho, p.Wo, p.Do, p.Ho, p.Wo, p.TX, p.PB, p.TY, a->kd, 1);
     if (rc) return rc;
-    const size_t smem = (size_t)p.SA * p.a_bytes + (size_t)p.SB * p.b_plane_bytes + 1024 + 1024;
+    const size_t smem = (size_t)p.SA * p.stage_bytes + 1024 + 1024;
     static bool configured[kMaxDevices] = {false};
     if (!configured[current_device()]) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -495,6 +427,7 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     if (rc) return rc;
     const int ntaps = a->kd * a->kh * a->kw;
     const size_t total = (size_t)ntaps * p.ktot * p.npad_total;
+    // source 1's channels start at the next CB boundary after source 0's in the partial row space
     if (p.S >= 64) {
         int blocks = (int)((total + 31) / 32); if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
         wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.part, a->dw, p.S, ntaps, p.ktot, p.npad_total, p.CB, p.mchunks0,

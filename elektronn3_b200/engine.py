@@ -34,29 +34,12 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def planar_empty(N, C, D, H, W, device, kw=None):
-    """Z-PLANAR layout of the wgrad operands: float16 (N, D, C, H, ceil8(W)); with kw: the x-shifted
-    gradient copies (N, D, kw, C, H, ceil8(W)) (include/e3b.h)"""
-    shape = (N, D, C, H, (W + 7) & ~7) if kw is None else (N, D, kw, C, H, (W + 7) & ~7)
-    return torch.empty(shape, dtype=torch.float16, device=device)
-
-
-def planar_from_ncdhw(x5):
-    """NCDHW -> z-planar float16 (test helper: the kernels write these copies themselves)"""
-    W = x5.shape[-1]
-    t = x5.permute(0, 2, 1, 3, 4).to(torch.float16)
-    if W % 8:
-        t = torch.nn.functional.pad(t, (0, (-W) % 8))
-    return t.contiguous()
-
-
 class QP:
-    """A device tensor in quad-planar layout (+ optionally its planar copy `pl`): float32 QP, or -- when
-    ``half`` -- the float16 QH operand layout."""
-    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W', 'pl', 'idx', 'half', 'scale', 'crop_off')
+    """A device tensor in quad-planar layout: float32 QP, or -- when ``half`` -- the float16 QH operand layout."""
+    __slots__ = ('t', 'N', 'C', 'D', 'H', 'W', 'idx', 'half', 'scale', 'crop_off')
 
-    def __init__(self, t, N, C, D, H, W, pl=None):
-        self.t, self.N, self.C, self.D, self.H, self.W, self.pl = t, N, C, D, H, W, pl
+    def __init__(self, t, N, C, D, H, W):
+        self.t, self.N, self.C, self.D, self.H, self.W = t, N, C, D, H, W
         self.idx = None            # pooled tensors: arg-max slots of the pooling windows (uint8)
         self.half = t.dtype == torch.float16
         self.scale = None          # gradients: device float[4] (bound bits, 2^k, 2^-k, -) of the fp16 scale
@@ -89,16 +72,13 @@ def _require_cuda(t, what):
 
 
 # ------------------------------------------------------------------------------------------ layout
-def pack_input(x5, planar=False):
-    """NCDHW float32 -> QP (reference: the tensor `Trainer._train_step` moves to the device, trainer.py:515)"""
+def pack_input(x5):
+    """NCDHW float32 -> QH (reference: the tensor `Trainer._train_step` moves to the device, trainer.py:515)"""
     _require_cuda(x5, 'input')
     x5 = x5.contiguous()
     N, C, D, H, W = x5.shape
     q = QP.empty_half(N, C, D, H, W, x5.device)
-    if planar:
-        q.pl = planar_empty(N, C, D, H, W, x5.device)
-    L.check(L.lib().e3b_pack_ncdhw(x5.data_ptr(), q.ptr, _p(q.pl), N, C, D, H, W, D, H, W, 0, 0, 0, _stream()),
-            'pack_ncdhw')
+    L.check(L.lib().e3b_pack_ncdhw(x5.data_ptr(), q.ptr, N, C, D, H, W, D, H, W, 0, 0, 0, _stream()), 'pack_ncdhw')
     return q
 
 
@@ -265,17 +245,19 @@ def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), b
 
 
 def wgrad(src0, dy, Co, k, pad, dw_shape, *, src1=None, off1=(0, 0, 0), layout=0, up_taps=0, up_co=0):
+    """dW of a convolution: src0 / src1 the QH activations it read, dy the (scaled) QH gradient of its output.  The kernel
+    reads the operand tensors of the forward / dgrad kernels directly (MN-major MMA operands): no extra copies."""
     a = L.WgradArgs()
     dev = src0.t.device
-    if src0.pl is None or dy.pl is None or (src1 is not None and src1.pl is None):
-        raise RuntimeError('wgrad: operands need their planar copies (forward was run without save=True?)')
-    a.src0, a.C0 = src0.pl.data_ptr(), src0.C
+    if not (src0.half and dy.half and (src1 is None or src1.half)):
+        raise RuntimeError('wgrad: operands must be float16 QH tensors')
+    a.src0, a.C0 = src0.ptr, src0.C
     a.N, a.D, a.H, a.W = src0.N, src0.D, src0.H, src0.W
     if src1 is not None:
-        a.src1, a.C1 = src1.pl.data_ptr(), src1.C
+        a.src1, a.C1 = src1.ptr, src1.C
         a.D1, a.H1, a.W1 = src1.D, src1.H, src1.W
         a.off1_d, a.off1_h, a.off1_w = off1
-    a.dy, a.Co = dy.pl.data_ptr(), Co
+    a.dy, a.Co = dy.ptr, Co
     a.kd, a.kh, a.kw = k
     a.pd, a.ph, a.pw = pad
     dw = torch.empty(dw_shape, dtype=torch.float32, device=dev)
@@ -286,7 +268,7 @@ def wgrad(src0, dy, Co, k, pad, dw_shape, *, src1=None, off1=(0, 0, 0), layout=0
     ws = torch.empty((n,), dtype=torch.float32, device=dev)
     a.workspace = ws.data_ptr()
     if dy.scale is not None:
-        a.dy_unscale = dy.scale.data_ptr() + 8          # the planar gradient copies hold 2^k * dy
+        a.dy_unscale = dy.scale.data_ptr() + 8          # the gradient tensor holds 2^k * dy
     L.check(L.lib().e3b_wgrad(ctypes.byref(a), _stream()), 'wgrad')
     return dw
 
@@ -310,10 +292,10 @@ def norm_finalize(stats, mode, G, N, C, S, gamma, beta, eps, rm, rv, momentum, d
     return st
 
 
-def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, planar=False):
-    """a = relu(y*scale+shift) (QH) and optionally the ceil-mode max-pooled tensor (QH).  planar=True also
-    writes the planar copies the weight-gradient kernel reads (training).  With write_a=False `y` is already
-    a QH activation (eval path) and is only pooled."""
+def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, save=False):
+    """a = relu(y*scale+shift) (QH) and optionally the ceil-mode max-pooled tensor (QH).  save=True (a backward pass will
+    follow) also records the arg-max slots of the pooling windows.  With write_a=False `y` is already a QH activation
+    (eval path) and is only pooled."""
     dev = y.t.device
     if write_a == y.half:
         raise RuntimeError('norm_act: y must be float32 QP when a is written, a QH activation otherwise')
@@ -323,16 +305,13 @@ def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, planar=Fals
     if pool is not None:
         pk = pool
         pooled = QP.empty_half(y.N, y.C, -(-y.D // pk[0]), -(-y.H // pk[1]), -(-y.W // pk[2]), dev)
-    a_pl = p_pl = pidx = None
-    if planar:
-        a_pl = planar_empty(y.N, y.C, y.D, y.H, y.W, dev)
-        (a if a is not None else y).pl = a_pl
-        if pooled is not None:
-            p_pl = pooled.pl = planar_empty(pooled.N, pooled.C, pooled.D, pooled.H, pooled.W, dev)
-            # arg-max slots for the backward pass (what MaxPool(return_indices=True) keeps in the reference)
-            pidx = pooled.idx = torch.empty(pooled.t.shape, dtype=torch.uint8, device=dev)
+    pidx = None
+    if save and pooled is not None:
+        # arg-max slots for the backward pass (what MaxPool(return_indices=True) keeps in the reference)
+        pidx = pooled.idx = torch.empty(pooled.t.shape[:1] + (cpad8(y.C) // 4,) + pooled.t.shape[2:5] + (4,), dtype=torch.uint8,
+                                        device=dev)
     L.check(L.lib().e3b_norm_act(y.ptr, _p(scale), _p(shift), a.ptr if a else None, pooled.ptr if pooled else None,
-                                 _p(a_pl), _p(p_pl), _p(pidx), y.N, y.C, y.D, y.H, y.W, pk[0], pk[1], pk[2],
+                                 _p(pidx), y.N, y.C, y.D, y.H, y.W, pk[0], pk[1], pk[2],
                                  1 if relu else 0, 1 if y.half else 0, _stream()), 'norm_act')
     return a, pooled
 
@@ -509,7 +488,7 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save):
         y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
                                    variant=var, w_unscale=wsc)
         u.y = y
-        u.a, u.pooled = norm_act(y, None, None, pool=pool, planar=save)
+        u.a, u.pooled = norm_act(y, None, None, pool=pool, save=save)
     else:
         n = spec.norm
         y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1,
@@ -522,7 +501,7 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save):
         u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, S, _affine(n, 'weight'), _affine(n, 'bias'), n.eps,
                                  rm, rv, mom, y.t.device)
         u.y, u.stats = y, stats
-        u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, planar=save)
+        u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, save=save)
     if not save:
         u.y = u.src0 = u.src1 = None
     return u
@@ -584,7 +563,7 @@ def _run_up(net, spec, dec, enc, training, save):
         y, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias,
                                scatter=spec.s, out_spatial=out_sp, w_unscale=wsc)
         u.y = y
-        u.a, _ = norm_act(y, None, None, planar=save)
+        u.a, _ = norm_act(y, None, None)
     else:
         n = spec.norm
         y, _, stats = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias,
@@ -596,7 +575,7 @@ def _run_up(net, spec, dec, enc, training, save):
         u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, y.D * y.H * y.W, _affine(n, 'weight'),
                                  _affine(n, 'bias'), n.eps, rm, rv, mom, y.t.device)
         u.y, u.stats = y, stats
-        u.a, _ = norm_act(y, u.nstate.scale, u.nstate.shift, planar=save)
+        u.a, _ = norm_act(y, u.nstate.scale, u.nstate.shift)
     if not save:
         u.y = u.dec = u.src0 = None
     return u, off1
@@ -616,7 +595,7 @@ def forward_features(net, x, training, save):
     cin = net.down[0][0].C0
     if x5.shape[1] != cin:
         raise RuntimeError(f'expected {cin} input channels, got {x5.shape[1]}')
-    cur = pack_input(x5, planar=save)
+    cur = pack_input(x5)
     return forward_features_qp(net, cur, training, save, squeeze, tuple(x.shape))
 
 
@@ -687,7 +666,7 @@ def forward(net, x, training, save):
 
 
 # ------------------------------------------------------------------------------------------ backward
-def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True, planar=True, conv_geom=None):
+def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True):
     """Backward of norm -> relu [-> pool] for unit `u`; returns (dy QP or s2d QP, dgamma, dbeta, dbias).
     g1 may be the gradient of a centre-cropped view of this unit's activation (``g1.crop_off`` set by
     _conv_unit_bwd): it is then added inside that box only (the backward of autocrop's slice is a zero pad)."""
@@ -749,14 +728,6 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True, planar=True,
         dy = QP.empty_half(N, C, a.D, a.H, a.W, dev)
     dy.scale = dy_scale            # the tensor holds 2^k * dy; conv_forward undoes it through dy_scale[2]
     args.dy = dy.ptr
-    if planar:
-        if s2d is not None or conv_geom is None:
-            kw_, pw_, wx_ = 1, 0, dy.W
-        else:
-            kw_, pw_, wx_ = conv_geom
-        dy.pl = planar_empty(dy.N, dy.C, dy.D, dy.H, wx_, dev, kw=kw_)
-        args.dy_planar = dy.pl.data_ptr()
-        args.planar_kw, args.planar_pw, args.planar_W = kw_, pw_, wx_
     args.relu = 1
     lib = L.lib()
     st = _stream()
@@ -775,9 +746,7 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
     """Backward of one conv -> norm -> relu [-> pool] unit: returns (dsrc0, dsrc1)."""
     spec = u.spec
     conv, n = spec.conv, spec.norm
-    dy, dgamma, dbeta, dbias = _norm_bwd(u, spec.Co, g0, g1, gp, want_bias=conv.bias is not None,
-                                         planar=conv.weight.requires_grad,
-                                         conv_geom=(spec.k[2], spec.pad[2], u.src0.W))
+    dy, dgamma, dbeta, dbias = _norm_bwd(u, spec.Co, g0, g1, gp, want_bias=conv.bias is not None)
     if dgamma is not None:
         _put(grads, n.weight, dgamma)
         _put(grads, n.bias, dbeta)
@@ -785,13 +754,7 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
         _put(grads, conv.bias, dbias)
     cropped = u.src1 is not None and (tuple(u.off1) != (0, 0, 0) or u.src1.spatial != u.src0.spatial)
     if conv.weight.requires_grad:
-        src1, off1 = u.src1, u.off1
-        if cropped and (any(spec.pad) or off1[2] % 8):
-            # the weight-gradient kernel reads a cropped second source in place only for un-padded convolutions and
-            # 16-byte aligned x offsets; otherwise hand it the cropped view as a tensor of its own (memory plumbing
-            # of an off-default configuration: VALID-mode training)
-            src1, off1 = _cropped_planar(u.src1, u.off1, u.src0.spatial), (0, 0, 0)
-        dw = wgrad(u.src0, dy, spec.Co, spec.k, spec.pad, tuple(conv.weight.shape), src1=src1, off1=off1)
+        dw = wgrad(u.src0, dy, spec.Co, spec.k, spec.pad, tuple(conv.weight.shape), src1=u.src1, off1=u.off1)
         _put(grads, conv.weight, dw)
     if not need_dx:
         return None, None
@@ -806,16 +769,6 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
     if cropped:
         d1.crop_off = tuple(u.off1)       # gradient of autocrop's slice of the skip tensor (models/unet.py:303-324)
     return d0, d1
-
-
-def _cropped_planar(src, off, spatial):
-    """The centre-cropped view of a tensor's z-planar copy (N, D, C, H, ceil8(W)) as a contiguous planar tensor."""
-    D, H, W = spatial
-    pl = src.pl[:, off[0]:off[0] + D, :, off[1]:off[1] + H, off[2]:off[2] + W]
-    if W % 8:
-        pl = torch.nn.functional.pad(pl, (0, (-W) % 8))
-    q = QP(src.t, src.N, src.C, D, H, W, pl=pl.contiguous())
-    return q
 
 
 def backward(net, tape, dlogits, need_dx):

@@ -40,9 +40,8 @@ int64_t e3b_launch_count(void);
  * NCDHW float32 -> QH (e3b_pack_ncdhw, e3b_gather_tiles) and QP -> NCDHW float32 (e3b_unpack_qp).  Used for the network input (reference: trainer.py:515 `inp.to(device)`)
  * and by tests.  src may be a sub-box of a larger volume (Predictor tiles, inference.py:179-189):
  * (Dv,Hv,Wv) are the extents of the allocation, (z0,y0,x0) the origin of the box inside it (may be
- * negative / overhanging: out-of-volume voxels read as 0, which is tiled_apply's zero padding).
- * dst_planar (optional): the z-planar float16 copy (N, D, C, H, ceil8(W)) that e3b_wgrad reads. */
-int e3b_pack_ncdhw(const float* src, void* dst_qh, void* dst_planar, int N, int C, int D, int H, int W,
+ * negative / overhanging: out-of-volume voxels read as 0, which is tiled_apply's zero padding). */
+int e3b_pack_ncdhw(const float* src, void* dst_qh, int N, int C, int D, int H, int W,
                    int Dv, int Hv, int Wv, int z0, int y0, int x0, void* stream);
 int e3b_unpack_qp(const float* src_qp, float* dst, int N, int C, int D, int H, int W, void* stream);
 
@@ -120,10 +119,11 @@ int e3b_debug_zs_prof(unsigned long long* out16, int reset);
 
 /* Weight gradient: dW[tap][ci][co] = sum_voxels x[v + tap - pad][ci] * dy[v][co]  (conv backward-filter
  * of nn.Conv3d at unet.py:131-149; with taps=1 on (x, space-to-depth dy) also ConvTranspose's).
- * fp16 operands (kind::f16), fp32 accumulate.  Operands are Z-PLANAR float16 tensors (row pitch padded to
- * 16 bytes = ceil8(W) elements), written by e3b_norm_act / e3b_norm_bwd_apply:  src0 (N, D, C0, H, ceil8(W));  src1 (N, D1, C1, H1, ceil8(W1)) read at offset off1
- * (only with zero padding);  dy (N, Do, kw, Co, Ho, ceil8(W)) = the kw x-shifted copies described at
- * e3b_norm_bwd_args.dy_planar.  Result is written in torch layout:
+ * fp16 operands (kind::f16), fp32 accumulate.  The operands are the QH tensors themselves, read as MN-major MMA operands
+ * (K = 16 consecutive x-voxels per MMA; stencil shifts are 16-byte start-address offsets, y taps are stacked in the
+ * MMA's M, z taps in its N):  src0 (N, C0, D, H, W);  src1 (N, C1, D1, H1, W1) read at the voxel offset off1 (the
+ * centre-cropped skip tensor of autocrop, unet.py:303-324: any offset);  dy (N, Co, Do, Ho, Wo), usually carrying the
+ * power-of-two scale of e3b_norm_bwd_args.dy_scale.  Result is written in torch layout:
  *   layout 0: dw (Co, C0+C1, kd, kh, kw)        (Conv)
  *   layout 1: dw (C0, Co/ntap_up, sd, sh, sw) with dy channels = tap*pad8(Co_up)+co  (ConvTranspose)
  * `workspace` holds split-K partials: e3b_wgrad_workspace_floats() floats. */
@@ -137,7 +137,7 @@ typedef struct e3b_wgrad_args {
     float* dw; int32_t layout; int32_t up_taps; int32_t up_co;
     float* workspace;
     const float* dy_unscale;                   /* optional device scalar multiplied into dw: 2^-k of the scaled gradient
-                                                  copies (e3b_norm_bwd_args.dy_scale + 2) */
+                                                  tensor (e3b_norm_bwd_args.dy_scale + 2) */
 } e3b_wgrad_args;
 int64_t e3b_wgrad_workspace_floats(const e3b_wgrad_args* args);
 int e3b_wgrad(const e3b_wgrad_args* args, void* stream);
@@ -154,13 +154,10 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
 /* a = relu(y*scale+shift): y QP (fp32), a QH; if pooled != NULL also pooled = maxpool_{(pk_d,pk_h,pk_w), ceil}(a) (QH).
  * scale/shift NULL = identity; a NULL = only the pooled tensor is written.  y_is_half: y is itself a QH
  * activation (eval path: the conv epilogue already activated it) and is only pooled.
- * a_planar / pooled_planar (optional): the same tensors as Z-PLANAR (N, D, C, H, ceil8(W)) float16 copies, the
- * operand layout of e3b_wgrad.
  * pool_idx (optional, uint8 (N, pad8(C)/4, Dp, Hp, Wp, 4)): per pooled voxel and channel the window slot
  * ((dz*pk_h+dy)*pk_w+dx) of the first maximum -- what nn.MaxPool3d(return_indices) would give; consumed by
  * e3b_norm_bwd_*. */
-int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled,
-                 void* a_planar, void* pooled_planar, uint8_t* pool_idx,
+int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled, uint8_t* pool_idx,
                  int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, int y_is_half, void* stream);
 
 /* backward of conv -> norm -> relu [-> pool] as autograd derives it:
@@ -169,8 +166,7 @@ int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a,
  *   finalize: m1,m2 per (n,c); dgamma, dbeta, dbias (conv bias grad); a bound on |dy| -> dy_scale[0]
  *   apply:    dy = rstd * (gamma*dr - m1 - xhat*m2), written as the QH operand 2^k * dy (k from the bound so
  *             that |2^k dy| <= 2^14; 2^k -> dy_scale[1], 2^-k -> dy_scale[2]), or space-to-depth (s2d=1:
- *             channel = tap*pad8(C)+c on the grid (ceil(D/sd),..)) for the transposed conv backward.
- *             The planar float32 copies for e3b_wgrad are unscaled. */
+ *             channel = tap*pad8(C)+c on the grid (ceil(D/sd),..)) for the transposed conv backward. */
 typedef struct e3b_norm_bwd_args {
     const float* y;                            /* conv output (pre-norm); with scale == NULL: the activation itself */
     const float* scale; const float* shift;    /* forward affine [N][pad8(C)] from e3b_norm_finalize: the activation
@@ -188,11 +184,6 @@ typedef struct e3b_norm_bwd_args {
     float* m1; float* m2;                      /* [N][pad8(C)] */
     float* dgamma; float* dbeta; float* dbias; /* [C] each; may be NULL */
     void* dy; int32_t s2d, sd, sh, sw;         /* QH output (scaled) */
-    void* dy_planar;                           /* optional: 2^k * dy (float16) in the layout e3b_wgrad contracts against,
-                                                  (N, D, kw, C, H, ceil8(Wx)) with the stencil's x shift applied:
-                                                  [n][z][dxi][c][y][xs] = dy[n][c][z][y][xs - (dxi - pw)];
-                                                  s2d: (N, Dw, 1, taps*pad8(C), Hw, ceil8(Ww)) */
-    int32_t planar_kw, planar_pw, planar_W;    /* kw, pw and input width Wx of the conv dy belongs to (0 -> 1,0,W) */
     int32_t relu;
     int32_t g1_crop;                           /* 1: g1 is the gradient of a CENTRE-CROPPED view of this tensor (autocrop,
                                                   unet.py:303-324; the backward of the slice is a zero pad): it has extents

@@ -2,7 +2,7 @@
 # Kernel-iteration visit: conv / network parity tests, then the per-layer benches and a bench line (no CPU / cuDNN arms).
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_unet_gpu.py -m gpu -q --tb=short --timeout 300 -x ${1:+-k "$1"} > gpurun_out/pytest_perf.log 2>&1
+timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_unet_gpu.py tests/test_protocol_gpu.py -m gpu -q --tb=short --timeout 300 -x ${1:+-k "$1"} > gpurun_out/pytest_perf.log 2>&1
 echo "pytest rc=$?"; tail -8 gpurun_out/pytest_perf.log
 E3B_ZS_PROF=1 ZS_SHAPES=1,2 timeout 300 python scripts/zs_bench.py 0 > gpurun_out/zs_bench.txt 2>&1; cat gpurun_out/zs_bench.txt
 timeout 300 python scripts/layer_bench.py > gpurun_out/layer_bench.txt 2>&1; cat gpurun_out/layer_bench.txt

@@ -20,7 +20,7 @@ __device__ uint64_t mk_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
 }
 
 // mode 0: issue profile; 1: wait cost; 2: MMA batches of `batch` separated by a commit; 3: MMAs + concurrent bulk copies
-__global__ void __launch_bounds__(128, 1) bench(int mode, int N, int batch, int copy_bytes, const uint8_t* gsrc, long long* out)
+__global__ void __launch_bounds__(128, 1) bench(int mode, int N, int batch, int copy_bytes, const uint8_t* gsrc, long long* out, int mn)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar, bar2, cbar[4];
@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int batch, int 
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tm = slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t idesc = umma_idesc_f16(N, 0, 0);
-    const uint64_t ad = mk_desc(smem_u32(smem), 2880, 160), bd = mk_desc(smem_u32(smem + 64 * 1024), (uint32_t)N * 16, 128);
+    // mn = 1: both operands MN-major (the weight-gradient kernel: K = voxels 16 B apart, 8-channel groups one tile plane apart)
+    const uint32_t idesc = umma_idesc_f16(N, mn, mn);
+    const uint64_t ad = mn ? mk_desc(smem_u32(smem), 128, 544) : mk_desc(smem_u32(smem), 2880, 160);
+    const uint64_t bd = mn ? mk_desc(smem_u32(smem + 64 * 1024), 128, 512) : mk_desc(smem_u32(smem + 64 * 1024), (uint32_t)N * 16, 128);
     if (mode == 0 && threadIdx.x == 0) {
         long long t[65];
         t[0] = clock64();
@@ -115,9 +117,9 @@ int main()
     uint8_t* g; cudaMalloc(&g, 64 * 1024 * 1024 + 65536); cudaMemset(g, 0, 64 * 1024 * 1024 + 65536);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     long long h[128];
-    auto run = [&](int mode, int N, int batch, int cb, int grid) {
+    auto run = [&](int mode, int N, int batch, int cb, int grid, int mn = 0) {
         cudaMemset(d, 0, sizeof(h));
-        bench<<<grid, 128, 200 * 1024>>>(mode, N, batch, cb, g, d);
+        bench<<<grid, 128, 200 * 1024>>>(mode, N, batch, cb, g, d, mn);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("mode %d ERROR %s\n", mode, cudaGetErrorString(e)); exit(1); }
         cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
@@ -139,6 +141,12 @@ int main()
         printf("N=96 with concurrent bulk copies of %5d B (148 CTAs): %lld cycles/MMA, copy rate %.1f B/cycle/SM\n", cb, h[0], h[1] / 1000.0);
         run(3, 64, 0, cb, 148);
         printf("N=64 with concurrent bulk copies of %5d B (148 CTAs): %lld cycles/MMA, copy rate %.1f B/cycle/SM\n", cb, h[0], h[1] / 1000.0);
+    }
+    for (int N : {48, 96, 128, 192, 256}) {
+        run(3, N, 0, 0, 148, 1);
+        const long long mnc = h[0];
+        run(3, N, 0, 0, 148, 0);
+        printf("N=%3d: %lld cycles/MMA with MN-major operands (LBO 128, SBO 544/512), %lld K-major\n", N, mnc, h[0]);
     }
     return 0;
 }

@@ -62,42 +62,15 @@ def from_qh_ref(q, C):
 
 
 def qp(eng, x):
-    """MMA operand (QH) + its planar float32 copy for the weight-gradient kernel"""
+    """MMA operand tensor (QH)"""
     N, C, D, H, W = x.shape
-    return eng.QP(to_qh_ref(x), N, C, D, H, W, pl=eng.planar_from_ncdhw(x))
+    return eng.QP(to_qh_ref(x), N, C, D, H, W)
 
 
 def qp32(eng, x):
     """float32 QP tensor (conv outputs, gradients w.r.t. activations)"""
     N, C, D, H, W = x.shape
     return eng.QP(to_qp_ref(x), N, C, D, H, W)
-
-
-def shifted_planar(eng, dy, kw, pw, Wx):
-    """test-side restatement of e3b_norm_bwd_args.dy_planar: float16 (N, D, kw, C, H, ceil8(Wx)) x-shifted copies"""
-    N, C, D, H, W = dy.shape
-    out = torch.zeros((N, D, kw, C, H, (Wx + 7) & ~7), device=dy.device, dtype=torch.float16)
-    src = dy.permute(0, 2, 1, 3, 4).to(torch.float16)
-    for dxi in range(kw):
-        sh = dxi - pw
-        lo, hi = max(sh, 0), min(W + sh, Wx)
-        if hi > lo:
-            out[:, :, dxi, :, :, lo:hi] = src[..., lo - sh:hi - sh]
-    return out
-
-
-def qp_dy(eng, dy, kw, pw, Wx):
-    q = qp(eng, dy)
-    q.pl = shifted_planar(eng, dy, kw, pw, Wx)
-    return q
-
-
-def same_operand(pl, q, scale=None):
-    """planar fp16 copy vs the QH operand: the same fp16 values (a gradient's planar copies carry its scale)"""
-    pl = pl.float()
-    if scale is not None:
-        pl = pl * scale[2]
-    return bool(((pl - q.float()).abs() <= 1e-3 * q.float().abs() + 1e-7).all())
 
 
 def assert_close(got, ref, tol, what=''):
@@ -115,9 +88,8 @@ def test_pack_unpack_layout(eng):
     x1 = dyadic((1, 1, 4, 4, 9), 1)
     assert torch.equal(eng.pack_input(x1).t, to_qh_ref(x1))
     x2 = dyadic((2, 19, 3, 4, 5), 2)                      # two 16-channel chunks, the second one ragged
-    qq = eng.pack_input(x2, planar=True)
+    qq = eng.pack_input(x2)
     assert torch.equal(qq.t, to_qh_ref(x2))
-    assert qq.pl.dtype == torch.float16 and torch.equal(qq.pl[..., :5].float(), x2.permute(0, 2, 1, 3, 4))
 
 
 CONV_CASES = [
@@ -341,6 +313,12 @@ WGRAD_CASES = [
     (1, 8, 0, 8, (8, 12, 12), (3, 3, 3), (0, 0, 0)),       # VALID
     (1, 160, 0, 16, (3, 8, 8), (3, 3, 3), (1, 1, 1)),      # > 128 input channels: two M chunks
     (1, 3, 0, 5, (5, 7, 9), (3, 3, 3), (1, 1, 1)),
+    (2, 32, 32, 32, (5, 40, 70), (3, 3, 3), (1, 1, 1)),    # virtual concat at the width of the BASELINE layers, ragged tiles
+    (1, 16, 0, 64, (4, 12, 36), (3, 3, 3), (1, 1, 1)),     # two N chunks
+    (1, 64, 0, 128, (2, 20, 40), (1, 3, 3), (0, 1, 1)),    # planar, 128 output channels
+    (1, 24, 0, 40, (6, 9, 11), (3, 3, 3), (0, 0, 0)),      # VALID, ragged channel counts
+    (1, 32, 0, 16, (1, 33, 65), (1, 3, 3), (0, 1, 1)),     # D = 1 (the 2D path)
+    (1, 256, 0, 32, (2, 6, 6), (3, 3, 3), (1, 1, 1)),      # 8 M chunks, tiny extent
 ]
 
 
@@ -354,8 +332,24 @@ def test_conv_wgrad(eng, case):
     y.backward(dy.double())
     src0 = qp(eng, x[:, :C0].contiguous())
     src1 = qp(eng, x[:, C0:].contiguous()) if C1 else None
-    dw = eng.wgrad(src0, qp_dy(eng, dy, k[2], pad[2], sp[2]), Co, k, pad, tuple(w.shape), src1=src1)
+    dw = eng.wgrad(src0, qp(eng, dy), Co, k, pad, tuple(w.shape), src1=src1)
     assert_close(dw, w.grad, 1e-6, 'wgrad')
+
+
+def test_conv_wgrad_cropped_second_source(eng):
+    """the skip tensor of a VALID network enters the conv as a centre-cropped view (autocrop, unet.py:303-324); any voxel
+    offset is a legal start (16-byte units), including x offsets that are not multiples of 8"""
+    N, C0, C1, Co, sp, off = 1, 16, 16, 32, (4, 10, 12), (2, 3, 5)
+    big = tuple(s + 2 * o for s, o in zip(sp, off))
+    x0 = dyadic((N, C0) + sp, 41, scale=2, lo=-2, hi=3)
+    x1 = dyadic((N, C1) + big, 42, scale=2, lo=-2, hi=3)
+    crop = x1[:, :, off[0]:off[0] + sp[0], off[1]:off[1] + sp[1], off[2]:off[2] + sp[2]]
+    w = torch.zeros((Co, C0 + C1, 3, 3, 3), dtype=torch.float64, device='cuda', requires_grad=True)
+    y = F.conv3d(torch.cat((x0, crop), 1).double(), w, None)
+    dy = dyadic(tuple(y.shape), 43, scale=2, lo=-2, hi=3)
+    y.backward(dy.double())
+    dw = eng.wgrad(qp(eng, x0), qp(eng, dy), Co, (3, 3, 3), (0, 0, 0), tuple(w.shape), src1=qp(eng, x1), off1=off)
+    assert_close(dw, w.grad, 1e-6, 'wgrad cropped concat')
 
 
 @pytest.mark.parametrize('case', [(1, 16, 8, (4, 8, 8), (2, 2, 2)), (2, 32, 16, (3, 8, 16), (1, 2, 2)),
@@ -375,7 +369,7 @@ def test_transposed_conv_backward(eng, case):
     d = dy.view(N, Co, D, s[0], H, s[1], W, s[2]).permute(0, 3, 5, 7, 1, 2, 4, 6).reshape(N, taps, Co, D, H, W)
     dpad = torch.zeros((N, taps, Cp, D, H, W), device='cuda')
     dpad[:, :, :Co] = d
-    dyq = qp_dy(eng, dpad.view(N, taps * Cp, D, H, W), 1, 0, W)
+    dyq = qp(eng, dpad.view(N, taps * Cp, D, H, W))
     wpk = eng.pack_weights(3, w.detach().float(), None, Ci, 0, Co, s)
     dx, _, _ = eng.conv_forward(dyq, wpk, eng.cpad16(Ci), Ci, (1, 1, 1), (0, 0, 0))
     assert_close(from_qp_ref(dx.t, Ci), x.grad, 1e-6, 'convT dgrad')
@@ -417,12 +411,12 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
     yq = qp32(eng, y)
     stats = torch.stack((y.double().sum(dim=(2, 3, 4)), (y.double() ** 2).sum(dim=(2, 3, 4))), dim=-1).contiguous()
     if mode == 0:
-        a, pooled = eng.norm_act(yq, None, None, pool=pool, planar=True)
+        a, pooled = eng.norm_act(yq, None, None, pool=pool, save=True)
         nstate = None
     else:
         nstate = eng.norm_finalize(stats, mode, G, N, C, S, gamma, beta, 1e-5, rm if mode == 2 else None,
                                    rv if mode == 2 else None, 0.1, y.device)
-        a, pooled = eng.norm_act(yq, nstate.scale, nstate.shift, pool=pool, planar=True)
+        a, pooled = eng.norm_act(yq, nstate.scale, nstate.shift, pool=pool, save=True)
     # activations / gradients that feed an MMA are stored rounded to TF32 (2^-11 relative)
     assert a.half and a.t.shape[1] == eng.cpad16(C) // 8
     assert_close(from_qh_ref(a, C), a_ref, 6e-4, 'norm+relu')
@@ -460,14 +454,6 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
     k = torch.log2(dy.scale[1]).item()
     assert k == round(k) and abs(dy.scale[1].item() * dy.scale[2].item() - 1.0) < 1e-6
     assert 2.0 ** 10 < dy.t.float().abs().max().item() <= 2.0 ** 14
-    # z-planar float32 copies for the wgrad kernel: the same values as the fp16 operand (both carry 10 mantissa bits)
-    assert same_operand(a.pl[..., :sp[2]], from_qh_ref(a, C).permute(0, 2, 1, 3, 4))
-    if pool is not None:
-        assert same_operand(pooled.pl[..., :pooled.W], from_qh_ref(pooled, C).permute(0, 2, 1, 3, 4))
-    dy3, _, _, _ = eng._norm_bwd(u, C, qp32(eng, g0), gp=gpq, conv_geom=(3, 1, sp[2]))
-    assert same_operand(dy3.pl[..., :sp[2]], shifted_planar(eng, from_qh_ref(dy3, C), 3, 1, sp[2])[..., :sp[2]], dy3.scale)
-    dy3v, _, _, _ = eng._norm_bwd(u, C, qp32(eng, g0), gp=gpq, conv_geom=(3, 0, sp[2] + 2))
-    assert same_operand(dy3v.pl[..., :sp[2] + 2], shifted_planar(eng, from_qh_ref(dy3v, C), 3, 0, sp[2] + 2)[..., :sp[2] + 2], dy3v.scale)
     if mode:
         assert_close(dgamma, gd.grad, 2e-4, 'dgamma')
         assert_close(dbeta, bd.grad, 2e-4, 'dbeta')
@@ -500,7 +486,6 @@ def test_norm_backward_space_to_depth(eng):
     D, H, W = coarse
     ref = full.view(N, C, D, 2, H, 2, W, 2).permute(0, 3, 5, 7, 1, 2, 4, 6).reshape(N, 8 * C, D, H, W)
     assert_close(from_qh_ref(dy, 8 * C), ref, 6e-4, 's2d')
-    assert same_operand(dy.pl[:, :, 0, :, :, :W], from_qh_ref(dy, 8 * C).permute(0, 2, 1, 3, 4), dy.scale)
 
 
 # ---------------------------------------------------------------------------------------- head

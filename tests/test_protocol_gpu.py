@@ -98,7 +98,9 @@ def test_reference_shape_matrix(e3, dim, n_blocks, planar):
     with torch.no_grad():
         o32 = ref32(copy.deepcopy(m0), x)
     assert rel(out.detach(), o32) < 2e-2
-    grads_within_tf32_noise(m0_with_grads(m0, m), x, g)
+    # (BatchNorm over 2 x a-handful-of voxels: the noise estimate itself scatters, hence the wider factor; a wrong tap,
+    # sign or missing term shows up as O(1))
+    grads_within_tf32_noise(m0_with_grads(m0, m), x, g, factor=6.0, floor=2e-2)
 
 
 def m0_with_grads(m0, m):
@@ -192,16 +194,26 @@ def ref32_nograd(m, x):
 def test_no_grad_forward_keeps_no_training_buffers(e3, monkeypatch):
     """validation under torch.no_grad() must not pay the training footprint (planar copies, pooling indices, fp32 y)"""
     from elektronn3_b200 import engine
-    calls = []
-    real = engine.planar_empty
-    monkeypatch.setattr(engine, 'planar_empty', lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    saves = []
+    real = engine.norm_act
+    monkeypatch.setattr(engine, 'norm_act', lambda *a, **k: (saves.append(bool(k.get('save'))), real(*a, **k))[1])
     m = e3.UNet(n_blocks=2, start_filts=8, normalization='group').cuda().train()
     x = torch.randn(1, 1, 16, 16, 16, device='cuda')
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
     with torch.no_grad():
         m(x)
-    assert not calls
-    m(x).sum().backward()
-    assert calls
+    torch.cuda.synchronize()
+    peak_nograd = torch.cuda.max_memory_allocated() - base
+    assert saves and not any(saves)            # no pooling indices, every fp32 conv output dropped after its norm
+    torch.cuda.reset_peak_memory_stats()
+    out = m(x)
+    torch.cuda.synchronize()
+    peak_grad = torch.cuda.max_memory_allocated() - base
+    out.sum().backward()
+    assert any(saves)
+    assert peak_nograd < peak_grad, (peak_nograd, peak_grad)
 
 
 # ------------------------------------------------------------------------------------------------ devices
