@@ -51,7 +51,9 @@ PRED_DOM_GFLOP_PER_TILE = 2 * 80 ** 3 * 32 * (64 * 27) / 1e9      # up_convs.2.c
 
 
 def dice_loss(logits, target, eps=1e-4):
-    """DiceLoss(apply_softmax=True) of the reference (modules/loss.py:165-233) restated in torch"""
+    """DiceLoss(apply_softmax=True) of the reference (modules/loss.py:165-233) restated in torch (E3B_BENCH_TORCH_LOSS=1:
+    the boundary consumer stays torch, as with the reference's own class); by default the step uses the drop-in
+    elektronn3_b200.DiceLoss (two fused CUDA passes over the logits)."""
     import torch
     prob = logits.softmax(1)
     onehot = torch.zeros_like(prob).scatter_(1, target.unsqueeze(1), 1.0)
@@ -274,6 +276,7 @@ def main():
     # optimizer step run eagerly, so that no NCCL call is captured (capturing it hung on the 2-GPU box in round 1).
     # E3B_BENCH_GRAPH=0: eager launches, N > 1 around stock DistributedDataParallel.
     use_graph = os.environ.get('E3B_BENCH_GRAPH', '1') != '0'
+    criterion = dice_loss if os.environ.get('E3B_BENCH_TORCH_LOSS') == '1' else e3.DiceLoss(apply_softmax=True).to(dev)
     gstep = None
     step_model = model
     params = [p for p in model.parameters()]
@@ -281,7 +284,7 @@ def main():
         if world > 1:                          # same initial weights on every rank (DDP broadcasts them at construction)
             for p in params:
                 dist.broadcast(p.data, 0)
-        gstep = e3.GraphedTrainStep(model, dice_loss, opt if world == 1 else None, BATCH, (BATCH[0],) + BATCH[2:])
+        gstep = e3.GraphedTrainStep(model, criterion, opt if world == 1 else None, BATCH, (BATCH[0],) + BATCH[2:])
     elif world > 1:
         step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
 
@@ -305,7 +308,7 @@ def main():
                 opt.step()
             return loss
         opt.zero_grad(set_to_none=True)
-        loss = dice_loss(step_model(x), t)
+        loss = criterion(step_model(x), t)
         loss.backward()
         opt.step()
         return loss

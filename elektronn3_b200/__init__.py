@@ -7,5 +7,6 @@ include/e3b.h).  There is no CPU or cuDNN fallback.
 from .unet import UNet  # noqa: F401
 from .inference import Predictor  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
+from .loss import DiceLoss  # noqa: F401
 
-__all__ = ['UNet', 'Predictor', 'GraphedTrainStep']
+__all__ = ['UNet', 'Predictor', 'GraphedTrainStep', 'DiceLoss']

@@ -121,6 +121,8 @@ SIGNATURES = {
     'e3b_head': (c_int, [ctypes.POINTER(HeadArgs), c_void_p]),
     'e3b_prob_argmax': (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_float, c_void_p]),
     'e3b_head_bwd': (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),
+    'e3b_dice_fwd': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_i64, c_int, c_float, c_float] + [c_void_p] * 4),
+    'e3b_dice_bwd': (c_int, [c_void_p] * 6 + [c_int, c_int, c_i64, c_int, c_void_p]),
 }
 
 _lib = None

@@ -444,6 +444,17 @@ static PFN_encodeTiled get_encode()
     return fn;
 }
 
+// L2 promotion of the activation tensor maps.  A halo-tile row is 10 voxels = 160 bytes starting 16 bytes before a
+// 128-byte boundary: with 256-byte promotion every such row pulls TWO 256-byte blocks from DRAM (ncu on the dominant layer:
+// 422 MB read for 134 MB of input, profiles/r02_ncu_zs_concat_*.csv).  E3B_TMA_PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B.
+CUtensorMapL2promotion tma_l2_promotion()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("E3B_TMA_PROMO"); v = e ? atoi(e) : 2; if (v < 0 || v > 3) v = 2; }
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 // QP tensor (N, Cq, Da, Ha, Wa, 4) viewed as 5D (W*4, H, D, Cq, N); box = (bx*4, by, bz, bcq, 1).
 // (D, H, W) are the extents of the VIEW starting at `ptr` (a centre-cropped skip tensor is a sub-box of
 // its allocation: out-of-view voxels read as 0, exactly like zero padding of the cropped tensor);
@@ -460,7 +471,7 @@ int make_qp_tensor_map(CUtensorMap* map, const float* ptr, int N, int Cq, int D,
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (box[0] > 256 || box[1] > 256 || box[2] > 256) return set_error("TMA box dimension > 256");
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tma_l2_promotion(),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;

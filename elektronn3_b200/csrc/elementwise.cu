@@ -344,19 +344,25 @@ struct VoxIn {
     unsigned char slot;
 };
 
+// STREAM: last use of the gradient tensors (the apply pass): evict-first loads.  The reduce pass loads them with the
+// default policy so that the apply pass, which walks the tensor in the opposite order, finds the tail in the 126 MB L2.
+template <bool STREAM>
+E3B_DEVINL float4 ld_grad(const float4* p) { return STREAM ? __ldcs(p) : __ldg(p); }
+
+template <bool STREAM>
 E3B_DEVINL void load_vox(const NormBwdDev& p, size_t o, int n, int cq, int z, int yy, int x, VoxIn& in)
 {
     in.y = p.y[o];
-    if (p.g0) in.g0 = __ldcs(p.g0 + o);
+    if (p.g0) in.g0 = ld_grad<STREAM>(p.g0 + o);
     if (p.g1) {
         if (!p.g1_crop) {
-            in.g1 = __ldcs(p.g1 + o);
+            in.g1 = ld_grad<STREAM>(p.g1 + o);
         } else {
             // backward of autocrop's slice of the skip tensor: zero outside the cropped box
             const int zc = z - p.g1_od, yc = yy - p.g1_oh, xc = x - p.g1_ow;
             in.g1 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (zc >= 0 && zc < p.g1_D && yc >= 0 && yc < p.g1_H && xc >= 0 && xc < p.g1_W)
-                in.g1 = __ldcs(p.g1 + ((((size_t)n * p.Cq + cq) * p.g1_D + zc) * p.g1_H + yc) * p.g1_W + xc);
+                in.g1 = ld_grad<STREAM>(p.g1 + ((((size_t)n * p.Cq + cq) * p.g1_D + zc) * p.g1_H + yc) * p.g1_W + xc);
         }
     }
     if (p.gp) {
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p
             const int v = v0 + j * stride;
             if (v < total) {
                 const int z = v / HW, r = v - z * HW, yy = r / p.W, x = r - yy * p.W;
-                load_vox(p, base + v, n, cq, z, yy, x, in[j]);
+                load_vox<false>(p, base + v, n, cq, z, yy, x, in[j]);
             }
         }
 #pragma unroll
@@ -600,7 +606,9 @@ __global__ void __launch_bounds__(1024) norm_bwd_finalize_block_kernel(
 static constexpr int kAppVpt = 1;
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
 {
-    const int cq = blockIdx.y, n = blockIdx.z;
+    // blocks walk the tensor BACKWARDS: the reduce pass that ran just before read it forwards, its tail is still in L2
+    const int cq = gridDim.y - 1 - blockIdx.y, n = gridDim.z - 1 - blockIdx.z;
+    const int bx = gridDim.x - 1 - blockIdx.x;
     const size_t nc = ((size_t)n * p.Cq + cq) * 4;
     float4 mu, rs, sc, sh, m1, m2;
     load_nc4(p.mean, nc, mu, 0.f); load_nc4(p.rstd, nc, rs, 1.f);
@@ -613,10 +621,10 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
         ga.z = c + 2 < p.C ? p.gamma[c + 2] : 0.f; ga.w = c + 3 < p.C ? p.gamma[c + 3] : 0.f;
     }
     const int HWg = p.Hg * p.Wg, Sg = p.Dg * HWg;
-    const int v0 = blockIdx.x * (256 * kAppVpt) + threadIdx.x;
+    const int v0 = bx * (256 * kAppVpt) + threadIdx.x;
     // fp16 range: dy is stored multiplied by 2^k (undone by the dgrad epilogue through dy_scale[2])
     const float dscale = dy_scale_from_bound(p.dy_scale[0]);
-    if (blockIdx.x == 0 && cq == 0 && n == 0 && threadIdx.x == 0) { p.dy_scale[1] = dscale; p.dy_scale[2] = 1.f / dscale; }
+    if (bx == 0 && cq == 0 && n == 0 && threadIdx.x == 0) { p.dy_scale[1] = dscale; p.dy_scale[2] = 1.f / dscale; }
     VoxIn in[kAppVpt];
     int zs[kAppVpt], ys[kAppVpt], xs[kAppVpt];
 #pragma unroll
@@ -627,7 +635,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
         ys[j] = hw / p.Wg; xs[j] = hw - ys[j] * p.Wg;
         if (v < Sg && zs[j] < p.D && ys[j] < p.H && xs[j] < p.W) {
             const size_t ov = ((((size_t)n * p.Cq + cq) * p.D + zs[j]) * p.H + ys[j]) * p.W + xs[j];
-            load_vox(p, ov, n, cq, zs[j], ys[j], xs[j], in[j]);
+            load_vox<true>(p, ov, n, cq, zs[j], ys[j], xs[j], in[j]);
         }
     }
 #pragma unroll
@@ -699,14 +707,16 @@ E3B_DEVINL void load_bwd_consts(const NormBwdDev& p, int n, int cq, BwdConsts& c
 // grid: (chunks of 256 x-groups, Cq, N)
 __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev p)
 {
-    const int cq = blockIdx.y, n = blockIdx.z;
+    // blocks walk the tensor BACKWARDS: the reduce pass that ran just before read it forwards, its tail is still in L2
+    const int cq = gridDim.y - 1 - blockIdx.y, n = gridDim.z - 1 - blockIdx.z;
+    const int bx = gridDim.x - 1 - blockIdx.x;
     BwdConsts c;
     load_bwd_consts(p, n, cq, c, true);
     const int Wg = p.W >> 2;
     const int total = p.D * p.H * Wg;
-    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int t = bx * 256 + threadIdx.x;
     const float dscale = dy_scale_from_bound(p.dy_scale[0]);
-    if (blockIdx.x == 0 && cq == 0 && n == 0 && threadIdx.x == 0) { p.dy_scale[1] = dscale; p.dy_scale[2] = 1.f / dscale; }
+    if (bx == 0 && cq == 0 && n == 0 && threadIdx.x == 0) { p.dy_scale[1] = dscale; p.dy_scale[2] = 1.f / dscale; }
     if (t >= total) return;
     const int row = t / Wg;
     const int xg = t - row * Wg;
@@ -714,7 +724,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev
     const size_t ov = (((size_t)n * p.Cq + cq) * p.D * p.H + row) * (size_t)p.W + x0;
     VoxIn in[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) load_vox(p, ov + j, n, cq, z, yy, x0 + j, in[j]);
+    for (int j = 0; j < 4; j++) load_vox<true>(p, ov + j, n, cq, z, yy, x0 + j, in[j]);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         float4 dr, xh;

@@ -19,6 +19,7 @@ int num_sms();            // of the current device
 int conv_ntile_width(int npad_total);
 int make_qp_tensor_map(CUtensorMap* map, const float* ptr, int N, int Cq, int D, int H, int W, int Da, int Ha, int Wa,
                        int bx, int by, int bz, int bcq);
+CUtensorMapL2promotion tma_l2_promotion();
 int conv_debug_read(unsigned long long* out16, int reset);
 int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream);
 int conv_zs_supported(int C0, int C1, int n_total, int kd, int kh, int kw, int scatter);

@@ -332,7 +332,7 @@ static int make_qh_map(CUtensorMap* map, const void* ptr, int N, int P, int D, i
     dims[4] = (cuuint64_t)N; strides[3] = sn; box[4] = 1;
     for (int i = 0; i < 4; i++) if (box[i] > 256) return set_error("wgrad: TMA box dimension > 256");
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tma_l2_promotion(),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;

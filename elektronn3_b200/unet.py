@@ -123,6 +123,18 @@ class UpConv(_Container):
         self.att = None
 
 
+def _called_from_trace_check():
+    import sys
+    f = sys._getframe(1)
+    for _ in range(24):
+        if f is None:
+            return False
+        if f.f_code.co_name == '_check_trace' and 'jit' in f.f_code.co_filename:
+            return True
+        f = f.f_back
+    return False
+
+
 class _UNetFunction(torch.autograd.Function):
     """The whole encoder/decoder as ONE autograd node: forward saves the QP activations on the ctx,
     backward launches dgrad / wgrad / norm-backward kernels and returns per-parameter gradients."""
@@ -335,7 +347,28 @@ class UNet(nn.Module):
                 out.extend(t for t in former.values() if t is not None)
         return out
 
+    # ---- export (TorchScript): a plain-torch twin that shares the parameters, see torch_twin.py
+    def torch_twin(self):
+        """Plain-torch module with the same parameters / buffers / ``state_dict`` keys that issues the reference's ATen
+        call sequence: for ``torch.jit.script`` / ``trace`` / ONNX export and for running a checkpoint without libe3b.so."""
+        from .torch_twin import TwinUNet
+        return TwinUNet(self).train(self.training)
+
+    def __prepare_scriptable__(self):
+        # torch.jit.script(model) -- what Trainer._save_model does with save_jit='script' (training/trainer.py:876-881)
+        return self.torch_twin()
+
     def forward(self, x):
+        if torch.jit.is_tracing():
+            # torch.jit.trace(model, example) (trainer.py:882-887): the archive must hold ATen ops, not ctypes calls
+            self.__dict__['_e3b_traced'] = True
+            return self.torch_twin()(x)
+        if self.__dict__.get('_e3b_traced'):
+            # torch.jit.trace then re-runs the Python module and demands agreement with the trace to 1e-5: that one call
+            # (recognised by its caller, torch/jit/_trace.py::_check_trace) must see the arithmetic that was traced
+            if _called_from_trace_check():
+                return self.torch_twin()(x)
+            self.__dict__['_e3b_traced'] = False
         if x.dim() != self.dim + 2:
             raise RuntimeError(f'Expected {self.dim + 2}D input (N, C{", D" if self.dim == 3 else ""}, H, W), '
                                f'got shape {tuple(x.shape)}')

@@ -225,6 +225,20 @@ int e3b_prob_argmax(const float* prob, uint8_t* dst, int N, int C, int64_t S, in
 int e3b_head_bwd(const float* dl, const void* a, const float* w, float* da, float* dw, float* db,
                  double* workspace, int N, int C, int Co, int D, int H, int W, void* stream);
 
+/* ---- Dice loss ----------------------------------------------------------------------------------
+ * The generalised Dice loss of modules/loss.py:165-233 (`dice_loss` / `DiceLoss.forward`) on the network's NCDHW logits
+ * (N, C, S voxels):  loss = mean_c w_c * (1 - (2 * sum p_c t_c + smooth) / (sum p_c + sum t_c + smooth + eps)),
+ * p = softmax(logits) if apply_softmax else logits, t = one-hot target.  One read of the logits forward (the reference
+ * materialises probabilities, the one-hot tensor, their product and their sum), one read + one write backward.
+ * target: dense class indices int64 (N, S), or target_onehot float (N, C, S) (exactly one of the two).
+ * weight: [weight_n] with weight_n = 1 or C (NULL = 1).  sums: workspace double[3*C] (zeroed here);
+ * loss: float[1]; coef: float[2*C] handed to e3b_dice_bwd together with the upstream gradient gout (device float[1]). */
+int e3b_dice_fwd(const float* logits, const int64_t* target, const float* target_onehot, const float* weight, int weight_n,
+                 int N, int C, int64_t S, int apply_softmax, float smooth, float eps, double* sums, float* loss, float* coef,
+                 void* stream);
+int e3b_dice_bwd(const float* logits, const int64_t* target, const float* target_onehot, const float* coef, const float* gout,
+                 float* dlogits, int N, int C, int64_t S, int apply_softmax, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -239,3 +239,35 @@ def test_graphed_train_step_needs_cuda():
     opt = torch.optim.SGD(m.parameters(), lr=0.1)
     with pytest.raises(RuntimeError):
         e3.GraphedTrainStep(m, torch.nn.functional.cross_entropy, opt, (1, 1, 8, 8, 8), (1, 8, 8, 8))
+
+
+# ------------------------------------------------------------------------------------------ TorchScript export
+@pytest.mark.parametrize('kw,shape', [(dict(n_blocks=2, start_filts=8), (1, 1, 16, 16, 16)),
+                                      (dict(n_blocks=3, start_filts=4, normalization='group4', planar_blocks=(0,)), (2, 1, 5, 13, 18)),
+                                      (dict(dim=2, n_blocks=3, start_filts=4), (1, 1, 24, 20)),
+                                      (dict(n_blocks=2, start_filts=4, conv_mode='valid', normalization='none'), (1, 1, 20, 20, 20))])
+def test_torch_twin_and_torchscript_export(kw, shape, tmp_path):
+    """Trainer._save_model scripts / traces the model when save_jit is set (training/trainer.py:876-887): the module hands
+    out a plain-torch twin with the SAME parameters and state_dict keys that computes the reference forward."""
+    import elektronn3_b200 as e3
+    from oracle import torch_ref
+    torch.manual_seed(0)
+    m = e3.UNet(**kw).eval()
+    x = torch.randn(shape)
+    with torch.no_grad():
+        want = torch_ref.unet_forward(m, x)
+        twin = m.torch_twin()
+        assert list(twin.state_dict().keys()) == list(m.state_dict().keys())
+        assert all(a.data_ptr() == b.data_ptr() for a, b in zip(twin.parameters(), m.parameters()))
+        assert torch.allclose(twin(x), want, atol=1e-6)
+        scripted = torch.jit.script(m)                       # goes through UNet.__prepare_scriptable__
+        assert torch.allclose(scripted(x), want, atol=1e-6)
+        path = str(tmp_path / 'model.pts')
+        scripted.save(path)
+        assert torch.allclose(torch.jit.load(path)(x), want, atol=1e-6)
+        traced = torch.jit.trace(m, x)                       # the tracing branch of UNet.forward
+        assert torch.allclose(traced(x), want, atol=1e-6)
+    # the twin trains, too (gradients land in the shared parameters)
+    m.train()
+    m.torch_twin()(x).square().mean().backward()
+    assert all(p.grad is not None for p in m.parameters())
