@@ -77,6 +77,14 @@ class NormBwdArgs(ctypes.Structure):
     ]
 
 
+class PackJob(ctypes.Structure):
+    """struct e3b_pack_job"""
+    _fields_ = [
+        ('w', c_void_p), ('scale', c_void_p), ('wscale', c_void_p), ('dst', c_void_p),
+        ('mode', c_i32), ('C0', c_i32), ('C1', c_i32), ('Co', c_i32), ('kd', c_i32), ('kh', c_i32), ('kw', c_i32),
+    ]
+
+
 class HeadArgs(ctypes.Structure):
     """struct e3b_head_args"""
     _fields_ = [
@@ -105,6 +113,9 @@ SIGNATURES = {
     'e3b_gather_tiles': (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
     'e3b_packed_weight_floats': (c_i64, [c_int] * 7),
     'e3b_pack_weights': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    'e3b_pack_job_table_bytes': (c_i64, [c_int]),
+    'e3b_pack_jobs_fill': (c_int, [ctypes.POINTER(PackJob), c_int, c_void_p, ctypes.POINTER(c_i64)]),
+    'e3b_pack_weights_batched': (c_int, [c_void_p, c_int, c_i64, c_void_p]),
     'e3b_conv': (c_int, [ctypes.POINTER(ConvArgs), c_void_p]),
     'e3b_conv_variant': (c_int, [c_int] * 7),
     'e3b_debug_zs_read': (c_int, [c_void_p, c_int]),

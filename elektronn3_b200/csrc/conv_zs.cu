@@ -91,8 +91,9 @@ struct ConvZsParams {
     int tiles_x, tiles_y;
     long long total_L;           // (n, y tile, x tile) chains x Do output planes
     int chunks0, chunks1;        // 16-channel K chunks of source 0 / 1
-    int NTW, R, SA;              // columns per output plane, ring blocks, plane-tile stages
+    int NTW, R, SA;              // columns per output plane (of one N tile), ring blocks, plane-tile stages
     int ZB;                      // input planes per stage
+    int ntiles;                  // N tiles of NTW columns: the grid is cut into ntiles groups of CTAs, one tile each
     uint32_t a0_bytes, a_stage_bytes, w_bytes, w_piece_bytes;
     const float* bias; int n_bias;
     float* dst0; int cq0; float* dst1; int cq0_alloc, cq1_alloc;
@@ -107,7 +108,7 @@ struct ConvZsParams {
 
 
 // this warp's statistics of sample n -> global [N][Cstat][2] (fp64 atomics), accumulators cleared
-E3B_DEVINL void zs_flush_stats(const ConvZsParams& p, int n, int lane, int bcol, bool reg_stats, float* rs, float* rq,
+E3B_DEVINL void zs_flush_stats(const ConvZsParams& p, int n, int co0, int lane, int bcol, bool reg_stats, float* rs, float* rq,
                                double* acc_s, double* acc_q)
 {
     if (reg_stats) {
@@ -121,7 +122,7 @@ E3B_DEVINL void zs_flush_stats(const ConvZsParams& p, int n, int lane, int bcol,
     }
 #pragma unroll
     for (int i = 0; i < 5; i++) {
-        const int ch = i * 16 + bcol;
+        const int ch = co0 + i * 16 + bcol;
         if (lane < 16 && i * 16 < p.NTW && ch < p.Cstat) {
             atomicAdd(p.stats + ((size_t)n * p.Cstat + ch) * 2, acc_s[i]);
             atomicAdd(p.stats + ((size_t)n * p.Cstat + ch) * 2 + 1, acc_q[i]);
@@ -249,8 +250,11 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot + (uint32_t)chain * (512u / CHAINS);      // this chain's half of the columns
 
+    // N tiles (wide outputs): CTA group `ntile` computes output columns [ntile * NTW, (ntile + 1) * NTW) of the whole volume
+    const int G = (int)gridDim.x / p.ntiles;
+    const int ntile = (int)blockIdx.x / G, bloc = (int)blockIdx.x % G;
     // this CTA's contiguous run of the linear (chain, output plane) space, cut into one contiguous part per chain
-    const long long C0 = p.total_L * blockIdx.x / gridDim.x, C1 = p.total_L * (blockIdx.x + 1) / gridDim.x;
+    const long long C0 = p.total_L * bloc / G, C1 = p.total_L * (bloc + 1) / G;
     const long long L0 = C0 + (C1 - C0) * chain / CHAINS, L1 = C0 + (C1 - C0) * (chain + 1) / CHAINS;
 
     if (role == 0) {
@@ -258,7 +262,8 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         if (lane == 0) {
             if (chain == 0) {                        // the weight image is shared by the chains
                 mbar_arrive_expect_tx(w_full, p.w_bytes);
-                for (uint32_t o = 0; o < p.w_bytes; o += p.w_piece_bytes) bulk_load_1d(w_base + o, p.wpk + o, p.w_piece_bytes, w_full);
+                const uint8_t* wsrc = p.wpk + (size_t)ntile * p.w_bytes;
+                for (uint32_t o = 0; o < p.w_bytes; o += p.w_piece_bytes) bulk_load_1d(w_base + o, wsrc + o, p.w_piece_bytes, w_full);
             }
             uint32_t sa = 0, pa = 0;
             uint32_t ws = 0, free_par = 0;           // ring slot of the next output plane to acquire, its barriers' parities
@@ -413,7 +418,8 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         // butterfly transpose-reduce leaves column (bit-reversed low nibble of the lane) in lanes 0..15
         const int bcol = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
-        for (int i = etid; i < kZsMaxN; i += 256) bias_s[i] = (p.bias && i < p.n_bias) ? p.bias[i] : 0.f;
+        const int co0 = ntile * p.NTW;          // first output column (channel) of this CTA's N tile
+        for (int i = etid; i < kZsMaxN; i += 256) bias_s[i] = (p.bias && co0 + i < p.n_bias) ? p.bias[co0 + i] : 0.f;
         // clear the whole ring once, then hand every block to the issuer
         if (eg == 0) {
             for (int c = 0; c < p.R * p.NTW; c += 16) tmem_st16_zero(lane_base + (uint32_t)c);
@@ -440,7 +446,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         for (long long L = L0; L < L1;) {
             const ZsPiece g = zs_piece(p, L, L1);
             if (p.stats && g.n != cur_n) {
-                if (cur_n >= 0) zs_flush_stats(p, cur_n, lane, bcol, reg_stats, rs, rq, acc_s, acc_q);
+                if (cur_n >= 0) zs_flush_stats(p, cur_n, co0, lane, bcol, reg_stats, rs, rq, acc_s, acc_q);
                 cur_n = g.n;
             }
             const int y = g.y0 + ry, x = g.x0 + rx;
@@ -496,7 +502,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                                 // operand tensor (QH): 16 columns = two 16-byte units (planes cg/8, cg/8 + 1)
 #pragma unroll
                                 for (int j8 = 0; j8 < 2; j8++) {
-                                    const int hpl = (cg >> 3) + j8;
+                                    const int hpl = ((co0 + cg) >> 3) + j8;
                                     if (hpl < p.cq0_alloc) {
                                         const uint2 lo = pack_half4(v[j8 * 8], v[j8 * 8 + 1], v[j8 * 8 + 2], v[j8 * 8 + 3]);
                                         const uint2 hi = pack_half4(v[j8 * 8 + 4], v[j8 * 8 + 5], v[j8 * 8 + 6], v[j8 * 8 + 7]);
@@ -506,7 +512,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                             } else {
 #pragma unroll
                                 for (int j4 = 0; j4 < 4; j4++) {
-                                    const int cq = (cg >> 2) + j4;
+                                    const int cq = ((co0 + cg) >> 2) + j4;
                                     const float4 val = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
                                     if (cq < p.cq0) {
                                         if (cq < p.cq0_alloc) reinterpret_cast<float4*>(p.dst0)[o0 + (size_t)cq * cstride + zoff] = val;
@@ -546,7 +552,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             }
             L += g.zb - g.za;
         }
-        if (p.stats && cur_n >= 0) zs_flush_stats(p, cur_n, lane, bcol, reg_stats, rs, rq, acc_s, acc_q);
+        if (p.stats && cur_n >= 0) zs_flush_stats(p, cur_n, co0, lane, bcol, reg_stats, rs, rq, acc_s, acc_q);
         ZP_ACC(6, t_all);
         if (p.prof && (ew & 3) == 0 && lane == 0) for (int i = 6; i < 12; i++) atomicAdd(&g_zs_prof[i], prof[i]);
     }
@@ -618,15 +624,23 @@ static bool zs_plan(int C0, int C1, int n_total, ZsPlan* out)
     return false;
 }
 
+// columns per N tile: the whole padded output width when its weight image fits shared memory, else tiles of 32 columns
+// (N = 3 * 32 = 96 per MMA); 0: this convolution is not served by the z-stacked kernel
+int conv_zs_ntile(int C0, int C1, int n_total)
+{
+    if (n_total % 16 || n_total < 16 || C0 <= 0 || C1 < 0) return 0;
+    if (n_total <= kZsMaxN && zs_plan(C0, C1, n_total, nullptr)) return n_total;
+    if (n_total % 32 == 0 && n_total <= 512 && zs_plan(C0, C1, 32, nullptr)) return 32;
+    return 0;
+}
+
 int conv_zs_supported(int C0, int C1, int n_total, int kd, int kh, int kw, int scatter)
 {
     static int disabled = -1;
     if (disabled < 0) { const char* e = getenv("E3B_CONV_VARIANT"); disabled = (e && atoi(e) == 0) ? 1 : 0; }
     if (disabled) return 0;
     if (scatter || kd != 3 || kh != 3 || kw != 3) return 0;
-    if (n_total % 16 || n_total < 16 || n_total > 80) return 0;
-    if (C0 <= 0 || C1 < 0) return 0;
-    return zs_plan(C0, C1, n_total, nullptr) ? 1 : 0;
+    return conv_zs_ntile(C0, C1, n_total) > 0 ? 1 : 0;
 }
 
 int conv_zs_prof_read(unsigned long long* out16, int reset)
@@ -657,8 +671,9 @@ int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream)
     p.Do = a->D + 2 * a->pd - 2; p.Ho = a->H + 2 * a->ph - 2; p.Wo = a->W + 2 * a->pw - 2;
     if (p.Do <= 0 || p.Ho <= 0 || p.Wo <= 0) return set_error("conv: empty output");
     p.pd = a->pd; p.ph = a->ph; p.pw = a->pw;
-    p.NTW = a->n_total;
-    if (p.NTW % 16 || p.NTW < 16 || p.NTW > 80) return set_error("conv(z-stacked): n_total %d not in 16..80", a->n_total);
+    p.NTW = conv_zs_ntile(a->C0, a->src1 ? a->C1 : 0, a->n_total);
+    if (p.NTW <= 0) return set_error("conv(z-stacked): output width %d / input channels %d not supported", a->n_total, a->C0);
+    p.ntiles = a->n_total / p.NTW;
     p.HX = kZsTX + 2; p.HY = kZsTY + 2;
     p.tiles_x = (p.Wo + kZsTX - 1) / kZsTX; p.tiles_y = (p.Ho + kZsTY - 1) / kZsTY;
     p.total_L = (long long)a->N * p.tiles_x * p.tiles_y * p.Do;
@@ -717,8 +732,11 @@ int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream)
         memset(g_zs_dbg_host, 0, 16 * 148 * sizeof(uint32_t));
         p.dbg = dbg_dev;
     }
-    long long grid = p.total_L < num_sms() ? p.total_L : num_sms();
+    long long grid = num_sms() / p.ntiles;                            // CTAs per N tile
+    if (grid > p.total_L) grid = p.total_L;
+    if (grid < 1) grid = 1;
     if (const char* e = getenv("E3B_ZS_GRID")) { const int gcap = atoi(e); if (gcap > 0 && gcap < grid) grid = gcap; }   // tests: long runs on small volumes
+    grid *= p.ntiles;
     if (pl.chains == 2) conv_zs_kernel<2><<<(int)grid, kZsThreads2, smem, stream>>>(m0, m1, p);
     else conv_zs_kernel<1><<<(int)grid, kZsThreads1, smem, stream>>>(m0, m1, p);
     return check_launch("conv_zs");

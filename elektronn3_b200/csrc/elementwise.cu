@@ -82,8 +82,9 @@ static PackDims pack_dims(int mode, int C0, int C1, int Co, int kd, int kh, int 
     PackDims d;
     const int t = kd * kh * kw;
     switch (mode) {
-    case 4: d.ktot = cpad16(C0) + (C1 > 0 ? cpad16(C1) : 0); d.ntot = cpad16(Co); d.taps = t; d.NT = d.ntot; return d;
-    case 5: d.ktot = cpad16(Co); d.ntot = cpad16(cpad8(C0) + (C1 > 0 ? cpad8(C1) : 0)); d.taps = t; d.NT = d.ntot; return d;
+    // z-stacked images: one image per N tile (conv_zs_ntile: the whole width, or tiles of 32 columns)
+    case 4: d.ktot = cpad16(C0) + (C1 > 0 ? cpad16(C1) : 0); d.ntot = cpad16(Co); d.taps = t; d.NT = conv_zs_ntile(C0, C1, d.ntot); return d;
+    case 5: d.ktot = cpad16(Co); d.ntot = cpad16(cpad8(C0) + (C1 > 0 ? cpad8(C1) : 0)); d.taps = t; d.NT = conv_zs_ntile(Co, 0, d.ntot); return d;
     case 0: d.ktot = cpad16(C0) + (C1 > 0 ? cpad16(C1) : 0); d.ntot = cpad16(Co); d.taps = t; break;
     case 1: d.ktot = cpad16(Co); d.ntot = cpad16(cpad8(C0) + (C1 > 0 ? cpad8(C1) : 0)); d.taps = t; break;
     case 2: d.ktot = cpad16(C0); d.ntot = t * cpad16(Co); d.taps = 1; break;
@@ -93,60 +94,90 @@ static PackDims pack_dims(int mode, int C0, int C1, int Co, int kd, int kh, int 
     return d;
 }
 
+// one element of a packed weight image (shared by the single-image and the batched kernel)
+E3B_DEVINL __half pack_weight_element(int mode, const float* __restrict__ w, const float* __restrict__ scale, float ws, int C0, int C1,
+                                      int Co, int tu, const PackDims& d, size_t i)
+{
+    const int C0p16 = cpad16(C0), C0p8 = cpad8(C0), Cop8 = cpad8(Co), Cop16 = cpad16(Co);
+    const int nchunks = d.ktot / 16;
+    size_t r = i;
+    const int k8 = (int)(r % 8); r /= 8;
+    int nn, kq, tap, chunk, nt = 0;
+    if (mode >= 4) {
+        // z-stacked image (conv_zs.cu): [N tile][chunk16][tap (dy,dx) 9][kq 2][N3 = (j, n)][8], block j holds z tap dz = 2 - j
+        const int n3 = (int)(r % (3 * d.NT)); r /= (size_t)(3 * d.NT);
+        kq = (int)(r % 2); r /= 2;
+        const int t9 = (int)(r % 9); r /= 9;
+        chunk = (int)(r % nchunks);
+        nt = (int)(r / nchunks);
+        nn = n3 % d.NT;
+        tap = (2 - n3 / d.NT) * 9 + t9;
+    } else {
+        nn = (int)(r % d.NT); r /= d.NT;
+        kq = (int)(r % 2); r /= 2;
+        tap = (int)(r % d.taps); r /= d.taps;
+        chunk = (int)(r % nchunks);
+        nt = (int)(r / nchunks);
+    }
+    const int k = chunk * 16 + kq * 8 + k8;
+    const int n = nt * d.NT + nn;
+    float v = 0.f;
+    if (mode == 0 || mode == 4) {
+        // K space [pad16(C0) | pad16(C1)] (the operand tensors of the two sources), N = output channel
+        int ci = -1;
+        if (k < C0p16) { if (k < C0) ci = k; }
+        else if (k - C0p16 < C1) ci = C0 + k - C0p16;
+        if (ci >= 0 && n < Co) {
+            v = w[((size_t)n * (C0 + C1) + ci) * d.taps + tap];
+            if (scale) v *= scale[n];
+        }
+    } else if (mode == 1 || mode == 5) {
+        // K = output channel of the forward conv, N space [pad8(C0) | pad8(C1)] (the fp32 QP gradient outputs)
+        int ci = -1;
+        if (n < C0p8) { if (n < C0) ci = n; }
+        else if (n - C0p8 < C1) ci = C0 + n - C0p8;
+        if (ci >= 0 && k < Co) v = w[((size_t)k * (C0 + C1) + ci) * d.taps + (d.taps - 1 - tap)];
+    } else if (mode == 2) {
+        const int t = n / Cop16, co = n % Cop16;
+        if (k < C0 && co < Co) v = w[((size_t)k * Co + co) * tu + t];
+    } else {
+        const int t = k / Cop8, co = k % Cop8;
+        if (t < tu && n < C0 && co < Co) v = w[((size_t)n * Co + co) * tu + t];
+    }
+    return __float2half_rn(v * ws);
+}
+
 __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, const float* __restrict__ scale,
                                     const float* __restrict__ wscale, __half* __restrict__ dst, int C0, int C1, int Co, int tu,
                                     PackDims d)
 {
     const float ws = wscale ? __ldg(wscale) : 1.f;       // power of two: max|w| -> [1, 2), undone in the conv epilogue
     const size_t total = (size_t)d.ktot * d.ntot * d.taps;
-    const int C0p16 = cpad16(C0), C0p8 = cpad8(C0), Cop8 = cpad8(Co), Cop16 = cpad16(Co);
-    const int nchunks = d.ktot / 16;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        size_t r = i;
-        const int k8 = (int)(r % 8); r /= 8;
-        int nn, kq, tap, chunk, nt = 0;
-        if (mode >= 4) {
-            // z-stacked image (conv_zs.cu): [chunk16][tap (dy,dx) 9][kq 2][N3 = (j, n)][8], block j holds z tap dz = 2 - j
-            const int n3 = (int)(r % (3 * d.NT)); r /= (size_t)(3 * d.NT);
-            kq = (int)(r % 2); r /= 2;
-            const int t9 = (int)(r % 9);
-            chunk = (int)(r / 9);
-            nn = n3 % d.NT;
-            tap = (2 - n3 / d.NT) * 9 + t9;
-        } else {
-            nn = (int)(r % d.NT); r /= d.NT;
-            kq = (int)(r % 2); r /= 2;
-            tap = (int)(r % d.taps); r /= d.taps;
-            chunk = (int)(r % nchunks);
-            nt = (int)(r / nchunks);
-        }
-        const int k = chunk * 16 + kq * 8 + k8;
-        const int n = nt * d.NT + nn;
-        float v = 0.f;
-        if (mode == 0 || mode == 4) {
-            // K space [pad16(C0) | pad16(C1)] (the operand tensors of the two sources), N = output channel
-            int ci = -1;
-            if (k < C0p16) { if (k < C0) ci = k; }
-            else if (k - C0p16 < C1) ci = C0 + k - C0p16;
-            if (ci >= 0 && n < Co) {
-                v = w[((size_t)n * (C0 + C1) + ci) * d.taps + tap];
-                if (scale) v *= scale[n];
-            }
-        } else if (mode == 1 || mode == 5) {
-            // K = output channel of the forward conv, N space [pad8(C0) | pad8(C1)] (the fp32 QP gradient outputs)
-            int ci = -1;
-            if (n < C0p8) { if (n < C0) ci = n; }
-            else if (n - C0p8 < C1) ci = C0 + n - C0p8;
-            if (ci >= 0 && k < Co) v = w[((size_t)k * (C0 + C1) + ci) * d.taps + (d.taps - 1 - tap)];
-        } else if (mode == 2) {
-            const int t = n / Cop16, co = n % Cop16;
-            if (k < C0 && co < Co) v = w[((size_t)k * Co + co) * tu + t];
-        } else {
-            const int t = k / Cop8, co = k % Cop8;
-            if (t < tu && n < C0 && co < Co) v = w[((size_t)n * Co + co) * tu + t];
-        }
-        dst[i] = __float2half_rn(v * ws);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = pack_weight_element(mode, w, scale, ws, C0, C1, Co, tu, d, i);
+}
+
+// All weight images of a network in ONE launch (a training step re-packs every image: 23 launches for BASELINE cfg 2):
+// blocks of 256 elements, each block finds its job in the (block-prefix-summed) job table.
+struct PackJobDev {
+    const float* w; const float* scale; const float* wscale; __half* dst;
+    int mode, C0, C1, Co, tu, first_block;
+    PackDims d;
+    unsigned long long total;
+};
+
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJobDev* __restrict__ jobs, int njobs)
+{
+    int lo = 0, hi = njobs - 1;                           // last job whose first_block <= blockIdx.x
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
     }
+    const PackJobDev j = jobs[lo];
+    const size_t i = (size_t)(blockIdx.x - j.first_block) * 256 + threadIdx.x;
+    if (i >= j.total) return;
+    const float ws = j.wscale ? __ldg(j.wscale) : 1.f;
+    j.dst[i] = pack_weight_element(j.mode, j.w, j.scale, ws, j.C0, j.C1, j.Co, j.tu, j.d, i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -740,6 +771,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev
 // ------------------------------------------------------------------------------------------------
 static constexpr int kHeadMaxCo = 16;
 
+// CO: compile-time bound on the output channels (4 for the usual 2..4 classes: no predicated-off FMA slots)
+template <int CO>
 __global__ void __launch_bounds__(256) head_kernel(const e3b_head_args p, int Cq)
 {
     extern __shared__ float sw[];      // [Co][Cq*4] weights then [Co] bias
@@ -766,13 +799,13 @@ __global__ void __launch_bounds__(256) head_kernel(const e3b_head_args p, int Cq
         const int zi = (p.flip & 1) ? p.D - 1 - (z + p.c0_d) : z + p.c0_d, yi = (p.flip & 2) ? p.H - 1 - (y + p.c0_h) : y + p.c0_h,
                   xi = (p.flip & 4) ? p.W - 1 - (x + p.c0_w) : x + p.c0_w;
         const size_t vin = ((size_t)zi * p.H + yi) * p.W + xi;
-        float acc[kHeadMaxCo];
+        float acc[CO];
 #pragma unroll
-        for (int co = 0; co < kHeadMaxCo; co++) acc[co] = co < p.Co ? sw[p.Co * Cp + co] : 0.f;
+        for (int co = 0; co < CO; co++) acc[co] = co < p.Co ? sw[p.Co * Cp + co] : 0.f;
         for (int cq = 0; cq < Cq; cq++) {
             const float4 v = unpack_half4(a[qh_index(n, Ch, cq, S, vin)]);
 #pragma unroll
-            for (int co = 0; co < kHeadMaxCo; co++) {
+            for (int co = 0; co < CO; co++) {
                 if (co < p.Co) {
                     const float* wr = sw + co * Cp + cq * 4;
                     acc[co] = fmaf(v.x, wr[0], fmaf(v.y, wr[1], fmaf(v.z, wr[2], fmaf(v.w, wr[3], acc[co]))));
@@ -789,28 +822,28 @@ __global__ void __launch_bounds__(256) head_kernel(const e3b_head_args p, int Cq
         if (p.out_mode == 1 || (p.out_mode == 2 && p.use_threshold)) {
             float mx = acc[0];
 #pragma unroll
-            for (int co = 1; co < kHeadMaxCo; co++) if (co < p.Co) mx = fmaxf(mx, acc[co]);
+            for (int co = 1; co < CO; co++) if (co < p.Co) mx = fmaxf(mx, acc[co]);
             float sum = 0.f;
 #pragma unroll
-            for (int co = 0; co < kHeadMaxCo; co++) if (co < p.Co) { acc[co] = expf(acc[co] - mx); sum += acc[co]; }
+            for (int co = 0; co < CO; co++) if (co < p.Co) { acc[co] = expf(acc[co] - mx); sum += acc[co]; }
             const float inv = 1.f / sum;
 #pragma unroll
-            for (int co = 0; co < kHeadMaxCo; co++) acc[co] *= inv;
+            for (int co = 0; co < CO; co++) acc[co] *= inv;
         }
         if (p.out_mode == 2) {
             if (p.use_threshold) {
 #pragma unroll
-                for (int co = 0; co < kHeadMaxCo; co++) if (co < p.Co && !(acc[co] > p.threshold)) acc[co] = 0.f;
+                for (int co = 0; co < CO; co++) if (co < p.Co && !(acc[co] > p.threshold)) acc[co] = 0.f;
             }
             int best = 0; float bv = acc[0];
 #pragma unroll
-            for (int co = 1; co < kHeadMaxCo; co++) if (co < p.Co && acc[co] > bv) { bv = acc[co]; best = co; }
+            for (int co = 1; co < CO; co++) if (co < p.Co && acc[co] > bv) { bv = acc[co]; best = co; }
             reinterpret_cast<uint8_t*>(p.dst)[nb * Sd + vout] = (uint8_t)best;
         } else {
             float* d = reinterpret_cast<float*>(p.dst);
             const float scl = p.acc_scale != 0.f ? p.acc_scale : 1.f;
 #pragma unroll
-            for (int co = 0; co < kHeadMaxCo; co++)
+            for (int co = 0; co < CO; co++)
                 if (co < p.Co) {
                     float v = acc[co];
                     if (p.round_half) v = __half2float(__float2half_rn(v));
@@ -969,7 +1002,7 @@ int e3b_unpack_qp(const float* src_qp, float* dst, int N, int C, int D, int H, i
 static bool pack_mode_ok(int mode, const PackDims& d, int kd, int kh, int kw)
 {
     if (mode < 0 || mode > 5 || d.NT <= 0) return false;
-    if (mode >= 4 && (kd != 3 || kh != 3 || kw != 3 || d.ntot > 80)) return false;
+    if (mode >= 4 && (kd != 3 || kh != 3 || kw != 3)) return false;
     return true;
 }
 
@@ -991,6 +1024,37 @@ int e3b_pack_weights(int mode, const float* w, const float* scale, const float* 
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mode, w, scale, wscale, reinterpret_cast<__half*>(dst), C0,
                                                                                 C1, Co, kd * kh * kw, d);
     return check_launch("pack_weights");
+}
+
+int e3b_pack_jobs_fill(const e3b_pack_job* jobs, int njobs, void* host_table, int64_t* total_blocks)
+{
+    if (!jobs || njobs <= 0 || !host_table || !total_blocks) return set_error("pack_jobs_fill: bad arguments");
+    PackJobDev* out = reinterpret_cast<PackJobDev*>(host_table);
+    int64_t blocks = 0;
+    for (int i = 0; i < njobs; i++) {
+        const e3b_pack_job& j = jobs[i];
+        if (j.mode < 0 || j.mode > 5) return set_error("pack_jobs_fill: bad mode %d", j.mode);
+        PackDims d = pack_dims(j.mode, j.C0, j.C1, j.Co, j.kd, j.kh, j.kw);
+        if (!pack_mode_ok(j.mode, d, j.kd, j.kh, j.kw)) return set_error("pack_jobs_fill: job %d: unsupported configuration", i);
+        PackJobDev& o = out[i];
+        o.w = j.w; o.scale = j.scale; o.wscale = j.wscale; o.dst = reinterpret_cast<__half*>(j.dst);
+        o.mode = j.mode; o.C0 = j.C0; o.C1 = j.C1; o.Co = j.Co; o.tu = j.kd * j.kh * j.kw; o.d = d;
+        o.total = (unsigned long long)d.ktot * d.ntot * d.taps;
+        o.first_block = (int)blocks;
+        blocks += (int64_t)((o.total + 255) / 256);
+        if (blocks > 0x7fffffff) return set_error("pack_jobs_fill: too many elements");
+    }
+    *total_blocks = blocks;
+    return 0;
+}
+
+int64_t e3b_pack_job_table_bytes(int njobs) { return (int64_t)njobs * (int64_t)sizeof(PackJobDev); }
+
+int e3b_pack_weights_batched(const void* device_table, int njobs, int64_t total_blocks, void* stream)
+{
+    if (!device_table || njobs <= 0 || total_blocks <= 0) return set_error("pack_weights_batched: bad arguments");
+    pack_weights_batched_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackJobDev*>(device_table), njobs);
+    return check_launch("pack_weights_batched");
 }
 
 int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_t S, const float* gamma, const float* beta,
@@ -1134,7 +1198,8 @@ int e3b_head(const e3b_head_args* a, void* stream)
     const int Cq = cpad8(a->C) / 4;
     const size_t total = (size_t)a->N * a->cn_d * a->cn_h * a->cn_w;
     const size_t smem = sizeof(float) * ((size_t)a->Co * Cq * 4 + a->Co);
-    head_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(*a, Cq);
+    if (a->Co <= 4) head_kernel<4><<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(*a, Cq);
+    else head_kernel<kHeadMaxCo><<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(*a, Cq);
     return check_launch("head");
 }
 

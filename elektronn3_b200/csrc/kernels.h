@@ -23,6 +23,7 @@ CUtensorMapL2promotion tma_l2_promotion();
 int conv_debug_read(unsigned long long* out16, int reset);
 int launch_conv_tc(const e3b_conv_args* a, cudaStream_t stream);
 int conv_zs_supported(int C0, int C1, int n_total, int kd, int kh, int kw, int scatter);
+int conv_zs_ntile(int C0, int C1, int n_total);
 int conv_zs_debug_read(uint32_t* out, int n);
 int conv_zs_prof_read(unsigned long long* out16, int reset);
 int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream);

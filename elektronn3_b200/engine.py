@@ -386,8 +386,56 @@ class Unit:
 
 class WeightSet:
     """What one forward (and the backward that follows it) needs besides the raw parameters: the per-tensor power-of-two
-    weight scales and, in eval mode, the folded BatchNorm factors."""
-    __slots__ = ('scales', 'folds')
+    weight scales, in eval mode the folded BatchNorm factors, in training mode the freshly packed weight images."""
+    __slots__ = ('scales', 'folds', 'images')
+
+
+class TrainImages:
+    """Training mode re-packs every weight image every step (WeightCache): persistent destination buffers, one persistent
+    scale table and ONE launch for all images (forward and dgrad layouts) through the library's job table."""
+
+    def __init__(self, net, specs):
+        lib = L.lib()
+        mods = [sp.conv if isinstance(sp, ConvSpec) else sp.up for sp in specs]
+        dev = mods[0].weight.device
+        self.sig = tuple(m.weight.data_ptr() for m in mods)
+        self.table = torch.empty((len(specs), 2), dtype=torch.float32, device=dev)
+        self.scales = {sp.name: WeightScale(self.table, i) for i, sp in enumerate(specs)}
+        self.img = {}
+        jobs = []
+        for i, (sp, mod) in enumerate(zip(specs, mods)):
+            w = mod.weight
+            if not w.is_contiguous():
+                raise RuntimeError(f'elektronn3_b200: parameter {sp.name}.weight must be contiguous')
+            if isinstance(sp, ConvSpec):
+                variants = ((4 if sp.variants[0] else 0, 'fwd'), (5 if sp.variants[1] else 1, 'bwd'))
+                dims = (sp.C0, sp.C1, sp.Co) + tuple(sp.k)
+            else:
+                variants = ((2, 'fwd'), (3, 'bwd'))
+                dims = (sp.Ci, 0, sp.Co) + tuple(sp.s)
+            for mode, key in variants:
+                n = lib.e3b_packed_weight_floats(mode, *dims)
+                if n <= 0:
+                    raise RuntimeError(f'elektronn3_b200: unsupported channel configuration for {sp.name}')
+                dst = torch.empty((n,), dtype=torch.float32, device=dev)
+                self.img[(sp.name, key)] = dst
+                j = L.PackJob()
+                j.w, j.scale, j.wscale, j.dst = w.data_ptr(), None, self.scales[sp.name].up_ptr, dst.data_ptr()
+                j.mode, j.C0, j.C1, j.Co, j.kd, j.kh, j.kw = (mode,) + dims
+                jobs.append(j)
+        self.njobs = len(jobs)
+        arr = (L.PackJob * self.njobs)(*jobs)
+        host = torch.empty((int(lib.e3b_pack_job_table_bytes(self.njobs)),), dtype=torch.uint8)
+        blocks = ctypes.c_int64(0)
+        L.check(lib.e3b_pack_jobs_fill(arr, self.njobs, host.data_ptr(), ctypes.byref(blocks)), 'pack_jobs_fill')
+        self.blocks = int(blocks.value)
+        self.dev_table = host.to(dev)
+        self.weights = [m.weight for m in mods]
+
+    def pack(self):
+        self.table.copy_(weight_scale_table(self.weights))
+        L.check(L.lib().e3b_pack_weights_batched(self.dev_table.data_ptr(), self.njobs, self.blocks, _stream()),
+                'pack_weights_batched')
 
 
 class Net:
@@ -396,6 +444,7 @@ class Net:
     def __init__(self, down, up, final_conv, dim, cache):
         self.down, self.up, self.final, self.dim, self.cache = down, up, final_conv, dim, cache
         self.wset = None
+        self.train_images = None
 
     def specs(self):
         for c1, c2, _ in self.down:
@@ -410,6 +459,15 @@ class Net:
 def prepare_weights(net, training):
     """-> WeightSet; cached like the packed images (never in training mode)."""
     specs = list(net.specs())
+    if training and not any(norm_mode(sp.norm, True)[0] == MODE_BATCH_EVAL for sp in specs):
+        ti = net.train_images
+        sig = tuple((sp.conv if isinstance(sp, ConvSpec) else sp.up).weight.data_ptr() for sp in specs)
+        if ti is None or ti.sig != sig:
+            ti = net.train_images = TrainImages(net, specs)
+        ti.pack()
+        ws = WeightSet()
+        ws.scales, ws.folds, ws.images = ti.scales, {}, ti.img
+        return ws
     params = []
     for sp in specs:
         mod = sp.conv if isinstance(sp, ConvSpec) else sp.up
@@ -433,6 +491,7 @@ def prepare_weights(net, training):
                 cscales.append(None)
         table = weight_scale_table(weights, cscales)
         ws.scales = {sp.name: WeightScale(table, i) for i, sp in enumerate(specs)}
+        ws.images = None
         return ws
     return net.cache.get(('weightset',), params, make, training)
 
@@ -456,6 +515,8 @@ def _conv_weights(net, spec, mode, training):
     conv = spec.conv
     pmode = 4 if spec.variants[0] else 0
     wsc = net.wset.scales[spec.name]
+    if net.wset.images is not None:
+        return net.wset.images[(spec.name, 'fwd')], (conv.bias.detach() if conv.bias is not None else None), wsc
     if nm == MODE_BATCH_EVAL:
         n = spec.norm
         params = (conv.weight, conv.bias, n.weight, n.bias, n.running_mean, n.running_var)
@@ -541,7 +602,9 @@ def _run_up(net, spec, dec, enc, training, save):
     u.dec = dec
     bias = up.bias.detach() if up.bias is not None else None
     wsc = net.wset.scales[spec.name]
-    if mode == MODE_BATCH_EVAL:
+    if net.wset.images is not None:
+        wpk = net.wset.images[(spec.name, 'fwd')]
+    elif mode == MODE_BATCH_EVAL:
         n = spec.norm
         params = (up.weight, up.bias, n.weight, n.bias, n.running_mean, n.running_var)
         fs, bias = net.wset.folds[spec.name]
@@ -760,9 +823,10 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
         return None, None
     dvar = spec.variants[1]
     wsc = net.wset.scales[spec.name]
-    wpk = net.cache.get((spec.name, 'dgrad'), (conv.weight,),
-                        lambda: pack_weights(5 if dvar else 1, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k, wscale=wsc),
-                        True)
+    if net.wset.images is not None:
+        wpk = net.wset.images[(spec.name, 'bwd')]
+    else:
+        wpk = pack_weights(5 if dvar else 1, conv.weight, None, spec.C0, spec.C1, spec.Co, spec.k, wscale=wsc)
     dpad = tuple(kk - 1 - pp for kk, pp in zip(spec.k, spec.pad))
     d0, d1, _ = conv_forward(dy, wpk, spec.n_total_dgrad, spec.C0, spec.k, dpad,
                              dst1_C=spec.C1 if u.src1 is not None else 0, variant=dvar, w_unscale=wsc)
@@ -817,8 +881,10 @@ def _backward(net, tape, dlogits, need_dx):
                         up_co=ups.Co)
             _put(grads, up.weight, dwu)
         wsc = net.wset.scales[ups.name]
-        wpk = net.cache.get((ups.name, 'up_dgrad'), (up.weight,),
-                            lambda: pack_weights(3, up.weight, None, ups.Ci, 0, ups.Co, ups.s, wscale=wsc), True)
+        if net.wset.images is not None:
+            wpk = net.wset.images[(ups.name, 'bwd')]
+        else:
+            wpk = pack_weights(3, up.weight, None, ups.Ci, 0, ups.Co, ups.s, wscale=wsc)
         g, _, _ = conv_forward(dy, wpk, cpad16(ups.Ci), ups.Ci, (1, 1, 1), (0, 0, 0), w_unscale=wsc)
     nd = len(net.down)
     dx = None

@@ -69,6 +69,18 @@ int64_t e3b_packed_weight_floats(int mode, int C0, int C1, int Co, int kd, int k
 int e3b_pack_weights(int mode, const float* w, const float* scale, const float* wscale, void* dst, int C0, int C1, int Co,
                      int kd, int kh, int kw, void* stream);
 
+/* All weight images of a network in ONE launch (a training step re-packs every image).  The caller describes the images
+ * once (pointers are those of the parameters and of persistent destination buffers), e3b_pack_jobs_fill() turns the
+ * descriptions into the library's device-table format in a HOST buffer of e3b_pack_job_table_bytes(njobs) bytes, the caller
+ * copies that buffer to the device (once) and calls e3b_pack_weights_batched() with the device copy every step. */
+typedef struct e3b_pack_job {
+    const float* w; const float* scale; const float* wscale; void* dst;    /* as e3b_pack_weights */
+    int32_t mode, C0, C1, Co, kd, kh, kw;
+} e3b_pack_job;
+int64_t e3b_pack_job_table_bytes(int njobs);
+int e3b_pack_jobs_fill(const e3b_pack_job* jobs, int njobs, void* host_table, int64_t* total_blocks);
+int e3b_pack_weights_batched(const void* device_table, int njobs, int64_t total_blocks, void* stream);
+
 /* ---- convolution ------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (kind::f16: fp16 operands, fp32 accumulate).
  * Replaces nn.Conv3d/Conv2d behind conv3 (models/unet.py:131-149) incl. its dgrad, the virtual

@@ -1,7 +1,11 @@
 #!/bin/bash
-# 2-GPU check of bench.py (graph for forward+backward, eager NCCL all-reduce + optimizer), tightly bounded
+# Two-GPU visit: the tests that need a second device, then bench.py under torchrun (train: weak scaling, Predictor: sharded).
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 100 python -m pytest tests/test_unet_gpu.py -m gpu -q -x -k "graphed" --timeout 80 2>&1 | tail -3
-E3B_BENCH_TIMEOUT=70 timeout 100 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2g.log 2>&1
-echo rc=$?; grep -a "^{" gpurun_out/bench_n2g.log | cut -c1-700; grep -a -i "error\|Traceback" gpurun_out/bench_n2g.log | head -5
+NG=${1:-2}
+nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/gpus_n$NG.txt 2>&1
+timeout 900 python -m pytest tests/test_protocol_gpu.py -m gpu -q --tb=short --timeout 600 -k "sharded or second_device or data_parallel" > gpurun_out/pytest_n$NG.log 2>&1
+echo "pytest rc=$?"; tail -15 gpurun_out/pytest_n$NG.log
+E3B_BENCH_TIMEOUT=600 timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29500 \
+  bench.py --gpus $NG --steps 20 --warmup 5 > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err
+echo "bench rc=$?"; cat gpurun_out/bench_n$NG.json | cut -c1-3000; tail -5 gpurun_out/bench_n$NG.err | cut -c1-300

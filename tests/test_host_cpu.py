@@ -43,7 +43,7 @@ def test_ctypes_structs_match_the_c_structs(tmp_path):
     """sizeof / offsetof of every argument struct as gcc sees include/e3b.h == the ctypes mirror"""
     from elektronn3_b200 import _lib
     structs = {'e3b_conv_args': _lib.ConvArgs, 'e3b_wgrad_args': _lib.WgradArgs,
-               'e3b_norm_bwd_args': _lib.NormBwdArgs, 'e3b_head_args': _lib.HeadArgs}
+               'e3b_norm_bwd_args': _lib.NormBwdArgs, 'e3b_head_args': _lib.HeadArgs, 'e3b_pack_job': _lib.PackJob}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, cls in structs.items():
         lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
@@ -222,15 +222,17 @@ def test_conv_kernel_selection_and_weight_image_sizes():
     v = lambda C0, C1, nt, k=(3, 3, 3), sc=0: lib.e3b_conv_variant(C0, C1, nt, k[0], k[1], k[2], sc)
     assert v(32, 0, 32) == 1 and v(32, 32, 32) == 1 and v(1, 0, 32) == 1      # cfg-2 full-resolution layers
     assert v(32, 0, 64) == 1 and v(64, 0, 32) == 1                            # 32 -> 64 and its dgrad
-    assert v(64, 0, 64) == 0 and v(128, 0, 64) == 0                           # weight image does not fit
-    assert v(32, 0, 96) == 0 and v(128, 0, 128) == 0                          # N = 3 * n_total > 256
+    assert v(64, 0, 64) == 1 and v(64, 0, 128) == 1 and v(32, 0, 96) == 1    # wide outputs: N tiles of 32 columns
+    assert v(128, 0, 64) == 0 and v(128, 0, 128) == 0 and v(64, 64, 64) == 0  # the image of a 32-column tile does not fit
+    assert v(64, 0, 48) == 0                                                  # neither whole (image too big) nor a multiple of 32
     assert v(32, 0, 32, (1, 3, 3)) == 0 and v(32, 0, 32, (1, 1, 1)) == 0      # planar / 1x1x1: halo-tile kernel
     assert v(32, 0, 32, (3, 3, 3), 1) == 0                                    # transposed conv (scatter)
     f = lib.e3b_packed_weight_floats
     for (C0, C1, Co) in [(32, 0, 32), (32, 32, 32), (3, 0, 8), (40, 0, 48)]:
         assert f(4, C0, C1, Co, 3, 3, 3) == f(0, C0, C1, Co, 3, 3, 3) > 0
         assert f(5, C0, C1, Co, 3, 3, 3) == f(1, C0, C1, Co, 3, 3, 3) > 0
-    assert f(4, 32, 0, 32, 1, 3, 3) == -1 and f(4, 32, 0, 128, 3, 3, 3) == -1
+    assert f(4, 64, 0, 64, 3, 3, 3) == f(0, 64, 0, 64, 3, 3, 3) > 0          # two N tiles, same number of elements
+    assert f(4, 32, 0, 32, 1, 3, 3) == -1 and f(4, 128, 0, 128, 3, 3, 3) == -1
 
 
 def test_graphed_train_step_needs_cuda():

@@ -155,6 +155,10 @@ ZS_CASES = [
     (1, 16, 0, 16, (70, 8, 8), (1, 1, 1)),                # one chain longer than the 32-block TMEM ring
     (1, 16, 0, 16, (1, 8, 8), (1, 1, 1)),                 # a single plane
     (2, 32, 0, 32, (40, 48, 40), (1, 1, 1)),              # more work than SMs: runs cut mid-chain, ring wrap-around
+    (1, 64, 0, 64, (10, 20, 12), (1, 1, 1)),              # wide output: two N tiles of 32 columns (one CTA group each)
+    (2, 64, 0, 128, (6, 16, 16), (1, 1, 1)),              # four N tiles
+    (1, 24, 0, 96, (5, 9, 11), (1, 1, 1)),                # three N tiles, ragged extents
+    (1, 32, 32, 64, (4, 16, 8), (1, 1, 1)),               # virtual concat into two N tiles
 ]
 
 
@@ -196,7 +200,10 @@ def test_conv_zstacked_forward_bias_relu_stats(eng, case):
 
 @pytest.mark.parametrize('case', [(1, 16, 0, 16, (4, 16, 8), (1, 1, 1)), (2, 32, 0, 64, (5, 10, 12), (1, 1, 1)),
                                   (1, 8, 0, 8, (8, 12, 12), (0, 0, 0)), (1, 16, 24, 32, (4, 16, 8), (1, 1, 1)),
-                                  (1, 32, 32, 32, (20, 24, 16), (1, 1, 1))])
+                                  (1, 32, 32, 32, (20, 24, 16), (1, 1, 1)),
+                                  (1, 64, 0, 64, (6, 12, 16), (1, 1, 1)),          # N tiles: two of 32 columns
+                                  (1, 64, 64, 64, (5, 16, 8), (1, 1, 1)),          # concat dgrad: four N tiles, two per destination
+                                  (1, 24, 40, 32, (4, 8, 8), (1, 1, 1))])          # destinations that end inside an N tile
 def test_conv_zstacked_dgrad(eng, case):
     N, C0, C1, Co, sp, pad = case
     k = (3, 3, 3)
