@@ -120,12 +120,14 @@ SIGNATURES = {
     'e3b_conv_variant': (c_int, [c_int] * 7),
     'e3b_debug_zs_read': (c_int, [c_void_p, c_int]),
     'e3b_debug_zs_prof': (c_int, [c_void_p, c_int]),
+    'e3b_debug_fused_prof': (c_int, [ctypes.POINTER(ctypes.c_ulonglong)]),
     'e3b_debug_conv_counters': (c_int, [c_void_p, c_int]),
     'e3b_wgrad_workspace_floats': (c_i64, [ctypes.POINTER(WgradArgs)]),
     'e3b_wgrad': (c_int, [ctypes.POINTER(WgradArgs), c_void_p]),
     'e3b_norm_finalize': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_i64, c_void_p, c_void_p, c_float,
                                   c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'e3b_norm_act': (c_int, [c_void_p] * 6 + [c_int] * 10 + [c_void_p]),
+    'e3b_norm_bwd_fused': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_reduce': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_finalize': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_apply': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),

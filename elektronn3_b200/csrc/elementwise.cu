@@ -380,13 +380,19 @@ struct VoxIn {
 template <bool STREAM>
 E3B_DEVINL float4 ld_grad(const float4* p) { return STREAM ? __ldcs(p) : __ldg(p); }
 
-template <bool STREAM>
+// GENERAL = false: the caller knows there is no pooled gradient and no cropped skip gradient
+template <bool STREAM, bool GENERAL = true>
 E3B_DEVINL void load_vox(const NormBwdDev& p, size_t o, int n, int cq, int z, int yy, int x, VoxIn& in)
 {
+    // every field the instantiation can read gets a value: a conditionally written field of a loop-local struct would
+    // otherwise live in local memory (ptxas keeps the "old" value across the predicated load)
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     in.y = p.y[o];
+    in.g0 = zero; in.g1 = zero;
+    if (GENERAL) { in.gp = zero; in.idx = make_uchar4(0, 0, 0, 0); in.slot = 255; }
     if (p.g0) in.g0 = ld_grad<STREAM>(p.g0 + o);
     if (p.g1) {
-        if (!p.g1_crop) {
+        if (!GENERAL || !p.g1_crop) {
             in.g1 = ld_grad<STREAM>(p.g1 + o);
         } else {
             // backward of autocrop's slice of the skip tensor: zero outside the cropped box
@@ -396,7 +402,7 @@ E3B_DEVINL void load_vox(const NormBwdDev& p, size_t o, int n, int cq, int z, in
                 in.g1 = ld_grad<STREAM>(p.g1 + ((((size_t)n * p.Cq + cq) * p.g1_D + zc) * p.g1_H + yc) * p.g1_W + xc);
         }
     }
-    if (p.gp) {
+    if (GENERAL && p.gp) {
         const int zw = z / p.wd, yw = yy / p.wh, xw = x / p.ww;
         in.slot = (unsigned char)(((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww));
         const size_t ow = ((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw;
@@ -407,6 +413,7 @@ E3B_DEVINL void load_vox(const NormBwdDev& p, size_t o, int n, int cq, int z, in
 
 // the masked upstream gradient dr = (g0 + g1 + unpool(gp)) * [a > 0] and xhat of one voxel.
 // `a` is recomputed bit-exactly from y (the arithmetic of norm_act_kernel), never read.
+template <bool GENERAL = true>
 E3B_DEVINL void voxel_grad(const NormBwdDev& p, const VoxIn& in, const float4& mu, const float4& rs, const float4& sc,
                            const float4& sh, float4& dr, float4& xh)
 {
@@ -417,7 +424,7 @@ E3B_DEVINL void voxel_grad(const NormBwdDev& p, const VoxIn& in, const float4& m
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.g0) g = in.g0;
     if (p.g1) { g.x += in.g1.x; g.y += in.g1.y; g.z += in.g1.z; g.w += in.g1.w; }
-    if (p.gp) {
+    if (GENERAL && p.gp) {
         if (in.idx.x == in.slot) g.x += in.gp.x;
         if (in.idx.y == in.slot) g.y += in.gp.y;
         if (in.idx.z == in.slot) g.z += in.gp.z;
@@ -763,6 +770,619 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev
         const float4 o = apply_formula(dr, xh, c.rs, c.ga, c.m1, c.m2);
         const float4 os = make_float4(o.x * dscale, o.y * dscale, o.z * dscale, o.w * dscale);
         store_qh(p.dy, os, n, p.Ch, cq, (size_t)p.D * p.H * p.W, (size_t)row * p.W + x0 + j);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused norm backward: reduce -> finalize -> apply in ONE persistent kernel, one sample at a time.
+//
+// The three-kernel path above reads y and the incoming gradient twice from HBM (603 MB per full-resolution 32-channel
+// layer of BASELINE cfg 2) with register-staged loads whose memory parallelism is bounded by occupancy.  Here:
+//   * group / instance normalisation has per-SAMPLE statistics and one sample's y + gradient (67 MB) fits the 126 MB L2:
+//     the kernel makes one ROUND per sample -- phase A reduces the sample, a grid barrier, phase B derives the group means
+//     (O(C) work, every CTA redundantly), phase C applies the backward formula to the same items.  y and the gradients
+//     cross HBM once; the second read is served by L2 -- or by shared memory, see below;
+//   * every CTA owns a fixed contiguous range of work items (an item = 512 voxels x 8 channels of every source tensor)
+//     and moves them through a ring of shared-memory stages with 1D bulk copies (cp.async.bulk + mbarrier): the copies
+//     of the next stages are in flight while the CTA computes, independent of register count and occupancy;
+//   * phase C walks the items BACKWARDS through the same ring: the last S items of phase A are still in shared memory and
+//     are not re-read at all (3 of ~7 items per CTA and round for the full-resolution layers of cfg 2), older items come
+//     out of L2 newest first; stages freed at the tail of phase C already prefetch the next sample's first items;
+//   * dy leaves as full 16-byte units (both 4-channel halves written by one thread).
+// Batch normalisation (statistics over the batch) runs the same code as ONE round over all samples.  The gradient's
+// power-of-two fp16 scale stays per tensor: it is taken from the first sample's bound; if a later sample needs a smaller
+// one, the samples already written are re-scaled in place (exact: a power of two).
+// ------------------------------------------------------------------------------------------------
+// q = v / d for 0 <= v < 2^31 as one wide multiply and a shift: mul = ceil(2^(31+l) / d), l = ceil(log2 d)
+// (error term < 1/d: exact)
+struct FastDiv {
+    uint32_t mul, shift;
+    E3B_DEVINL int div(int v) const { return (int)(((unsigned long long)(unsigned)v * mul) >> shift); }
+};
+static FastDiv make_fastdiv(int d)
+{
+    int l = 0;
+    while ((1ll << l) < d) l++;
+    FastDiv f;
+    f.shift = 31 + l;
+    f.mul = (uint32_t)(((1ull << f.shift) + (unsigned)d - 1) / (unsigned)d);
+    return f;
+}
+
+// Optional phase timeline of the fused kernel (E3B_FUSED_PROF, scripts/normbwd_bench.py): globaltimer stamps of thread 0 of
+// the first and the last CTA, [cta 2][round 4][stamp 8]: 0 round start, 1 phase A done, 2 grid barrier passed, 3 phase B
+// done, 4 phase C done, 5 / 6 time spent waiting for copies in phase A / C.
+__device__ unsigned long long g_fused_prof[64];
+
+struct FusedDev {
+    int mode, G;
+    double S;
+    const double* fwd_stats;
+    float *dgamma, *dbeta, *dbias;
+    unsigned int* counter;               // grid barrier (zeroed by the launch wrapper)
+    int per_sample;                      // 1: statistics per sample (group / instance / none), 0: over the batch
+    int nset;                            // samples per round: a divisor of N (batch statistics: N)
+    int Cp;
+    int stages;                          // ring depth
+    int g1_bulk;                         // the second gradient is staged by bulk copies (present and not cropped)
+    int prof;
+    double inv_count;                    // 1 / (elements a mean is taken over): S * C/G (group), S * N (batch)
+    FastDiv dHW, dW, dwd, dwh, dww;      // GENERAL variant: voxel index -> (z, y, x) and pooling / s2d window coordinates
+};
+
+static constexpr int kFusedMaxCp = 512;
+static constexpr int kItemVox = 512;                         // voxels per work item (x 2 channel quads x 16 B = 16 KB per tensor)
+static constexpr int kItemTensorBytes = 2 * kItemVox * 16;
+static constexpr int kFusedMaxStages = 8;
+static constexpr int kCtabSlots = kFusedMaxCp / 4;          // the constants of ALL rounds are staged up front when they fit
+
+// mu holds -mean * rstd: xhat = fma(y, rstd, mu).  thr: 0 with ReLU, -inf without (the mask is fma(y, sc, sh) > thr)
+struct QuadConsts { float4 mu, rs, sc, sh; float thr; };
+
+static constexpr int kQuadsPerThread = kItemVox / 128;       // a group of 4 warps covers the item's 512 voxels of one channel quad
+
+// 16-byte shared-memory load from a 32-bit shared address (volatile: stays behind the mbarrier wait that guards the stage)
+E3B_DEVINL float4 lds128(uint32_t saddr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
+// y and the staged gradients (g0 [+ g1]) of this thread's voxel quads of one item: all loads are issued before the first use
+static constexpr int kQuadBatch = 2;                          // quads whose loads are in flight together (register budget: 96)
+
+template <bool GENERAL, bool G1, bool FULL>
+E3B_DEVINL void fused_load_item(const NormBwdDev& p, const FusedDev& f, uint32_t sbase, uint32_t off_g0, uint32_t off_g1, int t128,
+                                int nv, int k0, float4* Y, float4* G)
+{
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kk = 0; kk < kQuadBatch; kk++) {
+        const int k = k0 + kk;
+        Y[kk] = zero; G[kk] = zero;
+        if (!FULL && k * 128 + t128 >= nv) continue;
+        Y[kk] = lds128(sbase + k * 2048);
+        if (!GENERAL || p.g0) G[kk] = lds128(sbase + off_g0 + k * 2048);
+    }
+    if (GENERAL ? f.g1_bulk != 0 : G1) {
+#pragma unroll
+        for (int kk = 0; kk < kQuadBatch; kk++) {
+            const int k = k0 + kk;
+            if (!FULL && k * 128 + t128 >= nv) continue;
+            const float4 t = lds128(sbase + off_g1 + k * 2048);
+            G[kk].x += t.x; G[kk].y += t.y; G[kk].z += t.z; G[kk].w += t.w;
+        }
+    }
+}
+
+// GENERAL variant: voxel coordinates, and the gradients that are gathered from global memory (cropped skip gradient,
+// un-pooling of the pooled gradient; L1 / L2 hits: 8 fine voxels share one coarse voxel)
+E3B_DEVINL void fused_gather(const NormBwdDev& p, const FusedDev& f, int n, int cq, int v, float4& g, int& z, int& yy, int& x)
+{
+    z = f.dHW.div(v);
+    const int r = v - z * (p.H * p.W);
+    yy = f.dW.div(r); x = r - yy * p.W;
+    if (p.g1 && !f.g1_bulk) {
+        // backward of autocrop's slice of the skip tensor: zero outside the cropped box
+        const int zc = z - p.g1_od, yc = yy - p.g1_oh, xc = x - p.g1_ow;
+        if (zc >= 0 && zc < p.g1_D && yc >= 0 && yc < p.g1_H && xc >= 0 && xc < p.g1_W) {
+            const float4 t = __ldg(p.g1 + ((((size_t)n * p.Cq + cq) * p.g1_D + zc) * p.g1_H + yc) * p.g1_W + xc);
+            g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        }
+    }
+    if (p.gp) {
+        const int zw = f.dwd.div(z), yw = f.dwh.div(yy), xw = f.dww.div(x);
+        const unsigned char slot = (unsigned char)(((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww));
+        const size_t ow = ((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw;
+        const uchar4 idxs = p.pool_idx[ow];
+        const float4 t = p.gp[ow];
+        if (idxs.x == slot) g.x += t.x;
+        if (idxs.y == slot) g.y += t.y;
+        if (idxs.z == slot) g.z += t.z;
+        if (idxs.w == slot) g.w += t.w;
+    }
+}
+
+// xhat, and the ReLU mask applied to the summed upstream gradient.  The mask is y * scale + shift > 0 (scale = 1, shift = 0
+// without a norm): the forward's TF32 rounding of the activation cannot turn a positive value into zero, so the mask does
+// not need it.
+E3B_DEVINL void fused_mask_xhat(const QuadConsts& c, const float4& yv, float4& g, float4& xh)
+{
+    xh = make_float4(fmaf(yv.x, c.rs.x, c.mu.x), fmaf(yv.y, c.rs.y, c.mu.y), fmaf(yv.z, c.rs.z, c.mu.z), fmaf(yv.w, c.rs.w, c.mu.w));
+    if (!(fmaf(yv.x, c.sc.x, c.sh.x) > c.thr)) g.x = 0.f;
+    if (!(fmaf(yv.y, c.sc.y, c.sh.y) > c.thr)) g.y = 0.f;
+    if (!(fmaf(yv.z, c.sc.z, c.sh.z) > c.thr)) g.z = 0.f;
+    if (!(fmaf(yv.w, c.sc.w, c.sh.w) > c.thr)) g.w = 0.f;
+}
+
+// phase A over one staged item (this thread: channel quad `cq`, voxels t128 + 128 k).
+// GENERAL = false ("lean"): g0 is present, no pooled gradient, no cropped skip gradient, no space-to-depth output; G1: a
+// second, un-cropped gradient is staged next to g0.  GENERAL = true decides all of that at run time.
+// FULL = all 512 voxels present: no bounds checks.
+template <bool GENERAL, bool G1, bool FULL>
+E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32_t sbase, uint32_t off_g0, uint32_t off_g1,
+                                  const QuadConsts& c, int t128, int n, int cq, int v0, int nv, float* s1, float* s2, float* md,
+                                  float* mx)
+{
+#pragma unroll
+    for (int k0 = 0; k0 < kQuadsPerThread; k0 += kQuadBatch) {
+    float4 Y[kQuadBatch], G[kQuadBatch];
+    fused_load_item<GENERAL, G1, FULL>(p, f, sbase, off_g0, off_g1, t128, nv, k0, Y, G);
+#pragma unroll
+    for (int kk = 0; kk < kQuadBatch; kk++) {
+        const int vl = (k0 + kk) * 128 + t128;
+        if (!FULL && vl >= nv) continue;
+        float4 dr = G[kk], xh;
+        if (GENERAL) { int z, yy, x; fused_gather(p, f, n, cq, v0 + vl, dr, z, yy, x); }
+        fused_mask_xhat(c, Y[kk], dr, xh);
+        s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
+        s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]); s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
+        md[0] = fmaxf(md[0], fabsf(dr.x)); md[1] = fmaxf(md[1], fabsf(dr.y)); md[2] = fmaxf(md[2], fabsf(dr.z)); md[3] = fmaxf(md[3], fabsf(dr.w));
+        mx[0] = fmaxf(mx[0], fabsf(xh.x)); mx[1] = fmaxf(mx[1], fabsf(xh.y)); mx[2] = fmaxf(mx[2], fabsf(xh.z)); mx[3] = fmaxf(mx[3], fabsf(xh.w));
+    }
+    }
+}
+
+// phase C over one staged item: dy = 2^k * rstd * (gamma * dr - m1 - xhat * m2); this thread writes the 8-byte half `hsel`
+// of its voxels' 16-byte units (the other half comes from the other warp group; L2 merges the sectors).
+// (fp16 has TF32's 10 mantissa bits: the fp16 rounding of the store is the operand rounding.)
+template <bool GENERAL, bool G1, bool FULL>
+E3B_DEVINL void fused_item_apply(const NormBwdDev& p, const FusedDev& f, uint32_t sbase, uint32_t off_g0, uint32_t off_g1,
+                                 const QuadConsts& c, const float4& ga, const float4& m1, const float4& m2, const float4& rk, int hsel,
+                                 int t128, int n, int cqp, int Cqp, int total, int v0, int nv, uint2* dy)
+{
+    const int cq = 2 * cqp + hsel;
+    // this thread's 8-byte half of its first voxel's unit; the other quads follow at 128 voxels = 2 KB
+    uint2* const dyp = dy + ((((size_t)n * p.Ch + cqp) * (size_t)total + (size_t)(v0 + t128)) * 2 + hsel);
+#pragma unroll
+    for (int k0 = 0; k0 < kQuadsPerThread; k0 += kQuadBatch) {
+    float4 Y[kQuadBatch], G[kQuadBatch];
+    fused_load_item<GENERAL, G1, FULL>(p, f, sbase, off_g0, off_g1, t128, nv, k0, Y, G);
+#pragma unroll
+    for (int kk = 0; kk < kQuadBatch; kk++) {
+        const int vl = (k0 + kk) * 128 + t128;
+        if (!FULL && vl >= nv) continue;
+        float4 dr = G[kk], xh;
+        int z = 0, yy = 0, x = 0;
+        if (GENERAL) fused_gather(p, f, n, cq, v0 + vl, dr, z, yy, x);
+        fused_mask_xhat(c, Y[kk], dr, xh);
+        // rstd * 2^k is folded into rk: o = rk * (ga * dr - m1 - xh * m2)
+        const uint2 o = pack_half4(rk.x * fmaf(-xh.x, m2.x, fmaf(ga.x, dr.x, -m1.x)), rk.y * fmaf(-xh.y, m2.y, fmaf(ga.y, dr.y, -m1.y)),
+                                   rk.z * fmaf(-xh.z, m2.z, fmaf(ga.z, dr.z, -m1.z)), rk.w * fmaf(-xh.w, m2.w, fmaf(ga.w, dr.w, -m1.w)));
+        if (!GENERAL || !p.s2d) {
+            dyp[(k0 + kk) * 256] = o;
+        } else {
+            // space-to-depth: channel = slot * Cp + c on the coarse grid
+            const int zw = f.dwd.div(z), yw = f.dwh.div(yy), xw = f.dww.div(x);
+            const int slot = ((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww);
+            const size_t unit = ((size_t)n * p.Ch + slot * Cqp + cqp) * ((size_t)p.Dw * p.Hw * p.Ww) + ((size_t)zw * p.Hw + yw) * p.Ww + xw;
+            dy[unit * 2 + hsel] = o;
+        }
+    }
+    }
+}
+
+static constexpr int kFusedThreads = 288;            // 8 consumer warps + 1 producer warp (one lane issues the bulk copies)
+static constexpr int kFusedBar = 1;                  // named barrier of the 256 consumer threads
+
+template <bool GENERAL, bool G1>
+__global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const NormBwdDev p, const FusedDev f)
+{
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ uint64_t full[kFusedMaxStages], empty[kFusedMaxStages];
+    __shared__ float4 ctab[kCtabSlots][5];           // per (sample, 4-channel quad): -mean * rstd, rstd, scale, shift, gamma
+    __shared__ float2 gm[kFusedMaxCp];               // (m1, m2) per (sample of the round, group) -- batch statistics: per channel
+    __shared__ float red[8][16];
+    __shared__ float bound_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = p.D * p.H * p.W;               // voxels per (n, 4-channel plane) slab
+    const int nchunks = (total + kItemVox - 1) / kItemVox;
+    const int Cqp = p.Cq >> 1;                       // pairs of channel quads (Cq is even: channels are padded to 8)
+    const int nset = f.nset, nrounds = p.N / nset;       // samples per round (a divisor of N); batch statistics: one round
+    const int Cp = f.Cp, S = f.stages;
+    const bool has_g0 = !GENERAL || p.g0 != nullptr, g1_bulk = GENERAL ? f.g1_bulk != 0 : G1;
+    const int nb = 1 + (has_g0 ? 1 : 0) + (g1_bulk ? 1 : 0);
+    const uint32_t stage_bytes = nb * kItemTensorBytes;
+    const uint32_t off_g0 = kItemTensorBytes, off_g1 = (has_g0 ? 2 : 1) * kItemTensorBytes;
+    const long long items = (long long)nset * Cqp * nchunks;                   // < 2^31 (checked by the launch wrapper)
+    const int i0 = (int)(items * blockIdx.x / gridDim.x), i1 = (int)(items * (blockIdx.x + 1) / gridDim.x);
+    const int cnt = i1 - i0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        // ---------------- producer: the whole kernel's copy schedule, throttled by the consumers' releases of the stages.
+        // Phase A walks the CTA's items forwards through the ring, phase C backwards through the SAME ring: the last S items
+        // of phase A are still staged when phase C starts and are not copied again.
+        if (lane != 0) return;
+        // start the bulk copies of work item `it` of the round whose first sample is n0 into stage s
+        auto issue = [&](int n0, int it, int s) {
+            const int sp = it / nchunks, chunk = it - sp * nchunks;
+            const int n = n0 + sp / Cqp, cqp = sp - (sp / Cqp) * Cqp;
+            const int v0 = chunk * kItemVox;
+            const uint32_t bytes = (uint32_t)min(kItemVox, total - v0) * 16u;
+            unsigned char* dst = ring + (size_t)s * stage_bytes;
+            mbar_arrive_expect_tx(&full[s], 2 * nb * bytes);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const size_t off = ((size_t)n * p.Cq + 2 * cqp + h) * (size_t)total + v0;
+                bulk_load_1d(dst + h * (kItemVox * 16), p.y + off, bytes, &full[s]);
+                if (has_g0) bulk_load_1d(dst + off_g0 + h * (kItemVox * 16), p.g0 + off, bytes, &full[s]);
+                if (g1_bulk) bulk_load_1d(dst + off_g1 + h * (kItemVox * 16), p.g1 + off, bytes, &full[s]);
+            }
+        };
+        uint32_t eparity = 0;                         // bit s: the phase of empty[s] the next refill of stage s waits for
+        auto refill = [&](int n0, int it, int s) {
+            mbar_wait(&empty[s], (eparity >> s) & 1u);
+            eparity ^= 1u << s;
+            issue(n0, it, s);
+        };
+        for (int j = 0; j < S && j < cnt; j++) issue(0, i0 + j, j);
+        for (int round = 0; round < nrounds; round++) {
+            const int n0 = round * nset;
+            for (int j = 0; j + S < cnt; j++) refill(n0, i0 + j + S, j % S);                       // phase A
+            for (int j = cnt - 1; j >= 0; j--) {                                                   // phase C
+                if (j - S >= 0) refill(n0, i0 + j - S, j % S);                                     // an older item of this round
+                else if (round + 1 < nrounds) refill(n0 + nset, i0 + j, j % S);                    // the next round's first items
+            }
+        }
+        return;
+    }
+    // ---------------- consumers (256 threads; they synchronise among themselves on a named barrier)
+    const int hsel = warp >> 2, t128 = threadIdx.x & 127;
+    const uint32_t ring_thread = smem_u32(ring) + (uint32_t)(hsel * kItemVox + t128) * 16u;     // this thread's first voxel quad of stage 0
+    const float relu_thr = p.relu ? 0.f : -INFINITY;
+    uint32_t parity = 0;                              // bit s: the phase of full[s] the next wait on stage s is for
+    float dscale = 0.f;                               // the tensor's fp16 scale so far (0: none yet); identical in every CTA
+    float bound_max = 0.f;
+    unsigned int bar_target = 0;
+    // Per-(sample, channel quad) constants.  Batch statistics are the same for every sample: one row per quad (cs = 0).
+    // ctab rows: (n - ctab_n0) * Cq + cq; all samples at once when they fit (the launch wrapper guarantees nset * Cq fits).
+    const int cs = f.per_sample ? 1 : 0;
+    const bool all_rounds = cs * p.N * p.Cq <= kCtabSlots;
+    auto fill_ctab = [&](int first, int count) {
+        for (int t = threadIdx.x; t < count * p.Cq; t += 256) {
+            const int j = t / p.Cq, cq = t - j * p.Cq;
+            const size_t nc = ((size_t)(first + j) * p.Cq + cq) * 4;
+            float4* row = ctab[t];
+            float4 mu, rs;
+            load_nc4(p.mean, nc, mu, 0.f); load_nc4(p.rstd, nc, rs, 1.f);
+            row[0] = make_float4(-mu.x * rs.x, -mu.y * rs.y, -mu.z * rs.z, -mu.w * rs.w); row[1] = rs;
+            load_nc4(p.scale, nc, row[2], 1.f); load_nc4(p.shift, nc, row[3], 0.f);
+            float4 ga = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.gamma) {
+                const int ch = cq * 4;
+                ga.x = ch < p.C ? p.gamma[ch] : 0.f; ga.y = ch + 1 < p.C ? p.gamma[ch + 1] : 0.f;
+                ga.z = ch + 2 < p.C ? p.gamma[ch + 2] : 0.f; ga.w = ch + 3 < p.C ? p.gamma[ch + 3] : 0.f;
+            }
+            row[4] = ga;
+        }
+    };
+    if (all_rounds) {
+        fill_ctab(0, cs ? p.N : 1);                   // while the first bulk copies are in flight
+        named_bar_sync(kFusedBar, 256);
+    }
+    for (int round = 0; round < nrounds; round++) {
+        const int n0 = round * nset;
+        const bool prof_on = f.prof && threadIdx.x == 0 && round < 4 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+        unsigned long long* prof = g_fused_prof + ((blockIdx.x == 0 ? 0 : 1) * 4 + (round & 3)) * 8;
+        unsigned long long wait_a = 0, wait_c = 0;
+        if (prof_on) prof[0] = globaltimer_ns();
+        if (!all_rounds) {
+            fill_ctab(n0, nset);                      // too many (sample, channel) pairs for the table: one round at a time
+            named_bar_sync(kFusedBar, 256);
+        }
+        const int ctab_n0 = all_rounds ? 0 : n0;
+        // ---------------- phase A: sums of dr and dr * xhat, max |dr| and |xhat| per (n, c).
+        // Warps 0-3 work on the first channel quad of the item's pair, warps 4-7 on the second: the per-channel constants
+        // stay in registers while the slab pair does not change.
+        {
+            float s1[4], s2[4], md[4], mx[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { s1[j] = 0.f; s2[j] = 0.f; md[j] = 0.f; mx[j] = 0.f; }
+            int cur_sp = -1, n = 0, cqp = 0;
+            int sp = i0 / nchunks, chunk = i0 - sp * nchunks;                   // item i0 + j = (slab pair sp, chunk)
+            QuadConsts c;
+            c.thr = relu_thr;
+            for (int j = 0; j <= cnt; j++) {
+                if (j == cnt || sp != cur_sp) {
+                    if (cur_sp >= 0) {
+                        // this slab pair's partial sums: warp shuffles -> shared memory -> 16 fp64 + 16 max atomics per CTA
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            for (int o = 16; o > 0; o >>= 1) {
+                                s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o);
+                                s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], o);
+                                md[q] = fmaxf(md[q], __shfl_xor_sync(0xffffffffu, md[q], o));
+                                mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
+                            }
+                        }
+                        if (lane == 0) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) { red[warp][q] = s1[q]; red[warp][4 + q] = s2[q]; red[warp][8 + q] = md[q]; red[warp][12 + q] = mx[q]; }
+                        }
+                        named_bar_sync(kFusedBar, 256);
+                        if (threadIdx.x < 32) {
+                            // thread (h, q): entry q of channel quad h, over that quad's four warps
+                            const int h = threadIdx.x >> 4, q = threadIdx.x & 15;
+                            const size_t ch = ((size_t)n * p.Cq + 2 * cqp + h) * 4 + (q & 3);
+                            if (q < 8) {
+                                double t = 0.0;
+                                for (int w = 0; w < 4; w++) t += (double)red[h * 4 + w][q];
+                                atomicAdd(p.sums + ch * 2 + (q >> 2), t);
+                            } else {
+                                float t = 0.f;
+                                for (int w = 0; w < 4; w++) t = fmaxf(t, red[h * 4 + w][q]);
+                                if (!(t < 3.0e38f)) t = 3.0e38f;               // inf / nan: the scale falls back to 1
+                                atomicMax(p.amax + ch * 2 + ((q >> 2) - 2), __float_as_uint(t));
+                            }
+                        }
+                        named_bar_sync(kFusedBar, 256);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { s1[q] = 0.f; s2[q] = 0.f; md[q] = 0.f; mx[q] = 0.f; }
+                    }
+                    if (j == cnt) break;
+                    cur_sp = sp;
+                    n = n0 + sp / Cqp; cqp = sp - (sp / Cqp) * Cqp;
+                    const float4* row = ctab[cs * (n - ctab_n0) * p.Cq + 2 * cqp + hsel];
+                    c.mu = row[0]; c.rs = row[1]; c.sc = row[2]; c.sh = row[3];
+                }
+                const int v0 = chunk * kItemVox, nv = min(kItemVox, total - v0);
+                const int s = j % S;
+                const unsigned long long tw = prof_on ? globaltimer_ns() : 0;
+                mbar_wait(&full[s], (parity >> s) & 1u);
+                if (prof_on) wait_a += globaltimer_ns() - tw;
+                parity ^= 1u << s;
+                const uint32_t sbase = ring_thread + (uint32_t)s * stage_bytes;
+                if (nv == kItemVox) fused_item_reduce<GENERAL, G1, true>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx);
+                else fused_item_reduce<GENERAL, G1, false>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx);
+                if (j + S < cnt) {                    // this warp is done with stage s: the producer may refill it
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                }
+                if (++chunk == nchunks) { chunk = 0; sp++; }
+            }
+        }
+        // ---------------- grid barrier: every CTA's sums of this round are in
+        if (prof_on) { prof[1] = globaltimer_ns(); prof[5] = wait_a; }
+        bar_target += gridDim.x;
+        named_bar_sync(kFusedBar, 256);
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(f.counter, 1u);
+            const uint64_t t0 = globaltimer_ns();
+            uint32_t spins = 0;
+            while (*reinterpret_cast<volatile unsigned int*>(f.counter) < bar_target) {
+                if ((++spins & 0x3FF) == 0 && globaltimer_ns() - t0 > E3B_WAIT_TIMEOUT_NS) __trap();     // never hang the box
+            }
+            __threadfence();
+            bound_s = 0.f;
+            if (prof_on) prof[2] = globaltimer_ns();
+        }
+        named_bar_sync(kFusedBar, 256);
+        // ---------------- phase B (every CTA, redundantly): the means m1, m2 per (sample of the round, group) -- batch
+        // statistics: per channel -- then the bound on |dy|.  sums / amax were written by other CTAs' atomics: read them
+        // from L2 (ld.cg); gamma and rstd come from the shared-memory table.  Two L2 round trips in all: every thread issues
+        // its loads before it uses any of them.
+        {
+            const int nent_c = (cs ? nset : 1) * Cp;                            // (sample, channel) entries of the round
+            // this thread's first (sample, channel) entry: its amax loads go out together with the loads of step 1
+            const int t0 = threadIdx.x, j0 = t0 / Cp, c0 = t0 - j0 * Cp;
+            unsigned int ad0 = 0, ax0 = 0;
+            if (t0 < nent_c && c0 < p.C && cs) {
+                ad0 = __ldcg(p.amax + ((size_t)(n0 + j0) * Cp + c0) * 2); ax0 = __ldcg(p.amax + ((size_t)(n0 + j0) * Cp + c0) * 2 + 1);
+            }
+            // step 1: the means.  Group mode with a power-of-two group size: one thread per (sample, channel) loads its own
+            // two sums (one L2 round trip for the whole table) and the group's lanes add up by shuffles; otherwise one
+            // thread per (sample, group) [group mode] or per channel [batch mode] walks its entries.
+            const int cg = f.mode == 1 ? p.C / f.G : 1;
+            if (f.mode == 1 && cg <= 32 && (cg & (cg - 1)) == 0 && Cp % cg == 0) {
+                for (int t = threadIdx.x; t - lane < nent_c; t += 256) {
+                    const int j = t / Cp, c = t - j * Cp, n = n0 + j;
+                    const bool valid = t < nent_c && c < p.C;
+                    double v1 = 0.0, v2 = 0.0;
+                    if (valid) {
+                        const double ga = (double)reinterpret_cast<const float*>(&ctab[cs * (n - ctab_n0) * p.Cq + (c >> 2)][4])[c & 3];
+                        v1 = ga * __ldcg(p.sums + ((size_t)n * Cp + c) * 2);
+                        v2 = ga * __ldcg(p.sums + ((size_t)n * Cp + c) * 2 + 1);
+                    }
+                    for (int o = cg >> 1; o > 0; o >>= 1) {
+                        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+                    }
+                    if (valid && (c & (cg - 1)) == 0) gm[j * f.G + c / cg] = make_float2((float)(v1 * f.inv_count), (float)(v2 * f.inv_count));
+                }
+            } else {
+                const int ngrp = f.mode == 1 ? f.G : (f.mode == 2 ? p.C : 0);
+                for (int t = threadIdx.x; t < (cs ? nset : 1) * ngrp; t += 256) {
+                    const int j = t / ngrp, g = t - j * ngrp;
+                    double m1 = 0.0, m2 = 0.0;
+                    if (f.mode == 1) {
+                        const int n = n0 + j;
+                        const float4* grow = ctab[cs * (n - ctab_n0) * p.Cq];
+#pragma unroll 4
+                        for (int q = 0; q < cg; q++) {
+                            const int cc = g * cg + q;
+                            const double ga = (double)reinterpret_cast<const float*>(&grow[(cc >> 2) * 5 + 4])[cc & 3];
+                            m1 += ga * __ldcg(p.sums + ((size_t)n * Cp + cc) * 2);
+                            m2 += ga * __ldcg(p.sums + ((size_t)n * Cp + cc) * 2 + 1);
+                        }
+                    } else {
+                        const double ga = (double)reinterpret_cast<const float*>(&ctab[g >> 2][4])[g & 3];
+#pragma unroll 4
+                        for (int q = 0; q < p.N; q++) {
+                            m1 += __ldcg(p.sums + ((size_t)q * Cp + g) * 2);
+                            m2 += __ldcg(p.sums + ((size_t)q * Cp + g) * 2 + 1);
+                        }
+                        m1 *= ga; m2 *= ga;
+                    }
+                    gm[t] = make_float2((float)(m1 * f.inv_count), (float)(m2 * f.inv_count));
+                }
+            }
+            named_bar_sync(kFusedBar, 256);
+            // step 2: |dy| = |rstd (gamma dr - m1 - xhat m2)| <= rstd (|gamma| max|dr| + |m1| + max|xhat| |m2|)
+            float bmax = 0.f;
+            for (int t = threadIdx.x; t < nent_c; t += 256) {
+                const int j = t / Cp, c = t - j * Cp;
+                if (c >= p.C) continue;
+                const int n = n0 + j;
+                const float4* row = ctab[cs * (n - ctab_n0) * p.Cq + (c >> 2)];
+                const float ga_abs = f.mode != 0 ? fabsf(reinterpret_cast<const float*>(&row[4])[c & 3]) : 1.f;
+                const float rs_c = reinterpret_cast<const float*>(&row[1])[c & 3];
+                float2 m = make_float2(0.f, 0.f);
+                if (f.mode == 1) m = gm[j * f.G + c / (p.C / f.G)];
+                else if (f.mode == 2) m = gm[c];
+                float b = 0.f;
+                for (int q = 0; q < (cs ? 1 : p.N); q++) {
+                    const size_t i = (size_t)(n + q) * Cp + c;
+                    const unsigned int ad = (cs && t == t0) ? ad0 : __ldcg(p.amax + i * 2), ax = (cs && t == t0) ? ax0 : __ldcg(p.amax + i * 2 + 1);
+                    const float bq = rs_c * (ga_abs * __uint_as_float(ad) + fabsf(m.x) + __uint_as_float(ax) * fabsf(m.y));
+                    b = fmaxf(b, bq < 3.0e38f ? bq : 3.0e38f);
+                }
+                bmax = fmaxf(bmax, b);
+            }
+            // one shared-memory atomic per warp (non-negative floats order like their bits)
+            const unsigned int wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(bmax));
+            if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(&bound_s), wmax);
+        }
+        named_bar_sync(kFusedBar, 256);
+        const float bound = bound_s;
+        if (prof_on) prof[3] = globaltimer_ns();
+        bound_max = fmaxf(bound_max, bound);
+        const float want = dy_scale_from_bound(bound);
+        if (dscale == 0.f) dscale = want;
+        else if (want < dscale) {
+            // a later round is larger than the scale chosen so far allows: bring the samples already written down to the
+            // new scale (a power of two: exact).  Rare -- the samples of one batch have similar gradient magnitudes.
+            const float factor = want / dscale;
+            const size_t units = (size_t)n0 * p.Ch * ((GENERAL && p.s2d) ? (size_t)p.Dw * p.Hw * p.Ww : (size_t)total);      // 16-byte units
+            uint4* q = reinterpret_cast<uint4*>(p.dy);
+            const __half2 f2 = __float2half2_rn(factor);
+            for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < units; i += (size_t)gridDim.x * 256) {
+                uint4 v = __ldcg(q + i);
+                __half2* h = reinterpret_cast<__half2*>(&v);
+                h[0] = __hmul2(h[0], f2); h[1] = __hmul2(h[1], f2); h[2] = __hmul2(h[2], f2); h[3] = __hmul2(h[3], f2);
+                q[i] = v;
+            }
+            dscale = want;
+        }
+        // ---------------- phase C: the backward formula, newest item first
+        {
+            uint2* dy = reinterpret_cast<uint2*>(p.dy);
+            int cur_sp = -1, n = 0, cqp = 0;
+            int sp = (i1 - 1) / nchunks, chunk = (i1 - 1) - sp * nchunks;
+            QuadConsts c;
+            c.thr = relu_thr;
+            float4 ga, m1, m2, rk;
+            for (int j = cnt - 1; j >= 0; j--) {
+                if (sp != cur_sp) {
+                    cur_sp = sp;
+                    n = n0 + sp / Cqp; cqp = sp - (sp / Cqp) * Cqp;
+                    const int cq = 2 * cqp + hsel;
+                    const float4* row = ctab[cs * (n - ctab_n0) * p.Cq + cq];
+                    c.mu = row[0]; c.rs = row[1]; c.sc = row[2]; c.sh = row[3];
+                    ga = row[4];
+                    {
+                        // the means of the four channels' groups
+                        float mm[4][2];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int ch = min(4 * cq + k, p.C - 1);
+                            float2 m = make_float2(0.f, 0.f);
+                            if (f.mode == 1) m = gm[(n - n0) * f.G + ch / (p.C / f.G)];
+                            else if (f.mode == 2) m = gm[ch];
+                            mm[k][0] = 4 * cq + k < p.C ? m.x : 0.f; mm[k][1] = 4 * cq + k < p.C ? m.y : 0.f;
+                        }
+                        m1 = make_float4(mm[0][0], mm[1][0], mm[2][0], mm[3][0]);
+                        m2 = make_float4(mm[0][1], mm[1][1], mm[2][1], mm[3][1]);
+                    }
+                    rk = make_float4(c.rs.x * dscale, c.rs.y * dscale, c.rs.z * dscale, c.rs.w * dscale);
+                }
+                const int v0 = chunk * kItemVox, nv = min(kItemVox, total - v0);
+                const int s = j % S;
+                if (j < cnt - S) {                    // not one of the items phase A left in the ring
+                    const unsigned long long tw = prof_on ? globaltimer_ns() : 0;
+                    mbar_wait(&full[s], (parity >> s) & 1u);
+                    if (prof_on) wait_c += globaltimer_ns() - tw;
+                    parity ^= 1u << s;
+                }
+                const uint32_t sbase = ring_thread + (uint32_t)s * stage_bytes;
+                if (nv == kItemVox) fused_item_apply<GENERAL, G1, true>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy);
+                else fused_item_apply<GENERAL, G1, false>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy);
+                if (j - S >= 0 || round + 1 < nrounds) {                      // the producer refills this stage
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                }
+                if (--chunk < 0) { chunk = nchunks - 1; sp--; }
+            }
+        }
+        if (prof_on) { prof[4] = globaltimer_ns(); prof[6] = wait_c; }
+        named_bar_sync(kFusedBar, 256);               // gm / ctab / bound_s are rewritten by the next round
+    }
+    if (blockIdx.x != 0) return;
+    // ---------------- CTA 0: the tensor's scale, and the parameter gradients from the complete sums (after the last grid
+    // barrier every (n, c) entry is final): dgamma = sum dr xhat, dbeta = sum dr, dbias = sum dy
+    if (threadIdx.x == 0) {
+        if (dscale == 0.f) dscale = 1.f;
+        p.dy_scale[0] = bound_max; p.dy_scale[1] = dscale; p.dy_scale[2] = 1.f / dscale;
+    }
+    if (!f.dgamma && !f.dbeta && !f.dbias) return;
+    for (int c = threadIdx.x; c < p.C; c += 256) {
+        const double ga = (p.gamma && f.mode != 0) ? (double)p.gamma[c] : 1.0;
+        double dg = 0.0, db = 0.0, dbi = 0.0;
+        double m1b = 0.0, m2b = 0.0;                  // batch statistics: one pair of means per channel
+        if (f.mode == 2) {
+            for (int q = 0; q < p.N; q++) { m1b += __ldcg(p.sums + ((size_t)q * Cp + c) * 2); m2b += __ldcg(p.sums + ((size_t)q * Cp + c) * 2 + 1); }
+            m1b *= ga * f.inv_count; m2b *= ga * f.inv_count;
+        }
+        for (int n = 0; n < p.N; n++) {
+            const size_t i = (size_t)n * Cp + c;
+            const double S1 = __ldcg(p.sums + i * 2), S2 = __ldcg(p.sums + i * 2 + 1);
+            dg += S2; db += S1;
+            if (f.dbias) {
+                double m1 = m1b, m2 = m2b;
+                if (f.mode == 1) {
+                    const int cg = p.C / f.G, c_first = (c / cg) * cg;
+                    m1 = 0.0; m2 = 0.0;
+                    for (int q = 0; q < cg; q++) {
+                        const double gq = p.gamma ? (double)p.gamma[c_first + q] : 1.0;
+                        m1 += gq * __ldcg(p.sums + ((size_t)n * Cp + c_first + q) * 2);
+                        m2 += gq * __ldcg(p.sums + ((size_t)n * Cp + c_first + q) * 2 + 1);
+                    }
+                    m1 *= f.inv_count; m2 *= f.inv_count;
+                }
+                const double rr = p.rstd ? (double)p.rstd[i] : 1.0, mu = p.mean ? (double)p.mean[i] : 0.0;
+                double sum_xhat = 0.0;
+                if (f.mode == 1 || f.mode == 2) sum_xhat = rr * (f.fwd_stats[((size_t)n * p.C + c) * 2] - f.S * mu);
+                dbi += rr * (ga * S1 - f.S * m1 - m2 * sum_xhat);
+            }
+        }
+        if (f.dgamma) f.dgamma[c] = (float)dg;
+        if (f.dbeta) f.dbeta[c] = (float)db;
+        if (f.dbias) f.dbias[c] = (float)dbi;
     }
 }
 
@@ -1188,6 +1808,88 @@ int e3b_norm_bwd_apply(const e3b_norm_bwd_args* a, void* stream)
     const dim3 grid((unsigned)((Sg + 256 * kAppVpt - 1) / (256 * kAppVpt)), p.Cq, a->N);
     norm_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("norm_bwd_apply");
+}
+
+int e3b_norm_bwd_fused(const e3b_norm_bwd_args* a, void* stream)
+{
+    NormBwdDev p;
+    if (fill_bwd(a, p)) return 1;
+    const int Cp = p.Cq * 4;
+    if (!a->amax || !a->dy_scale || !a->sums) return set_error("norm_bwd_fused: sums / amax / dy_scale buffers are required");
+    if (Cp > kFusedMaxCp) return set_error("norm_bwd_fused: more than %d channels: use the reduce / finalize / apply kernels", kFusedMaxCp);
+    if (a->mode == 1 && (a->G <= 0 || a->C % a->G)) return set_error("norm_bwd: bad group count");
+    if (a->dbias && (a->mode == 1 || a->mode == 2) && !a->fwd_stats) return set_error("norm_bwd: dbias needs fwd_stats");
+    if (a->s2d && (a->D % a->sd || a->H % a->sh || a->W % a->sw))
+        return set_error("norm_bwd_fused: space-to-depth output needs extents divisible by the stride (use the three-kernel path)");
+    const size_t sums_b = sizeof(double) * 2 * (size_t)a->N * Cp, amax_b = sizeof(unsigned int) * 2 * (size_t)a->N * Cp;
+    if (!((char*)a->amax == (char*)a->sums + sums_b && (char*)a->dy_scale == (char*)a->amax + amax_b))
+        return set_error("norm_bwd_fused: sums, amax and dy_scale must be one contiguous workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(a->sums, 0, sums_b + amax_b + sizeof(float) * 4, st);
+    if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
+    FusedDev f;
+    f.mode = a->mode; f.G = a->G; f.S = (double)a->D * a->H * a->W; f.fwd_stats = a->fwd_stats;
+    f.dgamma = a->dgamma; f.dbeta = a->dbeta; f.dbias = a->dbias;
+    f.counter = reinterpret_cast<unsigned int*>(a->dy_scale + 3);
+    f.per_sample = a->mode != 2;
+    f.Cp = Cp;
+    f.prof = getenv("E3B_FUSED_PROF") != nullptr;
+    f.inv_count = a->mode == 1 ? 1.0 / (f.S * (a->C / a->G)) : (a->mode == 2 ? 1.0 / (f.S * a->N) : 1.0);
+    f.dHW = make_fastdiv(p.H * p.W); f.dW = make_fastdiv(p.W);
+    f.dwd = make_fastdiv(p.wd); f.dwh = make_fastdiv(p.wh); f.dww = make_fastdiv(p.ww);
+    // persistent grid of co-resident CTAs (the kernel contains grid barriers): a cooperative launch, which the driver
+    // only starts when every CTA fits at once -- also next to kernels of other streams
+    const bool general = p.gp != nullptr || p.g1_crop != 0 || p.s2d != 0 || p.g0 == nullptr;
+    f.g1_bulk = (p.g1 != nullptr && !p.g1_crop) ? 1 : 0;
+    const int nb = 1 + (p.g0 != nullptr) + f.g1_bulk;
+    const int kRingBytes = 96 * 1024;               // two CTAs per SM
+    f.stages = kRingBytes / (nb * kItemTensorBytes);
+    if (f.stages > kFusedMaxStages) f.stages = kFusedMaxStages;
+    const size_t smem = (size_t)f.stages * nb * kItemTensorBytes;
+    void (*kern)(const NormBwdDev, const FusedDev) = general ? norm_bwd_fused_kernel<true, false>
+                                                     : (f.g1_bulk ? norm_bwd_fused_kernel<false, true> : norm_bwd_fused_kernel<false, false>);
+    static int per_sm[kMaxDevices][2][4] = {};
+    const int dev = current_device();
+    if (!per_sm[dev][general][nb]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes) != cudaSuccess)
+            return set_error("norm_bwd_fused: cannot reserve %d bytes of shared memory", kRingBytes);
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kFusedThreads, smem) != cudaSuccess || n < 1)
+            return set_error("norm_bwd_fused: occupancy query failed");
+        per_sm[dev][general][nb] = n > 2 ? 2 : n;
+    }
+    // samples per round: as many as keep the round's working set (sources + dy) inside L2, a divisor of N
+    f.nset = a->N;
+    if (f.per_sample) {
+        const double per_sample = (double)Cp * f.S * (4.0 * nb + 2.0);
+        const double budget = 100e6;                // of the 126 MB L2
+        long long lim = (long long)(budget / per_sample);
+        if (lim > kCtabSlots / p.Cq) lim = kCtabSlots / p.Cq;
+        if (lim < 1) lim = 1;
+        if (lim > a->N) lim = a->N;
+        while (a->N % lim) lim--;
+        f.nset = (int)lim;
+    }
+    const long long items = (long long)f.nset * (p.Cq / 2) * (((long long)p.D * p.H * p.W + kItemVox - 1) / kItemVox);
+    if (items >= (1ll << 31)) return set_error("norm_bwd_fused: tensor too large");
+    long long grid = (long long)num_sms() * per_sm[dev][general][nb];
+    if (grid > items) grid = items;
+    if (grid < 1) grid = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, p, f);
+    if (e != cudaSuccess) return set_error("norm_bwd_fused launch: %s", cudaGetErrorString(e));
+    return check_launch("norm_bwd_fused");
+}
+
+int e3b_debug_fused_prof(unsigned long long* out64)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out64, g_fused_prof, sizeof(unsigned long long) * 64);
+    if (e != cudaSuccess) return set_error("e3b_debug_fused_prof: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 int e3b_head(const e3b_head_args* a, void* stream)

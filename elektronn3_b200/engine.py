@@ -12,6 +12,7 @@ The sequence of operations follows the reference ``UNet.forward`` (models/unet.p
 derives from them.
 """
 import ctypes
+import os
 
 import torch
 
@@ -794,9 +795,16 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True):
     args.relu = 1
     lib = L.lib()
     st = _stream()
-    L.check(lib.e3b_norm_bwd_reduce(ctypes.byref(args), st), 'norm_bwd_reduce')
-    L.check(lib.e3b_norm_bwd_finalize(ctypes.byref(args), st), 'norm_bwd_finalize')
-    L.check(lib.e3b_norm_bwd_apply(ctypes.byref(args), st), 'norm_bwd_apply')
+    fused = Cp <= 512 and os.environ.get('E3B_NORM_BWD', 'fused') != 'split'
+    if s2d is not None and (a.D % s2d[0] or a.H % s2d[1] or a.W % s2d[2]):
+        fused = False              # autocrop dropped fine voxels: the three-kernel path zero-fills them
+    if fused:
+        # one persistent kernel: per sample reduce -> grid barrier -> apply, the second read served by L2
+        L.check(lib.e3b_norm_bwd_fused(ctypes.byref(args), st), 'norm_bwd_fused')
+    else:
+        L.check(lib.e3b_norm_bwd_reduce(ctypes.byref(args), st), 'norm_bwd_reduce')
+        L.check(lib.e3b_norm_bwd_finalize(ctypes.byref(args), st), 'norm_bwd_finalize')
+        L.check(lib.e3b_norm_bwd_apply(ctypes.byref(args), st), 'norm_bwd_apply')
     return dy, (pg[0] if has_affine else None), (pg[1] if has_affine else None), (pg[2] if want_bias else None)
 
 

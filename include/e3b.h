@@ -128,6 +128,8 @@ int e3b_debug_zs_read(uint32_t* out, int n);
 /* Developer aid (E3B_ZS_PROF): per-role cycle counters of the z-stacked kernel summed over CTAs (producer total /
  * wait, issuer total / waits / issue, epilogue total / wait / load / store / statistics / release). */
 int e3b_debug_zs_prof(unsigned long long* out16, int reset);
+/* phase timeline of the last e3b_norm_bwd_fused launch made with E3B_FUSED_PROF set: [cta 2][round 4][stamp 8] (ns) */
+int e3b_debug_fused_prof(unsigned long long* out64);
 
 /* Weight gradient: dW[tap][ci][co] = sum_voxels x[v + tap - pad][ci] * dy[v][co]  (conv backward-filter
  * of nn.Conv3d at unet.py:131-149; with taps=1 on (x, space-to-depth dy) also ConvTranspose's).
@@ -202,6 +204,11 @@ typedef struct e3b_norm_bwd_args {
                                                   (g1_D,g1_H,g1_W) and is added inside the box starting at (g1_od,g1_oh,g1_ow) */
     int32_t g1_od, g1_oh, g1_ow, g1_D, g1_H, g1_W;
 } e3b_norm_bwd_args;
+/* The three passes as ONE persistent kernel (reduce, grid barrier, finalize, apply), one sample at a time for per-sample
+ * statistics (group / instance / none): the apply pass re-reads the sample out of L2, so y and the incoming gradient cross
+ * HBM once.  Needs sums, amax and dy_scale as one contiguous workspace (in this order), at most 512 channels and, for
+ * s2d, extents divisible by the stride; otherwise use the three calls below. */
+int e3b_norm_bwd_fused(const e3b_norm_bwd_args* args, void* stream);
 int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* args, void* stream);
 int e3b_norm_bwd_finalize(const e3b_norm_bwd_args* args, void* stream);
 int e3b_norm_bwd_apply(const e3b_norm_bwd_args* args, void* stream);

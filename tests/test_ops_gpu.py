@@ -397,9 +397,15 @@ def _norm_ref(y, mode, G, gamma, beta, rm, rv, eps=1e-5):
 @pytest.mark.parametrize('mode,G,C,sp,pool', [(1, 8, 32, (6, 8, 10), None), (1, 8, 16, (5, 7, 9), (2, 2, 2)),
                                               (2, 1, 8, (4, 6, 8), (2, 2, 2)), (2, 1, 24, (3, 9, 8), (1, 2, 2)),
                                               (0, 1, 8, (4, 6, 8), (2, 2, 2)), (1, 3, 3, (4, 4, 4), None),
-                                              (1, 4, 8, (2, 3, 136), None), (2, 1, 8, (2, 4, 132), (1, 2, 2))])
-def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
-    N = 2
+                                              (1, 4, 8, (2, 3, 136), None), (2, 1, 8, (2, 4, 132), (1, 2, 2)),
+                                              (1, 2, 12, (4, 5, 6), None), (1, 4, 64, (4, 8, 8), None)])
+@pytest.mark.parametrize('path', ['fused', 'split', 'fused-rescale'])
+def test_norm_act_pool_forward_backward(eng, monkeypatch, mode, G, C, sp, pool, path):
+    """`path`: the one-kernel backward (reduce -> grid barrier -> apply per sample) or the three-kernel one; 'fused-rescale'
+    makes the second sample's gradient 2^12 times larger, so the per-tensor fp16 scale chosen after sample 0 has to be
+    lowered and sample 0 re-scaled in place."""
+    monkeypatch.setenv('E3B_NORM_BWD', 'split' if path == 'split' else 'fused')
+    N = 3 if path == 'fused-rescale' else 2
     rs = np.random.RandomState(31)
     y = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
     gamma = torch.from_numpy((1 + 0.2 * rs.standard_normal(C)).astype(np.float32)).cuda()
@@ -436,10 +442,14 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
         assert_close(rv, rvd, 1e-5, 'running_var')
     # backward: g0 on a, gp on pooled
     g0 = torch.from_numpy(rs.standard_normal(tuple(a_ref.shape)).astype(np.float32)).cuda()
+    if path == 'fused-rescale':
+        g0[1] *= 4096.0
     loss = (a_ref * g0.double()).sum()
     gpq = None
     if pool is not None:
         gp = torch.from_numpy(rs.standard_normal(tuple(outs[1].shape)).astype(np.float32)).cuda()
+        if path == 'fused-rescale':
+            gp[1] *= 4096.0
         loss = loss + (outs[1] * gp.double()).sum()
         gpq = qp32(eng, gp)
     loss.backward()
@@ -456,7 +466,12 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
     u.pooled = pooled
     dy, dgamma, dbeta, dbias = eng._norm_bwd(u, C, qp32(eng, g0), gp=gpq)
     assert dy.half and dy.scale is not None
-    assert_close(from_qh_ref(dy, C), yd.grad, 1e-3, 'norm bwd dy')
+    if path == 'fused-rescale' and mode != 2:
+        # per sample: the small samples sit 12 bits below the large one in the shared fp16 scale (fp16 subnormal steps)
+        for n in range(N):
+            assert_close(from_qh_ref(dy, C)[n], yd.grad[n], 1e-3 if n == 1 else 2e-2, 'norm bwd dy sample %d' % n)
+    else:
+        assert_close(from_qh_ref(dy, C), yd.grad, 1e-3, 'norm bwd dy')
     # the fp16 scale is a power of two that brings the largest |dy| into (2^10, 2^14]
     k = torch.log2(dy.scale[1]).item()
     assert k == round(k) and abs(dy.scale[1].item() * dy.scale[2].item() - 1.0) < 1e-6
@@ -469,9 +484,11 @@ def test_norm_act_pool_forward_backward(eng, mode, G, C, sp, pool):
     assert (dbias.double() - ref_dbias).abs().max().item() / scale < 1e-4
 
 
-def test_norm_backward_space_to_depth(eng):
-    """norm0/act0 backward of UpConv written tap-major for the transposed conv's dgrad GEMM, cropped fine grid"""
-    N, C, fine, s = 1, 8, (5, 7, 8), (2, 2, 2)
+@pytest.mark.parametrize('fine', [(5, 7, 8), (4, 6, 8)])
+def test_norm_backward_space_to_depth(eng, fine):
+    """norm0/act0 backward of UpConv written tap-major for the transposed conv's dgrad GEMM; (5, 7, 8): cropped fine
+    grid (three-kernel path), (4, 6, 8): the one-kernel path"""
+    N, C, s = 2, 8, (2, 2, 2)
     rs = np.random.RandomState(5)
     y = torch.from_numpy(rs.standard_normal((N, C) + fine).astype(np.float32)).cuda()
     g0 = torch.from_numpy(rs.standard_normal((N, C) + fine).astype(np.float32)).cuda()
