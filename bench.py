@@ -39,7 +39,7 @@ FWD_BWD_GFLOP = 1175.75          # algorithmic, SURVEY.md 8(d) / BASELINE.md 2.3
 # dominant kernel for the roofline: the conv of up_convs.1.conv1 (virtual concat 32+32 -> 32 at 4 x 64^3)
 DOM = dict(N=4, C0=32, C1=32, Co=32, S=64)
 DOM_GFLOP = 2 * 4 * 64 ** 3 * 32 * (64 * 27) / 1e9     # 115.96
-DOM_TRAFFIC = None               # dram__bytes_read + write of that launch from the round's ncu --set full capture (profiles/)
+DOM_TRAFFIC = 507.0e6            # dram__bytes_read + write of that launch: ncu --set full, profiles/r02_ncu_zs_concat.csv (cold L2; 268 MB algorithmic)
 
 PRED_MODEL_KW = dict(n_blocks=4, start_filts=32)
 PRED_VOL = (512, 512, 256)
