@@ -182,6 +182,34 @@ E3B_DEVINL void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// TMEM -> registers without waiting: several loads are put in flight, then ONE tcgen05.wait::ld (tmem_ld_wait32)
+E3B_DEVINL void tmem_ld16_raw(uint32_t taddr, uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// wait for the loads, then pin the 32 destination registers behind the wait (the compiler must not consume them earlier)
+E3B_DEVINL void tmem_ld_wait32(uint32_t* r)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+    asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                      "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
+
+// 32-byte global store (two adjacent 16-byte units; the address must be 32-byte aligned): one full sector per lane
+E3B_DEVINL void st_global_256(void* p, const uint4& a, const uint4& b)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+                 "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 // round-to-nearest fp32 -> tf32 (10 explicit mantissa bits).  The tensor core ignores the low 13 bits of
 // its fp32 operands (truncation, biased); tensors that feed an MMA are stored pre-rounded instead.
 E3B_DEVINL float tf32_rn(float x) {

@@ -16,9 +16,10 @@
 //    traffic is ~1.4x the activation size instead of 27x.
 //  * weights are pre-packed into the exact smem image (K-major, no swizzle) and streamed with 1D bulk
 //    copies in tap groups through their own mbarrier ring.
-//  * warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..5 epilogue
-//    (tcgen05.ld -> +bias -> [ReLU] -> per-channel sum / sum-of-squares for the following
-//    Group/BatchNorm -> coalesced 16-byte stores).  Two TMEM accumulator sets ping-pong so the epilogue
+//  * warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..5 and 6..9 two epilogue
+//    warpgroups on alternate 16-column groups (tcgen05.ld -> +bias -> [ReLU] -> per-channel sum /
+//    sum-of-squares for the following Group/BatchNorm -> coalesced 16-byte stores; the transposed conv's
+//    scatter pairs the two x taps of a coarse voxel into one 32-byte store).  Two TMEM accumulator sets ping-pong so the epilogue
 //    of tile i overlaps the MMAs of tile i+1.  CTAs are persistent over a static tile schedule.
 #include "common.cuh"
 #include "kernels.h"
@@ -27,7 +28,8 @@
 namespace e3b {
 
 static constexpr int kTX = 8, kTY = 16;
-static constexpr int kThreads = 192;
+static constexpr int kThreads = 320;      // warp 0 producer, warp 1 MMA issuer, warps 2..9: two epilogue warpgroups
+static constexpr int kEpiThreads = 256;
 
 struct ConvTcParams {
     // geometry
@@ -73,7 +75,7 @@ __device__ unsigned long long g_conv_dbg[16];
 // per-CTA statistics accumulators -> global [N][Cstat][2] (fp64 atomics: a few hundred per CTA, not per tile)
 E3B_DEVINL void flush_stats(const ConvTcParams& p, double* cta_stats, int n, int nt, int etid) {
     const int nslots = p.scatter ? (p.Cup < kStatSlots ? p.Cup : kStatSlots) : (p.NT < kStatSlots ? p.NT : kStatSlots);
-    for (int i = etid; i < nslots * 2; i += 128) {
+    for (int i = etid; i < nslots * 2; i += kEpiThreads) {
         const int si = i >> 1;
         const int ch = p.scatter ? si : nt * p.NT + si;
         const double v = cta_stats[i];
@@ -148,7 +150,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.SA; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < p.SB; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_barrier_init();
         tma_prefetch_desc(&tmap0);
         if (p.chunks1) tma_prefetch_desc(&tmap1);
@@ -253,11 +255,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         DBG_ACC(7, t_all);
         if (p.debug && leader) for (int i = 3; i < 8; i++) atomicAdd(&g_conv_dbg[i], dbg[i]);
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;          // GEMM row inside the tile
         const int ry = row >> 3, rx = row & 7;
-        const int etid = threadIdx.x - 64;      // 0..127
+        const int etid = threadIdx.x - 64;      // 0..255
+        const int eg = (warp - 2) >> 2;          // epilogue warpgroup: the two groups take alternate 16-column groups
         // butterfly transpose-reduce leaves column (bit-reversed low nibble of the lane) in lanes 0..15
         const int bcol = ((lane & 1) << 3) | ((lane & 2) << 1) | ((lane & 4) >> 1) | ((lane & 8) >> 3);
         int cur_n = -1, cur_nt = -1;
@@ -271,9 +274,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             decode_tile(p, t, nt, n, z0, y0, x0);
             if (p.stats && (n != cur_n || (!p.scatter && nt != cur_nt))) {
                 // the per-CTA statistics accumulators belong to one (sample, N tile): flush on change
-                named_bar_sync(1, 128);
+                named_bar_sync(1, kEpiThreads);
                 if (cur_n >= 0) flush_stats(p, cta_stats, cur_n, cur_nt, etid);
-                named_bar_sync(1, 128);
+                named_bar_sync(1, kEpiThreads);
                 cur_n = n; cur_nt = nt;
             }
             DBG_T0(t0);
@@ -287,7 +290,116 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             // visited channel-major so that the statistics of a channel group are reduced once for all taps.
             const int cspan = (p.scatter && p.Cup < p.NT) ? p.Cup : p.NT;      // columns per tap inside this tile
             const int ntp = p.NT / cspan;                                      // taps inside this tile
-            for (int cg = 0; cg < cspan; cg += 16) {
+            // Transposed conv with stride 2 along x: the taps (.., tk = 0) and (.., tk = 1) of a coarse voxel are adjacent
+            // fine voxels.  Handling them together turns two half-sector stores (16 B at a 32 B stride) into one 32-byte
+            // store per lane -- the scatter epilogue is bound by L2 write transactions, not by bytes.
+            const bool pair_x = p.scatter && p.sw == 2 && (ntp & 1) == 0;
+            const bool wide_ok = (p.Ws & 1) == 0;          // every fine row starts 32-byte aligned
+            for (int cg = eg * 16; pair_x && cg < cspan; cg += 32) {
+                float s[16], ss[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) { s[j] = 0.f; ss[j] = 0.f; }
+                const int co = (nt * p.NT + cg) % p.Cup;
+                float bias_v[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) bias_v[j] = (p.bias && co + j < p.n_bias) ? __ldg(p.bias + co + j) : 0.f;
+                for (int tp = 0; tp < ntp; tp += 2) {
+                    const int cb = tp * cspan + cg;
+                    const int tapi = (nt * p.NT + cb) / p.Cup;          // even: tk = 0; its partner tapi + 1 has tk = 1
+                    const int ti = tapi / (p.sh * p.sw), tj = (tapi / p.sw) % p.sh;
+                    for (int pl = 0; pl < npl; pl++) {
+                        const int z = z0 + pl;
+                        uint32_t r[32];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + (uint32_t)(pl * p.NT + cb);
+                        tmem_ld16_raw(taddr, r);
+                        tmem_ld16_raw(taddr + (uint32_t)cspan, r + 16);
+                        tmem_ld_wait32(r);
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            v[j] = fmaf(__uint_as_float(r[j]), oscale, bias_v[j & 15]);
+                            if (p.relu) v[j] = fmaxf(v[j], 0.f);
+                        }
+                        const int fz = z * p.sd + ti, fy = y * p.sh + tj, fx = x * 2;
+                        const bool sv0 = valid && fz < p.Ds && fy < p.Hs && fx < p.Ws;
+                        const bool sv1 = sv0 && fx + 1 < p.Ws;
+                        if (sv0) {
+                            if (p.half_out) {
+                                // operand tensor (QH): 16 channels = the 16-byte units of planes co/8 and co/8 + 1
+#pragma unroll
+                                for (int j8 = 0; j8 < 2; j8++) {
+                                    const int hpl = (co >> 3) + j8;
+                                    if (hpl < p.cq0_alloc) {
+                                        const uint2 a0 = pack_half4(v[j8 * 8], v[j8 * 8 + 1], v[j8 * 8 + 2], v[j8 * 8 + 3]);
+                                        const uint2 a1 = pack_half4(v[j8 * 8 + 4], v[j8 * 8 + 5], v[j8 * 8 + 6], v[j8 * 8 + 7]);
+                                        const uint2 b0 = pack_half4(v[16 + j8 * 8], v[16 + j8 * 8 + 1], v[16 + j8 * 8 + 2], v[16 + j8 * 8 + 3]);
+                                        const uint2 b1 = pack_half4(v[16 + j8 * 8 + 4], v[16 + j8 * 8 + 5], v[16 + j8 * 8 + 6], v[16 + j8 * 8 + 7]);
+                                        uint4* o = reinterpret_cast<uint4*>(p.dst0) +
+                                                   (((((size_t)n * p.cq0_alloc + hpl) * p.Ds + fz) * p.Hs + fy) * (size_t)p.Ws + fx);
+                                        const uint4 u0 = make_uint4(a0.x, a0.y, a1.x, a1.y), u1 = make_uint4(b0.x, b0.y, b1.x, b1.y);
+                                        if (sv1 && wide_ok) st_global_256(o, u0, u1);
+                                        else { o[0] = u0; if (sv1) o[1] = u1; }
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; j4++) {
+                                    const int cq = (co >> 2) + j4;
+                                    if (cq < p.cq0_alloc) {
+                                        float4* o = reinterpret_cast<float4*>(p.dst0) +
+                                                    (((((size_t)n * p.cq0_alloc + cq) * p.Ds + fz) * p.Hs + fy) * (size_t)p.Ws + fx);
+                                        const uint4 u0 = make_uint4(__float_as_uint(v[j4 * 4]), __float_as_uint(v[j4 * 4 + 1]),
+                                                                    __float_as_uint(v[j4 * 4 + 2]), __float_as_uint(v[j4 * 4 + 3]));
+                                        const uint4 u1 = make_uint4(__float_as_uint(v[16 + j4 * 4]), __float_as_uint(v[16 + j4 * 4 + 1]),
+                                                                    __float_as_uint(v[16 + j4 * 4 + 2]), __float_as_uint(v[16 + j4 * 4 + 3]));
+                                        if (sv1 && wide_ok) st_global_256(o, u0, u1);
+                                        else { *reinterpret_cast<uint4*>(o) = u0; if (sv1) *reinterpret_cast<uint4*>(o + 1) = u1; }
+                                    }
+                                }
+                            }
+                        }
+                        if (p.stats && sv0) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
+                            if (sv1) {
+#pragma unroll
+                                for (int j = 0; j < 16; j++) { s[j] += v[16 + j]; ss[j] = fmaf(v[16 + j], v[16 + j], ss[j]); }
+                            }
+                        }
+                    }
+                }
+                if (p.stats) {
+                    // per-channel sum / sumsq over the warp's 32 rows x npl planes x taps: 16-value butterfly
+#pragma unroll
+                    for (int step = 0; step < 4; step++) {
+                        const int keepn = 8 >> step;
+                        const int bit = 1 << step;
+                        const bool upper = (lane & bit) != 0;
+#pragma unroll
+                        for (int j = 0; j < keepn; j++) {
+                            float send_s = upper ? s[j] : s[j + keepn];
+                            float send_q = upper ? ss[j] : ss[j + keepn];
+                            float keep_s = upper ? s[j + keepn] : s[j];
+                            float keep_q = upper ? ss[j + keepn] : ss[j];
+                            s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                            ss[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+                        }
+                    }
+                    const float fs = s[0] + __shfl_xor_sync(0xffffffffu, s[0], 16);
+                    const float fq = ss[0] + __shfl_xor_sync(0xffffffffu, ss[0], 16);
+                    if (lane < 16) {
+                        const int si = co + bcol;
+                        if (si < kStatSlots) {
+                            atomicAdd(&cta_stats[si * 2], (double)fs);
+                            atomicAdd(&cta_stats[si * 2 + 1], (double)fq);
+                        } else if (si < p.Cstat) {
+                            atomicAdd(p.stats + ((size_t)n * p.Cstat + si) * 2, (double)fs);
+                            atomicAdd(p.stats + ((size_t)n * p.Cstat + si) * 2 + 1, (double)fq);
+                        }
+                    }
+                }
+            }
+            for (int cg = eg * 16; !pair_x && cg < cspan; cg += 32) {
                 float s[16], ss[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++) { s[j] = 0.f; ss[j] = 0.f; }
@@ -413,7 +525,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         DBG_ACC(9, t_all);
         if (p.debug && etid == 0) for (int i = 8; i < 10; i++) atomicAdd(&g_conv_dbg[i], dbg[i]);
         if (p.stats) {
-            named_bar_sync(1, 128);
+            named_bar_sync(1, kEpiThreads);
             if (cur_n >= 0) flush_stats(p, cta_stats, cur_n, cur_nt, etid);
         }
     }

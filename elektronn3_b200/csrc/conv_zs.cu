@@ -176,26 +176,6 @@ E3B_DEVINL void zs_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* dbg, 
 
 E3B_DEVINL void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// TMEM -> registers without waiting: several loads are put in flight, then ONE tcgen05.wait::ld (tmem_ld_wait32)
-E3B_DEVINL void tmem_ld16_raw(uint32_t taddr, uint32_t* r)
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-// wait for the loads, then pin the 32 destination registers behind the wait (the compiler must not consume them earlier)
-E3B_DEVINL void tmem_ld_wait32(uint32_t* r)
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
-    asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                      "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
-}
-
 // Optional cycle accounting of the pipeline roles (E3B_ZS_PROF, scripts/zs_bench.py): summed over CTAs.
 __device__ unsigned long long g_zs_prof[16];
 #define ZP_T0(var) long long var = 0; if (p.prof) var = clock64()

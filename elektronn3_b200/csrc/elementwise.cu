@@ -1834,6 +1834,10 @@ int e3b_norm_bwd_fused(const e3b_norm_bwd_args* a, void* stream)
     f.per_sample = a->mode != 2;
     f.Cp = Cp;
     f.prof = getenv("E3B_FUSED_PROF") != nullptr;
+    if (f.prof) {
+        static const unsigned long long zeros[64] = {0};
+        cudaMemcpyToSymbolAsync(g_fused_prof, zeros, sizeof(zeros), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    }
     f.inv_count = a->mode == 1 ? 1.0 / (f.S * (a->C / a->G)) : (a->mode == 2 ? 1.0 / (f.S * a->N) : 1.0);
     f.dHW = make_fastdiv(p.H * p.W); f.dW = make_fastdiv(p.W);
     f.dwd = make_fastdiv(p.wd); f.dwh = make_fastdiv(p.wh); f.dww = make_fastdiv(p.ww);
