@@ -26,38 +26,35 @@ E3B_DEVINL void store_qh(uint2* __restrict__ qh, const float4& v, int n, int Ch,
 // ------------------------------------------------------------------------------------------------
 // NCDHW box -> QH   (network input, Predictor tile gather)
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_kernel(const float* __restrict__ src, const int32_t* __restrict__ origins, uint2* __restrict__ dst,
-                            int N, int C, int Cq, int D, int H, int W, int Dv, int Hv, int Wv,
-                            int z0, int y0, int x0, int single, int flip)
+// grid: (voxel chunks, 8-channel planes, N); one thread writes one 16-byte unit (8 channels of one voxel): fully
+// coalesced stores, 32-bit index arithmetic (the first version decoded a flat 64-bit index per 8-byte half: 44 us for the
+// 4 MB input of cfg 2, now memory bound).  Padding channels of the 16-channel chunks are written as 0.
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, const int32_t* __restrict__ origins,
+                                                   uint4* __restrict__ dst, int C, int Ch, int D, int H, int W, int Dv, int Hv,
+                                                   int Wv, int z0, int y0, int x0, int single, int flip)
 {
-    // Cq = ceil16(C)/4 fp32 quads per voxel: the padding channels of the 16-channel chunks are written as 0
-    const size_t total = (size_t)N * Cq * D * H * W;
-    const size_t S = (size_t)D * H * W;
+    const int S = D * H * W, HW = H * W;
+    const int ch = blockIdx.y, n = blockIdx.z;
+    int oz = z0, oy = y0, ox = x0;
+    if (origins) { oz = origins[3 * n]; oy = origins[3 * n + 1]; ox = origins[3 * n + 2]; }
     const size_t plane = (size_t)Dv * Hv * Wv;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        size_t r = i;
-        const int x = (int)(r % W); r /= W;
-        const int y = (int)(r % H); r /= H;
-        const int z = (int)(r % D); r /= D;
-        const int cq = (int)(r % Cq);
-        const int n = (int)(r / Cq);
-        int oz = z0, oy = y0, ox = x0;
-        if (origins) { oz = origins[3 * n]; oy = origins[3 * n + 1]; ox = origins[3 * n + 2]; }
+    const float* sb = src + (single ? 0 : (size_t)n * C * plane) + (size_t)ch * 8 * plane;
+    const int nc = min(8, C - ch * 8);                  // real channels in this unit (<= 0: all padding)
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < S; v += gridDim.x * blockDim.x) {
+        const int z = v / HW, r = v - z * HW, y = r / W, x = r - y * W;
         // (flip: the tile is mirrored while it is gathered -- FlipAugment.forward of the Predictor's TTA)
         const int sz = ((flip & 1) ? D - 1 - z : z) + oz, sy = ((flip & 2) ? H - 1 - y : y) + oy,
                   sx = ((flip & 4) ? W - 1 - x : x) + ox;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (sz >= 0 && sz < Dv && sy >= 0 && sy < Hv && sx >= 0 && sx < Wv) {
+        float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (nc > 0 && sz >= 0 && sz < Dv && sy >= 0 && sy < Hv && sx >= 0 && sx < Wv) {
             const size_t vox = ((size_t)sz * Hv + sy) * Wv + sx;
-            const size_t nb = single ? 0 : (size_t)n * C * plane;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int c = cq * 4 + j;
-                if (c < C) v[j] = __ldg(src + nb + (size_t)c * plane + vox);
-            }
+            for (int j = 0; j < 8; j++)
+                if (j < nc) q[j] = __ldg(sb + (size_t)j * plane + vox);
         }
-        const float4 q = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
-        store_qh(dst, q, n, Cq >> 1, cq, S, ((size_t)z * H + y) * W + x);
+        const uint2 lo = pack_half4(tf32_rn(q[0]), tf32_rn(q[1]), tf32_rn(q[2]), tf32_rn(q[3]));
+        const uint2 hi = pack_half4(tf32_rn(q[4]), tf32_rn(q[5]), tf32_rn(q[6]), tf32_rn(q[7]));
+        dst[((size_t)n * Ch + ch) * S + v] = make_uint4(lo.x, lo.y, hi.x, hi.y);
     }
 }
 
@@ -1573,6 +1570,62 @@ __global__ void __launch_bounds__(256) head_bwd_w_kernel(const float* __restrict
     }
 }
 
+// <= 4 classes: one thread per 16-byte unit (8 channels of one voxel): full-sector loads of the activations, the
+// logit gradients are re-read once per 8 channels instead of once per 4, 32-bit indices.  grid: (chunks, Ch, N)
+__global__ void __launch_bounds__(256) head_bwd_w8_kernel(const float* __restrict__ dl, const uint4* __restrict__ a,
+                                                          double* __restrict__ ws, int Cp, int Ch, int Co, int S)
+{
+    constexpr int CO = 4;
+    const int ch = blockIdx.y, n = blockIdx.z;
+    float acc[CO][8], sb[CO];
+#pragma unroll
+    for (int co = 0; co < CO; co++) {
+        sb[co] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[co][j] = 0.f;
+    }
+    const uint4* ap = a + ((size_t)n * Ch + ch) * S;
+    const float* gp = dl + (size_t)n * Co * S;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < S; v += gridDim.x * blockDim.x) {
+        const uint4 u = ap[v];
+        const float4 lo = unpack_half4(make_uint2(u.x, u.y)), hi = unpack_half4(make_uint2(u.z, u.w));
+#pragma unroll
+        for (int co = 0; co < CO; co++) {
+            if (co < Co) {
+                const float g = gp[(size_t)co * S + v];
+                acc[co][0] = fmaf(g, lo.x, acc[co][0]); acc[co][1] = fmaf(g, lo.y, acc[co][1]);
+                acc[co][2] = fmaf(g, lo.z, acc[co][2]); acc[co][3] = fmaf(g, lo.w, acc[co][3]);
+                acc[co][4] = fmaf(g, hi.x, acc[co][4]); acc[co][5] = fmaf(g, hi.y, acc[co][5]);
+                acc[co][6] = fmaf(g, hi.z, acc[co][6]); acc[co][7] = fmaf(g, hi.w, acc[co][7]);
+                sb[co] += g;
+            }
+        }
+    }
+    __shared__ float red[8][CO * 9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int co = 0; co < CO; co++) {
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[co][j] += __shfl_xor_sync(0xffffffffu, acc[co][j], o);
+            sb[co] += __shfl_xor_sync(0xffffffffu, sb[co], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) red[warp][co * 9 + j] = acc[co][j];
+            red[warp][co * 9 + 8] = sb[co];
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < Co * 9; t += blockDim.x) {
+        double sum = 0.0;
+        for (int w = 0; w < 8; w++) sum += (double)red[w][t];
+        const int co = t / 9, j = t % 9;
+        if (j < 8) { if (ch * 8 + j < Cp) atomicAdd(ws + (size_t)co * Cp + ch * 8 + j, sum); }
+        else if (ch == 0) atomicAdd(ws + (size_t)Co * Cp + co, sum);
+    }
+}
+
 __global__ void head_bwd_finish_kernel(const double* __restrict__ ws, float* __restrict__ dw, float* __restrict__ db, int C,
                                        int Cp, int Co)
 {
@@ -1594,10 +1647,11 @@ int e3b_pack_ncdhw(const float* src, void* dst_qp, int N, int C, int D, int H, i
                    int Wv, int z0, int y0, int x0, void* stream)
 {
     if (N <= 0 || C <= 0) return set_error("pack: empty tensor");
-    const int Cq = cpad16(C) / 4;
-    const size_t total = (size_t)N * Cq * D * H * W;
-    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, nullptr, reinterpret_cast<uint2*>(dst_qp),
-                                                                        N, C, Cq, D, H, W, Dv, Hv, Wv, z0, y0, x0, 0, 0);
+    const int Ch = cpad16(C) / 8;
+    if ((long long)D * H * W >= (1ll << 31) || Ch > 65535 || N > 65535) return set_error("pack: tensor too large for the launch grid");
+    const dim3 grid(grid_for((size_t)D * H * W, 256, 4), Ch, N);
+    pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, nullptr, reinterpret_cast<uint4*>(dst_qp), C, Ch, D, H, W, Dv, Hv, Wv,
+                                                        z0, y0, x0, 0, 0);
     return check_launch("pack_ncdhw");
 }
 
@@ -1605,10 +1659,11 @@ int e3b_gather_tiles(const float* vol, const int32_t* origins, void* dst_qp, int
                      int Hv, int Wv, int flip, void* stream)
 {
     if (B <= 0 || C <= 0) return set_error("gather: empty batch");
-    const int Cq = cpad16(C) / 4;
-    const size_t total = (size_t)B * Cq * D * H * W;
-    pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vol, origins, reinterpret_cast<uint2*>(dst_qp),
-                                                                        B, C, Cq, D, H, W, Dv, Hv, Wv, 0, 0, 0, 1, flip);
+    const int Ch = cpad16(C) / 8;
+    if ((long long)D * H * W >= (1ll << 31) || Ch > 65535 || B > 65535) return set_error("gather: tile too large for the launch grid");
+    const dim3 grid(grid_for((size_t)D * H * W, 256, 4), Ch, B);
+    pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(vol, origins, reinterpret_cast<uint4*>(dst_qp), C, Ch, D, H, W, Dv, Hv, Wv,
+                                                        0, 0, 0, 1, flip);
     return check_launch("gather_tiles");
 }
 
@@ -1932,7 +1987,10 @@ int e3b_head_bwd(const float* dl, const void* a, const float* w, float* da, floa
     if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
     int bx = (8 * num_sms()) / Cq; if (bx < 1) bx = 1;
     const int Ch = cpad16(C) / 8;
-    if (Co <= 4) head_bwd_w_kernel<4><<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const uint2*>(a), workspace, N, Cq, Ch, Co, S);
+    if (Co <= 4 && S < ((size_t)1 << 31) && N <= 65535) {
+        int b8 = (8 * num_sms()) / (Ch * N); if (b8 < 1) b8 = 1;
+        head_bwd_w8_kernel<<<dim3(b8, Ch, N), 256, 0, st>>>(dl, reinterpret_cast<const uint4*>(a), workspace, Cp, Ch, Co, (int)S);
+    } else if (Co <= 4) head_bwd_w_kernel<4><<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const uint2*>(a), workspace, N, Cq, Ch, Co, S);
     else head_bwd_w_kernel<kHeadMaxCo><<<dim3(bx, Cq), 256, 0, st>>>(dl, reinterpret_cast<const uint2*>(a), workspace, N, Cq, Ch, Co, S);
     if (check_launch("head_bwd_w")) return 1;
     head_bwd_finish_kernel<<<(Co * C + 127) / 128 + 1, 128, 0, st>>>(workspace, dw, db, C, Cp, Co);
