@@ -1400,18 +1400,18 @@ __global__ void __launch_bounds__(256) head_kernel(const e3b_head_args p, int Cq
     }
     for (int i = threadIdx.x; i < p.Co; i += blockDim.x) sw[p.Co * Cp + i] = p.b ? p.b[i] : 0.f;
     __syncthreads();
-    const uint2* a = reinterpret_cast<const uint2*>(p.a);      // QH operand tensor
+    const uint4* a = reinterpret_cast<const uint4*>(p.a);      // QH operand tensor: 16-byte units of 8 channels
     const int Ch = cpad16(p.C) / 8;
-    const size_t box = (size_t)p.cn_d * p.cn_h * p.cn_w;
-    const size_t total = (size_t)p.N * box;
+    const unsigned box = (unsigned)p.cn_d * p.cn_h * p.cn_w;   // (the launch wrapper checks that N * box fits 32 bits)
+    const unsigned total = (unsigned)p.N * box;
     const size_t S = (size_t)p.D * p.H * p.W;
     const size_t Sd = (size_t)p.Dd * p.Hd * p.Wd;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int n = (int)(i / box);
-        size_t r = i % box;
-        const int x = (int)(r % p.cn_w); r /= p.cn_w;
-        const int y = (int)(r % p.cn_h);
-        const int z = (int)(r / p.cn_h);
+        unsigned r = i - (unsigned)n * box;
+        const int z = (int)(r / ((unsigned)p.cn_h * p.cn_w)); r -= (unsigned)z * p.cn_h * p.cn_w;
+        const int y = (int)(r / (unsigned)p.cn_w);
+        const int x = (int)(r - (unsigned)y * p.cn_w);
         // (flip: the features are the network output on a mirrored tile -- FlipAugment.backward of the TTA)
         const int zi = (p.flip & 1) ? p.D - 1 - (z + p.c0_d) : z + p.c0_d, yi = (p.flip & 2) ? p.H - 1 - (y + p.c0_h) : y + p.c0_h,
                   xi = (p.flip & 4) ? p.W - 1 - (x + p.c0_w) : x + p.c0_w;
@@ -1419,13 +1419,16 @@ __global__ void __launch_bounds__(256) head_kernel(const e3b_head_args p, int Cq
         float acc[CO];
 #pragma unroll
         for (int co = 0; co < CO; co++) acc[co] = co < p.Co ? sw[p.Co * Cp + co] : 0.f;
-        for (int cq = 0; cq < Cq; cq++) {
-            const float4 v = unpack_half4(a[qh_index(n, Ch, cq, S, vin)]);
+        for (int cq = 0; cq < Cq; cq += 2) {
+            // one full unit (8 channels) per load; Cq is even (channels are padded to 8)
+            const uint4 u = a[((size_t)n * Ch + (cq >> 1)) * S + vin];
+            const float4 v = unpack_half4(make_uint2(u.x, u.y)), v2 = unpack_half4(make_uint2(u.z, u.w));
 #pragma unroll
             for (int co = 0; co < CO; co++) {
                 if (co < p.Co) {
                     const float* wr = sw + co * Cp + cq * 4;
                     acc[co] = fmaf(v.x, wr[0], fmaf(v.y, wr[1], fmaf(v.z, wr[2], fmaf(v.w, wr[3], acc[co]))));
+                    acc[co] = fmaf(v2.x, wr[4], fmaf(v2.y, wr[5], fmaf(v2.z, wr[6], fmaf(v2.w, wr[7], acc[co]))));
                 }
             }
         }
@@ -1958,6 +1961,7 @@ int e3b_head(const e3b_head_args* a, void* stream)
     if (a->out_mode == 2 && (a->accumulate || a->round_half)) return set_error("head: accumulate / round_half apply to float outputs");
     const int Cq = cpad8(a->C) / 4;
     const size_t total = (size_t)a->N * a->cn_d * a->cn_h * a->cn_w;
+    if (total >= ((size_t)1 << 32)) return set_error("head: more than 2^32 output voxels in one call");
     const size_t smem = sizeof(float) * ((size_t)a->Co * Cq * 4 + a->Co);
     if (a->Co <= 4) head_kernel<4><<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(*a, Cq);
     else head_kernel<kHeadMaxCo><<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(*a, Cq);

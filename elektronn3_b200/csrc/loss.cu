@@ -27,26 +27,78 @@ E3B_DEVINL void load_probs(const float* __restrict__ x, size_t base, size_t S, i
     }
 }
 
-// sums[3][C] (fp64 atomics): I_c = sum p_c t_c, P_c = sum p_c, T_c = sum t_c.  target: dense int64 (N, S) or one-hot float (N, C, S)
+static constexpr int kVecC = 4;            // the vector path serves <= 4 classes
+// four consecutive voxels of one sample: softmax probabilities p[k][c] from float4 loads per channel
 template <bool SOFTMAX>
+E3B_DEVINL void load_probs4(const float* __restrict__ x, size_t base, size_t S, int C, float (*p)[kVecC])
+{
+    float mx[4] = {-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
+#pragma unroll
+    for (int c = 0; c < kVecC; c++) {
+        if (c < C) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + (size_t)c * S));
+            p[0][c] = v.x; p[1][c] = v.y; p[2][c] = v.z; p[3][c] = v.w;
+            mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z); mx[3] = fmaxf(mx[3], v.w);
+        }
+    }
+    if (SOFTMAX) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < kVecC; c++) if (c < C) { p[k][c] = expf(p[k][c] - mx[k]); sum += p[k][c]; }
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int c = 0; c < kVecC; c++) if (c < C) p[k][c] *= inv;
+        }
+    }
+}
+
+E3B_DEVINL void load_targets4(const long long* __restrict__ target, size_t i, int* t)
+{
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(target + i)), b = __ldg(reinterpret_cast<const longlong2*>(target + i + 2));
+    t[0] = (int)a.x; t[1] = (int)a.y; t[2] = (int)b.x; t[3] = (int)b.y;
+}
+
+// sums[3][C] (fp64 atomics): I_c = sum p_c t_c, P_c = sum p_c, T_c = sum t_c.  target: dense int64 (N, S) or one-hot float (N, C, S)
+// grid: (chunks, N); VEC: four voxels per thread and iteration (S % 4 == 0, dense targets)
+template <bool SOFTMAX, bool VEC>
 __global__ void __launch_bounds__(256) dice_fwd_kernel(const float* __restrict__ x, const long long* __restrict__ target,
                                                        const float* __restrict__ onehot, int N, int C, size_t S, double* __restrict__ sums)
 {
     float aI[kLossMaxC], aP[kLossMaxC], aT[kLossMaxC];
 #pragma unroll
     for (int c = 0; c < kLossMaxC; c++) { aI[c] = 0.f; aP[c] = 0.f; aT[c] = 0.f; }
-    const size_t total = (size_t)N * S;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t n = i / S, v = i - n * S;
-        const size_t base = n * C * S + v;
-        float p[kLossMaxC];
-        load_probs<SOFTMAX>(x, base, S, C, p);
-        const int t = target ? (int)target[i] : -1;
+    const size_t n = blockIdx.y;
+    if (VEC) {
+        for (unsigned v = (blockIdx.x * blockDim.x + threadIdx.x) * 4u; v < (unsigned)S; v += gridDim.x * blockDim.x * 4u) {
+            float p[4][kVecC];
+            int t[4];
+            load_targets4(target, n * S + v, t);
+            load_probs4<SOFTMAX>(x, n * C * S + v, S, C, p);
 #pragma unroll
-        for (int c = 0; c < kLossMaxC; c++) {
-            if (c < C) {
-                const float tc = target ? (c == t ? 1.f : 0.f) : onehot[base + (size_t)c * S];
-                aI[c] = fmaf(p[c], tc, aI[c]); aP[c] += p[c]; aT[c] += tc;
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int c = 0; c < kVecC; c++) {
+                    if (c < C) {
+                        const float tc = c == t[k] ? 1.f : 0.f;
+                        aI[c] = fmaf(p[k][c], tc, aI[c]); aP[c] += p[k][c]; aT[c] += tc;
+                    }
+                }
+            }
+        }
+    } else {
+        for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < (unsigned)S; v += gridDim.x * blockDim.x) {
+            const size_t base = n * C * S + v;
+            float p[kLossMaxC];
+            load_probs<SOFTMAX>(x, base, S, C, p);
+            const int t = target ? (int)target[n * S + v] : -1;
+#pragma unroll
+            for (int c = 0; c < kLossMaxC; c++) {
+                if (c < C) {
+                    const float tc = target ? (c == t ? 1.f : 0.f) : onehot[base + (size_t)c * S];
+                    aI[c] = fmaf(p[c], tc, aI[c]); aP[c] += p[c]; aT[c] += tc;
+                }
             }
         }
     }
@@ -88,7 +140,7 @@ __global__ void dice_finalize_kernel(const double* __restrict__ sums, const floa
     loss[0] = (float)(acc / C);
 }
 
-template <bool SOFTMAX>
+template <bool SOFTMAX, bool VEC>
 __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__ x, const long long* __restrict__ target,
                                                        const float* __restrict__ onehot, const float* __restrict__ coef,
                                                        const float* __restrict__ gout, float* __restrict__ dx, int N, int C, size_t S)
@@ -96,13 +148,41 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
     __shared__ float sc[2 * kLossMaxC];
     if (threadIdx.x < 2 * C) sc[threadIdx.x] = coef[threadIdx.x] * gout[0];
     __syncthreads();
-    const size_t total = (size_t)N * S;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t n = i / S, v = i - n * S;
+    const size_t n = blockIdx.y;
+    if (VEC) {
+        for (unsigned v = (blockIdx.x * blockDim.x + threadIdx.x) * 4u; v < (unsigned)S; v += gridDim.x * blockDim.x * 4u) {
+            float p[4][kVecC];
+            int t[4];
+            const size_t base = n * C * S + v;
+            load_targets4(target, n * S + v, t);
+            load_probs4<SOFTMAX>(x, base, S, C, p);
+            float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int c = 0; c < kVecC; c++)
+                    if (c < C) dot[k] = fmaf(p[k][c], fmaf(sc[c], c == t[k] ? 1.f : 0.f, sc[C + c]), dot[k]);
+            }
+#pragma unroll
+            for (int c = 0; c < kVecC; c++) {
+                if (c < C) {
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float g = fmaf(sc[c], c == t[k] ? 1.f : 0.f, sc[C + c]);
+                        o[k] = SOFTMAX ? p[k][c] * (g - dot[k]) : g;
+                    }
+                    *reinterpret_cast<float4*>(dx + base + (size_t)c * S) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        return;
+    }
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < (unsigned)S; v += gridDim.x * blockDim.x) {
         const size_t base = n * C * S + v;
         float p[kLossMaxC], g[kLossMaxC];
         load_probs<SOFTMAX>(x, base, S, C, p);
-        const int t = target ? (int)target[i] : -1;
+        const int t = target ? (int)target[n * S + v] : -1;
         float dot = 0.f;
 #pragma unroll
         for (int c = 0; c < kLossMaxC; c++) {
@@ -118,11 +198,12 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
     }
 }
 
-static int loss_grid(size_t total)
+static dim3 loss_grid(int N, size_t S, int waves, int vec)
 {
-    size_t b = (total + 255) / 256;
-    const size_t cap = (size_t)num_sms() * 8;
-    return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+    size_t b = (S / vec + 255) / 256;
+    size_t cap = ((size_t)num_sms() * waves + N - 1) / N;
+    if (cap < 1) cap = 1;
+    return dim3((unsigned)(b > cap ? cap : (b < 1 ? 1 : b)), (unsigned)N);
 }
 
 }  // namespace e3b
@@ -137,13 +218,21 @@ int e3b_dice_fwd(const float* logits, const int64_t* target, const float* target
     if (!logits || (!target && !target_onehot) || !sums || !loss || !coef) return set_error("dice: null pointer");
     if (C < 1 || C > kLossMaxC) return set_error("dice: 1..%d classes supported, got %d", kLossMaxC, C);
     if (N <= 0 || S <= 0) return set_error("dice: empty tensor");
+    if (N > 65535 || S >= ((int64_t)1 << 32)) return set_error("dice: tensor too large for the launch grid");
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 3 * C, st);
     if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
-    const size_t total = (size_t)N * S;
     const long long* t = reinterpret_cast<const long long*>(target);
-    if (apply_softmax) dice_fwd_kernel<true><<<loss_grid(total), 256, 0, st>>>(logits, t, target_onehot, N, C, (size_t)S, sums);
-    else dice_fwd_kernel<false><<<loss_grid(total), 256, 0, st>>>(logits, t, target_onehot, N, C, (size_t)S, sums);
+    // vector path: four voxels per thread (dense targets, S % 4 == 0, <= 4 classes: register budget); two CTAs per SM, so
+    // that only ~300 CTAs add their partial sums to the 3 C fp64 accumulators
+    const bool vec = t != nullptr && S % 4 == 0 && C <= 4 && ((uintptr_t)logits % 16 == 0) && ((uintptr_t)t % 16 == 0);
+    if (vec) {
+        if (apply_softmax) dice_fwd_kernel<true, true><<<loss_grid(N, (size_t)S, 2, 4), 256, 0, st>>>(logits, t, target_onehot, N, C, (size_t)S, sums);
+        else dice_fwd_kernel<false, true><<<loss_grid(N, (size_t)S, 2, 4), 256, 0, st>>>(logits, t, target_onehot, N, C, (size_t)S, sums);
+    } else {
+        if (apply_softmax) dice_fwd_kernel<true, false><<<loss_grid(N, (size_t)S, 4, 1), 256, 0, st>>>(logits, t, target_onehot, N, C, (size_t)S, sums);
+        else dice_fwd_kernel<false, false><<<loss_grid(N, (size_t)S, 4, 1), 256, 0, st>>>(logits, t, target_onehot, N, C, (size_t)S, sums);
+    }
     if (check_launch("dice_fwd")) return 1;
     dice_finalize_kernel<<<1, 32, 0, st>>>(sums, weight, weight_n, C, (double)smooth, (double)eps, loss, coef);
     return check_launch("dice_finalize");
@@ -155,10 +244,17 @@ int e3b_dice_bwd(const float* logits, const int64_t* target, const float* target
     if (!logits || (!target && !target_onehot) || !coef || !gout || !dlogits) return set_error("dice_bwd: null pointer");
     if (C < 1 || C > kLossMaxC) return set_error("dice_bwd: 1..%d classes supported, got %d", kLossMaxC, C);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t total = (size_t)N * S;
+    if (N > 65535 || S >= ((int64_t)1 << 32)) return set_error("dice_bwd: tensor too large for the launch grid");
     const long long* t = reinterpret_cast<const long long*>(target);
-    if (apply_softmax) dice_bwd_kernel<true><<<loss_grid(total), 256, 0, st>>>(logits, t, target_onehot, coef, gout, dlogits, N, C, (size_t)S);
-    else dice_bwd_kernel<false><<<loss_grid(total), 256, 0, st>>>(logits, t, target_onehot, coef, gout, dlogits, N, C, (size_t)S);
+    const bool vec = t != nullptr && S % 4 == 0 && C <= 4 && ((uintptr_t)logits % 16 == 0) && ((uintptr_t)t % 16 == 0) &&
+                     ((uintptr_t)dlogits % 16 == 0);
+    if (vec) {
+        if (apply_softmax) dice_bwd_kernel<true, true><<<loss_grid(N, (size_t)S, 8, 4), 256, 0, st>>>(logits, t, target_onehot, coef, gout, dlogits, N, C, (size_t)S);
+        else dice_bwd_kernel<false, true><<<loss_grid(N, (size_t)S, 8, 4), 256, 0, st>>>(logits, t, target_onehot, coef, gout, dlogits, N, C, (size_t)S);
+    } else {
+        if (apply_softmax) dice_bwd_kernel<true, false><<<loss_grid(N, (size_t)S, 8, 1), 256, 0, st>>>(logits, t, target_onehot, coef, gout, dlogits, N, C, (size_t)S);
+        else dice_bwd_kernel<false, false><<<loss_grid(N, (size_t)S, 8, 1), 256, 0, st>>>(logits, t, target_onehot, coef, gout, dlogits, N, C, (size_t)S);
+    }
     return check_launch("dice_bwd");
 }
 
