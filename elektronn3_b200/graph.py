@@ -10,6 +10,9 @@ of the eager path (tests/test_unet_gpu.py::test_graphed_train_step_matches_eager
     step = GraphedTrainStep(model, criterion, optimizer, inp_shape, target_shape)
     dloss, dout = step(batch['inp'], batch['target'])      # host (pinned) or device tensors
 
+    step.prefetch(next_batch['inp'], next_batch['target']) # optional: H2D of the next batch behind this step's kernels
+    dloss, dout = step()
+
 This is an optional accelerator next to the ``nn.Module`` drop-in: ``Trainer`` keeps working unchanged with
 the plain module (a maintainer would replace the body of ``_train_step`` by the call above).
 """
@@ -35,6 +38,7 @@ class GraphedTrainStep:
             raise RuntimeError('elektronn3_b200: GraphedTrainStep needs the model on a CUDA device')
         self.model, self.criterion, self.optimizer, self.grad_sync = model, criterion, optimizer, grad_sync
         from . import _lib
+        self._copy_stream, self._stage, self._has_staged = None, None, False
         self.inp = torch.zeros(inp_shape, dtype=torch.float32, device=dev)
         self.target = torch.zeros(target_shape, dtype=target_dtype, device=dev)
         # Warm-up on a side stream: lazy initialisation of kernels, allocator and optimizer state happens here, not
@@ -112,11 +116,40 @@ class GraphedTrainStep:
         # weight images keyed on them, so that an eager call of the module (validation) re-packs
         self.model.invalidate_weight_cache()
 
-    def __call__(self, inp, target):
+    def prefetch(self, inp, target):
+        """Start the H2D copy of the NEXT batch (pinned host tensors) on a copy stream, into staging buffers, while the
+        current replay is still running; the next ``step()`` (called without arguments) consumes it with a device-side
+        copy.  This is what a ``DataLoader(pin_memory=True)`` + ``.to(device, non_blocking=True)`` pipeline cannot do
+        on a single stream (training/trainer.py:515-517): the copy hides behind the previous step's kernels."""
+        dev = self.inp.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = (torch.empty_like(self.inp), torch.empty_like(self.target))
+            self._staged, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(dev))
+        self._copy_stream.wait_event(self._consumed)          # the staging buffers are free again
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[0].copy_(inp, non_blocking=True)
+            self._stage[1].copy_(target, non_blocking=True)
+            self._staged.record(self._copy_stream)
+        self._has_staged = True
+
+    def __call__(self, inp=None, target=None):
         """copy the batch into the graph's static buffers (H2D when they are host tensors), replay.
+        Without arguments: take the batch staged by ``prefetch``.
         Returns (dloss, dout): static device tensors, overwritten by the next call."""
-        self.inp.copy_(inp, non_blocking=True)
-        self.target.copy_(target, non_blocking=True)
+        if inp is None:
+            if not self._has_staged:
+                raise RuntimeError('GraphedTrainStep(): no batch given and none staged by prefetch()')
+            cur = torch.cuda.current_stream(self.inp.device)
+            cur.wait_event(self._staged)
+            self.inp.copy_(self._stage[0], non_blocking=True)
+            self.target.copy_(self._stage[1], non_blocking=True)
+            self._consumed.record(cur)
+            self._has_staged = False
+        else:
+            self.inp.copy_(inp, non_blocking=True)
+            self.target.copy_(target, non_blocking=True)
         self.graph.replay()
         self._invalidate()
         return self.dloss, self.dout
