@@ -39,6 +39,8 @@ FWD_BWD_GFLOP = 1175.75          # algorithmic, SURVEY.md 8(d) / BASELINE.md 2.3
 # dominant kernel for the roofline: the conv of up_convs.1.conv1 (virtual concat 32+32 -> 32 at 4 x 64^3)
 DOM = dict(N=4, C0=32, C1=32, Co=32, S=64)
 DOM_GFLOP = 2 * 4 * 64 ** 3 * 32 * (64 * 27) / 1e9     # 115.96
+# torch's fused multi-tensor SGD (one kernel for all parameters) in BOTH GPU arms; E3B_BENCH_FUSED_OPT=0: the foreach default
+FUSED_OPT = os.environ.get('E3B_BENCH_FUSED_OPT', '1') != '0'
 DOM_TRAFFIC = 507.0e6            # dram__bytes_read + write of that launch: ncu --set full, profiles/r02_ncu_zs_concat.csv (cold L2; 268 MB algorithmic)
 
 PRED_MODEL_KW = dict(n_blocks=4, start_filts=32)
@@ -269,7 +271,7 @@ def main():
 
     torch.manual_seed(1234 + rank)
     model = e3.UNet(**MODEL_KW).to(dev).train()
-    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, fused=FUSED_OPT)
     voxels = BATCH[0] * BATCH[2] * BATCH[3] * BATCH[4]
     # N = 1: the whole step is replayed as one CUDA graph (elektronn3_b200/graph.py).  N > 1: the graph ends after
     # backward; the data-parallel gradient average (one flat NCCL all-reduce: what DDP's buckets compute) and the
@@ -453,7 +455,7 @@ def ref_gpu_train(torch, dev, timed):
     torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = True, True
     try:
         m = e3.UNet(**MODEL_KW).to(dev).train()          # parameter container; the forward below is plain torch / cuDNN
-        opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9)
+        opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, fused=FUSED_OPT)
         x = torch.randn(BATCH, device=dev)
         t = torch.randint(0, 2, (BATCH[0],) + BATCH[2:], device=dev)
         xh, th = torch.randn(BATCH).pin_memory(), torch.randint(0, 2, (BATCH[0],) + BATCH[2:]).pin_memory()
