@@ -345,8 +345,11 @@ def main():
                 loss = gstep()[0]
                 if i + 1 < k:
                     gstep.prefetch(x_host, t_host)
+                if world > 1:                  # the graph ends after backward: gradient average + optimizer step, eagerly
+                    grad_sync()
+                    opt.step()
                 float(loss)
-        if gstep is not None and world == 1:
+        if gstep is not None:
             e2e_pipelined(3)
             ms_e2e = timed(lambda: e2e_pipelined(args.steps), 1)
             e2e_mode = 'H2D of batch i+1 on a copy stream behind the kernels of step i (GraphedTrainStep.prefetch)'
