@@ -846,10 +846,27 @@ E3B_DEVINL float4 lds128(uint32_t saddr)
     return v;
 }
 
+// Kernel variants: what is present is a compile-time fact wherever the common layer types allow it (no dead code, no
+// registers for absent inputs); variant 4 decides everything at run time.
+//   0: g0                         (conv -> norm -> relu inside a block)
+//   1: g0 + un-cropped g1         (last conv of an encoder block at the bottom level / SAME skip + direct gradient)
+//   2: g0, space-to-depth output  (norm0 of an UpConv: dy feeds the transposed conv's GEMMs)
+//   3: un-cropped g1 + pooled gp  (last conv of an encoder block: skip gradient + un-pooling)
+//   4: anything else (cropped skip gradient of VALID nets, ...)
+template <int VAR>
+struct FusedVar {
+    static constexpr bool coords = VAR >= 2;       // voxel coordinates are needed at all
+    E3B_DEVINL static bool g0(const NormBwdDev& p) { return VAR == 4 ? p.g0 != nullptr : VAR != 3; }
+    E3B_DEVINL static bool g1_bulk(const FusedDev& f) { return VAR == 4 ? f.g1_bulk != 0 : (VAR == 1 || VAR == 3); }
+    E3B_DEVINL static bool g1_crop(const NormBwdDev& p, const FusedDev& f) { return VAR == 4 && p.g1 != nullptr && !f.g1_bulk; }
+    E3B_DEVINL static bool gp(const NormBwdDev& p) { return VAR == 4 ? p.gp != nullptr : VAR == 3; }
+    E3B_DEVINL static bool s2d(const NormBwdDev& p) { return VAR == 4 ? p.s2d != 0 : VAR == 2; }
+};
+
 // y and the staged gradients (g0 [+ g1]) of this thread's voxel quads of one item: all loads are issued before the first use
 static constexpr int kQuadBatch = 2;                          // quads whose loads are in flight together (register budget: 96)
 
-template <bool GENERAL, bool G1, bool FULL>
+template <int VAR, bool FULL>
 E3B_DEVINL void fused_load_item(const NormBwdDev& p, const FusedDev& f, uint32_t sbase, uint32_t off_g0, uint32_t off_g1, int t128,
                                 int nv, int k0, float4* Y, float4* G)
 {
@@ -860,9 +877,9 @@ E3B_DEVINL void fused_load_item(const NormBwdDev& p, const FusedDev& f, uint32_t
         Y[kk] = zero; G[kk] = zero;
         if (!FULL && k * 128 + t128 >= nv) continue;
         Y[kk] = lds128(sbase + k * 2048);
-        if (!GENERAL || p.g0) G[kk] = lds128(sbase + off_g0 + k * 2048);
+        if (FusedVar<VAR>::g0(p)) G[kk] = lds128(sbase + off_g0 + k * 2048);
     }
-    if (GENERAL ? f.g1_bulk != 0 : G1) {
+    if (FusedVar<VAR>::g1_bulk(f)) {
 #pragma unroll
         for (int kk = 0; kk < kQuadBatch; kk++) {
             const int k = k0 + kk;
@@ -873,14 +890,15 @@ E3B_DEVINL void fused_load_item(const NormBwdDev& p, const FusedDev& f, uint32_t
     }
 }
 
-// GENERAL variant: voxel coordinates, and the gradients that are gathered from global memory (cropped skip gradient,
-// un-pooling of the pooled gradient; L1 / L2 hits: 8 fine voxels share one coarse voxel)
+// voxel coordinates, and the gradients that are gathered from global memory (cropped skip gradient, un-pooling of the
+// pooled gradient; L1 / L2 hits: 8 fine voxels share one coarse voxel)
+template <int VAR>
 E3B_DEVINL void fused_gather(const NormBwdDev& p, const FusedDev& f, int n, int cq, int v, float4& g, int& z, int& yy, int& x)
 {
     z = f.dHW.div(v);
     const int r = v - z * (p.H * p.W);
     yy = f.dW.div(r); x = r - yy * p.W;
-    if (p.g1 && !f.g1_bulk) {
+    if (FusedVar<VAR>::g1_crop(p, f)) {
         // backward of autocrop's slice of the skip tensor: zero outside the cropped box
         const int zc = z - p.g1_od, yc = yy - p.g1_oh, xc = x - p.g1_ow;
         if (zc >= 0 && zc < p.g1_D && yc >= 0 && yc < p.g1_H && xc >= 0 && xc < p.g1_W) {
@@ -888,7 +906,7 @@ E3B_DEVINL void fused_gather(const NormBwdDev& p, const FusedDev& f, int n, int 
             g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
         }
     }
-    if (p.gp) {
+    if (FusedVar<VAR>::gp(p)) {
         const int zw = f.dwd.div(z), yw = f.dwh.div(yy), xw = f.dww.div(x);
         const unsigned char slot = (unsigned char)(((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww));
         const size_t ow = ((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw;
@@ -914,10 +932,8 @@ E3B_DEVINL void fused_mask_xhat(const QuadConsts& c, const float4& yv, float4& g
 }
 
 // phase A over one staged item (this thread: channel quad `cq`, voxels t128 + 128 k).
-// GENERAL = false ("lean"): g0 is present, no pooled gradient, no cropped skip gradient, no space-to-depth output; G1: a
-// second, un-cropped gradient is staged next to g0.  GENERAL = true decides all of that at run time.
 // FULL = all 512 voxels present: no bounds checks.
-template <bool GENERAL, bool G1, bool FULL>
+template <int VAR, bool FULL>
 E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32_t sbase, uint32_t off_g0, uint32_t off_g1,
                                   const QuadConsts& c, int t128, int n, int cq, int v0, int nv, float* s1, float* s2, float* md,
                                   float* mx)
@@ -925,13 +941,13 @@ E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32
 #pragma unroll
     for (int k0 = 0; k0 < kQuadsPerThread; k0 += kQuadBatch) {
     float4 Y[kQuadBatch], G[kQuadBatch];
-    fused_load_item<GENERAL, G1, FULL>(p, f, sbase, off_g0, off_g1, t128, nv, k0, Y, G);
+    fused_load_item<VAR, FULL>(p, f, sbase, off_g0, off_g1, t128, nv, k0, Y, G);
 #pragma unroll
     for (int kk = 0; kk < kQuadBatch; kk++) {
         const int vl = (k0 + kk) * 128 + t128;
         if (!FULL && vl >= nv) continue;
         float4 dr = G[kk], xh;
-        if (GENERAL) { int z, yy, x; fused_gather(p, f, n, cq, v0 + vl, dr, z, yy, x); }
+        if (FusedVar<VAR>::coords) { int z, yy, x; fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x); }
         fused_mask_xhat(c, Y[kk], dr, xh);
         s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
         s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]); s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
@@ -944,7 +960,7 @@ E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32
 // phase C over one staged item: dy = 2^k * rstd * (gamma * dr - m1 - xhat * m2); this thread writes the 8-byte half `hsel`
 // of its voxels' 16-byte units (the other half comes from the other warp group; L2 merges the sectors).
 // (fp16 has TF32's 10 mantissa bits: the fp16 rounding of the store is the operand rounding.)
-template <bool GENERAL, bool G1, bool FULL>
+template <int VAR, bool FULL>
 E3B_DEVINL void fused_item_apply(const NormBwdDev& p, const FusedDev& f, uint32_t sbase, uint32_t off_g0, uint32_t off_g1,
                                  const QuadConsts& c, const float4& ga, const float4& m1, const float4& m2, const float4& rk, int hsel,
                                  int t128, int n, int cqp, int Cqp, int total, int v0, int nv, uint2* dy)
@@ -955,19 +971,19 @@ E3B_DEVINL void fused_item_apply(const NormBwdDev& p, const FusedDev& f, uint32_
 #pragma unroll
     for (int k0 = 0; k0 < kQuadsPerThread; k0 += kQuadBatch) {
     float4 Y[kQuadBatch], G[kQuadBatch];
-    fused_load_item<GENERAL, G1, FULL>(p, f, sbase, off_g0, off_g1, t128, nv, k0, Y, G);
+    fused_load_item<VAR, FULL>(p, f, sbase, off_g0, off_g1, t128, nv, k0, Y, G);
 #pragma unroll
     for (int kk = 0; kk < kQuadBatch; kk++) {
         const int vl = (k0 + kk) * 128 + t128;
         if (!FULL && vl >= nv) continue;
         float4 dr = G[kk], xh;
         int z = 0, yy = 0, x = 0;
-        if (GENERAL) fused_gather(p, f, n, cq, v0 + vl, dr, z, yy, x);
+        if (FusedVar<VAR>::coords) fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x);
         fused_mask_xhat(c, Y[kk], dr, xh);
         // rstd * 2^k is folded into rk: o = rk * (ga * dr - m1 - xh * m2)
         const uint2 o = pack_half4(rk.x * fmaf(-xh.x, m2.x, fmaf(ga.x, dr.x, -m1.x)), rk.y * fmaf(-xh.y, m2.y, fmaf(ga.y, dr.y, -m1.y)),
                                    rk.z * fmaf(-xh.z, m2.z, fmaf(ga.z, dr.z, -m1.z)), rk.w * fmaf(-xh.w, m2.w, fmaf(ga.w, dr.w, -m1.w)));
-        if (!GENERAL || !p.s2d) {
+        if (!FusedVar<VAR>::s2d(p)) {
             dyp[(k0 + kk) * 256] = o;
         } else {
             // space-to-depth: channel = slot * Cp + c on the coarse grid
@@ -983,7 +999,7 @@ E3B_DEVINL void fused_item_apply(const NormBwdDev& p, const FusedDev& f, uint32_
 static constexpr int kFusedThreads = 288;            // 8 consumer warps + 1 producer warp (one lane issues the bulk copies)
 static constexpr int kFusedBar = 1;                  // named barrier of the 256 consumer threads
 
-template <bool GENERAL, bool G1>
+template <int VAR>
 __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const NormBwdDev p, const FusedDev f)
 {
     extern __shared__ __align__(128) unsigned char ring[];
@@ -998,7 +1014,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
     const int Cqp = p.Cq >> 1;                       // pairs of channel quads (Cq is even: channels are padded to 8)
     const int nset = f.nset, nrounds = p.N / nset;       // samples per round (a divisor of N); batch statistics: one round
     const int Cp = f.Cp, S = f.stages;
-    const bool has_g0 = !GENERAL || p.g0 != nullptr, g1_bulk = GENERAL ? f.g1_bulk != 0 : G1;
+    const bool has_g0 = FusedVar<VAR>::g0(p), g1_bulk = FusedVar<VAR>::g1_bulk(f);
     const int nb = 1 + (has_g0 ? 1 : 0) + (g1_bulk ? 1 : 0);
     const uint32_t stage_bytes = nb * kItemTensorBytes;
     const uint32_t off_g0 = kItemTensorBytes, off_g1 = (has_g0 ? 2 : 1) * kItemTensorBytes;
@@ -1154,8 +1170,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                 if (prof_on) wait_a += globaltimer_ns() - tw;
                 parity ^= 1u << s;
                 const uint32_t sbase = ring_thread + (uint32_t)s * stage_bytes;
-                if (nv == kItemVox) fused_item_reduce<GENERAL, G1, true>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx);
-                else fused_item_reduce<GENERAL, G1, false>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx);
+                if (nv == kItemVox) fused_item_reduce<VAR, true>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx);
+                else fused_item_reduce<VAR, false>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx);
                 if (j + S < cnt) {                    // this warp is done with stage s: the producer may refill it
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
@@ -1275,7 +1291,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
             // a later round is larger than the scale chosen so far allows: bring the samples already written down to the
             // new scale (a power of two: exact).  Rare -- the samples of one batch have similar gradient magnitudes.
             const float factor = want / dscale;
-            const size_t units = (size_t)n0 * p.Ch * ((GENERAL && p.s2d) ? (size_t)p.Dw * p.Hw * p.Ww : (size_t)total);      // 16-byte units
+            const size_t units = (size_t)n0 * p.Ch * (FusedVar<VAR>::s2d(p) ? (size_t)p.Dw * p.Hw * p.Ww : (size_t)total);      // 16-byte units
             uint4* q = reinterpret_cast<uint4*>(p.dy);
             const __half2 f2 = __float2half2_rn(factor);
             for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < units; i += (size_t)gridDim.x * 256) {
@@ -1327,8 +1343,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                     parity ^= 1u << s;
                 }
                 const uint32_t sbase = ring_thread + (uint32_t)s * stage_bytes;
-                if (nv == kItemVox) fused_item_apply<GENERAL, G1, true>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy);
-                else fused_item_apply<GENERAL, G1, false>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy);
+                if (nv == kItemVox) fused_item_apply<VAR, true>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy);
+                else fused_item_apply<VAR, false>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy);
                 if (j - S >= 0 || round + 1 < nrounds) {                      // the producer refills this stage
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
@@ -1901,24 +1917,29 @@ int e3b_norm_bwd_fused(const e3b_norm_bwd_args* a, void* stream)
     f.dwd = make_fastdiv(p.wd); f.dwh = make_fastdiv(p.wh); f.dww = make_fastdiv(p.ww);
     // persistent grid of co-resident CTAs (the kernel contains grid barriers): a cooperative launch, which the driver
     // only starts when every CTA fits at once -- also next to kernels of other streams
-    const bool general = p.gp != nullptr || p.g1_crop != 0 || p.s2d != 0 || p.g0 == nullptr;
     f.g1_bulk = (p.g1 != nullptr && !p.g1_crop) ? 1 : 0;
+    int var = 4;
+    if (p.g0 && !p.gp && !p.g1_crop && !p.s2d) var = f.g1_bulk ? 1 : 0;
+    else if (p.g0 && !p.g1 && !p.gp && p.s2d) var = 2;
+    else if (!p.g0 && f.g1_bulk && p.gp && !p.s2d) var = 3;
     const int nb = 1 + (p.g0 != nullptr) + f.g1_bulk;
     const int kRingBytes = 96 * 1024;               // two CTAs per SM
     f.stages = kRingBytes / (nb * kItemTensorBytes);
     if (f.stages > kFusedMaxStages) f.stages = kFusedMaxStages;
     const size_t smem = (size_t)f.stages * nb * kItemTensorBytes;
-    void (*kern)(const NormBwdDev, const FusedDev) = general ? norm_bwd_fused_kernel<true, false>
-                                                     : (f.g1_bulk ? norm_bwd_fused_kernel<false, true> : norm_bwd_fused_kernel<false, false>);
-    static int per_sm[kMaxDevices][2][4] = {};
+    typedef void (*FusedKernel)(const NormBwdDev, const FusedDev);
+    static const FusedKernel kernels[5] = {norm_bwd_fused_kernel<0>, norm_bwd_fused_kernel<1>, norm_bwd_fused_kernel<2>,
+                                           norm_bwd_fused_kernel<3>, norm_bwd_fused_kernel<4>};
+    const FusedKernel kern = kernels[var];
+    static int per_sm[kMaxDevices][5][4] = {};
     const int dev = current_device();
-    if (!per_sm[dev][general][nb]) {
+    if (!per_sm[dev][var][nb]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes) != cudaSuccess)
             return set_error("norm_bwd_fused: cannot reserve %d bytes of shared memory", kRingBytes);
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kFusedThreads, smem) != cudaSuccess || n < 1)
             return set_error("norm_bwd_fused: occupancy query failed");
-        per_sm[dev][general][nb] = n > 2 ? 2 : n;
+        per_sm[dev][var][nb] = n > 2 ? 2 : n;
     }
     // samples per round: as many as keep the round's working set (sources + dy) inside L2, a divisor of N
     f.nset = a->N;
@@ -1934,7 +1955,7 @@ int e3b_norm_bwd_fused(const e3b_norm_bwd_args* a, void* stream)
     }
     const long long items = (long long)f.nset * (p.Cq / 2) * (((long long)p.D * p.H * p.W + kItemVox - 1) / kItemVox);
     if (items >= (1ll << 31)) return set_error("norm_bwd_fused: tensor too large");
-    long long grid = (long long)num_sms() * per_sm[dev][general][nb];
+    long long grid = (long long)num_sms() * per_sm[dev][var][nb];
     if (grid > items) grid = items;
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg = {};
