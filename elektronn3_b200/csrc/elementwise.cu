@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ uint64_t full[kFusedMaxStages], empty[kFusedMaxStages];
     __shared__ float4 ctab[kCtabSlots][5];           // per (sample, 4-channel quad): -mean * rstd, rstd, scale, shift, gamma
-    __shared__ float2 gm[kFusedMaxCp];               // (m1, m2) per (sample of the round, group) -- batch statistics: per channel
+    __shared__ float2 gm[kFusedMaxCp];               // (m1, m2) per (sample, group) -- batch statistics: per channel
     __shared__ float red[8][16];
     __shared__ float bound_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1076,6 +1076,9 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
     // ctab rows: (n - ctab_n0) * Cq + cq; all samples at once when they fit (the launch wrapper guarantees nset * Cq fits).
     const int cs = f.per_sample ? 1 : 0;
     const bool all_rounds = cs * p.N * p.Cq <= kCtabSlots;
+    // group means: indexed by the absolute sample when all samples fit (CTA 0 re-uses them for the parameter gradients
+    // after the last round), else by the sample's position inside the round
+    const bool gm_keep = f.mode != 1 || p.N * f.G <= kFusedMaxCp;
     auto fill_ctab = [&](int first, int count) {
         for (int t = threadIdx.x; t < count * p.Cq; t += 256) {
             const int j = t / p.Cq, cq = t - j * p.Cq;
@@ -1226,7 +1229,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                         v1 += __shfl_xor_sync(0xffffffffu, v1, o);
                         v2 += __shfl_xor_sync(0xffffffffu, v2, o);
                     }
-                    if (valid && (c & (cg - 1)) == 0) gm[j * f.G + c / cg] = make_float2((float)(v1 * f.inv_count), (float)(v2 * f.inv_count));
+                    if (valid && (c & (cg - 1)) == 0) gm[(gm_keep ? n : j) * f.G + c / cg] = make_float2((float)(v1 * f.inv_count), (float)(v2 * f.inv_count));
                 }
             } else {
                 const int ngrp = f.mode == 1 ? f.G : (f.mode == 2 ? p.C : 0);
@@ -1252,7 +1255,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                         }
                         m1 *= ga; m2 *= ga;
                     }
-                    gm[t] = make_float2((float)(m1 * f.inv_count), (float)(m2 * f.inv_count));
+                    gm[(f.mode == 1 && gm_keep ? n0 * ngrp : 0) + t] = make_float2((float)(m1 * f.inv_count), (float)(m2 * f.inv_count));
                 }
             }
             named_bar_sync(kFusedBar, 256);
@@ -1266,7 +1269,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                 const float ga_abs = f.mode != 0 ? fabsf(reinterpret_cast<const float*>(&row[4])[c & 3]) : 1.f;
                 const float rs_c = reinterpret_cast<const float*>(&row[1])[c & 3];
                 float2 m = make_float2(0.f, 0.f);
-                if (f.mode == 1) m = gm[j * f.G + c / (p.C / f.G)];
+                if (f.mode == 1) m = gm[(gm_keep ? n : j) * f.G + c / (p.C / f.G)];
                 else if (f.mode == 2) m = gm[c];
                 float b = 0.f;
                 for (int q = 0; q < (cs ? 1 : p.N); q++) {
@@ -1325,7 +1328,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                         for (int k = 0; k < 4; k++) {
                             const int ch = min(4 * cq + k, p.C - 1);
                             float2 m = make_float2(0.f, 0.f);
-                            if (f.mode == 1) m = gm[(n - n0) * f.G + ch / (p.C / f.G)];
+                            if (f.mode == 1) m = gm[(gm_keep ? n : n - n0) * f.G + ch / (p.C / f.G)];
                             else if (f.mode == 2) m = gm[ch];
                             mm[k][0] = 4 * cq + k < p.C ? m.x : 0.f; mm[k][1] = 4 * cq + k < p.C ? m.y : 0.f;
                         }
@@ -1366,20 +1369,19 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
     for (int c = threadIdx.x; c < p.C; c += 256) {
         const double ga = (p.gamma && f.mode != 0) ? (double)p.gamma[c] : 1.0;
         double dg = 0.0, db = 0.0, dbi = 0.0;
-        double m1b = 0.0, m2b = 0.0;                  // batch statistics: one pair of means per channel
-        if (f.mode == 2) {
-            for (int q = 0; q < p.N; q++) { m1b += __ldcg(p.sums + ((size_t)q * Cp + c) * 2); m2b += __ldcg(p.sums + ((size_t)q * Cp + c) * 2 + 1); }
-            m1b *= ga * f.inv_count; m2b *= ga * f.inv_count;
-        }
+        const int cg = f.mode == 1 ? p.C / f.G : 1;
+#pragma unroll 4
         for (int n = 0; n < p.N; n++) {
             const size_t i = (size_t)n * Cp + c;
             const double S1 = __ldcg(p.sums + i * 2), S2 = __ldcg(p.sums + i * 2 + 1);
             dg += S2; db += S1;
             if (f.dbias) {
-                double m1 = m1b, m2 = m2b;
-                if (f.mode == 1) {
-                    const int cg = p.C / f.G, c_first = (c / cg) * cg;
-                    m1 = 0.0; m2 = 0.0;
+                double m1 = 0.0, m2 = 0.0;
+                if (f.mode == 2) { m1 = (double)gm[c].x; m2 = (double)gm[c].y; }         // (single round: still in place)
+                else if (f.mode == 1 && gm_keep) { const float2 m = gm[n * f.G + c / cg]; m1 = (double)m.x; m2 = (double)m.y; }
+                else if (f.mode == 1) {
+                    // more (sample, group) pairs than the table holds: recompute from the sums
+                    const int c_first = (c / cg) * cg;
                     for (int q = 0; q < cg; q++) {
                         const double gq = p.gamma ? (double)p.gamma[c_first + q] : 1.0;
                         m1 += gq * __ldcg(p.sums + ((size_t)n * Cp + c_first + q) * 2);

@@ -176,8 +176,7 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
                 }
             }
         }
-        return;
-    }
+    } else {
     for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < (unsigned)S; v += gridDim.x * blockDim.x) {
         const size_t base = n * C * S + v;
         float p[kLossMaxC], g[kLossMaxC];
@@ -195,6 +194,7 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
 #pragma unroll
         for (int c = 0; c < kLossMaxC; c++)
             if (c < C) dx[base + (size_t)c * S] = SOFTMAX ? p[c] * (g[c] - dot) : g[c];
+    }
     }
 }
 
