@@ -223,43 +223,55 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// deterministic split-K reduction + scatter into the torch parameter layout.  A block of 8 warps owns 32 consecutive
-// elements: warp w adds the partials s = w, w + 8, ... (coalesced 128-byte rows), the eight sums meet in shared
+// deterministic split-K reduction + scatter into the torch parameter layout.  A block of 8 warps owns 128 consecutive
+// elements: warp w adds the partials s = w, w + 8, ... (coalesced 512-byte rows of float4), the eight sums meet in shared
 // memory and are added in warp order.  (One thread per element walking all S <= 148 partials was latency bound:
-// 25 us for the 16 MB of partials of a 32 -> 32 layer.)
+// 25 us for the 16 MB of partials of a 32 -> 32 layer; 128-byte rows: 11.7 us.)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int S, int ntaps,
                                                             int ktot, int npad_total, int CB, int mchunks0, int C0, int C1, int Co,
                                                             int layout, int up_taps, int up_co, int up_copad,
                                                             const float* __restrict__ dy_unscale)
 {
-    __shared__ float red[8][32];
-    const size_t total = (size_t)ntaps * ktot * npad_total;
+    // a block owns 128 consecutive elements (4 per lane: 512-byte rows); npad_total % 4 == 0, so a lane's four elements
+    // share (tap, input channel) and differ in the output column only
+    __shared__ float4 red[8][32];
+    const unsigned total = (unsigned)ntaps * ktot * npad_total;           // < 2^31 (checked by the launch wrapper)
     const float unscale = dy_unscale ? __ldg(dy_unscale) : 1.f;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (size_t i0 = (size_t)blockIdx.x * 32; i0 < total; i0 += (size_t)gridDim.x * 32) {
-        const size_t i = i0 + lane;
-        bool valid = i < total;
-        int nn = 0, ci = 0, tap = 0;
-        if (valid) {
-            nn = (int)(i % npad_total);
-            const int kk = (int)((i / npad_total) % ktot);
-            tap = (int)(i / ((size_t)npad_total * ktot));
-            if (kk < mchunks0 * CB) { valid = kk < C0; ci = kk; }
-            else { const int k1 = kk - mchunks0 * CB; valid = k1 < C1; ci = C0 + k1; }
-            if (layout == 0) valid = valid && nn < Co;
-            else valid = valid && (nn / up_copad < up_taps) && (nn % up_copad < up_co);
+    for (unsigned i0 = blockIdx.x * 128u; i0 < total; i0 += gridDim.x * 128u) {
+        const unsigned i = i0 + lane * 4u;
+        const bool inside = i < total;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (inside) {
+            const float4* q = reinterpret_cast<const float4*>(part + i);
+            const size_t step = (size_t)total / 4;                       // float4 units between consecutive partials
+#pragma unroll 4
+            for (int sp = w; sp < S; sp += 8) {
+                const float4 v = __ldcs(q + (size_t)sp * step);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
         }
-        float s = 0.f;
-        if (valid) for (int sp = w; sp < S; sp += 8) s += part[(size_t)sp * total + i];
         red[w][lane] = s;
         __syncthreads();
-        if (w == 0 && valid) {
-            float t = red[0][lane];
+        if (w == 0 && inside) {
+            float4 t = red[0][lane];
 #pragma unroll
-            for (int j = 1; j < 8; j++) t += red[j][lane];
-            t *= unscale;
-            if (layout == 0) dw[((size_t)nn * (C0 + C1) + ci) * ntaps + tap] = t;
-            else dw[((size_t)ci * up_co + nn % up_copad) * up_taps + nn / up_copad] = t;
+            for (int j = 1; j < 8; j++) { const float4 r = red[j][lane]; t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+            const unsigned row = i / (unsigned)npad_total;
+            const int nn0 = (int)(i - row * (unsigned)npad_total);
+            const int tap = (int)(row / (unsigned)ktot), kk = (int)(row - (unsigned)tap * ktot);
+            bool valid;
+            int ci;
+            if (kk < mchunks0 * CB) { valid = kk < C0; ci = kk; }
+            else { const int k1 = kk - mchunks0 * CB; valid = k1 < C1; ci = C0 + k1; }
+            const float tv[4] = {t.x * unscale, t.y * unscale, t.z * unscale, t.w * unscale};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int nn = nn0 + e;
+                if (!valid) continue;
+                if (layout == 0) { if (nn < Co) dw[((size_t)nn * (C0 + C1) + ci) * ntaps + tap] = tv[e]; }
+                else if (nn / up_copad < up_taps && nn % up_copad < up_co) dw[((size_t)ci * up_co + nn % up_copad) * up_taps + nn / up_copad] = tv[e];
+            }
         }
         __syncthreads();
     }
@@ -428,8 +440,8 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     const int ntaps = a->kd * a->kh * a->kw;
     const size_t total = (size_t)ntaps * p.ktot * p.npad_total;
     // source 1's channels start at the next CB boundary after source 0's in the partial row space
-    if (p.S >= 64) {
-        int blocks = (int)((total + 31) / 32); if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    if (p.S >= 16 && total < ((size_t)1 << 31) && p.npad_total % 4 == 0) {
+        int blocks = (int)((total + 127) / 128); if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
         wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.part, a->dw, p.S, ntaps, p.ktot, p.npad_total, p.CB, p.mchunks0,
                                                         a->C0, a->src1 ? a->C1 : 0, a->Co, a->layout, a->up_taps, a->up_co,
                                                         cpad8(a->up_co), a->dy_unscale);
