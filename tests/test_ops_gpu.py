@@ -484,6 +484,49 @@ def test_norm_act_pool_forward_backward(eng, monkeypatch, mode, G, C, sp, pool, 
     assert (dbias.double() - ref_dbias).abs().max().item() / scale < 1e-4
 
 
+@pytest.mark.parametrize('pool,direct', [(None, True), ((2, 2, 2), True), ((2, 2, 2), False)])
+def test_norm_backward_direct_plus_skip_gradient(eng, pool, direct):
+    """two un-cropped gradients on the same activation (g0 + g1: the fused kernel's variant 1; with a pooled gradient on
+    top: the run-time variant; skip + pooled gradient without a direct one: variant 3, the encoder's last conv)"""
+    N, C, G, sp = 2, 16, 4, (4, 6, 8)
+    rs = np.random.RandomState(77)
+    y = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
+    gamma = torch.from_numpy((1 + 0.2 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    beta = torch.from_numpy((0.1 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    yd = y.double().requires_grad_(True)
+    a_ref = F.relu(F.group_norm(yd, G, gamma.double(), beta.double(), 1e-5))
+    g0 = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
+    g1 = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
+    if not direct:
+        g0.zero_()
+    loss = (a_ref * (g0 + g1).double()).sum()
+    yq = qp32(eng, y)
+    S = sp[0] * sp[1] * sp[2]
+    stats = torch.stack((y.double().sum(dim=(2, 3, 4)), (y.double() ** 2).sum(dim=(2, 3, 4))), dim=-1).contiguous()
+    nstate = eng.norm_finalize(stats, 1, G, N, C, S, gamma, beta, 1e-5, None, None, 0.1, y.device)
+    a, pooled = eng.norm_act(yq, nstate.scale, nstate.shift, pool=pool, save=True)
+    gpq = None
+    if pool is not None:
+        # un-pool along the arg-max of the activations the kernels stored (rounded to 10 mantissa bits: a near-tie of the
+        # fp64 reference may resolve differently, which is not what this test is about)
+        a_k = from_qh_ref(a, C).double()
+        p_k, idx = F.max_pool3d(a_k, pool, pool, ceil_mode=True, return_indices=True)
+        gp = torch.from_numpy(rs.standard_normal(tuple(p_k.shape)).astype(np.float32)).cuda()
+        loss = loss + (a_ref * F.max_unpool3d(gp.double(), idx, pool, pool, output_size=sp)).sum()
+        gpq = qp32(eng, gp)
+    loss.backward()
+
+    class Spec:
+        pass
+    u = eng.Unit()
+    u.spec = Spec()
+    u.spec.norm = torch.nn.GroupNorm(G, C)
+    u.spec.norm.weight = torch.nn.Parameter(gamma)
+    u.a, u.y, u.pool, u.mode, u.G, u.nstate, u.stats, u.pooled = a, yq, pool, 1, G, nstate, stats, pooled
+    dy, dgamma, dbeta, dbias = eng._norm_bwd(u, C, qp32(eng, g0) if direct else None, g1=qp32(eng, g1), gp=gpq)
+    assert_close(from_qh_ref(dy, C), yd.grad, 1e-3, 'dy')
+
+
 @pytest.mark.parametrize('fine', [(5, 7, 8), (4, 6, 8)])
 def test_norm_backward_space_to_depth(eng, fine):
     """norm0/act0 backward of UpConv written tap-major for the transposed conv's dgrad GEMM; (5, 7, 8): cropped fine
