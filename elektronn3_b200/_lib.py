@@ -74,6 +74,7 @@ class NormBwdArgs(ctypes.Structure):
         ('relu', c_i32),
         ('g1_crop', c_i32),
         ('g1_od', c_i32), ('g1_oh', c_i32), ('g1_ow', c_i32), ('g1_D', c_i32), ('g1_H', c_i32), ('g1_W', c_i32),
+        ('act_slope', c_float),
     ]
 
 
@@ -126,11 +127,14 @@ SIGNATURES = {
     'e3b_wgrad': (c_int, [ctypes.POINTER(WgradArgs), c_void_p]),
     'e3b_norm_finalize': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_i64, c_void_p, c_void_p, c_float,
                                   c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    'e3b_norm_act': (c_int, [c_void_p] * 6 + [c_int] * 10 + [c_void_p]),
+    'e3b_norm_act': (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_float, c_int, c_void_p]),
     'e3b_norm_bwd_fused': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_reduce': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_finalize': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_apply': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
+    'e3b_add_qh': (c_int, [c_void_p] * 3 + [c_int] * 11 + [c_void_p]),
+    'e3b_upsample_qh': (c_int, [c_void_p] * 2 + [c_int] * 18 + [c_void_p]),
+    'e3b_upsample_bwd_qp': (c_int, [c_void_p] * 2 + [c_int] * 18 + [c_void_p]),
     'e3b_head': (c_int, [ctypes.POINTER(HeadArgs), c_void_p]),
     'e3b_prob_argmax': (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_float, c_void_p]),
     'e3b_head_bwd': (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),

@@ -240,17 +240,40 @@ struct NormActDev {
     uint2* a; uint2* pooled;     // QH outputs
     uchar4* pool_idx;
     int C, N, Cq, Ch, D, H, W, pkd, pkh, pkw, relu;
+    float slope;                 // activation code / negative slope, see act_fwd
     int Dp, Hp, Wp;
 };
 
-E3B_DEVINL float4 norm_relu_round(const float4& yv, const float4& sc, const float4& sh, bool affine, int relu)
+// Activation codes (e3b_norm_act `relu`, e3b_norm_bwd_args.relu): 0 identity ('lin'), 1 the leaky-ReLU family with the
+// negative slope `act_slope` (0 = ReLU, 0.1 = 'leaky', RReLU's eval slope ...), 2 SiLU  (get_activation, unet.py:183-199).
+E3B_DEVINL float act_fwd(float z, int act, float slope)
+{
+    if (act == 1) return slope == 0.f ? fmaxf(z, 0.f) : (z > 0.f ? z : z * slope);
+    if (act == 2) return z / (1.f + __expf(-z));
+    return z;
+}
+// upstream gradient g times the activation's derivative at the pre-activation z
+E3B_DEVINL float act_bwd(float z, float g, int act, float slope)
+{
+    if (act == 1) return z > 0.f ? g : (slope == 0.f ? 0.f : g * slope);
+    if (act == 2) { const float s = 1.f / (1.f + __expf(-z)); return g * s * fmaf(z, 1.f - s, 1.f); }
+    return g;
+}
+
+E3B_DEVINL float4 norm_affine(const float4& yv, const float4& sc, const float4& sh, bool affine)
 {
     float4 v = yv;
     if (affine) {
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
         v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
     }
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    return v;
+}
+
+E3B_DEVINL float4 norm_relu_round(const float4& yv, const float4& sc, const float4& sh, bool affine, int act, float slope)
+{
+    float4 v = norm_affine(yv, sc, sh, affine);
+    v.x = act_fwd(v.x, act, slope); v.y = act_fwd(v.y, act, slope); v.z = act_fwd(v.z, act, slope); v.w = act_fwd(v.w, act, slope);
     // activations are MMA operands of the next conv: store them rounded to TF32
     v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
     return v;
@@ -283,7 +306,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
     for (int j = 0; j < kVpt; j++) {
         const int v = v0 + j * 256;
         if (v >= S) continue;
-        const float4 r = norm_relu_round(yv[j], sc, sh, p.scale != nullptr, p.relu);
+        const float4 r = norm_relu_round(yv[j], sc, sh, p.scale != nullptr, p.relu, p.slope);
         if (p.a) store_qh(p.a, r, n, p.Ch, cq, (size_t)S, (size_t)v);
     }
 }
@@ -321,7 +344,7 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
                 const size_t vox = ((size_t)z * p.H + yy) * p.W + x;
                 float4 v;
                 if (p.yh) v = unpack_half4(p.yh[qh_index(n, p.Ch, cq, S, vox)]);
-                else v = norm_relu_round(p.y[base * p.H * p.W + vox], sc, sh, p.scale != nullptr, p.relu);
+                else v = norm_relu_round(p.y[base * p.H * p.W + vox], sc, sh, p.scale != nullptr, p.relu, p.slope);
                 if (p.a) store_qh(p.a, v, n, p.Ch, cq, S, vox);
                 const unsigned char slot = (unsigned char)((dz * p.pkh + dy) * p.pkw + dx);
                 if (v.x > m.x) { m.x = v.x; idx.x = slot; }
@@ -347,6 +370,7 @@ struct NormBwdDev {
     int Dw, Hw, Ww;
     int Dg, Hg, Wg;                          // extents of the thread grid (s2d: the un-cropped fine grid)
     int relu, s2d;
+    float slope;                             // activation code / negative slope, see act_fwd
     const float *gamma, *mean, *rstd, *m1, *m2;
     double* sums;
     unsigned int* amax;                      // [N][pad8(C)][2] max |dr|, max |xhat| (float bits; reduce pass)
@@ -408,15 +432,14 @@ E3B_DEVINL void load_vox(const NormBwdDev& p, size_t o, int n, int cq, int z, in
     }
 }
 
-// the masked upstream gradient dr = (g0 + g1 + unpool(gp)) * [a > 0] and xhat of one voxel.
-// `a` is recomputed bit-exactly from y (the arithmetic of norm_act_kernel), never read.
+// the upstream gradient through the activation, dr = (g0 + g1 + unpool(gp)) * act'(z) ([z > 0] for ReLU), and xhat of one voxel.
+// z is recomputed bit-exactly from y (the arithmetic of norm_act_kernel), never read.
 template <bool GENERAL = true>
 E3B_DEVINL void voxel_grad(const NormBwdDev& p, const VoxIn& in, const float4& mu, const float4& rs, const float4& sc,
                            const float4& sh, float4& dr, float4& xh)
 {
     const float4 yv = in.y;
-    float4 a = yv;
-    if (p.scale) a = norm_relu_round(yv, sc, sh, true, p.relu);
+    const float4 zv = norm_affine(yv, sc, sh, p.scale != nullptr);       // the pre-activation, recomputed as the forward did
     xh = make_float4((yv.x - mu.x) * rs.x, (yv.y - mu.y) * rs.y, (yv.z - mu.z) * rs.z, (yv.w - mu.w) * rs.w);
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.g0) g = in.g0;
@@ -427,12 +450,8 @@ E3B_DEVINL void voxel_grad(const NormBwdDev& p, const VoxIn& in, const float4& m
         if (in.idx.z == in.slot) g.z += in.gp.z;
         if (in.idx.w == in.slot) g.w += in.gp.w;
     }
-    if (p.relu) {
-        if (!(a.x > 0.f)) g.x = 0.f;
-        if (!(a.y > 0.f)) g.y = 0.f;
-        if (!(a.z > 0.f)) g.z = 0.f;
-        if (!(a.w > 0.f)) g.w = 0.f;
-    }
+    g.x = act_bwd(zv.x, g.x, p.relu, p.slope); g.y = act_bwd(zv.y, g.y, p.relu, p.slope);
+    g.z = act_bwd(zv.z, g.z, p.relu, p.slope); g.w = act_bwd(zv.w, g.w, p.relu, p.slope);
     dr = g;
 }
 
@@ -833,8 +852,9 @@ static constexpr int kItemTensorBytes = 2 * kItemVox * 16;
 static constexpr int kFusedMaxStages = 8;
 static constexpr int kCtabSlots = kFusedMaxCp / 4;          // the constants of ALL rounds are staged up front when they fit
 
-// mu holds -mean * rstd: xhat = fma(y, rstd, mu).  thr: 0 with ReLU, -inf without (the mask is fma(y, sc, sh) > thr)
-struct QuadConsts { float4 mu, rs, sc, sh; float thr; };
+// mu holds -mean * rstd: xhat = fma(y, rstd, mu).  slope: what the gradient is multiplied by where fma(y, sc, sh) <= 0
+// (0 ReLU, 1 no activation, else the leaky-ReLU slope)
+struct QuadConsts { float4 mu, rs, sc, sh; float slope; };
 
 static constexpr int kQuadsPerThread = kItemVox / 128;       // a group of 4 warps covers the item's 512 voxels of one channel quad
 
@@ -919,16 +939,16 @@ E3B_DEVINL void fused_gather(const NormBwdDev& p, const FusedDev& f, int n, int 
     }
 }
 
-// xhat, and the ReLU mask applied to the summed upstream gradient.  The mask is y * scale + shift > 0 (scale = 1, shift = 0
-// without a norm): the forward's TF32 rounding of the activation cannot turn a positive value into zero, so the mask does
-// not need it.
+// xhat, and the (leaky-)ReLU derivative applied to the summed upstream gradient: 1 where y * scale + shift > 0 (scale = 1,
+// shift = 0 without a norm), the negative slope elsewhere.  The forward's TF32 rounding of the activation cannot turn a
+// positive value into zero, so the mask does not need it.
 E3B_DEVINL void fused_mask_xhat(const QuadConsts& c, const float4& yv, float4& g, float4& xh)
 {
     xh = make_float4(fmaf(yv.x, c.rs.x, c.mu.x), fmaf(yv.y, c.rs.y, c.mu.y), fmaf(yv.z, c.rs.z, c.mu.z), fmaf(yv.w, c.rs.w, c.mu.w));
-    if (!(fmaf(yv.x, c.sc.x, c.sh.x) > c.thr)) g.x = 0.f;
-    if (!(fmaf(yv.y, c.sc.y, c.sh.y) > c.thr)) g.y = 0.f;
-    if (!(fmaf(yv.z, c.sc.z, c.sh.z) > c.thr)) g.z = 0.f;
-    if (!(fmaf(yv.w, c.sc.w, c.sh.w) > c.thr)) g.w = 0.f;
+    if (!(fmaf(yv.x, c.sc.x, c.sh.x) > 0.f)) g.x *= c.slope;
+    if (!(fmaf(yv.y, c.sc.y, c.sh.y) > 0.f)) g.y *= c.slope;
+    if (!(fmaf(yv.z, c.sc.z, c.sh.z) > 0.f)) g.z *= c.slope;
+    if (!(fmaf(yv.w, c.sc.w, c.sh.w) > 0.f)) g.w *= c.slope;
 }
 
 // phase A over one staged item (this thread: channel quad `cq`, voxels t128 + 128 k).
@@ -1067,7 +1087,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
     // ---------------- consumers (256 threads; they synchronise among themselves on a named barrier)
     const int hsel = warp >> 2, t128 = threadIdx.x & 127;
     const uint32_t ring_thread = smem_u32(ring) + (uint32_t)(hsel * kItemVox + t128) * 16u;     // this thread's first voxel quad of stage 0
-    const float relu_thr = p.relu ? 0.f : -INFINITY;
+    const float act_slope = p.relu ? p.slope : 1.f;
     uint32_t parity = 0;                              // bit s: the phase of full[s] the next wait on stage s is for
     float dscale = 0.f;                               // the tensor's fp16 scale so far (0: none yet); identical in every CTA
     float bound_max = 0.f;
@@ -1122,7 +1142,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
             int cur_sp = -1, n = 0, cqp = 0;
             int sp = i0 / nchunks, chunk = i0 - sp * nchunks;                   // item i0 + j = (slab pair sp, chunk)
             QuadConsts c;
-            c.thr = relu_thr;
+            c.slope = act_slope;
             for (int j = 0; j <= cnt; j++) {
                 if (j == cnt || sp != cur_sp) {
                     if (cur_sp >= 0) {
@@ -1311,7 +1331,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
             int cur_sp = -1, n = 0, cqp = 0;
             int sp = (i1 - 1) / nchunks, chunk = (i1 - 1) - sp * nchunks;
             QuadConsts c;
-            c.thr = relu_thr;
+            c.slope = act_slope;
             float4 ga, m1, m2, rk;
             for (int j = cnt - 1; j >= 0; j--) {
                 if (sp != cur_sp) {
@@ -1766,8 +1786,9 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
 }
 
 int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled, uint8_t* pool_idx, int N, int C,
-                 int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, int y_is_half, void* stream)
+                 int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, float act_slope, int y_is_half, void* stream)
 {
+    if (relu < 0 || relu > 2) return set_error("norm_act: unknown activation code %d", relu);
     const bool pooling = pooled || pool_idx;
     if (y_is_half && (!pooling || scale || a)) return set_error("norm_act: an fp16 input is only pooled (eval path)");
     if (!pooling) { pk_d = pk_h = pk_w = 1; }
@@ -1778,7 +1799,7 @@ int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a,
     p.yh = y_is_half ? reinterpret_cast<const uint2*>(y) : nullptr;
     p.a = reinterpret_cast<uint2*>(a); p.pooled = reinterpret_cast<uint2*>(pooled);
     p.pool_idx = reinterpret_cast<uchar4*>(pool_idx);
-    p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu;
+    p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu; p.slope = act_slope;
     p.Dp = (D + pk_d - 1) / pk_d; p.Hp = (H + pk_h - 1) / pk_h; p.Wp = (W + pk_w - 1) / pk_w;
     if (p.Cq > 65535 || N > 65535) return set_error("norm_act: too many channels / samples for the launch grid");
     if (pooling) {
@@ -1810,7 +1831,8 @@ static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)
     p.Dw = (a->D + p.wd - 1) / p.wd; p.Hw = (a->H + p.wh - 1) / p.wh; p.Ww = (a->W + p.ww - 1) / p.ww;
     p.Dg = a->D; p.Hg = a->H; p.Wg = a->W;
     if (a->s2d) { p.Dg = p.Dw * p.wd; p.Hg = p.Hw * p.wh; p.Wg = p.Ww * p.ww; }
-    p.relu = a->relu; p.s2d = a->s2d;
+    if (a->relu < 0 || a->relu > 2) return set_error("norm_bwd: unknown activation code %d", a->relu);
+    p.relu = a->relu; p.slope = a->act_slope; p.s2d = a->s2d;
     p.gamma = (a->mode == 0) ? nullptr : a->gamma;
     p.mean = a->mean; p.rstd = a->rstd; p.m1 = a->m1; p.m2 = a->m2;
     p.sums = a->sums; p.dy = reinterpret_cast<uint2*>(a->dy);
@@ -1892,6 +1914,7 @@ int e3b_norm_bwd_fused(const e3b_norm_bwd_args* a, void* stream)
     if (fill_bwd(a, p)) return 1;
     const int Cp = p.Cq * 4;
     if (!a->amax || !a->dy_scale || !a->sums) return set_error("norm_bwd_fused: sums / amax / dy_scale buffers are required");
+    if (a->relu == 2) return set_error("norm_bwd_fused: SiLU is served by the reduce / finalize / apply kernels");
     if (Cp > kFusedMaxCp) return set_error("norm_bwd_fused: more than %d channels: use the reduce / finalize / apply kernels", kFusedMaxCp);
     if (a->mode == 1 && (a->G <= 0 || a->C % a->G)) return set_error("norm_bwd: bad group count");
     if (a->dbias && (a->mode == 1 || a->mode == 2) && !a->fwd_stats) return set_error("norm_bwd: dbias needs fwd_stats");

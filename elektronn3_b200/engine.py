@@ -293,10 +293,35 @@ def norm_finalize(stats, mode, G, N, C, S, gamma, beta, eps, rm, rv, momentum, d
     return st
 
 
-def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, save=False):
-    """a = relu(y*scale+shift) (QH) and optionally the ceil-mode max-pooled tensor (QH).  save=True (a backward pass will
+ACT_RELU = (1, 0.0)
+
+
+def act_code(act, training):
+    """-> (code, negative slope) as the kernels take them (include/e3b.h) for an activation module produced by
+    get_activation (models/unet.py:183-199): 'relu', 'leaky', 'rrelu' (eval mode), 'silu', 'lin' or a module of those types."""
+    import torch.nn as nn
+    if act is None or isinstance(act, nn.ReLU):
+        return ACT_RELU
+    if isinstance(act, nn.Identity):
+        return (0, 0.0)
+    if isinstance(act, nn.LeakyReLU):
+        return (1, float(act.negative_slope))
+    if isinstance(act, nn.RReLU):
+        if training:
+            raise NotImplementedError('nn.RReLU draws a random slope per element in training mode: not on the B200 path '
+                                      '(eval mode, with the mean slope, is)')
+        return (1, (float(act.lower) + float(act.upper)) / 2)
+    if isinstance(act, nn.SiLU):
+        return (2, 0.0)
+    raise NotImplementedError(f'activation module {type(act).__name__} is not on the B200 path')
+
+
+def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, save=False, act=None):
+    """a = act(y*scale+shift) (QH) and optionally the ceil-mode max-pooled tensor (QH).  save=True (a backward pass will
     follow) also records the arg-max slots of the pooling windows.  With write_a=False `y` is already a QH activation
-    (eval path) and is only pooled."""
+    (eval path) and is only pooled.  act: (code, slope) of act_code; default ReLU (relu=False: identity)."""
+    if act is None:
+        act = ACT_RELU if relu else (0, 0.0)
     dev = y.t.device
     if write_a == y.half:
         raise RuntimeError('norm_act: y must be float32 QP when a is written, a QH activation otherwise')
@@ -313,7 +338,7 @@ def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, save=False)
                                         device=dev)
     L.check(L.lib().e3b_norm_act(y.ptr, _p(scale), _p(shift), a.ptr if a else None, pooled.ptr if pooled else None,
                                  _p(pidx), y.N, y.C, y.D, y.H, y.W, pk[0], pk[1], pk[2],
-                                 1 if relu else 0, 1 if y.half else 0, _stream()), 'norm_act')
+                                 act[0], act[1], 1 if y.half else 0, _stream()), 'norm_act')
     return a, pooled
 
 
@@ -321,8 +346,8 @@ def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, save=False)
 class ConvSpec:
     """A conv3 layer (models/unet.py:131-149) + the norm/activation that follows it."""
 
-    def __init__(self, name, conv, norm, C0, C1):
-        self.name, self.conv, self.norm = name, conv, norm
+    def __init__(self, name, conv, norm, C0, C1, act=None, explicit_pad=False):
+        self.name, self.conv, self.norm, self.act = name, conv, norm, act
         w = conv.weight
         self.Co = w.shape[0]
         self.C0, self.C1 = C0, C1
@@ -330,6 +355,8 @@ class ConvSpec:
         pads = tuple(conv.padding)
         if len(ks) == 2:
             ks, pads = (1,) + ks, (0,) + pads
+        if explicit_pad:           # the source tensor already carries the zero padding (ResizeSpec)
+            pads = (0, 0, 0)
         self.k, self.pad = ks, pads
         self.n_total = cpad16(self.Co)
         self.n_total_dgrad = cpad16(cpad8(C0) + (cpad8(C1) if C1 else 0))
@@ -351,8 +378,8 @@ class ConvSpec:
 class UpSpec:
     """upconv2 'transpose' (models/unet.py:152-165) + norm0/act0 of UpConv"""
 
-    def __init__(self, name, up, norm):
-        self.name, self.up, self.norm = name, up, norm
+    def __init__(self, name, up, norm, act=None):
+        self.name, self.up, self.norm, self.act = name, up, norm, act
         w = up.weight
         self.Ci, self.Co = w.shape[0], w.shape[1]
         s = tuple(w.shape[2:])
@@ -361,6 +388,26 @@ class UpSpec:
         self.s = s
         self.taps = s[0] * s[1] * s[2]
         self.n_total = self.taps * cpad16(self.Co)
+
+
+class ResizeSpec(ConvSpec):
+    """upconv2 'resizeconv_*' (ResizeConv, models/unet.py:411-449): nn.Upsample + conv3 / conv1, + norm0/act0 of UpConv.
+    The up-sampled tensor is produced with the conv's zero padding made explicit, so the conv is a ConvSpec with pad 0."""
+
+    def __init__(self, name, rc, norm, Ci, act=None):
+        super().__init__(name + '.conv', rc.conv, norm, Ci, 0, act=act, explicit_pad=True)
+        sf = rc.scale_factor
+        sf = (sf,) * 3 if isinstance(sf, int) else tuple(int(v) for v in sf)
+        if len(sf) == 2:
+            sf = (1,) + sf
+        if rc.dim == 2:
+            sf = (1, sf[1], sf[2])
+        self.s = sf
+        self.linear = 0 if rc.upsampling_mode == 'nearest' else 1
+        cpads = tuple(rc.conv.padding)
+        if len(cpads) == 2:
+            cpads = (0,) + cpads
+        self.conv_pad = cpads          # the padding of rc.conv (1 on 3-tap axes, 0 for conv1): where data starts in the padded tensor
 
 
 def norm_mode(norm, training):
@@ -382,7 +429,8 @@ def norm_mode(norm, training):
 
 class Unit:
     """Everything one conv -> norm -> relu [-> pool] stage leaves behind for the backward pass."""
-    __slots__ = ('spec', 'src0', 'src1', 'off1', 'y', 'a', 'pooled', 'pool', 'mode', 'G', 'nstate', 'stats', 'dec')
+    __slots__ = ('spec', 'src0', 'src1', 'off1', 'y', 'a', 'pooled', 'pool', 'mode', 'G', 'nstate', 'stats', 'dec', 'act',
+                 'resize')
 
 
 class WeightSet:
@@ -442,8 +490,9 @@ class TrainImages:
 class Net:
     """Flat description of a UNet instance (built by elektronn3_b200.unet.UNet)."""
 
-    def __init__(self, down, up, final_conv, dim, cache):
+    def __init__(self, down, up, final_conv, dim, cache, merge_add=False):
         self.down, self.up, self.final, self.dim, self.cache = down, up, final_conv, dim, cache
+        self.merge_add = merge_add       # merge_mode='add' (models/unet.py:399-401) instead of the channel concat
         self.wset = None
         self.train_images = None
 
@@ -531,26 +580,28 @@ def _conv_weights(net, spec, mode, training):
 
 
 def _run_unit(net, spec, src0, src1, off1, pool, training, save):
-    """conv -> norm -> relu [-> pool]  (DownConv.forward models/unet.py:244-253, UpConv :402-407)"""
+    """conv -> norm -> act [-> pool]  (DownConv.forward models/unet.py:244-253, UpConv :402-407)"""
     mode, G = norm_mode(spec.norm, training)
+    act = act_code(spec.act, training)
     wpk, bias, wsc = _conv_weights(net, spec, 0, training)
     u = Unit()
-    u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G = spec, src0, src1, off1, pool, mode, G
-    u.pooled = u.nstate = u.stats = u.dec = None
+    u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G, u.act = spec, src0, src1, off1, pool, mode, G, act
+    u.pooled = u.nstate = u.stats = u.dec = u.resize = None
     var = spec.variants[0]
-    if mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save):
+    if (mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save)) and act == ACT_RELU:
         # inference: the conv epilogue (folded BN, bias, ReLU) writes the next layer's operand directly
         a, _, _ = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
                                relu=True, half_out=True, variant=var, w_unscale=wsc)
         u.y = u.a = a
         if pool is not None:
             _, u.pooled = norm_act(a, None, None, write_a=False, pool=pool)
-    elif mode == MODE_NONE:
-        # training without normalisation: y is kept in float32 for the backward pass (identity affine)
+    elif mode == MODE_NONE or mode == MODE_BATCH_EVAL:
+        # no normalisation (or eval-mode BatchNorm folded into the weights) with a backward pass to follow / an activation
+        # the conv epilogue does not fuse: y is kept in float32 (identity affine), the activation kernel follows
         y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
                                    variant=var, w_unscale=wsc)
         u.y = y
-        u.a, u.pooled = norm_act(y, None, None, pool=pool, save=save)
+        u.a, u.pooled = norm_act(y, None, None, pool=pool, save=save, act=act)
     else:
         n = spec.norm
         y, _, stats = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1,
@@ -563,7 +614,7 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save):
         u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, S, _affine(n, 'weight'), _affine(n, 'bias'), n.eps,
                                  rm, rv, mom, y.t.device)
         u.y, u.stats = y, stats
-        u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, save=save)
+        u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, save=save, act=act)
     if not save:
         u.y = u.src0 = u.src1 = None
     return u
@@ -585,21 +636,60 @@ def _bn_running(n, training):
     return n.running_mean, n.running_var, float(n.momentum)
 
 
+def _autocrop(full, enc_spatial):
+    """autocrop (models/unet.py:256-325) -> (extents the up-sampled tensor is cropped to, offset of the centre crop of the
+    skip tensor): from_up loses one trailing voxel where (u - d) is odd (:294-301), from_down is centre-cropped (:303-324)"""
+    out_sp = tuple(u_ - ((u_ - d_) % 2) for u_, d_ in zip(full, enc_spatial))
+    for u_, d_ in zip(out_sp, enc_spatial):
+        if u_ > d_:
+            raise RuntimeError(f'autocrop: upsampled extent {out_sp} exceeds the skip tensor {enc_spatial} '
+                               '(models/unet.py:303-324 cannot crop from_down to a larger shape)')
+    return out_sp, tuple((d_ - u_) // 2 for u_, d_ in zip(out_sp, enc_spatial))
+
+
+def _run_resize(net, spec, dec, enc, training, save):
+    """ResizeConv -> autocrop -> norm0 -> act0  (UpConv.forward models/unet.py:385-398 with up_mode='resizeconv_*',
+    ResizeConv :411-449).  The up-sampled tensor carries the conv's zero padding explicitly: fine voxel f sits at
+    f + conv_pad, and only the fine voxels the (auto)cropped conv output reads are stored -- the conv is then VALID."""
+    s, k, cp = spec.s, spec.k, spec.conv_pad
+    full = (dec.D * s[0], dec.H * s[1], dec.W * s[2])
+    out_sp, off1 = _autocrop(full, enc.spatial)
+    ext = tuple(o + kk - 1 for o, kk in zip(out_sp, k))
+    R = tuple(min(f, e - p) for f, e, p in zip(full, ext, cp))
+    up = QP.empty_half(dec.N, dec.C, ext[0], ext[1], ext[2], dec.t.device)
+    geom = (dec.D, dec.H, dec.W) + ext + tuple(s) + tuple(cp) + R + (spec.linear,)
+    L.check(L.lib().e3b_upsample_qh(dec.ptr, up.ptr, dec.N, dec.C, *geom, _stream()), 'upsample_qh')
+    u = _run_unit(net, spec, up, None, (0, 0, 0), None, training, save)
+    u.resize = geom
+    return u, off1
+
+
+def _resize_bwd(u, dup):
+    """gradient of the padded up-sampled tensor (dgrad output, QP) -> gradient of the coarse decoder tensor (QP)"""
+    geom = u.resize
+    g = QP.empty(dup.N, dup.C, geom[0], geom[1], geom[2], dup.t.device)
+    L.check(L.lib().e3b_upsample_bwd_qp(dup.ptr, g.ptr, dup.N, dup.C, *geom, _stream()), 'upsample_bwd_qp')
+    return g
+
+
+def add_qh(a, b, off):
+    """merge_mode='add' (models/unet.py:399-401): a + b[centre crop at off], QH operand tensors"""
+    out = QP.empty_half(a.N, a.C, a.D, a.H, a.W, a.t.device)
+    L.check(L.lib().e3b_add_qh(a.ptr, b.ptr, out.ptr, a.N, a.C, a.D, a.H, a.W, b.D, b.H, b.W, off[0], off[1], off[2],
+                               _stream()), 'add_qh')
+    return out
+
+
 def _run_up(net, spec, dec, enc, training, save):
     """upconv -> autocrop -> norm0 -> act0  (UpConv.forward models/unet.py:385-398)"""
     mode, G = norm_mode(spec.norm, training)
+    act = act_code(spec.act, training)
     up = spec.up
     full = (dec.D * spec.s[0], dec.H * spec.s[1], dec.W * spec.s[2])
-    # autocrop (unet.py:294-301): from_up loses one voxel where (u - d) is odd
-    out_sp = tuple(u_ - ((u_ - d_) % 2) for u_, d_ in zip(full, enc.spatial))
-    for u_, d_ in zip(out_sp, enc.spatial):
-        if u_ > d_:
-            raise RuntimeError(f'autocrop: upsampled extent {out_sp} exceeds the skip tensor {enc.spatial} '
-                               '(models/unet.py:303-324 cannot crop from_down to a larger shape)')
-    off1 = tuple((d_ - u_) // 2 for u_, d_ in zip(out_sp, enc.spatial))
+    out_sp, off1 = _autocrop(full, enc.spatial)
     u = Unit()
-    u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G = spec, dec, None, (0, 0, 0), None, mode, G
-    u.pooled = u.nstate = u.stats = None
+    u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G, u.act = spec, dec, None, (0, 0, 0), None, mode, G, act
+    u.pooled = u.nstate = u.stats = u.resize = None
     u.dec = dec
     bias = up.bias.detach() if up.bias is not None else None
     wsc = net.wset.scales[spec.name]
@@ -619,15 +709,15 @@ def _run_up(net, spec, dec, enc, training, save):
     else:
         wpk = net.cache.get((spec.name, 'up'), (up.weight,),
                             lambda: pack_weights(2, up.weight, None, spec.Ci, 0, spec.Co, spec.s, wscale=wsc), training)
-    if mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save):
+    if (mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save)) and act == ACT_RELU:
         a, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias, relu=True,
                                scatter=spec.s, out_spatial=out_sp, half_out=True, w_unscale=wsc)
         u.y = u.a = a
-    elif mode == MODE_NONE:
+    elif mode == MODE_NONE or mode == MODE_BATCH_EVAL:
         y, _, _ = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias,
                                scatter=spec.s, out_spatial=out_sp, w_unscale=wsc)
         u.y = y
-        u.a, _ = norm_act(y, None, None)
+        u.a, _ = norm_act(y, None, None, act=act)
     else:
         n = spec.norm
         y, _, stats = conv_forward(dec, wpk, spec.n_total, spec.Co, (1, 1, 1), (0, 0, 0), bias=bias,
@@ -639,7 +729,7 @@ def _run_up(net, spec, dec, enc, training, save):
         u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, y.D * y.H * y.W, _affine(n, 'weight'),
                                  _affine(n, 'bias'), n.eps, rm, rv, mom, y.t.device)
         u.y, u.stats = y, stats
-        u.a, _ = norm_act(y, u.nstate.scale, u.nstate.shift)
+        u.a, _ = norm_act(y, u.nstate.scale, u.nstate.shift, act=act)
     if not save:
         u.y = u.dec = u.src0 = None
     return u, off1
@@ -676,11 +766,16 @@ def forward_features_qp(net, cur, training, save, squeeze=False, in_shape=None):
         tape.down.append((u1, u2))
     for i, (ups, c1, c2) in enumerate(net.up):
         e = enc[-(i + 2)]
-        u0, off1 = _run_up(net, ups, cur, e, training, save)
-        u1 = _run_unit(net, c1, u0.a, e, off1, None, training, save)
+        u0, off1 = (_run_resize if isinstance(ups, ResizeSpec) else _run_up)(net, ups, cur, e, training, save)
+        add_info = None
+        if net.merge_add:
+            u1 = _run_unit(net, c1, add_qh(u0.a, e, off1), None, (0, 0, 0), None, training, save)
+            add_info = (off1, e.spatial)
+        else:
+            u1 = _run_unit(net, c1, u0.a, e, off1, None, training, save)
         u2 = _run_unit(net, c2, u1.a, None, (0, 0, 0), None, training, save)
         cur = u2.a
-        tape.up.append((u0, u1, u2, len(net.down) - 2 - i))
+        tape.up.append((u0, u1, u2, len(net.down) - 2 - i, add_info))
     tape.final_in = cur
     return cur, tape
 
@@ -792,10 +887,11 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True):
         dy = QP.empty_half(N, C, a.D, a.H, a.W, dev)
     dy.scale = dy_scale            # the tensor holds 2^k * dy; conv_forward undoes it through dy_scale[2]
     args.dy = dy.ptr
-    args.relu = 1
+    args.relu, args.act_slope = getattr(u, 'act', ACT_RELU)
     lib = L.lib()
     st = _stream()
-    fused = Cp <= 512 and os.environ.get('E3B_NORM_BWD', 'fused') != 'split'
+    # (SiLU's derivative lives in the three-kernel path only: the persistent kernel serves the (leaky-)ReLU family)
+    fused = Cp <= 512 and args.relu != 2 and os.environ.get('E3B_NORM_BWD', 'fused') != 'split'
     if s2d is not None and (a.D % s2d[0] or a.H % s2d[1] or a.W % s2d[2]):
         fused = False              # autocrop dropped fine voxels: the three-kernel path zero-fills them
     if fused:
@@ -871,10 +967,19 @@ def _backward(net, tape, dlogits, need_dx):
 
     g = da
     skip = {}
-    for (u0, u1, u2, enc_index), (ups, c1, c2) in zip(reversed(tape.up), reversed(net.up)):
+    for (u0, u1, u2, enc_index, add_info), (ups, c1, c2) in zip(reversed(tape.up), reversed(net.up)):
         g, _ = _conv_unit_bwd(net, u2, g, None, None, grads, True)
         du, denc = _conv_unit_bwd(net, u1, g, None, None, grads, True)
+        if add_info is not None:
+            # merge_mode='add': the gradient of the sum goes to both summands; the skip tensor sees it through autocrop's slice
+            denc = QP(du.t, du.N, du.C, du.D, du.H, du.W)
+            if tuple(add_info[0]) != (0, 0, 0) or add_info[1] != du.spatial:
+                denc.crop_off = tuple(add_info[0])
         skip[enc_index] = denc
+        if isinstance(ups, ResizeSpec):
+            dup, _ = _conv_unit_bwd(net, u0, du, None, None, grads, True)
+            g = _resize_bwd(u0, dup)
+            continue
         # norm0/act0 backward, written space-to-depth for the transposed conv's GEMMs
         up = ups.up
         dy, dgamma, dbeta, dbias = _norm_bwd(u0, ups.Co, du, s2d=ups.s, want_bias=up.bias is not None)

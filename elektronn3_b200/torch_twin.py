@@ -57,12 +57,17 @@ class TwinUp(nn.Module):
         self.upconv, self.conv1, self.conv2 = b.upconv, b.conv1, b.conv2
         self.norm0, self.norm1, self.norm2 = b.norm0, b.norm1, b.norm2
         self.act0, self.act1, self.act2 = b.act0, b.act1, b.act2
+        self.add = b.merge_mode == 'add'
 
     def forward(self, enc: torch.Tensor, dec: torch.Tensor) -> torch.Tensor:
         up = self.upconv(dec)
         enc, up = _crop_pair(enc, up)
         up = self.act0(self.norm0(up))
-        y = self.act1(self.norm1(self.conv1(torch.cat((up, enc), 1))))
+        if self.add:
+            mrg = up + enc
+        else:
+            mrg = torch.cat((up, enc), 1)
+        y = self.act1(self.norm1(self.conv1(mrg)))
         return self.act2(self.norm2(self.conv2(y)))
 
 

@@ -14,9 +14,11 @@ protocol as used by ``Trainer`` (training/trainer.py:309,519-520,863-874) and ``
   ``torch.autograd.Function`` for the whole network) which launches the CUDA kernels through the C ABI.
 
 There is no CPU / cuDNN fallback: a non-CUDA input or a missing ``libe3b.so`` raises.
-Options of the reference that are outside the accelerated path raise ``NotImplementedError`` at
-construction (attention, ``up_mode != 'transpose'``, ``merge_mode='add'``, activations other than ReLU).
+Options: ``up_mode`` 'transpose' and the four 'resizeconv_*' modes, ``merge_mode`` 'concat' and 'add', activations
+'relu' / 'leaky' / 'silu' / 'lin' / 'rrelu' (eval mode) or modules of those types.  What is still outside the
+accelerated path raises ``NotImplementedError`` at construction (``attention=True``, 'prelu' and other modules).
 """
+import copy
 from typing import Sequence
 
 import torch
@@ -50,6 +52,23 @@ def _make_norm(normtype, C, dim):
                      '"group" or "group<G>", where <G> is the number of groups.')
 
 
+def _make_activation(activation):
+    """get_activation (models/unet.py:183-199): one module per call site; modules are deep-copied"""
+    if isinstance(activation, str):
+        table = {'relu': nn.ReLU, 'leaky': lambda: nn.LeakyReLU(negative_slope=0.1), 'rrelu': nn.RReLU, 'silu': nn.SiLU,
+                 'lin': nn.Identity}
+        if activation == 'prelu':
+            raise NotImplementedError('activation="prelu" (a learned slope) is not on the B200 path')
+        if activation not in table:
+            # (the reference returns None here and fails at the first forward)
+            raise ValueError(f'Unknown activation "{activation}"')
+        return table[activation]()
+    if not isinstance(activation, nn.Module):
+        raise ValueError(f'activation must be a string or a torch module, got {activation!r}')
+    engine.act_code(activation, False)          # NotImplementedError for module types without a kernel
+    return copy.deepcopy(activation)
+
+
 class _Container(nn.Module):
     """Parameter container mirroring a reference sub-block; the kernels are driven by UNet.forward."""
 
@@ -61,7 +80,7 @@ class _Container(nn.Module):
 class DownConv(_Container):
     """Parameters of DownConv (models/unet.py:202-253): conv1, conv2, norm0, norm1, pool."""
 
-    def __init__(self, cin, cout, pooling, planar, normalization, full_norm, dim, conv_mode):
+    def __init__(self, cin, cout, pooling, planar, normalization, full_norm, dim, conv_mode, activation='relu'):
         super().__init__()
         self.in_channels, self.out_channels, self.pooling, self.dim = cin, cout, pooling, dim
         self.normalization = normalization
@@ -79,7 +98,7 @@ class DownConv(_Container):
         else:
             self.pool = nn.Identity()
             self.pool_ks = -123
-        self.act1, self.act2 = nn.ReLU(), nn.ReLU()
+        self.act1, self.act2 = _make_activation(activation), _make_activation(activation)
         self.norm0 = _make_norm(normalization, cout, dim) if full_norm else nn.Identity()
         self.norm1 = _make_norm(normalization, cout, dim)
 
@@ -96,23 +115,55 @@ class DummyAttention(_Container):
     pass
 
 
+class ResizeConv(nn.Module):
+    """Parameters of ResizeConv (models/unet.py:411-449): 2x ``nn.Upsample`` + conv3 (padding 1) / conv1.  ``forward`` is
+    plain torch and serves the export twin only (torch_twin.py); the network runs e3b_upsample_qh + the conv kernels."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, planar=False, dim=3, upsampling_mode='nearest'):
+        super().__init__()
+        self.upsampling_mode = upsampling_mode
+        self.scale_factor = 2
+        if dim == 3 and planar:
+            self.scale_factor = (1, 2, 2)
+        self.dim = dim
+        self.upsample = nn.Upsample(scale_factor=self.scale_factor, mode=self.upsampling_mode)
+        C = _conv_cls(dim)
+        if kernel_size == 3:
+            k3, p3 = (3, 1) if not (planar and dim == 3) else ((1, 3, 3), (0, 1, 1))
+            self.conv = C(in_channels, out_channels, kernel_size=k3, padding=p3)
+        elif kernel_size == 1:
+            self.conv = C(in_channels, out_channels, kernel_size=1)
+        else:
+            raise ValueError(f'kernel_size={kernel_size} is not supported. Choose 1 or 3.')
+
+    def forward(self, x):
+        return self.conv(self.upsample(x))
+
+
 class UpConv(_Container):
     """Parameters of UpConv (models/unet.py:328-408): upconv, conv1, conv2, norm0..2."""
 
-    def __init__(self, cin, cout, planar, normalization, full_norm, dim, conv_mode):
+    def __init__(self, cin, cout, planar, normalization, full_norm, dim, conv_mode, activation='relu', merge_mode='concat',
+                 up_mode='transpose'):
         super().__init__()
         self.in_channels, self.out_channels = cin, cout
-        self.merge_mode, self.up_mode, self.normalization = 'concat', 'transpose', normalization
+        self.merge_mode, self.up_mode, self.normalization = merge_mode, up_mode, normalization
         pad = 1 if 'same' in conv_mode else 0
         k3, p3, k2 = 3, pad, 2
         if planar and dim == 3:
             k3, p3, k2 = (1, 3, 3), (0, pad, pad), (1, 2, 2)
         C = _conv_cls(dim)
         CT = nn.ConvTranspose3d if dim == 3 else nn.ConvTranspose2d
-        self.upconv = CT(cin, cout, kernel_size=k2, stride=k2)
-        self.conv1 = C(2 * cout, cout, kernel_size=k3, padding=p3)
+        if up_mode == 'transpose':               # upconv2, models/unet.py:152-175
+            self.upconv = CT(cin, cout, kernel_size=k2, stride=k2)
+        else:
+            mode = ('trilinear' if dim == 3 else 'bilinear') if 'linear' in up_mode else 'nearest'
+            self.upconv = ResizeConv(cin, cout, kernel_size=1 if up_mode.endswith('1') else 3, planar=planar, dim=dim,
+                                     upsampling_mode=mode)
+        self.conv1 = C(2 * cout if merge_mode == 'concat' else cout, cout, kernel_size=k3, padding=p3)
         self.conv2 = C(cout, cout, kernel_size=k3, padding=p3)
-        self.act0, self.act1, self.act2 = nn.ReLU(), nn.ReLU(), nn.ReLU()
+        self.act0, self.act1, self.act2 = (_make_activation(activation), _make_activation(activation),
+                                           _make_activation(activation))
         if full_norm:
             self.norm0 = _make_norm(normalization, cout, dim)
             self.norm1 = _make_norm(normalization, cout, dim)
@@ -206,14 +257,11 @@ class UNet(nn.Module):
                                'option.\nIf you still want to use batch normalization, set `normalization=batch` '
                                'instead.')
         # --- options outside the accelerated hot path
-        if up_mode != 'transpose':
-            raise NotImplementedError(f'up_mode="{up_mode}" is not on the B200 path (only "transpose")')
-        if merge_mode != 'concat':
-            raise NotImplementedError('merge_mode="add" is not on the B200 path (only "concat")')
+        if up_mode == 'upsample':
+            # (valid by the reference's check, but its upconv2 has no branch for it and returns None: unet.py:152-175)
+            raise NotImplementedError('up_mode="upsample" is not on the B200 path')
         if attention:
             raise NotImplementedError('attention=True (GridAttention) is not on the B200 path')
-        if not (activation == 'relu' or isinstance(activation, nn.ReLU)):
-            raise NotImplementedError(f'activation={activation!r} is not on the B200 path (only ReLU)')
 
         self.up_mode, self.merge_mode = up_mode, merge_mode
         self.out_channels, self.in_channels = out_channels, in_channels
@@ -230,13 +278,14 @@ class UNet(nn.Module):
             outs = start_filts * (2 ** i)
             self.down_convs.append(DownConv(ins, outs, pooling=i < n_blocks - 1, planar=i in planar_blocks,
                                             normalization=normalization, full_norm=full_norm, dim=dim,
-                                            conv_mode=conv_mode))
+                                            conv_mode=conv_mode, activation=activation))
         for i in range(n_blocks - 1):                   # models/unet.py:861-879
             ins = outs
             outs = ins // 2
             self.up_convs.append(UpConv(ins, outs, planar=(n_blocks - 2 - i) in planar_blocks,
                                         normalization=normalization, full_norm=full_norm, dim=dim,
-                                        conv_mode=conv_mode))
+                                        conv_mode=conv_mode, activation=activation, merge_mode=merge_mode,
+                                        up_mode=up_mode))
         self.conv_final = _conv_cls(dim)(outs, out_channels, kernel_size=1)
         self.apply(self.weight_init)
 
@@ -256,15 +305,21 @@ class UNet(nn.Module):
             down, up = [], []
             for i, b in enumerate(self.down_convs):
                 p = f'down_convs.{i}'
-                down.append((engine.ConvSpec(p + '.conv1', b.conv1, b.norm0, b.in_channels, 0),
-                             engine.ConvSpec(p + '.conv2', b.conv2, b.norm1, b.out_channels, 0),
+                down.append((engine.ConvSpec(p + '.conv1', b.conv1, b.norm0, b.in_channels, 0, act=b.act1),
+                             engine.ConvSpec(p + '.conv2', b.conv2, b.norm1, b.out_channels, 0, act=b.act2),
                              b.pool_kernel()))
             for i, b in enumerate(self.up_convs):
                 p = f'up_convs.{i}'
-                up.append((engine.UpSpec(p + '.upconv', b.upconv, b.norm0),
-                           engine.ConvSpec(p + '.conv1', b.conv1, b.norm1, b.out_channels, b.out_channels),
-                           engine.ConvSpec(p + '.conv2', b.conv2, b.norm2, b.out_channels, 0)))
-            net = engine.Net(down, up, self.conv_final, self.dim, cache)
+                if isinstance(b.upconv, ResizeConv):
+                    ups = engine.ResizeSpec(p + '.upconv', b.upconv, b.norm0, b.in_channels, act=b.act0)
+                else:
+                    ups = engine.UpSpec(p + '.upconv', b.upconv, b.norm0, act=b.act0)
+                add = b.merge_mode == 'add'
+                up.append((ups,
+                           engine.ConvSpec(p + '.conv1', b.conv1, b.norm1, b.out_channels, 0 if add else b.out_channels,
+                                           act=b.act1),
+                           engine.ConvSpec(p + '.conv2', b.conv2, b.norm2, b.out_channels, 0, act=b.act2)))
+            net = engine.Net(down, up, self.conv_final, self.dim, cache, merge_add=self.merge_mode == 'add')
             self.__dict__['_e3b_net'] = net
         return net
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define E3B_VERSION 220
+#define E3B_VERSION 230
 
 int e3b_version(void);
 const char* e3b_last_error(void);
@@ -157,7 +157,9 @@ int64_t e3b_wgrad_workspace_floats(const e3b_wgrad_args* args);
 int e3b_wgrad(const e3b_wgrad_args* args, void* stream);
 
 /* ---- normalisation + activation (+ pooling) -----------------------------------------------------
- * get_normalization (unet.py:77-111) + get_activation 'relu' (:183-186) + MaxPool(ceil_mode) (:225-229).
+ * get_normalization (unet.py:77-111) + get_activation (:183-199) + MaxPool(ceil_mode) (:225-229).
+ * Activation code `relu` (here and in e3b_norm_bwd_args): 0 identity ('lin'), 1 the leaky-ReLU family with negative slope
+ * `act_slope` (0 = nn.ReLU, 0.1 = 'leaky', (lower+upper)/2 = eval-mode nn.RReLU), 2 nn.SiLU.
  * mode: 0 none, 1 group/instance (G groups), 2 batch (training: batch stats + running update),
  *       3 batch eval (running stats).
  * finalize: stats [N][C][2] (from e3b_conv) -> per-(n,c) scale/shift and mean/rstd ([N][pad8(C)]). */
@@ -165,17 +167,18 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
                       const float* gamma, const float* beta, float eps,
                       float* running_mean, float* running_var, float momentum,
                       float* scale, float* shift, float* mean, float* rstd, void* stream);
-/* a = relu(y*scale+shift): y QP (fp32), a QH; if pooled != NULL also pooled = maxpool_{(pk_d,pk_h,pk_w), ceil}(a) (QH).
+/* a = act(y*scale+shift): y QP (fp32), a QH; if pooled != NULL also pooled = maxpool_{(pk_d,pk_h,pk_w), ceil}(a) (QH).
  * scale/shift NULL = identity; a NULL = only the pooled tensor is written.  y_is_half: y is itself a QH
  * activation (eval path: the conv epilogue already activated it) and is only pooled.
  * pool_idx (optional, uint8 (N, pad8(C)/4, Dp, Hp, Wp, 4)): per pooled voxel and channel the window slot
  * ((dz*pk_h+dy)*pk_w+dx) of the first maximum -- what nn.MaxPool3d(return_indices) would give; consumed by
  * e3b_norm_bwd_*. */
 int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled, uint8_t* pool_idx,
-                 int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, int y_is_half, void* stream);
+                 int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, float act_slope, int y_is_half,
+                 void* stream);
 
 /* backward of conv -> norm -> relu [-> pool] as autograd derives it:
- *   dr  = (g0 + g1 + unpool(gp)) * [a > 0]          g0,g1: same extents as y (either may be NULL)
+ *   dr  = (g0 + g1 + unpool(gp)) * act'(y*scale+shift)   ([a > 0] for ReLU)   g0,g1: same extents as y (either may be NULL)
  *   reduce:   sums[n][c] = (sum dr, sum dr*xhat)   (fp64 atomics, [N][pad8(C)][2]);  amax = (max|dr|, max|xhat|)
  *   finalize: m1,m2 per (n,c); dgamma, dbeta, dbias (conv bias grad); a bound on |dy| -> dy_scale[0]
  *   apply:    dy = rstd * (gamma*dr - m1 - xhat*m2), written as the QH operand 2^k * dy (k from the bound so
@@ -203,15 +206,34 @@ typedef struct e3b_norm_bwd_args {
                                                   unet.py:303-324; the backward of the slice is a zero pad): it has extents
                                                   (g1_D,g1_H,g1_W) and is added inside the box starting at (g1_od,g1_oh,g1_ow) */
     int32_t g1_od, g1_oh, g1_ow, g1_D, g1_H, g1_W;
+    float act_slope;                           /* negative slope of activation code relu == 1 (0 = ReLU) */
 } e3b_norm_bwd_args;
 /* The three passes as ONE persistent kernel (reduce, grid barrier, finalize, apply), one sample at a time for per-sample
  * statistics (group / instance / none): the apply pass re-reads the sample out of L2, so y and the incoming gradient cross
  * HBM once.  Needs sums, amax and dy_scale as one contiguous workspace (in this order), at most 512 channels and, for
- * s2d, extents divisible by the stride; otherwise use the three calls below. */
+ * s2d, extents divisible by the stride, and an activation of the (leaky-)ReLU family or none; otherwise use the three
+ * calls below. */
 int e3b_norm_bwd_fused(const e3b_norm_bwd_args* args, void* stream);
 int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* args, void* stream);
 int e3b_norm_bwd_finalize(const e3b_norm_bwd_args* args, void* stream);
 int e3b_norm_bwd_apply(const e3b_norm_bwd_args* args, void* stream);
+
+/* ---- options off the default UNet configuration ---------------------------------------------------
+ * merge_mode='add' (unet.py:399-401): dst = a + b[centre crop at (off_d, off_h, off_w)], QH operand tensors;
+ * a, dst (N, C, D, H, W), b (N, C, D1, H1, W1) -- the skip tensor after autocrop (unet.py:303-324). */
+int e3b_add_qh(const void* a, const void* b, void* dst, int N, int C, int D, int H, int W, int D1, int H1, int W1,
+               int off_d, int off_h, int off_w, void* stream);
+/* up_mode='resizeconv_*' (ResizeConv, unet.py:411-449): nn.Upsample(scale_factor = (sd, sh, sw) in {1, 2}, mode 'nearest'
+ * (linear = 0) or 'trilinear' / 'bilinear' with align_corners=False (linear = 1)) of a QH tensor (N, C, d, h, w), written
+ * into a QH tensor of extents (Dp, Hp, Wp) in which fine voxel f sits at f + off per axis, only fine voxels [0, R) per axis
+ * are stored and everything else is zero: the caller makes the zero padding of the conv that follows explicit (off = 1 on
+ * 3-tap axes) and folds autocrop's crop of that conv's OUTPUT (unet.py:294-301) into R, so that the conv itself is a
+ * plain VALID one.  e3b_upsample_bwd_qp is the transpose: the fp32 QP gradient of that padded tensor (the dgrad output)
+ * gathered onto the coarse grid. */
+int e3b_upsample_qh(const void* src, void* dst, int N, int C, int d, int h, int w, int Dp, int Hp, int Wp, int sd, int sh, int sw,
+                    int off_d, int off_h, int off_w, int Rd, int Rh, int Rw, int linear, void* stream);
+int e3b_upsample_bwd_qp(const float* gfine, float* gcoarse, int N, int C, int d, int h, int w, int Dp, int Hp, int Wp, int sd, int sh,
+                        int sw, int off_d, int off_h, int off_w, int Rd, int Rh, int Rw, int linear, void* stream);
 
 /* ---- 1x1x1 head --------------------------------------------------------------------------------
  * conv_final (unet.py:881,912) fused with Predictor's Softmax(1) / Argmax (inference.py:443-456,202-212).

@@ -41,6 +41,40 @@ CASES = {
                        x=(1, 1, 20, 20, 20), train=False),
 }
 
+# Options off the default configuration: goldens from the real reference pin the plain-torch
+# restatement (oracle/torch_ref.py) and the CUDA path; the C/numpy oracle covers the default configuration only.
+OPTION_CASES = {
+    'opt_leaky_train': dict(model=dict(n_blocks=3, start_filts=8, normalization='group', activation='leaky'),
+                            x=(2, 1, 16, 16, 16), train=True),
+    'opt_silu_train': dict(model=dict(n_blocks=2, start_filts=8, activation='silu'),
+                           x=(2, 1, 16, 16, 16), train=True),
+    'opt_lin_none_train': dict(model=dict(n_blocks=2, start_filts=8, normalization='none', activation='lin'),
+                               x=(1, 1, 8, 16, 16), train=True),
+    'opt_silu_eval': dict(model=dict(n_blocks=2, start_filts=8, activation='silu'),
+                          x=(1, 1, 16, 16, 16), train=False),
+    'opt_rrelu_eval': dict(model=dict(n_blocks=2, start_filts=8, normalization='group', activation='rrelu'),
+                           x=(1, 1, 16, 16, 16), train=False),
+    'opt_add_train': dict(model=dict(n_blocks=3, start_filts=8, normalization='group', merge_mode='add'),
+                          x=(2, 1, 16, 16, 16), train=True),
+    'opt_add_valid_train': dict(model=dict(n_blocks=2, start_filts=8, normalization='group', merge_mode='add',
+                                           conv_mode='valid'),
+                                x=(1, 1, 20, 20, 20), train=True),
+    'opt_resize_nearest_train': dict(model=dict(n_blocks=3, start_filts=8, normalization='group',
+                                                up_mode='resizeconv_nearest'),
+                                     x=(2, 1, 16, 16, 16), train=True),
+    'opt_resize_linear_train': dict(model=dict(n_blocks=2, start_filts=8, up_mode='resizeconv_linear'),
+                                    x=(2, 1, 8, 16, 16), train=True),
+    'opt_resize_nearest1_planar_train': dict(model=dict(n_blocks=3, start_filts=8, normalization='group',
+                                                        up_mode='resizeconv_nearest1', planar_blocks=(0,)),
+                                             x=(1, 1, 8, 16, 16), train=True),
+    'opt_resize_linear1_2d_train': dict(model=dict(dim=2, n_blocks=2, start_filts=8, up_mode='resizeconv_linear1'),
+                                        x=(2, 1, 16, 16), train=True),
+    # odd extents: ceil-mode pooling makes the up-sampled tensor one voxel too large -> autocrop of the resize-conv output
+    'opt_resize_linear_odd_train': dict(model=dict(n_blocks=3, start_filts=8, normalization='group',
+                                                   up_mode='resizeconv_linear'),
+                                        x=(1, 1, 11, 13, 18), train=True),
+}
+
 # Predictor / tiled_apply cases: model, volume shape, tile, overlap
 PRED_CASES = {
     'pred_small': dict(model=dict(n_blocks=2, start_filts=8), vol=(1, 1, 16, 24, 16),

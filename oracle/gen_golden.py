@@ -62,7 +62,10 @@ def main():
     torch.backends.mkldnn.enabled = True
     unet, loss_mod, inference = load_reference()
     os.makedirs(OUT, exist_ok=True)
-    for name, case in fx.CASES.items():
+    only = set(sys.argv[1:])           # optional: names of the cases to (re)generate
+    for name, case in list(fx.CASES.items()) + list(fx.OPTION_CASES.items()):
+        if only and name not in only:
+            continue
         model, shapes, sd = build_model(unet, case['model'])
         x = fx.make_input(case['x'])
         out = dict(keys=json.dumps(shapes), x_shape=np.array(case['x']))
@@ -70,9 +73,10 @@ def main():
         if case['train']:
             model.train()
             ncls = case['model'].get('out_channels', 2)
-            tgt = fx.make_target(case['x'], ncls)
             logits = model(xt)
             logits.retain_grad()
+            # (VALID nets: the target has the output's extents; SAME nets: those of the input, as before)
+            tgt = fx.make_target((case['x'][0], 1) + tuple(logits.shape[2:]), ncls)
             crit = loss_mod.DiceLoss(apply_softmax=True)
             loss = crit(logits, torch.from_numpy(tgt))
             loss.backward()
@@ -93,6 +97,8 @@ def main():
         print(name, out['logits'].shape, 'ok')
 
     for name, case in fx.PRED_CASES.items():
+        if only and name not in only:
+            continue
         model, shapes, sd = build_model(unet, case['model'])
         vol = fx.make_input(case['vol'], kind='neuro')
         out = dict(keys=json.dumps(shapes))

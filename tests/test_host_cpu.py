@@ -95,6 +95,34 @@ def test_constructor_validation_matches_reference_messages():
         e3.UNet(batch_norm=True)
     with pytest.raises(NotImplementedError):
         e3.UNet(attention=True)
+    with pytest.raises(ValueError):
+        e3.UNet(up_mode='resizeconv_nearest', merge_mode='add')        # models/unet.py:791-800
+    with pytest.raises(NotImplementedError):
+        e3.UNet(activation='prelu')
+    with pytest.raises(NotImplementedError):
+        e3.UNet(activation=torch.nn.Tanh())
+
+
+def test_option_modules_follow_the_reference_layout():
+    """up_mode / merge_mode / activation variants: state_dict keys, shapes and activation modules as
+    upconv2 / ResizeConv / get_activation build them (models/unet.py:152-199,411-449)"""
+    import elektronn3_b200 as e3
+    m = e3.UNet(n_blocks=2, start_filts=8, up_mode='resizeconv_linear', activation='leaky')
+    sd = m.state_dict()
+    assert tuple(sd['up_convs.0.upconv.conv.weight'].shape) == (8, 16, 3, 3, 3)
+    assert 'up_convs.0.upconv.weight' not in sd
+    assert isinstance(m.up_convs[0].act0, torch.nn.LeakyReLU) and m.up_convs[0].act0.negative_slope == 0.1
+    assert m.up_convs[0].act0 is not m.up_convs[0].act1
+    m1 = e3.UNet(n_blocks=2, start_filts=8, up_mode='resizeconv_nearest1', planar_blocks=(0,))
+    assert tuple(m1.state_dict()['up_convs.0.upconv.conv.weight'].shape) == (8, 16, 1, 1, 1)
+    assert m1.up_convs[0].upconv.scale_factor == (1, 2, 2)
+    ma = e3.UNet(n_blocks=2, start_filts=8, merge_mode='add', activation=torch.nn.SiLU())
+    assert tuple(ma.state_dict()['up_convs.0.conv1.weight'].shape) == (8, 8, 3, 3, 3)
+    assert isinstance(ma.down_convs[0].act1, torch.nn.SiLU)
+    from elektronn3_b200 import engine
+    assert engine.act_code(torch.nn.RReLU(), False) == (1, (1 / 8 + 1 / 3) / 2)
+    with pytest.raises(NotImplementedError):
+        engine.act_code(torch.nn.RReLU(), True)
 
 
 def test_state_dict_keys_follow_the_reference_naming():
@@ -247,7 +275,10 @@ def test_graphed_train_step_needs_cuda():
 @pytest.mark.parametrize('kw,shape', [(dict(n_blocks=2, start_filts=8), (1, 1, 16, 16, 16)),
                                       (dict(n_blocks=3, start_filts=4, normalization='group4', planar_blocks=(0,)), (2, 1, 5, 13, 18)),
                                       (dict(dim=2, n_blocks=3, start_filts=4), (1, 1, 24, 20)),
-                                      (dict(n_blocks=2, start_filts=4, conv_mode='valid', normalization='none'), (1, 1, 20, 20, 20))])
+                                      (dict(n_blocks=2, start_filts=4, conv_mode='valid', normalization='none'), (1, 1, 20, 20, 20)),
+                                      (dict(n_blocks=3, start_filts=4, normalization='group4', up_mode='resizeconv_linear',
+                                            activation='leaky'), (1, 1, 9, 12, 14)),
+                                      (dict(n_blocks=2, start_filts=4, merge_mode='add', activation='silu'), (1, 1, 8, 16, 16))])
 def test_torch_twin_and_torchscript_export(kw, shape, tmp_path):
     """Trainer._save_model scripts / traces the model when save_jit is set (training/trainer.py:876-887): the module hands
     out a plain-torch twin with the SAME parameters and state_dict keys that computes the reference forward."""

@@ -610,3 +610,110 @@ def test_errors_surface_as_exceptions(eng):
     w = dyadic((8, 8, 5, 5, 5), 62)
     with pytest.raises(RuntimeError):
         eng.conv_forward(qp(eng, x), w.flatten(), 16, 8, (5, 5, 5), (2, 2, 2))
+
+
+# ---------------------------------------------------------------------------------------- options
+_ACTS = {'leaky': ((1, 0.1), lambda t: F.leaky_relu(t, 0.1)), 'lin': ((0, 0.0), lambda t: t),
+         'rrelu_eval': ((1, (1 / 8 + 1 / 3) / 2), lambda t: F.rrelu(t, training=False)), 'silu': ((2, 0.0), F.silu)}
+
+
+@pytest.mark.parametrize('act', list(_ACTS))
+@pytest.mark.parametrize('mode,pool,path', [(1, None, 'fused'), (1, (2, 2, 2), 'fused'), (1, (2, 2, 2), 'split'),
+                                            (2, None, 'fused'), (0, (1, 2, 2), 'split')])
+def test_activations_forward_backward(eng, monkeypatch, act, mode, pool, path):
+    """get_activation's other choices (models/unet.py:183-199) through norm_act and both norm-backward paths (SiLU always
+    takes the three-kernel one) against float64 autograd"""
+    monkeypatch.setenv('E3B_NORM_BWD', 'split' if path == 'split' else 'fused')
+    code, fn = _ACTS[act]
+    N, C, G, sp = 2, 16, 4, (4, 6, 8)
+    rs = np.random.RandomState(5)
+    y = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
+    gamma = torch.from_numpy((1 + 0.2 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    beta = torch.from_numpy((0.1 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    rm, rv = torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
+    yd = y.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    a_ref = fn(_norm_ref(yd, mode, G, gd if mode else None, bd if mode else None, rm.double(), rv.double()))
+    p_ref = F.max_pool3d(a_ref, pool, pool, ceil_mode=True) if pool is not None else None
+    yq = qp32(eng, y)
+    S = sp[0] * sp[1] * sp[2]
+    stats = torch.stack((y.double().sum(dim=(2, 3, 4)), (y.double() ** 2).sum(dim=(2, 3, 4))), dim=-1).contiguous()
+    nstate = None
+    if mode:
+        nstate = eng.norm_finalize(stats, mode, G, N, C, S, gamma, beta, 1e-5, rm if mode == 2 else None,
+                                   rv if mode == 2 else None, 0.1, y.device)
+    a, pooled = eng.norm_act(yq, nstate.scale if mode else None, nstate.shift if mode else None, pool=pool, save=True, act=code)
+    assert_close(from_qh_ref(a, C), a_ref, 6e-4, 'norm+act')
+    g0 = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
+    loss = (a_ref * g0.double()).sum()
+    gpq = None
+    if pool is not None:
+        assert_close(from_qh_ref(pooled, C), p_ref, 6e-4, 'pool')
+        gp = torch.from_numpy(rs.standard_normal(tuple(p_ref.shape)).astype(np.float32)).cuda()
+        loss = loss + (p_ref * gp.double()).sum()
+        gpq = qp32(eng, gp)
+    loss.backward()
+
+    class Spec:
+        pass
+    u = eng.Unit()
+    u.spec = Spec()
+    u.spec.norm = torch.nn.GroupNorm(1, 1) if mode else None
+    if mode:
+        u.spec.norm.weight = torch.nn.Parameter(gamma)
+        u.spec.norm.eps = 1e-5
+    u.a, u.y, u.pool, u.mode, u.G, u.nstate, u.stats, u.pooled = a, yq, pool, mode, G, nstate, (stats if mode else None), pooled
+    u.act = code
+    dy, dgamma, dbeta, dbias = eng._norm_bwd(u, C, qp32(eng, g0), gp=gpq)
+    assert_close(from_qh_ref(dy, C), yd.grad, 1e-3, 'norm bwd dy (%s)' % act)
+    if mode:
+        assert_close(dgamma, gd.grad, 3e-4, 'dgamma')
+        assert_close(dbeta, bd.grad, 3e-4, 'dbeta')
+
+
+@pytest.mark.parametrize('C,sp,sp1,off', [(16, (4, 6, 8), (4, 6, 8), (0, 0, 0)), (8, (3, 5, 7), (7, 9, 9), (2, 2, 1)),
+                                          (24, (1, 6, 10), (1, 8, 12), (0, 1, 1))])
+def test_add_qh_with_centre_crop(eng, C, sp, sp1, off):
+    """merge_mode='add' (models/unet.py:399-401) after autocrop's centre crop of the skip tensor (:303-324)"""
+    a = dyadic((2, C) + sp, 1)
+    b = dyadic((2, C) + sp1, 2)
+    out = eng.add_qh(qp(eng, a), qp(eng, b), off)
+    ref = a + b[:, :, off[0]:off[0] + sp[0], off[1]:off[1] + sp[1], off[2]:off[2] + sp[2]]
+    assert_close(from_qh_ref(out, C), ref, 1e-6, 'add')
+    if eng.cpad16(C) != C:
+        assert from_qh_ref(out, eng.cpad16(C))[:, C:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize('mode', ['nearest', 'trilinear'])
+@pytest.mark.parametrize('C,sp,s,cp,crop', [(16, (3, 4, 5), (2, 2, 2), (1, 1, 1), (0, 0, 0)),
+                                            (8, (3, 4, 5), (2, 2, 2), (1, 1, 1), (1, 0, 1)),
+                                            (24, (4, 3, 6), (1, 2, 2), (0, 1, 1), (0, 1, 0)),
+                                            (8, (2, 5, 4), (2, 2, 2), (0, 0, 0), (1, 1, 0))])
+def test_upsample_into_padded_tensor_and_its_transpose(eng, mode, C, sp, s, cp, crop):
+    """nn.Upsample of ResizeConv (models/unet.py:411-449) written with the conv's zero padding explicit and autocrop's
+    trailing crop folded in; the backward kernel is checked against autograd of F.interpolate + F.pad."""
+    import ctypes  # noqa: F401
+    from elektronn3_b200 import _lib as L
+    N = 2
+    x = dyadic((N, C) + sp, 3)
+    full = tuple(a * b for a, b in zip(sp, s))
+    out_sp = tuple(f - c for f, c in zip(full, crop))                  # extents of the (auto)cropped conv output
+    k = tuple(2 * p + 1 for p in cp)
+    ext = tuple(o + kk - 1 for o, kk in zip(out_sp, k))
+    R = tuple(min(f, e - p) for f, e, p in zip(full, ext, cp))
+    xd = x.double().requires_grad_(True)
+    up = F.interpolate(xd, scale_factor=tuple(float(v) for v in s), mode=mode) if mode == 'nearest' else \
+        F.interpolate(xd, scale_factor=tuple(float(v) for v in s), mode=mode, align_corners=False)
+    up = up[:, :, :R[0], :R[1], :R[2]]
+    ref = F.pad(up, (cp[2], ext[2] - cp[2] - R[2], cp[1], ext[1] - cp[1] - R[1], cp[0], ext[0] - cp[0] - R[0]))
+    src = qp(eng, x)
+    dst = eng.QP.empty_half(N, C, ext[0], ext[1], ext[2], x.device)
+    geom = tuple(sp) + ext + tuple(s) + tuple(cp) + R + (0 if mode == 'nearest' else 1,)
+    L.check(L.lib().e3b_upsample_qh(src.ptr, dst.ptr, N, C, *geom, eng._stream()), 'upsample_qh')
+    assert_close(from_qh_ref(dst, C), ref, 1e-3 if mode != 'nearest' else 1e-6, 'upsample')
+    g = dyadic((N, C) + ext, 4)
+    (ref * g.double()).sum().backward()
+    u = eng.Unit()
+    u.resize = geom
+    got = eng._resize_bwd(u, qp32(eng, g))
+    assert_close(from_qp_ref(got.t, C), xd.grad, 1e-6, 'upsample backward')

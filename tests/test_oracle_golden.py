@@ -98,11 +98,11 @@ def _torch_model(case, sd, train):
     return m.train(train)
 
 
-@pytest.mark.parametrize('name', list(fx.CASES))
+@pytest.mark.parametrize('name', list(fx.CASES) + list(fx.OPTION_CASES))
 def test_torch_restatement_matches_reference(name):
     import torch
     from oracle import torch_ref
-    case = fx.CASES[name]
+    case = {**fx.CASES, **fx.OPTION_CASES}[name]
     g, sd = load_golden(name)
     m = _torch_model(case, sd, case['train'])
     x = torch.from_numpy(fx.make_input(case['x']))
