@@ -135,6 +135,8 @@ SIGNATURES = {
     'e3b_add_qh': (c_int, [c_void_p] * 3 + [c_int] * 11 + [c_void_p]),
     'e3b_upsample_qh': (c_int, [c_void_p] * 2 + [c_int] * 18 + [c_void_p]),
     'e3b_upsample_bwd_qp': (c_int, [c_void_p] * 2 + [c_int] * 18 + [c_void_p]),
+    'e3b_residual_add': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_i64, c_void_p]),
+    'e3b_qp_axpy': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_i64, c_void_p]),
     'e3b_head': (c_int, [ctypes.POINTER(HeadArgs), c_void_p]),
     'e3b_prob_argmax': (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_float, c_void_p]),
     'e3b_head_bwd': (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),

@@ -5,6 +5,9 @@
 //     the conv's zero padding made explicit (and autocrop's trailing-voxel crop of the conv OUTPUT folded in), so that the
 //     convolution that follows is a plain VALID one on the existing tensor-core kernels; the backward gathers the
 //     gradient of that padded tensor back onto the coarse grid (the transpose of the interpolation).
+//   * the residual shortcut of resunet's ConvBlock (models/resunet.py:252-261, `y += proj(inp)` between conv2 and norm2):
+//     y += r with the statistics of the SUM for the norm that follows (e3b_residual_add), and the accumulation of the
+//     shortcut's gradient into the gradient of the block input (e3b_qp_axpy).
 // All of them are HBM bound: one thread per 16-byte unit, coalesced along x.
 #include "common.cuh"
 #include "kernels.h"
@@ -153,6 +156,66 @@ static int fill_up(UpDev& p, int planes, int d, int h, int w, int Dp, int Hp, in
     return 0;
 }
 
+// y (QP fp32, in place) += r, r a QP fp32 tensor or a QH fp16 operand tensor of the same extents (N, C, S voxels);
+// stats (optional): per (n, c) sum and sum of squares of the result (fp64 atomics; zeroed by the caller).
+// grid: (voxel chunks, Cq, N)
+__global__ void __launch_bounds__(256) residual_add_kernel(float4* __restrict__ y, const float4* __restrict__ r32,
+                                                           const uint2* __restrict__ r16, double* __restrict__ stats, int C, int Cq,
+                                                           int Ch, int S)
+{
+    const int cq = blockIdx.y, n = blockIdx.z;
+    float4* yb = y + ((size_t)n * Cq + cq) * (size_t)S;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < S; v += gridDim.x * blockDim.x) {
+        float4 a = yb[v];
+        float4 b;
+        if (r32) b = __ldg(r32 + ((size_t)n * Cq + cq) * (size_t)S + v);
+        else b = unpack_half4(__ldg(r16 + (((size_t)n * Ch + (cq >> 1)) * (size_t)S + v) * 2 + (cq & 1)));
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        yb[v] = a;
+        s1[0] += a.x; s1[1] += a.y; s1[2] += a.z; s1[3] += a.w;
+        s2[0] = fmaf(a.x, a.x, s2[0]); s2[1] = fmaf(a.y, a.y, s2[1]); s2[2] = fmaf(a.z, a.z, s2[2]); s2[3] = fmaf(a.w, a.w, s2[3]);
+    }
+    if (!stats) return;
+    __shared__ float red[8][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { red[warp][j] = s1[j]; red[warp][4 + j] = s2[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += (double)red[w][threadIdx.x];
+        const int c = cq * 4 + (threadIdx.x & 3);
+        if (c < C) atomicAdd(stats + ((size_t)n * C + c) * 2 + (threadIdx.x >> 2), t);
+    }
+}
+
+// dst (QP fp32, in place) += alpha * src; src QP fp32 or QH fp16; alpha a device scalar (nullptr: 1)
+__global__ void __launch_bounds__(256) qp_axpy_kernel(float4* __restrict__ dst, const float4* __restrict__ s32, const uint2* __restrict__ s16,
+                                                      const float* __restrict__ alpha, int Cq, int Ch, int S)
+{
+    const int cq = blockIdx.y, n = blockIdx.z;
+    const float al = alpha ? __ldg(alpha) : 1.f;
+    float4* db = dst + ((size_t)n * Cq + cq) * (size_t)S;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < S; v += gridDim.x * blockDim.x) {
+        float4 a = db[v];
+        float4 b;
+        if (s32) b = __ldg(s32 + ((size_t)n * Cq + cq) * (size_t)S + v);
+        else b = unpack_half4(__ldg(s16 + (((size_t)n * Ch + (cq >> 1)) * (size_t)S + v) * 2 + (cq & 1)));
+        a.x = fmaf(al, b.x, a.x); a.y = fmaf(al, b.y, a.y); a.z = fmaf(al, b.z, a.z); a.w = fmaf(al, b.w, a.w);
+        db[v] = a;
+    }
+}
+
 static unsigned chunks_for(size_t S) { size_t c = (S + 255) / 256; return (unsigned)(c > 4096 ? 4096 : c); }
 
 }  // namespace e3b
@@ -202,6 +265,39 @@ int e3b_upsample_bwd_qp(const float* gfine, float* gcoarse, int N, int C, int d,
     qp_upsample_bwd_kernel<<<dim3(chunks_for((size_t)d * h * w), Cq, N), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(gfine), reinterpret_cast<float4*>(gcoarse), p);
     return check_launch("upsample_bwd_qp");
+}
+
+int e3b_residual_add(float* y_qp, const void* r, int r_is_half, double* stats, int N, int C, int64_t S, void* stream)
+{
+    if (!y_qp || !r) return set_error("residual_add: null tensor pointer");
+    if (N <= 0 || C <= 0 || S <= 0 || S >= (1ll << 31)) return set_error("residual_add: bad extents");
+    const int Cq = cpad8(C) / 4, Ch = cpad16(C) / 8;
+    if (Cq > 65535 || N > 65535) return set_error("residual_add: too many channels / samples for the launch grid");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stats) {
+        cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)N * C, st);
+        if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
+    }
+    // (few chunks per slab: every block ends in 8 fp64 atomics per statistic)
+    size_t chunks = ((size_t)S + 256 * 8 - 1) / (256 * 8);
+    const size_t cap = (size_t)(16 * num_sms()) / ((size_t)Cq * N) + 1;
+    if (chunks > cap) chunks = cap;
+    residual_add_kernel<<<dim3((unsigned)chunks, Cq, N), 256, 0, st>>>(
+        reinterpret_cast<float4*>(y_qp), r_is_half ? nullptr : reinterpret_cast<const float4*>(r),
+        r_is_half ? reinterpret_cast<const uint2*>(r) : nullptr, stats, C, Cq, Ch, (int)S);
+    return check_launch("residual_add");
+}
+
+int e3b_qp_axpy(float* dst_qp, const void* src, int src_is_half, const float* alpha, int N, int C, int64_t S, void* stream)
+{
+    if (!dst_qp || !src) return set_error("qp_axpy: null tensor pointer");
+    if (N <= 0 || C <= 0 || S <= 0 || S >= (1ll << 31)) return set_error("qp_axpy: bad extents");
+    const int Cq = cpad8(C) / 4, Ch = cpad16(C) / 8;
+    if (Cq > 65535 || N > 65535) return set_error("qp_axpy: too many channels / samples for the launch grid");
+    qp_axpy_kernel<<<dim3(chunks_for((size_t)S), Cq, N), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(dst_qp), src_is_half ? nullptr : reinterpret_cast<const float4*>(src),
+        src_is_half ? reinterpret_cast<const uint2*>(src) : nullptr, alpha, Cq, Ch, (int)S);
+    return check_launch("qp_axpy");
 }
 
 }  // extern "C"

@@ -51,9 +51,10 @@ class QP:
         return QP(torch.empty((N, cpad8(C) // 4, D, H, W, 4), dtype=torch.float32, device=device), N, C, D, H, W)
 
     @staticmethod
-    def empty_half(N, C, D, H, W, device):
-        """QH operand tensor; padding planes that no kernel writes (C % 16 in 1..8) must read as zero"""
-        alloc = torch.zeros if cpad16(C) != cpad8(C) else torch.empty
+    def empty_half(N, C, D, H, W, device, all_planes_written=False):
+        """QH operand tensor; padding planes that no kernel writes (C % 16 in 1..8) must read as zero.
+        all_planes_written: the producing kernel writes every 16-byte plane itself (pack / gather / add / upsample)."""
+        alloc = torch.zeros if (cpad16(C) != cpad8(C) and not all_planes_written) else torch.empty
         return QP(alloc((N, cpad16(C) // 8, D, H, W, 8), dtype=torch.float16, device=device), N, C, D, H, W)
 
     @property
@@ -78,7 +79,7 @@ def pack_input(x5):
     _require_cuda(x5, 'input')
     x5 = x5.contiguous()
     N, C, D, H, W = x5.shape
-    q = QP.empty_half(N, C, D, H, W, x5.device)
+    q = QP.empty_half(N, C, D, H, W, x5.device, all_planes_written=True)
     L.check(L.lib().e3b_pack_ncdhw(x5.data_ptr(), q.ptr, N, C, D, H, W, D, H, W, 0, 0, 0, _stream()), 'pack_ncdhw')
     return q
 
@@ -95,7 +96,7 @@ def gather_tiles(vol, origins, B, C, tile, flip=0):
     """Predictor tile gather (inference.py:179-189): vol (C, Dv, Hv, Wv) device tensor, origins int32 (B,3).
     flip: bit mask (D, H, W) of the test-time-augmentation mirror applied while gathering (inference.py:215-223)."""
     D, H, W = tile
-    q = QP.empty_half(B, C, D, H, W, vol.device)
+    q = QP.empty_half(B, C, D, H, W, vol.device, all_planes_written=True)
     L.check(L.lib().e3b_gather_tiles(vol.data_ptr(), origins.data_ptr(), q.ptr, B, C, D, H, W,
                                      vol.shape[-3], vol.shape[-2], vol.shape[-1], flip, _stream()), 'gather_tiles')
     return q
@@ -348,6 +349,7 @@ class ConvSpec:
 
     def __init__(self, name, conv, norm, C0, C1, act=None, explicit_pad=False):
         self.name, self.conv, self.norm, self.act = name, conv, norm, act
+        self.residual = False      # a shortcut is added between this conv and its norm (resunet ConvBlock.conv2)
         w = conv.weight
         self.Co = w.shape[0]
         self.C0, self.C1 = C0, C1
@@ -430,7 +432,7 @@ def norm_mode(norm, training):
 class Unit:
     """Everything one conv -> norm -> relu [-> pool] stage leaves behind for the backward pass."""
     __slots__ = ('spec', 'src0', 'src1', 'off1', 'y', 'a', 'pooled', 'pool', 'mode', 'G', 'nstate', 'stats', 'dec', 'act',
-                 'resize')
+                 'resize', 'res', 'res_grads')
 
 
 class WeightSet:
@@ -487,8 +489,18 @@ class TrainImages:
                 'pack_weights_batched')
 
 
+class Block:
+    """conv1 -> norm -> act -> conv2 [+ shortcut(block input)] -> norm -> act: DownConv / UpConv of models/unet.py (no shortcut)
+    and ConvBlock of models/resunet.py:212-261.  res: None, 'identity' or the ConvSpec of the 1x1x1 projection."""
+
+    def __init__(self, c1, c2, res=None):
+        self.c1, self.c2, self.res = c1, c2, res
+        c2.residual = res is not None
+
+
 class Net:
-    """Flat description of a UNet instance (built by elektronn3_b200.unet.UNet)."""
+    """Flat description of a UNet instance (built by elektronn3_b200.unet.UNet / resunet.UNet): down = [(blocks, pool kernel)],
+    up = [(UpSpec | ResizeSpec, blocks)]."""
 
     def __init__(self, down, up, final_conv, dim, cache, merge_add=False):
         self.down, self.up, self.final, self.dim, self.cache = down, up, final_conv, dim, cache
@@ -497,13 +509,17 @@ class Net:
         self.train_images = None
 
     def specs(self):
-        for c1, c2, _ in self.down:
-            yield c1
-            yield c2
-        for ups, c1, c2 in self.up:
+        def of_blocks(blocks):
+            for b in blocks:
+                yield b.c1
+                yield b.c2
+                if isinstance(b.res, ConvSpec):
+                    yield b.res
+        for blocks, _ in self.down:
+            yield from of_blocks(blocks)
+        for ups, blocks in self.up:
             yield ups
-            yield c1
-            yield c2
+            yield from of_blocks(blocks)
 
 
 def prepare_weights(net, training):
@@ -533,7 +549,7 @@ def prepare_weights(net, training):
             is_conv = isinstance(sp, ConvSpec)
             mod = sp.conv if is_conv else sp.up
             weights.append(mod.weight)
-            if norm_mode(sp.norm, training)[0] == MODE_BATCH_EVAL:
+            if norm_mode(sp.norm, training)[0] == MODE_BATCH_EVAL and not getattr(sp, 'residual', False):
                 f, b = _bn_fold(mod, sp.norm)
                 ws.folds[sp.name] = (f, b)
                 cscales.append((f, 0 if is_conv else 1))
@@ -567,7 +583,7 @@ def _conv_weights(net, spec, mode, training):
     wsc = net.wset.scales[spec.name]
     if net.wset.images is not None:
         return net.wset.images[(spec.name, 'fwd')], (conv.bias.detach() if conv.bias is not None else None), wsc
-    if nm == MODE_BATCH_EVAL:
+    if nm == MODE_BATCH_EVAL and not spec.residual:
         n = spec.norm
         params = (conv.weight, conv.bias, n.weight, n.bias, n.running_mean, n.running_var)
         s, b = net.wset.folds[spec.name]
@@ -579,16 +595,56 @@ def _conv_weights(net, spec, mode, training):
     return wpk, (conv.bias.detach() if conv.bias is not None else None), wsc
 
 
-def _run_unit(net, spec, src0, src1, off1, pool, training, save):
-    """conv -> norm -> act [-> pool]  (DownConv.forward models/unet.py:244-253, UpConv :402-407)"""
+def _shortcut(net, res, training):
+    """the shortcut branch of a resunet ConvBlock (models/resunet.py:246-250,257-258): -> (tensor, is_half).  Identity: the
+    block input itself (a QH activation); otherwise the 1x1x1 projection of the (virtually concatenated) block input, fp32 QP."""
+    kind, r0, r1, roff = res
+    if not isinstance(kind, ConvSpec):
+        return r0, 1
+    wp, bp, wscp = _conv_weights(net, kind, 0, training)
+    r, _, _ = conv_forward(r0, wp, kind.n_total, kind.Co, kind.k, kind.pad, src1=r1, off1=roff, bias=bp,
+                           variant=kind.variants[0], w_unscale=wscp)
+    return r, 0
+
+
+def _run_unit(net, spec, src0, src1, off1, pool, training, save, res=None):
+    """conv -> [+ shortcut] -> norm -> act [-> pool]  (DownConv.forward models/unet.py:244-253, UpConv :402-407; with
+    res = (kind, block input ...): ConvBlock.forward of models/resunet.py:252-261)"""
     mode, G = norm_mode(spec.norm, training)
     act = act_code(spec.act, training)
     wpk, bias, wsc = _conv_weights(net, spec, 0, training)
     u = Unit()
     u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G, u.act = spec, src0, src1, off1, pool, mode, G, act
-    u.pooled = u.nstate = u.stats = u.dec = u.resize = None
+    u.pooled = u.nstate = u.stats = u.dec = u.resize = u.res = u.res_grads = None
     var = spec.variants[0]
-    if (mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save)) and act == ACT_RELU:
+    if res is not None:
+        # y = conv2(..) + b; y += shortcut; the statistics of the SUM feed the norm (never folded into the weights)
+        y, _, _ = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
+                               variant=var, w_unscale=wsc)
+        r, r_half = _shortcut(net, res, training)
+        if (r.N, r.C) + r.spatial != (y.N, y.C) + y.spatial:
+            raise RuntimeError(f'residual shortcut of shape {(r.N, r.C) + r.spatial} cannot be added to the conv output '
+                               f'{(y.N, y.C) + y.spatial} (models/resunet.py:257-258; VALID convolutions shrink it)')
+        stats = None
+        if mode in (MODE_GROUP, MODE_BATCH):
+            stats = torch.empty((y.N, spec.Co, 2), dtype=torch.float64, device=y.t.device)
+        L.check(L.lib().e3b_residual_add(y.ptr, r.ptr, r_half, _p(stats), y.N, spec.Co, y.D * y.H * y.W, _stream()),
+                'residual_add')
+        u.y, u.stats, u.res = y, stats, res
+        if mode == MODE_NONE:
+            u.a, u.pooled = norm_act(y, None, None, pool=pool, save=save, act=act)
+        else:
+            n = spec.norm
+            rm = rv = None
+            mom = 0.0
+            if mode == MODE_BATCH:
+                rm, rv, mom = _bn_running(n, training)
+            elif mode == MODE_BATCH_EVAL:
+                rm, rv = n.running_mean, n.running_var
+            u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, y.D * y.H * y.W, _affine(n, 'weight'), _affine(n, 'bias'),
+                                     n.eps, rm, rv, mom, y.t.device)
+            u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, save=save, act=act)
+    elif (mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save)) and act == ACT_RELU:
         # inference: the conv epilogue (folded BN, bias, ReLU) writes the next layer's operand directly
         a, _, _ = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
                                relu=True, half_out=True, variant=var, w_unscale=wsc)
@@ -616,8 +672,20 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save):
         u.y, u.stats = y, stats
         u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, save=save, act=act)
     if not save:
-        u.y = u.src0 = u.src1 = None
+        u.y = u.src0 = u.src1 = u.res = None
     return u
+
+
+def _run_blocks(net, blocks, src0, src1, off1, pool, training, save):
+    """a stack of Blocks; the last one is followed by the pooling.  -> [(unit of conv1, unit of conv2)]"""
+    units = []
+    for bi, blk in enumerate(blocks):
+        u1 = _run_unit(net, blk.c1, src0, src1, off1, None, training, save)
+        res = (blk.res, src0, src1, off1) if blk.res is not None else None
+        u2 = _run_unit(net, blk.c2, u1.a, None, (0, 0, 0), pool if bi == len(blocks) - 1 else None, training, save, res=res)
+        units.append((u1, u2))
+        src0, src1, off1 = u2.a, None, (0, 0, 0)
+    return units
 
 
 def _affine(n, name):
@@ -656,7 +724,7 @@ def _run_resize(net, spec, dec, enc, training, save):
     out_sp, off1 = _autocrop(full, enc.spatial)
     ext = tuple(o + kk - 1 for o, kk in zip(out_sp, k))
     R = tuple(min(f, e - p) for f, e, p in zip(full, ext, cp))
-    up = QP.empty_half(dec.N, dec.C, ext[0], ext[1], ext[2], dec.t.device)
+    up = QP.empty_half(dec.N, dec.C, ext[0], ext[1], ext[2], dec.t.device, all_planes_written=True)
     geom = (dec.D, dec.H, dec.W) + ext + tuple(s) + tuple(cp) + R + (spec.linear,)
     L.check(L.lib().e3b_upsample_qh(dec.ptr, up.ptr, dec.N, dec.C, *geom, _stream()), 'upsample_qh')
     u = _run_unit(net, spec, up, None, (0, 0, 0), None, training, save)
@@ -674,7 +742,7 @@ def _resize_bwd(u, dup):
 
 def add_qh(a, b, off):
     """merge_mode='add' (models/unet.py:399-401): a + b[centre crop at off], QH operand tensors"""
-    out = QP.empty_half(a.N, a.C, a.D, a.H, a.W, a.t.device)
+    out = QP.empty_half(a.N, a.C, a.D, a.H, a.W, a.t.device, all_planes_written=True)
     L.check(L.lib().e3b_add_qh(a.ptr, b.ptr, out.ptr, a.N, a.C, a.D, a.H, a.W, b.D, b.H, b.W, off[0], off[1], off[2],
                                _stream()), 'add_qh')
     return out
@@ -689,7 +757,7 @@ def _run_up(net, spec, dec, enc, training, save):
     out_sp, off1 = _autocrop(full, enc.spatial)
     u = Unit()
     u.spec, u.src0, u.src1, u.off1, u.pool, u.mode, u.G, u.act = spec, dec, None, (0, 0, 0), None, mode, G, act
-    u.pooled = u.nstate = u.stats = u.resize = None
+    u.pooled = u.nstate = u.stats = u.resize = u.res = u.res_grads = None
     u.dec = dec
     bias = up.bias.detach() if up.bias is not None else None
     wsc = net.wset.scales[spec.name]
@@ -746,7 +814,7 @@ def forward_features(net, x, training, save):
     x5 = x.unsqueeze(2) if squeeze else x
     if x5.dim() != 5:
         raise RuntimeError(f'expected a {net.dim + 2}-dimensional input, got shape {tuple(x.shape)}')
-    cin = net.down[0][0].C0
+    cin = net.down[0][0][0].c1.C0
     if x5.shape[1] != cin:
         raise RuntimeError(f'expected {cin} input channels, got {x5.shape[1]}')
     cur = pack_input(x5)
@@ -758,24 +826,23 @@ def forward_features_qp(net, cur, training, save, squeeze=False, in_shape=None):
     tape.down, tape.up, tape.squeeze, tape.in_shape = [], [], squeeze, in_shape
     net.wset = tape.wset = prepare_weights(net, training)
     enc = []
-    for c1, c2, pool in net.down:
-        u1 = _run_unit(net, c1, cur, None, (0, 0, 0), None, training, save)
-        u2 = _run_unit(net, c2, u1.a, None, (0, 0, 0), pool, training, save)
-        enc.append(u2.a)
-        cur = u2.pooled if pool is not None else u2.a
-        tape.down.append((u1, u2))
-    for i, (ups, c1, c2) in enumerate(net.up):
+    for blocks, pool in net.down:
+        units = _run_blocks(net, blocks, cur, None, (0, 0, 0), pool, training, save)
+        last = units[-1][1]
+        enc.append(last.a)
+        cur = last.pooled if pool is not None else last.a
+        tape.down.append(units)
+    for i, (ups, blocks) in enumerate(net.up):
         e = enc[-(i + 2)]
         u0, off1 = (_run_resize if isinstance(ups, ResizeSpec) else _run_up)(net, ups, cur, e, training, save)
         add_info = None
         if net.merge_add:
-            u1 = _run_unit(net, c1, add_qh(u0.a, e, off1), None, (0, 0, 0), None, training, save)
+            units = _run_blocks(net, blocks, add_qh(u0.a, e, off1), None, (0, 0, 0), None, training, save)
             add_info = (off1, e.spatial)
         else:
-            u1 = _run_unit(net, c1, u0.a, e, off1, None, training, save)
-        u2 = _run_unit(net, c2, u1.a, None, (0, 0, 0), None, training, save)
-        cur = u2.a
-        tape.up.append((u0, u1, u2, len(net.down) - 2 - i, add_info))
+            units = _run_blocks(net, blocks, u0.a, e, off1, None, training, save)
+        cur = units[-1][1].a
+        tape.up.append((u0, units, len(net.down) - 2 - i, add_info))
     tape.final_in = cur
     return cur, tape
 
@@ -919,6 +986,8 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
         _put(grads, n.bias, dbeta)
     if conv.bias is not None:
         _put(grads, conv.bias, dbias)
+    if getattr(u, 'res', None) is not None:
+        _shortcut_bwd(net, u, dy, dbias, grads)
     cropped = u.src1 is not None and (tuple(u.off1) != (0, 0, 0) or u.src1.spatial != u.src0.spatial)
     if conv.weight.requires_grad:
         dw = wgrad(u.src0, dy, spec.Co, spec.k, spec.pad, tuple(conv.weight.shape), src1=u.src1, off1=u.off1)
@@ -936,6 +1005,55 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
                              dst1_C=spec.C1 if u.src1 is not None else 0, variant=dvar, w_unscale=wsc)
     if cropped:
         d1.crop_off = tuple(u.off1)       # gradient of autocrop's slice of the skip tensor (models/unet.py:303-324)
+    return d0, d1
+
+
+def _shortcut_bwd(net, u, dy, dbias, grads):
+    """gradient of the shortcut branch of a resunet ConvBlock: parameters of the projection, and u.res_grads = what has to
+    be added to the gradient of the block input (the scaled fp16 dy itself for the identity shortcut)."""
+    kind, r0, r1, roff = u.res
+    if not isinstance(kind, ConvSpec):
+        u.res_grads = ('dy', dy)
+        return
+    pc = kind.conv
+    if pc.bias is not None and dbias is not None:
+        _put(grads, pc.bias, dbias.clone())        # both biases are added to the same y: the same gradient
+    if pc.weight.requires_grad:
+        _put(grads, pc.weight, wgrad(r0, dy, kind.Co, kind.k, kind.pad, tuple(pc.weight.shape), src1=r1, off1=roff))
+    wsc = net.wset.scales[kind.name]
+    if net.wset.images is not None:
+        wpk = net.wset.images[(kind.name, 'bwd')]
+    else:
+        wpk = pack_weights(5 if kind.variants[1] else 1, pc.weight, None, kind.C0, kind.C1, kind.Co, kind.k, wscale=wsc)
+    p0, p1, _ = conv_forward(dy, wpk, kind.n_total_dgrad, kind.C0, kind.k, (0, 0, 0),
+                             dst1_C=kind.C1 if r1 is not None else 0, variant=kind.variants[1], w_unscale=wsc)
+    u.res_grads = ('qp', p0, p1)
+
+
+def _axpy(dst, src, alpha=None):
+    L.check(L.lib().e3b_qp_axpy(dst.ptr, src.ptr, 1 if src.half else 0, alpha, dst.N, dst.C, dst.D * dst.H * dst.W, _stream()),
+            'qp_axpy')
+
+
+def _blocks_bwd(net, units, g0, g1, gp, grads, need_dx):
+    """backward of a stack of Blocks; (g0, g1, gp) arrive at the last block's output.  -> gradients w.r.t. the two sources
+    of the first block"""
+    d0 = d1 = None
+    for bi in range(len(units) - 1, -1, -1):
+        u1, u2 = units[bi]
+        ga, _ = _conv_unit_bwd(net, u2, g0, g1, gp, grads, True)
+        need = bi > 0 or need_dx
+        d0, d1 = _conv_unit_bwd(net, u1, ga, None, None, grads, need)
+        rg = u2.res_grads
+        if rg is not None and need:
+            if rg[0] == 'dy':
+                _axpy(d0, rg[1], rg[1].scale.data_ptr() + 8)       # the tensor holds 2^k * dy: times dy_scale[2] = 2^-k
+            else:
+                _axpy(d0, rg[1])
+                if d1 is not None:
+                    _axpy(d1, rg[2])
+        u2.res_grads = None
+        g0, g1, gp = d0, None, None
     return d0, d1
 
 
@@ -967,9 +1085,8 @@ def _backward(net, tape, dlogits, need_dx):
 
     g = da
     skip = {}
-    for (u0, u1, u2, enc_index, add_info), (ups, c1, c2) in zip(reversed(tape.up), reversed(net.up)):
-        g, _ = _conv_unit_bwd(net, u2, g, None, None, grads, True)
-        du, denc = _conv_unit_bwd(net, u1, g, None, None, grads, True)
+    for (u0, units, enc_index, add_info), (ups, blocks) in zip(reversed(tape.up), reversed(net.up)):
+        du, denc = _blocks_bwd(net, units, g, None, None, grads, True)
         if add_info is not None:
             # merge_mode='add': the gradient of the sum goes to both summands; the skip tensor sees it through autocrop's slice
             denc = QP(du.t, du.N, du.C, du.D, du.H, du.W)
@@ -1002,13 +1119,12 @@ def _backward(net, tape, dlogits, need_dx):
     nd = len(net.down)
     dx = None
     for i in range(nd - 1, -1, -1):
-        u1, u2 = tape.down[i]
+        units = tape.down[i]
         # (the skip gradient always travels as g1: it may be the gradient of a centre-cropped view)
-        if u2.pool is not None:
-            g, _ = _conv_unit_bwd(net, u2, None, skip.get(i), g, grads, True)
+        if units[-1][1].pool is not None:
+            g, _ = _blocks_bwd(net, units, None, skip.get(i), g, grads, i > 0 or need_dx)
         else:
-            g, _ = _conv_unit_bwd(net, u2, g, skip.get(i), None, grads, True)
-        g, _ = _conv_unit_bwd(net, u1, g, None, None, grads, i > 0 or need_dx)
+            g, _ = _blocks_bwd(net, units, g, skip.get(i), None, grads, i > 0 or need_dx)
     if need_dx:
         dx = unpack(g)
         if tape.squeeze:

@@ -186,6 +186,41 @@ def _called_from_trace_check():
     return False
 
 
+def validate_unet_args(n_blocks, dim, planar_blocks, up_mode, merge_mode, batch_norm, attention):
+    """the reference's argument validation (models/unet.py:773-833, models/resunet.py:640-700), same exception types"""
+    if n_blocks < 1:
+        raise ValueError('n_blocks must be > 1.')
+    if dim not in {2, 3}:
+        raise ValueError('dim has to be 2 or 3')
+    if dim == 2 and tuple(planar_blocks) != ():
+        raise ValueError('If dim=2, you can\'t use planar_blocks since everything will be planar '
+                         '(2-dimensional) anyways.\nEither set dim=3 or set planar_blocks=().')
+    valid_up = ('transpose', 'upsample', 'resizeconv_nearest', 'resizeconv_linear', 'resizeconv_nearest1',
+                'resizeconv_linear1')
+    if up_mode not in valid_up:
+        raise ValueError(f'"{up_mode}" is not a valid mode for upsampling')
+    if merge_mode not in ('concat', 'add'):
+        raise ValueError(f'"{merge_mode}" is not a valid mode for merging up and down paths. '
+                         'Only "concat" and "add" are allowed.')
+    if 'resizeconv' in up_mode and merge_mode == 'add':
+        raise ValueError('up_mode "resizeconv" is incompatible with merge_mode "add"')
+    if len(planar_blocks) > n_blocks:
+        raise ValueError('planar_blocks can\'t be longer than n_blocks.')
+    if planar_blocks and (max(planar_blocks) >= n_blocks or min(planar_blocks) < 0):
+        raise ValueError('planar_blocks has invalid value range. All values have to be block indices, '
+                         'meaning integers between 0 and (n_blocks - 1).')
+    if batch_norm != 'unset':
+        raise RuntimeError('The `batch_norm` option has been replaced with the more general `normalization` '
+                           'option.\nIf you still want to use batch normalization, set `normalization=batch` '
+                           'instead.')
+    # --- options outside the accelerated hot path (SURVEY.md section 8f item 4)
+    if up_mode == 'upsample':
+        # (valid by the reference's check, but its upconv2 has no branch for it and returns None: unet.py:152-175)
+        raise NotImplementedError('up_mode="upsample" is not on the B200 path')
+    if attention:
+        raise NotImplementedError('attention=True (GridAttention) is not on the B200 path')
+
+
 class _UNetFunction(torch.autograd.Function):
     """The whole encoder/decoder as ONE autograd node: forward saves the QP activations on the ctx,
     backward launches dgrad / wgrad / norm-backward kernels and returns per-parameter gradients."""
@@ -230,38 +265,7 @@ class UNet(nn.Module):
             conv_mode: str = 'same',
     ):
         super().__init__()
-        # --- the reference's argument validation (models/unet.py:773-833), same exception types
-        if n_blocks < 1:
-            raise ValueError('n_blocks must be > 1.')
-        if dim not in {2, 3}:
-            raise ValueError('dim has to be 2 or 3')
-        if dim == 2 and tuple(planar_blocks) != ():
-            raise ValueError('If dim=2, you can\'t use planar_blocks since everything will be planar '
-                             '(2-dimensional) anyways.\nEither set dim=3 or set planar_blocks=().')
-        valid_up = ('transpose', 'upsample', 'resizeconv_nearest', 'resizeconv_linear', 'resizeconv_nearest1',
-                    'resizeconv_linear1')
-        if up_mode not in valid_up:
-            raise ValueError(f'"{up_mode}" is not a valid mode for upsampling')
-        if merge_mode not in ('concat', 'add'):
-            raise ValueError(f'"{merge_mode}" is not a valid mode for merging up and down paths. '
-                             'Only "concat" and "add" are allowed.')
-        if 'resizeconv' in up_mode and merge_mode == 'add':
-            raise ValueError('up_mode "resizeconv" is incompatible with merge_mode "add"')
-        if len(planar_blocks) > n_blocks:
-            raise ValueError('planar_blocks can\'t be longer than n_blocks.')
-        if planar_blocks and (max(planar_blocks) >= n_blocks or min(planar_blocks) < 0):
-            raise ValueError('planar_blocks has invalid value range. All values have to be block indices, '
-                             'meaning integers between 0 and (n_blocks - 1).')
-        if batch_norm != 'unset':
-            raise RuntimeError('The `batch_norm` option has been replaced with the more general `normalization` '
-                               'option.\nIf you still want to use batch normalization, set `normalization=batch` '
-                               'instead.')
-        # --- options outside the accelerated hot path
-        if up_mode == 'upsample':
-            # (valid by the reference's check, but its upconv2 has no branch for it and returns None: unet.py:152-175)
-            raise NotImplementedError('up_mode="upsample" is not on the B200 path')
-        if attention:
-            raise NotImplementedError('attention=True (GridAttention) is not on the B200 path')
+        validate_unet_args(n_blocks, dim, planar_blocks, up_mode, merge_mode, batch_norm, attention)
 
         self.up_mode, self.merge_mode = up_mode, merge_mode
         self.out_channels, self.in_channels = out_channels, in_channels
@@ -305,8 +309,8 @@ class UNet(nn.Module):
             down, up = [], []
             for i, b in enumerate(self.down_convs):
                 p = f'down_convs.{i}'
-                down.append((engine.ConvSpec(p + '.conv1', b.conv1, b.norm0, b.in_channels, 0, act=b.act1),
-                             engine.ConvSpec(p + '.conv2', b.conv2, b.norm1, b.out_channels, 0, act=b.act2),
+                down.append(([engine.Block(engine.ConvSpec(p + '.conv1', b.conv1, b.norm0, b.in_channels, 0, act=b.act1),
+                                           engine.ConvSpec(p + '.conv2', b.conv2, b.norm1, b.out_channels, 0, act=b.act2))],
                              b.pool_kernel()))
             for i, b in enumerate(self.up_convs):
                 p = f'up_convs.{i}'
@@ -315,10 +319,9 @@ class UNet(nn.Module):
                 else:
                     ups = engine.UpSpec(p + '.upconv', b.upconv, b.norm0, act=b.act0)
                 add = b.merge_mode == 'add'
-                up.append((ups,
-                           engine.ConvSpec(p + '.conv1', b.conv1, b.norm1, b.out_channels, 0 if add else b.out_channels,
-                                           act=b.act1),
-                           engine.ConvSpec(p + '.conv2', b.conv2, b.norm2, b.out_channels, 0, act=b.act2)))
+                up.append((ups, [engine.Block(
+                    engine.ConvSpec(p + '.conv1', b.conv1, b.norm1, b.out_channels, 0 if add else b.out_channels, act=b.act1),
+                    engine.ConvSpec(p + '.conv2', b.conv2, b.norm2, b.out_channels, 0, act=b.act2))]))
             net = engine.Net(down, up, self.conv_final, self.dim, cache, merge_add=self.merge_mode == 'add')
             self.__dict__['_e3b_net'] = net
         return net
@@ -347,8 +350,8 @@ class UNet(nn.Module):
             raise ValueError(f'expected {dim} spatial extents, got {tuple(in_spatial)}')
         pad = 1 if 'same' in self.conv_mode else 0
 
-        def conv2x(sp, planar):
-            lose = 2 * 2 * (1 - pad)                       # two 3-tap convolutions
+        def conv2x(sp, planar, nblocks=1):
+            lose = 2 * 2 * (1 - pad) * nblocks             # two 3-tap convolutions per block
             out = [sp[0] - (0 if (planar or dim == 2) else lose), sp[1] - lose, sp[2] - lose]
             if min(out) < 1:
                 raise RuntimeError(f'input extents {tuple(in_spatial)} are too small for this network')
@@ -356,7 +359,7 @@ class UNet(nn.Module):
         enc = []
         for i, b in enumerate(self.down_convs):
             planar = i in self.planar_blocks
-            cur = conv2x(cur, planar)
+            cur = conv2x(cur, planar, self._convs_per_block(i, True))
             enc.append(list(cur))
             if b.pooling:
                 k = b.pool_kernel()
@@ -369,8 +372,12 @@ class UNet(nn.Module):
             up = [u - ((u - d) % 2) for u, d in zip(up, e)]
             if any(u > d for u, d in zip(up, e)):
                 raise RuntimeError('autocrop: the upsampled tensor exceeds the skip tensor')
-            cur = conv2x(up, planar)
+            cur = conv2x(up, planar, self._convs_per_block(i, False))
         return tuple(cur[3 - dim:])
+
+    def _convs_per_block(self, i, down):
+        """two-conv blocks per level (resunet.UNet stacks several)"""
+        return 1
 
     def invalidate_weight_cache(self):
         """Drop the packed weight images (eval mode keeps them between calls).  Needed only after writing parameters

@@ -235,6 +235,16 @@ int e3b_upsample_qh(const void* src, void* dst, int N, int C, int d, int h, int 
 int e3b_upsample_bwd_qp(const float* gfine, float* gcoarse, int N, int C, int d, int h, int w, int Dp, int Hp, int Wp, int sd, int sh,
                         int sw, int off_d, int off_h, int off_w, int Rd, int Rh, int Rw, int linear, void* stream);
 
+/* The residual shortcut of resunet's ConvBlock (models/resunet.py:252-261: `y = conv2(..); y += proj(inp); y = norm2(y)`):
+ * y (QP fp32, N x C x S voxels, in place) += r, r the QP fp32 output of the 1x1x1 projection or -- identity shortcut -- the
+ * QH activation itself (r_is_half).  stats (optional, [N][C][2] fp64, zeroed here): sum / sum of squares of the SUM, what
+ * e3b_norm_finalize needs for the norm that follows.
+ * e3b_qp_axpy: dst (QP fp32, in place) += alpha * src (QP fp32 or QH fp16; alpha a device scalar, NULL = 1): the
+ * shortcut's gradient added to the gradient of the block input (with src = the scaled fp16 gradient dy and
+ * alpha = e3b_norm_bwd_args.dy_scale + 2 for the identity shortcut). */
+int e3b_residual_add(float* y_qp, const void* r, int r_is_half, double* stats, int N, int C, int64_t S, void* stream);
+int e3b_qp_axpy(float* dst_qp, const void* src, int src_is_half, const float* alpha, int N, int C, int64_t S, void* stream);
+
 /* ---- 1x1x1 head --------------------------------------------------------------------------------
  * conv_final (unet.py:881,912) fused with Predictor's Softmax(1) / Argmax (inference.py:443-456,202-212).
  * out_mode 0: logits float NCDHW; 1: softmax float NCDHW; 2: argmax uint8 (N,1,D,H,W).

@@ -56,9 +56,10 @@ OPTION_CASES = {
                            x=(1, 1, 16, 16, 16), train=False),
     'opt_add_train': dict(model=dict(n_blocks=3, start_filts=8, normalization='group', merge_mode='add'),
                           x=(2, 1, 16, 16, 16), train=True),
+    # (28^3 in -> 12^3 out: with a 4^3 output one ReLU whose pre-activation sits at 0 +- TF32 noise moves a bias gradient by 1/64)
     'opt_add_valid_train': dict(model=dict(n_blocks=2, start_filts=8, normalization='group', merge_mode='add',
                                            conv_mode='valid'),
-                                x=(1, 1, 20, 20, 20), train=True),
+                                x=(1, 1, 28, 28, 28), train=True),
     'opt_resize_nearest_train': dict(model=dict(n_blocks=3, start_filts=8, normalization='group',
                                                 up_mode='resizeconv_nearest'),
                                      x=(2, 1, 16, 16, 16), train=True),
@@ -73,6 +74,32 @@ OPTION_CASES = {
     'opt_resize_linear_odd_train': dict(model=dict(n_blocks=3, start_filts=8, normalization='group',
                                                    up_mode='resizeconv_linear'),
                                         x=(1, 1, 11, 13, 18), train=True),
+}
+
+# elektronn3.models.resunet.UNet: `arch='resunet'` selects the model class
+RESUNET_CASES = {
+    # no residual blocks: the arithmetic of the plain UNet under resunet's parameter names
+    'res0_train': dict(arch='resunet', model=dict(n_blocks=3, start_filts=8, normalization='group'),
+                       x=(2, 1, 16, 16, 16), train=True),
+    # one residual ConvBlock per level: projection shortcuts (channel counts differ everywhere but at the image)
+    'res1_train': dict(arch='resunet', model=dict(n_blocks=3, start_filts=8, normalization='group', enc_res_blocks=1,
+                                                  dec_res_blocks=1),
+                       x=(2, 1, 16, 16, 16), train=True),
+    # two per level: identity shortcuts as well, BatchNorm in training mode, a planar block
+    'res2_bn_train': dict(arch='resunet', model=dict(n_blocks=2, start_filts=8, enc_res_blocks=2, dec_res_blocks=2,
+                                                     planar_blocks=(0,)),
+                          x=(2, 1, 8, 16, 16), train=True),
+    # eval-mode BatchNorm around the shortcuts (never folded into the weights), odd extents
+    'res2_bn_eval': dict(arch='resunet', model=dict(n_blocks=3, start_filts=8, enc_res_blocks=2, dec_res_blocks=1),
+                         x=(1, 1, 11, 13, 18), train=False),
+    # merge_mode='add' (identity shortcut on the sum), leaky, resize-conv up-sampling in a separate case
+    'res1_add_leaky_train': dict(arch='resunet', model=dict(n_blocks=2, start_filts=8, normalization='group', enc_res_blocks=1,
+                                                            dec_res_blocks=1, merge_mode='add', activation='leaky'),
+                                 x=(1, 1, 16, 16, 16), train=True),
+    'res1_resize_none_train': dict(arch='resunet', model=dict(n_blocks=2, start_filts=8, normalization='none',
+                                                              enc_res_blocks=1, dec_res_blocks=2,
+                                                              up_mode='resizeconv_linear'),
+                                   x=(1, 1, 8, 16, 16), train=True),
 }
 
 # Predictor / tiled_apply cases: model, volume shape, tile, overlap

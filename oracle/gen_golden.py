@@ -45,12 +45,17 @@ def load_reference():
     _load('elektronn3.modules.lovasz_losses', f'{REF}/elektronn3/modules/lovasz_losses.py')
     loss = _load('elektronn3.modules.loss', f'{REF}/elektronn3/modules/loss.py')
     inference = _load('e3ref_inference', f'{REF}/elektronn3/inference/inference.py')
+    global RESUNET
+    RESUNET = _load('e3ref_resunet', f'{REF}/elektronn3/models/resunet.py')
     return unet, loss, inference
 
 
-def build_model(unet, kwargs):
+RESUNET = None
+
+
+def build_model(unet, kwargs, arch='unet'):
     torch.manual_seed(0)
-    model = unet.UNet(**kwargs)
+    model = (RESUNET if arch == 'resunet' else unet).UNet(**kwargs)
     shapes = fx.state_shapes_from_torch(model)
     sd = fx.make_state(shapes)
     model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
@@ -63,10 +68,10 @@ def main():
     unet, loss_mod, inference = load_reference()
     os.makedirs(OUT, exist_ok=True)
     only = set(sys.argv[1:])           # optional: names of the cases to (re)generate
-    for name, case in list(fx.CASES.items()) + list(fx.OPTION_CASES.items()):
+    for name, case in list(fx.CASES.items()) + list(fx.OPTION_CASES.items()) + list(fx.RESUNET_CASES.items()):
         if only and name not in only:
             continue
-        model, shapes, sd = build_model(unet, case['model'])
+        model, shapes, sd = build_model(unet, case['model'], case.get('arch', 'unet'))
         x = fx.make_input(case['x'])
         out = dict(keys=json.dumps(shapes), x_shape=np.array(case['x']))
         xt = torch.from_numpy(x)

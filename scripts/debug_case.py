@@ -1,11 +1,12 @@
-"""Per-parameter gradient error of one shape-matrix case (ours / cuDNN-TF32 / TF32-operand emulation vs fp32) for a few seeds."""
+"""Per-parameter gradient error of one case (ours / cuDNN-TF32 / TF32-operand emulation vs fp32) for a few seeds and
+both norm-backward paths.   usage: python scripts/debug_case.py"""
 import copy, sys, os
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
 import torch
 import elektronn3_b200 as e3
 from oracle import torch_ref
 
-def run(seed, kw, shape):
+def run(seed, kw, shape, verbose=False):
     torch.manual_seed(seed)
     m = e3.UNet(**kw).cuda().train()
     m0 = copy.deepcopy(m)
@@ -14,7 +15,7 @@ def run(seed, kw, shape):
     g = torch.randn_like(out)
     out.backward(g)
     ours = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
-    _, g32 = torch_ref.grads_with(m0, x, g, 'fp32')
+    o32, g32 = torch_ref.grads_with(m0, x, g, 'fp32')
     _, gtf = torch_ref.grads_with(m0, x, g, 'tf32')
     _, gem = torch_ref.grads_with(m0, x, g, 'emulate')
     gmax = max(v.abs().max().item() for v in g32.values())
@@ -22,12 +23,16 @@ def run(seed, kw, shape):
     for k, ref in g32.items():
         sc = max(ref.abs().max().item(), 1e-2 * gmax)
         eo = ((ours[k] - ref).abs().max() / sc).item(); et = ((gtf[k] - ref).abs().max() / sc).item(); ee = ((gem[k] - ref).abs().max() / sc).item()
+        if verbose:
+            print('   %-32s ours %.4f tf32 %.4f emu %.4f  scale %.3e' % (k, eo, et, ee, ref.abs().max().item()))
         if eo > 3 * max(et, ee) + 5e-3:
             bad.append((k, round(eo, 4), round(et, 4), round(ee, 4)))
-    print(seed, kw.get('planar_blocks'), shape, 'bad:', bad)
+    print(seed, os.environ.get('E3B_NORM_BWD'), kw, shape, 'logit err %.2e' % ((out - o32).abs().max() / o32.abs().max()).item(), 'bad:', bad)
 
-for seed in range(6):
-    run(seed, dict(n_blocks=2, planar_blocks=(0, 1)), (2, 1, 1, 4, 4))
-    run(seed, dict(n_blocks=2, dim=2), (2, 1, 4, 4))
-    run(seed, dict(n_blocks=3, planar_blocks=(0, 1, 2)), (2, 1, 1, 8, 8))
-    run(seed, dict(n_blocks=2, planar_blocks=(0, 1), normalization='group'), (2, 1, 1, 4, 4))
+for path in ('fused', 'split'):
+    os.environ['E3B_NORM_BWD'] = path
+    for seed in range(3):
+        run(seed, dict(n_blocks=2, start_filts=8, normalization='group', merge_mode='add', conv_mode='valid'), (1, 1, 20, 20, 20), verbose=seed == 0)
+        run(seed, dict(n_blocks=2, start_filts=8, normalization='group', merge_mode='concat', conv_mode='valid'), (1, 1, 20, 20, 20))
+        run(seed, dict(n_blocks=2, start_filts=8, normalization='batch', merge_mode='add', conv_mode='valid'), (2, 1, 20, 20, 20))
+        run(seed, dict(n_blocks=2, start_filts=16, normalization='group', merge_mode='add', conv_mode='valid'), (1, 1, 20, 20, 20))

@@ -304,3 +304,58 @@ def test_torch_twin_and_torchscript_export(kw, shape, tmp_path):
     m.train()
     m.torch_twin()(x).square().mean().backward()
     assert all(p.grad is not None for p in m.parameters())
+
+
+# ------------------------------------------------------------------------------------------ resunet
+def test_resunet_module_follows_the_reference_layout():
+    """state_dict keys / order / shapes of elektronn3.models.resunet.UNet (the golden files carry the key list of the real
+    reference module), constructor errors, shortcut kinds"""
+    import json
+    import elektronn3_b200 as e3
+    from conftest import load_golden
+    from oracle import fixtures as fx
+    for name, case in fx.RESUNET_CASES.items():
+        g, sd = load_golden(name)
+        m = e3.resunet.UNet(**case['model'])
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s, _ in json.loads(str(g['keys']))], name
+    m = e3.resunet.UNet(n_blocks=2, start_filts=8, enc_res_blocks=2, dec_res_blocks=1)
+    assert isinstance(m, e3.UNet)                                      # Predictor / GraphedTrainStep accept it
+    cb = m.down_convs[0].convs
+    assert not cb[0].residual and cb[1].residual and isinstance(cb[1].proj, torch.nn.Identity)   # no shortcut from the image
+    assert isinstance(m.down_convs[1].convs[0].proj, torch.nn.Conv3d)                            # 8 -> 16: projection
+    assert tuple(m.up_convs[0].convs[0].proj.weight.shape) == (8, 16, 1, 1, 1)                   # over the concat
+    net = m._net()
+    assert [type(b.res).__name__ for b in net.down[0][0]] == ['NoneType', 'str']
+    assert net.down[1][0][0].res.name == 'down_convs.1.convs.0.proj' and net.down[1][0][0].c2.residual
+    assert m.output_spatial((16, 16, 16)) == (16, 16, 16)
+    with pytest.raises(NotImplementedError):
+        e3.resunet.UNet(dim=2)
+    with pytest.raises(NotImplementedError):
+        e3.resunet.UNet(enc_res_blocks=1, conv_mode='valid')
+    with pytest.raises(ValueError):
+        e3.resunet.UNet(up_mode='bogus')
+
+
+@pytest.mark.parametrize('kw,shape', [(dict(n_blocks=2, start_filts=4), (1, 1, 8, 16, 16)),
+                                      (dict(n_blocks=3, start_filts=4, normalization='group4', enc_res_blocks=2, dec_res_blocks=1,
+                                            planar_blocks=(0,)), (2, 1, 5, 13, 18)),
+                                      (dict(n_blocks=2, start_filts=4, enc_res_blocks=1, dec_res_blocks=1, merge_mode='add',
+                                            activation='silu'), (1, 1, 8, 8, 16))])
+def test_resunet_twin_and_torchscript_export(kw, shape, tmp_path):
+    import elektronn3_b200 as e3
+    from oracle import torch_ref
+    torch.manual_seed(0)
+    m = e3.resunet.UNet(**kw).eval()
+    x = torch.randn(shape)
+    with torch.no_grad():
+        want = torch_ref.unet_forward(m, x)
+        twin = m.torch_twin()
+        assert list(twin.state_dict().keys()) == list(m.state_dict().keys())
+        assert torch.allclose(twin(x), want, atol=1e-6)
+        scripted = torch.jit.script(m)
+        assert torch.allclose(scripted(x), want, atol=1e-6)
+        path = str(tmp_path / 'res.pts')
+        scripted.save(path)
+        assert torch.allclose(torch.jit.load(path)(x), want, atol=1e-6)
+        traced = torch.jit.trace(m, x)
+        assert torch.allclose(traced(x), want, atol=1e-6)

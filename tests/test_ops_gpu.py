@@ -326,6 +326,9 @@ WGRAD_CASES = [
     (1, 24, 0, 40, (6, 9, 11), (3, 3, 3), (0, 0, 0)),      # VALID, ragged channel counts
     (1, 32, 0, 16, (1, 33, 65), (1, 3, 3), (0, 1, 1)),     # D = 1 (the 2D path)
     (1, 256, 0, 32, (2, 6, 6), (3, 3, 3), (1, 1, 1)),      # 8 M chunks, tiny extent
+    (1, 8, 0, 8, (8, 8, 8), (3, 3, 3), (0, 0, 0)),         # VALID at the bottom of a small net (merge_mode='add' golden)
+    (1, 8, 0, 16, (8, 8, 8), (3, 3, 3), (0, 0, 0)),
+    (1, 8, 0, 8, (6, 6, 6), (3, 3, 3), (0, 0, 0)),
 ]
 
 
@@ -717,3 +720,60 @@ def test_upsample_into_padded_tensor_and_its_transpose(eng, mode, C, sp, s, cp, 
     u.resize = geom
     got = eng._resize_bwd(u, qp32(eng, g))
     assert_close(from_qp_ref(got.t, C), xd.grad, 1e-6, 'upsample backward')
+
+
+# ---------------------------------------------------------------------------------------- resunet shortcut
+@pytest.mark.parametrize('C,sp,half', [(16, (4, 6, 8), True), (8, (3, 5, 7), False), (20, (2, 9, 11), True), (32, (8, 16, 16), False)])
+def test_residual_add_and_statistics(eng, C, sp, half):
+    """y += proj(inp) of ConvBlock (models/resunet.py:257-258) with the statistics of the sum; then the gradient accumulation"""
+    from elektronn3_b200 import _lib as L
+    N = 2
+    y = dyadic((N, C) + sp, 11)
+    r = dyadic((N, C) + sp, 12)
+    yq = qp32(eng, y)
+    rq = qp(eng, r) if half else qp32(eng, r)
+    stats = torch.empty((N, C, 2), dtype=torch.float64, device='cuda')
+    S = sp[0] * sp[1] * sp[2]
+    L.check(L.lib().e3b_residual_add(yq.ptr, rq.ptr, 1 if half else 0, stats.data_ptr(), N, C, S, eng._stream()), 'residual_add')
+    ref = (y + r).double()
+    assert_close(from_qp_ref(yq.t, C), ref, 1e-7, 'residual sum')
+    assert_close(stats[..., 0], ref.sum(dim=(2, 3, 4)), 1e-6, 'sum')
+    assert_close(stats[..., 1], (ref ** 2).sum(dim=(2, 3, 4)), 1e-6, 'sum of squares')
+    if eng.cpad8(C) != C:
+        assert from_qp_ref(yq.t, eng.cpad8(C))[:, C:].abs().max().item() == 0.0
+    # gradient accumulation: dst += alpha * src
+    g = dyadic((N, C) + sp, 13)
+    gq = qp32(eng, g)
+    alpha = torch.tensor([0.25], device='cuda')
+    eng._axpy(gq, rq, alpha.data_ptr())
+    assert_close(from_qp_ref(gq.t, C), g + 0.25 * r, 1e-7, 'axpy')
+    eng._axpy(gq, rq)
+    assert_close(from_qp_ref(gq.t, C), g + 1.25 * r, 1e-7, 'axpy (alpha = 1)')
+
+
+@pytest.mark.parametrize('C0,C1,Co,sp', [(8, 0, 16, (4, 8, 8)), (16, 16, 16, (4, 8, 16)), (32, 32, 32, (3, 10, 18)), (8, 8, 8, (5, 7, 9))])
+def test_projection_shortcut_conv_forward_backward(eng, C0, C1, Co, sp):
+    """the 1x1x1 projection of a residual ConvBlock (models/resunet.py:246-250) over the (virtual) concat: forward, dgrad
+    into both sources and the weight gradient in torch layout"""
+    N = 2
+    x = dyadic((N, C0 + C1) + sp, 31, scale=2, lo=-2, hi=3).double().requires_grad_(True)
+    w = dyadic((Co, C0 + C1, 1, 1, 1), 32, scale=2, lo=-2, hi=3).double().requires_grad_(True)
+    b = dyadic((Co,), 33)
+    y = F.conv3d(x, w, b.double())
+    dy = dyadic(tuple(y.shape), 34, scale=2, lo=-2, hi=3)
+    y.backward(dy.double())
+    k, pad = (1, 1, 1), (0, 0, 0)
+    src0 = qp(eng, x.detach()[:, :C0].float().contiguous())
+    src1 = qp(eng, x.detach()[:, C0:].float().contiguous()) if C1 else None
+    wpk = eng.pack_weights(0, w.detach().float(), None, C0, C1, Co, k)
+    out, _, _ = eng.conv_forward(src0, wpk, eng.cpad16(Co), Co, k, pad, src1=src1, bias=b)
+    assert_close(from_qp_ref(out.t, Co), y, 1e-6, 'projection forward')
+    dyq = qp(eng, dy)
+    dw = eng.wgrad(src0, dyq, Co, k, pad, tuple(w.shape), src1=src1)
+    assert_close(dw, w.grad, 1e-6, 'projection wgrad')
+    nd = eng.cpad16(eng.cpad8(C0) + (eng.cpad8(C1) if C1 else 0))
+    wpd = eng.pack_weights(1, w.detach().float(), None, C0, C1, Co, k)
+    d0, d1, _ = eng.conv_forward(dyq, wpd, nd, C0, k, pad, dst1_C=C1)
+    assert_close(from_qp_ref(d0.t, C0), x.grad[:, :C0], 1e-6, 'projection dgrad 0')
+    if C1:
+        assert_close(from_qp_ref(d1.t, C1), x.grad[:, C0:], 1e-6, 'projection dgrad 1')

@@ -93,16 +93,16 @@ def test_convT_is_gemm_plus_pixel_shuffle():
 def _torch_model(case, sd, train):
     import torch
     import elektronn3_b200 as e3
-    m = e3.UNet(**case['model'])
+    m = (e3.resunet.UNet if case.get('arch') == 'resunet' else e3.UNet)(**case['model'])
     m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
     return m.train(train)
 
 
-@pytest.mark.parametrize('name', list(fx.CASES) + list(fx.OPTION_CASES))
+@pytest.mark.parametrize('name', list(fx.CASES) + list(fx.OPTION_CASES) + list(fx.RESUNET_CASES))
 def test_torch_restatement_matches_reference(name):
     import torch
     from oracle import torch_ref
-    case = {**fx.CASES, **fx.OPTION_CASES}[name]
+    case = {**fx.CASES, **fx.OPTION_CASES, **fx.RESUNET_CASES}[name]
     g, sd = load_golden(name)
     m = _torch_model(case, sd, case['train'])
     x = torch.from_numpy(fx.make_input(case['x']))
