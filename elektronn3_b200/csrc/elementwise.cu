@@ -177,6 +177,35 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
     j.dst[i] = pack_weight_element(j.mode, j.w, j.scale, ws, j.C0, j.C1, j.Co, j.tu, j.d, i);
 }
 
+// per-tensor power-of-two weight scales: one block per tensor, table[b] = (2^k, 2^-k) with k = -floor(log2(max |w|))
+// (max |w| lands in [1, 2); 0 / non-finite maxima give k = 0), |k| <= 100
+__global__ void __launch_bounds__(256) weight_scales_kernel(const e3b_ws_job* __restrict__ jobs, float* __restrict__ table)
+{
+    const e3b_ws_job j = jobs[blockIdx.x];
+    float m = 0.f;
+    bool bad = false;
+    for (long long i = threadIdx.x; i < j.n; i += 256) {
+        const float v = fabsf(__ldg(j.w + i));
+        bad |= !(v <= 3.4e38f);                    // NaN / inf
+        m = fmaxf(m, v);
+    }
+    __shared__ float red[8];
+    __shared__ int redb[8];
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const int anyb = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = m; redb[threadIdx.x >> 5] = anyb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int w = 0; w < 8; w++) { m = fmaxf(m, red[w]); b |= redb[w]; }
+        float k = 0.f;
+        if (m > 0.f && !b) k = -floorf(log2f(fmaxf(m, 1e-37f)));
+        k = fminf(fmaxf(k, -100.f), 100.f);
+        table[2 * blockIdx.x] = exp2f(k);
+        table[2 * blockIdx.x + 1] = exp2f(-k);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // normalisation statistics -> per-(n,c) scale / shift (+ running stats)
 // ------------------------------------------------------------------------------------------------
@@ -1771,6 +1800,13 @@ int e3b_pack_weights_batched(const void* device_table, int njobs, int64_t total_
     if (!device_table || njobs <= 0 || total_blocks <= 0) return set_error("pack_weights_batched: bad arguments");
     pack_weights_batched_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackJobDev*>(device_table), njobs);
     return check_launch("pack_weights_batched");
+}
+
+int e3b_weight_scales(const e3b_ws_job* device_jobs, int njobs, float* table, void* stream)
+{
+    if (!device_jobs || !table || njobs <= 0) return set_error("weight_scales: bad arguments");
+    weight_scales_kernel<<<njobs, 256, 0, (cudaStream_t)stream>>>(device_jobs, table);
+    return check_launch("weight_scales");
 }
 
 int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_t S, const float* gamma, const float* beta,

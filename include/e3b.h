@@ -81,6 +81,12 @@ int64_t e3b_pack_job_table_bytes(int njobs);
 int e3b_pack_jobs_fill(const e3b_pack_job* jobs, int njobs, void* host_table, int64_t* total_blocks);
 int e3b_pack_weights_batched(const void* device_table, int njobs, int64_t total_blocks, void* stream);
 
+/* The per-tensor power-of-two weight scales (`wscale` above) of all weight tensors of a network in one launch:
+ * table[2*i] = 2^k, table[2*i+1] = 2^-k with k = -floor(log2(max |w_i|)), so that the scaled maximum lands in [1, 2)
+ * (k = 0 for all-zero or non-finite tensors, |k| <= 100).  device_jobs: njobs descriptors in DEVICE memory. */
+typedef struct e3b_ws_job { const float* w; int64_t n; } e3b_ws_job;
+int e3b_weight_scales(const e3b_ws_job* device_jobs, int njobs, float* table, void* stream);
+
 /* ---- convolution ------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (kind::f16: fp16 operands, fp32 accumulate).
  * Replaces nn.Conv3d/Conv2d behind conv3 (models/unet.py:131-149) incl. its dgrad, the virtual

@@ -43,7 +43,8 @@ def test_ctypes_structs_match_the_c_structs(tmp_path):
     """sizeof / offsetof of every argument struct as gcc sees include/e3b.h == the ctypes mirror"""
     from elektronn3_b200 import _lib
     structs = {'e3b_conv_args': _lib.ConvArgs, 'e3b_wgrad_args': _lib.WgradArgs,
-               'e3b_norm_bwd_args': _lib.NormBwdArgs, 'e3b_head_args': _lib.HeadArgs, 'e3b_pack_job': _lib.PackJob}
+               'e3b_norm_bwd_args': _lib.NormBwdArgs, 'e3b_head_args': _lib.HeadArgs, 'e3b_pack_job': _lib.PackJob,
+               'e3b_ws_job': _lib.WsJob}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, cls in structs.items():
         lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')

@@ -777,3 +777,22 @@ def test_projection_shortcut_conv_forward_backward(eng, C0, C1, Co, sp):
     assert_close(from_qp_ref(d0.t, C0), x.grad[:, :C0], 1e-6, 'projection dgrad 0')
     if C1:
         assert_close(from_qp_ref(d1.t, C1), x.grad[:, C0:], 1e-6, 'projection dgrad 1')
+
+
+def test_weight_scale_table_kernel_matches_the_torch_formula(eng):
+    """e3b_weight_scales (one launch for all weight tensors of a training step) == engine.weight_scale_table (torch ops)"""
+    from elektronn3_b200 import _lib as L
+    torch.manual_seed(3)
+    ws = [torch.randn(32, 32, 3, 3, 3, device='cuda') * 0.03, torch.randn(7, 5, 1, 3, 3, device='cuda') * 40.0,
+          torch.zeros(4, 4, 1, 1, 1, device='cuda'), torch.full((3, 3, 3), 2.0, device='cuda'),
+          torch.randn(128, 128, 3, 3, 3, device='cuda') * 1e-6, torch.tensor([0.99999994], device='cuda')]
+    jobs = (L.WsJob * len(ws))(*[L.WsJob(w.data_ptr(), w.numel()) for w in ws])
+    dev_jobs = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).cuda()
+    table = torch.empty((len(ws), 2), device='cuda')
+    L.check(L.lib().e3b_weight_scales(dev_jobs.data_ptr(), len(ws), table.data_ptr(), eng._stream()), 'weight_scales')
+    ref = eng.weight_scale_table(ws)
+    assert torch.equal(table, ref), (table, ref)
+    assert table[2].tolist() == [1.0, 1.0]
+    for w, (up, down) in zip(ws, table.tolist()):
+        if float(w.abs().max()) > 0:
+            assert 1.0 <= float(w.abs().max()) * up < 2.0 + 1e-6 and up * down == 1.0

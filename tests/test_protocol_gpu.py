@@ -440,3 +440,64 @@ def test_train_step_with_fused_dice_matches_torch_dice(e3):
     # tiny GroupNorm net amplifies that (fp16 operand rounding of the gradients flips): compare at 1e-3 of each tensor's scale
     for a, b in zip(g1, [p.grad for p in m.parameters()]):
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-6 + 1e-3 * float(b.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------ resunet + options
+def test_resunet_in_predictor_and_graphed_train_step(e3):
+    """elektronn3_b200.resunet.UNet through the same callers as the plain UNet: Predictor (tile for tile against the
+    reference-style tiled loop, inference.py:134-197) and GraphedTrainStep (graph replay == eager step)"""
+    from oracle import torch_ref
+    torch.manual_seed(21)
+    m = e3.resunet.UNet(n_blocks=2, start_filts=16, enc_res_blocks=2, dec_res_blocks=1).cuda()
+    with torch.no_grad():
+        for k, b in m.named_buffers():
+            if k.endswith('running_var'):
+                b.copy_(0.5 + torch.rand_like(b))
+            elif k.endswith('running_mean'):
+                b.copy_(0.1 * torch.randn_like(b))
+    m.eval()
+    vol = torch.randn(1, 1, 16, 32, 32)
+    tile, ovl = (8, 16, 16), (4, 8, 8)
+    ref = _ref_tiled(m, vol, tile, ovl, lambda t: torch_ref.unet_forward(m, t).softmax(1))
+    out = e3.Predictor(m, device='cuda', tile_shape=tile, overlap_shape=ovl, offset=(0, 0, 0), out_shape=(2, 16, 32, 32)).predict(vol)
+    assert rel(out, ref) < 4e-3
+    # training: eager vs graph replay
+    kw = dict(n_blocks=2, start_filts=8, normalization='group', enc_res_blocks=1, dec_res_blocks=2)
+    m_e = e3.resunet.UNet(**kw).cuda().train()
+    m_g = copy.deepcopy(m_e)
+    shape, tshape = (2, 1, 16, 16, 16), (2, 16, 16, 16)
+    crit = e3.DiceLoss()
+    o_e = torch.optim.SGD(m_e.parameters(), lr=1e-2, momentum=0.9)
+    o_g = torch.optim.SGD(m_g.parameters(), lr=1e-2, momentum=0.9)
+    step = e3.GraphedTrainStep(m_g, crit, o_g, shape, tshape, warmup=2)
+    for i in range(3):
+        x = torch.randn(shape, device='cuda')
+        t = torch.randint(0, 2, tshape, device='cuda')
+        o_e.zero_grad(set_to_none=True)
+        le = crit(m_e(x), t); le.backward(); o_e.step()
+        lg, _ = step(x, t)
+        assert abs(float(le) - float(lg)) <= 1e-4 * abs(float(le)) + 1e-6, (i, float(le), float(lg))
+
+
+@pytest.mark.parametrize('arch,kw,shape', [
+    ('resunet', dict(n_blocks=3, start_filts=32, normalization='group', enc_res_blocks=1, dec_res_blocks=1), (2, 1, 32, 32, 32)),
+    ('unet', dict(n_blocks=3, start_filts=32, normalization='group', up_mode='resizeconv_nearest', activation='leaky'), (2, 1, 32, 32, 32)),
+    ('unet', dict(n_blocks=3, start_filts=32, merge_mode='add', activation='silu'), (2, 1, 24, 32, 40)),
+])
+def test_options_at_baseline_widths_within_tf32_noise(e3, arch, kw, shape):
+    """the options and the residual net at cfg 2's channel widths (32 / 64 / 128: the tensor-core shapes, z-stacked and
+    halo-tile kernels, N tiles) against fp32 torch on the same GPU: logits at 4e-3 of their scale, every parameter gradient
+    within 3x the TF32 noise measured on the spot"""
+    torch.manual_seed(22)
+    cls = e3.resunet.UNet if arch == 'resunet' else e3.UNet
+    m = cls(**kw).cuda().train()
+    m0 = copy.deepcopy(m)
+    x = torch.randn(shape, device='cuda')
+    out = m(x)
+    g = torch.randn_like(out)
+    out.backward(g)
+    o32 = ref32(copy.deepcopy(m0), x)
+    assert rel(out.detach(), o32.detach()) < 4e-3
+    for (k, p), (_, q) in zip(m.named_parameters(), m0.named_parameters()):
+        q.grad = p.grad
+    grads_within_tf32_noise(m0, x, g)
