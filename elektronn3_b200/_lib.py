@@ -122,7 +122,7 @@ SIGNATURES = {
     'e3b_pack_job_table_bytes': (c_i64, [c_int]),
     'e3b_pack_jobs_fill': (c_int, [ctypes.POINTER(PackJob), c_int, c_void_p, ctypes.POINTER(c_i64)]),
     'e3b_pack_weights_batched': (c_int, [c_void_p, c_int, c_i64, c_void_p]),
-    'e3b_weight_scales': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    'e3b_weight_scales': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'e3b_conv': (c_int, [ctypes.POINTER(ConvArgs), c_void_p]),
     'e3b_conv_variant': (c_int, [c_int] * 7),
     'e3b_debug_zs_read': (c_int, [c_void_p, c_int]),

@@ -177,32 +177,39 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
     j.dst[i] = pack_weight_element(j.mode, j.w, j.scale, ws, j.C0, j.C1, j.Co, j.tu, j.d, i);
 }
 
-// per-tensor power-of-two weight scales: one block per tensor, table[b] = (2^k, 2^-k) with k = -floor(log2(max |w|))
-// (max |w| lands in [1, 2); 0 / non-finite maxima give k = 0), |k| <= 100
-__global__ void __launch_bounds__(256) weight_scales_kernel(const e3b_ws_job* __restrict__ jobs, float* __restrict__ table)
+// per-tensor power-of-two weight scales: grid (chunks, tensors); table[b] = (2^k, 2^-k) with k = -floor(log2(max |w|))
+// (max |w| lands in [1, 2); 0 / non-finite maxima give k = 0), |k| <= 100.  scratch[2b] collects the maximum (float bits of
+// a non-negative float order like unsigned integers), scratch[2b + 1] counts finished blocks; the last block of a tensor
+// writes the table row and leaves both words zero for the next call.
+static constexpr int kWsChunks = 16;
+__global__ void __launch_bounds__(256) weight_scales_kernel(const e3b_ws_job* __restrict__ jobs, float* __restrict__ table,
+                                                            unsigned int* __restrict__ scratch)
 {
-    const e3b_ws_job j = jobs[blockIdx.x];
+    const int b = blockIdx.y;
+    const e3b_ws_job j = jobs[b];
     float m = 0.f;
-    bool bad = false;
-    for (long long i = threadIdx.x; i < j.n; i += 256) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < j.n; i += 256ll * kWsChunks) {
         const float v = fabsf(__ldg(j.w + i));
-        bad |= !(v <= 3.4e38f);                    // NaN / inf
-        m = fmaxf(m, v);
+        m = (v <= 3.4e38f) ? fmaxf(m, v) : INFINITY;            // NaN / inf poison the maximum
     }
     __shared__ float red[8];
-    __shared__ int redb[8];
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const int anyb = __any_sync(0xffffffffu, bad);
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = m; redb[threadIdx.x >> 5] = anyb; }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
-        int b = 0;
-        for (int w = 0; w < 8; w++) { m = fmaxf(m, red[w]); b |= redb[w]; }
-        float k = 0.f;
-        if (m > 0.f && !b) k = -floorf(log2f(fmaxf(m, 1e-37f)));
-        k = fminf(fmaxf(k, -100.f), 100.f);
-        table[2 * blockIdx.x] = exp2f(k);
-        table[2 * blockIdx.x + 1] = exp2f(-k);
+        for (int w = 0; w < 8; w++) m = fmaxf(m, red[w]);
+        atomicMax(&scratch[2 * b], __float_as_uint(m));
+        __threadfence();
+        if (atomicAdd(&scratch[2 * b + 1], 1u) == (unsigned)gridDim.x - 1) {
+            __threadfence();
+            const float amax = __uint_as_float(atomicExch(&scratch[2 * b], 0u));
+            scratch[2 * b + 1] = 0u;
+            float k = 0.f;
+            if (amax > 0.f && amax <= 3.4e38f) k = -floorf(log2f(fmaxf(amax, 1e-37f)));
+            k = fminf(fmaxf(k, -100.f), 100.f);
+            table[2 * b] = exp2f(k);
+            table[2 * b + 1] = exp2f(-k);
+        }
     }
 }
 
@@ -1802,10 +1809,10 @@ int e3b_pack_weights_batched(const void* device_table, int njobs, int64_t total_
     return check_launch("pack_weights_batched");
 }
 
-int e3b_weight_scales(const e3b_ws_job* device_jobs, int njobs, float* table, void* stream)
+int e3b_weight_scales(const e3b_ws_job* device_jobs, int njobs, float* table, uint32_t* scratch, void* stream)
 {
-    if (!device_jobs || !table || njobs <= 0) return set_error("weight_scales: bad arguments");
-    weight_scales_kernel<<<njobs, 256, 0, (cudaStream_t)stream>>>(device_jobs, table);
+    if (!device_jobs || !table || !scratch || njobs <= 0 || njobs > 65535) return set_error("weight_scales: bad arguments");
+    weight_scales_kernel<<<dim3(kWsChunks, njobs), 256, 0, (cudaStream_t)stream>>>(device_jobs, table, scratch);
     return check_launch("weight_scales");
 }
 

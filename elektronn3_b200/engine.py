@@ -485,10 +485,11 @@ class TrainImages:
         # descriptors of the weight tensors for the one-launch scale table (e3b_weight_scales)
         ws = (L.WsJob * len(mods))(*[L.WsJob(m.weight.data_ptr(), m.weight.numel()) for m in mods])
         self.ws_jobs = torch.frombuffer(bytearray(bytes(ws)), dtype=torch.uint8).to(dev)
+        self.ws_scratch = torch.zeros((2 * len(mods),), dtype=torch.int32, device=dev)
 
     def pack(self):
-        L.check(L.lib().e3b_weight_scales(self.ws_jobs.data_ptr(), len(self.weights), self.table.data_ptr(), _stream()),
-                'weight_scales')
+        L.check(L.lib().e3b_weight_scales(self.ws_jobs.data_ptr(), len(self.weights), self.table.data_ptr(),
+                                          self.ws_scratch.data_ptr(), _stream()), 'weight_scales')
         L.check(L.lib().e3b_pack_weights_batched(self.dev_table.data_ptr(), self.njobs, self.blocks, _stream()),
                 'pack_weights_batched')
 

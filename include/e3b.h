@@ -83,9 +83,10 @@ int e3b_pack_weights_batched(const void* device_table, int njobs, int64_t total_
 
 /* The per-tensor power-of-two weight scales (`wscale` above) of all weight tensors of a network in one launch:
  * table[2*i] = 2^k, table[2*i+1] = 2^-k with k = -floor(log2(max |w_i|)), so that the scaled maximum lands in [1, 2)
- * (k = 0 for all-zero or non-finite tensors, |k| <= 100).  device_jobs: njobs descriptors in DEVICE memory. */
+ * (k = 0 for all-zero or non-finite tensors, |k| <= 100).  device_jobs: njobs descriptors in DEVICE memory; scratch:
+ * 2 * njobs uint32 of device memory, zero before the first call (every call leaves it zero again). */
 typedef struct e3b_ws_job { const float* w; int64_t n; } e3b_ws_job;
-int e3b_weight_scales(const e3b_ws_job* device_jobs, int njobs, float* table, void* stream);
+int e3b_weight_scales(const e3b_ws_job* device_jobs, int njobs, float* table, uint32_t* scratch, void* stream);
 
 /* ---- convolution ------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (kind::f16: fp16 operands, fp32 accumulate).

@@ -466,7 +466,7 @@ def test_resunet_in_predictor_and_graphed_train_step(e3):
     m_e = e3.resunet.UNet(**kw).cuda().train()
     m_g = copy.deepcopy(m_e)
     shape, tshape = (2, 1, 16, 16, 16), (2, 16, 16, 16)
-    crit = e3.DiceLoss()
+    crit = e3.DiceLoss().cuda()
     o_e = torch.optim.SGD(m_e.parameters(), lr=1e-2, momentum=0.9)
     o_g = torch.optim.SGD(m_g.parameters(), lr=1e-2, momentum=0.9)
     step = e3.GraphedTrainStep(m_g, crit, o_g, shape, tshape, warmup=2)
