@@ -493,7 +493,7 @@ def predictor_bench(torch, dist, e3, engine, _lib, dev, world, rank, timed, bf16
     vol_host = torch.randn((1, 1) + PRED_VOL).pin_memory()
     out_vox = PRED_VOL[0] * PRED_VOL[1] * PRED_VOL[2]
     kw = dict(device=dev, tile_shape=PRED_TILE, overlap_shape=PRED_OVL, offset=(0, 0, 0), out_shape=(2,) + PRED_VOL,
-              apply_softmax=True, tile_batch=8)
+              apply_softmax=True)
     p_e2e = e3.Predictor(m, **kw)
     p_dev = e3.Predictor(m, return_device=True, **kw)
     vol_dev = vol_host.to(dev)
@@ -504,8 +504,9 @@ def predictor_bench(torch, dist, e3, engine, _lib, dev, world, rank, timed, bf16
     launches = (_lib.launch_count() - l0) // reps
     ms_e2e = timed(lambda: p_e2e.predict(vol_host), reps) / reps
     st = dict(p_e2e.last_stats)
-    # dominant kernel alone: the eval-mode conv of up_convs.2.conv1 on one tile batch (8 x 80^3, 32+32 -> 32, folded BN + ReLU)
-    B, S = 8, PRED_TILE[0] + 2 * PRED_OVL[0]
+    # dominant kernel alone: the eval-mode conv of up_convs.2.conv1 on one tile batch (B x 80^3, 32+32 -> 32, folded BN + ReLU)
+    S = PRED_TILE[0] + 2 * PRED_OVL[0]
+    B = p_dev.tile_batch or p_dev._auto_tile_batch(32, 1, (S, S, S))        # what one forward pass of the run above held
     q0 = engine.QP.empty_half(B, 32, S, S, S, dev)
     q1 = engine.QP.empty_half(B, 32, S, S, S, dev)
     q0.t.normal_(), q1.t.normal_()
@@ -529,14 +530,14 @@ def predictor_bench(torch, dist, e3, engine, _lib, dev, world, rank, timed, bf16
     achieved = B * PRED_DOM_GFLOP_PER_TILE / ms_dom
     pred = dict(metric='voxels/s', value=out_vox / ms_dev * 1e3, unit='voxels/s', n_gpus=world, steps=reps, seconds_per_volume=ms_dev * 1e-3,
                 higher_is_better=True, scaling='strong', dtype='f16 operands / f32 accumulate', data='synthetic',
-                config=dict(workload=PRED_WORKLOAD, tile_batch=8, tiles=256,
+                config=dict(workload=PRED_WORKLOAD, tile_batch=int(B), tiles=256,
                             parallelism=(f'tile rows of the 8x8x4 tile grid sharded over {world} ranks, one NCCL gather of the '
                                          f'output slabs to rank 0') if world > 1 else 'single',
                             value_is='volume resident in HBM, result left in HBM', l2='268 MB volume + 537 MB result exceed the 126 MB L2'),
                 e2e=dict(value=out_vox / ms_e2e * 1e3, unit='voxels/s', seconds_per_volume=ms_e2e * 1e-3,
                          h2d_bytes_per_step=st.get('h2d_bytes'), d2h_bytes_per_step=st.get('d2h_bytes')),
                 gpu_launches=int(launches),
-                roofline=dict(bound='tensor', kernel=('conv_zs_kernel' if var else 'conv_tc_kernel') + ' on up_convs.2.conv1, one tile batch (32+32 -> 32 @ 8x80^3, folded BN + ReLU, fp16 out)',
+                roofline=dict(bound='tensor', kernel=('conv_zs_kernel' if var else 'conv_tc_kernel') + f' on up_convs.2.conv1, one tile batch (32+32 -> 32 @ {B}x80^3, folded BN + ReLU, fp16 out)',
                               achieved=achieved, peak=bf16_peak, unit='TFLOP/s', frac=achieved / bf16_peak, traffic=None,
                               ms_per_launch=ms_dom, peak_note=peak_note,
                               volume_tensor_frac=256 * PRED_TILE_GFLOP / ms_dev / bf16_peak / world))

@@ -103,7 +103,9 @@ def _is_set(a):
 class Predictor:
     """Same constructor and ``predict`` contract as the reference ``Predictor`` (inference.py:368-388,569).
 
-    Extra keyword arguments (not in the reference): ``tile_batch`` = tiles per forward pass;
+    Extra keyword arguments (not in the reference): ``tile_batch`` = tiles per forward pass (default ``None``: a whole row
+    of tiles when the free device memory allows -- the deep, small levels of the network only fill the GPU with many tiles
+    per launch: 0.097 -> 0.086 s per cfg-4 volume from 8 to 32 tiles);
     ``distributed`` = shard tiles over the ranks of the default process group (default: on if
     ``torch.distributed`` is initialised with more than one rank); ``result_on`` = ``'rank0'`` (the assembled
     volume is returned by rank 0, the other ranks return ``None``) or ``'all'``; ``return_device`` = leave the result
@@ -115,7 +117,7 @@ class Predictor:
                  overlap_shape=None, offset=None, out_shape=None, out_dtype=None, float16=False,
                  apply_softmax=True, transform=None, augmentations=None, strict_shapes=False,
                  apply_argmax=False, argmax_with_threshold=None, verbose=False, report_inp_stats=False,
-                 tile_batch=8, distributed=None, result_on='rank0', return_device=False):
+                 tile_batch=None, distributed=None, result_on='rank0', return_device=False):
         if device is None:
             device = torch.device('cuda')
         elif isinstance(device, str):
@@ -204,7 +206,7 @@ class Predictor:
         self.overlap_shape = np.array(overlap_shape) if overlap_shape is not None else None
         self.tile_shape = np.array(tile_shape) if tile_shape is not None else None
         self.out_shape = np.array(out_shape) if out_shape is not None else None
-        self.tile_batch = int(tile_batch)
+        self.tile_batch = None if tile_batch is None else max(1, int(tile_batch))
         self.distributed = distributed
         if result_on not in ('rank0', 'all'):
             raise ValueError("result_on must be 'rank0' or 'all'")
@@ -262,8 +264,9 @@ class Predictor:
                            len(h2d_events)) - 1
                 if need >= 0:
                     cur.wait_event(h2d_events[need])
-            for b0 in range(0, len(pos), self.tile_batch):
-                o = org[b0:b0 + self.tile_batch]
+            tb = self.tile_batch or self._auto_tile_batch(len(pos), C, in_tile)
+            for b0 in range(0, len(pos), tb):
+                o = org[b0:b0 + tb]
                 B = o.shape[0]
                 so, do = o[:, :3].contiguous(), o[:, 3:].contiguous()
                 for i, m in enumerate(masks):
@@ -284,6 +287,19 @@ class Predictor:
             if on_row_done is not None:
                 on_row_done(r)
         return ntiles
+
+    def _auto_tile_batch(self, row_tiles, C, in_tile):
+        """tiles per forward pass when the caller did not choose: the whole tile row, capped by a quarter of the free device
+        memory at ~12 fp16 activation tensors of the widest full-resolution layer per tile (a conservative bound on what
+        a no-grad forward keeps alive)"""
+        tb = self.__dict__.get('_tb_auto')
+        if tb is None:
+            vox = int(in_tile[0]) * int(in_tile[1]) * int(in_tile[2])
+            width = max(int(getattr(self.model, 'start_filts', 32)), int(C))
+            per_tile = vox * width * 2 * 12
+            free, _ = torch.cuda.mem_get_info(self.device)
+            tb = self.__dict__['_tb_auto'] = int(max(1, min(64, (free // 4) // max(per_tile, 1))))
+        return max(1, min(tb, row_tiles))
 
     def predict(self, inp):
         """inference.py:569-643.  ``inp``: np.ndarray or torch.Tensor (N, C, [D,] H, W); returns a CPU tensor
