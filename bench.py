@@ -340,19 +340,26 @@ def main():
             # K steps, each with the H2D copy of ITS pinned host batch and a D2H read of its loss (trainer.py:575), all K
             # copies inside the timed region.  The copy of batch i+1 is started on the copy stream right after replay i
             # is enqueued (GraphedTrainStep.prefetch), so only the first copy is exposed.
+            # The loss of every step is copied D2H right behind its replay and READ one step later (step_async): the host
+            # enqueues step i + 1 before it blocks on the loss of step i, so the device never waits for a launch.
             gstep.prefetch(x_host, t_host)
+            prev = None
             for i in range(k):
-                loss = gstep()[0]
+                fut = gstep.step_async()
                 if i + 1 < k:
                     gstep.prefetch(x_host, t_host)
                 if world > 1:                  # the graph ends after backward: gradient average + optimizer step, eagerly
                     grad_sync()
                     opt.step()
-                float(loss)
+                if prev is not None:
+                    prev.result()
+                prev = fut
+            prev.result()
         if gstep is not None:
             e2e_pipelined(3)
             ms_e2e = timed(lambda: e2e_pipelined(args.steps), 1)
-            e2e_mode = 'H2D of batch i+1 on a copy stream behind the kernels of step i (GraphedTrainStep.prefetch)'
+            e2e_mode = ('H2D of batch i+1 on a copy stream behind the kernels of step i (GraphedTrainStep.prefetch); the loss of '
+                        'every step is copied D2H behind its replay and read by the host one step later (step_async)')
         else:
             for _ in range(2):
                 e2e_step()

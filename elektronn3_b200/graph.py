@@ -39,6 +39,7 @@ class GraphedTrainStep:
         self.model, self.criterion, self.optimizer, self.grad_sync = model, criterion, optimizer, grad_sync
         from . import _lib
         self._copy_stream, self._stage, self._has_staged = None, None, False
+        self._loss_slots, self._loss_next = None, 0
         self.inp = torch.zeros(inp_shape, dtype=torch.float32, device=dev)
         self.target = torch.zeros(target_shape, dtype=target_dtype, device=dev)
         # Warm-up on a side stream: lazy initialisation of kernels, allocator and optimizer state happens here, not
@@ -153,3 +154,30 @@ class GraphedTrainStep:
         self.graph.replay()
         self._invalidate()
         return self.dloss, self.dout
+
+    def step_async(self, inp=None, target=None):
+        """``__call__`` + an asynchronous D2H copy of the step's loss into a pinned host slot: returns a ``LossFuture`` whose
+        ``result()`` waits for THAT copy only.  A loop that enqueues step i + 1 before it asks for the loss of step i keeps
+        the device busy while the host reads (``float(dloss)`` right after every step, training/trainer.py:575, idles the
+        device for a launch latency per step).  Two slots: at most two futures may be outstanding."""
+        self(inp, target)
+        if self._loss_slots is None:
+            self._loss_slots = [(torch.empty((), dtype=self.dloss.dtype).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+            self._loss_next = 0
+        host, ev = self._loss_slots[self._loss_next]
+        self._loss_next ^= 1
+        host.copy_(self.dloss.detach(), non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.inp.device))
+        return LossFuture(host, ev)
+
+
+class LossFuture:
+    """the loss of one ``GraphedTrainStep.step_async`` call, on its way to the host"""
+    __slots__ = ('_host', '_event')
+
+    def __init__(self, host, event):
+        self._host, self._event = host, event
+
+    def result(self):
+        self._event.synchronize()
+        return float(self._host)
