@@ -290,22 +290,8 @@ def main():
     elif world > 1:
         step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
 
-    sync_mode = {'coalesced': os.environ.get('E3B_BENCH_FLAT_ALLREDUCE') != '1'}
-
     def grad_sync():
-        """data-parallel gradient average over the ranks: what DistributedDataParallel's buckets compute"""
         grads = [p.grad for p in params]
-        if sync_mode['coalesced']:
-            # ONE grouped NCCL launch (ncclGroupStart / End) averaging all gradient tensors in place: no flatten /
-            # un-flatten copies, no separate division
-            try:
-                with dist._coalescing_manager(async_ops=False):
-                    for g in grads:
-                        dist.all_reduce(g, op=dist.ReduceOp.AVG)
-                return
-            except Exception as e:                     # an older / different c10d: fall back to the flat buffer
-                sync_mode['coalesced'] = False
-                sys.stderr.write(f'coalesced all-reduce unavailable ({e!r}); using one flat buffer\n')
         flat = torch._utils._flatten_dense_tensors(grads)
         dist.all_reduce(flat)
         flat.div_(world)
@@ -447,7 +433,7 @@ def main():
                             parallelism=f'dp{world}' if world > 1 else 'single',
                             launch=('eager launches' if not use_graph else
                                     'whole step replayed as one CUDA graph (GraphedTrainStep)' if world == 1 else
-                                    'forward+loss+backward replayed as one CUDA graph, one grouped NCCL all-reduce (AVG) of the gradient tensors and '
+                                    'forward+loss+backward replayed as one CUDA graph, flat NCCL all-reduce and '
                                     'optimizer step eager'),
                             l2='per-step working set (>3 GB of fp32 activations) exceeds the 126 MB L2; no flush needed'),
                 e2e=dict(value=e2e_value, unit='voxels/s', ms_per_step=ms_e2e / args.steps,
