@@ -52,6 +52,7 @@ class WgradArgs(ctypes.Structure):
         ('dw', c_void_p), ('layout', c_i32), ('up_taps', c_i32), ('up_co', c_i32),
         ('workspace', c_void_p),
         ('dy_unscale', c_void_p),
+        ('defer_reduce', c_i32),
     ]
 
 
@@ -131,6 +132,7 @@ SIGNATURES = {
     'e3b_debug_conv_counters': (c_int, [c_void_p, c_int]),
     'e3b_wgrad_workspace_floats': (c_i64, [ctypes.POINTER(WgradArgs)]),
     'e3b_wgrad': (c_int, [ctypes.POINTER(WgradArgs), c_void_p]),
+    'e3b_wgrad_reduce_batched': (c_int, [ctypes.POINTER(WgradArgs), c_int, c_void_p]),
     'e3b_norm_finalize': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_i64, c_void_p, c_void_p, c_float,
                                   c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'e3b_norm_act': (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_float, c_int, c_void_p]),

@@ -89,4 +89,10 @@ int e3b_wgrad(const e3b_wgrad_args* a, void* stream)
     return launch_wgrad_tc(a, (cudaStream_t)stream);
 }
 
+int e3b_wgrad_reduce_batched(const e3b_wgrad_args* args, int n, void* stream)
+{
+    if (!args || n <= 0) return set_error("wgrad_reduce_batched: no jobs");
+    return launch_wgrad_reduce_batched(args, n, (cudaStream_t)stream);
+}
+
 }  // extern "C"

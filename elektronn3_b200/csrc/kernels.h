@@ -28,6 +28,7 @@ int conv_zs_debug_read(uint32_t* out, int n);
 int conv_zs_prof_read(unsigned long long* out16, int reset);
 int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream);
 int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream);
+int launch_wgrad_reduce_batched(const e3b_wgrad_args* args, int n, cudaStream_t stream);
 int64_t wgrad_workspace_floats(const e3b_wgrad_args* a);
 
 __host__ __device__ static inline int cpad8(int c) { return (c + 7) & ~7; }

@@ -223,30 +223,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx0, const __grid_constant_
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// One split-K reduction: S partials of [ntaps][ktot][npad_total] floats -> dw in torch layout.
+struct WgReduceJob {
+    const float* part; float* dw; const float* dy_unscale;
+    int S, ntaps, ktot, npad_total, CB, mchunks0, C0, C1, Co, layout, up_taps, up_co, up_copad;
+    int first_block, nblocks, warp_mode;          // batched launch: this job's slice of the grid
+};
+
 // deterministic split-K reduction + scatter into the torch parameter layout.  A block of 8 warps owns 128 consecutive
 // elements: warp w adds the partials s = w, w + 8, ... (coalesced 512-byte rows of float4), the eight sums meet in shared
 // memory and are added in warp order.  (One thread per element walking all S <= 148 partials was latency bound:
 // 25 us for the 16 MB of partials of a 32 -> 32 layer; 128-byte rows: 11.7 us.)
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int S, int ntaps,
-                                                            int ktot, int npad_total, int CB, int mchunks0, int C0, int C1, int Co,
-                                                            int layout, int up_taps, int up_co, int up_copad,
-                                                            const float* __restrict__ dy_unscale)
+E3B_DEVINL void wgrad_reduce_warps(const WgReduceJob& j, unsigned block, unsigned nblocks)
 {
     // a block owns 128 consecutive elements (4 per lane: 512-byte rows); npad_total % 4 == 0, so a lane's four elements
     // share (tap, input channel) and differ in the output column only
     __shared__ float4 red[8][32];
-    const unsigned total = (unsigned)ntaps * ktot * npad_total;           // < 2^31 (checked by the launch wrapper)
-    const float unscale = dy_unscale ? __ldg(dy_unscale) : 1.f;
+    const unsigned total = (unsigned)j.ntaps * j.ktot * j.npad_total;           // < 2^31 (checked by the launch wrapper)
+    const float unscale = j.dy_unscale ? __ldg(j.dy_unscale) : 1.f;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (unsigned i0 = blockIdx.x * 128u; i0 < total; i0 += gridDim.x * 128u) {
+    for (unsigned i0 = block * 128u; i0 < total; i0 += nblocks * 128u) {
         const unsigned i = i0 + lane * 4u;
         const bool inside = i < total;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (inside) {
-            const float4* q = reinterpret_cast<const float4*>(part + i);
+            const float4* q = reinterpret_cast<const float4*>(j.part + i);
             const size_t step = (size_t)total / 4;                       // float4 units between consecutive partials
 #pragma unroll 4
-            for (int sp = w; sp < S; sp += 8) {
+            for (int sp = w; sp < j.S; sp += 8) {
                 const float4 v = __ldcs(q + (size_t)sp * step);
                 s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             }
@@ -256,49 +260,66 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
         if (w == 0 && inside) {
             float4 t = red[0][lane];
 #pragma unroll
-            for (int j = 1; j < 8; j++) { const float4 r = red[j][lane]; t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
-            const unsigned row = i / (unsigned)npad_total;
-            const int nn0 = (int)(i - row * (unsigned)npad_total);
-            const int tap = (int)(row / (unsigned)ktot), kk = (int)(row - (unsigned)tap * ktot);
+            for (int k = 1; k < 8; k++) { const float4 r = red[k][lane]; t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+            const unsigned row = i / (unsigned)j.npad_total;
+            const int nn0 = (int)(i - row * (unsigned)j.npad_total);
+            const int tap = (int)(row / (unsigned)j.ktot), kk = (int)(row - (unsigned)tap * j.ktot);
             bool valid;
             int ci;
-            if (kk < mchunks0 * CB) { valid = kk < C0; ci = kk; }
-            else { const int k1 = kk - mchunks0 * CB; valid = k1 < C1; ci = C0 + k1; }
+            if (kk < j.mchunks0 * j.CB) { valid = kk < j.C0; ci = kk; }
+            else { const int k1 = kk - j.mchunks0 * j.CB; valid = k1 < j.C1; ci = j.C0 + k1; }
             const float tv[4] = {t.x * unscale, t.y * unscale, t.z * unscale, t.w * unscale};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int nn = nn0 + e;
                 if (!valid) continue;
-                if (layout == 0) { if (nn < Co) dw[((size_t)nn * (C0 + C1) + ci) * ntaps + tap] = tv[e]; }
-                else if (nn / up_copad < up_taps && nn % up_copad < up_co) dw[((size_t)ci * up_co + nn % up_copad) * up_taps + nn / up_copad] = tv[e];
+                if (j.layout == 0) { if (nn < j.Co) j.dw[((size_t)nn * (j.C0 + j.C1) + ci) * j.ntaps + tap] = tv[e]; }
+                else if (nn / j.up_copad < j.up_taps && nn % j.up_copad < j.up_co)
+                    j.dw[((size_t)ci * j.up_co + nn % j.up_copad) * j.up_taps + nn / j.up_copad] = tv[e];
             }
         }
         __syncthreads();
     }
 }
 
-// one thread per element, walking all S partials: for layers whose contraction is split over fewer than 64 CTAs
-__global__ void wgrad_reduce_flat_kernel(const float* __restrict__ part, float* __restrict__ dw, int S, int ntaps, int ktot,
-                                         int npad_total, int CB, int mchunks0, int C0, int C1, int Co, int layout, int up_taps,
-                                         int up_co, int up_copad, const float* __restrict__ dy_unscale)
+// one thread per element, walking all S partials: for layers whose contraction is split over fewer than 16 CTAs
+E3B_DEVINL void wgrad_reduce_flat(const WgReduceJob& j, unsigned block, unsigned nblocks)
 {
-    const size_t total = (size_t)ntaps * ktot * npad_total;
-    const float unscale = dy_unscale ? __ldg(dy_unscale) : 1.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int nn = (int)(i % npad_total);
-        const int kk = (int)((i / npad_total) % ktot);
-        const int tap = (int)(i / ((size_t)npad_total * ktot));
+    const size_t total = (size_t)j.ntaps * j.ktot * j.npad_total;
+    const float unscale = j.dy_unscale ? __ldg(j.dy_unscale) : 1.f;
+    for (size_t i = (size_t)block * blockDim.x + threadIdx.x; i < total; i += (size_t)nblocks * blockDim.x) {
+        const int nn = (int)(i % j.npad_total);
+        const int kk = (int)((i / j.npad_total) % j.ktot);
+        const int tap = (int)(i / ((size_t)j.npad_total * j.ktot));
         int ci;
-        if (kk < mchunks0 * CB) { if (kk >= C0) continue; ci = kk; }
-        else { const int k1 = kk - mchunks0 * CB; if (k1 >= C1) continue; ci = C0 + k1; }
-        if (layout == 0) { if (nn >= Co) continue; }
-        else { if (nn / up_copad >= up_taps || nn % up_copad >= up_co) continue; }
+        if (kk < j.mchunks0 * j.CB) { if (kk >= j.C0) continue; ci = kk; }
+        else { const int k1 = kk - j.mchunks0 * j.CB; if (k1 >= j.C1) continue; ci = j.C0 + k1; }
+        if (j.layout == 0) { if (nn >= j.Co) continue; }
+        else { if (nn / j.up_copad >= j.up_taps || nn % j.up_copad >= j.up_co) continue; }
         float s = 0.f;
-        for (int sp = 0; sp < S; sp++) s += part[(size_t)sp * total + i];
+        for (int sp = 0; sp < j.S; sp++) s += j.part[(size_t)sp * total + i];
         s *= unscale;
-        if (layout == 0) dw[((size_t)nn * (C0 + C1) + ci) * ntaps + tap] = s;
-        else dw[((size_t)ci * up_co + nn % up_copad) * up_taps + nn / up_copad] = s;
+        if (j.layout == 0) j.dw[((size_t)nn * (j.C0 + j.C1) + ci) * j.ntaps + tap] = s;
+        else j.dw[((size_t)ci * j.up_co + nn % j.up_copad) * j.up_taps + nn / j.up_copad] = s;
     }
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgReduceJob j) { wgrad_reduce_warps(j, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256) wgrad_reduce_flat_kernel(const WgReduceJob j) { wgrad_reduce_flat(j, blockIdx.x, gridDim.x); }
+
+// The reductions of several layers in ONE launch (the weight gradients of a backward pass are only needed by the optimizer:
+// a dozen 5-10 us launches, each a ramp-up and a tail between two big kernels, become one).  The jobs travel as a kernel
+// parameter, so a CUDA graph captures them by value.
+static constexpr int kWgBatch = 16;
+struct WgReduceBatch { WgReduceJob j[kWgBatch]; int n; };
+__global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const __grid_constant__ WgReduceBatch b)
+{
+    int k = 0;
+    while (k + 1 < b.n && (int)blockIdx.x >= b.j[k + 1].first_block) k++;
+    const WgReduceJob& j = b.j[k];
+    const unsigned local = blockIdx.x - (unsigned)j.first_block;
+    if (j.warp_mode) wgrad_reduce_warps(j, local, (unsigned)j.nblocks);
+    else wgrad_reduce_flat(j, local, (unsigned)j.nblocks);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -408,6 +429,21 @@ int64_t wgrad_workspace_floats(const e3b_wgrad_args* a)
     return (int64_t)p.S * a->kd * a->kh * a->kw * p.ktot * p.npad_total;
 }
 
+static void fill_reduce_job(const e3b_wgrad_args* a, const WgradParams& p, WgReduceJob& j)
+{
+    const int ntaps = a->kd * a->kh * a->kw;
+    const size_t total = (size_t)ntaps * p.ktot * p.npad_total;
+    j.part = p.part; j.dw = a->dw; j.dy_unscale = a->dy_unscale;
+    j.S = p.S; j.ntaps = ntaps; j.ktot = p.ktot; j.npad_total = p.npad_total; j.CB = p.CB; j.mchunks0 = p.mchunks0;
+    // (source 1's channels start at the next CB boundary after source 0's in the partial row space)
+    j.C0 = a->C0; j.C1 = a->src1 ? a->C1 : 0; j.Co = a->Co; j.layout = a->layout; j.up_taps = a->up_taps; j.up_co = a->up_co;
+    j.up_copad = cpad8(a->up_co);
+    j.first_block = 0;
+    j.warp_mode = (p.S >= 16 && total < ((size_t)1 << 31) && p.npad_total % 4 == 0) ? 1 : 0;
+    if (j.warp_mode) { int blocks = (int)((total + 127) / 128); if (blocks > 8 * num_sms()) blocks = 8 * num_sms(); j.nblocks = blocks; }
+    else { int blocks = (int)((total + 255) / 256); if (blocks > 4 * num_sms()) blocks = 4 * num_sms(); j.nblocks = blocks; }
+}
+
 int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
 {
     WgradParams p;
@@ -437,21 +473,37 @@ int launch_wgrad_tc(const e3b_wgrad_args* a, cudaStream_t stream)
     wgrad_tc_kernel<<<p.units * p.S, kWgThreads, smem, stream>>>(mx0, mx1, mdy, p);
     rc = check_launch("wgrad_tc");
     if (rc) return rc;
-    const int ntaps = a->kd * a->kh * a->kw;
-    const size_t total = (size_t)ntaps * p.ktot * p.npad_total;
-    // source 1's channels start at the next CB boundary after source 0's in the partial row space
-    if (p.S >= 16 && total < ((size_t)1 << 31) && p.npad_total % 4 == 0) {
-        int blocks = (int)((total + 127) / 128); if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-        wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.part, a->dw, p.S, ntaps, p.ktot, p.npad_total, p.CB, p.mchunks0,
-                                                        a->C0, a->src1 ? a->C1 : 0, a->Co, a->layout, a->up_taps, a->up_co,
-                                                        cpad8(a->up_co), a->dy_unscale);
-    } else {
-        int blocks = (int)((total + 255) / 256); if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-        wgrad_reduce_flat_kernel<<<blocks, 256, 0, stream>>>(p.part, a->dw, p.S, ntaps, p.ktot, p.npad_total, p.CB, p.mchunks0,
-                                                             a->C0, a->src1 ? a->C1 : 0, a->Co, a->layout, a->up_taps, a->up_co,
-                                                             cpad8(a->up_co), a->dy_unscale);
-    }
+    if (a->defer_reduce) return 0;                     // the caller reduces several layers at once (e3b_wgrad_reduce_batched)
+    WgReduceJob j;
+    fill_reduce_job(a, p, j);
+    if (j.warp_mode) wgrad_reduce_kernel<<<j.nblocks, 256, 0, stream>>>(j);
+    else wgrad_reduce_flat_kernel<<<j.nblocks, 256, 0, stream>>>(j);
     return check_launch("wgrad_reduce");
+}
+
+int launch_wgrad_reduce_batched(const e3b_wgrad_args* args, int n, cudaStream_t stream)
+{
+    for (int i0 = 0; i0 < n; i0 += kWgBatch) {
+        WgReduceBatch b;
+        memset(&b, 0, sizeof(b));
+        b.n = n - i0 < kWgBatch ? n - i0 : kWgBatch;
+        int blocks = 0;
+        for (int i = 0; i < b.n; i++) {
+            const e3b_wgrad_args* a = args + i0 + i;
+            if (!a->workspace || !a->dw) return set_error("wgrad_reduce_batched: null workspace / dw");
+            WgradParams p;
+            const int rc = plan_wgrad(a, p);
+            if (rc) return rc;
+            p.part = a->workspace;
+            fill_reduce_job(a, p, b.j[i]);
+            b.j[i].first_block = blocks;
+            blocks += b.j[i].nblocks;
+        }
+        wgrad_reduce_batched_kernel<<<blocks, 256, 0, stream>>>(b);
+        const int rc = check_launch("wgrad_reduce_batched");
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // namespace e3b

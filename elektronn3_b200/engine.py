@@ -13,6 +13,7 @@ derives from them.
 """
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -246,9 +247,27 @@ def conv_forward(src0, wpk, n_total, Co, k, pad, *, src1=None, off1=(0, 0, 0), b
     return dst0, dst1, stats
 
 
+class _WgradDefer(threading.local):
+    """per thread (nn.DataParallel replicas run in threads): the deferred split-K reductions of the backward pass in flight"""
+    jobs = None
+
+
+_wg_defer = _WgradDefer()
+
+
+def flush_wgrad():
+    """reduce the split-K partials of every wgrad() call since begin_wgrad_defer() in one launch (per 16 layers)"""
+    jobs, _wg_defer.jobs = _wg_defer.jobs, None
+    if jobs:
+        arr = (L.WgradArgs * len(jobs))(*[j[0] for j in jobs])
+        L.check(L.lib().e3b_wgrad_reduce_batched(arr, len(jobs), _stream()), 'wgrad_reduce_batched')
+
+
 def wgrad(src0, dy, Co, k, pad, dw_shape, *, src1=None, off1=(0, 0, 0), layout=0, up_taps=0, up_co=0):
     """dW of a convolution: src0 / src1 the QH activations it read, dy the (scaled) QH gradient of its output.  The kernel
-    reads the operand tensors of the forward / dgrad kernels directly (MN-major MMA operands): no extra copies."""
+    reads the operand tensors of the forward / dgrad kernels directly (MN-major MMA operands): no extra copies.
+    Inside a network backward pass (engine._backward) the split-K reduction is deferred: the returned tensor is written by
+    flush_wgrad() at the end of the pass."""
     a = L.WgradArgs()
     dev = src0.t.device
     if not (src0.half and dy.half and (src1 is None or src1.half)):
@@ -271,6 +290,9 @@ def wgrad(src0, dy, Co, k, pad, dw_shape, *, src1=None, off1=(0, 0, 0), layout=0
     a.workspace = ws.data_ptr()
     if dy.scale is not None:
         a.dy_unscale = dy.scale.data_ptr() + 8          # the gradient tensor holds 2^k * dy
+    if _wg_defer.jobs is not None:
+        a.defer_reduce = 1
+        _wg_defer.jobs.append((a, ws, dw, dy.scale))    # (keeps the workspace and the scale alive until the flush)
     L.check(L.lib().e3b_wgrad(ctypes.byref(a), _stream()), 'wgrad')
     return dw
 
@@ -1066,7 +1088,14 @@ def backward(net, tape, dlogits, need_dx):
     """-> (dict id(param) -> grad tensor, dx or None)"""
     _require_cuda(dlogits, 'grad_output')
     with torch.cuda.device(dlogits.device):
-        return _backward(net, tape, dlogits, need_dx)
+        defer = os.environ.get('E3B_WGRAD_DEFER', '1') != '0'
+        _wg_defer.jobs = [] if defer else None
+        try:
+            out = _backward(net, tape, dlogits, need_dx)
+            flush_wgrad()
+            return out
+        finally:
+            _wg_defer.jobs = None
 
 
 def _backward(net, tape, dlogits, need_dx):

@@ -159,9 +159,14 @@ typedef struct e3b_wgrad_args {
     float* workspace;
     const float* dy_unscale;                   /* optional device scalar multiplied into dw: 2^-k of the scaled gradient
                                                   tensor (e3b_norm_bwd_args.dy_scale + 2) */
+    int32_t defer_reduce;                      /* 1: leave the split-K partials in `workspace`; dw is written later by
+                                                  e3b_wgrad_reduce_batched called with the same arguments */
 } e3b_wgrad_args;
 int64_t e3b_wgrad_workspace_floats(const e3b_wgrad_args* args);
 int e3b_wgrad(const e3b_wgrad_args* args, void* stream);
+/* The split-K reductions of n deferred e3b_wgrad calls (args[i] as passed to them; workspaces still alive) in one launch per
+ * 16 layers: the weight gradients of a backward pass are only needed by the optimizer at its end. */
+int e3b_wgrad_reduce_batched(const e3b_wgrad_args* args, int n, void* stream);
 
 /* ---- normalisation + activation (+ pooling) -----------------------------------------------------
  * get_normalization (unet.py:77-111) + get_activation (:183-199) + MaxPool(ceil_mode) (:225-229).
