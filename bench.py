@@ -264,8 +264,9 @@ def main():
 
     if args.profile_predictor:
         m = e3.UNet(**PRED_MODEL_KW).to(dev).eval()
-        p = e3.Predictor(m, device=dev, tile_shape=PRED_TILE, overlap_shape=PRED_OVL, offset=(0, 0, 0), out_shape=(2, 128, 128, 128))
-        x = torch.randn(1, 1, 128, 128, 128).pin_memory()
+        vol = tuple(int(v) for v in os.environ.get('E3B_PROFILE_VOL', '128,128,128').split(','))     # '512,128,256': rows of 8 tiles
+        p = e3.Predictor(m, device=dev, tile_shape=PRED_TILE, overlap_shape=PRED_OVL, offset=(0, 0, 0), out_shape=(2,) + vol)
+        x = torch.randn((1, 1) + vol).pin_memory()
         p.predict(x), p.predict(x)
         return
 
