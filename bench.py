@@ -18,6 +18,10 @@ TF32 path (restated in oracle/torch_ref.py) timed in this process with the same 
 (67.1 M output voxels); under --gpus N the tile grid is sharded over the ranks (strong scaling) and rank 0 assembles the
 result.  It carries its own value / e2e / roofline / ref_gpu / cpu_baseline.
 
+`variants` list (N = 1): the same train step for the rows SURVEY.md section 8(f) marks "next" -- the residual U-Net
+(elektronn3.models.resunet) and two option sets of the plain one (resize-conv up-sampling + leaky ReLU; merge_mode='add' +
+SiLU) -- each next to the reference's torch/cuDNN TF32 call sequence for that model on the same GPU (--no-variants skips it).
+
 `--impl reference`: the CPU arm alone (rank 0 only under torchrun), all host threads, bounded samples.
 """
 import argparse
@@ -208,6 +212,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-ref-gpu', action='store_true')
     ap.add_argument('--no-predictor', action='store_true')
+    ap.add_argument('--no-variants', action='store_true', help='skip the resunet / option variants of the train step')
     ap.add_argument('--profile-steps', type=int, default=0,
                     help='run only this many train steps after one warm-up and exit (for ncu; prints no bench line)')
     ap.add_argument('--profile-predictor', action='store_true', help='one warm Predictor pass on a 128^3 volume and exit (for ncu)')
@@ -446,6 +451,8 @@ def main():
         line['ref_gpu'] = ref_gpu
     if predictor is not None:
         line['predictor'] = predictor
+    if world == 1 and not args.no_ref_gpu and not args.no_variants:
+        line['variants'] = variants_bench(torch, e3, dev, timed)
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_train_baseline(steps=1, warmup=1)
         line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
@@ -455,6 +462,61 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+VARIANTS = [
+    ('resunet.UNet(n_blocks=3,start_filts=32,norm=GN,enc_res_blocks=1,dec_res_blocks=1)', 'resunet',
+     dict(n_blocks=3, start_filts=32, normalization='group', enc_res_blocks=1, dec_res_blocks=1)),
+    ("UNet(n_blocks=3,start_filts=32,norm=GN,up_mode='resizeconv_nearest',activation='leaky')", 'unet',
+     dict(n_blocks=3, start_filts=32, normalization='group', up_mode='resizeconv_nearest', activation='leaky')),
+    ("UNet(n_blocks=3,start_filts=32,norm=GN,merge_mode='add',activation='silu')", 'unet',
+     dict(n_blocks=3, start_filts=32, normalization='group', merge_mode='add', activation='silu')),
+]
+
+
+def variants_bench(torch, e3, dev, timed):
+    """The rows SURVEY.md section 8(f) marks "next", measured like the headline: the cfg-2 train step (fwd + DiceLoss + bwd + SGD on
+    (4,1,64^3), device-resident batch) of the residual U-Net and of two option sets, replayed as one CUDA graph, next to the
+    reference's torch/cuDNN TF32 call sequence for the same model on the same GPU (eager, cudnn.benchmark)."""
+    from oracle import torch_ref
+    out = []
+    vox = BATCH[0] * BATCH[2] * BATCH[3] * BATCH[4]
+    tshape = (BATCH[0],) + BATCH[2:]
+    x = torch.randn(BATCH, device=dev)
+    t = torch.randint(0, 2, tshape, device=dev)
+    for name, arch, kw in VARIANTS:
+        cls = e3.resunet.UNet if arch == 'resunet' else e3.UNet
+        torch.manual_seed(99)
+        m = cls(**kw).to(dev).train()
+        opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, fused=FUSED_OPT)
+        gstep = e3.GraphedTrainStep(m, e3.DiceLoss(apply_softmax=True).to(dev), opt, BATCH, tshape)
+        for _ in range(3):
+            gstep(x, t)
+        k = 10
+        ms = timed(lambda: gstep(x, t), k) / k
+        del gstep, opt
+        old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32)
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = True, True
+        try:
+            opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, fused=FUSED_OPT)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                loss = torch_ref.dice_loss(torch_ref.unet_forward(m, x), t)
+                loss.backward()
+                opt.step()
+            for _ in range(4):
+                step()
+            k = 5
+            ms_ref = timed(step, k) / k
+        finally:
+            torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = old
+        out.append(dict(workload=f'{name} train step (fwd+DiceLoss+bwd+SGD) on synthetic {tuple(BATCH)} fp32',
+                        value=vox / ms * 1e3, unit='voxels/s', ms_per_step=ms,
+                        ref_gpu_ms_per_step=ms_ref, speedup_device=ms_ref / ms))
+        del m, opt
+        torch.cuda.empty_cache()
+    return out
 
 
 def ref_gpu_train(torch, dev, timed):
