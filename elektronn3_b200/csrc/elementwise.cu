@@ -880,7 +880,20 @@ struct FusedDev {
     int prof;
     double inv_count;                    // 1 / (elements a mean is taken over): S * C/G (group), S * N (batch)
     FastDiv dHW, dW, dwd, dwh, dww;      // GENERAL variant: voxel index -> (z, y, x) and pooling / s2d window coordinates
+    // variant 5: the pooled gradient and the arg-max slots of an item's pooling windows are staged with the item.
+    // An item then covers whole windows: co_n coarse voxels starting at coarse index item_chunk_base(chunk) of the slab.
+    int co_n;                            // coarse voxels per item (a multiple of 4, <= 128)
+    int co_ipp;                          // items per fine plane (co_mode 1), unused otherwise
+    int co_mode;                         // 1: an item is 512 / W whole rows of one plane; 2: an item is 512 / (H W) whole planes
 };
+
+// first coarse voxel (index inside the (n, quad) slab of the pooled tensor) of the windows item `chunk` covers
+E3B_DEVINL int fused_coarse_base(const NormBwdDev& p, const FusedDev& f, int chunk)
+{
+    if (f.co_mode == 2) return chunk * f.co_n;
+    const int z = chunk / f.co_ipp, y0 = (chunk - z * f.co_ipp) * (512 / p.W);
+    return ((z / p.wd) * p.Hw + y0 / p.wh) * p.Ww;
+}
 
 static constexpr int kFusedMaxCp = 512;
 static constexpr int kItemVox = 512;                         // voxels per work item (x 2 channel quads x 16 B = 16 KB per tensor)
@@ -909,15 +922,21 @@ E3B_DEVINL float4 lds128(uint32_t saddr)
 //   2: g0, space-to-depth output  (norm0 of an UpConv: dy feeds the transposed conv's GEMMs)
 //   3: un-cropped g1 + pooled gp  (last conv of an encoder block: skip gradient + un-pooling)
 //   4: anything else (cropped skip gradient of VALID nets, ...)
+//   5: as 3, with the pooled gradient and the arg-max slots staged in shared memory with the item (items that cover whole
+//      pooling windows: even extents, rows / planes that divide the item) instead of gathered per voxel through L2
 template <int VAR>
 struct FusedVar {
     static constexpr bool coords = VAR >= 2;       // voxel coordinates are needed at all
-    E3B_DEVINL static bool g0(const NormBwdDev& p) { return VAR == 4 ? p.g0 != nullptr : VAR != 3; }
-    E3B_DEVINL static bool g1_bulk(const FusedDev& f) { return VAR == 4 ? f.g1_bulk != 0 : (VAR == 1 || VAR == 3); }
+    static constexpr bool gp_staged = VAR == 5;
+    E3B_DEVINL static bool g0(const NormBwdDev& p) { return VAR == 4 ? p.g0 != nullptr : (VAR != 3 && VAR != 5); }
+    E3B_DEVINL static bool g1_bulk(const FusedDev& f) { return VAR == 4 ? f.g1_bulk != 0 : (VAR == 1 || VAR == 3 || VAR == 5); }
     E3B_DEVINL static bool g1_crop(const NormBwdDev& p, const FusedDev& f) { return VAR == 4 && p.g1 != nullptr && !f.g1_bulk; }
-    E3B_DEVINL static bool gp(const NormBwdDev& p) { return VAR == 4 ? p.gp != nullptr : VAR == 3; }
+    E3B_DEVINL static bool gp(const NormBwdDev& p) { return VAR == 4 ? p.gp != nullptr : (VAR == 3 || VAR == 5); }
     E3B_DEVINL static bool s2d(const NormBwdDev& p) { return VAR == 4 ? p.s2d != 0 : VAR == 2; }
 };
+
+// where an item's staged pooling windows sit in shared memory (this thread's channel quad) and which coarse voxel is first
+struct CoarseStage { uint32_t gp, idx; int base; };
 
 // y and the staged gradients (g0 [+ g1]) of this thread's voxel quads of one item: all loads are issued before the first use
 static constexpr int kQuadBatch = 2;                          // quads whose loads are in flight together (register budget: 96)
@@ -949,7 +968,8 @@ E3B_DEVINL void fused_load_item(const NormBwdDev& p, const FusedDev& f, uint32_t
 // voxel coordinates, and the gradients that are gathered from global memory (cropped skip gradient, un-pooling of the
 // pooled gradient; L1 / L2 hits: 8 fine voxels share one coarse voxel)
 template <int VAR>
-E3B_DEVINL void fused_gather(const NormBwdDev& p, const FusedDev& f, int n, int cq, int v, float4& g, int& z, int& yy, int& x)
+E3B_DEVINL void fused_gather(const NormBwdDev& p, const FusedDev& f, int n, int cq, int v, float4& g, int& z, int& yy, int& x,
+                             const CoarseStage& co)
 {
     z = f.dHW.div(v);
     const int r = v - z * (p.H * p.W);
@@ -965,9 +985,20 @@ E3B_DEVINL void fused_gather(const NormBwdDev& p, const FusedDev& f, int n, int 
     if (FusedVar<VAR>::gp(p)) {
         const int zw = f.dwd.div(z), yw = f.dwh.div(yy), xw = f.dww.div(x);
         const unsigned char slot = (unsigned char)(((z - zw * p.wd) * p.wh + (yy - yw * p.wh)) * p.ww + (x - xw * p.ww));
-        const size_t ow = ((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw;
-        const uchar4 idxs = p.pool_idx[ow];
-        const float4 t = p.gp[ow];
+        uchar4 idxs;
+        float4 t;
+        if (FusedVar<VAR>::gp_staged) {
+            const uint32_t local = (uint32_t)(((zw * p.Hw + yw) * p.Ww + xw) - co.base);
+            uint32_t raw;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(co.idx + local * 4u));
+            idxs = make_uchar4((unsigned char)(raw & 255u), (unsigned char)((raw >> 8) & 255u), (unsigned char)((raw >> 16) & 255u),
+                               (unsigned char)(raw >> 24));
+            t = lds128(co.gp + local * 16u);
+        } else {
+            const size_t ow = ((((size_t)n * p.Cq + cq) * p.Dw + zw) * p.Hw + yw) * p.Ww + xw;
+            idxs = p.pool_idx[ow];
+            t = p.gp[ow];
+        }
         if (idxs.x == slot) g.x += t.x;
         if (idxs.y == slot) g.y += t.y;
         if (idxs.z == slot) g.z += t.z;
@@ -992,7 +1023,7 @@ E3B_DEVINL void fused_mask_xhat(const QuadConsts& c, const float4& yv, float4& g
 template <int VAR, bool FULL>
 E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32_t sbase, uint32_t off_g0, uint32_t off_g1,
                                   const QuadConsts& c, int t128, int n, int cq, int v0, int nv, float* s1, float* s2, float* md,
-                                  float* mx)
+                                  float* mx, const CoarseStage& co)
 {
 #pragma unroll
     for (int k0 = 0; k0 < kQuadsPerThread; k0 += kQuadBatch) {
@@ -1003,7 +1034,7 @@ E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32
         const int vl = (k0 + kk) * 128 + t128;
         if (!FULL && vl >= nv) continue;
         float4 dr = G[kk], xh;
-        if (FusedVar<VAR>::coords) { int z, yy, x; fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x); }
+        if (FusedVar<VAR>::coords) { int z, yy, x; fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x, co); }
         fused_mask_xhat(c, Y[kk], dr, xh);
         s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
         s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]); s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
@@ -1019,7 +1050,7 @@ E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32
 template <int VAR, bool FULL>
 E3B_DEVINL void fused_item_apply(const NormBwdDev& p, const FusedDev& f, uint32_t sbase, uint32_t off_g0, uint32_t off_g1,
                                  const QuadConsts& c, const float4& ga, const float4& m1, const float4& m2, const float4& rk, int hsel,
-                                 int t128, int n, int cqp, int Cqp, int total, int v0, int nv, uint2* dy)
+                                 int t128, int n, int cqp, int Cqp, int total, int v0, int nv, uint2* dy, const CoarseStage& co)
 {
     const int cq = 2 * cqp + hsel;
     // this thread's 8-byte half of its first voxel's unit; the other quads follow at 128 voxels = 2 KB
@@ -1034,7 +1065,7 @@ E3B_DEVINL void fused_item_apply(const NormBwdDev& p, const FusedDev& f, uint32_
         if (!FULL && vl >= nv) continue;
         float4 dr = G[kk], xh;
         int z = 0, yy = 0, x = 0;
-        if (FusedVar<VAR>::coords) fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x);
+        if (FusedVar<VAR>::coords) fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x, co);
         fused_mask_xhat(c, Y[kk], dr, xh);
         // rstd * 2^k is folded into rk: o = rk * (ga * dr - m1 - xh * m2)
         const uint2 o = pack_half4(rk.x * fmaf(-xh.x, m2.x, fmaf(ga.x, dr.x, -m1.x)), rk.y * fmaf(-xh.y, m2.y, fmaf(ga.y, dr.y, -m1.y)),
@@ -1072,7 +1103,10 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
     const int Cp = f.Cp, S = f.stages;
     const bool has_g0 = FusedVar<VAR>::g0(p), g1_bulk = FusedVar<VAR>::g1_bulk(f);
     const int nb = 1 + (has_g0 ? 1 : 0) + (g1_bulk ? 1 : 0);
-    const uint32_t stage_bytes = nb * kItemTensorBytes;
+    // variant 5: behind the fine tensors, per channel quad the item's pooled gradient (16 B per coarse voxel), then its slots (4 B)
+    const uint32_t co_gp_bytes = FusedVar<VAR>::gp_staged ? (uint32_t)f.co_n * 16u : 0u, co_idx_bytes = FusedVar<VAR>::gp_staged ? (uint32_t)f.co_n * 4u : 0u;
+    const uint32_t off_cgp = nb * kItemTensorBytes, off_cidx = off_cgp + 2 * co_gp_bytes;
+    const uint32_t stage_bytes = nb * kItemTensorBytes + 2 * (co_gp_bytes + co_idx_bytes);
     const uint32_t off_g0 = kItemTensorBytes, off_g1 = (has_g0 ? 2 : 1) * kItemTensorBytes;
     const long long items = (long long)nset * Cqp * nchunks;                   // < 2^31 (checked by the launch wrapper)
     const int i0 = (int)(items * blockIdx.x / gridDim.x), i1 = (int)(items * (blockIdx.x + 1) / gridDim.x);
@@ -1094,13 +1128,19 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
             const int v0 = chunk * kItemVox;
             const uint32_t bytes = (uint32_t)min(kItemVox, total - v0) * 16u;
             unsigned char* dst = ring + (size_t)s * stage_bytes;
-            mbar_arrive_expect_tx(&full[s], 2 * nb * bytes);
+            mbar_arrive_expect_tx(&full[s], 2 * nb * bytes + 2 * (co_gp_bytes + co_idx_bytes));
+            const size_t cbase = FusedVar<VAR>::gp_staged ? (size_t)fused_coarse_base(p, f, chunk) : 0;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const size_t off = ((size_t)n * p.Cq + 2 * cqp + h) * (size_t)total + v0;
                 bulk_load_1d(dst + h * (kItemVox * 16), p.y + off, bytes, &full[s]);
                 if (has_g0) bulk_load_1d(dst + off_g0 + h * (kItemVox * 16), p.g0 + off, bytes, &full[s]);
                 if (g1_bulk) bulk_load_1d(dst + off_g1 + h * (kItemVox * 16), p.g1 + off, bytes, &full[s]);
+                if (FusedVar<VAR>::gp_staged) {
+                    const size_t coff = ((size_t)n * p.Cq + 2 * cqp + h) * ((size_t)p.Dw * p.Hw * p.Ww) + cbase;
+                    bulk_load_1d(dst + off_cgp + h * co_gp_bytes, p.gp + coff, co_gp_bytes, &full[s]);
+                    bulk_load_1d(dst + off_cidx + h * co_idx_bytes, p.pool_idx + coff, co_idx_bytes, &full[s]);
+                }
             }
         };
         uint32_t eparity = 0;                         // bit s: the phase of empty[s] the next refill of stage s waits for
@@ -1122,7 +1162,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
     }
     // ---------------- consumers (256 threads; they synchronise among themselves on a named barrier)
     const int hsel = warp >> 2, t128 = threadIdx.x & 127;
-    const uint32_t ring_thread = smem_u32(ring) + (uint32_t)(hsel * kItemVox + t128) * 16u;     // this thread's first voxel quad of stage 0
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t ring_thread = ring_u32 + (uint32_t)(hsel * kItemVox + t128) * 16u;     // this thread's first voxel quad of stage 0
     const float act_slope = p.relu ? p.slope : 1.f;
     uint32_t parity = 0;                              // bit s: the phase of full[s] the next wait on stage s is for
     float dscale = 0.f;                               // the tensor's fp16 scale so far (0: none yet); identical in every CTA
@@ -1229,8 +1270,12 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                 if (prof_on) wait_a += globaltimer_ns() - tw;
                 parity ^= 1u << s;
                 const uint32_t sbase = ring_thread + (uint32_t)s * stage_bytes;
-                if (nv == kItemVox) fused_item_reduce<VAR, true>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx);
-                else fused_item_reduce<VAR, false>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx);
+                CoarseStage co;
+                co.gp = ring_u32 + (uint32_t)s * stage_bytes + off_cgp + (uint32_t)hsel * co_gp_bytes;
+                co.idx = ring_u32 + (uint32_t)s * stage_bytes + off_cidx + (uint32_t)hsel * co_idx_bytes;
+                co.base = FusedVar<VAR>::gp_staged ? fused_coarse_base(p, f, chunk) : 0;
+                if (nv == kItemVox) fused_item_reduce<VAR, true>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx, co);
+                else fused_item_reduce<VAR, false>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx, co);
                 if (j + S < cnt) {                    // this warp is done with stage s: the producer may refill it
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
@@ -1402,8 +1447,12 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                     parity ^= 1u << s;
                 }
                 const uint32_t sbase = ring_thread + (uint32_t)s * stage_bytes;
-                if (nv == kItemVox) fused_item_apply<VAR, true>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy);
-                else fused_item_apply<VAR, false>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy);
+                CoarseStage co;
+                co.gp = ring_u32 + (uint32_t)s * stage_bytes + off_cgp + (uint32_t)hsel * co_gp_bytes;
+                co.idx = ring_u32 + (uint32_t)s * stage_bytes + off_cidx + (uint32_t)hsel * co_idx_bytes;
+                co.base = FusedVar<VAR>::gp_staged ? fused_coarse_base(p, f, chunk) : 0;
+                if (nv == kItemVox) fused_item_apply<VAR, true>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy, co);
+                else fused_item_apply<VAR, false>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy, co);
                 if (j - S >= 0 || round + 1 < nrounds) {                      // the producer refills this stage
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
@@ -1990,16 +2039,30 @@ int e3b_norm_bwd_fused(const e3b_norm_bwd_args* a, void* stream)
     if (p.g0 && !p.gp && !p.g1_crop && !p.s2d) var = f.g1_bulk ? 1 : 0;
     else if (p.g0 && !p.g1 && !p.gp && p.s2d) var = 2;
     else if (!p.g0 && f.g1_bulk && p.gp && !p.s2d) var = 3;
+    f.co_n = 0; f.co_ipp = 1; f.co_mode = 0;
+    if (var == 3 && !getenv("E3B_FUSED_NO_STAGED_POOL")) {
+        // can an item (512 consecutive voxels) be made of whole pooling windows whose coarse voxels are contiguous?
+        const int HW = p.H * p.W;
+        const bool even = p.D % p.wd == 0 && p.H % p.wh == 0 && p.W % p.ww == 0 && p.W % 8 == 0;
+        if (even && HW % kItemVox == 0 && kItemVox % p.W == 0 && (kItemVox / p.W) % p.wh == 0 && p.wd <= 2) {
+            f.co_mode = 1; f.co_ipp = HW / kItemVox; f.co_n = (kItemVox / p.W / p.wh) * p.Ww;
+        } else if (even && kItemVox % HW == 0 && (kItemVox / HW) % p.wd == 0 && p.D % (kItemVox / HW) == 0) {
+            f.co_mode = 2; f.co_n = (kItemVox / HW / p.wd) * p.Hw * p.Ww;
+        }
+        if (f.co_mode && (f.co_n % 4 || f.co_n > 128 || f.co_n < 4)) f.co_mode = 0;
+        if (f.co_mode) var = 5;
+    }
     const int nb = 1 + (p.g0 != nullptr) + f.g1_bulk;
     const int kRingBytes = 96 * 1024;               // two CTAs per SM
-    f.stages = kRingBytes / (nb * kItemTensorBytes);
+    const size_t stage_bytes = (size_t)nb * kItemTensorBytes + (var == 5 ? (size_t)2 * f.co_n * 20 : 0);
+    f.stages = (int)(kRingBytes / stage_bytes);
     if (f.stages > kFusedMaxStages) f.stages = kFusedMaxStages;
-    const size_t smem = (size_t)f.stages * nb * kItemTensorBytes;
+    const size_t smem = (size_t)f.stages * stage_bytes;
     typedef void (*FusedKernel)(const NormBwdDev, const FusedDev);
-    static const FusedKernel kernels[5] = {norm_bwd_fused_kernel<0>, norm_bwd_fused_kernel<1>, norm_bwd_fused_kernel<2>,
-                                           norm_bwd_fused_kernel<3>, norm_bwd_fused_kernel<4>};
+    static const FusedKernel kernels[6] = {norm_bwd_fused_kernel<0>, norm_bwd_fused_kernel<1>, norm_bwd_fused_kernel<2>,
+                                           norm_bwd_fused_kernel<3>, norm_bwd_fused_kernel<4>, norm_bwd_fused_kernel<5>};
     const FusedKernel kern = kernels[var];
-    static int per_sm[kMaxDevices][5][4] = {};
+    static int per_sm[kMaxDevices][6][4] = {};
     const int dev = current_device();
     if (!per_sm[dev][var][nb]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes) != cudaSuccess)

@@ -487,11 +487,17 @@ def test_norm_act_pool_forward_backward(eng, monkeypatch, mode, G, C, sp, pool, 
     assert (dbias.double() - ref_dbias).abs().max().item() / scale < 1e-4
 
 
-@pytest.mark.parametrize('pool,direct', [(None, True), ((2, 2, 2), True), ((2, 2, 2), False)])
-def test_norm_backward_direct_plus_skip_gradient(eng, pool, direct):
+@pytest.mark.parametrize('pool,direct,sp', [(None, True, (4, 6, 8)), ((2, 2, 2), True, (4, 6, 8)), ((2, 2, 2), False, (4, 6, 8)),
+                                            # skip + pooled gradient on items made of whole pooling windows (variant 5: the
+                                            # pooled gradient and the slots are staged with the item): rows of one plane
+                                            # (H W = 512 and 1024), whole planes (H W = 128), planar pooling
+                                            ((2, 2, 2), False, (4, 16, 32)), ((2, 2, 2), False, (2, 32, 32)),
+                                            ((2, 2, 2), False, (8, 8, 16)), ((1, 2, 2), False, (3, 16, 32)),
+                                            ((2, 2, 2), False, (4, 64, 64))])
+def test_norm_backward_direct_plus_skip_gradient(eng, pool, direct, sp):
     """two un-cropped gradients on the same activation (g0 + g1: the fused kernel's variant 1; with a pooled gradient on
-    top: the run-time variant; skip + pooled gradient without a direct one: variant 3, the encoder's last conv)"""
-    N, C, G, sp = 2, 16, 4, (4, 6, 8)
+    top: the run-time variant; skip + pooled gradient without a direct one: variant 3 / 5, the encoder's last conv)"""
+    N, C, G = 2, 16, 4
     rs = np.random.RandomState(77)
     y = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
     gamma = torch.from_numpy((1 + 0.2 * rs.standard_normal(C)).astype(np.float32)).cuda()
