@@ -1,5 +1,6 @@
 #!/bin/bash
-# scratch visit: variant 5 of the fused norm backward
+# Same-box A/B of the fused norm backward with the un-pooling inputs staged with the item (FusedVar<5>, default) against the
+# per-voxel L2 gathers (E3B_FUSED_NO_STAGED_POOL=1): kernel tests, then the train-step bench line twice each.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_ops_gpu.py -m gpu -q --tb=short --timeout 120 -k "direct_plus_skip or norm_act_pool" 2>&1 | tail -6
