@@ -936,7 +936,23 @@ struct FusedVar {
 };
 
 // where an item's staged pooling windows sit in shared memory (this thread's channel quad) and which coarse voxel is first
-struct CoarseStage { uint32_t gp, idx; int base; };
+// (variant 5: an item is aligned to the pooling windows, so which coarse voxel and which window slot a thread's k-th voxel
+// of an item belongs to is the same for every item: tab[k] = local coarse index << 8 | slot inside the plane pair; zslot adds
+// the item's z parity)
+struct CoarseStage { uint32_t gp, idx; int base; int zslot; int tab[4]; };
+
+E3B_DEVINL void fused_unpool_staged(const CoarseStage& co, int k, float4& g)
+{
+    const uint32_t e = (uint32_t)co.tab[k];
+    const uint32_t local = e >> 8, slot = (e & 255u) + (uint32_t)co.zslot;
+    uint32_t raw;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(co.idx + local * 4u));
+    const float4 t = lds128(co.gp + local * 16u);
+    if ((raw & 255u) == slot) g.x += t.x;
+    if (((raw >> 8) & 255u) == slot) g.y += t.y;
+    if (((raw >> 16) & 255u) == slot) g.z += t.z;
+    if ((raw >> 24) == slot) g.w += t.w;
+}
 
 // y and the staged gradients (g0 [+ g1]) of this thread's voxel quads of one item: all loads are issued before the first use
 static constexpr int kQuadBatch = 2;                          // quads whose loads are in flight together (register budget: 96)
@@ -1034,7 +1050,8 @@ E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32
         const int vl = (k0 + kk) * 128 + t128;
         if (!FULL && vl >= nv) continue;
         float4 dr = G[kk], xh;
-        if (FusedVar<VAR>::coords) { int z, yy, x; fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x, co); }
+        if (FusedVar<VAR>::gp_staged) fused_unpool_staged(co, k0 + kk, dr);
+        else if (FusedVar<VAR>::coords) { int z, yy, x; fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x, co); }
         fused_mask_xhat(c, Y[kk], dr, xh);
         s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
         s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]); s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
@@ -1065,7 +1082,8 @@ E3B_DEVINL void fused_item_apply(const NormBwdDev& p, const FusedDev& f, uint32_
         if (!FULL && vl >= nv) continue;
         float4 dr = G[kk], xh;
         int z = 0, yy = 0, x = 0;
-        if (FusedVar<VAR>::coords) fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x, co);
+        if (FusedVar<VAR>::gp_staged) fused_unpool_staged(co, k0 + kk, dr);
+        else if (FusedVar<VAR>::coords) fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x, co);
         fused_mask_xhat(c, Y[kk], dr, xh);
         // rstd * 2^k is folded into rk: o = rk * (ga * dr - m1 - xh * m2)
         const uint2 o = pack_half4(rk.x * fmaf(-xh.x, m2.x, fmaf(ga.x, dr.x, -m1.x)), rk.y * fmaf(-xh.y, m2.y, fmaf(ga.y, dr.y, -m1.y)),
@@ -1165,6 +1183,19 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
     const uint32_t ring_u32 = smem_u32(ring);
     const uint32_t ring_thread = ring_u32 + (uint32_t)(hsel * kItemVox + t128) * 16u;     // this thread's first voxel quad of stage 0
     const float act_slope = p.relu ? p.slope : 1.f;
+    int co_tab[4] = {0, 0, 0, 0};
+    if (FusedVar<VAR>::gp_staged) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int vl = k * 128 + t128;
+            int pz = 0, r = vl;
+            if (f.co_mode == 2) { pz = vl / (p.H * p.W); r = vl - pz * (p.H * p.W); }
+            const int row = r / p.W, x = r - row * p.W;
+            const int local = ((pz / p.wd) * p.Hw + row / p.wh) * p.Ww + x / p.ww;
+            const int slot = ((f.co_mode == 2 ? pz % p.wd : 0) * p.wh + row % p.wh) * p.ww + x % p.ww;
+            co_tab[k] = (local << 8) | slot;
+        }
+    }
     uint32_t parity = 0;                              // bit s: the phase of full[s] the next wait on stage s is for
     float dscale = 0.f;                               // the tensor's fp16 scale so far (0: none yet); identical in every CTA
     float bound_max = 0.f;
@@ -1273,7 +1304,10 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                 CoarseStage co;
                 co.gp = ring_u32 + (uint32_t)s * stage_bytes + off_cgp + (uint32_t)hsel * co_gp_bytes;
                 co.idx = ring_u32 + (uint32_t)s * stage_bytes + off_cidx + (uint32_t)hsel * co_idx_bytes;
-                co.base = FusedVar<VAR>::gp_staged ? fused_coarse_base(p, f, chunk) : 0;
+                co.base = 0;
+                co.zslot = (FusedVar<VAR>::gp_staged && f.co_mode == 1) ? ((chunk / f.co_ipp) % p.wd) * (p.wh * p.ww) : 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) co.tab[k] = co_tab[k];
                 if (nv == kItemVox) fused_item_reduce<VAR, true>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx, co);
                 else fused_item_reduce<VAR, false>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx, co);
                 if (j + S < cnt) {                    // this warp is done with stage s: the producer may refill it
@@ -1450,7 +1484,10 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                 CoarseStage co;
                 co.gp = ring_u32 + (uint32_t)s * stage_bytes + off_cgp + (uint32_t)hsel * co_gp_bytes;
                 co.idx = ring_u32 + (uint32_t)s * stage_bytes + off_cidx + (uint32_t)hsel * co_idx_bytes;
-                co.base = FusedVar<VAR>::gp_staged ? fused_coarse_base(p, f, chunk) : 0;
+                co.base = 0;
+                co.zslot = (FusedVar<VAR>::gp_staged && f.co_mode == 1) ? ((chunk / f.co_ipp) % p.wd) * (p.wh * p.ww) : 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) co.tab[k] = co_tab[k];
                 if (nv == kItemVox) fused_item_apply<VAR, true>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy, co);
                 else fused_item_apply<VAR, false>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy, co);
                 if (j - S >= 0 || round + 1 < nrounds) {                      // the producer refills this stage
