@@ -501,3 +501,19 @@ def test_options_at_baseline_widths_within_tf32_noise(e3, arch, kw, shape):
     for (k, p), (_, q) in zip(m.named_parameters(), m0.named_parameters()):
         q.grad = p.grad
     grads_within_tf32_noise(m0, x, g)
+
+
+def test_resunet_odd_shapes_train(e3):
+    """residual blocks with ceil-mode pooling + autocrop in training: the projection shortcut of the decoder reads the
+    centre-cropped skip tensor (forward, weight gradient and both data gradients through the crop)"""
+    torch.manual_seed(23)
+    m = e3.resunet.UNet(n_blocks=3, start_filts=8, normalization='group', enc_res_blocks=2, dec_res_blocks=2).cuda().train()
+    x = torch.randn(1, 1, 11, 13, 18, device='cuda')
+    out = m(x)
+    out.square().mean().backward()
+    mref = copy.deepcopy(m)
+    mref.zero_grad()
+    o32 = ref32(mref, x)
+    o32.square().mean().backward()
+    assert rel(out.detach(), o32.detach()) < 6e-3
+    grads_close(m, mref)
