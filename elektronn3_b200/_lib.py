@@ -76,6 +76,7 @@ class NormBwdArgs(ctypes.Structure):
         ('g1_crop', c_i32),
         ('g1_od', c_i32), ('g1_oh', c_i32), ('g1_ow', c_i32), ('g1_D', c_i32), ('g1_H', c_i32), ('g1_W', c_i32),
         ('act_slope', c_float),
+        ('act_slope_dev', c_void_p), ('slope_sums', c_void_p), ('dslope', c_void_p),
     ]
 
 
@@ -135,7 +136,7 @@ SIGNATURES = {
     'e3b_wgrad_reduce_batched': (c_int, [ctypes.POINTER(WgradArgs), c_int, c_void_p]),
     'e3b_norm_finalize': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_i64, c_void_p, c_void_p, c_float,
                                   c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    'e3b_norm_act': (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_float, c_int, c_void_p]),
+    'e3b_norm_act': (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_float, c_void_p, c_int, c_void_p]),
     'e3b_norm_bwd_fused': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_reduce': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_finalize': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),

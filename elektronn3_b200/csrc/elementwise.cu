@@ -277,6 +277,7 @@ struct NormActDev {
     uchar4* pool_idx;
     int C, N, Cq, Ch, D, H, W, pkd, pkh, pkw, relu;
     float slope;                 // activation code / negative slope, see act_fwd
+    const float* slope_dev;      // nn.PReLU: the (learned) negative slope lives in device memory
     int Dp, Hp, Wp;
 };
 
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
     float4 sc, sh;
     load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
     const size_t base = ((size_t)n * p.Cq + cq) * (size_t)S;
+    const float slope = p.slope_dev ? __ldg(p.slope_dev) : p.slope;
     float4 yv[kVpt];
 #pragma unroll
     for (int j = 0; j < kVpt; j++) {
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
     for (int j = 0; j < kVpt; j++) {
         const int v = v0 + j * 256;
         if (v >= S) continue;
-        const float4 r = norm_relu_round(yv[j], sc, sh, p.scale != nullptr, p.relu, p.slope);
+        const float4 r = norm_relu_round(yv[j], sc, sh, p.scale != nullptr, p.relu, slope);
         if (p.a) store_qh(p.a, r, n, p.Ch, cq, (size_t)S, (size_t)v);
     }
 }
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
     load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
     const size_t base = ((size_t)n * p.Cq + cq) * p.D;
     const size_t S = (size_t)p.D * p.H * p.W;
+    const float slope = p.slope_dev ? __ldg(p.slope_dev) : p.slope;
     float4 m = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
     uchar4 idx = make_uchar4(0, 0, 0, 0);
 #pragma unroll
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
                 const size_t vox = ((size_t)z * p.H + yy) * p.W + x;
                 float4 v;
                 if (p.yh) v = unpack_half4(p.yh[qh_index(n, p.Ch, cq, S, vox)]);
-                else v = norm_relu_round(p.y[base * p.H * p.W + vox], sc, sh, p.scale != nullptr, p.relu, p.slope);
+                else v = norm_relu_round(p.y[base * p.H * p.W + vox], sc, sh, p.scale != nullptr, p.relu, slope);
                 if (p.a) store_qh(p.a, v, n, p.Ch, cq, S, vox);
                 const unsigned char slot = (unsigned char)((dz * p.pkh + dy) * p.pkw + dx);
                 if (v.x > m.x) { m.x = v.x; idx.x = slot; }
@@ -407,6 +410,8 @@ struct NormBwdDev {
     int Dg, Hg, Wg;                          // extents of the thread grid (s2d: the un-cropped fine grid)
     int relu, s2d;
     float slope;                             // activation code / negative slope, see act_fwd
+    const float* slope_dev;                  // nn.PReLU: the slope in device memory (three-kernel path only)
+    double* slope_sums;                      // [N][pad8(C)] sum over z <= 0 of g * z: the slope's gradient (reduce pass)
     const float *gamma, *mean, *rstd, *m1, *m2;
     double* sums;
     unsigned int* amax;                      // [N][pad8(C)][2] max |dr|, max |xhat| (float bits; reduce pass)
@@ -472,7 +477,7 @@ E3B_DEVINL void load_vox(const NormBwdDev& p, size_t o, int n, int cq, int z, in
 // z is recomputed bit-exactly from y (the arithmetic of norm_act_kernel), never read.
 template <bool GENERAL = true>
 E3B_DEVINL void voxel_grad(const NormBwdDev& p, const VoxIn& in, const float4& mu, const float4& rs, const float4& sc,
-                           const float4& sh, float4& dr, float4& xh)
+                           const float4& sh, float4& dr, float4& xh, float slope, float4* gz = nullptr)
 {
     const float4 yv = in.y;
     const float4 zv = norm_affine(yv, sc, sh, p.scale != nullptr);       // the pre-activation, recomputed as the forward did
@@ -486,8 +491,11 @@ E3B_DEVINL void voxel_grad(const NormBwdDev& p, const VoxIn& in, const float4& m
         if (in.idx.z == in.slot) g.z += in.gp.z;
         if (in.idx.w == in.slot) g.w += in.gp.w;
     }
-    g.x = act_bwd(zv.x, g.x, p.relu, p.slope); g.y = act_bwd(zv.y, g.y, p.relu, p.slope);
-    g.z = act_bwd(zv.z, g.z, p.relu, p.slope); g.w = act_bwd(zv.w, g.w, p.relu, p.slope);
+    if (gz)      // d a / d slope = z where z <= 0 (nn.PReLU)
+        *gz = make_float4(zv.x > 0.f ? 0.f : g.x * zv.x, zv.y > 0.f ? 0.f : g.y * zv.y, zv.z > 0.f ? 0.f : g.z * zv.z,
+                          zv.w > 0.f ? 0.f : g.w * zv.w);
+    g.x = act_bwd(zv.x, g.x, p.relu, slope); g.y = act_bwd(zv.y, g.y, p.relu, slope);
+    g.z = act_bwd(zv.z, g.z, p.relu, slope); g.w = act_bwd(zv.w, g.w, p.relu, slope);
     dr = g;
 }
 
@@ -503,6 +511,8 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p
     const int HW = p.H * p.W;
     const int total = p.D * HW;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float s3 = 0.f;                                          // nn.PReLU: sum over z <= 0 of g * z (all four channels)
+    const float slope = p.slope_dev ? __ldg(p.slope_dev) : p.slope;
     float md[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};       // max |dr|, max |xhat|: bound for the fp16 scale of dy
     const size_t base = ((size_t)n * p.Cq + cq) * (size_t)total;
     const int stride = gridDim.x * blockDim.x;
@@ -519,8 +529,9 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p
 #pragma unroll
         for (int j = 0; j < kRedVpt; j++) {
             if (v0 + j * stride >= total) continue;
-            float4 dr, xh;
-            voxel_grad(p, in[j], mu, rs, sc, sh, dr, xh);
+            float4 dr, xh, gz;
+            voxel_grad(p, in[j], mu, rs, sc, sh, dr, xh, slope, p.slope_sums ? &gz : nullptr);
+            if (p.slope_sums) s3 += (gz.x + gz.y) + (gz.z + gz.w);
             s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
             s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]);
             s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
@@ -557,6 +568,32 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdDev p
         if (!(t < 3.0e38f)) t = 3.0e38f;                     // inf / nan: the scale falls back to 1
         atomicMax(p.amax + (nc + j) * 2 + which, __float_as_uint(t));   // non-negative floats order like their bits
     }
+    if (p.slope_sums) {                       // (block-uniform; the shared buffer is free again after this barrier)
+        __syncthreads();
+        for (int o = 16; o > 0; o >>= 1) s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+        if (lane == 0) red[warp][0] = s3;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += (double)red[w][0];
+            atomicAdd(p.slope_sums + nc, t);
+        }
+    }
+}
+
+// nn.PReLU: the slope's gradient = the sum of the per-(n, channel quad) partial sums
+__global__ void prelu_finalize_kernel(const double* __restrict__ slope_sums, int n, float* __restrict__ dslope)
+{
+    __shared__ double red[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) t += slope_sums[i];
+    red[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) dslope[0] = (float)red[0];
 }
 
 __global__ void norm_bwd_finalize_kernel(const double* __restrict__ sums, const double* __restrict__ fwd_stats, int mode,
@@ -737,7 +774,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdDev p)
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (inside) {
             float4 dr, xh;
-            voxel_grad(p, in[j], mu, rs, sc, sh, dr, xh);
+            voxel_grad(p, in[j], mu, rs, sc, sh, dr, xh, p.slope_dev ? __ldg(p.slope_dev) : p.slope);
             o.x = rs.x * (ga.x * dr.x - m1.x - xh.x * m2.x);
             o.y = rs.y * (ga.y * dr.y - m1.y - xh.y * m2.y);
             o.z = rs.z * (ga.z * dr.z - m1.z - xh.z * m2.z);
@@ -818,7 +855,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_x4_kernel(const NormBwdDev
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         float4 dr, xh;
-        voxel_grad(p, in[j], c.mu, c.rs, c.sc, c.sh, dr, xh);
+        voxel_grad(p, in[j], c.mu, c.rs, c.sc, c.sh, dr, xh, p.slope_dev ? __ldg(p.slope_dev) : p.slope);
         const float4 o = apply_formula(dr, xh, c.rs, c.ga, c.m1, c.m2);
         const float4 os = make_float4(o.x * dscale, o.y * dscale, o.z * dscale, o.w * dscale);
         store_qh(p.dy, os, n, p.Ch, cq, (size_t)p.D * p.H * p.W, (size_t)row * p.W + x0 + j);
@@ -1915,9 +1952,11 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
 }
 
 int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled, uint8_t* pool_idx, int N, int C,
-                 int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, float act_slope, int y_is_half, void* stream)
+                 int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, float act_slope, const float* act_slope_dev, int y_is_half,
+                 void* stream)
 {
     if (relu < 0 || relu > 2) return set_error("norm_act: unknown activation code %d", relu);
+    if (act_slope_dev && relu != 1) return set_error("norm_act: a device-resident slope belongs to activation code 1");
     const bool pooling = pooled || pool_idx;
     if (y_is_half && (!pooling || scale || a)) return set_error("norm_act: an fp16 input is only pooled (eval path)");
     if (!pooling) { pk_d = pk_h = pk_w = 1; }
@@ -1928,7 +1967,7 @@ int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a,
     p.yh = y_is_half ? reinterpret_cast<const uint2*>(y) : nullptr;
     p.a = reinterpret_cast<uint2*>(a); p.pooled = reinterpret_cast<uint2*>(pooled);
     p.pool_idx = reinterpret_cast<uchar4*>(pool_idx);
-    p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu; p.slope = act_slope;
+    p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu; p.slope = act_slope; p.slope_dev = act_slope_dev;
     p.Dp = (D + pk_d - 1) / pk_d; p.Hp = (H + pk_h - 1) / pk_h; p.Wp = (W + pk_w - 1) / pk_w;
     if (p.Cq > 65535 || N > 65535) return set_error("norm_act: too many channels / samples for the launch grid");
     if (pooling) {
@@ -1962,6 +2001,9 @@ static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)
     if (a->s2d) { p.Dg = p.Dw * p.wd; p.Hg = p.Hw * p.wh; p.Wg = p.Ww * p.ww; }
     if (a->relu < 0 || a->relu > 2) return set_error("norm_bwd: unknown activation code %d", a->relu);
     p.relu = a->relu; p.slope = a->act_slope; p.s2d = a->s2d;
+    p.slope_dev = a->act_slope_dev; p.slope_sums = a->slope_sums;
+    if (a->act_slope_dev && a->relu != 1) return set_error("norm_bwd: a device-resident slope belongs to activation code 1");
+    if (a->dslope && !a->slope_sums) return set_error("norm_bwd: dslope needs the slope_sums workspace");
     p.gamma = (a->mode == 0) ? nullptr : a->gamma;
     p.mean = a->mean; p.rstd = a->rstd; p.m1 = a->m1; p.m2 = a->m2;
     p.sums = a->sums; p.dy = reinterpret_cast<uint2*>(a->dy);
@@ -1992,6 +2034,7 @@ int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* a, void* stream)
         if (e == cudaSuccess) e = cudaMemsetAsync(a->amax, 0, amax_b, (cudaStream_t)stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(a->dy_scale, 0, sizeof(float) * 4, (cudaStream_t)stream);
     }
+    if (e == cudaSuccess && a->slope_sums) e = cudaMemsetAsync(a->slope_sums, 0, sizeof(double) * (size_t)a->N * Cp, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error("memset: %s", cudaGetErrorString(e));
     const size_t vox = (size_t)p.D * p.H * p.W;
     int bx = (int)((vox + 256 * kRedVpt - 1) / (256 * kRedVpt));
@@ -2007,6 +2050,11 @@ int e3b_norm_bwd_finalize(const e3b_norm_bwd_args* a, void* stream)
     if (a->mode == 1 && (a->G <= 0 || a->C % a->G)) return set_error("norm_bwd: bad group count");
     if (a->dbias && (a->mode == 1 || a->mode == 2) && !a->fwd_stats) return set_error("norm_bwd: dbias needs fwd_stats");
     const int nt = a->N * Cp;
+    if (a->dslope) {
+        if (!a->slope_sums) return set_error("norm_bwd: dslope needs the slope_sums workspace");
+        prelu_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a->slope_sums, nt, a->dslope);
+        if (check_launch("prelu_finalize")) return 1;
+    }
     if (nt <= 1024) {
         const int threads = (nt + 31) & ~31;
         norm_bwd_finalize_block_kernel<<<1, threads, sizeof(double) * 3 * (size_t)nt, (cudaStream_t)stream>>>(
@@ -2044,6 +2092,7 @@ int e3b_norm_bwd_fused(const e3b_norm_bwd_args* a, void* stream)
     const int Cp = p.Cq * 4;
     if (!a->amax || !a->dy_scale || !a->sums) return set_error("norm_bwd_fused: sums / amax / dy_scale buffers are required");
     if (a->relu == 2) return set_error("norm_bwd_fused: SiLU is served by the reduce / finalize / apply kernels");
+    if (a->act_slope_dev || a->dslope) return set_error("norm_bwd_fused: nn.PReLU is served by the reduce / finalize / apply kernels");
     if (Cp > kFusedMaxCp) return set_error("norm_bwd_fused: more than %d channels: use the reduce / finalize / apply kernels", kFusedMaxCp);
     if (a->mode == 1 && (a->G <= 0 || a->C % a->G)) return set_error("norm_bwd: bad group count");
     if (a->dbias && (a->mode == 1 || a->mode == 2) && !a->fwd_stats) return set_error("norm_bwd: dbias needs fwd_stats");

@@ -316,26 +316,31 @@ def norm_finalize(stats, mode, G, N, C, S, gamma, beta, eps, rm, rv, momentum, d
     return st
 
 
-ACT_RELU = (1, 0.0)
+ACT_RELU = (1, 0.0, None)
 
 
 def act_code(act, training):
-    """-> (code, negative slope) as the kernels take them (include/e3b.h) for an activation module produced by
-    get_activation (models/unet.py:183-199): 'relu', 'leaky', 'rrelu' (eval mode), 'silu', 'lin' or a module of those types."""
+    """-> (code, negative slope, slope parameter or None) as the kernels take them (include/e3b.h) for an activation module
+    produced by get_activation (models/unet.py:183-199): 'relu', 'leaky', 'prelu', 'rrelu' (eval mode), 'silu', 'lin' or a
+    module of those types.  nn.PReLU's learned slope stays in device memory (third entry: the parameter)."""
     import torch.nn as nn
     if act is None or isinstance(act, nn.ReLU):
         return ACT_RELU
     if isinstance(act, nn.Identity):
-        return (0, 0.0)
+        return (0, 0.0, None)
     if isinstance(act, nn.LeakyReLU):
-        return (1, float(act.negative_slope))
+        return (1, float(act.negative_slope), None)
+    if isinstance(act, nn.PReLU):
+        if act.weight.numel() != 1:
+            raise NotImplementedError('nn.PReLU with one slope per channel is not on the B200 path (num_parameters=1 is)')
+        return (1, 0.0, act.weight)
     if isinstance(act, nn.RReLU):
         if training:
             raise NotImplementedError('nn.RReLU draws a random slope per element in training mode: not on the B200 path '
                                       '(eval mode, with the mean slope, is)')
-        return (1, (float(act.lower) + float(act.upper)) / 2)
+        return (1, (float(act.lower) + float(act.upper)) / 2, None)
     if isinstance(act, nn.SiLU):
-        return (2, 0.0)
+        return (2, 0.0, None)
     raise NotImplementedError(f'activation module {type(act).__name__} is not on the B200 path')
 
 
@@ -344,7 +349,8 @@ def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, save=False,
     follow) also records the arg-max slots of the pooling windows.  With write_a=False `y` is already a QH activation
     (eval path) and is only pooled.  act: (code, slope) of act_code; default ReLU (relu=False: identity)."""
     if act is None:
-        act = ACT_RELU if relu else (0, 0.0)
+        act = ACT_RELU if relu else (0, 0.0, None)
+    slope_dev = act[2].detach() if len(act) > 2 and act[2] is not None else None
     dev = y.t.device
     if write_a == y.half:
         raise RuntimeError('norm_act: y must be float32 QP when a is written, a QH activation otherwise')
@@ -361,7 +367,7 @@ def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, save=False,
                                         device=dev)
     L.check(L.lib().e3b_norm_act(y.ptr, _p(scale), _p(shift), a.ptr if a else None, pooled.ptr if pooled else None,
                                  _p(pidx), y.N, y.C, y.D, y.H, y.W, pk[0], pk[1], pk[2],
-                                 act[0], act[1], 1 if y.half else 0, _stream()), 'norm_act')
+                                 act[0], act[1], _p(slope_dev), 1 if y.half else 0, _stream()), 'norm_act')
     return a, pooled
 
 
@@ -454,7 +460,7 @@ def norm_mode(norm, training):
 class Unit:
     """Everything one conv -> norm -> relu [-> pool] stage leaves behind for the backward pass."""
     __slots__ = ('spec', 'src0', 'src1', 'off1', 'y', 'a', 'pooled', 'pool', 'mode', 'G', 'nstate', 'stats', 'dec', 'act',
-                 'resize', 'res', 'res_grads')
+                 'resize', 'res', 'res_grads', 'dslope')
 
 
 class WeightSet:
@@ -981,11 +987,19 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True):
         dy = QP.empty_half(N, C, a.D, a.H, a.W, dev)
     dy.scale = dy_scale            # the tensor holds 2^k * dy; conv_forward undoes it through dy_scale[2]
     args.dy = dy.ptr
-    args.relu, args.act_slope = getattr(u, 'act', ACT_RELU)
+    act = tuple(getattr(u, 'act', ACT_RELU)) + (None,)
+    args.relu, args.act_slope = act[0], act[1]
+    dslope = None
+    if act[2] is not None:                     # nn.PReLU: the slope is read from device memory; its gradient is one more sum
+        slope_ws = torch.empty((N * Cp,), dtype=torch.float64, device=dev)
+        dslope = torch.empty((1,), dtype=torch.float32, device=dev)
+        args.act_slope_dev, args.slope_sums, args.dslope = act[2].detach().data_ptr(), slope_ws.data_ptr(), dslope.data_ptr()
+    u.dslope = dslope
     lib = L.lib()
     st = _stream()
-    # (SiLU's derivative lives in the three-kernel path only: the persistent kernel serves the (leaky-)ReLU family)
-    fused = Cp <= 512 and args.relu != 2 and os.environ.get('E3B_NORM_BWD', 'fused') != 'split'
+    # (SiLU's derivative and PReLU's slope gradient live in the three-kernel path only: the persistent kernel serves the
+    # (leaky-)ReLU family)
+    fused = Cp <= 512 and args.relu != 2 and dslope is None and os.environ.get('E3B_NORM_BWD', 'fused') != 'split'
     if s2d is not None and (a.D % s2d[0] or a.H % s2d[1] or a.W % s2d[2]):
         fused = False              # autocrop dropped fine voxels: the three-kernel path zero-fills them
     if fused:
@@ -1013,6 +1027,8 @@ def _conv_unit_bwd(net, u, g0, g1, gp, grads, need_dx):
         _put(grads, n.bias, dbeta)
     if conv.bias is not None:
         _put(grads, conv.bias, dbias)
+    if u.dslope is not None:
+        _put(grads, spec.act.weight, u.dslope)
     if getattr(u, 'res', None) is not None:
         _shortcut_bwd(net, u, dy, dbias, grads)
     cropped = u.src1 is not None and (tuple(u.off1) != (0, 0, 0) or u.src1.spatial != u.src0.spatial)
@@ -1139,6 +1155,8 @@ def _backward(net, tape, dlogits, need_dx):
             _put(grads, ups.norm.bias, dbeta)
         if up.bias is not None:
             _put(grads, up.bias, dbias)
+        if u0.dslope is not None:
+            _put(grads, ups.act.weight, u0.dslope)
         dec = u0.dec
         if up.weight.requires_grad:
             dwu = wgrad(dec, dy, dy.C, (1, 1, 1), (0, 0, 0), tuple(up.weight.shape), layout=1, up_taps=ups.taps,

@@ -15,8 +15,8 @@ protocol as used by ``Trainer`` (training/trainer.py:309,519-520,863-874) and ``
 
 There is no CPU / cuDNN fallback: a non-CUDA input or a missing ``libe3b.so`` raises.
 Options: ``up_mode`` 'transpose' and the four 'resizeconv_*' modes, ``merge_mode`` 'concat' and 'add', activations
-'relu' / 'leaky' / 'silu' / 'lin' / 'rrelu' (eval mode) or modules of those types.  What is still outside the
-accelerated path raises ``NotImplementedError`` at construction (``attention=True``, 'prelu' and other modules).
+'relu' / 'leaky' / 'prelu' / 'silu' / 'lin' / 'rrelu' (eval mode) or modules of those types.  What is still outside the
+accelerated path raises ``NotImplementedError`` at construction (``attention=True``, activation modules of other types).
 """
 import copy
 from typing import Sequence
@@ -55,10 +55,8 @@ def _make_norm(normtype, C, dim):
 def _make_activation(activation):
     """get_activation (models/unet.py:183-199): one module per call site; modules are deep-copied"""
     if isinstance(activation, str):
-        table = {'relu': nn.ReLU, 'leaky': lambda: nn.LeakyReLU(negative_slope=0.1), 'rrelu': nn.RReLU, 'silu': nn.SiLU,
-                 'lin': nn.Identity}
-        if activation == 'prelu':
-            raise NotImplementedError('activation="prelu" (a learned slope) is not on the B200 path')
+        table = {'relu': nn.ReLU, 'leaky': lambda: nn.LeakyReLU(negative_slope=0.1), 'prelu': lambda: nn.PReLU(num_parameters=1),
+                 'rrelu': nn.RReLU, 'silu': nn.SiLU, 'lin': nn.Identity}
         if activation not in table:
             # (the reference returns None here and fails at the first forward)
             raise ValueError(f'Unknown activation "{activation}"')

@@ -171,7 +171,8 @@ int e3b_wgrad_reduce_batched(const e3b_wgrad_args* args, int n, void* stream);
 /* ---- normalisation + activation (+ pooling) -----------------------------------------------------
  * get_normalization (unet.py:77-111) + get_activation (:183-199) + MaxPool(ceil_mode) (:225-229).
  * Activation code `relu` (here and in e3b_norm_bwd_args): 0 identity ('lin'), 1 the leaky-ReLU family with negative slope
- * `act_slope` (0 = nn.ReLU, 0.1 = 'leaky', (lower+upper)/2 = eval-mode nn.RReLU), 2 nn.SiLU.
+ * `act_slope` (0 = nn.ReLU, 0.1 = 'leaky', (lower+upper)/2 = eval-mode nn.RReLU), 2 nn.SiLU.  nn.PReLU(num_parameters=1) is code 1
+ * with the learned slope read from device memory (`act_slope_dev`); its gradient comes out of the three-kernel backward.
  * mode: 0 none, 1 group/instance (G groups), 2 batch (training: batch stats + running update),
  *       3 batch eval (running stats).
  * finalize: stats [N][C][2] (from e3b_conv) -> per-(n,c) scale/shift and mean/rstd ([N][pad8(C)]). */
@@ -186,8 +187,8 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
  * ((dz*pk_h+dy)*pk_w+dx) of the first maximum -- what nn.MaxPool3d(return_indices) would give; consumed by
  * e3b_norm_bwd_*. */
 int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a, void* pooled, uint8_t* pool_idx,
-                 int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, float act_slope, int y_is_half,
-                 void* stream);
+                 int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, float act_slope,
+                 const float* act_slope_dev, int y_is_half, void* stream);
 
 /* backward of conv -> norm -> relu [-> pool] as autograd derives it:
  *   dr  = (g0 + g1 + unpool(gp)) * act'(y*scale+shift)   ([a > 0] for ReLU)   g0,g1: same extents as y (either may be NULL)
@@ -219,6 +220,9 @@ typedef struct e3b_norm_bwd_args {
                                                   (g1_D,g1_H,g1_W) and is added inside the box starting at (g1_od,g1_oh,g1_ow) */
     int32_t g1_od, g1_oh, g1_ow, g1_D, g1_H, g1_W;
     float act_slope;                           /* negative slope of activation code relu == 1 (0 = ReLU) */
+    const float* act_slope_dev;                /* nn.PReLU: the slope in device memory (overrides act_slope; three-kernel path) */
+    double* slope_sums;                        /* nn.PReLU: workspace [N][pad8(C)] (zeroed by e3b_norm_bwd_reduce) */
+    float* dslope;                             /* nn.PReLU: gradient of the slope, written by e3b_norm_bwd_finalize */
 } e3b_norm_bwd_args;
 /* The three passes as ONE persistent kernel (reduce, grid barrier, finalize, apply), one sample at a time for per-sample
  * statistics (group / instance / none): the apply pass re-reads the sample out of L2, so y and the incoming gradient cross

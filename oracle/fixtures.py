@@ -46,6 +46,10 @@ CASES = {
 OPTION_CASES = {
     'opt_leaky_train': dict(model=dict(n_blocks=3, start_filts=8, normalization='group', activation='leaky'),
                             x=(2, 1, 16, 16, 16), train=True),
+    'opt_prelu_train': dict(model=dict(n_blocks=3, start_filts=8, normalization='group', activation='prelu'),
+                            x=(2, 1, 16, 16, 16), train=True),
+    'opt_prelu_bn_eval': dict(model=dict(n_blocks=2, start_filts=8, activation='prelu'),
+                              x=(1, 1, 16, 16, 16), train=False),
     'opt_silu_train': dict(model=dict(n_blocks=2, start_filts=8, activation='silu'),
                            x=(2, 1, 16, 16, 16), train=True),
     'opt_lin_none_train': dict(model=dict(n_blocks=2, start_filts=8, normalization='none', activation='lin'),
@@ -133,6 +137,8 @@ def make_state(shapes, seed=1234):
             sd[key] = (0.1 * rs.standard_normal(shape)).astype(np.float32)
         elif key.endswith('running_var'):
             sd[key] = (0.5 + rs.random_sample(shape)).astype(np.float32)
+        elif '.act' in key and key.endswith('.weight'):      # nn.PReLU slope (get_activation 'prelu', unet.py:189-190)
+            sd[key] = (0.25 + 0.1 * rs.standard_normal(shape)).astype(np.float32)
         elif key.endswith('.weight') and len(shape) >= 3:
             rf = int(np.prod(shape[2:]))
             std = np.sqrt(2.0 / ((shape[0] + shape[1]) * rf))

@@ -99,9 +99,9 @@ def test_constructor_validation_matches_reference_messages():
     with pytest.raises(ValueError):
         e3.UNet(up_mode='resizeconv_nearest', merge_mode='add')        # models/unet.py:791-800
     with pytest.raises(NotImplementedError):
-        e3.UNet(activation='prelu')
-    with pytest.raises(NotImplementedError):
         e3.UNet(activation=torch.nn.Tanh())
+    with pytest.raises(NotImplementedError):
+        e3.UNet(activation=torch.nn.PReLU(num_parameters=8))           # one slope per channel
 
 
 def test_option_modules_follow_the_reference_layout():
@@ -120,8 +120,11 @@ def test_option_modules_follow_the_reference_layout():
     ma = e3.UNet(n_blocks=2, start_filts=8, merge_mode='add', activation=torch.nn.SiLU())
     assert tuple(ma.state_dict()['up_convs.0.conv1.weight'].shape) == (8, 8, 3, 3, 3)
     assert isinstance(ma.down_convs[0].act1, torch.nn.SiLU)
+    mp = e3.UNet(n_blocks=2, start_filts=8, activation='prelu')
+    assert tuple(mp.state_dict()['down_convs.0.act1.weight'].shape) == (1,) and 'up_convs.0.act0.weight' in mp.state_dict()
     from elektronn3_b200 import engine
-    assert engine.act_code(torch.nn.RReLU(), False) == (1, (1 / 8 + 1 / 3) / 2)
+    assert engine.act_code(torch.nn.RReLU(), False) == (1, (1 / 8 + 1 / 3) / 2, None)
+    assert engine.act_code(mp.down_convs[0].act1, True)[2] is mp.down_convs[0].act1.weight
     with pytest.raises(NotImplementedError):
         engine.act_code(torch.nn.RReLU(), True)
 

@@ -622,7 +622,7 @@ def test_errors_surface_as_exceptions(eng):
 
 
 # ---------------------------------------------------------------------------------------- options
-_ACTS = {'leaky': ((1, 0.1), lambda t: F.leaky_relu(t, 0.1)), 'lin': ((0, 0.0), lambda t: t),
+_ACTS = {'leaky': ((1, 0.1), lambda t: F.leaky_relu(t, 0.1)), 'lin': ((0, 0.0), lambda t: t), 'prelu': (None, None),
          'rrelu_eval': ((1, (1 / 8 + 1 / 3) / 2), lambda t: F.rrelu(t, training=False)), 'silu': ((2, 0.0), F.silu)}
 
 
@@ -634,6 +634,11 @@ def test_activations_forward_backward(eng, monkeypatch, act, mode, pool, path):
     takes the three-kernel one) against float64 autograd"""
     monkeypatch.setenv('E3B_NORM_BWD', 'split' if path == 'split' else 'fused')
     code, fn = _ACTS[act]
+    slope = sd = None
+    if act == 'prelu':                    # the learned slope of nn.PReLU lives in device memory; its gradient is a third sum
+        slope = torch.nn.Parameter(torch.tensor([0.3], device='cuda'))
+        sd = slope.detach().double().requires_grad_(True)
+        code, fn = (1, 0.0, slope), (lambda t: F.prelu(t, sd))
     N, C, G, sp = 2, 16, 4, (4, 6, 8)
     rs = np.random.RandomState(5)
     y = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
@@ -678,6 +683,10 @@ def test_activations_forward_backward(eng, monkeypatch, act, mode, pool, path):
     if mode:
         assert_close(dgamma, gd.grad, 3e-4, 'dgamma')
         assert_close(dbeta, bd.grad, 3e-4, 'dbeta')
+    if act == 'prelu':
+        assert_close(u.dslope, sd.grad, 3e-4, 'dslope')
+    else:
+        assert u.dslope is None
 
 
 @pytest.mark.parametrize('C,sp,sp1,off', [(16, (4, 6, 8), (4, 6, 8), (0, 0, 0)), (8, (3, 5, 7), (7, 9, 9), (2, 2, 1)),
