@@ -1,6 +1,9 @@
 #!/bin/bash
 # A/B on ONE box: bench line (train step + Predictor, no CPU / cuDNN arms) of the tree in _ab_old/ (an older commit, built
 # in-tree by the caller) and of the working tree, interleaved twice.  -> gpurun_out/ab.txt
+# Prepare the old tree here (it travels with the gpurun snapshot, git-ignored):
+#   mkdir _ab_old && git archive <commit> elektronn3_b200 include bench.py oracle/torch_ref.py oracle/__init__.py | tar -x -C _ab_old
+#   (cd _ab_old && python -m elektronn3_b200.build)
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 R=$(pwd)
