@@ -103,7 +103,7 @@ struct ConvZsParams {
     const uint8_t* wpk;
     uint32_t* dbg;               // host-mapped debug words or null
     int prof;                    // accumulate role timings into g_zs_prof
-    int skip;                    // tuning aid (E3B_ZS_SKIP): 1 no global stores, 2 no statistics, 4 no MMAs
+    int skip;                    // tuning aid (E3B_ZS_SKIP): 1 no global stores, 2 no statistics, 4 no MMAs, 8 streaming (evict-first) fp32 stores
 };
 
 
@@ -495,7 +495,10 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                                     const int cq = ((co0 + cg) >> 2) + j4;
                                     const float4 val = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
                                     if (cq < p.cq0) {
-                                        if (cq < p.cq0_alloc) reinterpret_cast<float4*>(p.dst0)[o0 + (size_t)cq * cstride + zoff] = val;
+                                        if (cq < p.cq0_alloc) {
+                                            float4* q = reinterpret_cast<float4*>(p.dst0) + (o0 + (size_t)cq * cstride + zoff);
+                                            if (p.skip & 8) __stcs(q, val); else *q = val;
+                                        }
                                     } else if (p.dst1 != nullptr && cq - p.cq0 < p.cq1_alloc) {
                                         reinterpret_cast<float4*>(p.dst1)[o1 + (size_t)(cq - p.cq0) * cstride + zoff] = val;
                                     }
