@@ -558,11 +558,13 @@ static PFN_encodeTiled get_encode()
 
 // L2 promotion of the activation tensor maps.  A halo-tile row is 10 voxels = 160 bytes starting 16 bytes before a
 // 128-byte boundary: with 256-byte promotion every such row pulls TWO 256-byte blocks from DRAM (ncu on the dominant layer:
-// 422 MB read for 134 MB of input, profiles/r02_ncu_zs_concat_*.csv).  E3B_TMA_PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B.
+// 422 MB read for 134 MB of input, profiles/r02_ncu_zs_concat_*.csv).  E3B_TMA_PROMO = 0 none, 1 64 B (default: the dominant conv
+// launch 120.7 -> 117.7 us in its training form, 104.2 -> 100.2 us in its inference form against 128 B on the same box,
+// profiles/r02_tma_promo_ab.txt), 2 128 B, 3 256 B.
 CUtensorMapL2promotion tma_l2_promotion()
 {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("E3B_TMA_PROMO"); v = e ? atoi(e) : 2; if (v < 0 || v > 3) v = 2; }
+    if (v < 0) { const char* e = getenv("E3B_TMA_PROMO"); v = e ? atoi(e) : 1; if (v < 0 || v > 3) v = 1; }
     return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
          : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
 }
