@@ -89,7 +89,9 @@ struct ConvZsParams {
     int pd, ph, pw;
     int HX, HY;                  // halo tile extents of one plane
     int tiles_x, tiles_y;
-    long long total_L;           // (n, y tile, x tile) chains x Do output planes
+    long long total_L;           // (n, y tile, x tile) chains x Do output planes (pair: (n, y tile, x tile pair) x Do)
+    int pair;                    // 1: the two chains of a CTA take x-ADJACENT tile columns over the same run of planes, so the
+                                 //    128-byte lines both halo tiles touch cross HBM once (they meet in L2 within microseconds)
     int chunks0, chunks1;        // 16-channel K chunks of source 0 / 1
     int NTW, R, SA;              // columns per output plane (of one N tile), ring blocks, plane-tile stages
     int ZB;                      // input planes per stage
@@ -133,11 +135,12 @@ E3B_DEVINL void zs_flush_stats(const ConvZsParams& p, int n, int co0, int lane, 
 
 struct ZsPiece { int n, y0, x0, za, zb; };      // output planes [za, zb) of one chain
 
-E3B_DEVINL ZsPiece zs_piece(const ConvZsParams& p, long long L, long long L1)
+E3B_DEVINL ZsPiece zs_piece(const ConvZsParams& p, long long L, long long L1, int chain_id)
 {
     ZsPiece g;
     int chain = (int)(L / p.Do);
     g.za = (int)(L - (long long)chain * p.Do);
+    if (p.pair) chain = 2 * chain + chain_id;
     const long long left = L1 - L;
     g.zb = (g.za + left < p.Do) ? (int)(g.za + left) : p.Do;
     const int xt = chain % p.tiles_x; chain /= p.tiles_x;
@@ -235,7 +238,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     const int ntile = (int)blockIdx.x / G, bloc = (int)blockIdx.x % G;
     // this CTA's contiguous run of the linear (chain, output plane) space, cut into one contiguous part per chain
     const long long C0 = p.total_L * bloc / G, C1 = p.total_L * (bloc + 1) / G;
-    const long long L0 = C0 + (C1 - C0) * chain / CHAINS, L1 = C0 + (C1 - C0) * (chain + 1) / CHAINS;
+    const long long L0 = p.pair ? C0 : C0 + (C1 - C0) * chain / CHAINS, L1 = p.pair ? C1 : C0 + (C1 - C0) * (chain + 1) / CHAINS;
 
     if (role == 0) {
         // ===================== TMA producer =====================
@@ -250,7 +253,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             unsigned long long prof[16] = {0};
             ZP_T0(t_all); ZP_T0(t);
             for (long long L = L0; L < L1;) {
-                const ZsPiece g = zs_piece(p, L, L1);
+                const ZsPiece g = zs_piece(p, L, L1, chain);
                 const int zlo = zs_in_lo(p, g), zhi = zs_in_hi(p, g);
                 int next_wait = g.za;
                 for (int zp = zlo; zp <= zhi; zp += p.ZB) {
@@ -305,7 +308,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         unsigned long long prof[16] = {0};
         ZP_T0(t_all); ZP_T0(t);
         for (long long L = L0; L < L1;) {
-            const ZsPiece g = zs_piece(p, L, L1);
+            const ZsPiece g = zs_piece(p, L, L1, chain);
             const int zlo = zs_in_lo(p, g), zhi = zs_in_hi(p, g);
             int next_in = g.za, next_commit = g.za, olo_prev = g.za;
             uint32_t cs = ws, s_lo = ws;         // slots of next_commit / of the lowest output plane fed by the current input plane
@@ -424,7 +427,7 @@ conv_zs_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         unsigned long long prof[16] = {0};
         ZP_T0(t_all); ZP_T0(t);
         for (long long L = L0; L < L1;) {
-            const ZsPiece g = zs_piece(p, L, L1);
+            const ZsPiece g = zs_piece(p, L, L1, chain);
             if (p.stats && g.n != cur_n) {
                 if (cur_n >= 0) zs_flush_stats(p, cur_n, co0, lane, bcol, reg_stats, rs, rq, acc_s, acc_q);
                 cur_n = g.n;
@@ -715,6 +718,8 @@ int launch_conv_zs(const e3b_conv_args* a, cudaStream_t stream)
         memset(g_zs_dbg_host, 0, 16 * 148 * sizeof(uint32_t));
         p.dbg = dbg_dev;
     }
+    p.pair = (pl.chains == 2 && p.tiles_x % 2 == 0 && !getenv("E3B_ZS_NO_PAIR")) ? 1 : 0;
+    if (p.pair) p.total_L = (long long)a->N * (p.tiles_x / 2) * p.tiles_y * p.Do;
     long long grid = num_sms() / p.ntiles;                            // CTAs per N tile
     if (grid > p.total_L) grid = p.total_L;
     if (grid < 1) grid = 1;
