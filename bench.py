@@ -45,7 +45,8 @@ DOM = dict(N=4, C0=32, C1=32, Co=32, S=64)
 DOM_GFLOP = 2 * 4 * 64 ** 3 * 32 * (64 * 27) / 1e9     # 115.96
 # torch's fused multi-tensor SGD (one kernel for all parameters) in BOTH GPU arms; E3B_BENCH_FUSED_OPT=0: the foreach default
 FUSED_OPT = os.environ.get('E3B_BENCH_FUSED_OPT', '1') != '0'
-DOM_TRAFFIC = 507.0e6            # dram__bytes_read + write of that launch: ncu --set full, profiles/r02_ncu_zs_concat.csv (cold L2; 268 MB algorithmic)
+DOM_TRAFFIC = 302.0e6            # dram__bytes_read + write of that launch: ncu --set full, profiles/r02_ncu_zs_concat_late.csv (cold L2; 268 MB
+                                 # algorithmic; 507 MB before the 64-byte L2 promotion and the paired chains)
 
 PRED_MODEL_KW = dict(n_blocks=4, start_filts=32)
 PRED_VOL = (512, 512, 256)
