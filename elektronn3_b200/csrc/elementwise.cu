@@ -1062,9 +1062,16 @@ E3B_DEVINL void fused_gather(const NormBwdDev& p, const FusedDev& f, int n, int 
 // xhat, and the (leaky-)ReLU derivative applied to the summed upstream gradient: 1 where y * scale + shift > 0 (scale = 1,
 // shift = 0 without a norm), the negative slope elsewhere.  The forward's TF32 rounding of the activation cannot turn a
 // positive value into zero, so the mask does not need it.
+template <bool SILU>
 E3B_DEVINL void fused_mask_xhat(const QuadConsts& c, const float4& yv, float4& g, float4& xh)
 {
     xh = make_float4(fmaf(yv.x, c.rs.x, c.mu.x), fmaf(yv.y, c.rs.y, c.mu.y), fmaf(yv.z, c.rs.z, c.mu.z), fmaf(yv.w, c.rs.w, c.mu.w));
+    if (SILU) {
+        // nn.SiLU (a compile-time variant of the kernel: the ReLU family pays nothing for it)
+        g.x = act_bwd(fmaf(yv.x, c.sc.x, c.sh.x), g.x, 2, 0.f); g.y = act_bwd(fmaf(yv.y, c.sc.y, c.sh.y), g.y, 2, 0.f);
+        g.z = act_bwd(fmaf(yv.z, c.sc.z, c.sh.z), g.z, 2, 0.f); g.w = act_bwd(fmaf(yv.w, c.sc.w, c.sh.w), g.w, 2, 0.f);
+        return;
+    }
     if (!(fmaf(yv.x, c.sc.x, c.sh.x) > 0.f)) g.x *= c.slope;
     if (!(fmaf(yv.y, c.sc.y, c.sh.y) > 0.f)) g.y *= c.slope;
     if (!(fmaf(yv.z, c.sc.z, c.sh.z) > 0.f)) g.z *= c.slope;
@@ -1073,7 +1080,7 @@ E3B_DEVINL void fused_mask_xhat(const QuadConsts& c, const float4& yv, float4& g
 
 // phase A over one staged item (this thread: channel quad `cq`, voxels t128 + 128 k).
 // FULL = all 512 voxels present: no bounds checks.
-template <int VAR, bool FULL>
+template <int VAR, bool FULL, bool SILU>
 E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32_t sbase, uint32_t off_g0, uint32_t off_g1,
                                   const QuadConsts& c, int t128, int n, int cq, int v0, int nv, float* s1, float* s2, float* md,
                                   float* mx, const CoarseStage& co)
@@ -1089,7 +1096,7 @@ E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32
         float4 dr = G[kk], xh;
         if (FusedVar<VAR>::gp_staged) fused_unpool_staged(co, k0 + kk, dr);
         else if (FusedVar<VAR>::coords) { int z, yy, x; fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x, co); }
-        fused_mask_xhat(c, Y[kk], dr, xh);
+        fused_mask_xhat<SILU>(c, Y[kk], dr, xh);
         s1[0] += dr.x; s1[1] += dr.y; s1[2] += dr.z; s1[3] += dr.w;
         s2[0] = fmaf(dr.x, xh.x, s2[0]); s2[1] = fmaf(dr.y, xh.y, s2[1]); s2[2] = fmaf(dr.z, xh.z, s2[2]); s2[3] = fmaf(dr.w, xh.w, s2[3]);
         md[0] = fmaxf(md[0], fabsf(dr.x)); md[1] = fmaxf(md[1], fabsf(dr.y)); md[2] = fmaxf(md[2], fabsf(dr.z)); md[3] = fmaxf(md[3], fabsf(dr.w));
@@ -1101,7 +1108,7 @@ E3B_DEVINL void fused_item_reduce(const NormBwdDev& p, const FusedDev& f, uint32
 // phase C over one staged item: dy = 2^k * rstd * (gamma * dr - m1 - xhat * m2); this thread writes the 8-byte half `hsel`
 // of its voxels' 16-byte units (the other half comes from the other warp group; L2 merges the sectors).
 // (fp16 has TF32's 10 mantissa bits: the fp16 rounding of the store is the operand rounding.)
-template <int VAR, bool FULL>
+template <int VAR, bool FULL, bool SILU>
 E3B_DEVINL void fused_item_apply(const NormBwdDev& p, const FusedDev& f, uint32_t sbase, uint32_t off_g0, uint32_t off_g1,
                                  const QuadConsts& c, const float4& ga, const float4& m1, const float4& m2, const float4& rk, int hsel,
                                  int t128, int n, int cqp, int Cqp, int total, int v0, int nv, uint2* dy, const CoarseStage& co)
@@ -1121,7 +1128,7 @@ E3B_DEVINL void fused_item_apply(const NormBwdDev& p, const FusedDev& f, uint32_
         int z = 0, yy = 0, x = 0;
         if (FusedVar<VAR>::gp_staged) fused_unpool_staged(co, k0 + kk, dr);
         else if (FusedVar<VAR>::coords) fused_gather<VAR>(p, f, n, cq, v0 + vl, dr, z, yy, x, co);
-        fused_mask_xhat(c, Y[kk], dr, xh);
+        fused_mask_xhat<SILU>(c, Y[kk], dr, xh);
         // rstd * 2^k is folded into rk: o = rk * (ga * dr - m1 - xh * m2)
         const uint2 o = pack_half4(rk.x * fmaf(-xh.x, m2.x, fmaf(ga.x, dr.x, -m1.x)), rk.y * fmaf(-xh.y, m2.y, fmaf(ga.y, dr.y, -m1.y)),
                                    rk.z * fmaf(-xh.z, m2.z, fmaf(ga.z, dr.z, -m1.z)), rk.w * fmaf(-xh.w, m2.w, fmaf(ga.w, dr.w, -m1.w)));
@@ -1141,7 +1148,7 @@ E3B_DEVINL void fused_item_apply(const NormBwdDev& p, const FusedDev& f, uint32_
 static constexpr int kFusedThreads = 288;            // 8 consumer warps + 1 producer warp (one lane issues the bulk copies)
 static constexpr int kFusedBar = 1;                  // named barrier of the 256 consumer threads
 
-template <int VAR>
+template <int VAR, bool SILU>
 __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const NormBwdDev p, const FusedDev f)
 {
     extern __shared__ __align__(128) unsigned char ring[];
@@ -1345,8 +1352,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                 co.zslot = (FusedVar<VAR>::gp_staged && f.co_mode == 1) ? ((chunk / f.co_ipp) % p.wd) * (p.wh * p.ww) : 0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) co.tab[k] = co_tab[k];
-                if (nv == kItemVox) fused_item_reduce<VAR, true>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx, co);
-                else fused_item_reduce<VAR, false>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx, co);
+                if (nv == kItemVox) fused_item_reduce<VAR, true, SILU>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx, co);
+                else fused_item_reduce<VAR, false, SILU>(p, f, sbase, off_g0, off_g1, c, t128, n, 2 * cqp + hsel, v0, nv, s1, s2, md, mx, co);
                 if (j + S < cnt) {                    // this warp is done with stage s: the producer may refill it
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
@@ -1525,8 +1532,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) norm_bwd_fused_kernel(const 
                 co.zslot = (FusedVar<VAR>::gp_staged && f.co_mode == 1) ? ((chunk / f.co_ipp) % p.wd) * (p.wh * p.ww) : 0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) co.tab[k] = co_tab[k];
-                if (nv == kItemVox) fused_item_apply<VAR, true>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy, co);
-                else fused_item_apply<VAR, false>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy, co);
+                if (nv == kItemVox) fused_item_apply<VAR, true, SILU>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy, co);
+                else fused_item_apply<VAR, false, SILU>(p, f, sbase, off_g0, off_g1, c, ga, m1, m2, rk, hsel, t128, n, cqp, Cqp, total, v0, nv, dy, co);
                 if (j - S >= 0 || round + 1 < nrounds) {                      // the producer refills this stage
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
@@ -2091,7 +2098,6 @@ int e3b_norm_bwd_fused(const e3b_norm_bwd_args* a, void* stream)
     if (fill_bwd(a, p)) return 1;
     const int Cp = p.Cq * 4;
     if (!a->amax || !a->dy_scale || !a->sums) return set_error("norm_bwd_fused: sums / amax / dy_scale buffers are required");
-    if (a->relu == 2) return set_error("norm_bwd_fused: SiLU is served by the reduce / finalize / apply kernels");
     if (a->act_slope_dev || a->dslope) return set_error("norm_bwd_fused: nn.PReLU is served by the reduce / finalize / apply kernels");
     if (Cp > kFusedMaxCp) return set_error("norm_bwd_fused: more than %d channels: use the reduce / finalize / apply kernels", kFusedMaxCp);
     if (a->mode == 1 && (a->G <= 0 || a->C % a->G)) return set_error("norm_bwd: bad group count");
@@ -2145,10 +2151,15 @@ int e3b_norm_bwd_fused(const e3b_norm_bwd_args* a, void* stream)
     if (f.stages > kFusedMaxStages) f.stages = kFusedMaxStages;
     const size_t smem = (size_t)f.stages * stage_bytes;
     typedef void (*FusedKernel)(const NormBwdDev, const FusedDev);
-    static const FusedKernel kernels[6] = {norm_bwd_fused_kernel<0>, norm_bwd_fused_kernel<1>, norm_bwd_fused_kernel<2>,
-                                           norm_bwd_fused_kernel<3>, norm_bwd_fused_kernel<4>, norm_bwd_fused_kernel<5>};
-    const FusedKernel kern = kernels[var];
-    static int per_sm[kMaxDevices][6][4] = {};
+    static const FusedKernel kernels[2][6] = {
+        {norm_bwd_fused_kernel<0, false>, norm_bwd_fused_kernel<1, false>, norm_bwd_fused_kernel<2, false>,
+         norm_bwd_fused_kernel<3, false>, norm_bwd_fused_kernel<4, false>, norm_bwd_fused_kernel<5, false>},
+        {norm_bwd_fused_kernel<0, true>, norm_bwd_fused_kernel<1, true>, norm_bwd_fused_kernel<2, true>,
+         norm_bwd_fused_kernel<3, true>, norm_bwd_fused_kernel<4, true>, norm_bwd_fused_kernel<5, true>}};
+    const int silu = a->relu == 2 ? 1 : 0;
+    const FusedKernel kern = kernels[silu][var];
+    var += 6 * silu;                                // (index of the per-kernel occupancy cache)
+    static int per_sm[kMaxDevices][12][4] = {};
     const int dev = current_device();
     if (!per_sm[dev][var][nb]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes) != cudaSuccess)

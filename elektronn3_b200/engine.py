@@ -997,9 +997,8 @@ def _norm_bwd(u, C, g0, g1=None, gp=None, s2d=None, want_bias=True):
     u.dslope = dslope
     lib = L.lib()
     st = _stream()
-    # (SiLU's derivative and PReLU's slope gradient live in the three-kernel path only: the persistent kernel serves the
-    # (leaky-)ReLU family)
-    fused = Cp <= 512 and args.relu != 2 and dslope is None and os.environ.get('E3B_NORM_BWD', 'fused') != 'split'
+    # (PReLU's slope gradient lives in the three-kernel path only; SiLU is a compile-time variant of the persistent kernel)
+    fused = Cp <= 512 and dslope is None and os.environ.get('E3B_NORM_BWD', 'fused') != 'split'
     if s2d is not None and (a.D % s2d[0] or a.H % s2d[1] or a.W % s2d[2]):
         fused = False              # autocrop dropped fine voxels: the three-kernel path zero-fills them
     if fused:

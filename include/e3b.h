@@ -227,8 +227,7 @@ typedef struct e3b_norm_bwd_args {
 /* The three passes as ONE persistent kernel (reduce, grid barrier, finalize, apply), one sample at a time for per-sample
  * statistics (group / instance / none): the apply pass re-reads the sample out of L2, so y and the incoming gradient cross
  * HBM once.  Needs sums, amax and dy_scale as one contiguous workspace (in this order), at most 512 channels and, for
- * s2d, extents divisible by the stride, and an activation of the (leaky-)ReLU family or none; otherwise use the three
- * calls below. */
+ * s2d, extents divisible by the stride, and no PReLU slope gradient (dslope); otherwise use the three calls below. */
 int e3b_norm_bwd_fused(const e3b_norm_bwd_args* args, void* stream);
 int e3b_norm_bwd_reduce(const e3b_norm_bwd_args* args, void* stream);
 int e3b_norm_bwd_finalize(const e3b_norm_bwd_args* args, void* stream);
