@@ -398,6 +398,44 @@ __global__ void __launch_bounds__(256) norm_act_pool_kernel(const NormActDev p)
     if (p.pool_idx) p.pool_idx[op] = idx;
 }
 
+// Pooling alone of a QH activation (inference: the conv epilogue already wrote the activated fp16 tensor, nothing is kept
+// for a backward pass): one thread per pooled voxel and 8-channel unit, whole 16-byte units in and out (the generic kernel
+// above reads 8-byte halves at a 32-byte stride: 3.3 TB/s on the 1 GB level-0 tensor of a 32-tile Predictor pass).
+// grid: (chunks of pooled voxels, Ch, N)
+__global__ void __launch_bounds__(256) pool_qh_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int Ch, int D, int H, int W,
+                                                      int pkd, int pkh, int pkw, int Dp, int Hp, int Wp)
+{
+    const int ch = blockIdx.y, n = blockIdx.z;
+    const int Sp = Dp * Hp * Wp, HWp = Hp * Wp;
+    const uint4* sb = src + ((size_t)n * Ch + ch) * ((size_t)D * H * W);
+    uint4* db = dst + ((size_t)n * Ch + ch) * (size_t)Sp;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Sp; v += gridDim.x * blockDim.x) {
+        const int zp = v / HWp, r = v - zp * HWp, yp = r / Wp, xp = r - yp * Wp;
+        __half2 m[4];
+        bool first = true;
+        for (int dz = 0; dz < pkd; dz++) {
+            const int z = zp * pkd + dz;
+            if (z >= D) break;
+            for (int dy = 0; dy < pkh; dy++) {
+                const int y = yp * pkh + dy;
+                if (y >= H) break;
+                for (int dx = 0; dx < pkw; dx++) {
+                    const int x = xp * pkw + dx;
+                    if (x >= W) break;
+                    const uint4 u = __ldg(sb + ((size_t)z * H + y) * W + x);
+                    const __half2* h = reinterpret_cast<const __half2*>(&u);
+                    if (first) { m[0] = h[0]; m[1] = h[1]; m[2] = h[2]; m[3] = h[3]; first = false; }
+                    else { m[0] = __hmax2(m[0], h[0]); m[1] = __hmax2(m[1], h[1]); m[2] = __hmax2(m[2], h[2]); m[3] = __hmax2(m[3], h[3]); }
+                }
+            }
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+        oh[0] = m[0]; oh[1] = m[1]; oh[2] = m[2]; oh[3] = m[3];
+        db[v] = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward of norm -> relu [-> pool]: per-voxel kernels
 // ------------------------------------------------------------------------------------------------
@@ -1977,7 +2015,13 @@ int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a,
     p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu; p.slope = act_slope; p.slope_dev = act_slope_dev;
     p.Dp = (D + pk_d - 1) / pk_d; p.Hp = (H + pk_h - 1) / pk_h; p.Wp = (W + pk_w - 1) / pk_w;
     if (p.Cq > 65535 || N > 65535) return set_error("norm_act: too many channels / samples for the launch grid");
-    if (pooling) {
+    if (pooling && y_is_half && !pool_idx && pooled && !getenv("E3B_POOL_GENERIC")) {
+        // inference: pooling only, whole 16-byte units
+        const size_t Sp = (size_t)p.Dp * p.Hp * p.Wp;
+        size_t chunks = (Sp + 255) / 256; if (chunks > 8192) chunks = 8192;
+        pool_qh_kernel<<<dim3((unsigned)chunks, p.Ch, N), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(pooled), p.Ch, D, H, W, pk_d, pk_h, pk_w, p.Dp, p.Hp, p.Wp);
+    } else if (pooling) {
         const dim3 grid((unsigned)(p.Dp * ((p.Hp * p.Wp + 255) / 256)), p.Cq, N);
         norm_act_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     } else {

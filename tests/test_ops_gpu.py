@@ -816,3 +816,19 @@ def test_weight_scale_table_kernel_matches_the_torch_formula(eng):
     for w, (up, down) in zip(ws, table.tolist()):
         if float(w.abs().max()) > 0:
             assert 1.0 <= float(w.abs().max()) * up < 2.0 + 1e-6 and up * down == 1.0
+
+
+@pytest.mark.parametrize('C,sp,pool', [(16, (4, 6, 8), (2, 2, 2)), (8, (5, 7, 9), (2, 2, 2)), (24, (3, 9, 10), (1, 2, 2)), (40, (1, 11, 13), (1, 2, 2))])
+@pytest.mark.parametrize('generic', [False, True])
+def test_pooling_of_an_fp16_activation(eng, monkeypatch, C, sp, pool, generic):
+    """inference path: the conv epilogue wrote the activated QH tensor, norm_act only pools it (ceil mode, MaxPool of
+    models/unet.py:225-229); the 16-byte-unit kernel and the generic one"""
+    if generic:
+        monkeypatch.setenv('E3B_POOL_GENERIC', '1')
+    x = dyadic((2, C) + sp, 17)
+    _, pooled = eng.norm_act(qp(eng, x), None, None, write_a=False, pool=pool)
+    ref = F.max_pool3d(x, pool, pool, ceil_mode=True)
+    assert (pooled.D, pooled.H, pooled.W) == tuple(ref.shape[2:])
+    assert_close(from_qh_ref(pooled, C), ref, 1e-7, 'pool')
+    if eng.cpad16(C) != C:
+        assert from_qh_ref(pooled, eng.cpad16(C))[:, C:].abs().max().item() == 0.0
