@@ -1,6 +1,6 @@
 """BASELINE cfg 4: Predictor tiled inference of UNet(n_blocks=4) over a 512x512x256 synthetic volume,
 tile_shape=(64,64,64), overlap=(8,8,8); host volume in, host result out (end to end), plus the
-device-resident part alone.   python scripts/pred_bench.py [tile_batch] [D H W]   -> one JSON line
+device-resident part alone.   python scripts/pred_bench.py [tile_batch | 0 = default] [D H W]   -> one JSON line
 Run under torchrun for the sharded variant (one process per GPU, NCCL all_gather of the slabs)."""
 import json
 import os
@@ -21,7 +21,7 @@ torch.cuda.set_device(lr)
 dev = torch.device('cuda', lr)
 if world > 1:
     dist.init_process_group('nccl', device_id=dev)
-tb = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+tb = int(sys.argv[1]) if len(sys.argv) > 1 and int(sys.argv[1]) > 0 else None      # None: the Predictor's default (a row of tiles)
 vol = tuple(int(v) for v in sys.argv[2:5]) if len(sys.argv) >= 5 else (512, 512, 256)
 torch.manual_seed(0)
 m = e3.UNet(n_blocks=4, start_filts=32).to(dev).eval()
