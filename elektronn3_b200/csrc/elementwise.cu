@@ -40,6 +40,11 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
     const size_t plane = (size_t)Dv * Hv * Wv;
     const float* sb = src + (single ? 0 : (size_t)n * C * plane) + (size_t)ch * 8 * plane;
     const int nc = min(8, C - ch * 8);                  // real channels in this unit (<= 0: all padding)
+    if (nc <= 0) {                                      // a plane of padding channels only: zero fill, no index arithmetic
+        for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < S; v += gridDim.x * blockDim.x)
+            dst[((size_t)n * Ch + ch) * S + v] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < S; v += gridDim.x * blockDim.x) {
         const int z = v / HW, r = v - z * HW, y = r / W, x = r - y * W;
         // (flip: the tile is mirrored while it is gathered -- FlipAugment.forward of the Predictor's TTA)
