@@ -137,8 +137,6 @@ SIGNATURES = {
     'e3b_norm_finalize': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_i64, c_void_p, c_void_p, c_float,
                                   c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'e3b_norm_act': (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_float, c_void_p, c_int, c_void_p]),
-    'e3b_norm_finalize_act': (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float] +
-                              [c_void_p] * 6 + [c_int, c_float, c_void_p, c_void_p]),
     'e3b_norm_bwd_fused': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_reduce': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),
     'e3b_norm_bwd_finalize': (c_int, [ctypes.POINTER(NormBwdArgs), c_void_p]),

@@ -221,61 +221,52 @@ __global__ void __launch_bounds__(256) weight_scales_kernel(const e3b_ws_job* __
 // ------------------------------------------------------------------------------------------------
 // normalisation statistics -> per-(n,c) scale / shift (+ running stats)
 // ------------------------------------------------------------------------------------------------
-// One (sample n, channel c) of the finalisation: -> scale, shift (the affine norm_act applies), mean, rstd (for the backward
-// pass); with batch statistics the thread of sample 0 also updates the running statistics.
-struct NormFinDev {
-    const double* stats; int mode, G, N, C, Cp; double S;
-    const float* gamma; const float* beta; float eps;
-    float* running_mean; float* running_var; float momentum;
-    float* scale; float* shift; float* mean_o; float* rstd_o;
-};
-
-E3B_DEVINL void norm_finalize_one(const NormFinDev& q, int n, int c, bool side_effects, float& sc, float& sh, float& mu_f, float& r_f)
-{
-    sc = 0.f; sh = 0.f; mu_f = 0.f; r_f = 1.f;
-    if (c >= q.C) return;
-    const int C = q.C, N = q.N, mode = q.mode;
-    const double ga = q.gamma ? (double)q.gamma[c] : 1.0, be = q.beta ? (double)q.beta[c] : 0.0;
-    double mu = 0.0, var = 1.0 - (double)q.eps;
-    if (mode == 0) { sc = 1.f; sh = 0.f; return; }
-    if (mode == 1) {
-        const int cg = C / q.G, g = c / cg;
-        double s = 0.0, ss = 0.0;
-        for (int j = 0; j < cg; j++) {
-            s += q.stats[((size_t)n * C + g * cg + j) * 2];
-            ss += q.stats[((size_t)n * C + g * cg + j) * 2 + 1];
-        }
-        const double cnt = q.S * cg;
-        mu = s / cnt; var = ss / cnt - mu * mu;
-    } else if (mode == 2) {
-        double s = 0.0, ss = 0.0;
-        for (int j = 0; j < N; j++) { s += q.stats[((size_t)j * C + c) * 2]; ss += q.stats[((size_t)j * C + c) * 2 + 1]; }
-        const double cnt = q.S * N;
-        mu = s / cnt; var = ss / cnt - mu * mu;
-        if (side_effects && n == 0 && q.running_mean) {
-            const double unb = cnt > 1 ? var * cnt / (cnt - 1.0) : var;
-            q.running_mean[c] = (float)((1.0 - q.momentum) * q.running_mean[c] + q.momentum * mu);
-            q.running_var[c] = (float)((1.0 - q.momentum) * q.running_var[c] + q.momentum * unb);
-        }
-    } else {
-        mu = q.running_mean[c]; var = q.running_var[c];
-    }
-    if (var < 0.0) var = 0.0;
-    const double r = 1.0 / sqrt(var + (double)q.eps);
-    sc = (float)(r * ga); sh = (float)(be - mu * r * ga);
-    mu_f = (float)mu; r_f = (float)r;
-}
-
-__global__ void norm_finalize_kernel(const NormFinDev q)
+__global__ void norm_finalize_kernel(const double* __restrict__ stats, int mode, int G, int N, int C, int Cp, double S,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                     float* running_mean, float* running_var, float momentum, float* __restrict__ scale,
+                                     float* __restrict__ shift, float* __restrict__ mean_o, float* __restrict__ rstd_o)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q.N * q.Cp) return;
-    const int n = i / q.Cp, c = i % q.Cp;
-    float sc, sh, mu_f, r_f;
-    norm_finalize_one(q, n, c, true, sc, sh, mu_f, r_f);
-    q.scale[i] = sc; q.shift[i] = sh;
-    if (q.mean_o) q.mean_o[i] = mu_f;
-    if (q.rstd_o) q.rstd_o[i] = r_f;
+    if (i >= N * Cp) return;
+    const int n = i / Cp, c = i % Cp;
+    float sc = 0.f, sh = 0.f, mu_f = 0.f, r_f = 1.f;
+    if (c < C) {
+        const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+        double mu = 0.0, var = 1.0 - (double)eps;
+        if (mode == 0) {
+            sc = 1.f; sh = 0.f;
+        } else {
+            if (mode == 1) {
+                const int cg = C / G, g = c / cg;
+                double s = 0.0, ss = 0.0;
+                for (int j = 0; j < cg; j++) {
+                    s += stats[((size_t)n * C + g * cg + j) * 2];
+                    ss += stats[((size_t)n * C + g * cg + j) * 2 + 1];
+                }
+                const double cnt = S * cg;
+                mu = s / cnt; var = ss / cnt - mu * mu;
+            } else if (mode == 2) {
+                double s = 0.0, ss = 0.0;
+                for (int j = 0; j < N; j++) { s += stats[((size_t)j * C + c) * 2]; ss += stats[((size_t)j * C + c) * 2 + 1]; }
+                const double cnt = S * N;
+                mu = s / cnt; var = ss / cnt - mu * mu;
+                if (n == 0 && running_mean) {
+                    const double unb = cnt > 1 ? var * cnt / (cnt - 1.0) : var;
+                    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mu);
+                    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+                }
+            } else {
+                mu = running_mean[c]; var = running_var[c];
+            }
+            if (var < 0.0) var = 0.0;
+            const double r = 1.0 / sqrt(var + (double)eps);
+            sc = (float)(r * ga); sh = (float)(be - mu * r * ga);
+            mu_f = (float)mu; r_f = (float)r;
+        }
+    }
+    scale[i] = sc; shift[i] = sh;
+    if (mean_o) mean_o[i] = mu_f;
+    if (rstd_o) rstd_o[i] = r_f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -290,8 +281,6 @@ struct NormActDev {
     uint2* a; uint2* pooled;     // QH outputs
     uchar4* pool_idx;
     int C, N, Cq, Ch, D, H, W, pkd, pkh, pkw, relu;
-    int fused_fin;               // 1: scale / shift are derived from the statistics by every block itself (e3b_norm_finalize_act)
-    NormFinDev fin;
     float slope;                 // activation code / negative slope, see act_fwd
     const float* slope_dev;      // nn.PReLU: the (learned) negative slope lives in device memory
     int Dp, Hp, Wp;
@@ -347,7 +336,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
     const int v0 = blockIdx.x * (256 * kVpt) + threadIdx.x;
     const size_t nc = ((size_t)n * p.Cq + cq) * 4;
     float4 sc, sh;
-    if (!p.fused_fin) { load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f); }
+    load_nc4(p.scale, nc, sc, 1.f); load_nc4(p.shift, nc, sh, 0.f);
     const size_t base = ((size_t)n * p.Cq + cq) * (size_t)S;
     const float slope = p.slope_dev ? __ldg(p.slope_dev) : p.slope;
     float4 yv[kVpt];
@@ -356,31 +345,11 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const NormActDev p)
         const int v = v0 + j * 256;
         if (v < S) yv[j] = __ldcs(p.y + base + v);
     }
-    if (p.fused_fin) {
-        // the finalisation of this block's four channels, while its loads are in flight (what a separate 4 us launch on the
-        // critical path did before); block 0 of the slab leaves scale / shift / mean / rstd for the backward pass and does
-        // BatchNorm's running-statistics update
-        __shared__ float fin_s[8];
-        if (threadIdx.x < 4) {
-            float a, b, mu_f, r_f;
-            const bool writer = blockIdx.x == 0;
-            norm_finalize_one(p.fin, n, cq * 4 + (int)threadIdx.x, writer, a, b, mu_f, r_f);
-            fin_s[threadIdx.x] = a; fin_s[4 + threadIdx.x] = b;
-            if (writer) {
-                const size_t i = nc + threadIdx.x;
-                p.fin.scale[i] = a; p.fin.shift[i] = b;
-                if (p.fin.mean_o) p.fin.mean_o[i] = mu_f;
-                if (p.fin.rstd_o) p.fin.rstd_o[i] = r_f;
-            }
-        }
-        __syncthreads();
-        sc = make_float4(fin_s[0], fin_s[1], fin_s[2], fin_s[3]); sh = make_float4(fin_s[4], fin_s[5], fin_s[6], fin_s[7]);
-    }
 #pragma unroll
     for (int j = 0; j < kVpt; j++) {
         const int v = v0 + j * 256;
         if (v >= S) continue;
-        const float4 r = norm_relu_round(yv[j], sc, sh, p.scale != nullptr || p.fused_fin, p.relu, slope);
+        const float4 r = norm_relu_round(yv[j], sc, sh, p.scale != nullptr, p.relu, slope);
         if (p.a) store_qh(p.a, r, n, p.Ch, cq, (size_t)S, (size_t)v);
     }
 }
@@ -2027,11 +1996,8 @@ int e3b_norm_finalize(const double* stats, int mode, int G, int N, int C, int64_
     if (mode == 1 && (G <= 0 || C % G)) return set_error("norm: num_channels %d not divisible by num_groups %d", C, G);
     if (mode == 3 && (!running_mean || !running_var)) return set_error("norm: eval-mode batch norm needs running stats");
     const int Cp = cpad8(C);
-    NormFinDev q;
-    q.stats = stats; q.mode = mode; q.G = G; q.N = N; q.C = C; q.Cp = Cp; q.S = (double)S; q.gamma = gamma; q.beta = beta; q.eps = eps;
-    q.running_mean = running_mean; q.running_var = running_var; q.momentum = momentum;
-    q.scale = scale; q.shift = shift; q.mean_o = mean; q.rstd_o = rstd;
-    norm_finalize_kernel<<<(N * Cp + 127) / 128, 128, 0, (cudaStream_t)stream>>>(q);
+    norm_finalize_kernel<<<(N * Cp + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        stats, mode, G, N, C, Cp, (double)S, gamma, beta, eps, running_mean, running_var, momentum, scale, shift, mean, rstd);
     return check_launch("norm_finalize");
 }
 
@@ -2051,7 +2017,7 @@ int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a,
     p.yh = y_is_half ? reinterpret_cast<const uint2*>(y) : nullptr;
     p.a = reinterpret_cast<uint2*>(a); p.pooled = reinterpret_cast<uint2*>(pooled);
     p.pool_idx = reinterpret_cast<uchar4*>(pool_idx);
-    p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu; p.slope = act_slope; p.slope_dev = act_slope_dev; p.fused_fin = 0;
+    p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = pk_d; p.pkh = pk_h; p.pkw = pk_w; p.relu = relu; p.slope = act_slope; p.slope_dev = act_slope_dev;
     p.Dp = (D + pk_d - 1) / pk_d; p.Hp = (H + pk_h - 1) / pk_h; p.Wp = (W + pk_w - 1) / pk_w;
     if (p.Cq > 65535 || N > 65535) return set_error("norm_act: too many channels / samples for the launch grid");
     if (pooling && y_is_half && !pool_idx && pooled && !getenv("E3B_POOL_GENERIC")) {
@@ -2069,34 +2035,6 @@ int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a,
         norm_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     }
     return check_launch("norm_act");
-}
-
-int e3b_norm_finalize_act(const double* stats, int mode, int G, int N, int C, int D, int H, int W, const float* gamma, const float* beta,
-                          float eps, float* running_mean, float* running_var, float momentum, float* scale, float* shift, float* mean,
-                          float* rstd, const float* y, void* a, int relu, float act_slope, const float* act_slope_dev, void* stream)
-{
-    if (mode == 1 && (G <= 0 || C % G)) return set_error("norm: num_channels %d not divisible by num_groups %d", C, G);
-    if (mode == 3 && (!running_mean || !running_var)) return set_error("norm: eval-mode batch norm needs running stats");
-    if ((mode == 1 || mode == 2) && !stats) return set_error("norm_finalize_act: statistics are required");
-    if (!y || !a || !scale || !shift) return set_error("norm_finalize_act: null tensor pointer");
-    if (relu < 0 || relu > 2) return set_error("norm_finalize_act: unknown activation code %d", relu);
-    if (act_slope_dev && relu != 1) return set_error("norm_finalize_act: a device-resident slope belongs to activation code 1");
-    NormActDev p;
-    p.y = reinterpret_cast<const float4*>(y); p.scale = nullptr; p.shift = nullptr; p.yh = nullptr;
-    p.a = reinterpret_cast<uint2*>(a); p.pooled = nullptr; p.pool_idx = nullptr;
-    p.C = C; p.N = N; p.Cq = cpad8(C) / 4; p.Ch = cpad16(C) / 8; p.D = D; p.H = H; p.W = W; p.pkd = p.pkh = p.pkw = 1;
-    p.relu = relu; p.slope = act_slope; p.slope_dev = act_slope_dev;
-    p.Dp = D; p.Hp = H; p.Wp = W;
-    p.fused_fin = 1;
-    NormFinDev& q = p.fin;
-    q.stats = stats; q.mode = mode; q.G = G; q.N = N; q.C = C; q.Cp = cpad8(C); q.S = (double)D * H * W; q.gamma = gamma; q.beta = beta;
-    q.eps = eps; q.running_mean = running_mean; q.running_var = running_var; q.momentum = momentum;
-    q.scale = scale; q.shift = shift; q.mean_o = mean; q.rstd_o = rstd;
-    if (p.Cq > 65535 || N > 65535) return set_error("norm_finalize_act: too many channels / samples for the launch grid");
-    const size_t S = (size_t)D * H * W;
-    const dim3 grid((unsigned)((S + 256 * kVpt - 1) / (256 * kVpt)), p.Cq, N);
-    norm_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-    return check_launch("norm_finalize_act");
 }
 
 static int fill_bwd(const e3b_norm_bwd_args* a, NormBwdDev& p)

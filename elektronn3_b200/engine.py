@@ -344,26 +344,6 @@ def act_code(act, training):
     raise NotImplementedError(f'activation module {type(act).__name__} is not on the B200 path')
 
 
-def norm_finalize_act(stats, mode, G, y, C, gamma, beta, eps, rm, rv, momentum, act=None):
-    """norm_finalize + norm_act (no pooling) as ONE launch: every block of the activation kernel derives its four channels'
-    scale / shift from the statistics while its loads are in flight.  -> (NormState, a)"""
-    if os.environ.get('E3B_NORM_FIN', 'fused') == 'split':
-        st = norm_finalize(stats, mode, G, y.N, C, y.D * y.H * y.W, gamma, beta, eps, rm, rv, momentum, y.t.device)
-        return st, norm_act(y, st.scale, st.shift, act=act)[0]
-    act = tuple(act if act is not None else ACT_RELU) + (None,)
-    slope_dev = act[2].detach() if act[2] is not None else None
-    dev = y.t.device
-    buf = torch.empty((4, y.N, cpad8(C)), dtype=torch.float32, device=dev)
-    st = NormState()
-    st.scale, st.shift, st.mean, st.rstd = buf[0], buf[1], buf[2], buf[3]
-    a = QP.empty_half(y.N, C, y.D, y.H, y.W, dev)
-    L.check(L.lib().e3b_norm_finalize_act(_p(stats), mode, G, y.N, C, y.D, y.H, y.W, _p(gamma), _p(beta), eps, _p(rm), _p(rv),
-                                          momentum, st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
-                                          st.rstd.data_ptr(), y.ptr, a.ptr, act[0], act[1], _p(slope_dev), _stream()),
-            'norm_finalize_act')
-    return st, a
-
-
 def norm_act(y, scale, shift, *, write_a=True, pool=None, relu=True, save=False, act=None):
     """a = act(y*scale+shift) (QH) and optionally the ceil-mode max-pooled tensor (QH).  save=True (a backward pass will
     follow) also records the arg-max slots of the pooling windows.  With write_a=False `y` is already a QH activation
@@ -694,13 +674,9 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save, res=None):
                 rm, rv, mom = _bn_running(n, training)
             elif mode == MODE_BATCH_EVAL:
                 rm, rv = n.running_mean, n.running_var
-            if pool is None:
-                u.nstate, u.a = norm_finalize_act(stats, mode, G, y, spec.Co, _affine(n, 'weight'), _affine(n, 'bias'), n.eps,
-                                                  rm, rv, mom, act=act)
-            else:
-                u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, y.D * y.H * y.W, _affine(n, 'weight'), _affine(n, 'bias'),
-                                         n.eps, rm, rv, mom, y.t.device)
-                u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, save=save, act=act)
+            u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, y.D * y.H * y.W, _affine(n, 'weight'), _affine(n, 'bias'),
+                                     n.eps, rm, rv, mom, y.t.device)
+            u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, save=save, act=act)
     elif (mode == MODE_BATCH_EVAL or (mode == MODE_NONE and not save)) and act == ACT_RELU:
         # inference: the conv epilogue (folded BN, bias, ReLU) writes the next layer's operand directly
         a, _, _ = conv_forward(src0, wpk, spec.n_total, spec.Co, spec.k, spec.pad, src1=src1, off1=off1, bias=bias,
@@ -724,14 +700,10 @@ def _run_unit(net, spec, src0, src1, off1, pool, training, save, res=None):
         mom = 0.0
         if mode == MODE_BATCH:
             rm, rv, mom = _bn_running(n, training)
+        u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, S, _affine(n, 'weight'), _affine(n, 'bias'), n.eps,
+                                 rm, rv, mom, y.t.device)
         u.y, u.stats = y, stats
-        if pool is None:
-            u.nstate, u.a = norm_finalize_act(stats, mode, G, y, spec.Co, _affine(n, 'weight'), _affine(n, 'bias'), n.eps,
-                                              rm, rv, mom, act=act)
-        else:
-            u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, S, _affine(n, 'weight'), _affine(n, 'bias'), n.eps,
-                                     rm, rv, mom, y.t.device)
-            u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, save=save, act=act)
+        u.a, u.pooled = norm_act(y, u.nstate.scale, u.nstate.shift, pool=pool, save=save, act=act)
     if not save:
         u.y = u.src0 = u.src1 = u.res = None
     return u
@@ -855,9 +827,10 @@ def _run_up(net, spec, dec, enc, training, save):
         mom = 0.0
         if mode == MODE_BATCH:
             rm, rv, mom = _bn_running(n, training)
+        u.nstate = norm_finalize(stats, mode, G, y.N, spec.Co, y.D * y.H * y.W, _affine(n, 'weight'),
+                                 _affine(n, 'bias'), n.eps, rm, rv, mom, y.t.device)
         u.y, u.stats = y, stats
-        u.nstate, u.a = norm_finalize_act(stats, mode, G, y, spec.Co, _affine(n, 'weight'), _affine(n, 'bias'), n.eps,
-                                          rm, rv, mom, act=act)
+        u.a, _ = norm_act(y, u.nstate.scale, u.nstate.shift, act=act)
     if not save:
         u.y = u.dec = u.src0 = None
     return u, off1

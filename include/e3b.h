@@ -190,13 +190,6 @@ int e3b_norm_act(const void* y, const float* scale, const float* shift, void* a,
                  int N, int C, int D, int H, int W, int pk_d, int pk_h, int pk_w, int relu, float act_slope,
                  const float* act_slope_dev, int y_is_half, void* stream);
 
-/* e3b_norm_finalize + e3b_norm_act (without pooling) in ONE launch: every block derives the scale / shift of its four channels
- * from `stats` while its loads are in flight; scale / shift / mean / rstd are still written (for the backward pass), and
- * BatchNorm's running statistics are updated, exactly as e3b_norm_finalize does. */
-int e3b_norm_finalize_act(const double* stats, int mode, int G, int N, int C, int D, int H, int W, const float* gamma, const float* beta,
-                          float eps, float* running_mean, float* running_var, float momentum, float* scale, float* shift, float* mean,
-                          float* rstd, const float* y, void* a, int relu, float act_slope, const float* act_slope_dev, void* stream);
-
 /* backward of conv -> norm -> relu [-> pool] as autograd derives it:
  *   dr  = (g0 + g1 + unpool(gp)) * act'(y*scale+shift)   ([a > 0] for ReLU)   g0,g1: same extents as y (either may be NULL)
  *   reduce:   sums[n][c] = (sum dr, sum dr*xhat)   (fp64 atomics, [N][pad8(C)][2]);  amax = (max|dr|, max|xhat|)

@@ -832,25 +832,3 @@ def test_pooling_of_an_fp16_activation(eng, monkeypatch, C, sp, pool, generic):
     assert_close(from_qh_ref(pooled, C), ref, 1e-7, 'pool')
     if eng.cpad16(C) != C:
         assert from_qh_ref(pooled, eng.cpad16(C))[:, C:].abs().max().item() == 0.0
-
-
-@pytest.mark.parametrize('mode,G,C,sp', [(1, 8, 32, (6, 8, 10)), (1, 4, 8, (2, 3, 136)), (2, 1, 24, (3, 9, 8)), (1, 3, 3, (4, 4, 4)),
-                                         (1, 8, 128, (4, 8, 8)), (2, 1, 8, (2, 4, 132))])
-def test_norm_finalize_fused_into_the_activation_kernel(eng, monkeypatch, mode, G, C, sp):
-    """e3b_norm_finalize_act == e3b_norm_finalize followed by e3b_norm_act, bit for bit: activation, the scale / shift /
-    mean / rstd left for the backward pass, BatchNorm's running statistics"""
-    N = 3
-    rs = np.random.RandomState(9)
-    y = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)).cuda()
-    gamma = torch.from_numpy((1 + 0.2 * rs.standard_normal(C)).astype(np.float32)).cuda()
-    beta = torch.from_numpy((0.1 * rs.standard_normal(C)).astype(np.float32)).cuda()
-    stats = torch.stack((y.double().sum(dim=(2, 3, 4)), (y.double() ** 2).sum(dim=(2, 3, 4))), dim=-1).contiguous()
-    out = {}
-    for path in ('split', 'fused'):
-        monkeypatch.setenv('E3B_NORM_FIN', path)
-        rm, rv = torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
-        st, a = eng.norm_finalize_act(stats, mode, G, qp32(eng, y), C, gamma, beta, 1e-5, rm if mode == 2 else None,
-                                      rv if mode == 2 else None, 0.1, act=(1, 0.1))
-        out[path] = (a.t.clone(), st.scale.clone(), st.shift.clone(), st.mean.clone(), st.rstd.clone(), rm.clone(), rv.clone())
-    for x_s, x_f, what in zip(out['split'], out['fused'], ('a', 'scale', 'shift', 'mean', 'rstd', 'running_mean', 'running_var')):
-        assert torch.equal(x_s, x_f), what
